@@ -1,0 +1,302 @@
+"""Problem zoo shared by the golden generator (reference API), the oracle tests and the GPU parity tests.
+
+Every builder takes an `api` namespace exposing Domain / Conditions / Equation (either the reference's
+`tedeous.data` or `torch_de_solver_b200`) and a dtype string, and returns a `Problem`.  The operator dicts
+follow the reference's example scripts (file:line in each docstring)."""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List
+
+import numpy as np
+import torch
+
+
+@dataclass
+class Problem:
+    name: str
+    domain: object
+    conditions: object
+    equation: object
+    mode: str
+    net_layers: List[int]            # [d, w, ..., n_out]  (mat mode: [])
+    compile_kwargs: Dict = field(default_factory=dict)
+    init: str = 'default'            # 'default' (Kaiming-uniform) | 'xavier'
+    mat_shape: tuple = ()
+
+
+def make_net(layers: List[int], dtype=torch.float32, init='default', seed=0) -> torch.nn.Sequential:
+    torch.manual_seed(seed)
+    mods = []
+    for i in range(len(layers) - 1):
+        mods.append(torch.nn.Linear(layers[i], layers[i + 1]))
+        if i < len(layers) - 2:
+            mods.append(torch.nn.Tanh())
+    net = torch.nn.Sequential(*mods)
+    if init == 'xavier':
+        for m in net.modules():
+            if isinstance(m, torch.nn.Linear):
+                torch.nn.init.xavier_normal_(m.weight)
+                torch.nn.init.zeros_(m.bias)
+    elif init == 'xavier_b':       # xavier weights, small random biases (keeps all gradients non-trivial)
+        for m in net.modules():
+            if isinstance(m, torch.nn.Linear):
+                torch.nn.init.xavier_normal_(m.weight)
+                torch.nn.init.uniform_(m.bias, -0.3, 0.3)
+    return net.to(dtype)
+
+
+def make_mat_model(shape, dtype=torch.float32, seed=0) -> torch.Tensor:
+    """mat-mode "model" = the solution values on the grid ([n_eq, N0, N1], tedeous/models.py:198-226).  The
+    default all-ones tensor has zero derivatives everywhere, so tests use a smooth field plus noise."""
+    torch.manual_seed(seed)
+    n_eq, n0, n1 = shape
+    x = torch.linspace(0, 1, n0)[:, None]
+    y = torch.linspace(0, 1, n1)[None, :]
+    base = torch.stack([torch.sin(3 * x + k) * torch.cos(2 * y - k) for k in range(n_eq)])
+    return (base + 0.05 * torch.rand(shape)).to(dtype)
+
+
+# --- config 1: Burgers (examples/examples_burgers/example_burgers_1d.py:35-80) ----------------------------
+def burgers(api, dtype='float32', n=100, mode='NN', layers=(2, 100, 100, 100, 1), h=0.001):
+    mu = 0.01 / math.pi
+    dom = api.Domain()
+    dom.variable('x', [-1, 1], n, dtype=dtype)
+    dom.variable('t', [0, 1], n, dtype=dtype)
+    bc = api.Conditions()
+    bc.dirichlet({'x': [-1, 1], 't': 0}, value=lambda g: -torch.sin(np.pi * g[:, 0]))
+    bc.dirichlet({'x': -1, 't': [0, 1]}, value=0)
+    bc.dirichlet({'x': 1, 't': [0, 1]}, value=0)
+    eq = api.Equation()
+    eq.add({
+        'du/dt**1': {'coeff': 1., 'du/dt': [1], 'pow': 1, 'var': 0},
+        '+u*du/dx': {'coeff': 1, 'u*du/dx': [[None], [0]], 'pow': [1, 1], 'var': [0, 0]},
+        '-mu*d2u/dx2': {'coeff': -mu, 'd2u/dx2': [0, 0], 'pow': 1, 'var': 0},
+    })
+    kw = dict(lambda_operator=1, lambda_bound=10)
+    if mode == 'NN':
+        kw['h'] = h
+    return Problem(f'burgers_{mode}', dom, bc, eq, mode, list(layers), kw)
+
+
+# --- config 2: wave (examples/examples_wave/example_wave_1d_basic.py:36-97) ---------------------------------
+def wave(api, dtype='float32', n=40, mode='autograd', layers=(2, 100, 100, 100, 1), h=0.01, operator_ic=True):
+    def exact(g):
+        x, t = g[:, 0], g[:, 1]
+        return torch.sin(np.pi * x) * torch.cos(2 * np.pi * t) + 0.5 * torch.sin(4 * np.pi * x) * torch.cos(8 * np.pi * t)
+    dom = api.Domain()
+    dom.variable('x', [0, 1], n, dtype=dtype)
+    dom.variable('t', [0, 1], n, dtype=dtype)
+    bc = api.Conditions()
+    bc.dirichlet({'x': [0, 1], 't': 0}, value=exact)
+    if operator_ic:
+        bc.operator({'x': [0, 1], 't': 0}, operator={'du/dt': {'coeff': 1, 'term': [1], 'pow': 1, 'var': 0}}, value=0)
+    bc.dirichlet({'x': 0, 't': [0, 1]}, value=exact)
+    bc.dirichlet({'x': 1, 't': [0, 1]}, value=exact)
+    eq = api.Equation()
+    eq.add({
+        'd2u/dt2**1': {'coeff': 1, 'd2u/dt2': [1, 1], 'pow': 1},
+        '-C*d2u/dx2**1': {'coeff': -4, 'd2u/dx2': [0, 0], 'pow': 1},
+    })
+    kw = dict(lambda_operator=1, lambda_bound=100)
+    if mode == 'NN':
+        kw['h'] = h
+    return Problem(f'wave_{mode}', dom, bc, eq, mode, list(layers), kw, init='xavier_b')
+
+
+# --- config 3: KdV periodic (examples/examples_korteweg_de_vries/example_KdV_periodic.py:22-148) -----------
+def kdv(api, dtype='float32', nx=30, nt=30, mode='autograd', layers=(2, 100, 100, 100, 1), h=0.01):
+    def soliton(x, t):
+        E = torch.exp(x)
+        return 2 / (torch.cosh((x - 4 * t) / 1.0)) ** 2 + 0 * E
+    dom = api.Domain()
+    dom.variable('x', [-10, 10], nx, dtype=dtype)
+    dom.variable('t', [0, 1], nt, dtype=dtype)
+    bc = api.Conditions()
+    bc.periodic([{'x': -10, 't': [0, 1]}, {'x': 10, 't': [0, 1]}])
+    x = dom.variable_dict['x']
+    bc.dirichlet({'x': [-10, 10], 't': 0}, value=soliton(x, torch.tensor([0.])))
+    eq = api.Equation()
+    eq.add({
+        '1*du/dt**1': {'coeff': 1, 'du/dt': [1], 'pow': 1, 'var': 0},
+        '6*u**1*du/dx**1': {'coeff': 6, 'u*du/dx': [[None], [0]], 'pow': [1, 1], 'var': [0, 0]},
+        'd3u/dx3**1': {'coeff': 1, 'd3u/dx3': [0, 0, 0], 'pow': 1, 'var': 0},
+    })
+    kw = dict(lambda_operator=1, lambda_bound=100)
+    if mode == 'NN':
+        kw['h'] = h
+    return Problem(f'kdv_{mode}', dom, bc, eq, mode, list(layers), kw)
+
+
+# --- config 5: Navier-Stokes 2D+t (examples/examples_navier_stokes/example_navier_stokes_2d_long_time.py:36-198)
+def navier_stokes(api, dtype='float32', n=8, layers=(3, 100, 100, 100, 100, 100, 100, 3)):
+    ro, mu = 1., 1.
+    A1, A2, A3 = 1., 1., 1.
+    dom = api.Domain()
+    dom.variable('x', [0, 5], n, dtype=dtype)
+    dom.variable('y', [0, 1], n, dtype=dtype)
+    dom.variable('t', [0, 5], n, dtype=dtype)
+    bc = api.Conditions()
+    for v in range(3):
+        bc.dirichlet({'x': [0, 5], 'y': [0, 1], 't': 0}, value=0, var=v)
+    inlet = lambda g: torch.sin(np.pi * g[:, 1]) * (A1 * torch.sin(np.pi * g[:, 2]) + A2 * torch.sin(3 * np.pi * g[:, 2])
+                                                    + A3 * torch.sin(5 * np.pi * g[:, 2]))
+    bc.dirichlet({'x': 0, 'y': [0, 1], 't': [0, 5]}, value=inlet, var=0)
+    bc.dirichlet({'x': 5, 'y': [0, 1], 't': [0, 5]}, value=0, var=0)
+    bc.dirichlet({'x': 0, 'y': [0, 1], 't': [0, 5]}, value=0, var=1)
+    bc.dirichlet({'x': 5, 'y': [0, 1], 't': [0, 5]}, value=0, var=1)
+    bc.dirichlet({'x': 5, 'y': [0, 1], 't': [0, 5]}, value=0, var=2)
+
+    def forcing(g):
+        return -torch.sin(np.pi * g[:, 0]) * torch.sin(np.pi * g[:, 1]) * torch.sin(np.pi * g[:, 2])
+    eq = api.Equation()
+    eq.add({
+        'du/dx': {'coeff': 1, 'term': [0], 'pow': 1, 'var': 0},
+        'dv/dy': {'coeff': 1, 'term': [1], 'pow': 1, 'var': 1},
+    })
+    eq.add({
+        'du/dt': {'coeff': 1, 'term': [2], 'pow': 1, 'var': 0},
+        'u * du/dx': {'coeff': 1, 'term': [[None], [0]], 'pow': [1, 1], 'var': [0, 0]},
+        'v * du/dy': {'coeff': 1, 'term': [[None], [1]], 'pow': [1, 1], 'var': [1, 0]},
+        '1/ro * dp/dx': {'coeff': 1 / ro, 'term': [0], 'pow': 1, 'var': 2},
+        '-mu * d2u/dx2': {'coeff': -mu, 'term': [0, 0], 'pow': 1, 'var': 0},
+        '-mu * d2u/dy2': {'coeff': -mu, 'term': [1, 1], 'pow': 1, 'var': 0},
+    })
+    eq.add({
+        'dv/dt': {'coeff': 1, 'term': [2], 'pow': 1, 'var': 1},
+        'u * dv/dx': {'coeff': 1, 'term': [[None], [0]], 'pow': [1, 1], 'var': [0, 1]},
+        'v * dv/dy': {'coeff': 1, 'term': [[None], [1]], 'pow': [1, 1], 'var': [1, 1]},
+        '1/ro * dp/dy': {'coeff': 1 / ro, 'term': [1], 'pow': 1, 'var': 2},
+        '-mu * d2v/dx2': {'coeff': -mu, 'term': [0, 0], 'pow': 1, 'var': 1},
+        '-mu * d2v/dy2': {'coeff': -mu, 'term': [1, 1], 'pow': 1, 'var': 1},
+        '-f(x, y, t)': {'coeff': forcing, 'term': [None], 'pow': 0},
+    })
+    return Problem('navier_stokes_autograd', dom, bc, eq, 'autograd', list(layers),
+                   dict(lambda_operator=1, lambda_bound=1000), init='xavier_b')
+
+
+# --- extra coverage: ODE with operator BC, nonlinear powers, tensor / callable coefficients ----------------
+def legendre_ode(api, dtype='float32', n=40, mode='autograd', layers=(1, 32, 32, 1), order=3, h=0.001):
+    """(1 - t^2) u'' - 2 t u' + n(n+1) u = 0, u(0) = P_n(0), u'(1) = P_n'(1)
+    (examples/examples_legendre/example_legendre.py pattern: callable coefficients, operator BC)."""
+    from numpy.polynomial import legendre as L
+    dom = api.Domain()
+    dom.variable('t', [0, 1], n, dtype=dtype)
+    t0, t1 = torch.tensor([[0.]]), torch.tensor([[1.]])
+    c = [0] * order + [1]
+    bc = api.Conditions()
+    bc.dirichlet(t0, value=torch.tensor([float(L.legval(0., c))]))
+    bc.operator(t1, operator={'du/dt': {'coeff': 1, 'du/dt': [0], 'pow': 1}},
+                value=torch.tensor([float(L.legval(1., L.legder(c)))]))
+    eq = api.Equation()
+    eq.add({
+        '(1-t^2)*d2u/dt2': {'coeff': lambda g: 1 - g[:, 0] ** 2, 'd2u/dt2': [0, 0], 'pow': 1},
+        '-2t*du/dt': {'coeff': lambda g: -2 * g[:, 0], 'du/dt': [0], 'pow': 1},
+        'n(n+1)u': {'coeff': float(order * (order + 1)), 'u': [None], 'pow': 1},
+    })
+    kw = dict(lambda_operator=1, lambda_bound=10)
+    if mode == 'NN':
+        kw['h'] = h
+    return Problem(f'legendre_{mode}', dom, bc, eq, mode, list(layers), kw)
+
+
+def nonlinear_mix(api, dtype='float32', n=16, mode='autograd', layers=(2, 24, 24, 2), h=0.01):
+    """Two-output system with powers, products across variables, 4th-order derivative, tensor coefficient,
+    forcing term, data condition and a per-type lambda list."""
+    dom = api.Domain()
+    dom.variable('x', [0, 1], n, dtype=dtype)
+    dom.variable('t', [0, 2], n, dtype=dtype)
+    N = (n + 1) ** 2
+    tdt = torch.float64 if dtype == 'float64' else torch.float32
+    coeff_t = torch.linspace(0.5, 1.5, N, dtype=tdt)
+    bc = api.Conditions()
+    bc.dirichlet({'x': [0, 1], 't': 0}, value=lambda g: torch.cos(g[:, 0]), var=0)
+    bc.dirichlet({'x': 0, 't': [0, 2]}, value=0.3, var=1)
+    bc.operator({'x': 1, 't': [0, 2]}, operator={'dv/dx': {'coeff': 2., 'term': [0], 'pow': 1, 'var': 1},
+                                                 'u': {'coeff': -1., 'term': [None], 'pow': 1, 'var': 0}}, value=0.1)
+    data_pts = torch.tensor([[0.25, 0.5], [0.5, 1.0], [0.75, 1.5]], dtype=tdt)
+    bc.data(data_pts, None, torch.tensor([0.1, 0.2, 0.3], dtype=tdt), var=1)
+    eq = api.Equation()
+    eq.add({
+        'du/dt': {'coeff': 1, 'term': [1], 'pow': 1, 'var': 0},
+        'c(x)*u^2*dv/dx': {'coeff': coeff_t, 'term': [[None], [0]], 'pow': [2, 1], 'var': [0, 1]},
+        '-0.01*d4u/dx4': {'coeff': -0.01, 'term': [0, 0, 0, 0], 'pow': 1, 'var': 0},
+        'f': {'coeff': lambda g: torch.sin(g[:, 0] + g[:, 1]), 'term': [None], 'pow': 0},
+    })
+    eq.add({
+        'd2v/dt2': {'coeff': 1, 'term': [1, 1], 'pow': 1, 'var': 1},
+        '(dv/dx)^2': {'coeff': 0.5, 'term': [0], 'pow': 2, 'var': 1},
+        'u*v': {'coeff': -1.5, 'term': [[None], [None]], 'pow': [1, 1], 'var': [0, 1]},
+        'd3u/dx3': {'coeff': 0.1, 'term': [0, 0, 0], 'pow': 1, 'var': 0},
+    })
+    kw = dict(lambda_operator=[1., 2.], lambda_bound=[10., 5., 3.])
+    if mode == 'NN':
+        kw['h'] = h
+    return Problem(f'nonlinear_mix_{mode}', dom, bc, eq, mode, list(layers), kw, init='xavier_b')
+
+
+# --- config 4: Poisson, mat mode -------------------------------------------------------
+def poisson_mat(api, dtype='float32', n=32, derivative_points=2):
+    dom = api.Domain()
+    dom.variable('x', [0, 1], n, dtype=dtype)
+    dom.variable('y', [0, 1], n, dtype=dtype)
+    bc = api.Conditions()
+    bc.dirichlet({'x': 0, 'y': [0, 1]}, value=0)
+    bc.dirichlet({'x': 1, 'y': [0, 1]}, value=0)
+    bc.dirichlet({'x': [0, 1], 'y': 0}, value=0)
+    bc.dirichlet({'x': [0, 1], 'y': 1}, value=lambda g: torch.sin(np.pi * g[:, 0]))
+    tdt = torch.float64 if dtype == 'float64' else torch.float32
+    xs = torch.linspace(0, 1, n + 1, dtype=tdt)
+    f = -2 * np.pi ** 2 * torch.sin(np.pi * xs)[:, None] * torch.sin(np.pi * xs)[None, :]
+    eq = api.Equation()
+    eq.add({
+        'd2u/dx2': {'coeff': 1, 'term': [0, 0], 'pow': 1},
+        'd2u/dy2': {'coeff': 1, 'term': [1, 1], 'pow': 1},
+        '-f': {'coeff': -f, 'term': [None], 'pow': 0},
+    })
+    return Problem(f'poisson_mat_p{derivative_points}', dom, bc, eq, 'mat', [],
+                   dict(lambda_operator=1, lambda_bound=100, derivative_points=derivative_points),
+                   mat_shape=(1, n + 1, n + 1))
+
+
+def kdv_mat(api, dtype='float32', n=24, derivative_points=2):
+    """Nonlinear mat-mode operator with 3rd derivative, periodic + operator conditions
+    (examples/examples_korteweg_de_vries/example_KdV_matrix.py pattern)."""
+    dom = api.Domain()
+    dom.variable('x', [0, 1], n, dtype=dtype)
+    dom.variable('t', [0, 1], n, dtype=dtype)
+    bc = api.Conditions()
+    bc.dirichlet({'x': [0, 1], 't': 0}, value=lambda g: torch.sin(2 * np.pi * g[:, 0]))
+    bc.periodic([{'x': 0, 't': [0, 1]}, {'x': 1, 't': [0, 1]}])
+    bc.operator({'x': 1, 't': [0, 1]}, operator={'du/dx': {'coeff': 1, 'term': [0], 'pow': 1}}, value=0.5)
+    eq = api.Equation()
+    eq.add({
+        'du/dt': {'coeff': 1, 'term': [1], 'pow': 1},
+        '6u*du/dx': {'coeff': 6, 'term': [[None], [0]], 'pow': [1, 1]},
+        'd3u/dx3': {'coeff': 1, 'term': [0, 0, 0], 'pow': 1},
+        '-f': {'coeff': lambda g: -torch.sin(g[0]) * torch.cos(g[1]), 'term': [None], 'pow': 0},
+    })
+    return Problem(f'kdv_mat_p{derivative_points}', dom, bc, eq, 'mat', [],
+                   dict(lambda_operator=1, lambda_bound=[10., 20., 30.], derivative_points=derivative_points),
+                   mat_shape=(1, n + 1, n + 1))
+
+
+ZOO: Dict[str, Callable] = {
+    # name -> (builder, kwargs).  Sizes chosen so the reference itself preprocesses them in seconds.
+    'burgers_NN_cfg1': lambda api, dt: burgers(api, dt, n=100, mode='NN'),
+    'burgers_NN_small': lambda api, dt: burgers(api, dt, n=24, mode='NN', layers=(2, 32, 32, 1)),
+    'burgers_autograd_4h': lambda api, dt: burgers(api, dt, n=40, mode='autograd', layers=(2, 100, 100, 100, 100, 1)),
+    'wave_autograd': lambda api, dt: wave(api, dt, n=40, mode='autograd'),
+    'wave_NN': lambda api, dt: wave(api, dt, n=20, mode='NN', layers=(2, 32, 32, 1)),
+    'kdv_autograd': lambda api, dt: kdv(api, dt, nx=30, nt=30, mode='autograd'),
+    'kdv_NN': lambda api, dt: kdv(api, dt, nx=20, nt=20, mode='NN', layers=(2, 32, 32, 1)),
+    'navier_stokes_autograd': lambda api, dt: navier_stokes(api, dt, n=8),
+    'legendre_autograd': lambda api, dt: legendre_ode(api, dt, mode='autograd'),
+    'legendre_NN': lambda api, dt: legendre_ode(api, dt, mode='NN'),
+    'nonlinear_mix_autograd': lambda api, dt: nonlinear_mix(api, dt, mode='autograd'),
+    'nonlinear_mix_NN': lambda api, dt: nonlinear_mix(api, dt, mode='NN'),
+    'poisson_mat_p2': lambda api, dt: poisson_mat(api, dt, n=32, derivative_points=2),
+    'poisson_mat_p3': lambda api, dt: poisson_mat(api, dt, n=24, derivative_points=3),
+    'kdv_mat_p2': lambda api, dt: kdv_mat(api, dt, n=24, derivative_points=2),
+}

@@ -1,0 +1,628 @@
+"""Lowering of a TEDEouS problem (equations + conditions + point sets) to the flat IR the CUDA kernels read.
+
+The reference evaluates the loss by walking Python dicts every step (eval.py:143-193, 433-461,
+derivative.py:30-132).  Here the walk happens once, at `Model.compile` time, and produces
+
+* a **jet spec** per point set: which pure partial derivatives d^k/dx_a^k (k <= 4) the operators need.  The
+  kernel propagates these as Taylor-mode channels through the tanh MLP (channel 0 = value);
+* a **term table**: every operator is `sum_t coeff_t * prod_f chan[f]^pow_f` over (variable, channel) pairs;
+  coeff is an immediate, a per-row buffer (callable / tensor coefficients, evaluated once) or a trainable
+  scalar (`nn.Parameter`, inverse problems);
+* a list of **segments**.  A segment is a set of residual rows that share operators and layout.  Each row
+  is a *group* of K evaluation points; the group's channel values are a fixed linear combination
+  V[m] = sum_{k,c} comb[m][k*J + c] * jet_c(x_k) of the per-point jets ("identity" for K = 1).  That one
+  mechanism covers interior residuals (K = 1), Dirichlet/data rows (K = 1, value only), periodic rows
+  (K = 2, V = u(x0) - u(x1)) and NN-mode one-sided finite-difference boundary operators (K = 3..5 shifted
+  points, V = literal stencil - SURVEY B.1 q3);
+* **loss slots**: slot s < n_eq is equation s (denominator = number of interior rows), the following
+  slots are the boundary types in order of first appearance, all divided by the *longest* type
+  (`dict_to_matrix` zero-padding, eval.py:55-87).
+
+All arrays are numpy structured arrays whose dtypes mirror the C structs in include/tdb200.h.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .finite_diffs import Finite_diffs
+from .points_type import Points_type
+
+MAX_LAYERS = 16
+MAX_DIRS = 4
+MAX_ORDER = 4
+MAX_COLS = 8
+MAX_K = 32
+MAX_M = 8
+MAX_J = 8
+ROWS_PER_TILE = 128          # (points x jet channels) rows a CTA tile holds; must match the kernel
+
+SEGMENT_DTYPE = np.dtype([
+    ('n_groups', '<i8'), ('pts_off', '<i8'), ('tgt_off', '<i8'), ('field_off', '<i8'),
+    ('K', '<i4'), ('M', '<i4'), ('n_cols', '<i4'), ('n_dirs', '<i4'),
+    ('dir_axis', '<i4', (MAX_DIRS,)), ('dir_order', '<i4', (MAX_DIRS,)),
+    ('col_term_begin', '<i4', (MAX_COLS,)), ('col_term_end', '<i4', (MAX_COLS,)),
+    ('col_slot', '<i4', (MAX_COLS,)),
+    ('identity', '<i4'), ('comb_off', '<i4'),
+], align=True)
+
+TERM_DTYPE = np.dtype([
+    ('coeff', '<f4'), ('kind', '<i4'), ('idx', '<i8'), ('fac_begin', '<i4'), ('fac_end', '<i4'),
+], align=True)
+
+FACTOR_DTYPE = np.dtype([
+    ('var', '<i4'), ('chan', '<i4'), ('pow', '<f4'), ('ipow', '<i4'),
+], align=True)
+
+COEFF_CONST, COEFF_BUFFER, COEFF_PARAM = 0, 1, 2
+
+
+class UnsupportedProblem(NotImplementedError):
+    """Raised for problem features the fused CUDA path does not implement (no silent CPU fallback)."""
+
+
+# ----------------------------------------------------------------------------------------------------
+# network description
+# ----------------------------------------------------------------------------------------------------
+@dataclass
+class NetSpec:
+    widths: List[int]                      # [d, w1, ..., n_out]
+    linears: List[torch.nn.Linear]
+    coeff_params: List[torch.nn.Parameter] = field(default_factory=list)
+
+    @property
+    def n_layers(self):
+        return len(self.linears)
+
+    @property
+    def n_net_params(self):
+        return sum(l.weight.numel() + l.bias.numel() for l in self.linears)
+
+    def param_tensors(self) -> List[torch.Tensor]:
+        out = []
+        for l in self.linears:
+            out += [l.weight, l.bias]
+        return out + list(self.coeff_params)
+
+
+def net_spec(model: torch.nn.Module) -> NetSpec:
+    """Accepts `Sequential(Linear, Tanh, ..., Linear)` (every BASELINE config)."""
+    if not isinstance(model, torch.nn.Sequential):
+        raise UnsupportedProblem('the fused path supports torch.nn.Sequential(Linear, Tanh, ..., Linear) '
+                                 f'only, got {type(model).__name__}')
+    mods = list(model.children())
+    if len(mods) < 3 or len(mods) % 2 == 0:
+        raise UnsupportedProblem('expected Linear, Tanh, ..., Linear (odd number of modules, >= 3)')
+    linears = []
+    for i, m in enumerate(mods):
+        if i % 2 == 0:
+            if not isinstance(m, torch.nn.Linear) or m.bias is None:
+                raise UnsupportedProblem(f'module {i} must be a Linear with bias, got {m}')
+            linears.append(m)
+        elif not isinstance(m, torch.nn.Tanh):
+            raise UnsupportedProblem(f'module {i} must be Tanh, got {m}')
+    if len(linears) > MAX_LAYERS:
+        raise UnsupportedProblem(f'at most {MAX_LAYERS} Linear layers')
+    widths = [linears[0].in_features] + [l.out_features for l in linears]
+    for a, b in zip(linears[:-1], linears[1:]):
+        if a.out_features != b.in_features:
+            raise UnsupportedProblem('inconsistent layer widths')
+    if max(widths[1:-1]) > 128:
+        raise UnsupportedProblem('hidden width > 128 is not supported by the fused path')
+    if widths[0] > 4 or widths[-1] > 8:
+        raise UnsupportedProblem('at most 4 inputs and 8 outputs')
+    # trainable scalar coefficients registered on the net (tedeous/models.py:183-195)
+    own = {id(p) for l in linears for p in (l.weight, l.bias)}
+    extra = [p for p in model.parameters() if id(p) not in own]
+    return NetSpec(widths, linears, extra)
+
+
+# ----------------------------------------------------------------------------------------------------
+# operators -> term tables
+# ----------------------------------------------------------------------------------------------------
+@dataclass
+class FactorIR:
+    var: int
+    axes: Tuple[int, ...]        # () = value, (0, 0) = d2/dx0^2
+    pow: float
+
+
+@dataclass
+class TermIR:
+    coeff: object                # float | torch.Tensor (per row) | nn.Parameter
+    factors: List[FactorIR]
+
+
+def _pure_axes(spec) -> Tuple[int, ...]:
+    if spec == [None] or spec is None or spec == []:
+        return ()
+    axes = tuple(a for a in spec if a is not None)
+    return axes
+
+
+def parse_operator(op: dict, rows: torch.Tensor, coeff_rows: Optional[Callable] = None) -> List[TermIR]:
+    """Unified operator dict -> list of TermIR.  `rows` are the points the operator is evaluated at
+    (callable coefficients are evaluated on them once); `coeff_rows(tensor)` maps a full-grid tensor
+    coefficient onto `rows`."""
+    terms = []
+    for label, term in op.items():
+        dif_dir = list(term.keys())[1]
+        specs, pows, vars_ = term[dif_dir], term['pow'], term['var']
+        if not isinstance(specs, list) or (specs and not isinstance(specs[0], list)):
+            specs = [specs]
+        facs = []
+        for spec, pw, var in zip(specs, pows, vars_):
+            if callable(pw):
+                raise UnsupportedProblem(f"term {label!r}: callable 'pow' is not supported by the fused path")
+            facs.append(FactorIR(int(var), _pure_axes(spec), float(pw)))
+        coeff = term['coeff']
+        if isinstance(coeff, tuple):          # reference NN-prepared form (callable, grid)
+            coeff = coeff[0]
+        if isinstance(coeff, torch.nn.Parameter):
+            pass
+        elif callable(coeff):
+            coeff = coeff(rows).reshape(-1).detach()
+        elif isinstance(coeff, torch.Tensor):
+            coeff = coeff.reshape(-1).detach()
+            if coeff.numel() == 1:
+                coeff = float(coeff)
+            elif coeff_rows is not None:
+                coeff = coeff_rows(coeff)
+        else:
+            coeff = float(coeff)
+        if isinstance(coeff, torch.Tensor) and not isinstance(coeff, torch.nn.Parameter) \
+                and coeff.numel() != rows.shape[0]:
+            raise ValueError(f'term {label!r}: coefficient has {coeff.numel()} entries for {rows.shape[0]} rows')
+        terms.append(TermIR(coeff, facs))
+    return terms
+
+
+@dataclass
+class JetSpec:
+    dirs: List[Tuple[int, int]]          # (axis, max order), sorted by axis
+
+    @property
+    def J(self):
+        return 1 + sum(o for _, o in self.dirs)
+
+    def channel(self, axes: Tuple[int, ...]) -> int:
+        if not axes:
+            return 0
+        base = 1
+        for a, o in self.dirs:
+            if a == axes[0]:
+                return base + len(axes) - 1
+            base += o
+        raise KeyError(axes)
+
+
+def jet_spec(term_lists: Sequence[List[TermIR]]) -> JetSpec:
+    order: Dict[int, int] = {}
+    for terms in term_lists:
+        for t in terms:
+            for f in t.factors:
+                if not f.axes:
+                    continue
+                if len(set(f.axes)) != 1:
+                    raise UnsupportedProblem(f'mixed partial derivative {list(f.axes)} is not supported by the '
+                                             'fused path (pure partials up to order 4 only)')
+                if len(f.axes) > MAX_ORDER:
+                    raise UnsupportedProblem(f'derivative order {len(f.axes)} > {MAX_ORDER}')
+                order[f.axes[0]] = max(order.get(f.axes[0], 0), len(f.axes))
+    dirs = sorted(order.items())
+    js = JetSpec(dirs)
+    if len(dirs) > MAX_DIRS or js.J > MAX_J:
+        raise UnsupportedProblem(f'jet set too large (J = {js.J}, {len(dirs)} directions)')
+    return js
+
+
+# ----------------------------------------------------------------------------------------------------
+# segments
+# ----------------------------------------------------------------------------------------------------
+@dataclass
+class SegmentIR:
+    name: str
+    points: torch.Tensor                 # [n_groups * K, d], group-major
+    K: int
+    jet: JetSpec
+    comb: Optional[np.ndarray]           # [M, K * J] or None (identity)
+    chan_of: Callable[[FactorIR], int]   # factor -> virtual channel index
+    cols: List[List[TermIR]]             # one term list per residual column
+    slots: List[int]
+    targets: Optional[torch.Tensor]      # [n_groups, n_cols]
+    row_index: Optional[torch.Tensor] = None   # position of each group inside its field column
+    n_groups_global: Optional[int] = None
+
+    @property
+    def n_groups(self):
+        return self.points.shape[0] // self.K
+
+    @property
+    def M(self):
+        return self.jet.J if self.comb is None else self.comb.shape[0]
+
+
+def points_per_tile(J: int, K: int) -> int:
+    """Points a 128-row tile holds: the largest multiple of lcm(4, K) with J * P <= 128."""
+    pmax = ROWS_PER_TILE // J
+    step = K * 4 // np.gcd(K, 4)
+    p = (pmax // step) * step
+    if p == 0:
+        raise UnsupportedProblem(f'group of {K} points with {J} jet channels does not fit a tile')
+    return int(p)
+
+
+@dataclass
+class ProblemIR:
+    mode: str
+    d: int
+    net: NetSpec
+    segments: List[SegmentIR]
+    n_eq: int
+    bnd_types: List[str]
+    slot_len: List[int]                  # denominator of every slot (global)
+    slot_lambda: List[float]
+    n_interior: int
+
+    @property
+    def n_slots(self):
+        return self.n_eq + len(self.bnd_types)
+
+    def slot_scale(self) -> np.ndarray:
+        return np.array([l / n for l, n in zip(self.slot_lambda, self.slot_len)], dtype=np.float64)
+
+
+def _lambda_list(lam, n, what) -> List[float]:
+    if isinstance(lam, torch.Tensor):
+        lam = lam.reshape(-1).tolist()
+    if isinstance(lam, (int, float)):
+        return [float(lam)] * n
+    lam = [float(x) for x in lam]
+    if len(lam) != n:
+        raise ValueError(f'{what}: expected {n} lambdas, got {len(lam)}')
+    return lam
+
+
+def _value_term(var: int) -> List[TermIR]:
+    return [TermIR(1.0, [FactorIR(int(var), (), 1.0)])]
+
+
+def _is_linear(terms: List[TermIR]) -> bool:
+    return all(len(t.factors) == 1 and t.factors[0].pow == 1.0 and not isinstance(t.coeff, torch.nn.Parameter)
+               for t in terms)
+
+
+def _stencil_segment(name, bnd, terms, target, slot, h, variant, type_name, row_index) -> SegmentIR:
+    """NN-mode boundary operator on points of one point type: literal one-sided shifted evaluations
+    (tedeous/finite_diffs.py:120-223 via input_preprocessing.py:371-408, eval.py:264-281)."""
+    d = bnd.shape[1]
+    # distinct derivative specs -> virtual channels; distinct shift vectors -> group points
+    chan_specs: List[Tuple[int, ...]] = [()]
+    for t in terms:
+        for f in t.factors:
+            if f.axes not in chan_specs:
+                chan_specs.append(f.axes)
+    shift_list: List[Tuple[int, ...]] = []
+    weights: List[Dict[int, float]] = []
+    for axes in chan_specs:
+        if not axes:
+            sch, sg = [[0] * d], [1.0]
+        else:
+            sch, sg = Finite_diffs(list(axes), d, type_name).scheme_choose(variant, h=h)
+        w: Dict[int, float] = {}
+        for s, c in zip(sch, sg):
+            s = tuple(s)
+            if s not in shift_list:
+                shift_list.append(s)
+            k = shift_list.index(s)
+            w[k] = w.get(k, 0.0) + float(c)
+        weights.append(w)
+    K, M = len(shift_list), len(chan_specs)
+    if K > MAX_K or M > MAX_M:
+        raise UnsupportedProblem(f'{name}: stencil too large (K = {K}, M = {M})')
+    comb = np.zeros((M, K), dtype=np.float64)
+    for m, w in enumerate(weights):
+        for k, c in w.items():
+            comb[m, k] = c
+    # group-major points: x + shift * h, computed like Points_type.shift_points (tedeous/points_type.py:22-37)
+    pts = bnd.unsqueeze(1).repeat(1, K, 1)
+    for k, s in enumerate(shift_list):
+        for a, mult in enumerate(s):
+            if mult != 0:
+                pts[:, k, a] = bnd[:, a] + mult * h
+    return SegmentIR(name, pts.reshape(-1, d).contiguous(), K, JetSpec([]), comb,
+                     lambda f: chan_specs.index(f.axes), [terms], [slot], target.reshape(-1, 1),
+                     row_index=row_index)
+
+
+def _interior_literal_fd(name, pts, cols, slots, h) -> SegmentIR:
+    """Optional literal NN-mode interior evaluation: central differences with step h as shifted forwards
+    (tedeous/derivative.py:30-58) instead of exact jets."""
+    d = pts.shape[1]
+    chan_specs: List[Tuple[int, ...]] = [()]
+    for terms in cols:
+        for t in terms:
+            for f in t.factors:
+                if f.axes not in chan_specs:
+                    chan_specs.append(f.axes)
+    shift_list, weights = [], []
+    for axes in chan_specs:
+        sch, sg = ([[0] * d], [1.0]) if not axes else Finite_diffs(list(axes), d, 'central').scheme_choose('1', h=h)
+        w = {}
+        for s, c in zip(sch, sg):
+            s = tuple(s)
+            if s not in shift_list:
+                shift_list.append(s)
+            k = shift_list.index(s)
+            w[k] = w.get(k, 0.0) + float(c)
+        weights.append(w)
+    K, M = len(shift_list), len(chan_specs)
+    if K > MAX_K or M > MAX_M:
+        raise UnsupportedProblem(f'{name}: stencil too large (K = {K}, M = {M})')
+    comb = np.zeros((M, K))
+    for m, w in enumerate(weights):
+        for k, c in w.items():
+            comb[m, k] = c
+    p = pts.unsqueeze(1).repeat(1, K, 1)
+    for k, s in enumerate(shift_list):
+        for a, mult in enumerate(s):
+            if mult != 0:
+                p[:, k, a] = pts[:, a] + mult * h
+    return SegmentIR(name, p.reshape(-1, d).contiguous(), K, JetSpec([]), comb,
+                     lambda f: chan_specs.index(f.axes), cols, slots, None)
+
+
+def lower_problem(mode: str, grid: torch.Tensor, prepared_operator: List[dict], bconds: Optional[List[dict]],
+                  model: torch.nn.Module, lambda_operator, lambda_bound, h: float = 0.001,
+                  inner_order: str = '1', boundary_order: str = '2', nn_interior: str = 'jet',
+                  shard: Tuple[int, int] = (0, 1)) -> ProblemIR:
+    """Build the IR for modes 'NN' and 'autograd'.
+
+    `shard = (rank, world)` keeps only this rank's contiguous block of every segment's rows; slot
+    denominators stay global so per-rank partial losses / gradients simply add."""
+    if mode not in ('NN', 'autograd'):
+        raise ValueError(mode)
+    net = net_spec(model)
+    d = grid.shape[1]
+    if d != net.widths[0]:
+        raise ValueError(f'grid has {d} columns but the network takes {net.widths[0]} inputs')
+    n_eq = len(prepared_operator)
+    if n_eq > MAX_COLS:
+        raise UnsupportedProblem(f'at most {MAX_COLS} equations')
+    segments: List[SegmentIR] = []
+
+    # ---- interior residual --------------------------------------------------------------------------
+    if mode == 'NN':
+        central = Points_type(grid).central_mask()
+        pts = grid[central].contiguous()
+        coeff_rows = (lambda c: c[central] if c.numel() == grid.shape[0] else c)
+    else:
+        central = None
+        pts = grid.contiguous()
+        coeff_rows = None
+    cols = [parse_operator(eq, pts, coeff_rows) for eq in prepared_operator]
+    n_interior = pts.shape[0]
+    if mode == 'NN' and nn_interior == 'literal':
+        seg = _interior_literal_fd('operator', pts, cols, list(range(n_eq)), h)
+    else:
+        js = jet_spec(cols)
+        seg = SegmentIR('operator', pts, 1, js, None, lambda f, js=js: js.channel(f.axes), cols,
+                        list(range(n_eq)), None)
+    segments.append(seg)
+
+    # ---- boundary rows ------------------------------------------------------------------------------
+    bnd_types: List[str] = []
+    type_len: Dict[str, int] = {}
+    if not bconds:
+        raise UnsupportedProblem('a problem without boundary conditions has no finite loss in the reference '
+                                 '(losses.py:250-255)')
+    ptype = Points_type(grid) if mode == 'NN' else None
+    for ci, bc in enumerate(bconds):
+        kind = bc['type']
+        if kind not in bnd_types:
+            bnd_types.append(kind)
+            type_len[kind] = 0
+        slot = n_eq + bnd_types.index(kind)
+        bop, var = bc['bop'], bc['var']
+        name = f'bc{ci}:{kind}'
+        if kind == 'periodic':
+            sides = [b.to(grid.dtype) for b in bc['bnd']]
+            n = sides[0].shape[0]
+            if any(s.shape[0] != n for s in sides):
+                raise ValueError(f'{name}: periodic sides must have the same number of points')
+            target = torch.zeros(n, dtype=grid.dtype, device=grid.device)   # bval [0.] zero-pads (q2)
+            K = len(sides)
+            sign = [1.0] + [-1.0] * (K - 1)
+            pts_g = torch.stack(sides, dim=1).reshape(-1, d).contiguous()
+            if bop is None:
+                comb = np.array([sign])
+                segments.append(SegmentIR(name, pts_g, K, JetSpec([]), comb, lambda f: 0,
+                                          [_value_term(var)], [slot], target.reshape(-1, 1),
+                                          row_index=torch.arange(type_len[kind], type_len[kind] + n)))
+            else:
+                if mode == 'NN':
+                    raise UnsupportedProblem(f'{name}: NN-mode periodic condition with an operator')
+                terms = parse_operator(bop, sides[0])
+                if not _is_linear(terms) or any(isinstance(t.coeff, torch.Tensor) for t in terms):
+                    raise UnsupportedProblem(f'{name}: periodic operator must be linear with constant coefficients')
+                js = jet_spec([terms])
+                J = js.J
+                comb = np.zeros((J, K * J))
+                for k in range(K):
+                    for c in range(J):
+                        comb[c, k * J + c] = sign[k]
+                segments.append(SegmentIR(name, pts_g, K, js, comb, lambda f, js=js: js.channel(f.axes),
+                                          [terms], [slot], target.reshape(-1, 1),
+                                          row_index=torch.arange(type_len[kind], type_len[kind] + n)))
+            type_len[kind] += n
+            continue
+
+        bnd = bc['bnd'].to(grid.dtype)
+        n = bnd.shape[0]
+        target = bc['bval'].reshape(-1).to(grid.dtype)
+        if target.numel() != n:
+            raise ValueError(f'{name}: {target.numel()} target values for {n} boundary points')
+        base = type_len[kind]
+        if kind == 'dirichlet' or (kind == 'data' and bop is None):
+            segments.append(SegmentIR(name, bnd.contiguous(), 1, JetSpec([]), None, lambda f: 0,
+                                      [_value_term(var)], [slot], target.reshape(-1, 1),
+                                      row_index=torch.arange(base, base + n)))
+        elif kind in ('operator', 'data', 'robin'):
+            if kind == 'robin':
+                if mode == 'NN':
+                    raise UnsupportedProblem('NN-mode robin conditions fail in the reference too (eval.py:357-388)')
+                terms = _robin_terms(bop, bnd, var)
+            else:
+                terms = None
+            if mode == 'autograd':
+                terms = terms or parse_operator(bop, bnd)
+                js = jet_spec([terms])
+                segments.append(SegmentIR(name, bnd.contiguous(), 1, js, None,
+                                          lambda f, js=js: js.channel(f.axes), [terms], [slot],
+                                          target.reshape(-1, 1), row_index=torch.arange(base, base + n)))
+            else:
+                _, names = ptype.bnd_types(bnd)
+                order = []
+                for nm in names:
+                    if nm not in order:
+                        order.append(nm)
+                for nm in order:
+                    idx = torch.tensor([i for i, x in enumerate(names) if x == nm], device=bnd.device)
+                    sub = bnd[idx]
+                    terms_t = parse_operator(bop, sub, lambda c, idx=idx: c[idx] if c.numel() == n else c)
+                    variant = inner_order if nm == 'central' else boundary_order
+                    segments.append(_stencil_segment(f'{name}:{nm}', sub, terms_t, target[idx], slot, h,
+                                                     variant, nm, base + idx.cpu()))
+        else:
+            raise ValueError(f'unknown condition type {kind!r}')
+        type_len[kind] += n
+
+    max_len = max(type_len.values())
+    lam_op = _lambda_list(lambda_operator, n_eq, 'lambda_operator')
+    lam_b = _lambda_list(lambda_bound, len(bnd_types), 'lambda_bound')
+    ir = ProblemIR(mode, d, net, segments, n_eq, bnd_types,
+                   [n_interior] * n_eq + [max_len] * len(bnd_types), lam_op + lam_b, n_interior)
+    ir.type_len = [type_len[t] for t in bnd_types]
+    for s in ir.segments:
+        s.n_groups_global = s.n_groups
+    if shard[1] > 1:
+        _shard_segments(ir, *shard)
+    return ir
+
+
+def _robin_terms(bop: dict, bnd: torch.Tensor, var: int) -> List[TermIR]:
+    """value = alpha * u + sum_beta beta * (whole bop applied) with alpha, betas = the terms' coefficients
+    (tedeous/eval.py:357-388; the alpha*u term is counted again inside every beta term - SURVEY B.1 q5)."""
+    coeffs = [bop[k]['coeff'] for k in bop]
+    alpha, betas = coeffs[0], coeffs[1:]
+    base = parse_operator(bop, bnd)
+
+    def scale(c, t):
+        c = c(bnd).reshape(-1) if callable(c) else c
+        if isinstance(t.coeff, torch.nn.Parameter):
+            raise UnsupportedProblem('robin condition with trainable coefficients')
+        return t.coeff * c
+
+    a = alpha(bnd).reshape(-1) if callable(alpha) else float(alpha)
+    terms = [TermIR(a, [FactorIR(int(var), (), 1.0)])]
+    for beta in betas:
+        for t in base:
+            terms.append(TermIR(scale(beta, t), list(t.factors)))
+    return terms
+
+
+def _shard_segments(ir: ProblemIR, rank: int, world: int) -> None:
+    for s in ir.segments:
+        n = s.n_groups
+        lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+        s.points = s.points[lo * s.K: hi * s.K].contiguous()
+        if s.targets is not None:
+            s.targets = s.targets[lo:hi].contiguous()
+        if s.row_index is not None:
+            s.row_index = s.row_index[lo:hi]
+        for terms in s.cols:
+            for t in terms:
+                if isinstance(t.coeff, torch.Tensor) and not isinstance(t.coeff, torch.nn.Parameter):
+                    t.coeff = t.coeff[lo:hi].contiguous()
+        s.shard_range = (lo, hi)
+
+
+# ----------------------------------------------------------------------------------------------------
+# flattening for the C ABI
+# ----------------------------------------------------------------------------------------------------
+@dataclass
+class FlatIR:
+    seg: np.ndarray
+    terms: np.ndarray
+    factors: np.ndarray
+    comb: np.ndarray                 # float32
+    points: torch.Tensor             # [total_points, d] float32 on the device
+    targets: torch.Tensor            # float32
+    coeffs: torch.Tensor             # float32
+    n_fields: int
+    cparam_index: Dict[int, int]
+
+
+def flatten(ir: ProblemIR, device) -> FlatIR:
+    seg = np.zeros(len(ir.segments), dtype=SEGMENT_DTYPE)
+    terms, factors, comb = [], [], []
+    pts, tgts, coefs = [], [], []
+    pts_off = tgt_off = coef_off = field_off = 0
+    cparam_index = {id(p): i for i, p in enumerate(ir.net.coeff_params)}
+    for si, s in enumerate(ir.segments):
+        r = seg[si]
+        J = s.jet.J
+        r['n_groups'], r['pts_off'], r['K'], r['M'], r['n_cols'] = s.n_groups, pts_off, s.K, s.M, len(s.cols)
+        r['n_dirs'] = len(s.jet.dirs)
+        for i, (a, o) in enumerate(s.jet.dirs):
+            r['dir_axis'][i], r['dir_order'][i] = a, o
+        points_per_tile(J, s.K)                       # validates the tile shape
+        if s.M > J * s.K:
+            raise UnsupportedProblem(f'{s.name}: more virtual channels than evaluated jets')
+        r['identity'] = 1 if s.comb is None else 0
+        r['comb_off'] = sum(c.size for c in comb)
+        if s.comb is not None:
+            assert s.comb.shape == (s.M, s.K * J), (s.comb.shape, s.M, s.K, J)
+            comb.append(np.asarray(s.comb, dtype=np.float32).reshape(-1))
+        r['field_off'] = field_off
+        field_off += s.n_groups * len(s.cols)
+        if s.targets is not None:
+            r['tgt_off'] = tgt_off
+            tgts.append(s.targets.reshape(-1).to(device=device, dtype=torch.float32))
+            tgt_off += s.targets.numel()
+        else:
+            r['tgt_off'] = -1
+        for ci, (tl, slot) in enumerate(zip(s.cols, s.slots)):
+            r['col_term_begin'][ci] = len(terms)
+            for t in tl:
+                fb = len(factors)
+                for f in t.factors:
+                    ip = int(f.pow) if float(f.pow).is_integer() and 0 <= f.pow <= 16 else -1
+                    factors.append((f.var, s.chan_of(f), f.pow, ip))
+                    if f.var >= ir.net.widths[-1]:
+                        raise ValueError(f'{s.name}: var {f.var} but the network has {ir.net.widths[-1]} outputs')
+                if isinstance(t.coeff, torch.nn.Parameter):
+                    if id(t.coeff) not in cparam_index:
+                        raise UnsupportedProblem('trainable coefficient is not registered on the network '
+                                                 '(use parameter_registr)')
+                    terms.append((0.0, COEFF_PARAM, cparam_index[id(t.coeff)], fb, len(factors)))
+                elif isinstance(t.coeff, torch.Tensor):
+                    terms.append((0.0, COEFF_BUFFER, coef_off, fb, len(factors)))
+                    coefs.append(t.coeff.reshape(-1).to(device=device, dtype=torch.float32))
+                    coef_off += t.coeff.numel()
+                else:
+                    terms.append((float(t.coeff), COEFF_CONST, 0, fb, len(factors)))
+            r['col_term_end'][ci] = len(terms)
+            r['col_slot'][ci] = slot
+        pts.append(s.points.to(device=device, dtype=torch.float32))
+        pts_off += s.points.shape[0]
+
+    def cat(lst):
+        return torch.cat(lst).contiguous() if lst else torch.zeros(1, dtype=torch.float32, device=device)
+    return FlatIR(seg, np.array(terms, dtype=TERM_DTYPE) if terms else np.zeros(0, TERM_DTYPE),
+                  np.array(factors, dtype=FACTOR_DTYPE) if factors else np.zeros(0, FACTOR_DTYPE),
+                  np.concatenate(comb).astype(np.float32) if comb else np.zeros(1, np.float32),
+                  torch.cat(pts).contiguous(), cat(tgts), cat(coefs), field_off, cparam_index)
