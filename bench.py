@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Benchmark of the residual-loss hot path: collocation points per second for one loss + gradient step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+* A *step* is one evaluation of loss and the full parameter gradient over every collocation point
+  (`Solution.evaluate(); loss.backward()` in the reference, one `tdb200_loss_grad` call here), plus the NCCL
+  all-reduce of the [loss terms | gradient] vector when N > 1.
+* Default workload = BASELINE.json configs[1]: wave equation 1D+t, mode 'autograd' (2nd-order jets), 10^6
+  collocation points per GPU, tanh MLP 2-100-100-100-1.  Scaling is weak: every rank holds 10^6 points.
+* `value` is timed with inputs resident in HBM; `e2e` goes through the public API (`Solution.evaluate` +
+  `loss.backward()`) with the step's point set copied from pinned host memory and the result read back.
+* `--impl reference` times the CPU port of the reference's algorithm (oracle/tedeous_oracle.py, torch CPU,
+  all host threads) on a bounded sample of the same workload.
+
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+METRIC = 'collocation pts/s for loss+grad step'
+UNIT = 'pts/s'
+
+# algorithmic FLOPs per point: 3 (fwd, bwd-data, bwd-weight) * J jet channels * 2 * sum(in*out)  
+WORKLOADS = {
+    # name: (builder name in tests/problems.py, kwargs, J, description)
+    'wave_autograd_1e6': dict(fn='wave', kw=dict(n=999, mode='autograd', layers=(2, 100, 100, 100, 1)), J=5,
+                              desc='wave 1D+t autograd, 1000x1000 pts/GPU, MLP 2-100-100-100-1'),
+    'burgers_NN_cfg1': dict(fn='burgers', kw=dict(n=100, mode='NN', layers=(2, 100, 100, 100, 1)), J=4,
+                            desc='Burgers 1D NN mode, 101x101 grid (9801 central pts), MLP 2-100-100-100-1'),
+    'burgers_autograd_1e6': dict(fn='burgers', kw=dict(n=999, mode='autograd', layers=(2, 100, 100, 100, 1)), J=4,
+                                 desc='Burgers 1D autograd, 1000x1000 pts/GPU'),
+    'kdv_autograd_1e6': dict(fn='kdv', kw=dict(nx=999, nt=999, mode='autograd', layers=(2, 100, 100, 100, 1)), J=5,
+                             desc='KdV periodic autograd, 1000x1000 pts/GPU'),
+    'ns_autograd_1e6': dict(fn='navier_stokes', kw=dict(n=99, layers=(3, 100, 100, 100, 100, 100, 100, 3)), J=6,
+                            desc='Navier-Stokes 2D+t autograd, 100^3 pts/GPU, MLP 3-100x6-3'),
+}
+
+
+def flop_per_point(layers, J):
+    return 3 * J * 2 * sum(a * b for a, b in zip(layers[:-1], layers[1:]))
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile('w', suffix='.csv', delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-i', str(self.idx), '-lms', '100'], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(',')]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1])); mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), c[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def load_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), 'measured'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
+
+
+def measure_tf32_tflops(device, seconds=1.0):
+    """Dense TF32 cuBLAS throughput of this GPU (the 3xTF32 roofline denominator is this / 3)."""
+    n = 8192
+    a = torch.randn(n, n, device=device)
+    b = torch.randn(n, n, device=device)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize(device)
+        best = 0.0
+        t_end = time.time() + seconds
+        while time.time() < t_end:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); a @ b; e1.record(); e1.synchronize()
+            best = max(best, 2 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    del a, b
+    return best
+
+
+def make_problem(workload, api, world):
+    """The workload with `world` times more nodes along the first axis (weak scaling: every rank keeps the
+    single-GPU number of points)."""
+    import problems
+    spec = WORKLOADS[workload]
+    kw = dict(spec['kw'])
+    if world > 1:
+        if 'nx' in kw:
+            kw['nx'] = (kw['nx'] + 1) * world - 1
+        else:
+            kw['n0'] = (kw['n'] + 1) * world - 1
+    return spec, getattr(problems, spec['fn'])(api, 'float32', **kw)
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    import torch_de_solver_b200 as tdb
+    import problems
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.gpus > 1 and world != args.gpus:
+        raise SystemExit(f'--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    torch.set_default_device(dev)
+
+    spec, prob = make_problem(args.workload, tdb, world)
+    net = problems.make_net(prob.net_layers, torch.float32, prob.init).to(dev)
+    model = tdb.Model(net, prob.domain, prob.equation, prob.conditions)
+    model.compile(prob.mode, **prob.compile_kwargs, shard=(rank, world) if world > 1 else None)
+    sol = model.solution_cls
+    plan = sol._plan
+    n_local = sol._ir.segments[0].n_groups
+    n_global = sol._ir.n_interior
+    params = list(net.parameters())
+
+    def step_resident():
+        out = plan.loss_grad()
+        if world > 1:
+            dist.all_reduce(out)
+        return out
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    def timed(fn, steps):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for e0, e1 in ev:
+            flush.zero_()
+            e0.record()
+            fn()
+            e1.record()
+        torch.cuda.synchronize(dev)
+        return [e0.elapsed_time(e1) for e0, e1 in ev]
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    t_wall = time.time()
+    times = timed(step_resident, args.steps)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    total_ms = sum(times)
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t)
+    ms_per_step = total_ms / args.steps
+    value = n_global / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API, host buffers ----------------------------------------------
+    flat = plan.flat
+    host_in = [t.detach().cpu().pin_memory() for t in (flat.points, flat.targets, flat.coeffs)]
+    dev_in = [flat.points, flat.targets, flat.coeffs]
+    host_out = torch.empty(plan.out_size, dtype=torch.float32).pin_memory()
+    h2d = sum(t.numel() * 4 for t in host_in)
+    d2h = host_out.numel() * 4
+
+    def step_e2e():
+        for h, d in zip(host_in, dev_in):
+            d.copy_(h, non_blocking=True)
+        for p in params:
+            p.grad = None
+        loss, _ = sol.evaluate()
+        loss.backward()
+        host_out.copy_(sol._last_out, non_blocking=True)
+
+    for _ in range(3):
+        step_e2e()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e2e_steps = max(3, min(args.steps, 20))
+    e2e_times = timed(step_e2e, e2e_steps)
+    e2e_ms = sum(e2e_times)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t)
+    e2e_value = n_global / (e2e_ms / e2e_steps * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = load_peaks()
+    torch.set_default_device('cpu')
+    tf32 = measure_tf32_tflops(dev)
+    fpp = flop_per_point(prob.net_layers, spec['J'])
+    achieved = (n_local / (statistics.mean(times) * 1e-3)) * fpp / 1e12
+    peak = tf32 / 3.0
+    cpu = cpu_baseline(args.workload) if not args.no_cpu_baseline else None
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': args.workload, 'description': spec['desc'], 'points_per_gpu': n_local,
+                   'points_total': n_global, 'mlp': list(prob.net_layers), 'mode': prob.mode,
+                   'jet_channels': spec['J'], 'kernel': 'simt-fp32' if plan.launches_per_call == 3 else 'tcgen05-3xtf32',
+                   'l2': 'flushed between timed steps (256 MB write)', 'parallelism': f'dp{world} (points sharded)'},
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'ms_per_step': e2e_ms / e2e_steps},
+        'gpu_launches': args.steps * plan.launches_per_call,
+        'clocks': clocks,
+        'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+                     'frac': achieved / peak if peak else None, 'traffic': None,
+                     'flop_per_point': fpp,
+                     'peak_source': f'cuBLAS TF32 8192^3 measured live = {tf32:.1f} TFLOP/s, / 3 for 3xTF32 '
+                                    f'(MEASURED_PEAKS.json [{peak_src}] bf16 = {peaks.get("bf16_tflops")})'},
+        'cpu_baseline': cpu,
+        'wall_s': time.time() - t_wall,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------
+CPU_SAMPLE = {   # bounded CPU samples of the same operators (reference cost is flat in N)
+    'wave_autograd_1e6': dict(fn='wave', kw=dict(n=315, mode='autograd', layers=(2, 100, 100, 100, 1))),
+    'burgers_NN_cfg1': dict(fn='burgers', kw=dict(n=100, mode='NN', layers=(2, 100, 100, 100, 1))),
+    'burgers_autograd_1e6': dict(fn='burgers', kw=dict(n=315, mode='autograd', layers=(2, 100, 100, 100, 1))),
+    'kdv_autograd_1e6': dict(fn='kdv', kw=dict(nx=199, nt=199, mode='autograd', layers=(2, 100, 100, 100, 1))),
+    'ns_autograd_1e6': dict(fn='navier_stokes', kw=dict(n=20, layers=(3, 100, 100, 100, 100, 100, 100, 3))),
+}
+
+
+def cpu_step_time(workload, steps=3, warmup=1):
+    """Times the oracle port (same call pattern as the reference) on the host cores."""
+    import problems
+    import torch_de_solver_b200 as tdb
+    from oracle import tedeous_oracle as orc
+    torch.set_default_device('cpu')
+    spec = CPU_SAMPLE[workload]
+    prob = getattr(problems, spec['fn'])(tdb, 'float32', **spec['kw'])
+    grid = prob.domain.build(prob.mode)
+    bconds = prob.conditions.build(prob.domain.variable_dict)
+    net = problems.make_net(prob.net_layers, torch.float32, prob.init)
+    kw = prob.compile_kwargs
+    sol = orc.OracleSolution(grid, prob.equation.equation_lst, bconds, net, prob.mode, kw['lambda_operator'],
+                             kw['lambda_bound'], h=kw.get('h', 0.001))
+    params = list(net.parameters())
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        orc.loss_and_grad(sol, params)
+        ts.append(time.perf_counter() - t0)
+    n = sol.op.shape[0]
+    return n, ts[warmup:], f"{spec['fn']} {spec['kw']} -> {n} operator points"
+
+
+def cpu_baseline(workload):
+    n, ts, sample = cpu_step_time(workload)
+    return {'value': n / min(ts), 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': sample + f'; min of {len(ts)} steps after 1 warm-up; torch {torch.__version__} CPU, '
+                               f'os.cpu_count()={os.cpu_count()}'}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    n, ts, sample = cpu_step_time(args.workload, steps=max(1, min(args.steps, 5)), warmup=min(max(args.warmup, 1), 2))
+    ms = statistics.mean(ts) * 1e3
+    val = n / (ms * 1e-3)
+    spec = WORKLOADS[args.workload]
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': len(ts), 'warmup': min(max(args.warmup, 1), 2), 'ms_per_step': ms, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': args.workload, 'description': spec['desc'], 'sample': sample},
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+                         'sample': sample},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='wave_autograd_1e6', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,178 @@
+/* tdb200.h - C ABI of libtedeous_b200.so: the B200 (sm_100a) residual-loss hot path of TEDEouS.
+ *
+ * The reference (ITMO-NSS-team/torch_DE_solver v0.4.11) is pure Python and has no FFI layer; the seam every
+ * caller goes through is `Solution.evaluate()` followed by `loss.backward()`:
+ *     tedeous/solution.py:129-168      Solution.evaluate            -> tdb200_loss_grad / tdb200_mat_loss_grad
+ *     tedeous/eval.py:223-232          Operator.operator_compute    -> tdb200_eval_fields (op part)
+ *     tedeous/eval.py:433-461          Bounds.apply_bcs             -> tdb200_eval_fields (bval part)
+ *     tedeous/derivative.py:30-132     Derivative_NN / _autograd    -> jet channels inside tdb200_loss_grad
+ *     tedeous/derivative.py:135-323    Derivative_mat               -> tdb200_mat_loss_grad
+ *     tedeous/finite_diffs.py:244-268  Finite_diffs.scheme_choose   -> host side (stencil combos in `comb`)
+ *     tedeous/losses.py:84-135         Losses._default_loss         -> out[0..2+n_slots) of tdb200_loss_grad
+ *     tedeous/optimizers/closure.py:60 loss.backward()              -> out[2+n_slots ..) (the flat gradient)
+ *
+ * Conventions: plain pointers and sizes only; every `*_dev` pointer is device memory owned by the caller
+ * (torch); every entry returns 0 on success or a negative tdb200_status, with a message available from
+ * tdb200_last_error(); launches are asynchronous on the `stream` argument (a cudaStream_t passed as void*).
+ * A plan is not thread-safe; distinct plans are independent.  There is no CPU fallback.
+ */
+#ifndef TDB200_H
+#define TDB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDB200_MAX_LAYERS 16
+#define TDB200_MAX_DIRS 4
+#define TDB200_MAX_COLS 8
+#define TDB200_MAX_K 32
+#define TDB200_MAX_M 8
+#define TDB200_MAX_J 8
+#define TDB200_ROWS_PER_TILE 128
+
+typedef enum {
+  TDB200_OK = 0,
+  TDB200_ERR_INVALID = -1,      /* bad argument / unsupported shape */
+  TDB200_ERR_CUDA = -2,         /* CUDA runtime error (see tdb200_last_error) */
+  TDB200_ERR_NO_DEVICE = -3,    /* no sm_100 device */
+  TDB200_ERR_ALLOC = -4
+} tdb200_status;
+
+/* One segment = a set of residual rows sharing operators and layout (see torch_de_solver_b200/plan.py).
+ * A row is a group of K evaluation points; its channel values are V[m] = sum comb[m][k*J+c] * jet_c(x_k)
+ * (identity != 0: K == 1 and V == jets). */
+typedef struct {
+  int64_t n_groups;
+  int64_t pts_off;                       /* first row of `pts` */
+  int64_t tgt_off;                       /* first float in `targets`, -1: zero targets */
+  int64_t field_off;                     /* first float in the fields output */
+  int32_t K, M, n_cols, n_dirs;
+  int32_t dir_axis[TDB200_MAX_DIRS];     /* jet directions: input axis ... */
+  int32_t dir_order[TDB200_MAX_DIRS];    /* ... and highest derivative order (1..4) */
+  int32_t col_term_begin[TDB200_MAX_COLS];
+  int32_t col_term_end[TDB200_MAX_COLS];
+  int32_t col_slot[TDB200_MAX_COLS];     /* loss slot every residual column accumulates into */
+  int32_t identity;
+  int32_t comb_off;                      /* first float of this segment's [M][K*J] matrix in `comb` */
+} tdb200_segment;
+
+/* term = coeff * prod_f chan[f]^pow_f;  kind 0: immediate `coeff`, 1: per-row buffer coeffs[idx + row],
+ * 2: trainable scalar number `idx` (appended after the network parameters) */
+typedef struct {
+  float coeff;
+  int32_t kind;
+  int64_t idx;
+  int32_t fac_begin, fac_end;
+} tdb200_term;
+
+typedef struct {
+  int32_t var;        /* network output */
+  int32_t chan;       /* virtual channel */
+  float pow;
+  int32_t ipow;       /* integer power 0..16, or -1 -> powf */
+} tdb200_factor;
+
+typedef struct {
+  int32_t n_layers;                          /* Linear layers, >= 2; tanh between them */
+  int32_t widths[TDB200_MAX_LAYERS + 1];     /* d, w1, ..., n_out */
+  int32_t n_cparams;                         /* trainable scalar coefficients */
+} tdb200_net;
+
+typedef struct tdb200_plan tdb200_plan;
+
+/* Build a plan for modes 'NN' / 'autograd'.  Host arrays are copied. */
+int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_segment* segments,
+                       int32_t n_terms, const tdb200_term* terms, int32_t n_factors,
+                       const tdb200_factor* factors, int32_t n_comb, const float* comb, int32_t n_slots,
+                       int32_t device, tdb200_plan** out);
+
+/* Bind the (caller-owned, device) point / target / coefficient buffers.  pts is [n_pts, d] row-major. */
+int tdb200_plan_set_points(tdb200_plan* plan, const float* pts_dev, int64_t n_pts, const float* targets_dev,
+                           int64_t n_targets, const float* coeffs_dev, int64_t n_coeffs);
+
+/* Per-slot lambda and 1/len (global row count of the slot): scale = lambda/len enters the gradient. */
+int tdb200_plan_set_slots(tdb200_plan* plan, const double* slot_lambda, const double* slot_len);
+
+/* Choose the kernel implementation: 0 = auto, 1 = SIMT fp32, 2 = tcgen05 3xTF32 (errors if unsupported). */
+int tdb200_plan_set_impl(tdb200_plan* plan, int32_t impl);
+
+/* Number of floats of the output vector of tdb200_loss_grad: 2 + n_slots + n_params. */
+int64_t tdb200_plan_out_size(const tdb200_plan* plan);
+int64_t tdb200_plan_n_params(const tdb200_plan* plan);
+int64_t tdb200_plan_n_fields(const tdb200_plan* plan);
+/* Kernel launches one tdb200_loss_grad call enqueues. */
+int32_t tdb200_plan_launches_per_call(const tdb200_plan* plan);
+
+/* One optimiser-step evaluation (replaces Solution.evaluate + loss.backward).
+ * params_dev: host array of 2*n_layers + n_cparams device pointers (W0, b0, W1, b1, ..., c0, ...), W row-major
+ * [out, in] as torch.nn.Linear stores it.
+ * out_dev[0] = loss, out_dev[1] = loss_normalized (lambda == 1), out_dev[2 + s] = mean-square of slot s,
+ * out_dev[2 + n_slots ...] = d loss / d params in the order of params_dev, flattened.
+ * With several GPUs every rank gets partial sums that add up across ranks (slot_len is global). */
+int tdb200_loss_grad(tdb200_plan* plan, const float* const* params_dev, float* out_dev, void* stream);
+
+/* Forward only: per-row operator values (before subtracting targets) into fields_dev[n_fields]; also fills
+ * out_dev[0 .. 2+n_slots) when out_dev != NULL. */
+int tdb200_eval_fields(tdb200_plan* plan, const float* const* params_dev, float* fields_dev, float* out_dev,
+                       void* stream);
+
+void tdb200_plan_destroy(tdb200_plan* plan);
+
+/* ---- mat mode (tedeous/derivative.py:135-323): grid-stencil residual + adjoint --------------------- */
+
+/* 1-D derivative operator D^order along one axis as a banded matrix: row i, offsets -b..b.
+ * Interior rows share `interior`; the first/last n_edge rows have their own coefficients. */
+typedef struct {
+  int32_t var, axis, order;              /* which field, which axis, how many applications of D */
+  int32_t half_width;                    /* b */
+  int32_t n_edge;
+  int32_t coef_off;                      /* into `band`: interior[2b+1], lo[n_edge][2b+1], hi[n_edge][2b+1] */
+} tdb200_mat_field;                      /* derivative field F_q = D^order_axis u_var */
+
+typedef struct {
+  int32_t n_eq, n_var, n0, n1;           /* model is [n_var, n0, n1]; n_eq residual columns */
+  int32_t n_fields;                      /* distinct derivative fields (field 0..n_var-1 = values) */
+} tdb200_mat_desc;
+
+typedef struct tdb200_mat_plan tdb200_mat_plan;
+
+/* terms/factors as above with factor.chan = derivative-field index; term kind 1 buffers are [n0*n1]. */
+int tdb200_mat_plan_create(const tdb200_mat_desc* desc, const tdb200_mat_field* fields, int32_t n_band,
+                           const float* band, const int32_t* eq_term_begin, const int32_t* eq_term_end,
+                           int32_t n_terms, const tdb200_term* terms, int32_t n_factors,
+                           const tdb200_factor* factors, int32_t device, tdb200_mat_plan** out);
+int tdb200_mat_plan_set_coeffs(tdb200_mat_plan* plan, const float* coeffs_dev, int64_t n_coeffs);
+
+/* Boundary rows: row r = sum_k sign[k] * (bop or value)(cell[r*K + k]); `cells` are flat indices i0*n1+i1.
+ * bc_term_begin == bc_term_end: value of `var`.  slot is relative to the boundary slots. */
+typedef struct {
+  int64_t n_rows;
+  int64_t cell_off;                      /* into cells_dev (n_rows*K ints) */
+  int64_t tgt_off;                       /* into targets_dev (n_rows floats) */
+  int32_t K, var, slot;
+  int32_t term_begin, term_end;
+  float sign[4];
+} tdb200_mat_bc;
+
+int tdb200_mat_plan_set_bcs(tdb200_mat_plan* plan, int32_t n_bcs, const tdb200_mat_bc* bcs,
+                            const int32_t* cells_dev, const float* targets_dev, int32_t n_slots,
+                            const double* slot_lambda, const double* slot_len);
+
+/* out_dev[0] = loss, [1] = loss_normalized, [2 + s] = slot mean squares (n_eq + n_bc_slots);
+ * grad_dev [n_var, n0, n1] = d loss / d u. */
+int tdb200_mat_loss_grad(tdb200_mat_plan* plan, const float* u_dev, float* grad_dev, float* out_dev,
+                         void* stream);
+int64_t tdb200_mat_plan_out_size(const tdb200_mat_plan* plan);
+int32_t tdb200_mat_plan_launches_per_call(const tdb200_mat_plan* plan);
+void tdb200_mat_plan_destroy(tdb200_mat_plan* plan);
+
+const char* tdb200_last_error(void);
+int tdb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDB200_H */

@@ -1,0 +1,61 @@
+"""Test helper: executes a lowered ProblemIR (torch_de_solver_b200.plan) with plain torch autograd on the CPU.
+
+It mirrors what the CUDA kernel does with the IR (jets -> virtual channels -> term table -> residual ->
+slot sums) so the *lowering* can be validated against the golden fixtures without a GPU.  It lives under
+tests/ on purpose: the product has no CPU path."""
+import torch
+
+from torch_de_solver_b200.plan import ProblemIR
+
+
+def _jets(model, pts, jet):
+    """[n_pts, J, n_out] values of every jet channel."""
+    pts = pts.clone().requires_grad_(True)
+    out = model(pts)
+    n_out = out.shape[1]
+    chans = [out]
+    for axis, order in jet.dirs:
+        cur = out
+        for _ in range(order):
+            cols = []
+            for v in range(n_out):
+                g, = torch.autograd.grad(cur[:, v].sum(), pts, create_graph=True)
+                cols.append(g[:, axis])
+            cur = torch.stack(cols, 1)
+            chans.append(cur)
+    return torch.stack(chans, 1)
+
+
+def evaluate_ir(ir: ProblemIR, model, dtype=torch.float64):
+    """-> (loss, loss_normalized, slot_mse list, fields per segment)"""
+    sums = [torch.zeros((), dtype=dtype) for _ in range(ir.n_slots)]
+    fields = []
+    for s in ir.segments:
+        pts = s.points.to(dtype)
+        J, K, M = s.jet.J, s.K, s.M
+        jets = _jets(model, pts, s.jet)                           # [n*K, J, n_out]
+        n = s.n_groups
+        jets = jets.reshape(n, K * J, -1)
+        if s.comb is None:
+            V = jets
+        else:
+            V = torch.einsum('mq,nqv->nmv', torch.as_tensor(s.comb, dtype=dtype), jets)
+        cols = []
+        for terms, slot in zip(s.cols, s.slots):
+            val = torch.zeros(n, dtype=dtype)
+            for t in terms:
+                c = t.coeff
+                prod = c.to(dtype).reshape(-1) if isinstance(c, torch.Tensor) else torch.full((n,), float(c), dtype=dtype)
+                for f in t.factors:
+                    prod = prod * V[:, s.chan_of(f), f.var] ** f.pow
+                val = val + prod
+            cols.append(val)
+        vals = torch.stack(cols, 1)
+        fields.append(vals)
+        res = vals - (s.targets.to(dtype) if s.targets is not None else 0.)
+        for ci, slot in enumerate(s.slots):
+            sums[slot] = sums[slot] + (res[:, ci] ** 2).sum()
+    mse = [sm / ln for sm, ln in zip(sums, ir.slot_len)]
+    loss = sum(l * m for l, m in zip(ir.slot_lambda, mse))
+    loss_n = sum(mse)
+    return loss, loss_n, mse, fields

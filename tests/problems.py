@@ -59,10 +59,10 @@ def make_mat_model(shape, dtype=torch.float32, seed=0) -> torch.Tensor:
 
 
 # --- config 1: Burgers (examples/examples_burgers/example_burgers_1d.py:35-80) ----------------------------
-def burgers(api, dtype='float32', n=100, mode='NN', layers=(2, 100, 100, 100, 1), h=0.001):
+def burgers(api, dtype='float32', n=100, mode='NN', layers=(2, 100, 100, 100, 1), h=0.001, n0=None):
     mu = 0.01 / math.pi
     dom = api.Domain()
-    dom.variable('x', [-1, 1], n, dtype=dtype)
+    dom.variable('x', [-1, 1], n0 or n, dtype=dtype)
     dom.variable('t', [0, 1], n, dtype=dtype)
     bc = api.Conditions()
     bc.dirichlet({'x': [-1, 1], 't': 0}, value=lambda g: -torch.sin(np.pi * g[:, 0]))
@@ -81,12 +81,12 @@ def burgers(api, dtype='float32', n=100, mode='NN', layers=(2, 100, 100, 100, 1)
 
 
 # --- config 2: wave (examples/examples_wave/example_wave_1d_basic.py:36-97) ---------------------------------
-def wave(api, dtype='float32', n=40, mode='autograd', layers=(2, 100, 100, 100, 1), h=0.01, operator_ic=True):
+def wave(api, dtype='float32', n=40, mode='autograd', layers=(2, 100, 100, 100, 1), h=0.01, operator_ic=True, n0=None):
     def exact(g):
         x, t = g[:, 0], g[:, 1]
         return torch.sin(np.pi * x) * torch.cos(2 * np.pi * t) + 0.5 * torch.sin(4 * np.pi * x) * torch.cos(8 * np.pi * t)
     dom = api.Domain()
-    dom.variable('x', [0, 1], n, dtype=dtype)
+    dom.variable('x', [0, 1], n0 or n, dtype=dtype)
     dom.variable('t', [0, 1], n, dtype=dtype)
     bc = api.Conditions()
     bc.dirichlet({'x': [0, 1], 't': 0}, value=exact)
@@ -130,11 +130,11 @@ def kdv(api, dtype='float32', nx=30, nt=30, mode='autograd', layers=(2, 100, 100
 
 
 # --- config 5: Navier-Stokes 2D+t (examples/examples_navier_stokes/example_navier_stokes_2d_long_time.py:36-198)
-def navier_stokes(api, dtype='float32', n=8, layers=(3, 100, 100, 100, 100, 100, 100, 3)):
+def navier_stokes(api, dtype='float32', n=8, layers=(3, 100, 100, 100, 100, 100, 100, 3), n0=None):
     ro, mu = 1., 1.
     A1, A2, A3 = 1., 1., 1.
     dom = api.Domain()
-    dom.variable('x', [0, 5], n, dtype=dtype)
+    dom.variable('x', [0, 5], n0 or n, dtype=dtype)
     dom.variable('y', [0, 1], n, dtype=dtype)
     dom.variable('t', [0, 5], n, dtype=dtype)
     bc = api.Conditions()

@@ -1,0 +1,170 @@
+"""GPU parity: the fused CUDA path (through Model.compile / Solution.evaluate -> the C ABI) against the golden
+fixtures of the unmodified reference and against the oracle.
+
+Tolerances are the north star's: loss <= 1e-5 relative, gradient norm <= 1e-4 relative; we also bound the
+gradient *vector* error.  The reference values are the fp64 goldens (NN-mode fp32 finite differences carry
+their own cancellation noise)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import problems
+import torch_de_solver_b200 as tdb
+from helpers import load_golden, oracle_eval, set_weights
+
+pytestmark = pytest.mark.gpu
+NET_CASES = sorted(k for k in problems.ZOO if 'mat' not in k)
+LOSS_RTOL, GRADNORM_RTOL, GRADVEC_RTOL = 1e-5, 1e-4, 2e-4
+
+
+@pytest.fixture()
+def cuda_default():
+    torch.set_default_device('cuda:0')
+    yield torch.device('cuda:0')
+    torch.set_default_device('cpu')
+
+
+def fused(name, weights, **opts):
+    prob = problems.ZOO[name](tdb, 'float32')
+    net = problems.make_net(prob.net_layers, torch.float32, prob.init)
+    set_weights(list(net.parameters()), weights)
+    net = net.to('cuda:0')
+    model = tdb.Model(net, prob.domain, prob.equation, prob.conditions)
+    model.compile(prob.mode, **prob.compile_kwargs, **opts)
+    return prob, net, model.solution_cls
+
+
+@pytest.mark.parametrize('name', NET_CASES)
+def test_loss_and_gradient_match_reference(name, cuda_default):
+    g = load_golden(name, 'float64')
+    prob, net, sol = fused(name, g['weights'])
+    loss, loss_n = sol.evaluate()
+    assert loss.shape == (1,) and loss_n.shape == (1,)
+    loss.backward()
+    grad = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).double().cpu().numpy()
+    assert float(loss) == pytest.approx(float(g['loss']), rel=LOSS_RTOL)
+    assert float(loss_n) == pytest.approx(float(g['loss_normalized']), rel=LOSS_RTOL)
+    gn = np.linalg.norm(g['grad'])
+    assert abs(np.linalg.norm(grad) - gn) <= GRADNORM_RTOL * gn
+    assert np.linalg.norm(grad - g['grad']) <= GRADVEC_RTOL * gn
+    np.testing.assert_allclose(sol.op_mse.cpu().numpy(), g['op_mse'], rtol=5e-4)
+    np.testing.assert_allclose(sol.bval_mse.cpu().numpy(), g['bval_mse'], rtol=1e-4)
+    assert sol.bval_keys == [str(k) for k in g['bval_keys']]
+    assert sol.bval_length == [int(x) for x in g['bval_length']]
+
+
+@pytest.mark.parametrize('name', NET_CASES)
+def test_fields_match_reference(name, cuda_default):
+    """op / bval / true_bval as the callbacks read them (Solution attributes)."""
+    g = load_golden(name, 'float64')
+    prob, net, sol = fused(name, g['weights'])
+    sol.evaluate()
+    op = sol.op.cpu().double().numpy()
+    assert op.shape[0] == int(g['op_rows'])
+    scale = np.abs(g['op_head']).max() + 1e-12
+    atol = 3e-3 * scale if prob.mode == 'NN' else 2e-4 * scale
+    np.testing.assert_allclose(op[:256], g['op_head'], atol=atol, rtol=1e-3)
+    np.testing.assert_allclose(sol.true_bval.cpu().numpy(), g['true_bval'], atol=1e-6, rtol=1e-6)
+    bscale = np.abs(g['bval']).max() + 1e-12
+    np.testing.assert_allclose(sol.bval.cpu().numpy(), g['bval'], atol=1e-4 * bscale, rtol=1e-4)
+
+
+@pytest.mark.parametrize('name', ['burgers_NN_small', 'wave_NN', 'kdv_NN'])
+def test_literal_fd_interior(name, cuda_default):
+    """nn_interior='literal' (shifted evaluations, the reference's own arithmetic in fp32) agrees with the fp64
+    reference up to fp32 cancellation noise of the finite differences."""
+    g = load_golden(name, 'float64')
+    prob, net, sol = fused(name, g['weights'], nn_interior='literal')
+    loss, _ = sol.evaluate()
+    assert float(loss) == pytest.approx(float(g['loss']), rel=2e-3)
+
+
+def test_repeatable_and_param_update(cuda_default):
+    """Two calls give bit-identical results (fixed reduction order); weights are re-read every call."""
+    g = load_golden('burgers_NN_small', 'float64')
+    prob, net, sol = fused('burgers_NN_small', g['weights'])
+    a = sol._plan.loss_grad().clone()
+    b = sol._plan.loss_grad().clone()
+    assert torch.equal(a, b)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(1.01)
+    c = sol._plan.loss_grad()
+    assert not torch.equal(a, c)
+
+
+def test_gradient_is_derivative_of_loss(cuda_default):
+    """Size-independent property: directional finite difference of the fused loss matches <grad, v>."""
+    g = load_golden('kdv_autograd', 'float64')
+    prob, net, sol = fused('kdv_autograd', g['weights'])
+    params = list(net.parameters())
+    out = sol._plan.loss_grad()
+    grad = out[2 + sol._n_slots:].double()
+    torch.manual_seed(1)
+    v = [torch.randn_like(p) for p in params]
+    vflat = torch.cat([x.reshape(-1) for x in v]).double()
+    eps = 1e-3
+    losses = []
+    for s in (+1, -1):
+        with torch.no_grad():
+            for p, d in zip(params, v):
+                p.add_(s * eps * d)
+        losses.append(float(sol._plan.loss_grad()[0]))
+        with torch.no_grad():
+            for p, d in zip(params, v):
+                p.sub_(s * eps * d)
+    fd = (losses[0] - losses[1]) / (2 * eps)
+    assert fd == pytest.approx(float(grad @ vflat), rel=2e-3)
+
+
+def test_large_grid_consistency(cuda_default):
+    """Full-size property (10^6 points): the loss of a grid equals the row-weighted mean of the losses of its two
+    halves, and the training loop runs."""
+    prob = problems.wave(tdb, 'float32', n=999, mode='autograd')
+    net = problems.make_net(prob.net_layers, torch.float32, prob.init).to('cuda:0')
+    model = tdb.Model(net, prob.domain, prob.equation, prob.conditions)
+    model.compile(prob.mode, **prob.compile_kwargs)
+    sol = model.solution_cls
+    full = sol._plan.loss_grad().double()
+    parts = []
+    for r in range(2):
+        m = tdb.Model(net, prob.domain, prob.equation, prob.conditions)
+        m.compile(prob.mode, **prob.compile_kwargs, shard=(r, 2))
+        parts.append(m.solution_cls._plan.loss_grad().double())
+    tot = parts[0] + parts[1]
+    assert float(tot[0]) == pytest.approx(float(full[0]), rel=1e-5)
+    k = 2 + sol._n_slots
+    gn = float(full[k:].norm())
+    assert float((tot[k:] - full[k:]).norm()) <= 1e-4 * gn
+
+
+def test_training_reduces_loss(cuda_default):
+    g = load_golden('burgers_NN_small', 'float64')
+    prob = problems.ZOO['burgers_NN_small'](tdb, 'float32')
+    net = problems.make_net(prob.net_layers, torch.float32, prob.init).to('cuda:0')
+    model = tdb.Model(net, prob.domain, prob.equation, prob.conditions)
+    model.compile(prob.mode, **prob.compile_kwargs)
+    l0 = float(model.solution_cls.evaluate()[0])
+    model.train(tdb.Optimizer('Adam', {'lr': 1e-3}), 60)
+    l1 = float(model.solution_cls.evaluate()[0])
+    assert l1 < 0.7 * l0
+
+
+def test_c_abi_errors(cuda_default):
+    from torch_de_solver_b200 import _native
+    lib = _native.load()
+    net = _native.NetDesc()
+    net.n_layers = 1
+    h = C.c_void_p()
+    rc = lib.tdb200_plan_create(C.byref(net), 0, None, 0, None, 0, None, 0, None, 1, 0, C.byref(h))
+    assert rc < 0 and lib.tdb200_last_error()
+
+
+def test_cpu_device_raises():
+    prob = problems.ZOO['burgers_NN_small'](tdb, 'float32')
+    net = problems.make_net(prob.net_layers)
+    model = tdb.Model(net, prob.domain, prob.equation, prob.conditions)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        model.compile(prob.mode, **prob.compile_kwargs)

@@ -1,0 +1,81 @@
+"""Host logic: the IR produced by plan.lower_problem, executed in fp64 on the CPU (tests/ir_interp.py), must
+reproduce the reference's loss / gradient.  autograd-mode problems agree to rounding; NN-mode problems
+agree to the O(h^2) truncation of the central differences the jets replace (boundary stencils are literal)."""
+import numpy as np
+import pytest
+import torch
+
+import problems
+from helpers import build, load_golden
+from ir_interp import evaluate_ir
+from torch_de_solver_b200.input_preprocessing import Operator_bcond_preproc
+from torch_de_solver_b200.plan import lower_problem, flatten, points_per_tile
+from torch_de_solver_b200.solution import deepcopy_equation
+
+NET_CASES = sorted(k for k in problems.ZOO if 'mat' not in k)
+
+
+def lower(name, dtype='float64', nn_interior='jet', shard=(0, 1), weights=None):
+    g = load_golden(name, dtype)
+    prob, grid, bconds, model = build(name, dtype, g['weights'] if weights is None else weights)
+    kw = prob.compile_kwargs
+    eq = Operator_bcond_preproc(grid, prob.equation.equation_lst, bconds, h=kw.get('h', 0.001)).set_strategy(prob.mode)
+    eq = deepcopy_equation(eq)
+    ir = lower_problem(prob.mode, grid, eq.operator_prepare(), eq.bnd_prepare(), model, kw['lambda_operator'],
+                       kw['lambda_bound'], h=kw.get('h', 0.001), nn_interior=nn_interior, shard=shard)
+    return g, prob, model, ir
+
+
+@pytest.mark.parametrize('name', NET_CASES)
+def test_ir_matches_reference(name):
+    g, prob, model, ir = lower(name)
+    loss, loss_n, mse, _ = evaluate_ir(ir, model)
+    params = list(model.parameters())
+    grads = torch.autograd.grad(loss, params)
+    grad = torch.cat([x.reshape(-1) for x in grads]).numpy()
+    exact = prob.mode == 'autograd'
+    rel = 1e-10 if exact else 2e-4          # NN: central-difference truncation (h^2 u''' / 6 ...), see DESIGN.md
+    assert float(loss) == pytest.approx(float(g['loss']), rel=rel)
+    assert float(loss_n) == pytest.approx(float(g['loss_normalized']), rel=rel)
+    n_eq = ir.n_eq
+    np.testing.assert_allclose([float(m) for m in mse[:n_eq]], g['op_mse'], rtol=1e-9 if exact else 2e-3)
+    # boundary columns: the reference's mean is over the padded length = max over types
+    np.testing.assert_allclose([float(m) for m in mse[n_eq:]], g['bval_mse'], rtol=1e-9 if exact else 1e-9)
+    gn = np.linalg.norm(g['grad'])
+    assert np.linalg.norm(grad - g['grad']) <= (1e-9 if exact else 5e-4) * gn
+    assert ir.bnd_types == [str(k) for k in g['bval_keys']]
+    assert ir.type_len == [int(x) for x in g['bval_length']]
+
+
+@pytest.mark.parametrize('name', [k for k in NET_CASES if '_NN' in k and 'mix' not in k])
+def test_literal_fd_interior_matches_reference_fp64(name):
+    """nn_interior='literal' restates NN mode as shifted evaluations: agrees with the fp64 reference to rounding."""
+    g, prob, model, ir = lower(name, nn_interior='literal')
+    loss, loss_n, mse, _ = evaluate_ir(ir, model)
+    assert float(loss) == pytest.approx(float(g['loss']), rel=1e-9)
+    np.testing.assert_allclose([float(m) for m in mse[:ir.n_eq]], g['op_mse'], rtol=1e-7)
+
+
+def test_sharded_ir_sums_to_full():
+    name = 'nonlinear_mix_autograd'
+    g, prob, model, ir = lower(name)
+    full, _, _, _ = evaluate_ir(ir, model)
+    parts = []
+    for r in range(3):
+        _, _, _, ir_r = lower(name, shard=(r, 3))
+        parts.append(float(evaluate_ir(ir_r, model)[0]))
+    assert sum(parts) == pytest.approx(float(full), rel=1e-12)
+
+
+def test_flatten_layout():
+    g, prob, model, ir = lower('navier_stokes_autograd')
+    flat = flatten(ir, torch.device('cpu'))
+    assert len(flat.seg) == len(ir.segments)
+    seg0 = flat.seg[0]
+    assert seg0['identity'] == 1 and seg0['K'] == 1 and seg0['n_cols'] == 3
+    assert list(seg0['dir_axis'][:3]) == [0, 1, 2] and list(seg0['dir_order'][:3]) == [2, 2, 1]
+    assert flat.points.shape[0] == sum(s.points.shape[0] for s in ir.segments)
+    assert int(seg0['n_groups']) == 729
+    # forcing term is a per-row buffer
+    assert (flat.terms['kind'] == 1).sum() == 1
+    assert points_per_tile(6, 1) == 20 and points_per_tile(4, 1) == 32 and points_per_tile(1, 3) == 120

@@ -1,0 +1,55 @@
+"""Builds libtedeous_b200.so in-tree with nvcc for sm_100a (no torch headers: the library is a plain C ABI)."""
+import glob
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+LIB_DIR = os.path.join(PKG, 'lib')
+LIB = os.path.join(LIB_DIR, 'libtedeous_b200.so')
+NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
+              '-Xcompiler', '-fPIC', '--use_fast_math=false', '-Xptxas', '-v']
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(PKG, 'csrc', '*.cu')))
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = sources() + glob.glob(os.path.join(PKG, 'csrc', '*.cuh')) + glob.glob(os.path.join(ROOT, 'include', '*.h'))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    os.makedirs(LIB_DIR, exist_ok=True)
+    objs = []
+    for src in sources():
+        obj = os.path.join(LIB_DIR, os.path.basename(src)[:-3] + '.o')
+        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != '--use_fast_math=false'] + \
+              ['-I', os.path.join(ROOT, 'include'), '-I', os.path.join(PKG, 'csrc'), '-c', src, '-o', obj]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError(f'nvcc failed for {src}')
+        with open(obj + '.ptxas.log', 'w') as f:
+            f.write(res.stderr)
+        objs.append(obj)
+    cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-cudart', 'static']
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError('link failed')
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose=True))

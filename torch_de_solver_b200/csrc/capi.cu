@@ -1,0 +1,294 @@
+// C ABI of libtedeous_b200.so - plan management and launch sequencing for the NN / autograd path.
+// See include/tdb200.h for the contract and the reference interfaces every entry replaces.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return TDB200_ERR_CUDA;
+}
+#define CU(call)                                         \
+  do {                                                   \
+    cudaError_t e__ = (call);                            \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+template <class T>
+int upload(T** dst, const T* src, size_t n) {
+  *dst = nullptr;
+  if (n == 0) n = 1;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(dst), n * sizeof(T));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+  if (src) {
+    e = cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+  }
+  return 0;
+}
+}  // namespace
+
+struct tdb200_plan {
+  tdb200_net net{};
+  int device = 0;
+  int n_sms = 0;
+  int n_slots = 0;
+  int impl = 0;
+  std::vector<tdb200_segment> segs;
+  std::vector<int> seg_tile_begin;
+  int n_tiles = 0;
+  int64_t n_fields = 0;
+  // device copies of the program
+  tdb200_segment* d_segs = nullptr;
+  int* d_seg_tile_begin = nullptr;
+  tdb200_term* d_terms = nullptr;
+  tdb200_factor* d_factors = nullptr;
+  float* d_comb = nullptr;
+  float* d_slot_scale = nullptr;
+  double* d_slot_lambda = nullptr;
+  double* d_slot_len = nullptr;
+  // caller-owned buffers
+  const float* pts = nullptr;
+  const float* targets = nullptr;
+  const float* coeffs = nullptr;
+  int64_t n_pts = 0;
+  // workspace
+  float* arena = nullptr;
+  float* arena_t = nullptr;
+  float* part_grad = nullptr;
+  double* part_loss = nullptr;
+  float* scratch = nullptr;
+  int grid = 0;
+  tdb::JetArgs args{};
+};
+
+static int points_per_tile(int J, int K) {
+  int step = K;
+  if (step % 4) step = (step % 2) ? step * 4 : step * 2;
+  return ((tdb::kRows / J) / step) * step;
+}
+
+extern "C" {
+
+const char* tdb200_last_error(void) { return g_err.c_str(); }
+int tdb200_version(void) { return 100; }
+
+int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_segment* segments,
+                       int32_t n_terms, const tdb200_term* terms, int32_t n_factors,
+                       const tdb200_factor* factors, int32_t n_comb, const float* comb, int32_t n_slots,
+                       int32_t device, tdb200_plan** out) {
+  if (!net || !segments || !out || n_segments <= 0) return fail(TDB200_ERR_INVALID, "null argument");
+  if (net->n_layers < 2 || net->n_layers > TDB200_MAX_LAYERS) return fail(TDB200_ERR_INVALID, "n_layers out of range");
+  if (n_slots <= 0 || n_slots > 32) return fail(TDB200_ERR_INVALID, "n_slots must be 1..32");
+  if (net->n_cparams < 0 || net->n_cparams > tdb::kMaxCParams) return fail(TDB200_ERR_INVALID, "too many coefficient parameters");
+  const int L = net->n_layers;
+  if (net->widths[0] < 1 || net->widths[0] > 4) return fail(TDB200_ERR_INVALID, "input dimension must be 1..4");
+  if (net->widths[L] < 1 || net->widths[L] > tdb::kMaxOut) return fail(TDB200_ERR_INVALID, "output dimension must be 1..8");
+  int wmax = 0;
+  for (int l = 1; l < L; ++l) {
+    if (net->widths[l] < 1 || net->widths[l] > tdb::kMaxW) return fail(TDB200_ERR_INVALID, "hidden width must be 1..128");
+    wmax = net->widths[l] > wmax ? net->widths[l] : wmax;
+  }
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) return fail(TDB200_ERR_NO_DEVICE, "no CUDA device");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(TDB200_ERR_NO_DEVICE, "tedeous-b200 kernels are built for sm_100a only");
+
+  auto* p = new tdb200_plan();
+  p->net = *net;
+  p->device = device;
+  p->n_sms = prop.multiProcessorCount;
+  p->n_slots = n_slots;
+  p->segs.assign(segments, segments + n_segments);
+  p->seg_tile_begin.resize(n_segments + 1);
+  int tiles = 0;
+  for (int s = 0; s < n_segments; ++s) {
+    const tdb200_segment& sg = segments[s];
+    int J = 1;
+    if (sg.n_dirs < 0 || sg.n_dirs > TDB200_MAX_DIRS) { delete p; return fail(TDB200_ERR_INVALID, "n_dirs out of range"); }
+    for (int i = 0; i < sg.n_dirs; ++i) {
+      if (sg.dir_order[i] < 1 || sg.dir_order[i] > 4 || sg.dir_axis[i] < 0 || sg.dir_axis[i] >= net->widths[0]) {
+        delete p; return fail(TDB200_ERR_INVALID, "bad jet direction");
+      }
+      J += sg.dir_order[i];
+    }
+    if (J > TDB200_MAX_J || sg.K < 1 || sg.K > TDB200_MAX_K || sg.M < 1 || sg.M > TDB200_MAX_M ||
+        sg.n_cols < 1 || sg.n_cols > TDB200_MAX_COLS || sg.M > J * sg.K) {
+      delete p; return fail(TDB200_ERR_INVALID, "segment shape out of range");
+    }
+    if (sg.identity && (sg.K != 1 || sg.M != J)) { delete p; return fail(TDB200_ERR_INVALID, "identity segment needs K == 1, M == J"); }
+    const int P = points_per_tile(J, sg.K);
+    if (P <= 0) { delete p; return fail(TDB200_ERR_INVALID, "group does not fit a tile"); }
+    const int G = P / sg.K;
+    p->seg_tile_begin[s] = tiles;
+    tiles += (int)((sg.n_groups + G - 1) / G);
+    p->n_fields += sg.n_groups * sg.n_cols;
+    for (int c = 0; c < sg.n_cols; ++c)
+      if (sg.col_slot[c] < 0 || sg.col_slot[c] >= n_slots) { delete p; return fail(TDB200_ERR_INVALID, "slot out of range"); }
+  }
+  p->seg_tile_begin[n_segments] = tiles;
+  p->n_tiles = tiles;
+
+  int rc;
+  if ((rc = upload(&p->d_segs, segments, n_segments))) { tdb200_plan_destroy(p); return rc; }
+  if ((rc = upload(&p->d_seg_tile_begin, p->seg_tile_begin.data(), p->seg_tile_begin.size()))) { tdb200_plan_destroy(p); return rc; }
+  if ((rc = upload(&p->d_terms, terms, n_terms))) { tdb200_plan_destroy(p); return rc; }
+  if ((rc = upload(&p->d_factors, factors, n_factors))) { tdb200_plan_destroy(p); return rc; }
+  if ((rc = upload(&p->d_comb, comb, n_comb))) { tdb200_plan_destroy(p); return rc; }
+  if ((rc = upload<float>(&p->d_slot_scale, nullptr, n_slots))) { tdb200_plan_destroy(p); return rc; }
+  if ((rc = upload<double>(&p->d_slot_lambda, nullptr, n_slots))) { tdb200_plan_destroy(p); return rc; }
+  if ((rc = upload<double>(&p->d_slot_len, nullptr, n_slots))) { tdb200_plan_destroy(p); return rc; }
+
+  tdb::JetArgs& a = p->args;
+  a.n_layers = L;
+  int off = 0;
+  for (int l = 0; l <= L; ++l) a.widths[l] = net->widths[l];
+  for (int l = 0; l < L; ++l) {
+    a.w_off[l] = off; off += net->widths[l] * net->widths[l + 1];
+    a.b_off[l] = off; off += net->widths[l + 1];
+  }
+  a.n_net_params = off;
+  a.n_cparams = net->n_cparams;
+  a.n_params = off + net->n_cparams;
+  a.n_params_pad = (a.n_params + 31) / 32 * 32;
+  a.wmax = wmax;
+  a.n_segs = n_segments;
+  a.n_tiles = tiles;
+  a.n_slots = n_slots;
+  a.d = net->widths[0];
+  a.scratch_per_cta = (long long)2 * (L - 1) * wmax * tdb::kRows;
+
+  p->grid = tiles < p->n_sms ? (tiles > 0 ? tiles : 1) : p->n_sms;
+  if ((rc = upload<float>(&p->arena, nullptr, a.n_params_pad))) { tdb200_plan_destroy(p); return rc; }
+  if ((rc = upload<float>(&p->arena_t, nullptr, a.n_params_pad))) { tdb200_plan_destroy(p); return rc; }
+  if ((rc = upload<float>(&p->part_grad, nullptr, (size_t)p->grid * a.n_params_pad))) { tdb200_plan_destroy(p); return rc; }
+  if ((rc = upload<double>(&p->part_loss, nullptr, (size_t)p->grid * n_slots))) { tdb200_plan_destroy(p); return rc; }
+  if ((rc = upload<float>(&p->scratch, nullptr, (size_t)p->grid * a.scratch_per_cta))) { tdb200_plan_destroy(p); return rc; }
+  a.arena = p->arena;
+  a.arena_t = p->arena_t;
+  a.segs = p->d_segs;
+  a.seg_tile_begin = p->d_seg_tile_begin;
+  a.terms = p->d_terms;
+  a.factors = p->d_factors;
+  a.comb = p->d_comb;
+  a.slot_scale = p->d_slot_scale;
+  a.part_grad = p->part_grad;
+  a.part_loss = p->part_loss;
+  a.scratch = p->scratch;
+  *out = p;
+  return TDB200_OK;
+}
+
+int tdb200_plan_set_points(tdb200_plan* p, const float* pts_dev, int64_t n_pts, const float* targets_dev,
+                           int64_t n_targets, const float* coeffs_dev, int64_t n_coeffs) {
+  if (!p || !pts_dev) return fail(TDB200_ERR_INVALID, "null argument");
+  int64_t need = 0;
+  for (const auto& sg : p->segs) {
+    const int64_t end = sg.pts_off + sg.n_groups * sg.K;
+    need = end > need ? end : need;
+    if (sg.tgt_off >= 0 && (!targets_dev || sg.tgt_off + sg.n_groups * sg.n_cols > n_targets))
+      return fail(TDB200_ERR_INVALID, "targets buffer too small");
+  }
+  if (need > n_pts) return fail(TDB200_ERR_INVALID, "points buffer too small");
+  (void)n_coeffs;
+  p->pts = pts_dev;
+  p->targets = targets_dev;
+  p->coeffs = coeffs_dev;
+  p->n_pts = n_pts;
+  p->args.pts = pts_dev;
+  p->args.targets = targets_dev;
+  p->args.coeffs = coeffs_dev;
+  return TDB200_OK;
+}
+
+int tdb200_plan_set_slots(tdb200_plan* p, const double* slot_lambda, const double* slot_len) {
+  if (!p || !slot_lambda || !slot_len) return fail(TDB200_ERR_INVALID, "null argument");
+  std::vector<float> scale(p->n_slots);
+  for (int s = 0; s < p->n_slots; ++s) {
+    if (!(slot_len[s] > 0)) return fail(TDB200_ERR_INVALID, "slot_len must be positive");
+    scale[s] = (float)(slot_lambda[s] / slot_len[s]);
+  }
+  CU(cudaSetDevice(p->device));
+  CU(cudaMemcpy(p->d_slot_scale, scale.data(), p->n_slots * sizeof(float), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(p->d_slot_lambda, slot_lambda, p->n_slots * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(p->d_slot_len, slot_len, p->n_slots * sizeof(double), cudaMemcpyHostToDevice));
+  return TDB200_OK;
+}
+
+int tdb200_plan_set_impl(tdb200_plan* p, int32_t impl) {
+  if (!p) return fail(TDB200_ERR_INVALID, "null plan");
+  if (impl < 0 || impl > 1) return fail(TDB200_ERR_INVALID, "implementation not available in this build");
+  p->impl = impl;
+  return TDB200_OK;
+}
+
+int64_t tdb200_plan_out_size(const tdb200_plan* p) { return p ? 2 + p->n_slots + p->args.n_params : 0; }
+int64_t tdb200_plan_n_params(const tdb200_plan* p) { return p ? p->args.n_params : 0; }
+int64_t tdb200_plan_n_fields(const tdb200_plan* p) { return p ? p->n_fields : 0; }
+int32_t tdb200_plan_launches_per_call(const tdb200_plan* p) { return p ? 3 : 0; }
+
+static int run(tdb200_plan* p, const float* const* params, float* fields, float* out, int do_grad, void* stream) {
+  if (!p || !params) return fail(TDB200_ERR_INVALID, "null argument");
+  if (!p->pts) return fail(TDB200_ERR_INVALID, "tdb200_plan_set_points was not called");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CU(cudaSetDevice(p->device));
+  tdb::PackArgs pk{};
+  const tdb::JetArgs& a = p->args;
+  pk.n_layers = a.n_layers;
+  for (int l = 0; l <= a.n_layers; ++l) pk.widths[l] = a.widths[l];
+  for (int l = 0; l < a.n_layers; ++l) {
+    pk.w_off[l] = a.w_off[l];
+    pk.b_off[l] = a.b_off[l];
+    pk.W[l] = params[2 * l];
+    pk.b[l] = params[2 * l + 1];
+    if (!pk.W[l] || !pk.b[l]) return fail(TDB200_ERR_INVALID, "null parameter pointer");
+  }
+  pk.n_net_params = a.n_net_params;
+  pk.n_cparams = a.n_cparams;
+  for (int i = 0; i < a.n_cparams; ++i) pk.c[i] = params[2 * a.n_layers + i];
+  pk.arena = p->arena;
+  pk.arena_t = p->arena_t;
+  CU(tdb::launch_pack_params(pk, s));
+  tdb::JetArgs call = a;
+  call.fields = fields;
+  call.do_grad = do_grad;
+  CU(tdb::launch_jet_simt(call, p->grid, s));
+  if (out) {
+    CU(tdb::launch_reduce_partials(p->part_grad, p->part_loss, p->grid, do_grad ? a.n_params : 0, a.n_params_pad,
+                                   p->n_slots, p->d_slot_lambda, p->d_slot_len, out, s));
+  }
+  return TDB200_OK;
+}
+
+int tdb200_loss_grad(tdb200_plan* p, const float* const* params_dev, float* out_dev, void* stream) {
+  if (!out_dev) return fail(TDB200_ERR_INVALID, "null output");
+  return run(p, params_dev, nullptr, out_dev, 1, stream);
+}
+
+int tdb200_eval_fields(tdb200_plan* p, const float* const* params_dev, float* fields_dev, float* out_dev,
+                       void* stream) {
+  if (!fields_dev) return fail(TDB200_ERR_INVALID, "null fields buffer");
+  return run(p, params_dev, fields_dev, out_dev, 0, stream);
+}
+
+void tdb200_plan_destroy(tdb200_plan* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  cudaFree(p->d_segs); cudaFree(p->d_seg_tile_begin); cudaFree(p->d_terms); cudaFree(p->d_factors);
+  cudaFree(p->d_comb); cudaFree(p->d_slot_scale); cudaFree(p->d_slot_lambda); cudaFree(p->d_slot_len);
+  cudaFree(p->arena); cudaFree(p->arena_t); cudaFree(p->part_grad); cudaFree(p->part_loss); cudaFree(p->scratch);
+  delete p;
+}
+
+}  // extern "C"

@@ -1,0 +1,73 @@
+"""Compatibility views with the reference's `Operator` / `Bounds` interface (tedeous/eval.py:90-232, 235-461).
+
+Inside `Solution` they are thin views over the fused plan: `operator_compute()` / `apply_bcs()` launch the
+forward-only kernel (`tdb200_eval_fields`) and return the per-point fields.  Constructed stand-alone with
+the reference's signatures they build a small plan of their own, so code that used the reference's seams
+directly (optimizers/closure.py:113-114, landscape_visualization/_aux/PINN_loss_data.py:21-27) keeps working.
+The returned tensors are detached: gradients come from `Solution.evaluate()` only."""
+from typing import List, Tuple
+
+import torch
+
+from .device import check_device
+
+
+def _solution_for(grid, prepared_operator, prepared_bconds, model, mode, derivative_points):
+    from .input_preprocessing import Operator_bcond_preproc
+    from .solution import Solution
+    eq = Operator_bcond_preproc(grid, prepared_operator, prepared_bconds).set_strategy(mode)
+    return Solution(grid, eq, model, mode, None, 1, 1, derivative_points=derivative_points)
+
+
+class Operator:
+    def __init__(self, grid, prepared_operator, model, mode, weak_form=None, derivative_points=2,
+                 batch_size=None):
+        if weak_form not in (None, []):
+            raise NotImplementedError('weak form is not implemented by the fused path')
+        grid = check_device(grid)
+        # a plan needs at least one condition; a single dummy Dirichlet row is never read back
+        dummy = [{'bnd': (grid[:1] if mode != 'mat' else grid.reshape(grid.shape[0], -1)[:, :1].T),
+                  'bop': None, 'bval': torch.zeros(1, device=grid.device), 'var': 0, 'type': 'dirichlet'}]
+        self._sol = _solution_for(grid, prepared_operator, dummy, model, mode, derivative_points)
+        self._init_common()
+
+    def _init_common(self):
+        self.grid = self._sol.grid
+        self.model = self._sol.model
+        self.mode = self._sol.mode
+        self.batch_size = None
+        self.n_batches = 1
+        self.current_batch_i = 0
+
+    @classmethod
+    def _from_solution(cls, sol):
+        self = cls.__new__(cls)
+        self._sol = sol
+        self._init_common()
+        return self
+
+    def _pde_compute(self) -> torch.Tensor:
+        self._sol._fields_cache = None
+        return self._sol.op
+
+    def operator_compute(self) -> torch.Tensor:
+        return self._pde_compute()
+
+
+class Bounds:
+    def __init__(self, grid, prepared_bconds, model, mode, weak_form=None, derivative_points=2):
+        grid = check_device(grid)
+        dummy_op = [{'u': {'coeff': 1., 'u': [None], 'pow': 1, 'var': 0}}]
+        self._sol = _solution_for(grid, dummy_op, prepared_bconds, model, mode, derivative_points)
+        self.grid, self.model, self.mode = self._sol.grid, self._sol.model, mode
+
+    @classmethod
+    def _from_solution(cls, sol):
+        self = cls.__new__(cls)
+        self._sol = sol
+        self.grid, self.model, self.mode = sol.grid, sol.model, sol.mode
+        return self
+
+    def apply_bcs(self) -> Tuple[torch.Tensor, torch.Tensor, List[str], List[int]]:
+        self._sol._fields_cache = None
+        return self._sol.bval, self._sol.true_bval, list(self._sol.bval_keys), list(self._sol.bval_length)

@@ -1,0 +1,335 @@
+"""`Solution` - the drop-in boundary (tedeous/solution.py:23-168).
+
+`Solution(grid, equal_cls, model, mode, weak_form, lambda_operator, lambda_bound, tol, derivative_points,
+batch_size).evaluate()` returns `(loss [1], loss_normalized [1])` exactly like the reference, but one call
+enqueues the fused CUDA plan (libtedeous_b200.so) instead of walking the operator dicts through ATen:
+
+* loss and the full parameter gradient are produced by the same launch sequence; `loss.backward()` (or
+  `torch.autograd.grad(loss, params)`) just hands the already-computed gradient to autograd through a
+  custom `torch.autograd.Function`, so `Closure._closure` (optimizers/closure.py:49-64) works unchanged;
+* `op`, `bval`, `true_bval`, `bval_keys`, `bval_length` (read by callbacks, adaptive_lambda.py:91-105) are
+  materialised lazily by a forward-only launch (`tdb200_eval_fields`);
+* there is no CPU path: a CPU default device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from copy import deepcopy
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _native
+from .device import check_device, device_type
+from .input_preprocessing import lambda_prepare
+from .plan import (ProblemIR, UnsupportedProblem, flatten, lower_problem)
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f'{what} lives on {t.device}: the tedeous-b200 hot path runs on CUDA (sm_100a) only '
+                           "and has no CPU fallback - call solver_device('cuda') first")
+
+
+class FusedPlan:
+    """Owns one tdb200_plan (modes 'NN' / 'autograd') and the device buffers bound to it."""
+
+    def __init__(self, ir: ProblemIR, device: torch.device, impl: int = 0):
+        self.ir = ir
+        self.device = device
+        self.lib = _native.load()
+        self.flat = flatten(ir, device)
+        f = self.flat
+        net = _native.NetDesc()
+        net.n_layers = ir.net.n_layers
+        for i, w in enumerate(ir.net.widths):
+            net.widths[i] = w
+        net.n_cparams = len(ir.net.coeff_params)
+        handle = C.c_void_p()
+        dev_index = device.index if device.index is not None else torch.cuda.current_device()
+        _native.check(self.lib.tdb200_plan_create(
+            C.byref(net), len(f.seg), _native.np_ptr(f.seg), len(f.terms), _native.np_ptr(f.terms),
+            len(f.factors), _native.np_ptr(f.factors), len(f.comb), _native.np_ptr(f.comb), ir.n_slots,
+            dev_index, C.byref(handle)), 'tdb200_plan_create')
+        self.handle = handle
+        _native.check(self.lib.tdb200_plan_set_points(
+            handle, f.points.data_ptr(), f.points.shape[0], f.targets.data_ptr(), f.targets.numel(),
+            f.coeffs.data_ptr(), f.coeffs.numel()), 'tdb200_plan_set_points')
+        self.set_lambdas(ir.slot_lambda)
+        if impl:
+            _native.check(self.lib.tdb200_plan_set_impl(handle, impl), 'tdb200_plan_set_impl')
+        self.out_size = int(self.lib.tdb200_plan_out_size(handle))
+        self.n_params = int(self.lib.tdb200_plan_n_params(handle))
+        self.n_fields = int(self.lib.tdb200_plan_n_fields(handle))
+        self.launches_per_call = int(self.lib.tdb200_plan_launches_per_call(handle))
+        self._ptrs = (C.c_void_p * (2 * ir.net.n_layers + len(ir.net.coeff_params)))()
+
+    @property
+    def slot_lambda(self):
+        return self.ir.slot_lambda
+
+    def set_lambdas(self, slot_lambda):
+        self.ir.slot_lambda = [float(x) for x in slot_lambda]
+        lam = np.asarray(self.ir.slot_lambda, dtype=np.float64)
+        ln = np.asarray(self.ir.slot_len, dtype=np.float64)
+        _native.check(self.lib.tdb200_plan_set_slots(self.handle, _native.np_ptr(lam), _native.np_ptr(ln)),
+                      'tdb200_plan_set_slots')
+
+    def set_impl(self, impl: int):
+        _native.check(self.lib.tdb200_plan_set_impl(self.handle, impl), 'tdb200_plan_set_impl')
+        self.launches_per_call = int(self.lib.tdb200_plan_launches_per_call(self.handle))
+
+    def _param_ptrs(self):
+        for i, p in enumerate(self.ir.net.param_tensors()):
+            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError('network parameters must be contiguous float32 CUDA tensors '
+                                   f'(got {p.dtype} on {p.device})')
+            self._ptrs[i] = p.data_ptr()
+        return self._ptrs
+
+    def loss_grad(self) -> torch.Tensor:
+        """-> flat [2 + n_slots + n_params] tensor (loss, loss_normalized, slot MSEs, gradient)."""
+        out = torch.empty(self.out_size, dtype=torch.float32, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _native.check(self.lib.tdb200_loss_grad(self.handle, self._param_ptrs(), out.data_ptr(), stream),
+                      'tdb200_loss_grad')
+        return out
+
+    def eval_fields(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        fields = torch.empty(max(self.n_fields, 1), dtype=torch.float32, device=self.device)
+        out = torch.empty(self.out_size, dtype=torch.float32, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _native.check(self.lib.tdb200_eval_fields(self.handle, self._param_ptrs(), fields.data_ptr(),
+                                                  out.data_ptr(), stream), 'tdb200_eval_fields')
+        return fields, out
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                self.lib.tdb200_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class _FusedLoss(torch.autograd.Function):
+    """loss = plan(params); backward returns the gradient the same launch already produced."""
+
+    @staticmethod
+    def forward(ctx, sol, *params):
+        out = sol._run_plan()
+        ctx.sol = sol
+        ctx.flat_grad = out[2 + sol._n_slots:]
+        ctx.shapes = [p.shape for p in params]
+        sol._last_out = out
+        return out[0:1].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        flat = ctx.flat_grad * g
+        grads, off = [], 0
+        for shp in ctx.shapes:
+            n = int(np.prod(shp)) if len(shp) else 1
+            grads.append(flat[off:off + n].view(shp))
+            off += n
+        return (None, *grads)
+
+
+class Solution:
+    """Same constructor and public attributes as tedeous.solution.Solution."""
+
+    def __init__(self, grid: torch.Tensor, equal_cls, model, mode: str, weak_form, lambda_operator,
+                 lambda_bound, tol: float = 0, derivative_points: int = 2, batch_size: int = None,
+                 shard: Optional[Tuple[int, int]] = None, process_group=None, nn_interior: str = 'jet',
+                 impl: int = 0):
+        if weak_form not in (None, []):
+            raise UnsupportedProblem('weak-form loss is not implemented by the fused path (SURVEY 8 a11)')
+        if tol != 0:
+            raise UnsupportedProblem('causal loss (tol != 0) is not implemented by the fused path yet (SURVEY 8 a10)')
+        if batch_size is not None and mode != 'NN':
+            raise UnsupportedProblem('mini-batching is not implemented by the fused path; shard points over '
+                                     'GPUs instead')
+        self.grid = check_device(grid)
+        _require_cuda(self.grid, 'grid')
+        self.mode = mode
+        self.weak_form = weak_form
+        self.lambda_operator = lambda_operator
+        self.lambda_bound = lambda_bound
+        self.tol = tol
+        self.derivative_points = derivative_points
+        self.batch_size = None
+        self.equal_cls = equal_cls
+        self._shard = shard or (0, 1)
+        self._pg = process_group
+        self._nn_interior = nn_interior
+        self._impl = impl
+        equal_copy = deepcopy_equation(equal_cls)
+        self._prepared_operator = equal_copy.operator_prepare()
+        self.prepared_bconds = equal_copy.bnd_prepare()
+        self._h = getattr(equal_cls, 'h', 0.001)
+        self._inner_order = getattr(equal_cls, 'inner_order', '1')
+        self._boundary_order = getattr(equal_cls, 'boundary_order', '2')
+        self._fields_cache = None
+        self._last_out = None
+        self.loss = None
+        self.loss_normalized = None
+        self._build(model)
+        from .eval import Operator, Bounds          # thin views over this object (compat shims)
+        self.operator = Operator._from_solution(self)
+        self.boundary = Bounds._from_solution(self)
+
+    # -- plan construction -------------------------------------------------------------------------
+    def _build(self, model):
+        if self.mode == 'mat':
+            from .mat import MatPlan
+            self.model = check_device(model)
+            _require_cuda(self.model, 'mat-mode model tensor')
+            self._plan = MatPlan(self.grid, self._prepared_operator, self.prepared_bconds, self.model,
+                                 self.lambda_operator, self.lambda_bound, self.derivative_points,
+                                 shard=self._shard, process_group=self._pg)
+            self._n_slots = self._plan.n_slots
+            self.bval_keys = list(self._plan.bnd_types)
+            self.bval_length = list(self._plan.type_len)
+            return
+        self.model = model.to(self.grid.device)
+        for p in self.model.parameters():
+            _require_cuda(p, 'model parameter')
+        ir = lower_problem(self.mode, self.grid, self._prepared_operator, self.prepared_bconds, self.model,
+                           self.lambda_operator, self.lambda_bound, h=self._h, inner_order=self._inner_order,
+                           boundary_order=self._boundary_order, nn_interior=self._nn_interior,
+                           shard=self._shard)
+        self._ir = ir
+        self._plan = FusedPlan(ir, self.grid.device, impl=self._impl)
+        self._n_slots = ir.n_slots
+        self.bval_keys = list(ir.bnd_types)
+        self.bval_length = list(ir.type_len)
+
+    def _model_change(self, new_model) -> None:
+        """Swap the model (Cache callback, tedeous/solution.py:109-127): rebuilds the plan's parameter view."""
+        self._build(new_model)
+        self._fields_cache = None
+
+    # -- evaluation --------------------------------------------------------------------------------
+    def _run_plan(self) -> torch.Tensor:
+        out = self._plan.loss_grad()
+        if self._shard[1] > 1:
+            import torch.distributed as dist
+            dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self._pg)
+        return out
+
+    def _sync_lambdas(self):
+        n_eq = self._n_slots - len(self.bval_keys)
+        lam_op = lambda_prepare(torch.empty(1, n_eq), self.lambda_operator).reshape(-1).tolist()
+        lam_b = lambda_prepare(torch.empty(1, len(self.bval_keys)), self.lambda_bound).reshape(-1).tolist()
+        lam = [float(x) for x in lam_op + lam_b]
+        if len(lam) != self._n_slots:
+            raise ValueError(f'expected {self._n_slots} lambdas, got {len(lam)}')
+        if lam != list(self._plan.slot_lambda):
+            self._plan.set_lambdas(lam)
+
+    def evaluate(self, save_graph: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+        """One loss evaluation (tedeous/solution.py:129-168)."""
+        self._sync_lambdas()
+        self._fields_cache = None
+        if self.mode == 'mat':
+            params = [self.model]
+        else:
+            params = self._plan.ir.net.param_tensors()
+        needs_grad = save_graph and torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        if needs_grad:
+            loss = _FusedLoss.apply(self, *params)
+        else:
+            self._last_out = self._run_plan()
+            loss = self._last_out[0:1].clone()
+        self.loss = loss
+        self.loss_normalized = self._last_out[1:2].clone()
+        n_eq = self._n_slots - len(self.bval_keys)
+        dt = torch.float32
+        self.lambda_operator = lambda_prepare(torch.empty(1, n_eq), self.lambda_operator).to(dt)
+        self.lambda_bound = lambda_prepare(torch.empty(1, len(self.bval_keys)), self.lambda_bound).to(dt)
+        return self.loss, self.loss_normalized
+
+    # per-column mean squares of the last evaluation (the natural partial results)
+    @property
+    def op_mse(self) -> torch.Tensor:
+        n_eq = self._n_slots - len(self.bval_keys)
+        return self._last_out[2:2 + n_eq]
+
+    @property
+    def bval_mse(self) -> torch.Tensor:
+        n_eq = self._n_slots - len(self.bval_keys)
+        return self._last_out[2 + n_eq:2 + self._n_slots]
+
+    @property
+    def flat_grad(self) -> torch.Tensor:
+        return self._last_out[2 + self._n_slots:]
+
+    # -- per-point fields on demand ----------------------------------------------------------------
+    def _fields(self):
+        if self._fields_cache is None:
+            if self._shard[1] > 1:
+                raise UnsupportedProblem('per-point fields are not gathered across ranks')
+            if self.mode == 'mat':
+                self._fields_cache = self._plan.eval_fields(self.model)
+            else:
+                self._fields_cache = _assemble_fields(self._plan)
+        return self._fields_cache
+
+    @property
+    def op(self) -> torch.Tensor:
+        return self._fields()[0]
+
+    @property
+    def bval(self) -> torch.Tensor:
+        return self._fields()[1]
+
+    @property
+    def true_bval(self) -> torch.Tensor:
+        return self._fields()[2]
+
+
+def _assemble_fields(plan: FusedPlan):
+    """op [N, n_eq], bval / true_bval [max_len, n_types] zero padded (eval.py:55-87)."""
+    ir = plan.ir
+    fields, _ = plan.eval_fields()
+    seg_rec = plan.flat.seg
+    n_types = len(ir.bnd_types)
+    max_len = max(ir.type_len)
+    bval = torch.zeros(max_len, n_types, dtype=torch.float32, device=plan.device)
+    tval = torch.zeros_like(bval)
+    op = None
+    for s, rec in zip(ir.segments, seg_rec):
+        off, n, nc = int(rec['field_off']), s.n_groups, len(s.cols)
+        vals = fields[off:off + n * nc].reshape(n, nc)
+        if s.slots[0] < ir.n_eq:
+            op = vals
+        else:
+            col = s.slots[0] - ir.n_eq
+            idx = s.row_index.to(plan.device)
+            bval[idx, col] = vals[:, 0]
+            tval[idx, col] = s.targets.reshape(-1).to(device=plan.device, dtype=torch.float32)
+    return op, bval, tval
+
+
+def deepcopy_equation(equal_cls):
+    """deepcopy that keeps tensors / nn.Parameters / callables by reference (tedeous/solution.py:62, 90-107:
+    trainable coefficients must stay the live Parameter objects)."""
+    memo = {}
+
+    def keep(obj):
+        memo[id(obj)] = obj
+
+    def walk(o):
+        if isinstance(o, torch.Tensor) or callable(o) and not isinstance(o, type):
+            keep(o)
+        elif isinstance(o, dict):
+            for v in o.values():
+                walk(v)
+        elif isinstance(o, (list, tuple)):
+            for v in o:
+                walk(v)
+    walk(getattr(equal_cls, 'operator', None))
+    walk(getattr(equal_cls, 'bconds', None))
+    keep(equal_cls.grid)
+    return deepcopy(equal_cls, memo)
