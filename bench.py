@@ -48,7 +48,10 @@ WORKLOADS = {
                              desc='KdV periodic autograd, 1000x1000 pts/GPU'),
     'ns_autograd_1e6': dict(fn='navier_stokes', kw=dict(n=99, layers=(3, 100, 100, 100, 100, 100, 100, 3)), J=6,
                             desc='Navier-Stokes 2D+t autograd, 100^3 pts/GPU, MLP 3-100x6-3'),
+    'poisson_mat_4096': dict(fn='poisson_mat', kw=dict(n=4095, derivative_points=2), J=0, mat=True,
+                             desc="Poisson 2D mode 'mat', 4096x4096 grid, u_xx + u_yy - f, Dirichlet edges"),
 }
+MAT_BYTES_PER_CELL = 12      # read u, read the forcing tensor, write d loss / d u (fp32) - SURVEY 8d
 
 
 def flop_per_point(layers, J):
@@ -167,6 +170,8 @@ def run_b200(args):
         dist.init_process_group('nccl', device_id=dev)
     torch.set_default_device(dev)
 
+    if WORKLOADS[args.workload].get('mat'):
+        return run_b200_mat(args, dev, tdb, problems)
     spec, prob = make_problem(args.workload, tdb, world)
     net = problems.make_net(prob.net_layers, torch.float32, prob.init).to(dev)
     model = tdb.Model(net, prob.domain, prob.equation, prob.conditions)
@@ -220,7 +225,7 @@ def run_b200(args):
     flat = plan.flat
     host_in = [t.detach().cpu().pin_memory() for t in (flat.points, flat.targets, flat.coeffs)]
     dev_in = [flat.points, flat.targets, flat.coeffs]
-    host_out = torch.empty(plan.out_size, dtype=torch.float32).pin_memory()
+    host_out = torch.empty(plan.out_size, dtype=torch.float32, device='cpu').pin_memory()
     h2d = sum(t.numel() * 4 for t in host_in)
     d2h = host_out.numel() * 4
 
@@ -284,6 +289,77 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_b200_mat(args, dev, tdb, problems):
+    """mat-mode workload (1 GPU): HBM-bound stencil kernel."""
+    spec = WORKLOADS[args.workload]
+    prob = getattr(problems, spec['fn'])(tdb, 'float32', **spec['kw'])
+    u = problems.make_mat_model(prob.mat_shape, torch.float32).to(dev).contiguous()
+    model = tdb.Model(u, prob.domain, prob.equation, prob.conditions)
+    model.compile('mat', **prob.compile_kwargs)
+    sol = model.solution_cls
+    plan = sol._plan
+    n_cells = plan.n_cells
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def timed(fn, steps):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for e0, e1 in ev:
+            flush.zero_()
+            e0.record(); fn(); e1.record()
+        torch.cuda.synchronize(dev)
+        return [e0.elapsed_time(e1) for e0, e1 in ev]
+
+    step = lambda: plan.loss_grad_raw(u)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    t_wall = time.time()
+    times = timed(step, args.steps)
+    clocks = sampler.stop()
+    ms = statistics.mean(times)
+    # e2e: forcing tensor + boundary targets from pinned host memory every step, loss terms read back
+    host_in = [plan._coeffs.detach().cpu().pin_memory(), plan._targets.detach().cpu().pin_memory()]
+    dev_in = [plan._coeffs, plan._targets]
+    host_out = torch.empty(plan.out_size, dtype=torch.float32, device='cpu').pin_memory()
+    u.requires_grad_()
+
+    def step_e2e():
+        for h, d in zip(host_in, dev_in):
+            d.copy_(h, non_blocking=True)
+        u.grad = None
+        loss, _ = sol.evaluate()
+        loss.backward()
+        host_out.copy_(sol._last_out, non_blocking=True)
+    for _ in range(3):
+        step_e2e()
+    torch.cuda.synchronize(dev)
+    e2e_steps = max(3, min(args.steps, 20))
+    e2e_ms = statistics.mean(timed(step_e2e, e2e_steps))
+    peaks, peak_src = load_peaks()
+    achieved = n_cells * MAT_BYTES_PER_CELL / (ms * 1e-3) / 1e9
+    torch.set_default_device('cpu')
+    cpu = cpu_baseline(args.workload) if not args.no_cpu_baseline else None
+    line = {
+        'metric': METRIC, 'value': n_cells / (ms * 1e-3), 'unit': UNIT, 'n_gpus': 1, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': args.workload, 'description': spec['desc'], 'cells': n_cells, 'mode': 'mat',
+                   'l2': 'flushed between timed steps (256 MB write)', 'parallelism': 'single GPU'},
+        'e2e': {'value': n_cells / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': sum(t.numel() * 4 for t in host_in),
+                'd2h_bytes_per_step': host_out.numel() * 4, 'ms_per_step': e2e_ms},
+        'gpu_launches': args.steps * plan.launches_per_call,
+        'clocks': clocks,
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                     'frac': achieved / peaks['hbm_gbs'], 'traffic': None,
+                     'bytes_per_cell': MAT_BYTES_PER_CELL, 'peak_source': f'MEASURED_PEAKS.json [{peak_src}] hbm_gbs'},
+        'cpu_baseline': cpu,
+        'wall_s': time.time() - t_wall,
+    }
+    print(json.dumps(line))
+
+
 # ----------------------------------------------------------------------------------------------------
 CPU_SAMPLE = {   # bounded CPU samples of the same operators (reference cost is flat in N, BASELINE.md 2)
     'wave_autograd_1e6': dict(fn='wave', kw=dict(n=315, mode='autograd', layers=(2, 100, 100, 100, 1))),
@@ -291,6 +367,7 @@ CPU_SAMPLE = {   # bounded CPU samples of the same operators (reference cost is 
     'burgers_autograd_1e6': dict(fn='burgers', kw=dict(n=315, mode='autograd', layers=(2, 100, 100, 100, 1))),
     'kdv_autograd_1e6': dict(fn='kdv', kw=dict(nx=199, nt=199, mode='autograd', layers=(2, 100, 100, 100, 1))),
     'ns_autograd_1e6': dict(fn='navier_stokes', kw=dict(n=20, layers=(3, 100, 100, 100, 100, 100, 100, 3))),
+    'poisson_mat_4096': dict(fn='poisson_mat', kw=dict(n=255, derivative_points=2)),
 }
 
 
@@ -304,11 +381,16 @@ def cpu_step_time(workload, steps=3, warmup=1):
     prob = getattr(problems, spec['fn'])(tdb, 'float32', **spec['kw'])
     grid = prob.domain.build(prob.mode)
     bconds = prob.conditions.build(prob.domain.variable_dict)
-    net = problems.make_net(prob.net_layers, torch.float32, prob.init)
     kw = prob.compile_kwargs
+    if prob.mode == 'mat':
+        net = problems.make_mat_model(prob.mat_shape, torch.float32)
+        params = [net.requires_grad_()]
+    else:
+        net = problems.make_net(prob.net_layers, torch.float32, prob.init)
+        params = list(net.parameters())
     sol = orc.OracleSolution(grid, prob.equation.equation_lst, bconds, net, prob.mode, kw['lambda_operator'],
-                             kw['lambda_bound'], h=kw.get('h', 0.001))
-    params = list(net.parameters())
+                             kw['lambda_bound'], h=kw.get('h', 0.001),
+                             derivative_points=kw.get('derivative_points', 2))
     ts = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()

@@ -165,6 +165,10 @@ int tdb200_mat_plan_set_bcs(tdb200_mat_plan* plan, int32_t n_bcs, const tdb200_m
  * grad_dev [n_var, n0, n1] = d loss / d u. */
 int tdb200_mat_loss_grad(tdb200_mat_plan* plan, const float* u_dev, float* grad_dev, float* out_dev,
                          void* stream);
+/* Forward only: op_dev [n0*n1, n_eq] residual fields, bval_dev [total boundary rows] row values (either may be
+ * NULL); out_dev as above. */
+int tdb200_mat_eval_fields(tdb200_mat_plan* plan, const float* u_dev, float* op_dev, float* bval_dev,
+                           float* out_dev, void* stream);
 int64_t tdb200_mat_plan_out_size(const tdb200_mat_plan* plan);
 int32_t tdb200_mat_plan_launches_per_call(const tdb200_mat_plan* plan);
 void tdb200_mat_plan_destroy(tdb200_mat_plan* plan);

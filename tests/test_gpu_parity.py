@@ -50,7 +50,8 @@ def test_loss_and_gradient_match_reference(name, cuda_default):
     assert abs(np.linalg.norm(grad) - gn) <= GRADNORM_RTOL * gn
     assert np.linalg.norm(grad - g['grad']) <= GRADVEC_RTOL * gn
     np.testing.assert_allclose(sol.op_mse.cpu().numpy(), g['op_mse'], rtol=5e-4)
-    np.testing.assert_allclose(sol.bval_mse.cpu().numpy(), g['bval_mse'], rtol=1e-4)
+    # NN-mode one-sided boundary stencils are literal fp32 differences (3u - 4u + u) / 2h: cancellation noise
+    np.testing.assert_allclose(sol.bval_mse.cpu().numpy(), g['bval_mse'], rtol=1e-3 if prob.mode == 'NN' else 1e-4)
     assert sol.bval_keys == [str(k) for k in g['bval_keys']]
     assert sol.bval_length == [int(x) for x in g['bval_length']]
 
@@ -79,6 +80,63 @@ def test_literal_fd_interior(name, cuda_default):
     prob, net, sol = fused(name, g['weights'], nn_interior='literal')
     loss, _ = sol.evaluate()
     assert float(loss) == pytest.approx(float(g['loss']), rel=2e-3)
+
+
+MAT_CASES = sorted(k for k in problems.ZOO if 'mat' in k)
+
+
+def fused_mat(name, weights):
+    prob = problems.ZOO[name](tdb, 'float32')
+    u = torch.as_tensor(weights, dtype=torch.float32).reshape(prob.mat_shape).to('cuda:0')
+    model = tdb.Model(u, prob.domain, prob.equation, prob.conditions)
+    model.compile('mat', **prob.compile_kwargs)
+    return prob, model.solution_cls
+
+
+@pytest.mark.parametrize('name', MAT_CASES)
+def test_mat_loss_and_gradient_match_reference(name, cuda_default):
+    g = load_golden(name, 'float64')
+    prob, sol = fused_mat(name, g['weights'])
+    sol.model.requires_grad_()
+    loss, loss_n = sol.evaluate()
+    loss.backward()
+    grad = sol.model.grad.reshape(-1).double().cpu().numpy()
+    assert float(loss) == pytest.approx(float(g['loss']), rel=LOSS_RTOL)
+    assert float(loss_n) == pytest.approx(float(g['loss_normalized']), rel=LOSS_RTOL)
+    gn = np.linalg.norm(g['grad'])
+    assert abs(np.linalg.norm(grad) - gn) <= GRADNORM_RTOL * gn
+    assert np.linalg.norm(grad - g['grad']) <= GRADVEC_RTOL * gn
+    np.testing.assert_allclose(sol.op_mse.cpu().numpy(), g['op_mse'], rtol=1e-4)
+    np.testing.assert_allclose(sol.bval_mse.cpu().numpy(), g['bval_mse'], rtol=1e-4)
+    assert sol.bval_keys == [str(k) for k in g['bval_keys']]
+    assert sol.bval_length == [int(x) for x in g['bval_length']]
+    op = sol.op.cpu().double().numpy()
+    scale = np.abs(g['op_head']).max()
+    np.testing.assert_allclose(op[:256], g['op_head'], atol=2e-4 * scale, rtol=1e-3)
+    bscale = np.abs(g['bval']).max()
+    np.testing.assert_allclose(sol.bval.cpu().numpy(), g['bval'], atol=2e-4 * bscale, rtol=1e-4)
+    np.testing.assert_allclose(sol.true_bval.cpu().numpy(), g['true_bval'], atol=1e-6)
+
+
+def test_mat_large_grid_properties(cuda_default):
+    """4096 x 4096 Poisson (BASELINE config 4): size-independent checks - the exact solution of the discrete
+    problem has zero loss and zero gradient; the loss is quadratic along any direction (linear operator)."""
+    n = 4095
+    prob = problems.poisson_mat(tdb, 'float32', n=n)
+    x = torch.linspace(0, 1, n + 1)
+    u = (torch.sin(np.pi * x)[:, None] * torch.sin(np.pi * x)[None, :]).reshape(1, n + 1, n + 1).contiguous()
+    model = tdb.Model(u, prob.domain, prob.equation, prob.conditions)
+    model.compile('mat', **prob.compile_kwargs)
+    plan = model.solution_cls._plan
+    torch.manual_seed(0)
+    v = torch.randn_like(u)
+    l = [float(plan.loss_grad_raw((u + t * v).contiguous())[0][0]) for t in (-1e-3, 0.0, 1e-3, 2e-3)]
+    # quadratic in t  <=>  third finite difference vanishes
+    third = l[3] - 3 * l[2] + 3 * l[1] - l[0]
+    assert abs(third) <= 2e-3 * max(abs(x) for x in l)
+    out, grad = plan.loss_grad_raw(u)
+    fd = (l[2] - l[0]) / 2e-3
+    assert fd == pytest.approx(float((grad * v).sum()), rel=5e-3, abs=1e-3 * abs(l[1]))
 
 
 def test_repeatable_and_param_update(cuda_default):

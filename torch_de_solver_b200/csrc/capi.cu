@@ -80,6 +80,7 @@ static int points_per_tile(int J, int K) {
 extern "C" {
 
 const char* tdb200_last_error(void) { return g_err.c_str(); }
+void tdb200_set_error_(const char* msg) { g_err = msg ? msg : ""; }
 int tdb200_version(void) { return 100; }
 
 int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_segment* segments,

@@ -118,16 +118,15 @@ class _FusedLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, sol, *params):
-        out = sol._run_plan()
-        ctx.sol = sol
-        ctx.flat_grad = out[2 + sol._n_slots:]
+        out, flat_grad = sol._run_plan()
+        ctx.flat_grad = flat_grad
         ctx.shapes = [p.shape for p in params]
         sol._last_out = out
         return out[0:1].clone()
 
     @staticmethod
     def backward(ctx, g):
-        flat = ctx.flat_grad * g
+        flat = ctx.flat_grad.reshape(-1) * g
         grads, off = [], 0
         for shp in ctx.shapes:
             n = int(np.prod(shp)) if len(shp) else 1
@@ -211,12 +210,15 @@ class Solution:
         self._fields_cache = None
 
     # -- evaluation --------------------------------------------------------------------------------
-    def _run_plan(self) -> torch.Tensor:
+    def _run_plan(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """-> (out [2 + n_slots (+ n_params)], flat gradient)."""
+        if self.mode == 'mat':
+            return self._plan.loss_grad_raw(self.model)
         out = self._plan.loss_grad()
         if self._shard[1] > 1:
             import torch.distributed as dist
             dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self._pg)
-        return out
+        return out, out[2 + self._n_slots:]
 
     def _sync_lambdas(self):
         n_eq = self._n_slots - len(self.bval_keys)
@@ -240,7 +242,7 @@ class Solution:
         if needs_grad:
             loss = _FusedLoss.apply(self, *params)
         else:
-            self._last_out = self._run_plan()
+            self._last_out, self._last_grad = self._run_plan()
             loss = self._last_out[0:1].clone()
         self.loss = loss
         self.loss_normalized = self._last_out[1:2].clone()
@@ -261,9 +263,6 @@ class Solution:
         n_eq = self._n_slots - len(self.bval_keys)
         return self._last_out[2 + n_eq:2 + self._n_slots]
 
-    @property
-    def flat_grad(self) -> torch.Tensor:
-        return self._last_out[2 + self._n_slots:]
 
     # -- per-point fields on demand ----------------------------------------------------------------
     def _fields(self):
