@@ -64,6 +64,8 @@ struct tdb200_plan {
   // workspace
   float* arena = nullptr;
   float* arena_t = nullptr;
+  float* img_f = nullptr;
+  float* img_b = nullptr;
   float* part_grad = nullptr;
   double* part_loss = nullptr;
   float* scratch = nullptr;
@@ -173,6 +175,15 @@ int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_s
   p->grid = tiles < p->n_sms ? (tiles > 0 ? tiles : 1) : p->n_sms;
   if ((rc = upload<float>(&p->arena, nullptr, a.n_params_pad))) { tdb200_plan_destroy(p); return rc; }
   if ((rc = upload<float>(&p->arena_t, nullptr, a.n_params_pad))) { tdb200_plan_destroy(p); return rc; }
+  {
+    const size_t img = (size_t)L * tdb::kMaxW * tdb::kWLd;
+    if ((rc = upload<float>(&p->img_f, nullptr, img))) { tdb200_plan_destroy(p); return rc; }
+    if ((rc = upload<float>(&p->img_b, nullptr, img))) { tdb200_plan_destroy(p); return rc; }
+    cudaMemset(p->img_f, 0, img * sizeof(float));
+    cudaMemset(p->img_b, 0, img * sizeof(float));
+    a.img_f = p->img_f;
+    a.img_b = p->img_b;
+  }
   if ((rc = upload<float>(&p->part_grad, nullptr, (size_t)p->grid * a.n_params_pad))) { tdb200_plan_destroy(p); return rc; }
   if ((rc = upload<double>(&p->part_loss, nullptr, (size_t)p->grid * n_slots))) { tdb200_plan_destroy(p); return rc; }
   if ((rc = upload<float>(&p->scratch, nullptr, (size_t)p->grid * a.scratch_per_cta))) { tdb200_plan_destroy(p); return rc; }
@@ -260,6 +271,8 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
   for (int i = 0; i < a.n_cparams; ++i) pk.c[i] = params[2 * a.n_layers + i];
   pk.arena = p->arena;
   pk.arena_t = p->arena_t;
+  pk.img_f = p->img_f;
+  pk.img_b = p->img_b;
   CU(tdb::launch_pack_params(pk, s));
   tdb::JetArgs call = a;
   call.fields = fields;
@@ -288,7 +301,7 @@ void tdb200_plan_destroy(tdb200_plan* p) {
   cudaSetDevice(p->device);
   cudaFree(p->d_segs); cudaFree(p->d_seg_tile_begin); cudaFree(p->d_terms); cudaFree(p->d_factors);
   cudaFree(p->d_comb); cudaFree(p->d_slot_scale); cudaFree(p->d_slot_lambda); cudaFree(p->d_slot_len);
-  cudaFree(p->arena); cudaFree(p->arena_t); cudaFree(p->part_grad); cudaFree(p->part_loss); cudaFree(p->scratch);
+  cudaFree(p->arena); cudaFree(p->arena_t); cudaFree(p->img_f); cudaFree(p->img_b); cudaFree(p->part_grad); cudaFree(p->part_loss); cudaFree(p->scratch);
   delete p;
 }
 

@@ -28,6 +28,8 @@ struct JetArgs {
   int wmax;                            // widest hidden layer of this net
   const float* arena;                  // packed parameters, same layout as the flat gradient
   const float* arena_t;                // W_l transposed ([in][out]) at w_off[l]
+  const float* img_f;                  // per layer [kMaxW][kWLd]: W^T grouped per warp (forward GEMM tile image)
+  const float* img_b;                  // per layer [kMaxW][kWLd]: W grouped per warp (backward-data GEMM tile image)
   const tdb200_segment* segs;
   int n_segs;
   const int* seg_tile_begin;           // [n_segs + 1]
@@ -61,6 +63,8 @@ struct PackArgs {
   const float* c[kMaxCParams];
   float* arena;
   float* arena_t;
+  float* img_f;
+  float* img_b;
 };
 
 // host-side launchers (jet_simt.cu)

@@ -33,6 +33,11 @@ __global__ void pack_params_kernel(PackArgs a) {
       a.arena[a.w_off[l] + i] = w;
       const int n = i / in, k = i - n * in;
       a.arena_t[a.w_off[l] + k * out + n] = w;
+      // padded images the GEMM tiles copy verbatim: [reduction index][8 warp groups x 16]
+      const int tf = (out + 7) / 8 <= 4 ? 4 : (out + 7) / 8 <= 8 ? 8 : (out + 7) / 8 <= 13 ? 13 : 16;
+      const int tb = (in + 7) / 8 <= 4 ? 4 : (in + 7) / 8 <= 8 ? 8 : (in + 7) / 8 <= 13 ? 13 : 16;
+      a.img_f[(size_t)l * kMaxW * kWLd + k * kWLd + (n / tf) * 16 + n % tf] = w;
+      a.img_b[(size_t)l * kMaxW * kWLd + n * kWLd + (k / tb) * 16 + k % tb] = w;
     }
     for (int i = tid; i < out; i += nth) a.arena[a.b_off[l] + i] = a.b[l][i];
   }
@@ -91,13 +96,10 @@ __device__ inline Smem carve(float* base, int wmax) {
 // ------------------------------------------------------------------------------------------------
 // weight tile loader: src is [I][Jd] (reduction index major); column j of warp-group j / TN lands at
 // wS[i][ (j / TN) * 16 + j % TN ] so every warp reads its TN columns with 16-byte broadcast loads.
-template <int TN>
-__device__ __forceinline__ void load_weights(float* __restrict__ wS, const float* __restrict__ src, int I,
-                                             int Jd) {
-  for (int idx = threadIdx.x; idx < I * Jd; idx += kThreads) {
-    const int i = idx / Jd, j = idx - i * Jd;
-    wS[i * kWLd + (j / TN) * 16 + (j % TN)] = __ldg(src + idx);
-  }
+__device__ __forceinline__ void load_weight_image(float* __restrict__ wS, const float* __restrict__ img, int I) {
+  const float4* s4 = reinterpret_cast<const float4*>(img);
+  float4* d4 = reinterpret_cast<float4*>(wS);
+  for (int idx = threadIdx.x; idx < I * (kWLd / 4); idx += kThreads) d4[idx] = __ldg(s4 + idx);
 }
 
 // out[j][r] = sum_i in[i][r] * w[i][j]   for r < R (multiple of 4), j < Jd <= 8 * TN
@@ -140,13 +142,6 @@ __device__ __forceinline__ void gemm_rows(const float* __restrict__ in, const fl
 
 __device__ __forceinline__ int pick_tn(int jd) { return (jd + 7) / 8; }
 
-__device__ __forceinline__ void load_weights_any(float* wS, const float* src, int I, int Jd) {
-  const int t = pick_tn(Jd);
-  if (t <= 4) load_weights<4>(wS, src, I, Jd);
-  else if (t <= 8) load_weights<8>(wS, src, I, Jd);
-  else if (t <= 13) load_weights<13>(wS, src, I, Jd);
-  else load_weights<16>(wS, src, I, Jd);
-}
 __device__ __forceinline__ void gemm_rows_any(const float* in, const float* wS, float* out, int I, int Jd, int R) {
   const int t = pick_tn(Jd);
   if (t <= 4) gemm_rows<4>(in, wS, out, I, Jd, R);
@@ -195,7 +190,7 @@ __device__ __forceinline__ void gemm_wgrad(const float* __restrict__ g, const fl
 #pragma unroll
     for (int b = 0; b < TW; ++b) {
       const int k = tk + 16 * b;
-      if (k < Kd) dst[(size_t)n * Kd + k] += acc[a][b];
+      if (k < Kd) atomicAdd(dst + (size_t)n * Kd + k, acc[a][b]);   // RED: single owner per address, no stall
     }
   }
 }
@@ -295,7 +290,7 @@ __global__ void __launch_bounds__(kThreads, 1) jet_simt_kernel(const JetArgs a) 
     // ---- hidden layers 1 .. L-2: GEMM + tanh-jet epilogue ---------------------------------------
     for (int l = 1; l <= L - 2; ++l) {
       const int Kd = a.widths[l], Nd = a.widths[l + 1];
-      load_weights_any(sm.wS, a.arena_t + a.w_off[l], Kd, Nd);
+      load_weight_image(sm.wS, a.img_f + (size_t)l * kMaxW * kWLd, Kd);
       __syncthreads();
       gemm_rows_any(cur, sm.wS, oth, Kd, Nd, R);
       __syncthreads();
@@ -307,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, 1) jet_simt_kernel(const JetArgs a) 
         float* row = oth + (size_t)n * kLd;
         const float av = tanhf(row[p] + __ldg(bl + n));
         row[p] = av;
-        if (a.do_grad) ysave[(size_t)n * kRows + p] = av;
+        if (a.do_grad) { ysave[(size_t)n * kRows + p] = av; zsave[(size_t)n * kRows + p] = av; }
         if (J > 1) {
           const TanhF f(av);
           int c = 1;
@@ -434,12 +429,12 @@ __global__ void __launch_bounds__(kThreads, 1) jet_simt_kernel(const JetArgs a) 
         const int v = idx / Kl, k = idx - v * Kl;
         float s = 0.f;
         for (int r = 0; r < R; ++r) s = fmaf(GU[v * R + r], cur[(size_t)k * kLd + r], s);
-        dWl[idx] += s;
+        atomicAdd(dWl + idx, s);
       }
       if (tid < n_out) {
         float s = 0.f;
         for (int p = 0; p < P; ++p) s += GU[tid * R + p];
-        my_grad[a.b_off[L - 1] + tid] += s;
+        atomicAdd(my_grad + a.b_off[L - 1] + tid, s);
       }
       for (int idx = tid; idx < Kl * R; idx += kThreads) {
         const int k = idx / R, r = idx - k * R;
@@ -454,13 +449,24 @@ __global__ void __launch_bounds__(kThreads, 1) jet_simt_kernel(const JetArgs a) 
     for (int t = L - 2; t >= 0; --t) {
       const int Nd = a.widths[t + 1];                       // width of this tanh layer's output
       const float* ysave = my_scratch + (size_t)(2 * t) * save_stride;
-      const float* zsave = ysave + save_stride;
       const float* W0 = a.arena + a.w_off[0];
+      // saved block of this layer ([a; z'; z''; ...], or just Y for layer 0) -> cur (free until Y_{t-1} is needed)
+      {
+        const float* blk = t == 0 ? ysave : ysave + save_stride;
+        const int nr4 = (t == 0 ? P : R) / 4;
+        for (int idx = tid; idx < Nd * nr4; idx += kThreads) {
+          const int k = idx / nr4, r4 = idx - k * nr4;
+          *reinterpret_cast<float4*>(cur + (size_t)k * kLd + r4 * 4) =
+              *reinterpret_cast<const float4*>(blk + (size_t)k * kRows + r4 * 4);
+        }
+      }
+      __syncthreads();
       // tanh-jet adjoint in place: oth holds gY, becomes gZ
       for (int idx = tid; idx < Nd * P; idx += kThreads) {
         const int n = idx / P, p = idx - n * P;
         float* row = oth + (size_t)n * kLd;
-        const float av = ysave[(size_t)n * kRows + p];
+        const float* srow = cur + (size_t)n * kLd;
+        const float av = srow[p];
         const TanhF f(av);
         float g0 = row[p] * f.f1;
         int c = 1;
@@ -468,7 +474,7 @@ __global__ void __launch_bounds__(kThreads, 1) jet_simt_kernel(const JetArgs a) 
           const int o = sg.dir_order[i];
           float z[4] = {0.f, 0.f, 0.f, 0.f}, gy[4], gz[4];
           if (t == 0) z[0] = __ldg(W0 + n * d + sg.dir_axis[i]);
-          else for (int k = 0; k < o; ++k) z[k] = zsave[(size_t)n * kRows + (c + k) * P + p];
+          else for (int k = 0; k < o; ++k) z[k] = srow[(c + k) * P + p];
           for (int k = 0; k < o; ++k) gy[k] = row[(c + k) * P + p];
           g0 += tanh_jet_bwd(f, z, gy, o, gz);
           for (int k = 0; k < o; ++k) row[(c + k) * P + p] = gz[k];
@@ -482,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) jet_simt_kernel(const JetArgs a) 
         const float* row = oth + (size_t)n * kLd;
         float s = 0.f;
         for (int p = 0; p < P; ++p) s += row[p];
-        my_grad[a.b_off[t] + n] += s;
+        atomicAdd(my_grad + a.b_off[t] + n, s);
       }
       if (t == 0) {
         // dW0[n][ax] = sum_p gz0[n][p] x[p][ax] + sum_{dirs on ax} sum_p gz1[n][p]
@@ -497,7 +503,7 @@ __global__ void __launch_bounds__(kThreads, 1) jet_simt_kernel(const JetArgs a) 
               for (int p = 0; p < P; ++p) s += row[c * P + p];
             c += sg.dir_order[i];
           }
-          my_grad[a.w_off[0] + idx] += s;
+          atomicAdd(my_grad + a.w_off[0] + idx, s);
         }
         __syncthreads();
         break;
@@ -510,7 +516,7 @@ __global__ void __launch_bounds__(kThreads, 1) jet_simt_kernel(const JetArgs a) 
         *reinterpret_cast<float4*>(cur + (size_t)k * kLd + r4 * 4) =
             *reinterpret_cast<const float4*>(yprev + (size_t)k * kRows + r4 * 4);
       }
-      load_weights_any(sm.wS, a.arena + a.w_off[t], Nd, Kd);   // W_t as [n][k]: reduction over n
+      load_weight_image(sm.wS, a.img_b + (size_t)t * kMaxW * kWLd, Nd);   // W_t as [n][k]: reduction over n
       __syncthreads();
       gemm_wgrad_any(oth, cur, my_grad + a.w_off[t], Nd, Kd, R);
       __syncthreads();

@@ -20,6 +20,8 @@ constexpr int kMatTY = 32, kMatTX = 64, kMatThreads = 256;
 constexpr int kMatMaxFields = 12;
 constexpr int kMatMaxVar = 4;
 constexpr int kMatMaxHalo = 8;
+constexpr int kMatMaxTaps = 64;
+constexpr int kMatMaxForcing = 16;
 
 struct MatArgs {
   int n_eq, n_var, n0, n1, n_fields;
@@ -36,6 +38,15 @@ struct MatArgs {
   float* op_out;                           // optional [n0*n1][n_eq]
   double* part_loss;                       // [n_ctas][n_eq]
   int tiles_x, tiles_y;
+  // fast path (every equation = constant-coefficient linear terms + forcing): composite interior taps
+  int linear;                              // 1: tables below are valid
+  int edge_y, edge_x;                      // rows / columns with special (one-sided) coefficients at each end
+  int tap_begin[TDB200_MAX_COLS + 1];      // taps of equation e: [tap_begin[e], tap_begin[e+1])
+  short tap_var[kMatMaxTaps], tap_axis[kMatMaxTaps], tap_m[kMatMaxTaps];
+  float tap_w[kMatMaxTaps];
+  int frc_begin[TDB200_MAX_COLS + 1];      // forcing terms of equation e
+  float frc_const[kMatMaxForcing];
+  long long frc_buf[kMatMaxForcing];       // coefficient buffer offset, -1: constant only
 };
 
 __device__ __forceinline__ float band_coef(const float* __restrict__ band, const tdb200_mat_field& f, int n, int i, int m) {
@@ -93,6 +104,67 @@ __global__ void __launch_bounds__(kMatThreads) mat_residual_adjoint_kernel(const
       us[v * uplane + idx] = val;
     }
   __syncthreads();
+
+  // ---- fast path: interior tile of a linear constant-coefficient operator ---------------------------
+  // (uniform per CTA) the residual is one composite stencil, the gradient its transpose applied to the seeds
+  const bool fast = a.linear && ty0 - 2 * hy >= a.edge_y && ty0 + kMatTY + 2 * hy <= a.n0 - a.edge_y &&
+                    tx0 - 2 * hx >= a.edge_x && tx0 + kMatTX + 2 * hx <= a.n1 - a.edge_x;
+  if (fast) {
+    float lacc[TDB200_MAX_COLS];
+#pragma unroll
+    for (int e = 0; e < TDB200_MAX_COLS; ++e) lacc[e] = 0.f;
+    float* ss = as;                                          // [n_eq][ry][rx] residual seeds
+    for (int idx = tid; idx < rplane; idx += kMatThreads) {
+      const int ly = idx / rx, lx = idx - ly * rx;
+      const int gy = ty0 - hy + ly, gx = tx0 - hx + lx;
+      const size_t cell = (size_t)gy * a.n1 + gx;
+      const bool core = ly >= hy && ly < hy + kMatTY && lx >= hx && lx < hx + kMatTX;
+      const float* uc = us + (ly + hy) * ux + lx + hx;
+      for (int e = 0; e < a.n_eq; ++e) {
+        float res = 0.f;
+        for (int t = a.frc_begin[e]; t < a.frc_begin[e + 1]; ++t)
+          res += a.frc_buf[t] >= 0 ? __ldg(a.coeffs + a.frc_buf[t] + cell) : a.frc_const[t];
+        for (int t = a.tap_begin[e]; t < a.tap_begin[e + 1]; ++t) {
+          const int off = a.tap_var[t] * uplane + (a.tap_axis[t] == 0 ? a.tap_m[t] * ux : a.tap_m[t]);
+          res = fmaf(a.tap_w[t], uc[off], res);
+        }
+        if (core) {
+          lacc[e] += res * res;
+          if (a.op_out) a.op_out[cell * a.n_eq + e] = res;
+        }
+        ss[e * rplane + idx] = 2.f * a.eq_scale[e] * res;
+      }
+    }
+    for (int e = 0; e < a.n_eq; ++e) {
+      double v = (double)lacc[e];
+      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((tid & 31) == 0) red[tid >> 5][e] = v;
+    }
+    __syncthreads();
+    if (tid < a.n_eq) {
+      double s = 0.0;
+      for (int w = 0; w < kMatThreads / 32; ++w) s += red[w][tid];
+      a.part_loss[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * a.n_eq + tid] = s;
+    }
+    if (!a.grad) return;
+    for (int idx = tid; idx < kMatTY * kMatTX; idx += kMatThreads) {
+      const int cy = idx / kMatTX, cx = idx - cy * kMatTX;
+      const float* sc = ss + (cy + hy) * rx + cx + hx;
+      float g[kMatMaxVar];
+#pragma unroll
+      for (int v = 0; v < kMatMaxVar; ++v) g[v] = 0.f;
+      for (int e = 0; e < a.n_eq; ++e)
+        for (int t = a.tap_begin[e]; t < a.tap_begin[e + 1]; ++t) {
+          const int off = e * rplane - (a.tap_axis[t] == 0 ? a.tap_m[t] * rx : a.tap_m[t]);
+          const float c = a.tap_w[t] * sc[off];
+#pragma unroll
+          for (int v = 0; v < kMatMaxVar; ++v) if (v == a.tap_var[t]) g[v] += c;
+        }
+      const size_t cell = (size_t)(ty0 + cy) * a.n1 + tx0 + cx;
+      for (int v = 0; v < a.n_var; ++v) a.grad[(size_t)v * N + cell] = g[v];
+    }
+    return;
+  }
 
   // ---- phase 2: fields, residual, loss, field adjoints on tile + halo -------------------------------
   float loss_acc[TDB200_MAX_COLS];
@@ -440,6 +512,54 @@ int tdb200_mat_plan_create(const tdb200_mat_desc* desc, const tdb200_mat_field* 
   if (hy > tdb::kMatMaxHalo || hx > tdb::kMatMaxHalo) { delete p; return mat_invalid("stencil reach too large"); }
   a.hy = hy; a.hx = hx;
   for (int e = 0; e < desc->n_eq; ++e) { a.eq_term_begin[e] = eq_term_begin[e]; a.eq_term_end[e] = eq_term_end[e]; }
+  {  // fast-path analysis: constant-coefficient linear terms + forcing only
+    bool linear = true;
+    int n_taps = 0, n_frc = 0, ey = 0, ex = 0;
+    for (int e = 0; e < desc->n_eq && linear; ++e) {
+      a.tap_begin[e] = n_taps;
+      a.frc_begin[e] = n_frc;
+      for (int t = eq_term_begin[e]; t < eq_term_end[e] && linear; ++t) {
+        const tdb200_term& tm = terms[t];
+        int live = 0, fq = -1;
+        for (int f = tm.fac_begin; f < tm.fac_end; ++f) {
+          if (factors[f].ipow == 0) continue;
+          ++live;
+          fq = factors[f].chan;
+          if (factors[f].ipow != 1) linear = false;
+        }
+        if (live == 0) {
+          if (n_frc >= tdb::kMatMaxForcing || tm.kind == 2) { linear = false; break; }
+          a.frc_const[n_frc] = tm.kind == 0 ? tm.coeff : 0.f;
+          a.frc_buf[n_frc] = tm.kind == 1 ? tm.idx : -1;
+          ++n_frc;
+        } else if (live == 1 && tm.kind == 0 && linear) {
+          const tdb200_mat_field& f = fields[fq];
+          if (f.order == 0) {
+            if (n_taps >= tdb::kMatMaxTaps) { linear = false; break; }
+            a.tap_var[n_taps] = (short)f.var; a.tap_axis[n_taps] = 1; a.tap_m[n_taps] = 0; a.tap_w[n_taps] = tm.coeff;
+            ++n_taps;
+          } else {
+            const float* interior = band + f.coef_off;
+            for (int m = -f.half_width; m <= f.half_width; ++m) {
+              const float w = interior[m + f.half_width];
+              if (w == 0.f) continue;
+              if (n_taps >= tdb::kMatMaxTaps) { linear = false; break; }
+              a.tap_var[n_taps] = (short)f.var; a.tap_axis[n_taps] = (short)f.axis; a.tap_m[n_taps] = (short)m;
+              a.tap_w[n_taps] = tm.coeff * w;
+              ++n_taps;
+            }
+            if (f.axis == 0) ey = f.n_edge > ey ? f.n_edge : ey; else ex = f.n_edge > ex ? f.n_edge : ex;
+          }
+        } else {
+          linear = false;
+        }
+      }
+    }
+    a.tap_begin[desc->n_eq] = n_taps;
+    a.frc_begin[desc->n_eq] = n_frc;
+    a.linear = linear ? 1 : 0;
+    a.edge_y = ey; a.edge_x = ex;
+  }
   a.tiles_x = (desc->n1 + tdb::kMatTX - 1) / tdb::kMatTX;
   a.tiles_y = (desc->n0 + tdb::kMatTY - 1) / tdb::kMatTY;
   p->n_ctas = a.tiles_x * a.tiles_y;
