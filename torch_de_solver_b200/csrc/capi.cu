@@ -69,8 +69,18 @@ struct tdb200_plan {
   float* part_grad = nullptr;
   double* part_loss = nullptr;
   float* scratch = nullptr;
-  int grid = 0;
+  int grid = 0;                    // SIMT kernel CTAs when it runs every segment
   tdb::JetArgs args{};
+  // tensor-core path: segment 0 (interior) on tcgen05, the remaining segments on the SIMT kernel
+  bool tc_eligible = false;
+  int tc_tiles = 0, tc_grid = 0;
+  int simt_rest_tiles = 0, simt_rest_grid = 0;
+  int* d_seg_tile_begin_tc = nullptr;
+  int* d_seg_tile_begin_rest = nullptr;
+  float* wimg = nullptr;
+  float* tc_scratch = nullptr;
+  long long tc_scratch_per_cta = 0;
+  int grad_rows = 0, loss_rows = 0;   // allocated rows of the partial buffers
 };
 
 static int points_per_tile(int J, int K) {
@@ -173,6 +183,34 @@ int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_s
   a.scratch_per_cta = (long long)2 * (L - 1) * wmax * tdb::kRows;
 
   p->grid = tiles < p->n_sms ? (tiles > 0 ? tiles : 1) : p->n_sms;
+  {  // can the interior segment run on the tensor cores?
+    const tdb200_segment& s0 = segments[0];
+    bool ok = L >= 3 && L - 2 <= 3 && net->widths[1] <= 104 && net->widths[L] <= tdb::kMaxOut;
+    for (int l = 2; l < L; ++l) ok = ok && net->widths[l] == net->widths[1];
+    int J0 = 1;
+    for (int i = 0; i < s0.n_dirs; ++i) J0 += s0.dir_order[i];
+    ok = ok && s0.identity && s0.K == 1 && J0 <= 8 && s0.n_groups > 0;
+    p->tc_eligible = ok;
+    if (ok) {
+      const int P = 48 / J0;
+      p->tc_tiles = (int)((s0.n_groups + P - 1) / P);
+      p->tc_grid = p->tc_tiles < p->n_sms ? p->tc_tiles : p->n_sms;
+      std::vector<int> tb(n_segments + 1, p->tc_tiles), rb(n_segments + 1, 0);
+      tb[0] = 0;
+      for (int s = 1; s <= n_segments; ++s) rb[s] = p->seg_tile_begin[s] - p->seg_tile_begin[1];
+      p->simt_rest_tiles = rb[n_segments];
+      p->simt_rest_grid = p->simt_rest_tiles < p->n_sms ? p->simt_rest_tiles : p->n_sms;
+      if ((rc = upload(&p->d_seg_tile_begin_tc, tb.data(), tb.size()))) { tdb200_plan_destroy(p); return rc; }
+      if ((rc = upload(&p->d_seg_tile_begin_rest, rb.data(), rb.size()))) { tdb200_plan_destroy(p); return rc; }
+      const size_t wimg_floats = (size_t)(L - 2) * 2 * 13312;
+      if ((rc = upload<float>(&p->wimg, nullptr, wimg_floats))) { tdb200_plan_destroy(p); return rc; }
+      cudaMemset(p->wimg, 0, wimg_floats * sizeof(float));
+      p->tc_scratch_per_cta = (long long)2 * (L - 1) * 48 * 104;
+      if ((rc = upload<float>(&p->tc_scratch, nullptr, (size_t)p->tc_grid * p->tc_scratch_per_cta))) { tdb200_plan_destroy(p); return rc; }
+    }
+  }
+  p->grad_rows = p->grid + 2 * p->tc_grid + p->simt_rest_grid;
+  p->loss_rows = p->grid + p->tc_grid + p->simt_rest_grid;
   if ((rc = upload<float>(&p->arena, nullptr, a.n_params_pad))) { tdb200_plan_destroy(p); return rc; }
   if ((rc = upload<float>(&p->arena_t, nullptr, a.n_params_pad))) { tdb200_plan_destroy(p); return rc; }
   {
@@ -184,8 +222,8 @@ int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_s
     a.img_f = p->img_f;
     a.img_b = p->img_b;
   }
-  if ((rc = upload<float>(&p->part_grad, nullptr, (size_t)p->grid * a.n_params_pad))) { tdb200_plan_destroy(p); return rc; }
-  if ((rc = upload<double>(&p->part_loss, nullptr, (size_t)p->grid * n_slots))) { tdb200_plan_destroy(p); return rc; }
+  if ((rc = upload<float>(&p->part_grad, nullptr, (size_t)p->grad_rows * a.n_params_pad))) { tdb200_plan_destroy(p); return rc; }
+  if ((rc = upload<double>(&p->part_loss, nullptr, (size_t)p->loss_rows * n_slots))) { tdb200_plan_destroy(p); return rc; }
   if ((rc = upload<float>(&p->scratch, nullptr, (size_t)p->grid * a.scratch_per_cta))) { tdb200_plan_destroy(p); return rc; }
   a.arena = p->arena;
   a.arena_t = p->arena_t;
@@ -240,7 +278,9 @@ int tdb200_plan_set_slots(tdb200_plan* p, const double* slot_lambda, const doubl
 
 int tdb200_plan_set_impl(tdb200_plan* p, int32_t impl) {
   if (!p) return fail(TDB200_ERR_INVALID, "null plan");
-  if (impl < 0 || impl > 1) return fail(TDB200_ERR_INVALID, "implementation not available in this build");
+  if (impl < 0 || impl > 2) return fail(TDB200_ERR_INVALID, "impl must be 0 (auto), 1 (SIMT) or 2 (tcgen05)");
+  if (impl == 2 && !p->tc_eligible)
+    return fail(TDB200_ERR_INVALID, "tcgen05 path needs equal hidden widths <= 104, 1..3 W x W layers and an identity interior segment");
   p->impl = impl;
   return TDB200_OK;
 }
@@ -248,7 +288,15 @@ int tdb200_plan_set_impl(tdb200_plan* p, int32_t impl) {
 int64_t tdb200_plan_out_size(const tdb200_plan* p) { return p ? 2 + p->n_slots + p->args.n_params : 0; }
 int64_t tdb200_plan_n_params(const tdb200_plan* p) { return p ? p->args.n_params : 0; }
 int64_t tdb200_plan_n_fields(const tdb200_plan* p) { return p ? p->n_fields : 0; }
-int32_t tdb200_plan_launches_per_call(const tdb200_plan* p) { return p ? 3 : 0; }
+static bool use_tc(const tdb200_plan* p) {
+  if (!p->tc_eligible || p->impl == 1) return false;
+  return p->impl == 2 || p->segs[0].n_groups >= 4096;
+}
+int32_t tdb200_plan_launches_per_call(const tdb200_plan* p) {
+  if (!p) return 0;
+  if (!use_tc(p)) return 3;
+  return 4 + (p->simt_rest_tiles > 0 ? 1 : 0);
+}
 
 static int run(tdb200_plan* p, const float* const* params, float* fields, float* out, int do_grad, void* stream) {
   if (!p || !params) return fail(TDB200_ERR_INVALID, "null argument");
@@ -277,10 +325,34 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
   tdb::JetArgs call = a;
   call.fields = fields;
   call.do_grad = do_grad;
-  CU(tdb::launch_jet_simt(call, p->grid, s));
+  int grad_rows = p->grid, loss_rows = p->grid;
+  if (use_tc(p)) {
+    CU(tdb::launch_pack_tc_images(pk, p->wimg, s));
+    tdb::JetArgs tc = call;
+    tc.seg_tile_begin = p->d_seg_tile_begin_tc;
+    tc.n_tiles = p->tc_tiles;
+    tc.scratch = p->tc_scratch;
+    tc.scratch_per_cta = p->tc_scratch_per_cta;
+    CU(tdb::launch_jet_tc(tc, p->wimg, p->tc_grid, s));
+    grad_rows = 2 * p->tc_grid;
+    loss_rows = p->tc_grid;
+    if (p->simt_rest_tiles > 0) {
+      tdb::JetArgs rest = call;
+      rest.seg_tile_begin = p->d_seg_tile_begin_rest;
+      rest.n_tiles = p->simt_rest_tiles;
+      rest.part_grad = p->part_grad + (size_t)grad_rows * a.n_params_pad;
+      rest.part_loss = p->part_loss + (size_t)loss_rows * p->n_slots;
+      CU(tdb::launch_jet_simt(rest, p->simt_rest_grid, s));
+      grad_rows += p->simt_rest_grid;
+      loss_rows += p->simt_rest_grid;
+    }
+  } else {
+    CU(tdb::launch_jet_simt(call, p->grid, s));
+  }
   if (out) {
-    CU(tdb::launch_reduce_partials(p->part_grad, p->part_loss, p->grid, do_grad ? a.n_params : 0, a.n_params_pad,
-                                   p->n_slots, p->d_slot_lambda, p->d_slot_len, out, s));
+    CU(tdb::launch_reduce_partials(p->part_grad, do_grad ? grad_rows : 0, p->part_loss, loss_rows,
+                                   do_grad ? a.n_params : 0, a.n_params_pad, p->n_slots, p->d_slot_lambda,
+                                   p->d_slot_len, out, s));
   }
   return TDB200_OK;
 }
@@ -301,7 +373,8 @@ void tdb200_plan_destroy(tdb200_plan* p) {
   cudaSetDevice(p->device);
   cudaFree(p->d_segs); cudaFree(p->d_seg_tile_begin); cudaFree(p->d_terms); cudaFree(p->d_factors);
   cudaFree(p->d_comb); cudaFree(p->d_slot_scale); cudaFree(p->d_slot_lambda); cudaFree(p->d_slot_len);
-  cudaFree(p->arena); cudaFree(p->arena_t); cudaFree(p->img_f); cudaFree(p->img_b); cudaFree(p->part_grad); cudaFree(p->part_loss); cudaFree(p->scratch);
+  cudaFree(p->arena); cudaFree(p->arena_t); cudaFree(p->img_f); cudaFree(p->img_b);
+  cudaFree(p->d_seg_tile_begin_tc); cudaFree(p->d_seg_tile_begin_rest); cudaFree(p->wimg); cudaFree(p->tc_scratch); cudaFree(p->part_grad); cudaFree(p->part_loss); cudaFree(p->scratch);
   delete p;
 }
 

@@ -71,9 +71,13 @@ struct PackArgs {
 size_t jet_simt_smem_bytes(int wmax);
 cudaError_t launch_pack_params(const PackArgs& a, cudaStream_t s);
 cudaError_t launch_jet_simt(const JetArgs& a, int grid, cudaStream_t s);
-cudaError_t launch_reduce_partials(const float* part_grad, const double* part_loss, int n_ctas, int n_params,
-                                   int n_params_pad, int n_slots, const double* slot_lambda,
-                                   const double* slot_len, float* out, cudaStream_t s);
+cudaError_t launch_reduce_partials(const float* part_grad, int n_grad_rows, const double* part_loss,
+                                   int n_loss_rows, int n_params, int n_params_pad, int n_slots,
+                                   const double* slot_lambda, const double* slot_len, float* out, cudaStream_t s);
+// tensor-core path (jet_tc.cu)
+size_t jet_tc_smem_bytes();
+cudaError_t launch_pack_tc_images(const PackArgs& a, float* img, cudaStream_t s);
+cudaError_t launch_jet_tc(const JetArgs& a, const float* wimg, int grid, cudaStream_t s);
 
 // tanh and its derivatives as functions of a = tanh(z):  f1 = 1 - a^2, f_{k+1} = d f_k / dz
 struct TanhF {

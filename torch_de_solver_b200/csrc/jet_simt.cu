@@ -547,21 +547,22 @@ cudaError_t launch_jet_simt(const JetArgs& a, int grid, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // deterministic cross-CTA reduction + loss assembly
 // ------------------------------------------------------------------------------------------------
-__global__ void reduce_partials_kernel(const float* __restrict__ part_grad, const double* __restrict__ part_loss,
-                                       int n_ctas, int n_params, int n_params_pad, int n_slots,
+__global__ void reduce_partials_kernel(const float* __restrict__ part_grad, int n_grad_rows,
+                                       const double* __restrict__ part_loss, int n_loss_rows, int n_params,
+                                       int n_params_pad, int n_slots,
                                        const double* __restrict__ slot_lambda, const double* __restrict__ slot_len,
                                        float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_params) {
     float s = 0.f;
-    for (int c = 0; c < n_ctas; ++c) s += part_grad[(size_t)c * n_params_pad + i];
+    for (int c = 0; c < n_grad_rows; ++c) s += part_grad[(size_t)c * n_params_pad + i];
     out[2 + n_slots + i] = s;
   }
   if (blockIdx.x == 0 && threadIdx.x < 32) {
     double loss = 0.0, lossn = 0.0;
     for (int s = threadIdx.x; s < n_slots; s += 32) {
       double acc = 0.0;
-      for (int c = 0; c < n_ctas; ++c) acc += part_loss[(size_t)c * n_slots + s];
+      for (int c = 0; c < n_loss_rows; ++c) acc += part_loss[(size_t)c * n_slots + s];
       const double mse = acc / slot_len[s];
       out[2 + s] = (float)mse;
       loss += slot_lambda[s] * mse;
@@ -575,13 +576,13 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part_grad, cons
   }
 }
 
-cudaError_t launch_reduce_partials(const float* part_grad, const double* part_loss, int n_ctas, int n_params,
-                                   int n_params_pad, int n_slots, const double* slot_lambda,
-                                   const double* slot_len, float* out, cudaStream_t s) {
+cudaError_t launch_reduce_partials(const float* part_grad, int n_grad_rows, const double* part_loss,
+                                   int n_loss_rows, int n_params, int n_params_pad, int n_slots,
+                                   const double* slot_lambda, const double* slot_len, float* out, cudaStream_t s) {
   const int threads = 256;
   const int blocks = max(1, (n_params + threads - 1) / threads);
-  reduce_partials_kernel<<<blocks, threads, 0, s>>>(part_grad, part_loss, n_ctas, n_params, n_params_pad,
-                                                   n_slots, slot_lambda, slot_len, out);
+  reduce_partials_kernel<<<blocks, threads, 0, s>>>(part_grad, n_grad_rows, part_loss, n_loss_rows, n_params,
+                                                   n_params_pad, n_slots, slot_lambda, slot_len, out);
   return cudaGetLastError();
 }
 
