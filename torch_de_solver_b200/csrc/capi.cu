@@ -202,7 +202,7 @@ int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_s
       p->simt_rest_grid = p->simt_rest_tiles < p->n_sms ? p->simt_rest_tiles : p->n_sms;
       if ((rc = upload(&p->d_seg_tile_begin_tc, tb.data(), tb.size()))) { tdb200_plan_destroy(p); return rc; }
       if ((rc = upload(&p->d_seg_tile_begin_rest, rb.data(), rb.size()))) { tdb200_plan_destroy(p); return rc; }
-      const size_t wimg_floats = (size_t)(L - 2) * 2 * 13312;
+      const size_t wimg_floats = (size_t)(L - 2) * 4 * 13312;
       if ((rc = upload<float>(&p->wimg, nullptr, wimg_floats))) { tdb200_plan_destroy(p); return rc; }
       cudaMemset(p->wimg, 0, wimg_floats * sizeof(float));
       p->tc_scratch_per_cta = (long long)2 * (L - 1) * 48 * 104;

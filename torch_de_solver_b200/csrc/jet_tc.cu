@@ -7,12 +7,13 @@
 // Orientation: D[neuron, (point, channel)] = W . Y^T, i.e. accumulator lanes are neurons and columns are the
 // (point, jet-channel) pairs of the tile.  A thread that owns lane n therefore sees every jet channel of every
 // point for its neuron, so the tanh-jet rule and its adjoint are thread-local TMEM -> registers -> smem epilogues.
-//   forward      D[n,(pc)]  = sum_k W[n,k]  Y[(pc),k]      A = W image (K-major),  B = activations (K-major)
-//   backward     D[k,(pc)]  = sum_n W[n,k] gZ[(pc),n]      A = W image (MN-major), B = gZ (K-major)
-//   weight grad dW[n,k]    += sum_pc gZ[(pc),n] Y[(pc),k]   A = gZ (MN-major), B = Y (MN-major); dW stays in TMEM
+//   forward      D[n,(pc)]  = sum_k W[n,k]   Y[(pc),k]     A = W image   (smem, K-major), B = activations (K-major)
+//   backward     D[k,(pc)]  = sum_n W^T[k,n] gZ[(pc),n]    A = W^T image (smem, K-major), B = gZ (K-major)
+//   weight grad dW[n,k]    += sum_pc gZ[n,(pc)] Y[(pc),k]   A = gZ straight from the epilogue registers into TMEM
+//                                                          (tcgen05.st), B = Y (smem, MN-major); dW stays in TMEM
 //                                                          for the whole kernel and is flushed once per CTA.
-// Operands live in shared memory in the canonical 128-byte-swizzle UMMA layout ([k-block of 32][row][32 floats]);
-// one buffer serves as K-major or MN-major operand depending on the instruction descriptor.
+// K-major operands use the canonical 128-byte swizzle ([k-block of 32][row][32 floats], 16-byte chunks XOR row);
+// the MN-major tf32 operand needs the 32-byte-base variant (SWIZZLE_128B_BASE32B: 4-row atoms, 32-byte chunks).
 #include "common.cuh"
 
 namespace tdb {
@@ -26,22 +27,31 @@ constexpr int kTcWBlock = kTcWRows * 32;
 constexpr int kTcWFloats = 4 * kTcWBlock;        // 13312 floats = 52 KB
 constexpr int kTcMaxMma = 3;                     // W x W layers whose dW fits TMEM (64 + 3 * 128 <= 512 columns)
 constexpr int kTcSavePitch = 104;
+// TMEM columns: D accumulator | gZ hi | gZ lo (A operands of the weight-gradient MMA) | dW slots (112 each)
+constexpr uint32_t kTmD = 0, kTmAHi = 64, kTmALo = 120, kTmDw = 176, kTmDwCols = 112;
 
 // float offset of element (row, k) inside a swizzled operand buffer with `rows` rows per k-block
 __host__ __device__ __forceinline__ int sw_off(int row, int k, int rows) {
   return (k >> 5) * rows * 32 + row * 32 + ((((k & 31) >> 2) ^ (row & 7)) << 2) + (k & 3);
 }
 
+// float offset of element (K-row r, MN index k) of an MN-major tf32 operand (SWIZZLE_128B_BASE32B)
+__host__ __device__ __forceinline__ int sw_off_mn(int r, int k, int rows) {
+  return (k >> 5) * rows * 32 + r * 32 + ((((k & 31) >> 3) ^ (r & 3)) << 3) + (k & 7);
+}
+
 // ------------------------------------------------------------------------------------------------
-// weight images: [layer][hi|lo][4 k-blocks][104 rows][32], hi = tf32(w) (round to nearest), lo = w - hi
+// weight images: [layer][W hi | W lo | W^T hi | W^T lo][4 k-blocks][104 rows][32]; hi = tf32(w) (rna), lo = w - hi
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_tc_images_kernel(PackArgs a, float* __restrict__ img) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nth = gridDim.x * blockDim.x;
   for (int l = 1; l <= a.n_layers - 2; ++l) {
     const int in = a.widths[l], out = a.widths[l + 1];
-    float* hi = img + (size_t)(l - 1) * 2 * kTcWFloats;
+    float* hi = img + (size_t)(l - 1) * 4 * kTcWFloats;
     float* lo = hi + kTcWFloats;
+    float* thi = lo + kTcWFloats;
+    float* tlo = thi + kTcWFloats;
     const float* __restrict__ W = a.W[l];
     for (int i = tid; i < in * out; i += nth) {
       const int n = i / in, k = i - n * in;
@@ -49,9 +59,11 @@ __global__ void pack_tc_images_kernel(PackArgs a, float* __restrict__ img) {
       uint32_t hb;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(w));
       const float h = __uint_as_float(hb);
-      const int o = sw_off(n, k, kTcWRows);
+      const int o = sw_off(n, k, kTcWRows), ot = sw_off(k, n, kTcWRows);
       hi[o] = h;
       lo[o] = w - h;
+      thi[ot] = h;
+      tlo[ot] = w - h;
     }
   }
 }
@@ -66,13 +78,14 @@ cudaError_t launch_pack_tc_images(const PackArgs& a, float* img, cudaStream_t s)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                             uint32_t layout_type = 2 /* SWIZZLE_128B */) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;             // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
   return d;
 }
 // kind::tf32 instruction descriptor: D = f32, A = B = tf32, majors, N >> 3, M >> 4
@@ -85,6 +98,12 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a, uint64_t 
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
       :: "r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+      :: "r"(d_tmem), "r"(a_tmem), "l"(b), "r"(idesc), "r"(accum) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
@@ -129,6 +148,28 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, float a) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" :: "r"(taddr), "r"(__float_as_uint(a)) : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};"
+               :: "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+               :: "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                  "r"(__float_as_uint(v[3])) : "memory");
+}
+// store `count` (1..8, warp-uniform) consecutive columns
+__device__ __forceinline__ void tmem_st_n(uint32_t taddr, const float* v, int count) {
+  int c = 0;
+  if (count & 4) { tmem_st4(taddr, v); c = 4; }
+  if (count == 8) { tmem_st4(taddr + 4, v + 4); return; }
+  if (count & 2) { tmem_st2(taddr + c, v + c); c += 2; }
+  if (count & 1) tmem_st1(taddr + c, v[c]);
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void split_store(float* hi_buf, float* lo_buf, int off, float y) {
   uint32_t hb;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(y));
@@ -157,35 +198,18 @@ __device__ __forceinline__ void issue_forward(uint32_t d_tmem, const float* w_hi
     }
   }
 }
-// D[128 (k) x 48] = A(W image read MN-major: M = k, K = n) . B(gZ, K-major over n)
-__device__ __forceinline__ void issue_backward(uint32_t d_tmem, const float* w_hi, const float* w_lo,
-                                               const float* b_hi, const float* b_lo, int ksteps) {
-  constexpr uint32_t idesc = umma_idesc(128, kTcCols, 1, 0);
-  const uint32_t wa = smem_u32(w_hi), wl = smem_u32(w_lo), ba = smem_u32(b_hi), bl = smem_u32(b_lo);
-  uint32_t acc = 0;
-  for (int pass = 0; pass < 3; ++pass) {
-    const uint32_t A = pass == 0 ? wl : wa;
-    const uint32_t B = pass == 1 ? bl : ba;
-    for (int s = 0; s < ksteps; ++s) {
-      const uint32_t ao = (uint32_t)s * 1024;                                   // 8 rows (n) of every k-block
-      const uint32_t bo = (uint32_t)(s >> 2) * kTcActBlock * 4 + (uint32_t)(s & 3) * 32;
-      umma_tf32(d_tmem, umma_desc(A + ao, kTcWBlock * 4, 1024), umma_desc(B + bo, 16, 1024), idesc, acc);
-      acc = 1;
-    }
-  }
-}
-// dW[128 (n) x 128 (k)] += A(gZ read MN-major: M = n, K = (pc)) . B(Y read MN-major: N = k, K = (pc))
-__device__ __forceinline__ void issue_wgrad(uint32_t d_tmem, const float* g_hi, const float* g_lo,
+// dW[128 (n) x 112 (k)] += A(gZ in TMEM: lanes n, columns (pc)) . B(Y in smem read MN-major: N = k, K = (pc))
+__device__ __forceinline__ void issue_wgrad(uint32_t d_tmem, uint32_t a_hi_tmem, uint32_t a_lo_tmem,
                                             const float* y_hi, const float* y_lo, uint32_t accumulate) {
-  constexpr uint32_t idesc = umma_idesc(128, 128, 1, 1);
-  const uint32_t ga = smem_u32(g_hi), gl = smem_u32(g_lo), ya = smem_u32(y_hi), yl = smem_u32(y_lo);
+  constexpr uint32_t idesc = umma_idesc(128, 112, 0, 1);
+  const uint32_t ya = smem_u32(y_hi), yl = smem_u32(y_lo);
   uint32_t acc = accumulate;
   for (int pass = 0; pass < 3; ++pass) {
-    const uint32_t A = pass == 0 ? gl : ga;
+    const uint32_t A = pass == 0 ? a_lo_tmem : a_hi_tmem;
     const uint32_t B = pass == 1 ? yl : ya;
     for (int s = 0; s < kTcCols / 8; ++s) {
-      const uint32_t o = (uint32_t)s * 1024;
-      umma_tf32(d_tmem, umma_desc(A + o, kTcActBlock * 4, 1024), umma_desc(B + o, kTcActBlock * 4, 1024), idesc, acc);
+      // 8 (pc) rows = two 4-row swizzle atoms (SBO = 512 B); MN blocks of 32 k at LBO = one k-block
+      umma_tf32_ts(d_tmem, A + (uint32_t)s * 8, umma_desc(B + (uint32_t)s * 1024, kTcActBlock * 4, 512, 1), idesc, acc);
       acc = 1;
     }
   }
@@ -265,6 +289,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
   tc_fence_after();
   const uint32_t tmem = *sm.tmem_ptr;
   const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);    // this warp's lane window
+  {  // the gZ operand columns of TMEM must hold zeros where no (point, channel) column exists
+    const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (half == 0)
+      for (uint32_t c = kTmAHi; c < kTmDw; c += 8) tmem_st_n(t_lane + c, z8, 8);
+    tmem_st_wait();
+  }
   uint32_t phase = 0;
   uint32_t dw_started = 0;
   int resident = 0;                                     // W x W layer whose image is in shared memory
@@ -286,7 +316,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       const int p = i / d, ax = i - p * d;
       sm.xS[p * 4 + ax] = p < p_valid ? __ldg(a.pts + (size_t)(sg.pts_off + g_first + p) * d + ax) : 0.f;
     }
-    if (resident != 1) { load_w_image(sm, wimg); resident = 1; }   // layer 1 weights
+    if (resident != 2) { load_w_image(sm, wimg); resident = 2; }   // W of layer 1 (key = 2 * layer + transposed)
     __syncthreads();
 
     // ---- layer 0 (K = d): thread-local ----------------------------------------------------------------
@@ -325,7 +355,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       __syncthreads();
       if (tid == 0) {
         tc_fence_after();
-        issue_forward(tmem, sm.w_hi, sm.w_lo, sm.a_hi, sm.a_lo, ksteps);
+        issue_forward(tmem + kTmD, sm.w_hi, sm.w_lo, sm.a_hi, sm.a_lo, ksteps);
         umma_commit(sm.bar);
       }
       mbar_wait(sm.bar, phase);
@@ -333,13 +363,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       tc_fence_after();
       // the weights of the next GEMM (layer l + 1 forward, or layer n_mma again for the backward sweep) can be
       // fetched while the epilogue runs: the tensor core is done with the image
-      if (l < n_mma) { load_w_image(sm, wimg + (size_t)l * 2 * kTcWFloats); resident = l + 1; }
+      if (l < n_mma) { load_w_image(sm, wimg + (size_t)l * 4 * kTcWFloats); resident = 2 * (l + 1); }
       float* ysave = my_scratch + (size_t)(2 * l) * save_block;
       float* zsave = ysave + save_block;
       const float bl = live ? a.arena[a.b_off[l] + n] : 0.f;
       for (int p = p_lo; p < p_hi; ++p) {
         float zc[8];
-        tmem_ld8(t_lane + (uint32_t)(p * J), zc);
+        tmem_ld8(t_lane + kTmD + (uint32_t)(p * J), zc);
         if (!live) continue;
         const float av = tanhf(zc[0] + bl);
         const TanhF f(av);
@@ -450,9 +480,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       float w0[4] = {0.f, 0.f, 0.f, 0.f};
       if (t == 0 && live)
         for (int ax = 0; ax < d; ++ax) w0[ax] = a.arena[a.w_off[0] + n * d + ax];
+      if (t > 0 && resident != 2 * t + 1) {            // W_t^T for the backward-data GEMM of this layer
+        load_w_image(sm, wimg + (size_t)(t - 1) * 4 * kTcWFloats + 2 * kTcWFloats);
+        resident = 2 * t + 1;
+      }
       for (int p = p_lo; p < p_hi; ++p) {
         const int r = p * J;
-        float gy[8];
+        float gy[8], gzv[8], ghi[8], glo[8];
         if (t == n_mma) {
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -462,38 +496,61 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
             gy[c] = s;
           }
         } else {
-          tmem_ld8(t_lane + (uint32_t)r, gy);
+          tmem_ld8(t_lane + kTmD + (uint32_t)r, gy);
         }
-        if (!live) continue;
-        const float av = ysave[(size_t)r * kTcSavePitch + n];
-        const TanhF f(av);
-        float g0 = gy[0] * f.f1;
-        int c = 1;
-        for (int i = 0; i < ndirs; ++i) {
-          const int o = sg.dir_order[i];
-          float z[4] = {0.f, 0.f, 0.f, 0.f}, gz[4];
-          if (t == 0) z[0] = w0[sg.dir_axis[i]];
-          else for (int k = 0; k < o; ++k) z[k] = zsave[(size_t)(r + c + k) * kTcSavePitch + n];
-          g0 += tanh_jet_bwd(f, z, gy + c, o, gz);
-          if (t == 0) dw0[sg.dir_axis[i]] += gz[0];
-          else for (int k = 0; k < o; ++k) split_store(sm.b_hi, sm.b_lo, sw_off(r + c + k, n, kTcCols), gz[k]);
-          c += o;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) gzv[c] = 0.f;
+        if (live) {
+          const float av = ysave[(size_t)r * kTcSavePitch + n];
+          const TanhF f(av);
+          float g0 = gy[0] * f.f1;
+          int c = 1;
+          for (int i = 0; i < ndirs; ++i) {
+            const int o = sg.dir_order[i];
+            float z[4] = {0.f, 0.f, 0.f, 0.f}, gz[4];
+            if (t == 0) z[0] = w0[sg.dir_axis[i]];
+            else for (int k = 0; k < o; ++k) z[k] = zsave[(size_t)(r + c + k) * kTcSavePitch + n];
+            g0 += tanh_jet_bwd(f, z, gy + c, o, gz);
+            if (t == 0) dw0[sg.dir_axis[i]] += gz[0];
+            for (int k = 0; k < o; ++k) gzv[c + k] = gz[k];
+            c += o;
+          }
+          gzv[0] = g0;
+          db += g0;
+          if (t == 0) for (int ax = 0; ax < d; ++ax) dw0[ax] = fmaf(g0, sm.xS[p * 4 + ax], dw0[ax]);
         }
-        db += g0;
-        if (t == 0) for (int ax = 0; ax < d; ++ax) dw0[ax] = fmaf(g0, sm.xS[p * 4 + ax], dw0[ax]);
-        else split_store(sm.b_hi, sm.b_lo, sw_off(r, n, kTcCols), g0);
+        if (t > 0) {
+          // gZ goes to shared memory (B operand of the backward-data GEMM, K-major over n) and to TMEM
+          // (A operand of the weight-gradient GEMM: lanes n, columns (pc)), both as hi / lo tf32 pairs
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t hb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(gzv[c]));
+            ghi[c] = __uint_as_float(hb);
+            glo[c] = gzv[c] - ghi[c];
+          }
+          if (live)
+            for (int c = 0; c < J; ++c) {
+              const int o = sw_off(r + c, n, kTcCols);
+              sm.b_hi[o] = ghi[c];
+              sm.b_lo[o] = glo[c];
+            }
+          tmem_st_n(t_lane + kTmAHi + (uint32_t)r, ghi, J);
+          tmem_st_n(t_lane + kTmALo + (uint32_t)r, glo, J);
+        }
       }
       if (live) atomicAdd(my_grad + a.b_off[t] + n, db);
       if (t == 0) {
         if (live) for (int ax = 0; ax < d; ++ax) atomicAdd(my_grad + a.w_off[0] + n * d + ax, dw0[ax]);
         break;
       }
-      // Y_{t-1} (all channels) back from scratch as the second operand of the weight-gradient GEMM
+      tmem_st_wait();
+      // Y_{t-1} (all channels) back from scratch as the MN-major B operand of the weight-gradient GEMM
       {
         const float* yprev = my_scratch + (size_t)(2 * (t - 1)) * save_block;
         for (int idx = tid; idx < PJ * kTcSavePitch; idx += kTcThreads) {
           const int r = idx / kTcSavePitch, k = idx - r * kTcSavePitch;
-          if (k < W) split_store(sm.a_hi, sm.a_lo, sw_off(r, k, kTcCols), yprev[idx]);
+          if (k < W) split_store(sm.a_hi, sm.a_lo, sw_off_mn(r, k, kTcCols), yprev[idx]);
         }
       }
       fence_async_smem();
@@ -501,17 +558,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       __syncthreads();
       if (tid == 0) {
         tc_fence_after();
-        issue_wgrad(tmem + 64 + (uint32_t)(t - 1) * 128, sm.b_hi, sm.b_lo, sm.a_hi, sm.a_lo, dw_started);
-        issue_backward(tmem, sm.w_hi, sm.w_lo, sm.b_hi, sm.b_lo, ksteps);
+        issue_wgrad(tmem + kTmDw + (uint32_t)(t - 1) * kTmDwCols, tmem + kTmAHi, tmem + kTmALo, sm.a_hi, sm.a_lo,
+                    dw_started);
+        issue_forward(tmem + kTmD, sm.w_hi, sm.w_lo, sm.b_hi, sm.b_lo, ksteps);   // A = W_t^T image
         umma_commit(sm.bar);
       }
       mbar_wait(sm.bar, phase);
       phase ^= 1;
       tc_fence_after();
-      if (t > 1) {                                  // weights of the next layer down
-        load_w_image(sm, wimg + (size_t)(t - 2) * 2 * kTcWFloats);
-        resident = t - 1;
-      }
     }
     dw_started = 1;
     tc_fence_before();
@@ -522,13 +576,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
   __syncthreads();
   tc_fence_after();
   if (a.do_grad && dw_started) {
+    float* row0 = a.part_grad + (size_t)blockIdx.x * 2 * a.n_params_pad;       // dW lives in the half-0 row
     for (int t = 1; t <= n_mma; ++t) {
-      float* dst = my_grad + a.w_off[t];
-      for (int k0 = half * 64; k0 < half * 64 + 64; k0 += 16) {
-        float v[16];
-        tmem_ld16(t_lane + 64 + (uint32_t)(t - 1) * 128 + (uint32_t)k0, v);
+      float* dst = row0 + a.w_off[t];
+      for (int k0 = half * 56; k0 < half * 56 + 56; k0 += 8) {
+        float v[8];
+        tmem_ld8(t_lane + kTmDw + (uint32_t)(t - 1) * kTmDwCols + (uint32_t)k0, v);
         if (live)
-          for (int j = 0; j < 16; ++j)
+          for (int j = 0; j < 8; ++j)
             if (k0 + j < W) dst[(size_t)n * W + k0 + j] = v[j];
       }
     }
