@@ -74,6 +74,7 @@ struct tdb200_plan {
   // tensor-core path: segment 0 (interior) on tcgen05, the remaining segments on the SIMT kernel
   bool tc_eligible = false;
   int tc_tiles = 0, tc_grid = 0;
+  int tc_sig[3] = {0, 0, 0};
   int simt_rest_tiles = 0, simt_rest_grid = 0;
   int* d_seg_tile_begin_tc = nullptr;
   int* d_seg_tile_begin_rest = nullptr;
@@ -185,14 +186,14 @@ int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_s
   p->grid = tiles < p->n_sms ? (tiles > 0 ? tiles : 1) : p->n_sms;
   {  // can the interior segment run on the tensor cores?
     const tdb200_segment& s0 = segments[0];
-    bool ok = L >= 3 && L - 2 <= 3 && net->widths[1] <= 104 && net->widths[L] <= tdb::kMaxOut;
+    bool ok = L >= 3 && L - 2 <= 2 && net->widths[1] <= 104 && net->widths[L] <= tdb::kMaxOut;
     for (int l = 2; l < L; ++l) ok = ok && net->widths[l] == net->widths[1];
-    int J0 = 1;
-    for (int i = 0; i < s0.n_dirs; ++i) J0 += s0.dir_order[i];
-    ok = ok && s0.identity && s0.K == 1 && J0 <= 8 && s0.n_groups > 0;
+    for (int i = 0; i < 3; ++i) p->tc_sig[i] = i < s0.n_dirs ? s0.dir_order[i] : 0;
+    ok = ok && s0.identity && s0.K == 1 && s0.n_dirs <= 3 && s0.n_groups > 0 &&
+         tdb::jet_tc_supports(p->tc_sig[0], p->tc_sig[1], p->tc_sig[2]);
     p->tc_eligible = ok;
     if (ok) {
-      const int P = 48 / J0;
+      const int P = tdb::jet_tc_points_per_tile(p->tc_sig[0], p->tc_sig[1], p->tc_sig[2]);
       p->tc_tiles = (int)((s0.n_groups + P - 1) / P);
       p->tc_grid = p->tc_tiles < p->n_sms ? p->tc_tiles : p->n_sms;
       std::vector<int> tb(n_segments + 1, p->tc_tiles), rb(n_segments + 1, 0);
@@ -280,7 +281,7 @@ int tdb200_plan_set_impl(tdb200_plan* p, int32_t impl) {
   if (!p) return fail(TDB200_ERR_INVALID, "null plan");
   if (impl < 0 || impl > 2) return fail(TDB200_ERR_INVALID, "impl must be 0 (auto), 1 (SIMT) or 2 (tcgen05)");
   if (impl == 2 && !p->tc_eligible)
-    return fail(TDB200_ERR_INVALID, "tcgen05 path needs equal hidden widths <= 104, 1..3 W x W layers and an identity interior segment");
+    return fail(TDB200_ERR_INVALID, "tcgen05 path needs equal hidden widths <= 104, 1 or 2 W x W layers and an identity interior segment with pure partials along <= 3 axes");
   p->impl = impl;
   return TDB200_OK;
 }
@@ -333,7 +334,7 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
     tc.n_tiles = p->tc_tiles;
     tc.scratch = p->tc_scratch;
     tc.scratch_per_cta = p->tc_scratch_per_cta;
-    CU(tdb::launch_jet_tc(tc, p->wimg, p->tc_grid, s));
+    CU(tdb::launch_jet_tc(tc, p->wimg, p->tc_sig[0], p->tc_sig[1], p->tc_sig[2], p->tc_grid, s));
     grad_rows = 2 * p->tc_grid;
     loss_rows = p->tc_grid;
     if (p->simt_rest_tiles > 0) {

@@ -25,10 +25,11 @@ constexpr int kTcActBlock = kTcCols * 32;        // floats per k-block of an act
 constexpr int kTcActFloats = 4 * kTcActBlock;    // 6144 floats = 24 KB
 constexpr int kTcWBlock = kTcWRows * 32;
 constexpr int kTcWFloats = 4 * kTcWBlock;        // 13312 floats = 52 KB
-constexpr int kTcMaxMma = 3;                     // W x W layers whose dW fits TMEM (64 + 3 * 128 <= 512 columns)
+constexpr int kTcMaxMma = 2;                     // W x W layers: Z_l, dW_l and the operands all stay in TMEM
 constexpr int kTcSavePitch = 104;
-// TMEM columns: D accumulator | gZ hi | gZ lo (A operands of the weight-gradient MMA) | dW slots (112 each)
-constexpr uint32_t kTmD = 0, kTmAHi = 64, kTmALo = 120, kTmDw = 176, kTmDwCols = 112;
+// TMEM columns: Z_1 | Z_2 (forward accumulators, kept for the backward sweep) | D_bwd | gZ hi | gZ lo (A operands
+// of the weight-gradient MMA) | dW slots (112 columns each)
+constexpr uint32_t kTmZ = 0, kTmDb = 96, kTmAHi = 144, kTmALo = 192, kTmDw = 240, kTmDwCols = 112;
 
 // float offset of element (row, k) inside a swizzled operand buffer with `rows` rows per k-block
 __host__ __device__ __forceinline__ int sw_off(int row, int k, int rows) {
@@ -216,28 +217,99 @@ __device__ __forceinline__ void issue_wgrad(uint32_t d_tmem, uint32_t a_hi_tmem,
 }
 
 // ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+// tanh with ~1e-7 absolute error: odd polynomial near 0 (Cephes tanhf), 1 - 2 / (exp(2|x|) + 1) elsewhere
+__device__ __forceinline__ float tanh_acc(float x) {
+  const float ax = fabsf(x);
+  if (ax < 0.625f) {
+    const float s = x * x;
+    const float p = ((((-5.70498872745e-3f * s + 2.06390887954e-2f) * s - 5.37397155531e-2f) * s +
+                      1.33314422036e-1f) * s - 3.33332819422e-1f);
+    return fmaf(x * s, p, x);
+  }
+  const float e = __expf(2.f * ax);
+  return copysignf(1.f - __fdividef(2.f, e + 1.f), x);
+}
+
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 24 consecutive columns of this warp's lane window
+__device__ __forceinline__ void tmem_ld24(uint32_t taddr, float* v) {
+  tmem_ld8_nowait(taddr, v);
+  tmem_ld8_nowait(taddr + 8, v + 8);
+  tmem_ld8_nowait(taddr + 16, v + 16);
+  tmem_ld_wait();
+}
+// exactly C (compile time, <= 24) columns
+template <int C>
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const float* v) {
+  int c = 0;
+#pragma unroll
+  for (; c + 4 <= C; c += 4) tmem_st4(taddr + c, v + c);
+  if (C & 2) { tmem_st2(taddr + c, v + c); c += 2; }
+  if (C & 1) tmem_st1(taddr + c, v[c]);
+}
+
+// warp-wide sum of 32 per-lane values: afterwards lane L holds the total of v[L] over the warp (31 shuffles)
+__device__ __forceinline__ float warp_multi_reduce32(float* v, int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float keep = up ? v[i + off] : v[i];
+      const float send = up ? v[i] : v[i + off];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+// bulk (TMA, 1-D) copy of one weight image pair into shared memory, completion on an mbarrier
+__device__ __forceinline__ void bulk_load_image(float* dst, const float* src, uint64_t* bar) {
+  constexpr uint32_t kBytes = 2 * kTcWFloats * 4, kChunk = 8192;
+  const uint32_t b = smem_u32(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(kBytes) : "memory");
+  for (uint32_t o = 0; o < kBytes; o += kChunk)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst) + o), "l"(reinterpret_cast<const char*>(src) + o), "r"(kChunk), "r"(b)
+                 : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
 struct TcSmem {
   float *w_hi, *w_lo, *a_hi, *a_lo, *b_hi, *b_lo;
-  float *xS, *uS, *guS, *wlS, *cgS;
+  float *xS, *uS, *guS, *uP, *wlS, *cgS;
   double* lossS;
-  uint64_t* bar;
+  uint64_t *bar, *wbar;
   uint32_t* tmem_ptr;
 };
 constexpr size_t kTcSmemBytes = (size_t)(2 * kTcWFloats + 4 * kTcActFloats) * 4 + 1024 /*align*/ +
-                                (kTcCols * 4 + 2 * kMaxOut * kTcCols + kMaxOut * kTcSavePitch + kMaxCParams) * 4 +
-                                32 * 8 + 64;
+                                (kTcCols * 4 + 2 * kMaxOut * kTcCols + 4 * kMaxOut * kTcCols +
+                                 kMaxOut * kTcSavePitch + kMaxCParams) * 4 + 32 * 8 + 64;
 
 size_t jet_tc_smem_bytes() { return kTcSmemBytes; }
 
-__device__ __forceinline__ void load_w_image(const TcSmem& sm, const float* __restrict__ img) {
-  const float4* s4 = reinterpret_cast<const float4*>(img);
-  float4* d4 = reinterpret_cast<float4*>(sm.w_hi);               // w_hi and w_lo are contiguous
-  for (int i = threadIdx.x; i < 2 * kTcWFloats / 4; i += kTcThreads) d4[i] = __ldg(s4 + i);
-}
-
+// Jet signature: derivative orders of up to three directions (sorted by input axis); J = 1 + O0 + O1 + O2.
+template <int O0, int O1, int O2>
 __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, const float* __restrict__ wimg) {
+  constexpr int J = 1 + O0 + O1 + O2;
+  constexpr int ND = (O0 > 0) + (O1 > 0) + (O2 > 0);
+  constexpr int PH = 24 / J;                   // points per half tile
+  constexpr int P = 2 * PH;                    // points per tile
+  constexpr int C = PH * J;                    // columns per half (<= 24)
+  constexpr int ORD[3] = {O0, O1, O2};
   extern __shared__ uint8_t smem_raw_tc[];
   TcSmem sm;
   {
@@ -252,24 +324,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
     sm.xS = f; f += kTcCols * 4;
     sm.uS = f; f += kMaxOut * kTcCols;
     sm.guS = f; f += kMaxOut * kTcCols;
+    sm.uP = f; f += 4 * kMaxOut * kTcCols;
     sm.wlS = f; f += kMaxOut * kTcSavePitch;
     sm.cgS = f; f += kMaxCParams;
     sm.lossS = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(f) + 15) & ~uintptr_t(15));
     sm.bar = reinterpret_cast<uint64_t*>(sm.lossS + 32);
-    sm.tmem_ptr = reinterpret_cast<uint32_t*>(sm.bar + 1);
+    sm.wbar = sm.bar + 1;
+    sm.tmem_ptr = reinterpret_cast<uint32_t*>(sm.wbar + 1);
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = (warp & 3) * 32 + lane;                 // neuron = TMEM lane owned by this thread
   const int half = warp >> 2;                           // which half of the tile's points
   const int L = a.n_layers, W = a.widths[1], n_out = a.widths[L], d = a.d;
-  const int n_mma = L - 2;
+  const int n_mma = L - 2;                              // 1 or 2
   const int ksteps = (W + 7) / 8;
   const bool live = n < W;
-  // two gradient-partial rows per CTA (one per point half): every address has a single owner thread, so the
-  // fp32 accumulation order is fixed and results are bit-reproducible
+  const int col0 = half * C;                            // first (point, channel) column of this thread
+  // two gradient-partial rows per CTA (one per half): a single owner thread per address -> bit-reproducible
   float* const my_grad = a.part_grad + ((size_t)blockIdx.x * 2 + half) * a.n_params_pad;
-  float* const my_scratch = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;
-  const size_t save_block = (size_t)kTcCols * kTcSavePitch;          // one saved [48][104] block
 
   // ---- one-time setup --------------------------------------------------------------------------------
   for (int i = tid; i < 2 * a.n_params_pad; i += kTcThreads)
@@ -278,7 +350,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
   if (tid < 32) sm.lossS[tid] = 0.0;
   if (tid < kMaxCParams) sm.cgS[tid] = 0.f;
   for (int i = tid; i < n_out * W; i += kTcThreads) sm.wlS[(i / W) * kTcSavePitch + i % W] = a.arena[a.w_off[L - 1] + i];
-  if (tid == 0) mbar_init(sm.bar, 1);
+  if (tid == 0) { mbar_init(sm.bar, 1); mbar_init(sm.wbar, 1); }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(sm.tmem_ptr)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -292,60 +364,59 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
   {  // the gZ operand columns of TMEM must hold zeros where no (point, channel) column exists
     const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (half == 0)
-      for (uint32_t c = kTmAHi; c < kTmDw; c += 8) tmem_st_n(t_lane + c, z8, 8);
+      for (uint32_t c = kTmAHi; c < kTmDw; c += 8) { tmem_st4(t_lane + c, z8); tmem_st4(t_lane + c + 4, z8); }
     tmem_st_wait();
   }
-  uint32_t phase = 0;
+  uint32_t phase = 0, wphase = 0;                       // wphase is only used by thread 0
   uint32_t dw_started = 0;
-  int resident = 0;                                     // W x W layer whose image is in shared memory
+  // per-layer parameters this thread needs all the time
+  float bias[3] = {0.f, 0.f, 0.f}, w0[4] = {0.f, 0.f, 0.f, 0.f}, wl[kMaxOut];
+  if (live) {
+    for (int l = 0; l <= n_mma; ++l) bias[l] = a.arena[a.b_off[l] + n];
+    for (int ax = 0; ax < d; ++ax) w0[ax] = a.arena[a.w_off[0] + n * d + ax];
+  }
+#pragma unroll
+  for (int v = 0; v < kMaxOut; ++v) wl[v] = (live && v < n_out) ? a.arena[a.w_off[L - 1] + v * W + n] : 0.f;
 
-  int seg_i = 0;
+  const tdb200_segment& sg = a.segs[0];
+  const int ncols = sg.n_cols;
+  int dir_axis[3] = {0, 0, 0};
+  for (int i = 0; i < ND; ++i) dir_axis[i] = sg.dir_axis[i];
+
+  if (tid == 0) bulk_load_image(sm.w_hi, wimg, sm.wbar);          // W_1 for the first tile
+
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    while (tile >= a.seg_tile_begin[seg_i + 1]) ++seg_i;
-    const tdb200_segment& sg = a.segs[seg_i];
-    const int ndirs = sg.n_dirs, ncols = sg.n_cols;
-    int J = 1;
-    for (int i = 0; i < ndirs; ++i) J += sg.dir_order[i];
-    const int P = kTcCols / J;
-    const int Ph = (P + 1) / 2;
-    const int p_lo = half == 0 ? 0 : Ph, p_hi = half == 0 ? Ph : P;
-    const long long g_first = (long long)(tile - a.seg_tile_begin[seg_i]) * P;
+    const long long g_first = (long long)tile * P;
     const int p_valid = (int)min((long long)P, sg.n_groups - g_first);
-
     for (int i = tid; i < P * d; i += kTcThreads) {
       const int p = i / d, ax = i - p * d;
       sm.xS[p * 4 + ax] = p < p_valid ? __ldg(a.pts + (size_t)(sg.pts_off + g_first + p) * d + ax) : 0.f;
     }
-    if (resident != 2) { load_w_image(sm, wimg); resident = 2; }   // W of layer 1 (key = 2 * layer + transposed)
     __syncthreads();
 
+    float yk[3][24];                                    // outputs of tanh layers 0..n_mma for this thread's columns
+
     // ---- layer 0 (K = d): thread-local ----------------------------------------------------------------
-    if (live) {
-      const float* W0 = a.arena + a.w_off[0];
-      const float b0 = a.arena[a.b_off[0] + n];
-      float w0[4];
-      for (int ax = 0; ax < d; ++ax) w0[ax] = W0[n * d + ax];
-      float* ysave = my_scratch;
-      for (int p = p_lo; p < p_hi; ++p) {
-        float z0 = b0;
-        for (int ax = 0; ax < d; ++ax) z0 = fmaf(w0[ax], sm.xS[p * 4 + ax], z0);
-        const float av = tanhf(z0);
-        const TanhF f(av);
-        int r = p * J;
-        split_store(sm.a_hi, sm.a_lo, sw_off(r, n, kTcCols), av);
-        ysave[(size_t)r * kTcSavePitch + n] = av;
-        int c = 1;
-        for (int i = 0; i < ndirs; ++i) {
-          const int o = sg.dir_order[i];
-          float z[4] = {w0[sg.dir_axis[i]], 0.f, 0.f, 0.f}, y[4];
-          tanh_jet_fwd(f, z, o, y);
-          for (int k = 0; k < o; ++k) {
-            split_store(sm.a_hi, sm.a_lo, sw_off(r + c + k, n, kTcCols), y[k]);
-            ysave[(size_t)(r + c + k) * kTcSavePitch + n] = y[k];
-          }
-          c += o;
-        }
+#pragma unroll
+    for (int p = 0; p < PH; ++p) {
+      float z0 = bias[0];
+      for (int ax = 0; ax < d; ++ax) z0 = fmaf(w0[ax], sm.xS[(half * PH + p) * 4 + ax], z0);
+      const float av = tanh_acc(z0);
+      const TanhF f(av);
+      yk[0][p * J] = av;
+      int c = 1;
+#pragma unroll
+      for (int i = 0; i < ND; ++i) {
+        float z[4] = {w0[dir_axis[i]], 0.f, 0.f, 0.f}, y[4];
+        tanh_jet_fwd(f, z, ORD[i], y);
+#pragma unroll
+        for (int k = 0; k < ORD[i]; ++k) yk[0][p * J + c + k] = y[k];
+        c += ORD[i];
       }
+    }
+    if (live) {
+#pragma unroll
+      for (int j = 0; j < C; ++j) split_store(sm.a_hi, sm.a_lo, sw_off(col0 + j, n, kTcCols), yk[0][j]);
     }
 
     // ---- W x W layers: tensor-core GEMM + thread-local tanh-jet epilogue ------------------------------
@@ -354,56 +425,54 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       tc_fence_before();
       __syncthreads();
       if (tid == 0) {
+        mbar_wait(sm.wbar, wphase); wphase ^= 1;        // W_l image has landed
         tc_fence_after();
-        issue_forward(tmem + kTmD, sm.w_hi, sm.w_lo, sm.a_hi, sm.a_lo, ksteps);
+        issue_forward(tmem + kTmZ + 48u * (uint32_t)(l - 1), sm.w_hi, sm.w_lo, sm.a_hi, sm.a_lo, ksteps);
         umma_commit(sm.bar);
       }
       mbar_wait(sm.bar, phase);
       phase ^= 1;
       tc_fence_after();
-      // the weights of the next GEMM (layer l + 1 forward, or layer n_mma again for the backward sweep) can be
-      // fetched while the epilogue runs: the tensor core is done with the image
-      if (l < n_mma) { load_w_image(sm, wimg + (size_t)l * 4 * kTcWFloats); resident = 2 * (l + 1); }
-      float* ysave = my_scratch + (size_t)(2 * l) * save_block;
-      float* zsave = ysave + save_block;
-      const float bl = live ? a.arena[a.b_off[l] + n] : 0.f;
-      for (int p = p_lo; p < p_hi; ++p) {
-        float zc[8];
-        tmem_ld8(t_lane + kTmD + (uint32_t)(p * J), zc);
-        if (!live) continue;
-        const float av = tanhf(zc[0] + bl);
+      // next image (W_{l+1}, or W_{n_mma}^T for the backward sweep) streams in behind the epilogue
+      if (tid == 0)
+        bulk_load_image(sm.w_hi, wimg + (size_t)(l < n_mma ? l : n_mma - 1) * 4 * kTcWFloats + (l < n_mma ? 0 : 2 * kTcWFloats), sm.wbar);
+      float z[24];
+      tmem_ld24(t_lane + kTmZ + 48u * (uint32_t)(l - 1) + (uint32_t)col0, z);
+#pragma unroll
+      for (int p = 0; p < PH; ++p) {
+        const float av = tanh_acc(z[p * J] + bias[l]);
         const TanhF f(av);
-        const int r = p * J;
-        split_store(sm.a_hi, sm.a_lo, sw_off(r, n, kTcCols), av);
-        ysave[(size_t)r * kTcSavePitch + n] = av;
-        zsave[(size_t)r * kTcSavePitch + n] = av;
+        yk[l][p * J] = av;
         int c = 1;
-        for (int i = 0; i < ndirs; ++i) {
-          const int o = sg.dir_order[i];
+#pragma unroll
+        for (int i = 0; i < ND; ++i) {
           float y[4];
-          tanh_jet_fwd(f, zc + c, o, y);
-          for (int k = 0; k < o; ++k) {
-            split_store(sm.a_hi, sm.a_lo, sw_off(r + c + k, n, kTcCols), y[k]);
-            ysave[(size_t)(r + c + k) * kTcSavePitch + n] = y[k];
-            zsave[(size_t)(r + c + k) * kTcSavePitch + n] = zc[c + k];
-          }
-          c += o;
+          tanh_jet_fwd(f, z + p * J + c, ORD[i], y);
+#pragma unroll
+          for (int k = 0; k < ORD[i]; ++k) yk[l][p * J + c + k] = y[k];
+          c += ORD[i];
         }
       }
-    }
-    tc_fence_before();
-    __syncthreads();
-
-    // ---- last layer (n_out <= 8 outputs): u[v][r] = sum_n Wl[v][n] Y[r][n] -----------------------------
-    const int PJ = P * J;
-    for (int idx = tid; idx < n_out * PJ; idx += kTcThreads) {
-      const int v = idx / PJ, r = idx - v * PJ;
-      float s = (r % J) == 0 ? a.arena[a.b_off[L - 1] + v] : 0.f;
-      const float* wl = sm.wlS + v * kTcSavePitch;
-      for (int k = 0; k < W; ++k) {
-        const int o = sw_off(r, k, kTcCols);
-        s = fmaf(wl[k], sm.a_hi[o] + sm.a_lo[o], s);
+      if (live && l < n_mma) {
+#pragma unroll
+        for (int j = 0; j < C; ++j) split_store(sm.a_hi, sm.a_lo, sw_off(col0 + j, n, kTcCols), yk[l][j]);
       }
+    }
+
+    // ---- last layer: u[v][col] = sum_n Wl[v][n] y[n][col]  (warp multi-value reduction, fixed order) ------
+    for (int v = 0; v < n_out; ++v) {
+      float t32[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) t32[j] = (j < C && live) ? wl[v] * yk[n_mma][j] : 0.f;
+      const float tot = warp_multi_reduce32(t32, lane);
+      if (lane < C) sm.uP[((warp & 3) * kMaxOut + v) * kTcCols + col0 + lane] = tot;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < n_out * 2 * C; idx += kTcThreads) {
+      const int v = idx / (2 * C), r = idx - v * (2 * C);
+      float s = (r % J) == 0 ? a.arena[a.b_off[L - 1] + v] : 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) s += sm.uP[(w * kMaxOut + v) * kTcCols + r];
       sm.uS[v * kTcCols + r] = s;
       sm.guS[v * kTcCols + r] = 0.f;
     }
@@ -454,118 +523,112 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       }
     }
     __syncthreads();
-    if (!a.do_grad) continue;
+    if (!a.do_grad) {
+      // forward-only evaluation: the image prefetched for the backward sweep is not needed; fetch W_1 instead
+      if (tid == 0) { mbar_wait(sm.wbar, wphase); wphase ^= 1; bulk_load_image(sm.w_hi, wimg, sm.wbar); }
+      continue;
+    }
 
-    // ---- backward of the last layer: dWl, dbl (thread-local partial sums over this thread's points) ----
-    if (tid < n_out) {                                   // warp 0 -> half 0 row
+    // ---- backward of the last layer: dWl, dbl; gY of the last tanh layer ---------------------------------
+    if (tid < n_out) {                                   // warp 0 -> half-0 row
       float s = 0.f;
       for (int p = 0; p < P; ++p) s += sm.guS[tid * kTcCols + p * J];
       atomicAdd(my_grad + a.b_off[L - 1] + tid, s);
     }
-    if (live) {
-      const float* ylast = my_scratch + (size_t)(2 * n_mma) * save_block;      // Y of the last hidden layer
-      for (int v = 0; v < n_out; ++v) {
-        float s = 0.f;
-        for (int r = p_lo * J; r < p_hi * J; ++r) s = fmaf(sm.guS[v * kTcCols + r], ylast[(size_t)r * kTcSavePitch + n], s);
-        atomicAdd(my_grad + a.w_off[L - 1] + v * W + n, s);
+    float gy[24];
+#pragma unroll
+    for (int j = 0; j < 24; ++j) gy[j] = 0.f;
+    for (int v = 0; v < n_out; ++v) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        const float g = sm.guS[v * kTcCols + col0 + j];
+        s = fmaf(g, yk[n_mma][j], s);
+        gy[j] = fmaf(wl[v], g, gy[j]);
       }
+      if (live) atomicAdd(my_grad + a.w_off[L - 1] + v * W + n, s);
     }
 
     // ---- backward sweep over the tanh layers t = n_mma .. 0 ------------------------------------------
-    float dw0[4] = {0.f, 0.f, 0.f, 0.f};
     for (int t = n_mma; t >= 0; --t) {
-      const float* ysave = my_scratch + (size_t)(2 * t) * save_block;
-      const float* zsave = ysave + save_block;
-      float db = 0.f;
-      float w0[4] = {0.f, 0.f, 0.f, 0.f};
-      if (t == 0 && live)
-        for (int ax = 0; ax < d; ++ax) w0[ax] = a.arena[a.w_off[0] + n * d + ax];
-      if (t > 0 && resident != 2 * t + 1) {            // W_t^T for the backward-data GEMM of this layer
-        load_w_image(sm, wimg + (size_t)(t - 1) * 4 * kTcWFloats + 2 * kTcWFloats);
-        resident = 2 * t + 1;
-      }
-      for (int p = p_lo; p < p_hi; ++p) {
-        const int r = p * J;
-        float gy[8], gzv[8], ghi[8], glo[8];
-        if (t == n_mma) {
+      float z[24];
+      if (t > 0) tmem_ld24(t_lane + kTmZ + 48u * (uint32_t)(t - 1) + (uint32_t)col0, z);
+      if (t < n_mma) tmem_ld24(t_lane + kTmDb + (uint32_t)col0, gy);
+      float gz[24];
+      float db = 0.f, dw0[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float s = 0.f;
-            if (c < J && live)
-              for (int v = 0; v < n_out; ++v) s = fmaf(sm.wlS[v * kTcSavePitch + n], sm.guS[v * kTcCols + r + c], s);
-            gy[c] = s;
-          }
-        } else {
-          tmem_ld8(t_lane + kTmD + (uint32_t)r, gy);
-        }
+      for (int p = 0; p < PH; ++p) {
+        const float av = yk[t][p * J];
+        const TanhF f(av);
+        float g0 = gy[p * J] * f.f1;
+        int c = 1;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) gzv[c] = 0.f;
-        if (live) {
-          const float av = ysave[(size_t)r * kTcSavePitch + n];
-          const TanhF f(av);
-          float g0 = gy[0] * f.f1;
-          int c = 1;
-          for (int i = 0; i < ndirs; ++i) {
-            const int o = sg.dir_order[i];
-            float z[4] = {0.f, 0.f, 0.f, 0.f}, gz[4];
-            if (t == 0) z[0] = w0[sg.dir_axis[i]];
-            else for (int k = 0; k < o; ++k) z[k] = zsave[(size_t)(r + c + k) * kTcSavePitch + n];
-            g0 += tanh_jet_bwd(f, z, gy + c, o, gz);
-            if (t == 0) dw0[sg.dir_axis[i]] += gz[0];
-            for (int k = 0; k < o; ++k) gzv[c + k] = gz[k];
-            c += o;
-          }
-          gzv[0] = g0;
-          db += g0;
-          if (t == 0) for (int ax = 0; ax < d; ++ax) dw0[ax] = fmaf(g0, sm.xS[p * 4 + ax], dw0[ax]);
-        }
-        if (t > 0) {
-          // gZ goes to shared memory (B operand of the backward-data GEMM, K-major over n) and to TMEM
-          // (A operand of the weight-gradient GEMM: lanes n, columns (pc)), both as hi / lo tf32 pairs
+        for (int i = 0; i < ND; ++i) {
+          float zz[4] = {0.f, 0.f, 0.f, 0.f}, gg[4];
+          if (t == 0) zz[0] = w0[dir_axis[i]];
+          else {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            uint32_t hb;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(gzv[c]));
-            ghi[c] = __uint_as_float(hb);
-            glo[c] = gzv[c] - ghi[c];
+            for (int k = 0; k < ORD[i]; ++k) zz[k] = z[p * J + c + k];
           }
-          if (live)
-            for (int c = 0; c < J; ++c) {
-              const int o = sw_off(r + c, n, kTcCols);
-              sm.b_hi[o] = ghi[c];
-              sm.b_lo[o] = glo[c];
-            }
-          tmem_st_n(t_lane + kTmAHi + (uint32_t)r, ghi, J);
-          tmem_st_n(t_lane + kTmALo + (uint32_t)r, glo, J);
+          g0 += tanh_jet_bwd(f, zz, gy + p * J + c, ORD[i], gg);
+          if (t == 0) dw0[dir_axis[i]] += gg[0];
+#pragma unroll
+          for (int k = 0; k < ORD[i]; ++k) gz[p * J + c + k] = gg[k];
+          c += ORD[i];
         }
+        gz[p * J] = g0;
+        db += g0;
+        if (t == 0)
+          for (int ax = 0; ax < d; ++ax) dw0[ax] = fmaf(g0, sm.xS[(half * PH + p) * 4 + ax], dw0[ax]);
       }
       if (live) atomicAdd(my_grad + a.b_off[t] + n, db);
       if (t == 0) {
         if (live) for (int ax = 0; ax < d; ++ax) atomicAdd(my_grad + a.w_off[0] + n * d + ax, dw0[ax]);
         break;
       }
-      tmem_st_wait();
-      // Y_{t-1} (all channels) back from scratch as the MN-major B operand of the weight-gradient GEMM
+      // gZ -> shared memory (B operand of the backward-data GEMM) and TMEM (A operand of the weight-gradient GEMM);
+      // Y_{t-1} -> shared memory as the MN-major B operand of the weight-gradient GEMM.  All hi / lo tf32 pairs.
       {
-        const float* yprev = my_scratch + (size_t)(2 * (t - 1)) * save_block;
-        for (int idx = tid; idx < PJ * kTcSavePitch; idx += kTcThreads) {
-          const int r = idx / kTcSavePitch, k = idx - r * kTcSavePitch;
-          if (k < W) split_store(sm.a_hi, sm.a_lo, sw_off_mn(r, k, kTcCols), yprev[idx]);
+        float ghi[24], glo[24];
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+          const float g = live ? gz[j] : 0.f;
+          uint32_t hb;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(g));
+          ghi[j] = __uint_as_float(hb);
+          glo[j] = g - ghi[j];
         }
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < C; ++j) {
+            const int o = sw_off(col0 + j, n, kTcCols);
+            sm.b_hi[o] = ghi[j];
+            sm.b_lo[o] = glo[j];
+            split_store(sm.a_hi, sm.a_lo, sw_off_mn(col0 + j, n, kTcCols), yk[t - 1][j]);
+          }
+        }
+        tmem_st_cols<C>(t_lane + kTmAHi + (uint32_t)col0, ghi);
+        tmem_st_cols<C>(t_lane + kTmALo + (uint32_t)col0, glo);
+        tmem_st_wait();
       }
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
       if (tid == 0) {
+        mbar_wait(sm.wbar, wphase); wphase ^= 1;        // W_t^T image has landed
         tc_fence_after();
         issue_wgrad(tmem + kTmDw + (uint32_t)(t - 1) * kTmDwCols, tmem + kTmAHi, tmem + kTmALo, sm.a_hi, sm.a_lo,
                     dw_started);
-        issue_forward(tmem + kTmD, sm.w_hi, sm.w_lo, sm.b_hi, sm.b_lo, ksteps);   // A = W_t^T image
+        issue_forward(tmem + kTmDb, sm.w_hi, sm.w_lo, sm.b_hi, sm.b_lo, ksteps);   // A = W_t^T image
         umma_commit(sm.bar);
       }
       mbar_wait(sm.bar, phase);
       phase ^= 1;
       tc_fence_after();
+      if (tid == 0) {                                   // next image: W_{t-1}^T, or W_1 for the next tile
+        const float* nxt = t > 1 ? wimg + (size_t)(t - 2) * 4 * kTcWFloats + 2 * kTcWFloats : wimg;
+        bulk_load_image(sm.w_hi, nxt, sm.wbar);
+      }
     }
     dw_started = 1;
     tc_fence_before();
@@ -573,6 +636,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
   }
 
   // ---- flush: dW accumulators (TMEM) and per-CTA scalars ----------------------------------------------
+  if (tid == 0) { mbar_wait(sm.wbar, wphase); wphase ^= 1; }   // drain the last prefetch before exiting
   __syncthreads();
   tc_fence_after();
   if (a.do_grad && dw_started) {
@@ -589,21 +653,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
     }
   }
   if (tid < a.n_slots) a.part_loss[(size_t)blockIdx.x * a.n_slots + tid] = sm.lossS[tid];
-  if (a.do_grad && tid < a.n_cparams) my_grad[a.n_net_params + tid] = sm.cgS[tid];   // warp 0 -> half 0 row
+  if (a.do_grad && tid < a.n_cparams) my_grad[a.n_net_params + tid] = sm.cgS[tid];   // warp 0 -> half-0 row
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
 }
 
-cudaError_t launch_jet_tc(const JetArgs& a, const float* wimg, int grid, cudaStream_t s) {
+// ------------------------------------------------------------------------------------------------
+// dispatch on the jet signature
+// ------------------------------------------------------------------------------------------------
+template <int O0, int O1, int O2>
+static cudaError_t launch_sig(const JetArgs& a, const float* wimg, int grid, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(jet_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(jet_tc_kernel<O0, O1, O2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kTcSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  jet_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, s>>>(a, wimg);
+  jet_tc_kernel<O0, O1, O2><<<grid, kTcThreads, kTcSmemBytes, s>>>(a, wimg);
   return cudaGetLastError();
+}
+
+#define TDB_TC_SIGS(X) \
+  X(0, 0, 0) X(1, 0, 0) X(2, 0, 0) X(3, 0, 0) X(4, 0, 0) \
+  X(1, 1, 0) X(2, 1, 0) X(1, 2, 0) X(2, 2, 0) X(3, 1, 0) X(1, 3, 0) X(3, 2, 0) X(2, 3, 0) X(4, 1, 0) X(1, 4, 0) \
+  X(4, 2, 0) X(2, 4, 0) X(3, 3, 0) X(1, 1, 1) X(2, 1, 1) X(2, 2, 1) X(2, 2, 2)
+
+bool jet_tc_supports(int o0, int o1, int o2) {
+#define X(A, B, Cc) if (o0 == A && o1 == B && o2 == Cc) return true;
+  TDB_TC_SIGS(X)
+#undef X
+  return false;
+}
+int jet_tc_points_per_tile(int o0, int o1, int o2) { return 2 * (24 / (1 + o0 + o1 + o2)); }
+
+cudaError_t launch_jet_tc(const JetArgs& a, const float* wimg, int o0, int o1, int o2, int grid, cudaStream_t s) {
+#define X(A, B, Cc) if (o0 == A && o1 == B && o2 == Cc) return launch_sig<A, B, Cc>(a, wimg, grid, s);
+  TDB_TC_SIGS(X)
+#undef X
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace tdb
