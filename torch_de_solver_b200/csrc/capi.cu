@@ -210,7 +210,7 @@ int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_s
       if ((rc = upload<float>(&p->tc_scratch, nullptr, (size_t)p->tc_grid * p->tc_scratch_per_cta))) { tdb200_plan_destroy(p); return rc; }
     }
   }
-  p->grad_rows = p->grid + 2 * p->tc_grid + p->simt_rest_grid;
+  p->grad_rows = p->grid + tdb::jet_tc_partial_rows() * p->tc_grid + p->simt_rest_grid;
   p->loss_rows = p->grid + p->tc_grid + p->simt_rest_grid;
   if ((rc = upload<float>(&p->arena, nullptr, a.n_params_pad))) { tdb200_plan_destroy(p); return rc; }
   if ((rc = upload<float>(&p->arena_t, nullptr, a.n_params_pad))) { tdb200_plan_destroy(p); return rc; }
@@ -335,7 +335,7 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
     tc.scratch = p->tc_scratch;
     tc.scratch_per_cta = p->tc_scratch_per_cta;
     CU(tdb::launch_jet_tc(tc, p->wimg, p->tc_sig[0], p->tc_sig[1], p->tc_sig[2], p->tc_grid, s));
-    grad_rows = 2 * p->tc_grid;
+    grad_rows = tdb::jet_tc_partial_rows() * p->tc_grid;
     loss_rows = p->tc_grid;
     if (p->simt_rest_tiles > 0) {
       tdb::JetArgs rest = call;

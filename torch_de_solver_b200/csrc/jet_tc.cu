@@ -18,7 +18,8 @@
 
 namespace tdb {
 
-constexpr int kTcThreads = 256;
+constexpr int kTcThreads = 512;                  // 16 warps: 4 lane windows x 4 column parts
+constexpr int kTcParts = 4;
 constexpr int kTcCols = 48;                      // (point, channel) columns per tile = MMA N
 constexpr int kTcWRows = 104;                    // rows of the weight image (neurons padded to 8)
 constexpr int kTcActBlock = kTcCols * 32;        // floats per k-block of an activation operand
@@ -182,20 +183,25 @@ __device__ __forceinline__ void split_store(float* hi_buf, float* lo_buf, int of
 // ------------------------------------------------------------------------------------------------
 // MMA issue helpers (one thread).  All operand buffers are 1024-byte aligned.
 // ------------------------------------------------------------------------------------------------
-// D[128 x 48] (+)= A(W image, K-major) . B(act, K-major), 3xTF32
+// D[128 x 48] (+)= A(W image, K-major) . B(act, K-major), 3xTF32.  Fully unrolled: descriptor offsets are immediates.
 __device__ __forceinline__ void issue_forward(uint32_t d_tmem, const float* w_hi, const float* w_lo,
                                               const float* b_hi, const float* b_lo, int ksteps) {
   constexpr uint32_t idesc = umma_idesc(128, kTcCols, 0, 0);
-  const uint32_t wa = smem_u32(w_hi), wl = smem_u32(w_lo), ba = smem_u32(b_hi), bl = smem_u32(b_lo);
+  const uint64_t dwh = umma_desc(smem_u32(w_hi), 16, 1024), dwl = umma_desc(smem_u32(w_lo), 16, 1024);
+  const uint64_t dbh = umma_desc(smem_u32(b_hi), 16, 1024), dbl = umma_desc(smem_u32(b_lo), 16, 1024);
   uint32_t acc = 0;
+#pragma unroll
   for (int pass = 0; pass < 3; ++pass) {
-    const uint32_t A = pass == 0 ? wl : wa;          // lo*hi, hi*lo, hi*hi
-    const uint32_t B = pass == 1 ? bl : ba;
-    for (int s = 0; s < ksteps; ++s) {
-      const uint32_t ao = (uint32_t)(s >> 2) * kTcWBlock * 4 + (uint32_t)(s & 3) * 32;
-      const uint32_t bo = (uint32_t)(s >> 2) * kTcActBlock * 4 + (uint32_t)(s & 3) * 32;
-      umma_tf32(d_tmem, umma_desc(A + ao, 16, 1024), umma_desc(B + bo, 16, 1024), idesc, acc);
-      acc = 1;
+    const uint64_t A = pass == 0 ? dwl : dwh;        // lo*hi, hi*lo, hi*hi
+    const uint64_t B = pass == 1 ? dbl : dbh;
+#pragma unroll
+    for (int s = 0; s < 13; ++s) {
+      if (s < ksteps) {
+        const uint64_t ao = ((uint64_t)(s >> 2) * kTcWBlock * 4 + (uint64_t)(s & 3) * 32) >> 4;
+        const uint64_t bo = ((uint64_t)(s >> 2) * kTcActBlock * 4 + (uint64_t)(s & 3) * 32) >> 4;
+        umma_tf32(d_tmem, A + ao, B + bo, idesc, acc);
+        acc = 1;
+      }
     }
   }
 }
@@ -203,14 +209,16 @@ __device__ __forceinline__ void issue_forward(uint32_t d_tmem, const float* w_hi
 __device__ __forceinline__ void issue_wgrad(uint32_t d_tmem, uint32_t a_hi_tmem, uint32_t a_lo_tmem,
                                             const float* y_hi, const float* y_lo, uint32_t accumulate) {
   constexpr uint32_t idesc = umma_idesc(128, 112, 0, 1);
-  const uint32_t ya = smem_u32(y_hi), yl = smem_u32(y_lo);
+  // 8 (pc) rows = two 4-row swizzle atoms (SBO = 512 B); MN blocks of 32 k at LBO = one k-block
+  const uint64_t dyh = umma_desc(smem_u32(y_hi), kTcActBlock * 4, 512, 1), dyl = umma_desc(smem_u32(y_lo), kTcActBlock * 4, 512, 1);
   uint32_t acc = accumulate;
+#pragma unroll
   for (int pass = 0; pass < 3; ++pass) {
     const uint32_t A = pass == 0 ? a_lo_tmem : a_hi_tmem;
-    const uint32_t B = pass == 1 ? yl : ya;
+    const uint64_t B = pass == 1 ? dyl : dyh;
+#pragma unroll
     for (int s = 0; s < kTcCols / 8; ++s) {
-      // 8 (pc) rows = two 4-row swizzle atoms (SBO = 512 B); MN blocks of 32 k at LBO = one k-block
-      umma_tf32_ts(d_tmem, A + (uint32_t)s * 8, umma_desc(B + (uint32_t)s * 1024, kTcActBlock * 4, 512, 1), idesc, acc);
+      umma_tf32_ts(d_tmem, A + (uint32_t)s * 8, B + (uint64_t)(s * 1024 >> 4), idesc, acc);
       acc = 1;
     }
   }
@@ -242,11 +250,10 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// 24 consecutive columns of this warp's lane window
-__device__ __forceinline__ void tmem_ld24(uint32_t taddr, float* v) {
+// 16 consecutive columns of this warp's lane window (a part owns at most 12 of them)
+__device__ __forceinline__ void tmem_ld16w(uint32_t taddr, float* v) {
   tmem_ld8_nowait(taddr, v);
   tmem_ld8_nowait(taddr + 8, v + 8);
-  tmem_ld8_nowait(taddr + 16, v + 16);
   tmem_ld_wait();
 }
 // exactly C (compile time, <= 24) columns
@@ -292,7 +299,7 @@ struct TcSmem {
   float *w_hi, *w_lo, *a_hi, *a_lo, *b_hi, *b_lo;
   float *xS, *uS, *guS, *uP, *wlS, *cgS;
   double* lossS;
-  uint64_t *bar, *wbar;
+  uint64_t *bar, *wbar, *gbar;
   uint32_t* tmem_ptr;
 };
 constexpr size_t kTcSmemBytes = (size_t)(2 * kTcWFloats + 4 * kTcActFloats) * 4 + 1024 /*align*/ +
@@ -302,13 +309,14 @@ constexpr size_t kTcSmemBytes = (size_t)(2 * kTcWFloats + 4 * kTcActFloats) * 4 
 size_t jet_tc_smem_bytes() { return kTcSmemBytes; }
 
 // Jet signature: derivative orders of up to three directions (sorted by input axis); J = 1 + O0 + O1 + O2.
-template <int O0, int O1, int O2>
+template <int O0, int O1, int O2, int NMMA>
 __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, const float* __restrict__ wimg) {
   constexpr int J = 1 + O0 + O1 + O2;
   constexpr int ND = (O0 > 0) + (O1 > 0) + (O2 > 0);
-  constexpr int PH = 24 / J;                   // points per half tile
-  constexpr int P = 2 * PH;                    // points per tile
-  constexpr int C = PH * J;                    // columns per half (<= 24)
+  constexpr int PH = 12 / J;                   // points per column part
+  constexpr int P = kTcParts * PH;             // points per tile
+  constexpr int C = PH * J;                    // columns per part (<= 12)
+  constexpr int n_mma = NMMA;                  // W x W layers (1 or 2)
   constexpr int ORD[3] = {O0, O1, O2};
   extern __shared__ uint8_t smem_raw_tc[];
   TcSmem sm;
@@ -330,27 +338,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
     sm.lossS = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(f) + 15) & ~uintptr_t(15));
     sm.bar = reinterpret_cast<uint64_t*>(sm.lossS + 32);
     sm.wbar = sm.bar + 1;
-    sm.tmem_ptr = reinterpret_cast<uint32_t*>(sm.wbar + 1);
+    sm.gbar = sm.bar + 2;
+    sm.tmem_ptr = reinterpret_cast<uint32_t*>(sm.bar + 3);
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = (warp & 3) * 32 + lane;                 // neuron = TMEM lane owned by this thread
-  const int half = warp >> 2;                           // which half of the tile's points
+  const int half = warp >> 2;                           // which column part (0..3) of the tile this thread owns
   const int L = a.n_layers, W = a.widths[1], n_out = a.widths[L], d = a.d;
-  const int n_mma = L - 2;                              // 1 or 2
   const int ksteps = (W + 7) / 8;
   const bool live = n < W;
   const int col0 = half * C;                            // first (point, channel) column of this thread
-  // two gradient-partial rows per CTA (one per half): a single owner thread per address -> bit-reproducible
-  float* const my_grad = a.part_grad + ((size_t)blockIdx.x * 2 + half) * a.n_params_pad;
+  // one gradient-partial row per column part: a single owner thread per address -> bit-reproducible
+  float* const my_grad = a.part_grad + ((size_t)blockIdx.x * kTcParts + half) * a.n_params_pad;
 
   // ---- one-time setup --------------------------------------------------------------------------------
-  for (int i = tid; i < 2 * a.n_params_pad; i += kTcThreads)
-    a.part_grad[(size_t)blockIdx.x * 2 * a.n_params_pad + i] = 0.f;
+  for (int i = tid; i < kTcParts * a.n_params_pad; i += kTcThreads)
+    a.part_grad[(size_t)blockIdx.x * kTcParts * a.n_params_pad + i] = 0.f;
   for (int i = tid; i < 4 * kTcActFloats; i += kTcThreads) sm.a_hi[i] = 0.f;      // pad rows / columns stay zero
   if (tid < 32) sm.lossS[tid] = 0.0;
   if (tid < kMaxCParams) sm.cgS[tid] = 0.f;
   for (int i = tid; i < n_out * W; i += kTcThreads) sm.wlS[(i / W) * kTcSavePitch + i % W] = a.arena[a.w_off[L - 1] + i];
-  if (tid == 0) { mbar_init(sm.bar, 1); mbar_init(sm.wbar, 1); }
+  if (tid == 0) { mbar_init(sm.bar, 1); mbar_init(sm.wbar, 1); mbar_init(sm.gbar, 1); }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(sm.tmem_ptr)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -367,7 +375,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       for (uint32_t c = kTmAHi; c < kTmDw; c += 8) { tmem_st4(t_lane + c, z8); tmem_st4(t_lane + c + 4, z8); }
     tmem_st_wait();
   }
-  uint32_t phase = 0, wphase = 0;                       // wphase is only used by thread 0
+  uint32_t phase = 0, wphase = 0, gphase = 0;           // wphase is only used by thread 0
+  bool wgrad_pending = false;                           // weight-gradient MMAs still reading TMEM A / Y operand
   uint32_t dw_started = 0;
   // per-layer parameters this thread needs all the time
   float bias[3] = {0.f, 0.f, 0.f}, w0[4] = {0.f, 0.f, 0.f, 0.f}, wl[kMaxOut];
@@ -394,7 +403,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
     }
     __syncthreads();
 
-    float yk[3][24];                                    // outputs of tanh layers 0..n_mma for this thread's columns
+    float yk[NMMA + 1][12];                             // outputs of tanh layers 0..n_mma for this thread's columns
 
     // ---- layer 0 (K = d): thread-local ----------------------------------------------------------------
 #pragma unroll
@@ -414,12 +423,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
         c += ORD[i];
       }
     }
+    if (wgrad_pending) { mbar_wait(sm.gbar, gphase); gphase ^= 1; wgrad_pending = false; }   // Y operand is free again
     if (live) {
 #pragma unroll
       for (int j = 0; j < C; ++j) split_store(sm.a_hi, sm.a_lo, sw_off(col0 + j, n, kTcCols), yk[0][j]);
     }
 
     // ---- W x W layers: tensor-core GEMM + thread-local tanh-jet epilogue ------------------------------
+#pragma unroll
     for (int l = 1; l <= n_mma; ++l) {
       fence_async_smem();
       tc_fence_before();
@@ -436,8 +447,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       // next image (W_{l+1}, or W_{n_mma}^T for the backward sweep) streams in behind the epilogue
       if (tid == 0)
         bulk_load_image(sm.w_hi, wimg + (size_t)(l < n_mma ? l : n_mma - 1) * 4 * kTcWFloats + (l < n_mma ? 0 : 2 * kTcWFloats), sm.wbar);
-      float z[24];
-      tmem_ld24(t_lane + kTmZ + 48u * (uint32_t)(l - 1) + (uint32_t)col0, z);
+      float z[16];
+      tmem_ld16w(t_lane + kTmZ + 48u * (uint32_t)(l - 1) + (uint32_t)col0, z);
 #pragma unroll
       for (int p = 0; p < PH; ++p) {
         const float av = tanh_acc(z[p * J] + bias[l]);
@@ -468,8 +479,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       if (lane < C) sm.uP[((warp & 3) * kMaxOut + v) * kTcCols + col0 + lane] = tot;
     }
     __syncthreads();
-    for (int idx = tid; idx < n_out * 2 * C; idx += kTcThreads) {
-      const int v = idx / (2 * C), r = idx - v * (2 * C);
+    for (int idx = tid; idx < n_out * kTcParts * C; idx += kTcThreads) {
+      const int v = idx / (kTcParts * C), r = idx - v * (kTcParts * C);
       float s = (r % J) == 0 ? a.arena[a.b_off[L - 1] + v] : 0.f;
 #pragma unroll
       for (int w = 0; w < 4; ++w) s += sm.uP[(w * kMaxOut + v) * kTcCols + r];
@@ -530,14 +541,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
     }
 
     // ---- backward of the last layer: dWl, dbl; gY of the last tanh layer ---------------------------------
-    if (tid < n_out) {                                   // warp 0 -> half-0 row
+    if (tid < n_out) {                                   // warp 0 -> part-0 row
       float s = 0.f;
       for (int p = 0; p < P; ++p) s += sm.guS[tid * kTcCols + p * J];
       atomicAdd(my_grad + a.b_off[L - 1] + tid, s);
     }
-    float gy[24];
+    float gy[16];
 #pragma unroll
-    for (int j = 0; j < 24; ++j) gy[j] = 0.f;
+    for (int j = 0; j < 16; ++j) gy[j] = 0.f;
     for (int v = 0; v < n_out; ++v) {
       float s = 0.f;
 #pragma unroll
@@ -550,11 +561,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
     }
 
     // ---- backward sweep over the tanh layers t = n_mma .. 0 ------------------------------------------
+#pragma unroll
     for (int t = n_mma; t >= 0; --t) {
-      float z[24];
-      if (t > 0) tmem_ld24(t_lane + kTmZ + 48u * (uint32_t)(t - 1) + (uint32_t)col0, z);
-      if (t < n_mma) tmem_ld24(t_lane + kTmDb + (uint32_t)col0, gy);
-      float gz[24];
+      float z[16];
+      if (t > 0) tmem_ld16w(t_lane + kTmZ + 48u * (uint32_t)(t - 1) + (uint32_t)col0, z);
+      if (t < n_mma) tmem_ld16w(t_lane + kTmDb + (uint32_t)col0, gy);
+      float gz[12];
       float db = 0.f, dw0[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int p = 0; p < PH; ++p) {
@@ -588,8 +600,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       }
       // gZ -> shared memory (B operand of the backward-data GEMM) and TMEM (A operand of the weight-gradient GEMM);
       // Y_{t-1} -> shared memory as the MN-major B operand of the weight-gradient GEMM.  All hi / lo tf32 pairs.
+      if (wgrad_pending) { mbar_wait(sm.gbar, gphase); gphase ^= 1; wgrad_pending = false; tc_fence_after(); }
       {
-        float ghi[24], glo[24];
+        float ghi[12], glo[12];
 #pragma unroll
         for (int j = 0; j < C; ++j) {
           const float g = live ? gz[j] : 0.f;
@@ -617,11 +630,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       if (tid == 0) {
         mbar_wait(sm.wbar, wphase); wphase ^= 1;        // W_t^T image has landed
         tc_fence_after();
-        issue_wgrad(tmem + kTmDw + (uint32_t)(t - 1) * kTmDwCols, tmem + kTmAHi, tmem + kTmALo, sm.a_hi, sm.a_lo,
-                    dw_started);
         issue_forward(tmem + kTmDb, sm.w_hi, sm.w_lo, sm.b_hi, sm.b_lo, ksteps);   // A = W_t^T image
         umma_commit(sm.bar);
+        // the weight gradient is not on the critical path: it runs behind the next adjoint epilogue
+        issue_wgrad(tmem + kTmDw + (uint32_t)(t - 1) * kTmDwCols, tmem + kTmAHi, tmem + kTmALo, sm.a_hi, sm.a_lo,
+                    dw_started);
+        umma_commit(sm.gbar);
       }
+      wgrad_pending = true;
       mbar_wait(sm.bar, phase);
       phase ^= 1;
       tc_fence_after();
@@ -637,13 +653,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
 
   // ---- flush: dW accumulators (TMEM) and per-CTA scalars ----------------------------------------------
   if (tid == 0) { mbar_wait(sm.wbar, wphase); wphase ^= 1; }   // drain the last prefetch before exiting
+  if (wgrad_pending) { mbar_wait(sm.gbar, gphase); gphase ^= 1; wgrad_pending = false; }
   __syncthreads();
   tc_fence_after();
   if (a.do_grad && dw_started) {
-    float* row0 = a.part_grad + (size_t)blockIdx.x * 2 * a.n_params_pad;       // dW lives in the half-0 row
+    float* row0 = a.part_grad + (size_t)blockIdx.x * kTcParts * a.n_params_pad;   // dW lives in the part-0 row
     for (int t = 1; t <= n_mma; ++t) {
       float* dst = row0 + a.w_off[t];
-      for (int k0 = half * 56; k0 < half * 56 + 56; k0 += 8) {
+      for (int k0 = half * 32; k0 < half * 32 + 32 && k0 < (int)kTmDwCols; k0 += 8) {
         float v[8];
         tmem_ld8(t_lane + kTmDw + (uint32_t)(t - 1) * kTmDwCols + (uint32_t)k0, v);
         if (live)
@@ -662,16 +679,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
 // ------------------------------------------------------------------------------------------------
 // dispatch on the jet signature
 // ------------------------------------------------------------------------------------------------
-template <int O0, int O1, int O2>
+template <int O0, int O1, int O2, int NMMA>
 static cudaError_t launch_sig(const JetArgs& a, const float* wimg, int grid, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(jet_tc_kernel<O0, O1, O2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(jet_tc_kernel<O0, O1, O2, NMMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kTcSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  jet_tc_kernel<O0, O1, O2><<<grid, kTcThreads, kTcSmemBytes, s>>>(a, wimg);
+  jet_tc_kernel<O0, O1, O2, NMMA><<<grid, kTcThreads, kTcSmemBytes, s>>>(a, wimg);
   return cudaGetLastError();
 }
 
@@ -686,10 +703,14 @@ bool jet_tc_supports(int o0, int o1, int o2) {
 #undef X
   return false;
 }
-int jet_tc_points_per_tile(int o0, int o1, int o2) { return 2 * (24 / (1 + o0 + o1 + o2)); }
+int jet_tc_points_per_tile(int o0, int o1, int o2) { return kTcParts * (12 / (1 + o0 + o1 + o2)); }
+int jet_tc_partial_rows() { return kTcParts; }
 
 cudaError_t launch_jet_tc(const JetArgs& a, const float* wimg, int o0, int o1, int o2, int grid, cudaStream_t s) {
-#define X(A, B, Cc) if (o0 == A && o1 == B && o2 == Cc) return launch_sig<A, B, Cc>(a, wimg, grid, s);
+  const int n_mma = a.n_layers - 2;
+#define X(A, B, Cc)                                                            \
+  if (o0 == A && o1 == B && o2 == Cc)                                          \
+    return n_mma == 1 ? launch_sig<A, B, Cc, 1>(a, wimg, grid, s) : launch_sig<A, B, Cc, 2>(a, wimg, grid, s);
   TDB_TC_SIGS(X)
 #undef X
   return cudaErrorInvalidValue;
