@@ -1,6 +1,7 @@
 // C ABI of libtedeous_b200.so - plan management and launch sequencing for the NN / autograd path.
 // See include/tdb200.h for the contract and the reference interfaces every entry replaces.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -334,7 +335,19 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
     tc.n_tiles = p->tc_tiles;
     tc.scratch = p->tc_scratch;
     tc.scratch_per_cta = p->tc_scratch_per_cta;
+    long long* dbg = nullptr;
+    if (getenv("TDB200_TC_TIMING")) { cudaMalloc(&dbg, sizeof(long long) * 16 * p->tc_grid); }
+    tc.dbg = dbg;
     CU(tdb::launch_jet_tc(tc, p->wimg, p->tc_sig[0], p->tc_sig[1], p->tc_sig[2], p->tc_grid, s));
+    if (dbg) {
+      std::vector<long long> h(16 * p->tc_grid);
+      cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+      cudaFree(dbg);
+      const int tiles_per_cta = (p->tc_tiles + p->tc_grid - 1) / p->tc_grid;
+      fprintf(stderr, "[tdb200 tc timing] cycles per tile (thread 0 of CTA 0, %d tiles):", tiles_per_cta);
+      for (int i = 0; i < 13; ++i) fprintf(stderr, " p%d=%lld", i, h[i] / tiles_per_cta);
+      fprintf(stderr, "\n");
+    }
     grad_rows = tdb::jet_tc_partial_rows() * p->tc_grid;
     loss_rows = p->tc_grid;
     if (p->simt_rest_tiles > 0) {

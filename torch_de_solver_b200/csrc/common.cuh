@@ -49,6 +49,7 @@ struct JetArgs {
   long long scratch_per_cta;
   float* fields;                       // optional per-row operator values
   int do_grad;
+  long long* dbg;                      // optional [gridDim.x][16] phase cycle counters (TDB200_TC_TIMING=1)
 };
 
 struct PackArgs {

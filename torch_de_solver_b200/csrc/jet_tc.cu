@@ -95,6 +95,13 @@ __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int a_mn, int b_
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -183,27 +190,34 @@ __device__ __forceinline__ void split_store(float* hi_buf, float* lo_buf, int of
 // ------------------------------------------------------------------------------------------------
 // MMA issue helpers (one thread).  All operand buffers are 1024-byte aligned.
 // ------------------------------------------------------------------------------------------------
-// D[128 x 48] (+)= A(W image, K-major) . B(act, K-major), 3xTF32.  Fully unrolled: descriptor offsets are immediates.
+// The issue helpers are called by every lane of one warp (warp-uniform control flow keeps the descriptors in
+// uniform registers); each tcgen05.mma itself is issued by the elected lane.
+// D[128 x 48] (+)= A(W image, K-major) . B(act, K-major), 3xTF32.  KS = K-steps of 8 (compile time).
+template <int KS>
 __device__ __forceinline__ void issue_forward(uint32_t d_tmem, const float* w_hi, const float* w_lo,
-                                              const float* b_hi, const float* b_lo, int ksteps) {
+                                              const float* b_hi, const float* b_lo) {
   constexpr uint32_t idesc = umma_idesc(128, kTcCols, 0, 0);
   const uint64_t dwh = umma_desc(smem_u32(w_hi), 16, 1024), dwl = umma_desc(smem_u32(w_lo), 16, 1024);
   const uint64_t dbh = umma_desc(smem_u32(b_hi), 16, 1024), dbl = umma_desc(smem_u32(b_lo), 16, 1024);
-  uint32_t acc = 0;
+  const bool leader = elect_one();
 #pragma unroll
   for (int pass = 0; pass < 3; ++pass) {
     const uint64_t A = pass == 0 ? dwl : dwh;        // lo*hi, hi*lo, hi*hi
     const uint64_t B = pass == 1 ? dbl : dbh;
 #pragma unroll
-    for (int s = 0; s < 13; ++s) {
-      if (s < ksteps) {
-        const uint64_t ao = ((uint64_t)(s >> 2) * kTcWBlock * 4 + (uint64_t)(s & 3) * 32) >> 4;
-        const uint64_t bo = ((uint64_t)(s >> 2) * kTcActBlock * 4 + (uint64_t)(s & 3) * 32) >> 4;
-        umma_tf32(d_tmem, A + ao, B + bo, idesc, acc);
-        acc = 1;
-      }
+    for (int s = 0; s < KS; ++s) {
+      const uint64_t ao = ((uint64_t)(s >> 2) * kTcWBlock * 4 + (uint64_t)(s & 3) * 32) >> 4;
+      const uint64_t bo = ((uint64_t)(s >> 2) * kTcActBlock * 4 + (uint64_t)(s & 3) * 32) >> 4;
+      if (leader) umma_tf32(d_tmem, A + ao, B + bo, idesc, (pass | s) ? 1u : 0u);
     }
   }
+}
+__device__ __forceinline__ void issue_forward_any(uint32_t d_tmem, const float* w_hi, const float* w_lo,
+                                                  const float* b_hi, const float* b_lo, int ksteps) {
+  if (ksteps == 13) issue_forward<13>(d_tmem, w_hi, w_lo, b_hi, b_lo);
+  else if (ksteps <= 4) issue_forward<4>(d_tmem, w_hi, w_lo, b_hi, b_lo);     // zero-padded images: extra steps add 0
+  else if (ksteps <= 8) issue_forward<8>(d_tmem, w_hi, w_lo, b_hi, b_lo);
+  else issue_forward<13>(d_tmem, w_hi, w_lo, b_hi, b_lo);
 }
 // dW[128 (n) x 112 (k)] += A(gZ in TMEM: lanes n, columns (pc)) . B(Y in smem read MN-major: N = k, K = (pc))
 __device__ __forceinline__ void issue_wgrad(uint32_t d_tmem, uint32_t a_hi_tmem, uint32_t a_lo_tmem,
@@ -211,16 +225,14 @@ __device__ __forceinline__ void issue_wgrad(uint32_t d_tmem, uint32_t a_hi_tmem,
   constexpr uint32_t idesc = umma_idesc(128, 112, 0, 1);
   // 8 (pc) rows = two 4-row swizzle atoms (SBO = 512 B); MN blocks of 32 k at LBO = one k-block
   const uint64_t dyh = umma_desc(smem_u32(y_hi), kTcActBlock * 4, 512, 1), dyl = umma_desc(smem_u32(y_lo), kTcActBlock * 4, 512, 1);
-  uint32_t acc = accumulate;
+  const bool leader = elect_one();
 #pragma unroll
   for (int pass = 0; pass < 3; ++pass) {
     const uint32_t A = pass == 0 ? a_lo_tmem : a_hi_tmem;
     const uint64_t B = pass == 1 ? dyl : dyh;
 #pragma unroll
-    for (int s = 0; s < kTcCols / 8; ++s) {
-      umma_tf32_ts(d_tmem, A + (uint32_t)s * 8, B + (uint64_t)(s * 1024 >> 4), idesc, acc);
-      acc = 1;
-    }
+    for (int s = 0; s < kTcCols / 8; ++s)
+      if (leader) umma_tf32_ts(d_tmem, A + (uint32_t)s * 8, B + (uint64_t)(s * 1024 >> 4), idesc, (pass | s) ? 1u : accumulate);
   }
 }
 
@@ -375,7 +387,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       for (uint32_t c = kTmAHi; c < kTmDw; c += 8) { tmem_st4(t_lane + c, z8); tmem_st4(t_lane + c + 4, z8); }
     tmem_st_wait();
   }
-  uint32_t phase = 0, wphase = 0, gphase = 0;           // wphase is only used by thread 0
+  long long tacc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) tacc[i] = 0;
+  long long tlast = clock64();
+#define TMARK(i) do { if (a.dbg) { const long long tn_ = clock64(); tacc[i] += tn_ - tlast; tlast = tn_; } } while (0)
+  uint32_t phase = 0, wphase = 0, gphase = 0;           // wphase is only used by warp 0
   bool wgrad_pending = false;                           // weight-gradient MMAs still reading TMEM A / Y operand
   uint32_t dw_started = 0;
   // per-layer parameters this thread needs all the time
@@ -402,6 +419,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       sm.xS[p * 4 + ax] = p < p_valid ? __ldg(a.pts + (size_t)(sg.pts_off + g_first + p) * d + ax) : 0.f;
     }
     __syncthreads();
+    TMARK(0);
 
     float yk[NMMA + 1][12];                             // outputs of tanh layers 0..n_mma for this thread's columns
 
@@ -435,15 +453,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      TMARK(1);
+      if (warp == 0) {
         mbar_wait(sm.wbar, wphase); wphase ^= 1;        // W_l image has landed
+        TMARK(2);
         tc_fence_after();
-        issue_forward(tmem + kTmZ + 48u * (uint32_t)(l - 1), sm.w_hi, sm.w_lo, sm.a_hi, sm.a_lo, ksteps);
-        umma_commit(sm.bar);
+        issue_forward_any(tmem + kTmZ + 48u * (uint32_t)(l - 1), sm.w_hi, sm.w_lo, sm.a_hi, sm.a_lo, ksteps);
+        if (elect_one()) umma_commit(sm.bar);
+        __syncwarp();
+        TMARK(3);
       }
       mbar_wait(sm.bar, phase);
       phase ^= 1;
       tc_fence_after();
+      TMARK(4);
       // next image (W_{l+1}, or W_{n_mma}^T for the backward sweep) streams in behind the epilogue
       if (tid == 0)
         bulk_load_image(sm.w_hi, wimg + (size_t)(l < n_mma ? l : n_mma - 1) * 4 * kTcWFloats + (l < n_mma ? 0 : 2 * kTcWFloats), sm.wbar);
@@ -470,6 +493,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       }
     }
 
+    TMARK(5);
     // ---- last layer: u[v][col] = sum_n Wl[v][n] y[n][col]  (warp multi-value reduction, fixed order) ------
     for (int v = 0; v < n_out; ++v) {
       float t32[32];
@@ -489,6 +513,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
     }
     __syncthreads();
 
+    TMARK(6);
     // ---- operator terms, residual, loss, adjoint seeds (one thread per point) -------------------------
     if (tid < p_valid) {
       const int p = tid;
@@ -536,10 +561,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
     __syncthreads();
     if (!a.do_grad) {
       // forward-only evaluation: the image prefetched for the backward sweep is not needed; fetch W_1 instead
-      if (tid == 0) { mbar_wait(sm.wbar, wphase); wphase ^= 1; bulk_load_image(sm.w_hi, wimg, sm.wbar); }
+      if (warp == 0) { mbar_wait(sm.wbar, wphase); wphase ^= 1; __syncwarp(); if (tid == 0) bulk_load_image(sm.w_hi, wimg, sm.wbar); }
       continue;
     }
 
+    TMARK(7);
     // ---- backward of the last layer: dWl, dbl; gY of the last tanh layer ---------------------------------
     if (tid < n_out) {                                   // warp 0 -> part-0 row
       float s = 0.f;
@@ -627,20 +653,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      TMARK(8);
+      if (warp == 0) {
         mbar_wait(sm.wbar, wphase); wphase ^= 1;        // W_t^T image has landed
+        TMARK(9);
         tc_fence_after();
-        issue_forward(tmem + kTmDb, sm.w_hi, sm.w_lo, sm.b_hi, sm.b_lo, ksteps);   // A = W_t^T image
-        umma_commit(sm.bar);
+        issue_forward_any(tmem + kTmDb, sm.w_hi, sm.w_lo, sm.b_hi, sm.b_lo, ksteps);   // A = W_t^T image
+        if (elect_one()) umma_commit(sm.bar);
+        __syncwarp();
         // the weight gradient is not on the critical path: it runs behind the next adjoint epilogue
         issue_wgrad(tmem + kTmDw + (uint32_t)(t - 1) * kTmDwCols, tmem + kTmAHi, tmem + kTmALo, sm.a_hi, sm.a_lo,
                     dw_started);
-        umma_commit(sm.gbar);
+        if (elect_one()) umma_commit(sm.gbar);
+        __syncwarp();
+        TMARK(10);
       }
       wgrad_pending = true;
       mbar_wait(sm.bar, phase);
       phase ^= 1;
       tc_fence_after();
+      TMARK(11);
       if (tid == 0) {                                   // next image: W_{t-1}^T, or W_1 for the next tile
         const float* nxt = t > 1 ? wimg + (size_t)(t - 2) * 4 * kTcWFloats + 2 * kTcWFloats : wimg;
         bulk_load_image(sm.w_hi, nxt, sm.wbar);
@@ -649,10 +681,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
     dw_started = 1;
     tc_fence_before();
     __syncthreads();
+    TMARK(12);
   }
+  if (a.dbg && tid == 0)
+    for (int i = 0; i < 16; ++i) a.dbg[(size_t)blockIdx.x * 16 + i] = tacc[i];
 
   // ---- flush: dW accumulators (TMEM) and per-CTA scalars ----------------------------------------------
-  if (tid == 0) { mbar_wait(sm.wbar, wphase); wphase ^= 1; }   // drain the last prefetch before exiting
+  if (warp == 0) { mbar_wait(sm.wbar, wphase); wphase ^= 1; }   // drain the last prefetch before exiting
   if (wgrad_pending) { mbar_wait(sm.gbar, gphase); gphase ^= 1; wgrad_pending = false; }
   __syncthreads();
   tc_fence_after();
