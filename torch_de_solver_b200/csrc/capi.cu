@@ -191,7 +191,10 @@ int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_s
     for (int l = 2; l < L; ++l) ok = ok && net->widths[l] == net->widths[1];
     for (int i = 0; i < 3; ++i) p->tc_sig[i] = i < s0.n_dirs ? s0.dir_order[i] : 0;
     ok = ok && s0.identity && s0.K == 1 && s0.n_dirs <= 3 && s0.n_groups > 0 &&
-         tdb::jet_tc_supports(p->tc_sig[0], p->tc_sig[1], p->tc_sig[2]);
+         tdb::jet_tc_supports(p->tc_sig[0], p->tc_sig[1], p->tc_sig[2]) &&
+         s0.col_term_end[s0.n_cols - 1] <= 48 && n_terms >= 0;
+    if (ok)   // every factor of the interior segment must sit in the first 96 entries (cached in shared memory)
+      for (int t = 0; t < s0.col_term_end[s0.n_cols - 1]; ++t) ok = ok && terms[t].fac_end <= 96;
     p->tc_eligible = ok;
     if (ok) {
       const int P = tdb::jet_tc_points_per_tile(p->tc_sig[0], p->tc_sig[1], p->tc_sig[2]);
@@ -233,6 +236,8 @@ int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_s
   a.seg_tile_begin = p->d_seg_tile_begin;
   a.terms = p->d_terms;
   a.factors = p->d_factors;
+  a.n_terms = n_terms;
+  a.n_factors = n_factors;
   a.comb = p->d_comb;
   a.slot_scale = p->d_slot_scale;
   a.part_grad = p->part_grad;

@@ -36,6 +36,7 @@ struct JetArgs {
   int n_tiles;
   const tdb200_term* terms;
   const tdb200_factor* factors;
+  int n_terms, n_factors;
   const float* comb;
   const float* pts;
   const float* targets;

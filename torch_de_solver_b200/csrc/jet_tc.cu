@@ -310,13 +310,17 @@ __device__ __forceinline__ void bulk_load_image(float* dst, const float* src, ui
 struct TcSmem {
   float *w_hi, *w_lo, *a_hi, *a_lo, *b_hi, *b_lo;
   float *xS, *uS, *guS, *uP, *wlS, *cgS;
+  tdb200_term* termS;
+  tdb200_factor* facS;
   double* lossS;
   uint64_t *bar, *wbar, *gbar;
   uint32_t* tmem_ptr;
 };
+constexpr int kTcMaxTerms = 48, kTcMaxFactors = 96;   // operator program cached in shared memory
 constexpr size_t kTcSmemBytes = (size_t)(2 * kTcWFloats + 4 * kTcActFloats) * 4 + 1024 /*align*/ +
-                                (kTcCols * 4 + 2 * kMaxOut * kTcCols + 4 * kMaxOut * kTcCols +
-                                 kMaxOut * kTcSavePitch + kMaxCParams) * 4 + 32 * 8 + 64;
+                                (2 * kTcCols * 4 + 2 * kMaxOut * kTcCols + 4 * kMaxOut * kTcCols +
+                                 kMaxOut * kTcSavePitch + kMaxCParams) * 4 + 32 * 8 + 64 +
+                                kTcMaxTerms * sizeof(tdb200_term) + kTcMaxFactors * sizeof(tdb200_factor) + 16;
 
 size_t jet_tc_smem_bytes() { return kTcSmemBytes; }
 
@@ -341,7 +345,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
     sm.a_lo = f; f += kTcActFloats;
     sm.b_hi = f; f += kTcActFloats;
     sm.b_lo = f; f += kTcActFloats;
-    sm.xS = f; f += kTcCols * 4;
+    sm.xS = f; f += 2 * kTcCols * 4;                   // double buffered: the next tile's points are prefetched
     sm.uS = f; f += kMaxOut * kTcCols;
     sm.guS = f; f += kMaxOut * kTcCols;
     sm.uP = f; f += 4 * kMaxOut * kTcCols;
@@ -352,6 +356,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
     sm.wbar = sm.bar + 1;
     sm.gbar = sm.bar + 2;
     sm.tmem_ptr = reinterpret_cast<uint32_t*>(sm.bar + 3);
+    sm.termS = reinterpret_cast<tdb200_term*>((reinterpret_cast<uintptr_t>(sm.tmem_ptr + 2) + 15) & ~uintptr_t(15));
+    sm.facS = reinterpret_cast<tdb200_factor*>(sm.termS + kTcMaxTerms);
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = (warp & 3) * 32 + lane;                 // neuron = TMEM lane owned by this thread
@@ -370,6 +376,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
   if (tid < 32) sm.lossS[tid] = 0.0;
   if (tid < kMaxCParams) sm.cgS[tid] = 0.f;
   for (int i = tid; i < n_out * W; i += kTcThreads) sm.wlS[(i / W) * kTcSavePitch + i % W] = a.arena[a.w_off[L - 1] + i];
+  for (int i = tid; i < min(kTcMaxTerms, a.n_terms); i += kTcThreads) sm.termS[i] = a.terms[i];
+  for (int i = tid; i < min(kTcMaxFactors, a.n_factors); i += kTcThreads) sm.facS[i] = a.factors[i];
   if (tid == 0) { mbar_init(sm.bar, 1); mbar_init(sm.wbar, 1); mbar_init(sm.gbar, 1); }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(sm.tmem_ptr)) : "memory");
@@ -411,14 +419,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
 
   if (tid == 0) bulk_load_image(sm.w_hi, wimg, sm.wbar);          // W_1 for the first tile
 
+  auto load_points = [&](int tile_idx, float* dst) {
+    const long long gf = (long long)tile_idx * P;
+    const int pv = (int)min((long long)P, sg.n_groups - gf);
+    for (int i = tid; i < P * d; i += kTcThreads) {
+      const int p = i / d, ax = i - p * d;
+      dst[p * 4 + ax] = p < pv ? __ldg(a.pts + (size_t)(sg.pts_off + gf + p) * d + ax) : 0.f;
+    }
+  };
+  load_points(blockIdx.x, sm.xS);
+  int xbuf = 0;
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const long long g_first = (long long)tile * P;
     const int p_valid = (int)min((long long)P, sg.n_groups - g_first);
-    for (int i = tid; i < P * d; i += kTcThreads) {
-      const int p = i / d, ax = i - p * d;
-      sm.xS[p * 4 + ax] = p < p_valid ? __ldg(a.pts + (size_t)(sg.pts_off + g_first + p) * d + ax) : 0.f;
-    }
-    __syncthreads();
+    float* const xcur = sm.xS + xbuf * kTcCols * 4;
+    __syncthreads();                                    // this tile's points (loaded one tile ahead) are visible
+    if (tile + (int)gridDim.x < a.n_tiles) load_points(tile + gridDim.x, sm.xS + (xbuf ^ 1) * kTcCols * 4);
+    xbuf ^= 1;
     TMARK(0);
 
     float yk[NMMA + 1][12];                             // outputs of tanh layers 0..n_mma for this thread's columns
@@ -427,7 +444,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
 #pragma unroll
     for (int p = 0; p < PH; ++p) {
       float z0 = bias[0];
-      for (int ax = 0; ax < d; ++ax) z0 = fmaf(w0[ax], sm.xS[(half * PH + p) * 4 + ax], z0);
+      for (int ax = 0; ax < d; ++ax) z0 = fmaf(w0[ax], xcur[(half * PH + p) * 4 + ax], z0);
       const float av = tanh_acc(z0);
       const TanhF f(av);
       yk[0][p * J] = av;
@@ -521,11 +538,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       for (int col = 0; col < ncols; ++col) {
         float val = 0.f;
         for (int t = sg.col_term_begin[col]; t < sg.col_term_end[col]; ++t) {
-          const tdb200_term tm = a.terms[t];
+          const tdb200_term tm = sm.termS[t];
           float prod = tm.kind == 0 ? tm.coeff : tm.kind == 1 ? __ldg(a.coeffs + tm.idx + row)
                                                                : a.arena[a.n_net_params + tm.idx];
           for (int fi = tm.fac_begin; fi < tm.fac_end; ++fi) {
-            const tdb200_factor fc = a.factors[fi];
+            const tdb200_factor fc = sm.facS[fi];
             prod *= pow_i(sm.uS[fc.var * kTcCols + p * J + fc.chan], fc.ipow, fc.pow);
           }
           val += prod;
@@ -538,17 +555,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
         if (!a.do_grad) continue;
         const float seed = 2.f * __ldg(a.slot_scale + slot) * res;
         for (int t = sg.col_term_begin[col]; t < sg.col_term_end[col]; ++t) {
-          const tdb200_term tm = a.terms[t];
+          const tdb200_term tm = sm.termS[t];
           const float cf = tm.kind == 0 ? tm.coeff : tm.kind == 1 ? __ldg(a.coeffs + tm.idx + row)
                                                                    : a.arena[a.n_net_params + tm.idx];
           float full = 1.f;
           for (int fi = tm.fac_begin; fi < tm.fac_end; ++fi) {
-            const tdb200_factor fc = a.factors[fi];
+            const tdb200_factor fc = sm.facS[fi];
             const float x = sm.uS[fc.var * kTcCols + p * J + fc.chan];
             float part = seed * cf * dpow_i(x, fc.ipow, fc.pow);
             for (int fj = tm.fac_begin; fj < tm.fac_end; ++fj) {
               if (fj == fi) continue;
-              const tdb200_factor fo = a.factors[fj];
+              const tdb200_factor fo = sm.facS[fj];
               part *= pow_i(sm.uS[fo.var * kTcCols + p * J + fo.chan], fo.ipow, fo.pow);
             }
             sm.guS[fc.var * kTcCols + p * J + fc.chan] += part;
@@ -617,7 +634,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
         gz[p * J] = g0;
         db += g0;
         if (t == 0)
-          for (int ax = 0; ax < d; ++ax) dw0[ax] = fmaf(g0, sm.xS[(half * PH + p) * 4 + ax], dw0[ax]);
+          for (int ax = 0; ax < d; ++ax) dw0[ax] = fmaf(g0, xcur[(half * PH + p) * 4 + ax], dw0[ax]);
       }
       if (live) atomicAdd(my_grad + a.b_off[t] + n, db);
       if (t == 0) {
