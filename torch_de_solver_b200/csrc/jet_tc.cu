@@ -312,6 +312,9 @@ struct TcSmem {
   float *xS, *uS, *guS, *uP, *wlS, *cgS;
   tdb200_term* termS;
   tdb200_factor* facS;
+  tdb200_segment* segS;
+  float* scaleS;          // [32] lambda / len per slot
+  double* lossT;          // [kTcCols][TDB200_MAX_COLS] per-point-thread loss accumulators (no atomics)
   double* lossS;
   uint64_t *bar, *wbar, *gbar;
   uint32_t* tmem_ptr;
@@ -320,7 +323,8 @@ constexpr int kTcMaxTerms = 48, kTcMaxFactors = 96;   // operator program cached
 constexpr size_t kTcSmemBytes = (size_t)(2 * kTcWFloats + 4 * kTcActFloats) * 4 + 1024 /*align*/ +
                                 (2 * kTcCols * 4 + 2 * kMaxOut * kTcCols + 4 * kMaxOut * kTcCols +
                                  kMaxOut * kTcSavePitch + kMaxCParams) * 4 + 32 * 8 + 64 +
-                                kTcMaxTerms * sizeof(tdb200_term) + kTcMaxFactors * sizeof(tdb200_factor) + 16;
+                                kTcMaxTerms * sizeof(tdb200_term) + kTcMaxFactors * sizeof(tdb200_factor) + 16 +
+                                sizeof(tdb200_segment) + 32 * 4 + kTcCols * TDB200_MAX_COLS * 8 + 32;
 
 size_t jet_tc_smem_bytes() { return kTcSmemBytes; }
 
@@ -358,6 +362,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
     sm.tmem_ptr = reinterpret_cast<uint32_t*>(sm.bar + 3);
     sm.termS = reinterpret_cast<tdb200_term*>((reinterpret_cast<uintptr_t>(sm.tmem_ptr + 2) + 15) & ~uintptr_t(15));
     sm.facS = reinterpret_cast<tdb200_factor*>(sm.termS + kTcMaxTerms);
+    sm.segS = reinterpret_cast<tdb200_segment*>(sm.facS + kTcMaxFactors);
+    sm.scaleS = reinterpret_cast<float*>(sm.segS + 1);
+    sm.lossT = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sm.scaleS + 32) + 15) & ~uintptr_t(15));
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = (warp & 3) * 32 + lane;                 // neuron = TMEM lane owned by this thread
@@ -378,6 +385,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
   for (int i = tid; i < n_out * W; i += kTcThreads) sm.wlS[(i / W) * kTcSavePitch + i % W] = a.arena[a.w_off[L - 1] + i];
   for (int i = tid; i < min(kTcMaxTerms, a.n_terms); i += kTcThreads) sm.termS[i] = a.terms[i];
   for (int i = tid; i < min(kTcMaxFactors, a.n_factors); i += kTcThreads) sm.facS[i] = a.factors[i];
+  for (int i = tid; i < (int)(sizeof(tdb200_segment) / 4); i += kTcThreads)
+    reinterpret_cast<uint32_t*>(sm.segS)[i] = reinterpret_cast<const uint32_t*>(a.segs)[i];
+  if (tid < a.n_slots) sm.scaleS[tid] = a.slot_scale[tid];
+  for (int i = tid; i < kTcCols * TDB200_MAX_COLS; i += kTcThreads) sm.lossT[i] = 0.0;
   if (tid == 0) { mbar_init(sm.bar, 1); mbar_init(sm.wbar, 1); mbar_init(sm.gbar, 1); }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(sm.tmem_ptr)) : "memory");
@@ -412,7 +423,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
 #pragma unroll
   for (int v = 0; v < kMaxOut; ++v) wl[v] = (live && v < n_out) ? a.arena[a.w_off[L - 1] + v * W + n] : 0.f;
 
-  const tdb200_segment& sg = a.segs[0];
+  const tdb200_segment& sg = *sm.segS;                  // shared-memory copy (set up above, visible after the sync)
   const int ncols = sg.n_cols;
   int dir_axis[3] = {0, 0, 0};
   for (int i = 0; i < ND; ++i) dir_axis[i] = sg.dir_axis[i];
@@ -424,8 +435,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
     const int pv = (int)min((long long)P, sg.n_groups - gf);
     for (int i = tid; i < P * d; i += kTcThreads) {
       const int p = i / d, ax = i - p * d;
-      dst[p * 4 + ax] = p < pv ? __ldg(a.pts + (size_t)(sg.pts_off + gf + p) * d + ax) : 0.f;
+      if (p < pv)      // asynchronous copy: nobody waits for the load until the next tile starts
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dst + p * 4 + ax)),
+                     "l"(a.pts + (size_t)(sg.pts_off + gf + p) * d + ax) : "memory");
+      else
+        dst[p * 4 + ax] = 0.f;
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
   load_points(blockIdx.x, sm.xS);
   int xbuf = 0;
@@ -433,6 +449,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
     const long long g_first = (long long)tile * P;
     const int p_valid = (int)min((long long)P, sg.n_groups - g_first);
     float* const xcur = sm.xS + xbuf * kTcCols * 4;
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();                                    // this tile's points (loaded one tile ahead) are visible
     if (tile + (int)gridDim.x < a.n_tiles) load_points(tile + gridDim.x, sm.xS + (xbuf ^ 1) * kTcCols * 4);
     xbuf ^= 1;
@@ -551,9 +568,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
         const float tgt = sg.tgt_off >= 0 ? __ldg(a.targets + sg.tgt_off + row * ncols + col) : 0.f;
         const float res = val - tgt;
         const int slot = sg.col_slot[col];
-        atomicAdd(&sm.lossS[slot], (double)res * (double)res);
+        sm.lossT[p * TDB200_MAX_COLS + col] += (double)res * (double)res;
         if (!a.do_grad) continue;
-        const float seed = 2.f * __ldg(a.slot_scale + slot) * res;
+        const float seed = 2.f * sm.scaleS[slot] * res;
         for (int t = sg.col_term_begin[col]; t < sg.col_term_end[col]; ++t) {
           const tdb200_term tm = sm.termS[t];
           const float cf = tm.kind == 0 ? tm.coeff : tm.kind == 1 ? __ldg(a.coeffs + tm.idx + row)
@@ -721,7 +738,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       }
     }
   }
-  if (tid < a.n_slots) a.part_loss[(size_t)blockIdx.x * a.n_slots + tid] = sm.lossS[tid];
+  if (tid < a.n_slots) {
+    double s = 0.0;
+    for (int col = 0; col < ncols; ++col)
+      if (sg.col_slot[col] == tid)
+        for (int p = 0; p < P; ++p) s += sm.lossT[p * TDB200_MAX_COLS + col];
+    a.part_loss[(size_t)blockIdx.x * a.n_slots + tid] = s;
+  }
   if (a.do_grad && tid < a.n_cparams) my_grad[a.n_net_params + tid] = sm.cgS[tid];   // warp 0 -> half-0 row
   tc_fence_before();
   __syncthreads();
