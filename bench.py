@@ -267,10 +267,10 @@ def run_b200(args):
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'vs_baseline': None, 'dtype': 'f32' if plan.launches_per_call == 3 else 'tf32x3 (fp32 accumulate)', 'data': 'synthetic',
         'config': {'workload': args.workload, 'description': spec['desc'], 'points_per_gpu': n_local,
                    'points_total': n_global, 'mlp': list(prob.net_layers), 'mode': prob.mode,
-                   'jet_channels': spec['J'], 'kernel': 'simt-fp32' if plan.launches_per_call == 3 else 'tcgen05-3xtf32',
+                   'jet_channels': spec['J'], 'kernel': 'simt-fp32' if plan.launches_per_call == 3 else 'tcgen05-3xtf32 (interior) + simt-fp32 (boundary rows)',
                    'l2': 'flushed between timed steps (256 MB write)', 'parallelism': f'dp{world} (points sharded)'},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': e2e_ms / e2e_steps},

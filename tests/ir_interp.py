@@ -31,6 +31,9 @@ def evaluate_ir(ir: ProblemIR, model, dtype=torch.float64):
     sums = [torch.zeros((), dtype=dtype) for _ in range(ir.n_slots)]
     fields = []
     for s in ir.segments:
+        if s.n_groups == 0:          # a rank may own no row of a small segment
+            fields.append(torch.zeros(0, len(s.cols), dtype=dtype))
+            continue
         pts = s.points.to(dtype)
         J, K, M = s.jet.J, s.K, s.M
         jets = _jets(model, pts, s.jet)                           # [n*K, J, n_out]
