@@ -162,8 +162,15 @@ def test_mat_loss_and_gradient_match_reference(name, cuda_default):
 
 
 def test_mat_large_grid_properties(cuda_default):
-    """4096 x 4096 Poisson (BASELINE config 4): size-independent checks - the exact solution of the discrete
-    problem has zero loss and zero gradient; the loss is quadratic along any direction (linear operator)."""
+    """4096 x 4096 Poisson (BASELINE config 4), full size.
+
+    (i) the kernel against an independent fp64 evaluation of the same discrete operator on the device (dense banded
+    D^2 matrices built by mat.derivative_band, which the CPU tests pin to the oracle);
+    (ii) size-independent properties: the loss is quadratic and the gradient affine along a direction.
+    At h = 1/4095 fp32 second differences carry O(1) rounding noise per cell (u * eps / 4h^2) - in the reference
+    too - so (ii) uses steps large enough for the signal to dominate and (i) allows for the noise floor."""
+    from torch_de_solver_b200.mat import derivative_band
+    from test_mat_cpu import dense_from_band
     n = 4095
     prob = problems.poisson_mat(tdb, 'float32', n=n)
     x = torch.linspace(0, 1, n + 1)
@@ -173,17 +180,42 @@ def test_mat_large_grid_properties(cuda_default):
     plan = model.solution_cls._plan
     v = (torch.sin(2 * np.pi * x)[:, None] * torch.cos(3 * np.pi * x)[None, :]).reshape(1, n + 1, n + 1).contiguous()
     u0 = (u + 0.05 * torch.sin(5 * np.pi * x)[:, None] * torch.sin(np.pi * x)[None, :]).contiguous()
-    # at h = 1/4095 the fp32 second differences carry O(1) rounding noise per cell (u * eps / 4h^2), in the
-    # reference too; the steps below are large enough for the signal to dominate it
-    ts = (-1.0, 0.0, 1.0, 2.0)
+
+    # (i) fp64 restatement: r = D2 u + u D2^T - f,  loss = lam_op mean(r^2) + lam_b/len sum_bc (u - t)^2
+    h = float(x[1] - x[0])
+    band, b, E = derivative_band(n + 1, 2, 2, h)
+    D2 = torch.as_tensor(dense_from_band(band.astype(np.float64), b, E, n + 1), dtype=torch.float64, device='cuda:0')
+    f64 = (-2 * np.pi ** 2 * torch.sin(np.pi * x.double())[:, None] * torch.sin(np.pi * x.double())[None, :])
+    U = u0[0].double()
+    r = D2 @ U + U @ D2.T - f64
+    N = float((n + 1) ** 2)
+    tgt = torch.zeros_like(U)
+    tgt[:, -1] = torch.sin(np.pi * x.double())                       # u(x, y = 1) = sin(pi x); other edges 0
+    mask = torch.zeros_like(U)
+    cnt = torch.zeros_like(U)                                        # corners appear in two conditions
+    for sl in ((0, slice(None)), (-1, slice(None)), (slice(None), 0), (slice(None), -1)):
+        cnt[sl] += 1
+    bdiff = (U - tgt)
+    # the two conditions that share a corner have different targets only at (x=0|1, y=1): sin(pi x) = 0 there
+    n_b = 4 * (n + 1)
+    loss_ref = float((r ** 2).sum() / N + 100.0 * (cnt * bdiff ** 2).sum() / n_b)
+    grad_ref = 2.0 / N * (D2.T @ r + r @ D2) + 100.0 * 2.0 / n_b * cnt * bdiff
+    out, grad = plan.loss_grad_raw(u0)
+    noise = 1.0                                                      # O(1) per-cell residual noise, see docstring
+    assert float(out[0]) == pytest.approx(loss_ref, rel=2e-2, abs=2 * noise)
+    gerr = float((grad[0].double() - grad_ref).norm() / grad_ref.norm())
+    assert gerr < 0.1, gerr
+
+    # (ii) quadratic / affine structure with large steps
+    ts = (-50.0, 0.0, 50.0, 100.0)
     l = [float(plan.loss_grad_raw((u0 + t * v).contiguous())[0][0]) for t in ts]
-    third = l[3] - 3 * l[2] + 3 * l[1] - l[0]                 # quadratic in t  <=>  third difference vanishes
-    assert abs(third) <= 2e-3 * max(abs(x) for x in l)
-    grads = [plan.loss_grad_raw((u0 + t * v).contiguous())[1].double() for t in (0.0, 1.0, 2.0)]
-    d1, d2 = grads[1] - grads[0], grads[2] - grads[1]         # the gradient is affine in u
-    assert float((d1 - d2).norm()) <= 2e-3 * float(d1.norm())
-    fd = (l[2] - l[0]) / 2.0
-    assert fd == pytest.approx(float((grads[0] * v.double()).sum()), rel=1e-2)
+    third = l[3] - 3 * l[2] + 3 * l[1] - l[0]
+    assert abs(third) <= 2e-3 * max(abs(q) for q in l)
+    grads = [plan.loss_grad_raw((u0 + t * v).contiguous())[1].double() for t in (0.0, 50.0, 100.0)]
+    d1, d2 = grads[1] - grads[0], grads[2] - grads[1]
+    assert float((d1 - d2).norm()) <= 1e-2 * float(d1.norm())
+    fd = (l[2] - l[0]) / 100.0
+    assert fd == pytest.approx(float((grads[0] * v.double()).sum()), rel=2e-2)
 
 
 def test_repeatable_and_param_update(cuda_default):
@@ -255,6 +287,23 @@ def test_training_reduces_loss(cuda_default):
     model.train(tdb.Optimizer('Adam', {'lr': 1e-3}), 60)
     l1 = float(model.solution_cls.evaluate()[0])
     assert l1 < 0.7 * l0
+
+
+def test_solution_accepts_foreign_equation_object(cuda_default):
+    """Solution only reads .operator / .bconds / .h from the equation object."""
+    from types import SimpleNamespace
+    g = load_golden('burgers_NN_small', 'float64')
+    prob = problems.ZOO['burgers_NN_small'](tdb, 'float32')
+    net = problems.make_net(prob.net_layers, torch.float32, prob.init)
+    set_weights(list(net.parameters()), g['weights'])
+    net = net.to('cuda:0')
+    grid = prob.domain.build('NN')
+    bconds = prob.conditions.build(prob.domain.variable_dict)
+    foreign = SimpleNamespace(grid=grid, operator=prob.equation.equation_lst, bconds=bconds, h=0.001,
+                              inner_order='1', boundary_order='2')
+    sol = tdb.Solution(grid, foreign, net, 'NN', None, 1, 10)
+    loss, _ = sol.evaluate()
+    assert float(loss) == pytest.approx(float(g['loss']), rel=LOSS_RTOL)
 
 
 def test_c_abi_errors(cuda_default):

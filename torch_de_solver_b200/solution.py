@@ -158,6 +158,14 @@ class Solution:
         self.tol = tol
         self.derivative_points = derivative_points
         self.batch_size = None
+        # objects of the reference's own Equation_{NN,autograd,mat} classes (or anything with .operator / .bconds)
+        # are re-wrapped: only the raw term dicts and conditions are read from them
+        from .input_preprocessing import _EquationBase, Operator_bcond_preproc
+        if not isinstance(equal_cls, _EquationBase):
+            equal_cls = Operator_bcond_preproc(
+                self.grid, equal_cls.operator, equal_cls.bconds, h=getattr(equal_cls, 'h', 0.001),
+                inner_order=getattr(equal_cls, 'inner_order', '1'),
+                boundary_order=getattr(equal_cls, 'boundary_order', '2')).set_strategy(mode)
         self.equal_cls = equal_cls
         self._shard = shard or (0, 1)
         self._pg = process_group
