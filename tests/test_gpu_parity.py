@@ -161,8 +161,9 @@ def test_mat_loss_and_gradient_match_reference(name, cuda_default):
     np.testing.assert_allclose(sol.true_bval.cpu().numpy(), g['true_bval'], atol=1e-6)
 
 
-def test_mat_large_grid_properties(cuda_default):
-    """4096 x 4096 Poisson (BASELINE config 4), full size.
+@pytest.mark.parametrize('n,amp,gtol', [(511, 0.05, 2e-3), (4095, 2.0, 5e-2)])
+def test_mat_large_grid_properties(n, amp, gtol, cuda_default):
+    """512 x 512 (interior fast-path tiles, low rounding noise) and 4096 x 4096 Poisson (BASELINE config 4, full size).
 
     (i) the kernel against an independent fp64 evaluation of the same discrete operator on the device (dense banded
     D^2 matrices built by mat.derivative_band, which the CPU tests pin to the oracle);
@@ -171,7 +172,6 @@ def test_mat_large_grid_properties(cuda_default):
     too - so (ii) uses steps large enough for the signal to dominate and (i) allows for the noise floor."""
     from torch_de_solver_b200.mat import derivative_band
     from test_mat_cpu import dense_from_band
-    n = 4095
     prob = problems.poisson_mat(tdb, 'float32', n=n)
     x = torch.linspace(0, 1, n + 1)
     u = (torch.sin(np.pi * x)[:, None] * torch.sin(np.pi * x)[None, :]).reshape(1, n + 1, n + 1).contiguous()
@@ -179,7 +179,7 @@ def test_mat_large_grid_properties(cuda_default):
     model.compile('mat', **prob.compile_kwargs)
     plan = model.solution_cls._plan
     v = (torch.sin(2 * np.pi * x)[:, None] * torch.cos(3 * np.pi * x)[None, :]).reshape(1, n + 1, n + 1).contiguous()
-    u0 = (u + 0.05 * torch.sin(5 * np.pi * x)[:, None] * torch.sin(np.pi * x)[None, :]).contiguous()
+    u0 = (u + amp * torch.sin(5 * np.pi * x)[:, None] * torch.sin(np.pi * x)[None, :]).contiguous()
 
     # (i) fp64 restatement: r = D2 u + u D2^T - f,  loss = lam_op mean(r^2) + lam_b/len sum_bc (u - t)^2
     h = float(x[1] - x[0])
@@ -202,9 +202,9 @@ def test_mat_large_grid_properties(cuda_default):
     grad_ref = 2.0 / N * (D2.T @ r + r @ D2) + 100.0 * 2.0 / n_b * cnt * bdiff
     out, grad = plan.loss_grad_raw(u0)
     noise = 1.0                                                      # O(1) per-cell residual noise, see docstring
-    assert float(out[0]) == pytest.approx(loss_ref, rel=2e-2, abs=2 * noise)
+    assert float(out[0]) == pytest.approx(loss_ref, rel=1e-3, abs=(2 * noise if n > 1000 else 1e-3))
     gerr = float((grad[0].double() - grad_ref).norm() / grad_ref.norm())
-    assert gerr < 0.1, gerr
+    assert gerr < gtol, gerr
 
     # (ii) quadratic / affine structure with large steps
     ts = (-50.0, 0.0, 50.0, 100.0)
