@@ -44,6 +44,10 @@ struct MatArgs {
   int tap_begin[TDB200_MAX_COLS + 1];      // taps of equation e: [tap_begin[e], tap_begin[e+1])
   short tap_var[kMatMaxTaps], tap_axis[kMatMaxTaps], tap_m[kMatMaxTaps];
   float tap_w[kMatMaxTaps];
+  int n_lin;                               // linear terms (all equations), for edge cells of the fast path
+  short lin_eq[kMatMaxTaps], lin_q[kMatMaxTaps];
+  float lin_c[kMatMaxTaps];
+  int lin1;                                // 1: single equation, single field, <= 16 taps -> register-tap kernel path
   int frc_begin[TDB200_MAX_COLS + 1];      // forcing terms of equation e
   float frc_const[kMatMaxForcing];
   long long frc_buf[kMatMaxForcing];       // coefficient buffer offset, -1: constant only
@@ -80,6 +84,107 @@ __device__ __forceinline__ float field_value(const MatArgs& a, const tdb200_mat_
   return s;
 }
 
+// ---- register-tap path: one linear constant-coefficient equation on one field -------------------------
+// Interior cells use a composite tap list held in registers; the few cells whose stencil rows are special
+// (one-sided rows near the domain edge) evaluate the banded operators directly.
+template <int NT>
+__device__ __forceinline__ void mat_lin1_path(const MatArgs& a, float* us, float* ss, double (*red)[TDB200_MAX_COLS],
+                                              int ty0, int tx0) {
+  const int hy = a.hy, hx = a.hx;
+  const int ux = kMatTX + 4 * hx;
+  const int ry = kMatTY + 2 * hy, rx = kMatTX + 2 * hx;
+  const int tid = threadIdx.x;
+  const int nt = a.tap_begin[1];
+  float tw[NT];
+  int tou[NT], tos[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const bool on = t < nt;
+    tw[t] = on ? a.tap_w[t] : 0.f;
+    const int m = on ? a.tap_m[t] : 0;
+    const bool ax0 = on && a.tap_axis[t] == 0;
+    tou[t] = ax0 ? m * ux : m;
+    tos[t] = ax0 ? -m * rx : -m;
+  }
+  const float scale2 = 2.f * a.eq_scale[0];
+  const int zy = a.edge_y, zx = a.edge_x;                 // rows / columns with their own coefficients
+  float lacc = 0.f;
+  // phase 2: residual seeds on tile + halo
+  {
+    int ly = tid / rx, lx = tid - ly * rx;
+    const int dly = kMatThreads / rx, dlx = kMatThreads - dly * rx;
+    for (; ly < ry; ly += dly, lx += dlx) {
+      if (lx >= rx) { lx -= rx; ++ly; if (ly >= ry) break; }
+      const int gy = ty0 - hy + ly, gx = tx0 - hx + lx;
+      float seed = 0.f;
+      if (gy >= 0 && gy < a.n0 && gx >= 0 && gx < a.n1) {
+        const size_t cell = (size_t)gy * a.n1 + gx;
+        float res = 0.f;
+        for (int t = a.frc_begin[0]; t < a.frc_begin[1]; ++t)
+          res += a.frc_buf[t] >= 0 ? __ldg(a.coeffs + a.frc_buf[t] + cell) : a.frc_const[t];
+        const float* uc = us + (ly + hy) * ux + lx + hx;
+        if (gy >= zy && gy < a.n0 - zy && gx >= zx && gx < a.n1 - zx) {
+#pragma unroll
+          for (int t = 0; t < NT; ++t) res = fmaf(tw[t], uc[tou[t]], res);
+        } else {
+          for (int t = 0; t < a.n_lin; ++t)
+            res = fmaf(a.lin_c[t], field_value(a, a.fld[a.lin_q[t]], us, ux, 0, ly + hy, lx + hx, gy, gx), res);
+        }
+        if (ly >= hy && ly < hy + kMatTY && lx >= hx && lx < hx + kMatTX) {
+          lacc += res * res;
+          if (a.op_out) a.op_out[cell] = res;
+        }
+        seed = scale2 * res;
+      }
+      ss[ly * rx + lx] = seed;
+    }
+  }
+  {
+    double v = (double)lacc;
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0) red[tid >> 5][0] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int w = 0; w < kMatThreads / 32; ++w) s += red[w][0];
+    a.part_loss[(size_t)(blockIdx.y * gridDim.x + blockIdx.x)] = s;
+  }
+  if (!a.grad) return;
+  // phase 3: transposed stencil -> gradient of the tile (kMatTX == 64: lx = tid & 63)
+  const int zy3 = zy + hy, zx3 = zx + hx;                  // cells that gather from a special row
+  for (int cy = tid >> 6; cy < kMatTY; cy += kMatThreads >> 6) {
+    const int cx = tid & 63;
+    const int gy = ty0 + cy, gx = tx0 + cx;
+    if (gy >= a.n0 || gx >= a.n1) continue;
+    const float* sc = ss + (cy + hy) * rx + cx + hx;
+    float g = 0.f;
+    if (gy >= zy3 && gy < a.n0 - zy3 && gx >= zx3 && gx < a.n1 - zx3) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) g = fmaf(tw[t], sc[tos[t]], g);
+    } else {
+      for (int t = 0; t < a.n_lin; ++t) {
+        const tdb200_mat_field& f = a.fld[a.lin_q[t]];
+        float s = 0.f;
+        if (f.order == 0) s = sc[0];
+        else if (f.axis == 0) {
+          for (int m = -f.half_width; m <= f.half_width; ++m) {
+            const int yy = gy + m;
+            if (yy >= 0 && yy < a.n0) s = fmaf(band_coef(a.band, f, a.n0, yy, -m), sc[m * rx], s);
+          }
+        } else {
+          for (int m = -f.half_width; m <= f.half_width; ++m) {
+            const int xx = gx + m;
+            if (xx >= 0 && xx < a.n1) s = fmaf(band_coef(a.band, f, a.n1, xx, -m), sc[m], s);
+          }
+        }
+        g = fmaf(a.lin_c[t], s, g);
+      }
+    }
+    a.grad[(size_t)gy * a.n1 + gx] = g;
+  }
+}
+
 __global__ void __launch_bounds__(kMatThreads) mat_residual_adjoint_kernel(const MatArgs a) {
   extern __shared__ __align__(16) float sm[];
   const int hy = a.hy, hx = a.hx;
@@ -95,15 +200,28 @@ __global__ void __launch_bounds__(kMatThreads) mat_residual_adjoint_kernel(const
   const size_t N = (size_t)a.n0 * a.n1;
 
   // ---- phase 1: u tile + 2 halos -> smem (zero outside the domain) --------------------------------
-  for (int v = 0; v < a.n_var; ++v)
-    for (int idx = tid; idx < uplane; idx += kMatThreads) {
-      const int ly = idx / ux, lx = idx - ly * ux;
+  for (int v = 0; v < a.n_var; ++v) {
+    int ly = tid / ux, lx = tid - ly * ux;
+    const int dly = kMatThreads / ux, dlx = kMatThreads - dly * ux;
+    for (; ly < uy; ly += dly, lx += dlx) {
+      if (lx >= ux) { lx -= ux; ++ly; if (ly >= uy) break; }
       const int gy = ty0 - 2 * hy + ly, gx = tx0 - 2 * hx + lx;
       float val = 0.f;
       if (gy >= 0 && gy < a.n0 && gx >= 0 && gx < a.n1) val = __ldg(a.u + (size_t)v * N + (size_t)gy * a.n1 + gx);
-      us[v * uplane + idx] = val;
+      us[v * uplane + ly * ux + lx] = val;
     }
+  }
   __syncthreads();
+
+  if (a.lin1) {
+    const int nt = a.tap_begin[1];
+    if (nt <= 4) mat_lin1_path<4>(a, us, as, red, ty0, tx0);
+    else if (nt <= 6) mat_lin1_path<6>(a, us, as, red, ty0, tx0);
+    else if (nt <= 8) mat_lin1_path<8>(a, us, as, red, ty0, tx0);
+    else if (nt <= 12) mat_lin1_path<12>(a, us, as, red, ty0, tx0);
+    else mat_lin1_path<16>(a, us, as, red, ty0, tx0);
+    return;
+  }
 
   // ---- fast path: interior tile of a linear constant-coefficient operator ---------------------------
   // (uniform per CTA) the residual is one composite stencil, the gradient its transpose applied to the seeds
@@ -514,7 +632,7 @@ int tdb200_mat_plan_create(const tdb200_mat_desc* desc, const tdb200_mat_field* 
   for (int e = 0; e < desc->n_eq; ++e) { a.eq_term_begin[e] = eq_term_begin[e]; a.eq_term_end[e] = eq_term_end[e]; }
   {  // fast-path analysis: constant-coefficient linear terms + forcing only
     bool linear = true;
-    int n_taps = 0, n_frc = 0, ey = 0, ex = 0;
+    int n_taps = 0, n_frc = 0, ey = 0, ex = 0, n_lin = 0;
     for (int e = 0; e < desc->n_eq && linear; ++e) {
       a.tap_begin[e] = n_taps;
       a.frc_begin[e] = n_frc;
@@ -534,6 +652,8 @@ int tdb200_mat_plan_create(const tdb200_mat_desc* desc, const tdb200_mat_field* 
           ++n_frc;
         } else if (live == 1 && tm.kind == 0 && linear) {
           const tdb200_mat_field& f = fields[fq];
+          if (n_lin < tdb::kMatMaxTaps) { a.lin_eq[n_lin] = (short)e; a.lin_q[n_lin] = (short)fq; a.lin_c[n_lin] = tm.coeff; }
+          ++n_lin;
           if (f.order == 0) {
             if (n_taps >= tdb::kMatMaxTaps) { linear = false; break; }
             a.tap_var[n_taps] = (short)f.var; a.tap_axis[n_taps] = 1; a.tap_m[n_taps] = 0; a.tap_w[n_taps] = tm.coeff;
@@ -557,7 +677,9 @@ int tdb200_mat_plan_create(const tdb200_mat_desc* desc, const tdb200_mat_field* 
     }
     a.tap_begin[desc->n_eq] = n_taps;
     a.frc_begin[desc->n_eq] = n_frc;
-    a.linear = linear ? 1 : 0;
+    a.linear = (linear && n_lin <= tdb::kMatMaxTaps) ? 1 : 0;
+    a.n_lin = n_lin;
+    a.lin1 = (a.linear && desc->n_eq == 1 && desc->n_var == 1 && n_taps <= 16) ? 1 : 0;
     a.edge_y = ey; a.edge_x = ex;
   }
   a.tiles_x = (desc->n1 + tdb::kMatTX - 1) / tdb::kMatTX;
