@@ -171,6 +171,9 @@ int tdb200_mat_eval_fields(tdb200_mat_plan* plan, const float* u_dev, float* op_
                            float* out_dev, void* stream);
 int64_t tdb200_mat_plan_out_size(const tdb200_mat_plan* plan);
 int32_t tdb200_mat_plan_launches_per_call(const tdb200_mat_plan* plan);
+/* Which residual kernel tdb200_mat_loss_grad launches: 0 = generic tiled kernel (any operator), 1 = register-tap
+ * kernel (one linear constant-coefficient equation), 2 = vectorised cross-stencil kernel (1 + n1 % 4 == 0). */
+int32_t tdb200_mat_plan_kernel_kind(const tdb200_mat_plan* plan);
 void tdb200_mat_plan_destroy(tdb200_mat_plan* plan);
 
 const char* tdb200_last_error(void);

@@ -237,10 +237,11 @@ def nonlinear_mix(api, dtype='float32', n=16, mode='autograd', layers=(2, 24, 24
 
 
 # --- config 4: Poisson, mat mode -------------------------------------------------------
-def poisson_mat(api, dtype='float32', n=32, derivative_points=2):
+def poisson_mat(api, dtype='float32', n=32, derivative_points=2, ny=None):
+    ny = n if ny is None else ny
     dom = api.Domain()
     dom.variable('x', [0, 1], n, dtype=dtype)
-    dom.variable('y', [0, 1], n, dtype=dtype)
+    dom.variable('y', [0, 1], ny, dtype=dtype)
     bc = api.Conditions()
     bc.dirichlet({'x': 0, 'y': [0, 1]}, value=0)
     bc.dirichlet({'x': 1, 'y': [0, 1]}, value=0)
@@ -248,7 +249,8 @@ def poisson_mat(api, dtype='float32', n=32, derivative_points=2):
     bc.dirichlet({'x': [0, 1], 'y': 1}, value=lambda g: torch.sin(np.pi * g[:, 0]))
     tdt = torch.float64 if dtype == 'float64' else torch.float32
     xs = torch.linspace(0, 1, n + 1, dtype=tdt)
-    f = -2 * np.pi ** 2 * torch.sin(np.pi * xs)[:, None] * torch.sin(np.pi * xs)[None, :]
+    ys = torch.linspace(0, 1, ny + 1, dtype=tdt)
+    f = -2 * np.pi ** 2 * torch.sin(np.pi * xs)[:, None] * torch.sin(np.pi * ys)[None, :]
     eq = api.Equation()
     eq.add({
         'd2u/dx2': {'coeff': 1, 'term': [0, 0], 'pow': 1},
@@ -257,7 +259,29 @@ def poisson_mat(api, dtype='float32', n=32, derivative_points=2):
     })
     return Problem(f'poisson_mat_p{derivative_points}', dom, bc, eq, 'mat', [],
                    dict(lambda_operator=1, lambda_bound=100, derivative_points=derivative_points),
-                   mat_shape=(1, n + 1, n + 1))
+                   mat_shape=(1, n + 1, ny + 1))
+
+
+def heat_mat(api, dtype='float32', n=32, nt=32, derivative_points=2):
+    """Linear constant-coefficient operator with different stencil reach per axis: u_t - 0.1 u_xx + 0.5 u - f."""
+    dom = api.Domain()
+    dom.variable('x', [0, 1], n, dtype=dtype)
+    dom.variable('t', [0, 1], nt, dtype=dtype)
+    bc = api.Conditions()
+    bc.dirichlet({'x': [0, 1], 't': 0}, value=lambda g: torch.sin(np.pi * g[:, 0]))
+    bc.dirichlet({'x': 0, 't': [0, 1]}, value=0)
+    bc.dirichlet({'x': 1, 't': [0, 1]}, value=0)
+    eq = api.Equation()
+    eq.add({
+        'du/dt': {'coeff': 1, 'term': [1], 'pow': 1},
+        '-a*d2u/dx2': {'coeff': -0.1, 'term': [0, 0], 'pow': 1},
+        '0.5u': {'coeff': 0.5, 'term': [None], 'pow': 1},
+        '-f': {'coeff': lambda g: -torch.sin(np.pi * g[0]) * torch.exp(-g[1]), 'term': [None], 'pow': 0},
+        'c': {'coeff': 0.25, 'term': [None], 'pow': 0},
+    })
+    return Problem(f'heat_mat_p{derivative_points}', dom, bc, eq, 'mat', [],
+                   dict(lambda_operator=1, lambda_bound=10, derivative_points=derivative_points),
+                   mat_shape=(1, n + 1, nt + 1))
 
 
 def kdv_mat(api, dtype='float32', n=24, derivative_points=2):
@@ -299,4 +323,8 @@ ZOO: Dict[str, Callable] = {
     'poisson_mat_p2': lambda api, dt: poisson_mat(api, dt, n=32, derivative_points=2),
     'poisson_mat_p3': lambda api, dt: poisson_mat(api, dt, n=24, derivative_points=3),
     'kdv_mat_p2': lambda api, dt: kdv_mat(api, dt, n=24, derivative_points=2),
+    # grids with n1 % 4 == 0: served by the vectorised cross-stencil kernel (one tile, every cell next to an edge)
+    'poisson_mat_p2_rect': lambda api, dt: poisson_mat(api, dt, n=40, ny=63, derivative_points=2),
+    'poisson_mat_p3_rect': lambda api, dt: poisson_mat(api, dt, n=24, ny=43, derivative_points=3),
+    'heat_mat_p2': lambda api, dt: heat_mat(api, dt, n=31, nt=47, derivative_points=2),
 }

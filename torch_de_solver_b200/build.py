@@ -30,8 +30,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
     os.makedirs(LIB_DIR, exist_ok=True)
-    objs = []
-    for src in sources():
+    def compile_one(src):
         obj = os.path.join(LIB_DIR, os.path.basename(src)[:-3] + '.o')
         cmd = [nvcc] + [f for f in NVCC_FLAGS if f != '--use_fast_math=false'] + \
               ['-I', os.path.join(ROOT, 'include'), '-I', os.path.join(PKG, 'csrc'), '-c', src, '-o', obj]
@@ -42,7 +41,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f'nvcc failed for {src}')
         with open(obj + '.ptxas.log', 'w') as f:
             f.write(res.stderr)
-        objs.append(obj)
+        return obj
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=4) as ex:      # one nvcc process per translation unit
+        objs = list(ex.map(compile_one, sources()))
     cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-cudart', 'static']
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

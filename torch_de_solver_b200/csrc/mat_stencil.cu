@@ -10,6 +10,7 @@
 //      coefficient tensors, write the gradient (12 B / cell for Poisson) + halo re-reads served by L2.
 //   2. a small kernel for the boundary rows (gather, residual, scatter-add of the adjoint),
 //   3. a finalize kernel (ordered reduction of per-CTA loss partials, loss assembly).
+#include <stdlib.h>
 #include <string>
 #include <vector>
 #include "common.cuh"
@@ -47,7 +48,10 @@ struct MatArgs {
   int n_lin;                               // linear terms (all equations), for edge cells of the fast path
   short lin_eq[kMatMaxTaps], lin_q[kMatMaxTaps];
   float lin_c[kMatMaxTaps];
-  int lin1;                                // 1: single equation, single field, <= 16 taps -> register-tap kernel path
+  int lin1;                                // 1: single equation, single field, <= 16 taps, reach <= 4 -> mat_lin1_kernel
+  float l1_fconst;                         // lin1: sum of the constant forcing terms
+  const float* l1_fbuf[2];                 // lin1: up to two forcing buffers (absolute pointers, set per call)
+  float cx_wy[9], cx_wx[9], cx_wc;         // cross kernel: weights by offset (index offset + reach), merged centre
   int frc_begin[TDB200_MAX_COLS + 1];      // forcing terms of equation e
   float frc_const[kMatMaxForcing];
   long long frc_buf[kMatMaxForcing];       // coefficient buffer offset, -1: constant only
@@ -84,85 +88,347 @@ __device__ __forceinline__ float field_value(const MatArgs& a, const tdb200_mat_
   return s;
 }
 
-// ---- register-tap path: one linear constant-coefficient equation on one field -------------------------
-// Interior cells use a composite tap list held in registers; the few cells whose stencil rows are special
-// (one-sided rows near the domain edge) evaluate the banded operators directly.
-template <int NT>
-__device__ __forceinline__ void mat_lin1_path(const MatArgs& a, float* us, float* ss, double (*red)[TDB200_MAX_COLS],
-                                              int ty0, int tx0) {
+// ---- register-tap kernel: one linear constant-coefficient equation on one field -----------------------
+// (Poisson, heat, wave ... in mat mode.)  128 x 32 tiles, compile-time shared-memory pitches so that every tap of
+// every unrolled cell is one LDS with an immediate offset; interior CTAs run without any per-cell bounds or
+// edge-row checks.  Cells whose stencil rows are special (one-sided rows near the domain edge) evaluate the
+// banded operators directly.  HBM traffic per cell: read u, read the forcing buffer(s), write the gradient.
+constexpr int kL1TY = 32, kL1TX = 128, kL1MaxH = 4;         // tile; composite stencil reach per axis <= 4
+constexpr int kL1PU = kL1TX + 4 * kL1MaxH;                  // pitch of the u region (tile + 2 halos)
+constexpr int kL1PR = kL1TX + 2 * kL1MaxH;                  // pitch of the seed region (tile + halo)
+constexpr int kL1UY = kL1TY + 4 * kL1MaxH, kL1RY = kL1TY + 2 * kL1MaxH;
+constexpr size_t kL1Smem = (size_t)(kL1UY * kL1PU + kL1RY * kL1PR) * sizeof(float);
+
+template <int NT, bool INTERIOR>
+__device__ __forceinline__ float mat_lin1_tile(const MatArgs& a, float* __restrict__ us, float* __restrict__ ss,
+                                               int ty0, int tx0) {
   const int hy = a.hy, hx = a.hx;
-  const int ux = kMatTX + 4 * hx;
-  const int ry = kMatTY + 2 * hy, rx = kMatTX + 2 * hx;
-  const int tid = threadIdx.x;
-  const int nt = a.tap_begin[1];
+  const int uy = kL1TY + 4 * hy, ux = kL1TX + 4 * hx, ry = kL1TY + 2 * hy, rx = kL1TX + 2 * hx;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // ---- phase 1: u tile + 2 halos -> shared memory (zero outside the domain) ----
+#pragma unroll
+  for (int i = 0; i < kL1UY / 8; ++i) {
+    const int ly = warp + 8 * i;
+    if (ly < uy) {
+      const int gy = ty0 - 2 * hy + ly;
+      const bool rowok = INTERIOR || (gy >= 0 && gy < a.n0);
+      const long long rbase = (long long)gy * a.n1 + (tx0 - 2 * hx);
+#pragma unroll
+      for (int j = 0; j < (kL1PU + 31) / 32; ++j) {
+        const int lx = lane + 32 * j;
+        if (lx < ux) {
+          const int gx = tx0 - 2 * hx + lx;
+          float v = 0.f;
+          if (INTERIOR || (rowok && gx >= 0 && gx < a.n1)) v = __ldg(a.u + rbase + lx);
+          us[ly * kL1PU + lx] = v;
+        }
+      }
+    }
+  }
   float tw[NT];
   int tou[NT], tos[NT];
+  const int nt = a.tap_begin[1];
 #pragma unroll
   for (int t = 0; t < NT; ++t) {
     const bool on = t < nt;
     tw[t] = on ? a.tap_w[t] : 0.f;
     const int m = on ? a.tap_m[t] : 0;
     const bool ax0 = on && a.tap_axis[t] == 0;
-    tou[t] = ax0 ? m * ux : m;
-    tos[t] = ax0 ? -m * rx : -m;
+    tou[t] = ax0 ? m * kL1PU : m;
+    tos[t] = ax0 ? -m * kL1PR : -m;
   }
   const float scale2 = 2.f * a.eq_scale[0];
-  const int zy = a.edge_y, zx = a.edge_x;                 // rows / columns with their own coefficients
+  const float fc0 = a.l1_fconst;
+  const float* __restrict__ f0 = a.l1_fbuf[0];
+  const float* __restrict__ f1 = a.l1_fbuf[1];
+  const int zy = a.edge_y, zx = a.edge_x;                  // rows / columns with their own coefficients
   float lacc = 0.f;
-  // phase 2: residual seeds on tile + halo
-  {
-    int ly = tid / rx, lx = tid - ly * rx;
-    const int dly = kMatThreads / rx, dlx = kMatThreads - dly * rx;
-    for (; ly < ry; ly += dly, lx += dlx) {
-      if (lx >= rx) { lx -= rx; ++ly; if (ly >= ry) break; }
-      const int gy = ty0 - hy + ly, gx = tx0 - hx + lx;
-      float seed = 0.f;
-      if (gy >= 0 && gy < a.n0 && gx >= 0 && gx < a.n1) {
-        const size_t cell = (size_t)gy * a.n1 + gx;
-        float res = 0.f;
-        for (int t = a.frc_begin[0]; t < a.frc_begin[1]; ++t)
-          res += a.frc_buf[t] >= 0 ? __ldg(a.coeffs + a.frc_buf[t] + cell) : a.frc_const[t];
-        const float* uc = us + (ly + hy) * ux + lx + hx;
-        if (gy >= zy && gy < a.n0 - zy && gx >= zx && gx < a.n1 - zx) {
+  __syncthreads();
+  // ---- phase 2: residual seeds on tile + halo ----
 #pragma unroll
-          for (int t = 0; t < NT; ++t) res = fmaf(tw[t], uc[tou[t]], res);
-        } else {
-          for (int t = 0; t < a.n_lin; ++t)
-            res = fmaf(a.lin_c[t], field_value(a, a.fld[a.lin_q[t]], us, ux, 0, ly + hy, lx + hx, gy, gx), res);
+  for (int i = 0; i < kL1RY / 8; ++i) {
+    const int ly = warp + 8 * i;
+    if (ly < ry) {
+      const int gy = ty0 - hy + ly;
+      const long long rbase = (long long)gy * a.n1 + (tx0 - hx);
+#pragma unroll
+      for (int j = 0; j < (kL1PR + 31) / 32; ++j) {
+        const int lx = lane + 32 * j;
+        if (lx < rx) {
+          const int gx = tx0 - hx + lx;
+          float seed = 0.f;
+          if (INTERIOR || (gy >= 0 && gy < a.n0 && gx >= 0 && gx < a.n1)) {
+            float res = fc0;
+            if (f0) res += __ldg(f0 + rbase + lx);
+            if (f1) res += __ldg(f1 + rbase + lx);
+            const float* uc = us + (ly + hy) * kL1PU + lx + hx;
+            if (INTERIOR || (gy >= zy && gy < a.n0 - zy && gx >= zx && gx < a.n1 - zx)) {
+#pragma unroll
+              for (int t = 0; t < NT; ++t) res = fmaf(tw[t], uc[tou[t]], res);
+            } else {
+              for (int t = 0; t < a.n_lin; ++t)
+                res = fmaf(a.lin_c[t], field_value(a, a.fld[a.lin_q[t]], us, kL1PU, 0, ly + hy, lx + hx, gy, gx), res);
+            }
+            if (ly >= hy && ly < hy + kL1TY && lx >= hx && lx < hx + kL1TX) lacc = fmaf(res, res, lacc);
+            seed = scale2 * res;
+          }
+          ss[ly * kL1PR + lx] = seed;
         }
-        if (ly >= hy && ly < hy + kMatTY && lx >= hx && lx < hx + kMatTX) {
-          lacc += res * res;
-          if (a.op_out) a.op_out[cell] = res;
-        }
-        seed = scale2 * res;
       }
-      ss[ly * rx + lx] = seed;
     }
   }
-  {
-    double v = (double)lacc;
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((tid & 31) == 0) red[tid >> 5][0] = v;
+  __syncthreads();
+  if (!a.grad) return lacc;
+  // ---- phase 3: transposed stencil -> gradient of the tile ----
+  const int zy3 = zy + hy, zx3 = zx + hx;                  // cells that gather from a special row
+#pragma unroll
+  for (int i = 0; i < kL1TY / 8; ++i) {
+    const int cy = warp + 8 * i, gy = ty0 + cy;
+#pragma unroll
+    for (int j = 0; j < kL1TX / 32; ++j) {
+      const int cx = lane + 32 * j, gx = tx0 + cx;
+      if (INTERIOR || (gy < a.n0 && gx < a.n1)) {
+        const float* sc = ss + (cy + hy) * kL1PR + cx + hx;
+        float g = 0.f;
+        if (INTERIOR || (gy >= zy3 && gy < a.n0 - zy3 && gx >= zx3 && gx < a.n1 - zx3)) {
+#pragma unroll
+          for (int t = 0; t < NT; ++t) g = fmaf(tw[t], sc[tos[t]], g);
+        } else {
+          for (int t = 0; t < a.n_lin; ++t) {
+            const tdb200_mat_field& f = a.fld[a.lin_q[t]];
+            float s = 0.f;
+            if (f.order == 0) s = sc[0];
+            else if (f.axis == 0) {
+              for (int m = -f.half_width; m <= f.half_width; ++m) {
+                const int yy = gy + m;
+                if (yy >= 0 && yy < a.n0) s = fmaf(band_coef(a.band, f, a.n0, yy, -m), sc[m * kL1PR], s);
+              }
+            } else {
+              for (int m = -f.half_width; m <= f.half_width; ++m) {
+                const int xx = gx + m;
+                if (xx >= 0 && xx < a.n1) s = fmaf(band_coef(a.band, f, a.n1, xx, -m), sc[m], s);
+              }
+            }
+            g = fmaf(a.lin_c[t], s, g);
+          }
+        }
+        a.grad[(size_t)gy * a.n1 + gx] = g;
+      }
+    }
+  }
+  return lacc;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(256, 3) mat_lin1_kernel(const MatArgs a) {
+  extern __shared__ __align__(16) float sm_l1[];
+  float* us = sm_l1;
+  float* ss = sm_l1 + kL1UY * kL1PU;
+  __shared__ double red[8];
+  const int ty0 = blockIdx.y * kL1TY, tx0 = blockIdx.x * kL1TX;
+  const bool interior = ty0 - 2 * a.hy >= a.edge_y && ty0 + kL1TY + 2 * a.hy <= a.n0 - a.edge_y &&
+                        tx0 - 2 * a.hx >= a.edge_x && tx0 + kL1TX + 2 * a.hx <= a.n1 - a.edge_x;
+  const float lacc = interior ? mat_lin1_tile<NT, true>(a, us, ss, ty0, tx0) : mat_lin1_tile<NT, false>(a, us, ss, ty0, tx0);
+  double v = (double)lacc;
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    a.part_loss[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+template <int NT>
+static cudaError_t launch_mat_lin1_nt(const MatArgs& a, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(mat_lin1_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kL1Smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((a.n1 + kL1TX - 1) / kL1TX, (a.n0 + kL1TY - 1) / kL1TY);
+  mat_lin1_kernel<NT><<<grid, 256, kL1Smem, s>>>(a);
+  return cudaGetLastError();
+}
+static cudaError_t launch_mat_lin1(const MatArgs& a, cudaStream_t s) {
+  const int nt = a.tap_begin[1];
+  if (nt <= 4) return launch_mat_lin1_nt<4>(a, s);
+  if (nt <= 6) return launch_mat_lin1_nt<6>(a, s);
+  if (nt <= 8) return launch_mat_lin1_nt<8>(a, s);
+  if (nt <= 12) return launch_mat_lin1_nt<12>(a, s);
+  return launch_mat_lin1_nt<16>(a, s);
+}
+static int mat_lin1_ctas(const MatArgs& a) {
+  return ((a.n1 + kL1TX - 1) / kL1TX) * ((a.n0 + kL1TY - 1) / kL1TY);
+}
+
+// ---- vectorised cross-stencil kernel -----------------------------------------------------------------------
+// Same contract as mat_lin1_kernel for operators whose composite interior stencil is a cross with reach HY / HX
+// (compile-time masks of the non-zero offsets) on grids with n1 % 4 == 0: the u tile is staged with 16-byte
+// cp.async (zero fill outside the domain), every thread works on float4 column groups (LDS.128 / LDG.128 /
+// STG.128), the forcing values of the residual pass are fetched into registers before the staging wait so that
+// both HBM streams are in flight together.  Cells whose stencil rows are special (one-sided rows near the domain
+// edge) are recomputed afterwards by compact fix-up passes with the banded operators (boundary CTAs only).
+constexpr int kCxTY = 32, kCxTX = 128;
+constexpr int kCxPU = kCxTX + 16;                           // u region columns [tx0 - 8, tx0 + 136)
+constexpr int kCxPR = kCxTX + 8;                            // seed region columns [tx0 - 4, tx0 + 132)
+constexpr int kCxQU = kCxPU / 4, kCxQR = kCxPR / 4;         // float4 groups per row
+
+__device__ __forceinline__ void cp_async16(float* dst, const float* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src),
+               "r"(src_bytes) : "memory");
+}
+
+// sum over the cross taps for the 4 cells of one column group.  REV: transposed stencil, g[c] += w[d] * s[c - d].
+template <int HY, int HX, unsigned MY, unsigned MX, bool REV, int PITCH>
+__device__ __forceinline__ void cx_apply(const float* __restrict__ c, const float* wy, const float* wx, float wc, float* r) {
+  const float4 c0 = *reinterpret_cast<const float4*>(c);
+  float w[12];
+  w[4] = c0.x; w[5] = c0.y; w[6] = c0.z; w[7] = c0.w;
+  if (MX != 0) {
+    const float4 cl = *reinterpret_cast<const float4*>(c - 4), cr = *reinterpret_cast<const float4*>(c + 4);
+    w[0] = cl.x; w[1] = cl.y; w[2] = cl.z; w[3] = cl.w;
+    w[8] = cr.x; w[9] = cr.y; w[10] = cr.z; w[11] = cr.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[i] = fmaf(wc, w[4 + i], r[i]);
+#pragma unroll
+  for (int dx = -HX; dx <= HX; ++dx) {
+    if (dx == 0 || !(MX & (1u << (dx + HX)))) continue;
+    const float wgt = wx[dx + HX];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = fmaf(wgt, w[4 + i + (REV ? -dx : dx)], r[i]);
+  }
+#pragma unroll
+  for (int dy = -HY; dy <= HY; ++dy) {
+    if (dy == 0 || !(MY & (1u << (dy + HY)))) continue;
+    const float wgt = wy[dy + HY];
+    const float4 v = *reinterpret_cast<const float4*>(c + (REV ? -dy : dy) * PITCH);
+    r[0] = fmaf(wgt, v.x, r[0]); r[1] = fmaf(wgt, v.y, r[1]); r[2] = fmaf(wgt, v.z, r[2]); r[3] = fmaf(wgt, v.w, r[3]);
+  }
+}
+
+template <int HY, int HX, unsigned MY, unsigned MX, bool INTERIOR>
+__device__ __forceinline__ float mat_cross_tile(const MatArgs& a, float* __restrict__ us, float* __restrict__ ss,
+                                                int ty0, int tx0) {
+  constexpr int UY = kCxTY + 4 * HY, RY = kCxTY + 2 * HY;
+  constexpr int N2 = (RY * kCxQR + 255) / 256;               // residual-pass items per thread
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = a.n0, n1 = a.n1;
+  // ---- phase 1: stage u (tile + 2 halos), asynchronously ----
+  for (int idx = tid; idx < UY * kCxQU; idx += 256) {
+    const int ly = idx / kCxQU, q = idx - ly * kCxQU;
+    const int gy = ty0 - 2 * HY + ly, gx = tx0 - 8 + 4 * q;
+    const bool ok = INTERIOR || (gy >= 0 && gy < n0 && gx >= 0 && gx < n1);
+    cp_async16(us + ly * kCxPU + 4 * q, ok ? a.u + (size_t)gy * n1 + gx : a.u, ok ? 16 : 0);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  // ---- forcing values of this thread's residual items -> registers (overlaps the staging) ----
+  const float* __restrict__ f0 = a.l1_fbuf[0];
+  const float* __restrict__ f1 = a.l1_fbuf[1];
+  float4 fv[N2];
+#pragma unroll
+  for (int k = 0; k < N2; ++k) {
+    const int idx = tid + 256 * k;
+    const int ly = idx / kCxQR, q = idx - ly * kCxQR;
+    const int gy = ty0 - HY + ly, gx = tx0 - 4 + 4 * q;
+    fv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (idx < RY * kCxQR && (INTERIOR || (gy >= 0 && gy < n0 && gx >= 0 && gx < n1))) {
+      const size_t cell = (size_t)gy * n1 + gx;
+      if (f0) fv[k] = __ldg(reinterpret_cast<const float4*>(f0 + cell));
+      if (f1) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(f1 + cell));
+        fv[k].x += t.x; fv[k].y += t.y; fv[k].z += t.z; fv[k].w += t.w;
+      }
+    }
+  }
+  float wy[2 * HY + 1], wx[2 * HX + 1];
+#pragma unroll
+  for (int i = 0; i <= 2 * HY; ++i) wy[i] = a.cx_wy[i];
+#pragma unroll
+  for (int i = 0; i <= 2 * HX; ++i) wx[i] = a.cx_wx[i];
+  const float wc = a.cx_wc, fc0 = a.l1_fconst, scale2 = 2.f * a.eq_scale[0];
+  const int zy = a.edge_y, zx = a.edge_x;
+  float lacc = 0.f;
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  // ---- phase 2: residual seeds on tile + halo ----
+#pragma unroll
+  for (int k = 0; k < N2; ++k) {
+    const int idx = tid + 256 * k;
+    if (idx < RY * kCxQR) {
+      const int ly = idx / kCxQR, q = idx - ly * kCxQR;
+      float r[4] = {fv[k].x + fc0, fv[k].y + fc0, fv[k].z + fc0, fv[k].w + fc0};
+      cx_apply<HY, HX, MY, MX, false, kCxPU>(us + (ly + HY) * kCxPU + 4 * q + 4, wy, wx, wc, r);
+      const bool core = ly >= HY && ly < HY + kCxTY && q >= 1 && q <= kCxTX / 4;
+      float sd[4];
+      if (INTERIOR) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { sd[i] = scale2 * r[i]; if (core) lacc = fmaf(r[i], r[i], lacc); }
+      } else {
+        const int gy = ty0 - HY + ly, gx = tx0 - 4 + 4 * q;
+        const bool rowreg = gy >= zy && gy < n0 - zy;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const bool reg = rowreg && gx + i >= zx && gx + i < n1 - zx;   // regular interior row of the operators
+          sd[i] = reg ? scale2 * r[i] : 0.f;
+          if (core && reg) lacc = fmaf(r[i], r[i], lacc);
+        }
+      }
+      *reinterpret_cast<float4*>(ss + ly * kCxPR + 4 * q) = make_float4(sd[0], sd[1], sd[2], sd[3]);
+    }
+  }
+  if (!INTERIOR) {
+    __syncthreads();
+    // fix-up: in-domain cells of the seed region whose stencil rows are special.  (a) whole special rows,
+    // warp-uniform; (b) special columns of the remaining rows, compact enumeration
+    auto special_seed = [&](int ly, int lx) {                // (ly, lx): seed-region coordinates
+      const int gy = ty0 - HY + ly, gx = tx0 - 4 + lx;
+      const size_t cell = (size_t)gy * n1 + gx;
+      float res = fc0;
+      if (f0) res += __ldg(f0 + cell);
+      if (f1) res += __ldg(f1 + cell);
+      for (int t = 0; t < a.n_lin; ++t)
+        res = fmaf(a.lin_c[t], field_value(a, a.fld[a.lin_q[t]], us, kCxPU, 0, ly + HY, lx + 4, gy, gx), res);
+      if (ly >= HY && ly < HY + kCxTY && lx >= 4 && lx < 4 + kCxTX) lacc = fmaf(res, res, lacc);
+      ss[ly * kCxPR + lx] = scale2 * res;
+    };
+    for (int ly = warp; ly < RY; ly += 8) {
+      const int gy = ty0 - HY + ly;
+      if (gy < 0 || gy >= n0 || (gy >= zy && gy < n0 - zy)) continue;
+      for (int lx = 4 - HX + lane; lx < 4 + kCxTX + HX; lx += 32) {
+        const int gx = tx0 - 4 + lx;
+        if (gx >= 0 && gx < n1) special_seed(ly, lx);
+      }
+    }
+    for (int k = tid; k < RY * 2 * zx; k += 256) {
+      const int ly = k / (2 * zx), ci = k - ly * (2 * zx);
+      const int gy = ty0 - HY + ly, gx = ci < zx ? ci : n1 - 2 * zx + ci;
+      const int lx = gx - (tx0 - 4);
+      if (gy >= zy && gy < n0 - zy && lx >= 4 - HX && lx < 4 + kCxTX + HX) special_seed(ly, lx);
+    }
   }
   __syncthreads();
-  if (tid == 0) {
-    double s = 0.0;
-    for (int w = 0; w < kMatThreads / 32; ++w) s += red[w][0];
-    a.part_loss[(size_t)(blockIdx.y * gridDim.x + blockIdx.x)] = s;
-  }
-  if (!a.grad) return;
-  // phase 3: transposed stencil -> gradient of the tile (kMatTX == 64: lx = tid & 63)
-  const int zy3 = zy + hy, zx3 = zx + hx;                  // cells that gather from a special row
-  for (int cy = tid >> 6; cy < kMatTY; cy += kMatThreads >> 6) {
-    const int cx = tid & 63;
-    const int gy = ty0 + cy, gx = tx0 + cx;
-    if (gy >= a.n0 || gx >= a.n1) continue;
-    const float* sc = ss + (cy + hy) * rx + cx + hx;
-    float g = 0.f;
-    if (gy >= zy3 && gy < a.n0 - zy3 && gx >= zx3 && gx < a.n1 - zx3) {
+  if (!a.grad) return lacc;
+  // ---- phase 3: transposed stencil -> gradient of the tile ----
 #pragma unroll
-      for (int t = 0; t < NT; ++t) g = fmaf(tw[t], sc[tos[t]], g);
-    } else {
+  for (int i = 0; i < kCxTY / 8; ++i) {
+    const int cy = warp + 8 * i, gy = ty0 + cy, gx = tx0 + 4 * lane;
+    if (INTERIOR || (gy < n0 && gx < n1)) {
+      float g[4] = {0.f, 0.f, 0.f, 0.f};
+      cx_apply<HY, HX, MY, MX, true, kCxPR>(ss + (cy + HY) * kCxPR + 4 * lane + 4, wy, wx, wc, g);
+      *reinterpret_cast<float4*>(a.grad + (size_t)gy * n1 + gx) = make_float4(g[0], g[1], g[2], g[3]);
+    }
+  }
+  if (!INTERIOR) {
+    __syncthreads();                                         // the fix-up overwrites cells stored above
+    const int zy3 = zy + HY, zx3 = zx + HX;                  // cells that gather from a special row
+    auto special_grad = [&](int cy, int cx) {
+      const int gy = ty0 + cy, gx = tx0 + cx;
+      const float* sc = ss + (cy + HY) * kCxPR + cx + 4;
+      float g = 0.f;
       for (int t = 0; t < a.n_lin; ++t) {
         const tdb200_mat_field& f = a.fld[a.lin_q[t]];
         float s = 0.f;
@@ -170,19 +436,88 @@ __device__ __forceinline__ void mat_lin1_path(const MatArgs& a, float* us, float
         else if (f.axis == 0) {
           for (int m = -f.half_width; m <= f.half_width; ++m) {
             const int yy = gy + m;
-            if (yy >= 0 && yy < a.n0) s = fmaf(band_coef(a.band, f, a.n0, yy, -m), sc[m * rx], s);
+            if (yy >= 0 && yy < n0) s = fmaf(band_coef(a.band, f, n0, yy, -m), sc[m * kCxPR], s);
           }
         } else {
           for (int m = -f.half_width; m <= f.half_width; ++m) {
             const int xx = gx + m;
-            if (xx >= 0 && xx < a.n1) s = fmaf(band_coef(a.band, f, a.n1, xx, -m), sc[m], s);
+            if (xx >= 0 && xx < n1) s = fmaf(band_coef(a.band, f, n1, xx, -m), sc[m], s);
           }
         }
         g = fmaf(a.lin_c[t], s, g);
       }
+      a.grad[(size_t)gy * n1 + gx] = g;
+    };
+    for (int cy = warp; cy < kCxTY; cy += 8) {
+      const int gy = ty0 + cy;
+      if (gy >= n0 || (gy >= zy3 && gy < n0 - zy3)) continue;
+      for (int cx = lane; cx < kCxTX; cx += 32)
+        if (tx0 + cx < n1) special_grad(cy, cx);
     }
-    a.grad[(size_t)gy * a.n1 + gx] = g;
+    for (int k = tid; k < kCxTY * 2 * zx3; k += 256) {
+      const int cy = k / (2 * zx3), ci = k - cy * (2 * zx3);
+      const int gy = ty0 + cy, gx = ci < zx3 ? ci : n1 - 2 * zx3 + ci;
+      const int cx = gx - tx0;
+      if (gy < n0 && gy >= zy3 && gy < n0 - zy3 && cx >= 0 && cx < kCxTX && gx >= 0) special_grad(cy, cx);
+    }
   }
+  return lacc;
+}
+
+template <int HY, int HX, unsigned MY, unsigned MX>
+__global__ void __launch_bounds__(256, 3) mat_cross_kernel(const MatArgs a) {
+  constexpr int UY = kCxTY + 4 * HY;
+  extern __shared__ __align__(16) float sm_cx[];
+  float* us = sm_cx;
+  float* ss = sm_cx + UY * kCxPU;
+  __shared__ double red[8];
+  const int ty0 = blockIdx.y * kCxTY, tx0 = blockIdx.x * kCxTX;
+  const bool interior = ty0 - 2 * HY >= a.edge_y && ty0 + kCxTY + 2 * HY <= a.n0 - a.edge_y &&
+                        tx0 - 8 >= a.edge_x && tx0 + kCxTX + 8 <= a.n1 - a.edge_x;
+  const float lacc = interior ? mat_cross_tile<HY, HX, MY, MX, true>(a, us, ss, ty0, tx0)
+                              : mat_cross_tile<HY, HX, MY, MX, false>(a, us, ss, ty0, tx0);
+  double v = (double)lacc;
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    a.part_loss[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+template <int HY, int HX, unsigned MY, unsigned MX>
+static cudaError_t launch_mat_cross_t(const MatArgs& a, cudaStream_t s) {
+  constexpr size_t smem = (size_t)((kCxTY + 4 * HY) * kCxPU + (kCxTY + 2 * HY) * kCxPR) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(mat_cross_kernel<HY, HX, MY, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((a.n1 + kCxTX - 1) / kCxTX, (a.n0 + kCxTY - 1) / kCxTY);
+  mat_cross_kernel<HY, HX, MY, MX><<<grid, 256, smem, s>>>(a);
+  return cudaGetLastError();
+}
+// instantiated cross shapes: (reach y, reach x, mask y, mask x); mask bit (d + reach) <=> offset d is non-zero
+#define TDB_CROSS_SHAPES(X) \
+  X(2, 2, 0x11u, 0x11u) X(1, 2, 0x5u, 0x11u) X(2, 1, 0x11u, 0x5u) X(1, 1, 0x5u, 0x5u) X(4, 4, 0x1EFu, 0x1EFu) \
+  X(2, 0, 0x11u, 0x0u) X(0, 2, 0x0u, 0x11u)
+static bool mat_cross_supported(int hy, int hx, unsigned my, unsigned mx) {
+#define X(A, B, C, D) if (hy == A && hx == B && (my & ~C) == 0 && (mx & ~D) == 0) return true;
+  TDB_CROSS_SHAPES(X)
+#undef X
+  return false;
+}
+static cudaError_t launch_mat_cross(const MatArgs& a, int hy, int hx, unsigned my, unsigned mx, cudaStream_t s) {
+#define X(A, B, C, D) if (hy == A && hx == B && (my & ~C) == 0 && (mx & ~D) == 0) return launch_mat_cross_t<A, B, C, D>(a, s);
+  TDB_CROSS_SHAPES(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+static int mat_cross_ctas(const MatArgs& a) {
+  return ((a.n1 + kCxTX - 1) / kCxTX) * ((a.n0 + kCxTY - 1) / kCxTY);
 }
 
 __global__ void __launch_bounds__(kMatThreads) mat_residual_adjoint_kernel(const MatArgs a) {
@@ -212,16 +547,6 @@ __global__ void __launch_bounds__(kMatThreads) mat_residual_adjoint_kernel(const
     }
   }
   __syncthreads();
-
-  if (a.lin1) {
-    const int nt = a.tap_begin[1];
-    if (nt <= 4) mat_lin1_path<4>(a, us, as, red, ty0, tx0);
-    else if (nt <= 6) mat_lin1_path<6>(a, us, as, red, ty0, tx0);
-    else if (nt <= 8) mat_lin1_path<8>(a, us, as, red, ty0, tx0);
-    else if (nt <= 12) mat_lin1_path<12>(a, us, as, red, ty0, tx0);
-    else mat_lin1_path<16>(a, us, as, red, ty0, tx0);
-    return;
-  }
 
   // ---- fast path: interior tile of a linear constant-coefficient operator ---------------------------
   // (uniform per CTA) the residual is one composite stencil, the gradient its transpose applied to the seeds
@@ -413,7 +738,15 @@ struct MatBcArgs {
   const float* u;
   float* grad;
   float* bval_out;                         // optional, per row
-  double* slot_sum;                        // [n_bc_slots]
+  double* slot_sum;                        // [n_bc_slots]; zero on entry, reset by the finalizing block
+  // finalize (run by the last block to finish): ordered reduction of the per-CTA loss partials + loss assembly
+  const double* part_loss;
+  int n_ctas, n_bc_slots;
+  double n_cells;
+  const double* slot_lambda;
+  const double* slot_len;
+  float* out;
+  unsigned int* ticket;                    // zero on entry, reset by the finalizing block
 };
 
 __device__ float global_field(const MatBcArgs& a, const tdb200_mat_field& f, int cell) {
@@ -454,7 +787,15 @@ __device__ void scatter_field_adjoint(const MatBcArgs& a, const tdb200_mat_field
   }
 }
 
-__global__ void mat_bc_kernel(const MatBcArgs a) {
+__device__ void mat_finalize_block(const double* __restrict__ part_loss, int n_ctas, int n_eq, double n_cells,
+                                   double* __restrict__ bc_sum, int n_bc_slots, const double* __restrict__ slot_lambda,
+                                   const double* __restrict__ slot_len, float* __restrict__ out);
+
+__global__ void __launch_bounds__(128) mat_bc_kernel(const MatBcArgs a) {
+  __shared__ double sh_slot[32];
+  __shared__ unsigned int sh_ticket;
+  if (threadIdx.x < 32) sh_slot[threadIdx.x] = 0.0;
+  __syncthreads();
   const long long total = a.bc_row_begin[a.n_bcs];
   for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < total;
        row += (long long)gridDim.x * blockDim.x) {
@@ -483,7 +824,17 @@ __global__ void mat_bc_kernel(const MatBcArgs a) {
     }
     if (a.bval_out) a.bval_out[row] = val;
     const float res = val - a.targets[bc.tgt_off + r];
-    atomicAdd(a.slot_sum + bc.slot, (double)res * (double)res);
+    {  // block-level accumulation: one shared-memory atomic per warp when the warp's rows share a slot
+      const unsigned act = __activemask();
+      double sq = (double)res * (double)res;
+      const int slot0 = __shfl_sync(act, bc.slot, __ffs(act) - 1);
+      if (act == 0xffffffffu && __all_sync(act, bc.slot == slot0)) {
+        for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(act, sq, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sh_slot[slot0], sq);
+      } else {
+        atomicAdd(&sh_slot[bc.slot], sq);
+      }
+    }
     if (!a.grad) continue;
     const float seed = 2.f * a.slot_scale[bc.slot] * res;
     for (int k = 0; k < bc.K; ++k) {
@@ -509,38 +860,59 @@ __global__ void mat_bc_kernel(const MatBcArgs a) {
       }
     }
   }
+  __syncthreads();
+  if ((int)threadIdx.x < a.n_bc_slots && sh_slot[threadIdx.x] != 0.0) atomicAdd(a.slot_sum + threadIdx.x, sh_slot[threadIdx.x]);
+  if (!a.out) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) sh_ticket = atomicAdd(a.ticket, 1u);
+  __syncthreads();
+  if (sh_ticket != gridDim.x - 1) return;
+  // last block: every other block's slot sums are visible
+  __threadfence();
+  if (threadIdx.x == 0) *a.ticket = 0u;
+  mat_finalize_block(a.part_loss, a.n_ctas, a.n_eq, a.n_cells, a.slot_sum, a.n_bc_slots, a.slot_lambda, a.slot_len, a.out);
 }
 
-__global__ void mat_finalize_kernel(const double* __restrict__ part_loss, int n_ctas, int n_eq, double n_cells,
-                                    const double* __restrict__ bc_sum, int n_bc_slots,
-                                    const double* __restrict__ slot_lambda, const double* __restrict__ slot_len,
-                                    float* __restrict__ out) {
+// ordered reduction of the per-CTA loss partials + loss assembly, by one block of any size <= 256
+__device__ void mat_finalize_block(const double* __restrict__ part_loss, int n_ctas, int n_eq, double n_cells,
+                                   double* __restrict__ bc_sum, int n_bc_slots, const double* __restrict__ slot_lambda,
+                                   const double* __restrict__ slot_len, float* __restrict__ out) {
   __shared__ double sh[256];
   __shared__ double mse[32];
   for (int e = 0; e < n_eq; ++e) {
     double s = 0.0;
     for (int c = threadIdx.x; c < n_ctas; c += blockDim.x) s += part_loss[(size_t)c * n_eq + e];
-    sh[threadIdx.x] = s;
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
     __syncthreads();
-    for (int o = blockDim.x / 2; o; o >>= 1) {
-      if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-      __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) t += sh[w];
+      mse[e] = t / n_cells;
     }
-    if (threadIdx.x == 0) mse[e] = sh[0] / n_cells;
     __syncthreads();
   }
   if (threadIdx.x == 0) {
     double loss = 0.0, lossn = 0.0;
     for (int e = 0; e < n_eq; ++e) { out[2 + e] = (float)mse[e]; loss += slot_lambda[e] * mse[e]; lossn += mse[e]; }
     for (int s = 0; s < n_bc_slots; ++s) {
-      const double m = bc_sum[s] / slot_len[n_eq + s];
+      const double m = *reinterpret_cast<volatile double*>(bc_sum + s) / slot_len[n_eq + s];
       out[2 + n_eq + s] = (float)m;
       loss += slot_lambda[n_eq + s] * m;
       lossn += m;
+      bc_sum[s] = 0.0;                                       // ready for the next call
     }
     out[0] = (float)loss;
     out[1] = (float)lossn;
   }
+}
+
+__global__ void mat_finalize_kernel(const double* __restrict__ part_loss, int n_ctas, int n_eq, double n_cells,
+                                    double* __restrict__ bc_sum, int n_bc_slots,
+                                    const double* __restrict__ slot_lambda, const double* __restrict__ slot_len,
+                                    float* __restrict__ out) {
+  mat_finalize_block(part_loss, n_ctas, n_eq, n_cells, bc_sum, n_bc_slots, slot_lambda, slot_len, out);
 }
 
 }  // namespace tdb
@@ -569,7 +941,14 @@ struct tdb200_mat_plan {
   double* d_slot_lambda = nullptr;
   double* d_slot_len = nullptr;
   double* d_part_loss = nullptr;
+  long long l1_fbuf_off[2] = {-1, -1};     // lin1 kernel: forcing buffer offsets into the coefficient arena
+  int l1_n_fbuf = 0;
+  bool l1_regs = false;
   double* d_bc_sum = nullptr;
+  unsigned int* d_ticket = nullptr;
+  int cx_hy = 0, cx_hx = 0;                // cross kernel: reach and non-zero offset masks of the composite stencil
+  unsigned cx_my = 0, cx_mx = 0;
+  bool cross = false;
   int n_ctas = 0;
   int n_bc_slots = 0;
   int n_slots = 0;
@@ -679,7 +1058,32 @@ int tdb200_mat_plan_create(const tdb200_mat_desc* desc, const tdb200_mat_field* 
     a.frc_begin[desc->n_eq] = n_frc;
     a.linear = (linear && n_lin <= tdb::kMatMaxTaps) ? 1 : 0;
     a.n_lin = n_lin;
-    a.lin1 = (a.linear && desc->n_eq == 1 && desc->n_var == 1 && n_taps <= 16) ? 1 : 0;
+    int n_fbuf = 0;
+    float fconst = 0.f;
+    for (int t = 0; t < n_frc && a.linear; ++t) {
+      if (a.frc_buf[t] >= 0) { if (n_fbuf < 2) p->l1_fbuf_off[n_fbuf] = a.frc_buf[t]; ++n_fbuf; }
+      else fconst += a.frc_const[t];
+    }
+    a.l1_fconst = fconst;
+    p->l1_n_fbuf = n_fbuf;
+    a.lin1 = (a.linear && desc->n_eq == 1 && desc->n_var == 1 && n_fbuf <= 2 && hy <= tdb::kL1MaxH &&
+              hx <= tdb::kL1MaxH) ? 1 : 0;
+    p->l1_regs = n_taps <= 16;                            // the register-tap kernel holds at most 16 taps
+    if (getenv("TDB200_MAT_NO_LIN1")) a.lin1 = 0;        // debugging aid: force the generic kernel
+    if (a.lin1) {                                         // composite cross stencil: weights by offset
+      for (int i = 0; i < 9; ++i) a.cx_wy[i] = a.cx_wx[i] = 0.f;
+      a.cx_wc = 0.f;
+      unsigned my = 0, mx = 0;
+      for (int t = 0; t < n_taps; ++t) {
+        const int m = a.tap_m[t];
+        if (m == 0) a.cx_wc += a.tap_w[t];
+        else if (a.tap_axis[t] == 0) { a.cx_wy[m + hy] += a.tap_w[t]; my |= 1u << (m + hy); }
+        else { a.cx_wx[m + hx] += a.tap_w[t]; mx |= 1u << (m + hx); }
+      }
+      p->cx_hy = hy; p->cx_hx = hx; p->cx_my = my; p->cx_mx = mx;
+      p->cross = tdb::mat_cross_supported(hy, hx, my, mx) && desc->n1 % 4 == 0 && !getenv("TDB200_MAT_NO_CROSS");
+      if (!p->cross && !p->l1_regs) a.lin1 = 0;           // neither specialised kernel applies
+    }
     a.edge_y = ey; a.edge_x = ex;
   }
   a.tiles_x = (desc->n1 + tdb::kMatTX - 1) / tdb::kMatTX;
@@ -694,7 +1098,10 @@ int tdb200_mat_plan_create(const tdb200_mat_desc* desc, const tdb200_mat_field* 
   if (n_terms) MCU(cudaMemcpy(p->d_terms, terms, sizeof(tdb200_term) * n_terms, cudaMemcpyHostToDevice));
   MCU(cudaMalloc(&p->d_factors, sizeof(tdb200_factor) * (n_factors > 0 ? n_factors : 1)));
   if (n_factors) MCU(cudaMemcpy(p->d_factors, factors, sizeof(tdb200_factor) * n_factors, cudaMemcpyHostToDevice));
-  MCU(cudaMalloc(&p->d_part_loss, sizeof(double) * (size_t)p->n_ctas * desc->n_eq));
+  {
+    const int l1 = a.lin1 ? tdb::mat_lin1_ctas(a) : 0;   // (the cross kernel uses the same tiling)
+    MCU(cudaMalloc(&p->d_part_loss, sizeof(double) * (size_t)(p->n_ctas > l1 ? p->n_ctas : l1) * desc->n_eq));
+  }
   a.band = p->d_band; a.terms = p->d_terms; a.factors = p->d_factors; a.part_loss = p->d_part_loss;
   tdb::MatBcArgs& b = p->bc;
   b.n_var = desc->n_var; b.n0 = desc->n0; b.n1 = desc->n1; b.n_fields = desc->n_fields; b.n_eq = desc->n_eq;
@@ -743,6 +1150,9 @@ int tdb200_mat_plan_set_bcs(tdb200_mat_plan* p, int32_t n_bcs, const tdb200_mat_
   MCU(cudaMalloc(&p->d_slot_len, sizeof(double) * n_slots));
   MCU(cudaMemcpy(p->d_slot_len, slot_len, sizeof(double) * n_slots, cudaMemcpyHostToDevice));
   MCU(cudaMalloc(&p->d_bc_sum, sizeof(double) * (p->n_bc_slots > 0 ? p->n_bc_slots : 1)));
+  MCU(cudaMemset(p->d_bc_sum, 0, sizeof(double) * (p->n_bc_slots > 0 ? p->n_bc_slots : 1)));
+  if (!p->d_ticket) MCU(cudaMalloc(&p->d_ticket, sizeof(unsigned int)));
+  MCU(cudaMemset(p->d_ticket, 0, sizeof(unsigned int)));
   for (int e = 0; e < n_eq; ++e) p->args.eq_scale[e] = (float)(slot_lambda[e] / slot_len[e]);
   tdb::MatBcArgs& b = p->bc;
   b.bcs = p->d_bcs; b.n_bcs = n_bcs; b.bc_row_begin = p->d_bc_row_begin; b.cells = cells_dev; b.targets = targets_dev;
@@ -759,21 +1169,42 @@ static int mat_run(tdb200_mat_plan* p, const float* u, float* grad, float* op_ou
   MCU(cudaSetDevice(p->device));
   tdb::MatArgs a = p->args;
   a.u = u; a.grad = grad; a.op_out = op_out;
-  MCU(cudaMemsetAsync(p->d_bc_sum, 0, sizeof(double) * (p->n_bc_slots > 0 ? p->n_bc_slots : 1), s));
-  dim3 grid(a.tiles_x, a.tiles_y);
-  tdb::mat_residual_adjoint_kernel<<<grid, tdb::kMatThreads, p->smem, s>>>(a);
-  MCU(cudaGetLastError());
+  int n_ctas = p->n_ctas;
+  if (a.lin1 && !op_out) {
+    // specialised kernels (loss + gradient, or loss only); per-cell operator values go through the generic kernel
+    for (int i = 0; i < 2; ++i) a.l1_fbuf[i] = i < p->l1_n_fbuf ? a.coeffs + p->l1_fbuf_off[i] : nullptr;
+    auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    const bool vec_ok = aligned16(u) && aligned16(grad) && aligned16(a.l1_fbuf[0]) && aligned16(a.l1_fbuf[1]);
+    if (p->cross && !vec_ok && !p->l1_regs) return mat_invalid("mat-mode tensors must be 16-byte aligned");
+    if (p->cross && vec_ok) {
+      MCU(tdb::launch_mat_cross(a, p->cx_hy, p->cx_hx, p->cx_my, p->cx_mx, s));
+      n_ctas = tdb::mat_cross_ctas(a);
+    } else {
+      MCU(tdb::launch_mat_lin1(a, s));
+      n_ctas = tdb::mat_lin1_ctas(a);
+    }
+  } else {
+    dim3 grid(a.tiles_x, a.tiles_y);
+    tdb::mat_residual_adjoint_kernel<<<grid, tdb::kMatThreads, p->smem, s>>>(a);
+    MCU(cudaGetLastError());
+  }
+  // boundary rows; the last block to finish reduces the loss partials and assembles the loss (and re-zeroes the
+  // slot sums and its ticket for the next call)
   if (p->n_bc_rows > 0) {
     tdb::MatBcArgs b = p->bc;
     b.u = u; b.grad = grad; b.bval_out = bval_out;
+    b.part_loss = p->d_part_loss; b.n_ctas = n_ctas; b.n_bc_slots = p->n_bc_slots;
+    b.n_cells = (double)p->desc.n0 * (double)p->desc.n1;
+    b.slot_lambda = p->d_slot_lambda; b.slot_len = p->d_slot_len; b.out = out; b.ticket = p->d_ticket;
     const int blocks = (int)((p->n_bc_rows + 127) / 128);
     tdb::mat_bc_kernel<<<blocks < 1184 ? blocks : 1184, 128, 0, s>>>(b);
     MCU(cudaGetLastError());
+  } else {
+    tdb::mat_finalize_kernel<<<1, 256, 0, s>>>(p->d_part_loss, n_ctas, p->desc.n_eq,
+                                              (double)p->desc.n0 * (double)p->desc.n1, p->d_bc_sum, p->n_bc_slots,
+                                              p->d_slot_lambda, p->d_slot_len, out);
+    MCU(cudaGetLastError());
   }
-  tdb::mat_finalize_kernel<<<1, 256, 0, s>>>(p->d_part_loss, p->n_ctas, p->desc.n_eq,
-                                            (double)p->desc.n0 * (double)p->desc.n1, p->d_bc_sum, p->n_bc_slots,
-                                            p->d_slot_lambda, p->d_slot_len, out);
-  MCU(cudaGetLastError());
   return TDB200_OK;
 }
 
@@ -788,14 +1219,19 @@ int tdb200_mat_eval_fields(tdb200_mat_plan* p, const float* u_dev, float* op_dev
 }
 
 int64_t tdb200_mat_plan_out_size(const tdb200_mat_plan* p) { return p ? 2 + p->n_slots : 0; }
-int32_t tdb200_mat_plan_launches_per_call(const tdb200_mat_plan* p) { return p ? (p->n_bc_rows > 0 ? 3 : 2) : 0; }
+int32_t tdb200_mat_plan_launches_per_call(const tdb200_mat_plan* p) { return p ? 2 : 0; }
+
+int32_t tdb200_mat_plan_kernel_kind(const tdb200_mat_plan* p) {
+  if (!p || !p->args.lin1) return 0;
+  return p->cross ? 2 : 1;
+}
 
 void tdb200_mat_plan_destroy(tdb200_mat_plan* p) {
   if (!p) return;
   cudaSetDevice(p->device);
   cudaFree(p->d_band); cudaFree(p->d_terms); cudaFree(p->d_factors); cudaFree(p->d_bcs); cudaFree(p->d_bc_row_begin);
   cudaFree(p->d_slot_scale); cudaFree(p->d_slot_lambda); cudaFree(p->d_slot_len); cudaFree(p->d_part_loss);
-  cudaFree(p->d_bc_sum);
+  cudaFree(p->d_bc_sum); cudaFree(p->d_ticket);
   delete p;
 }
 
