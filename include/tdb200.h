@@ -172,7 +172,8 @@ int tdb200_mat_eval_fields(tdb200_mat_plan* plan, const float* u_dev, float* op_
 int64_t tdb200_mat_plan_out_size(const tdb200_mat_plan* plan);
 int32_t tdb200_mat_plan_launches_per_call(const tdb200_mat_plan* plan);
 /* Which residual kernel tdb200_mat_loss_grad launches: 0 = generic tiled kernel (any operator), 1 = register-tap
- * kernel (one linear constant-coefficient equation), 2 = vectorised cross-stencil kernel (1 + n1 % 4 == 0). */
+ * kernel (one linear constant-coefficient equation), 2 = vectorised cross-stencil kernel (1 + n1 % 4 == 0),
+ * 3 = persistent TMA-pipelined cross-stencil kernel (2 + at most one forcing buffer). */
 int32_t tdb200_mat_plan_kernel_kind(const tdb200_mat_plan* plan);
 void tdb200_mat_plan_destroy(tdb200_mat_plan* plan);
 

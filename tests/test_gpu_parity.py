@@ -228,7 +228,7 @@ def test_mat_large_grid_properties(n, amp, gtol, cuda_default):
 @pytest.mark.parametrize('case', ['poisson_p2_64x64', 'poisson_p2_40x132', 'poisson_p2_200x260', 'poisson_p3_72x136',
                                   'heat_p2_96x128', 'heat_p2_33x260'])
 def test_mat_specialised_kernels_agree(case, cuda_default, monkeypatch):
-    """The vectorised cross-stencil kernel, the register-tap kernel and the generic tiled kernel evaluate the same
+    """The persistent TMA kernel, the vectorised cross-stencil kernel, the register-tap kernel and the generic tiled kernel evaluate the same
     loss and gradient (interior tiles, all four kinds of boundary tiles, partial tiles)."""
     kind, p, shape = case.split('_')
     n0, n1 = (int(x) for x in shape.split('x'))
@@ -239,9 +239,10 @@ def test_mat_specialised_kernels_agree(case, cuda_default, monkeypatch):
         prob = problems.heat_mat(tdb, 'float32', n=n0 - 1, nt=n1 - 1, derivative_points=dp)
     u = torch.as_tensor(np.random.default_rng(3).random(prob.mat_shape, dtype=np.float32)).to('cuda:0').contiguous()
     res = {}
-    for tag, env in (('cross-vec4', None), ('register-tap', 'TDB200_MAT_NO_CROSS'), ('generic', 'TDB200_MAT_NO_LIN1')):
-        monkeypatch.delenv('TDB200_MAT_NO_CROSS', raising=False)
-        monkeypatch.delenv('TDB200_MAT_NO_LIN1', raising=False)
+    for tag, env in (('cross-tma', None), ('cross-vec4', 'TDB200_MAT_NO_TMA'), ('register-tap', 'TDB200_MAT_NO_CROSS'),
+                     ('generic', 'TDB200_MAT_NO_LIN1')):
+        for e in ('TDB200_MAT_NO_TMA', 'TDB200_MAT_NO_CROSS', 'TDB200_MAT_NO_LIN1'):
+            monkeypatch.delenv(e, raising=False)
         if env:
             monkeypatch.setenv(env, '1')
         model = tdb.Model(u.clone(), prob.domain, prob.equation, prob.conditions)
@@ -253,7 +254,7 @@ def test_mat_specialised_kernels_agree(case, cuda_default, monkeypatch):
         assert torch.equal(grad, grad2) and float(out[0]) == pytest.approx(float(out2[0]), rel=1e-6)
         res[tag] = (out.double().cpu().numpy(), grad.double().cpu().numpy())
     ref_out, ref_grad = res['generic']
-    for tag in ('cross-vec4', 'register-tap'):
+    for tag in ('cross-tma', 'cross-vec4', 'register-tap'):
         out, grad = res[tag]
         np.testing.assert_allclose(out, ref_out, rtol=2e-5)
         assert np.abs(grad - ref_grad).max() <= 2e-4 * np.abs(ref_grad).max(), tag

@@ -10,6 +10,7 @@
 //      coefficient tensors, write the gradient (12 B / cell for Poisson) + halo re-reads served by L2.
 //   2. a small kernel for the boundary rows (gather, residual, scatter-add of the adjoint),
 //   3. a finalize kernel (ordered reduction of per-CTA loss partials, loss assembly).
+#include <cuda.h>
 #include <stdlib.h>
 #include <string>
 #include <vector>
@@ -520,6 +521,288 @@ static int mat_cross_ctas(const MatArgs& a) {
   return ((a.n1 + kCxTX - 1) / kCxTX) * ((a.n0 + kCxTY - 1) / kCxTY);
 }
 
+// ---- persistent TMA cross-stencil kernel -----------------------------------------------------------------
+// The production path for BASELINE config 4.  One CTA pair per SM walks over the 128 x 32 tiles; a single thread
+// stages tile t+1 (the u box with both halos and the forcing box with one halo, out-of-range elements zero
+// filled by the TMA unit) with two cp.async.bulk.tensor.2d loads completing on an mbarrier while all threads work
+// on tile t: the HBM stream never stops, nothing is staged through registers and no thread computes a load address.
+constexpr int kCtThreads = 256;
+
+__device__ __forceinline__ uint32_t ct_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ct_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(ct_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ct_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(ct_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ct_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = ct_smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void ct_tma_load_2d(float* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               :: "r"(ct_smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(ct_smem_u32(bar)) : "memory");
+}
+
+// in-domain cells of the seed region whose stencil rows are special: (a) whole special rows, warp-uniform;
+// (b) special columns of the remaining rows, compact enumeration
+template <int HY, int HX>
+__device__ __forceinline__ void cx_fix_seeds(const MatArgs& a, const float* __restrict__ us, float* __restrict__ ss,
+                                             int ty0, int tx0, float& lacc) {
+  constexpr int RY = kCxTY + 2 * HY;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = a.n0, n1 = a.n1, zy = a.edge_y, zx = a.edge_x;
+  const float* __restrict__ f0 = a.l1_fbuf[0];
+  const float* __restrict__ f1 = a.l1_fbuf[1];
+  const float fc0 = a.l1_fconst, scale2 = 2.f * a.eq_scale[0];
+  auto special_seed = [&](int ly, int lx) {                // (ly, lx): seed-region coordinates
+    const int gy = ty0 - HY + ly, gx = tx0 - 4 + lx;
+    const size_t cell = (size_t)gy * n1 + gx;
+    float res = fc0;
+    if (f0) res += __ldg(f0 + cell);
+    if (f1) res += __ldg(f1 + cell);
+    for (int t = 0; t < a.n_lin; ++t)
+      res = fmaf(a.lin_c[t], field_value(a, a.fld[a.lin_q[t]], us, kCxPU, 0, ly + HY, lx + 4, gy, gx), res);
+    if (ly >= HY && ly < HY + kCxTY && lx >= 4 && lx < 4 + kCxTX) lacc = fmaf(res, res, lacc);
+    ss[ly * kCxPR + lx] = scale2 * res;
+  };
+  for (int ly = warp; ly < RY; ly += 8) {
+    const int gy = ty0 - HY + ly;
+    if (gy < 0 || gy >= n0 || (gy >= zy && gy < n0 - zy)) continue;
+    for (int lx = 4 - HX + lane; lx < 4 + kCxTX + HX; lx += 32) {
+      const int gx = tx0 - 4 + lx;
+      if (gx >= 0 && gx < n1) special_seed(ly, lx);
+    }
+  }
+  for (int k = tid; k < RY * 2 * zx; k += kCtThreads) {
+    const int ly = k / (2 * zx), ci = k - ly * (2 * zx);
+    const int gy = ty0 - HY + ly, gx = ci < zx ? ci : n1 - 2 * zx + ci;
+    const int lx = gx - (tx0 - 4);
+    if (gy >= zy && gy < n0 - zy && lx >= 4 - HX && lx < 4 + kCxTX + HX) special_seed(ly, lx);
+  }
+}
+
+// cells of the tile whose transposed stencil gathers from a special row
+template <int HY, int HX>
+__device__ __forceinline__ void cx_fix_grad(const MatArgs& a, const float* __restrict__ ss, int ty0, int tx0) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = a.n0, n1 = a.n1;
+  const int zy3 = a.edge_y + HY, zx3 = a.edge_x + HX;
+  auto special_grad = [&](int cy, int cx) {
+    const int gy = ty0 + cy, gx = tx0 + cx;
+    const float* sc = ss + (cy + HY) * kCxPR + cx + 4;
+    float g = 0.f;
+    for (int t = 0; t < a.n_lin; ++t) {
+      const tdb200_mat_field& f = a.fld[a.lin_q[t]];
+      float s = 0.f;
+      if (f.order == 0) s = sc[0];
+      else if (f.axis == 0) {
+        for (int m = -f.half_width; m <= f.half_width; ++m) {
+          const int yy = gy + m;
+          if (yy >= 0 && yy < n0) s = fmaf(band_coef(a.band, f, n0, yy, -m), sc[m * kCxPR], s);
+        }
+      } else {
+        for (int m = -f.half_width; m <= f.half_width; ++m) {
+          const int xx = gx + m;
+          if (xx >= 0 && xx < n1) s = fmaf(band_coef(a.band, f, n1, xx, -m), sc[m], s);
+        }
+      }
+      g = fmaf(a.lin_c[t], s, g);
+    }
+    a.grad[(size_t)gy * n1 + gx] = g;
+  };
+  for (int cy = warp; cy < kCxTY; cy += 8) {
+    const int gy = ty0 + cy;
+    if (gy >= n0 || (gy >= zy3 && gy < n0 - zy3)) continue;
+    for (int cx = lane; cx < kCxTX; cx += 32)
+      if (tx0 + cx < n1) special_grad(cy, cx);
+  }
+  for (int k = tid; k < kCxTY * 2 * zx3; k += kCtThreads) {
+    const int cy = k / (2 * zx3), ci = k - cy * (2 * zx3);
+    const int gy = ty0 + cy, gx = ci < zx3 ? ci : n1 - 2 * zx3 + ci;
+    const int cx = gx - tx0;
+    if (gy < n0 && gy >= zy3 && gy < n0 - zy3 && cx >= 0 && cx < kCxTX) special_grad(cy, cx);
+  }
+}
+
+// per stage: u box [UY][PU] then forcing box [RY][PR]; both sub-buffers start 128-byte aligned (TMA destination)
+__host__ __device__ constexpr size_t ct_round32(size_t n) { return (n + 31) / 32 * 32; }
+template <int HY, int HX>
+__host__ __device__ constexpr size_t ct_u_floats() { return ct_round32((size_t)(kCxTY + 4 * HY) * kCxPU); }
+template <int HY, int HX>
+__host__ __device__ constexpr size_t ct_stage_floats() { return ct_u_floats<HY, HX>() + ct_round32((size_t)(kCxTY + 2 * HY) * kCxPR); }
+template <int HY, int HX>
+constexpr size_t ct_smem_bytes() {
+  return (2 * ct_stage_floats<HY, HX>() + ct_round32((size_t)(kCxTY + 2 * HY) * kCxPR)) * sizeof(float) + 128 /*align*/ + 64;
+}
+
+template <int HY, int HX, unsigned MY, unsigned MX>
+__global__ void __launch_bounds__(kCtThreads, 2) mat_cross_tma_kernel(const MatArgs a, const __grid_constant__ CUtensorMap map_u,
+                                                                      const __grid_constant__ CUtensorMap map_f) {
+  constexpr int UY = kCxTY + 4 * HY, RY = kCxTY + 2 * HY;
+  constexpr int N2 = (RY * kCxQR + kCtThreads - 1) / kCtThreads;
+  constexpr uint32_t kTxBytes = (uint32_t)((UY * kCxPU + RY * kCxPR) * sizeof(float));
+  extern __shared__ uint8_t sm_ct_raw[];
+  float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sm_ct_raw) + 127) & ~uintptr_t(127));
+  float* ss = base + 2 * ct_stage_floats<HY, HX>();          // seeds [RY][PR]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ss + ct_round32((size_t)RY * kCxPR));
+  __shared__ double red[kCtThreads / 32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = a.n0, n1 = a.n1;
+  const int tiles_x = (n1 + kCxTX - 1) / kCxTX, n_tiles = tiles_x * ((n0 + kCxTY - 1) / kCxTY);
+  const bool has_f = a.l1_fbuf[0] != nullptr;
+  if (tid == 0) {
+    ct_mbar_init(bars, 1);
+    ct_mbar_init(bars + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto stage_tile = [&](int tile, int st) {                  // one thread
+    float* us = base + st * ct_stage_floats<HY, HX>();
+    float* fs = us + ct_u_floats<HY, HX>();
+    const int ty0 = (tile / tiles_x) * kCxTY, tx0 = (tile % tiles_x) * kCxTX;
+    ct_mbar_expect_tx(bars + st, has_f ? kTxBytes : (uint32_t)(UY * kCxPU * sizeof(float)));
+    ct_tma_load_2d(us, &map_u, tx0 - 8, ty0 - 2 * HY, bars + st);
+    if (has_f) ct_tma_load_2d(fs, &map_f, tx0 - 4, ty0 - HY, bars + st);
+  };
+  float wy[2 * HY + 1], wx[2 * HX + 1];
+#pragma unroll
+  for (int i = 0; i <= 2 * HY; ++i) wy[i] = a.cx_wy[i];
+#pragma unroll
+  for (int i = 0; i <= 2 * HX; ++i) wx[i] = a.cx_wx[i];
+  const float wc = a.cx_wc, fc0 = a.l1_fconst, scale2 = 2.f * a.eq_scale[0];
+  const int zy = a.edge_y, zx = a.edge_x;
+  double dacc = 0.0;
+  uint32_t phase[2] = {0u, 0u};
+  int tile = blockIdx.x, st = 0;
+  if (tid == 0 && tile < n_tiles) stage_tile(tile, 0);
+  for (; tile < n_tiles; tile += gridDim.x, st ^= 1) {
+    if (tid == 0 && tile + (int)gridDim.x < n_tiles) stage_tile(tile + gridDim.x, st ^ 1);
+    const float* us = base + st * ct_stage_floats<HY, HX>();
+    const float* fs = us + ct_u_floats<HY, HX>();
+    const int ty0 = (tile / tiles_x) * kCxTY, tx0 = (tile % tiles_x) * kCxTX;
+    const bool interior = ty0 - 2 * HY >= zy && ty0 + kCxTY + 2 * HY <= n0 - zy && tx0 - 8 >= zx && tx0 + kCxTX + 8 <= n1 - zx;
+    ct_mbar_wait(bars + st, phase[st]);
+    phase[st] ^= 1u;
+    float lacc = 0.f;
+    // ---- residual seeds on tile + halo ----
+#pragma unroll
+    for (int k = 0; k < N2; ++k) {
+      const int idx = tid + kCtThreads * k;
+      if (idx < RY * kCxQR) {
+        const int ly = idx / kCxQR, q = idx - ly * kCxQR;
+        float r[4] = {fc0, fc0, fc0, fc0};
+        if (has_f) {
+          const float4 fv = *reinterpret_cast<const float4*>(fs + ly * kCxPR + 4 * q);
+          r[0] += fv.x; r[1] += fv.y; r[2] += fv.z; r[3] += fv.w;
+        }
+        cx_apply<HY, HX, MY, MX, false, kCxPU>(us + (ly + HY) * kCxPU + 4 * q + 4, wy, wx, wc, r);
+        const bool core = ly >= HY && ly < HY + kCxTY && q >= 1 && q <= kCxTX / 4;
+        float sd[4];
+        if (interior) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { sd[i] = scale2 * r[i]; if (core) lacc = fmaf(r[i], r[i], lacc); }
+        } else {
+          const int gy = ty0 - HY + ly, gx = tx0 - 4 + 4 * q;
+          const bool rowreg = gy >= zy && gy < n0 - zy;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const bool reg = rowreg && gx + i >= zx && gx + i < n1 - zx;   // regular interior row of the operators
+            sd[i] = reg ? scale2 * r[i] : 0.f;
+            if (core && reg) lacc = fmaf(r[i], r[i], lacc);
+          }
+        }
+        *reinterpret_cast<float4*>(ss + ly * kCxPR + 4 * q) = make_float4(sd[0], sd[1], sd[2], sd[3]);
+      }
+    }
+    if (!interior) {                                         // CTA-uniform
+      __syncthreads();
+      cx_fix_seeds<HY, HX>(a, us, ss, ty0, tx0, lacc);
+    }
+    dacc += (double)lacc;
+    __syncthreads();
+    // ---- transposed stencil -> gradient of the tile ----
+    if (a.grad) {
+#pragma unroll
+      for (int i = 0; i < kCxTY / 8; ++i) {
+        const int cy = warp + 8 * i, gy = ty0 + cy, gx = tx0 + 4 * lane;
+        if (gy < n0 && gx < n1) {
+          float g[4] = {0.f, 0.f, 0.f, 0.f};
+          cx_apply<HY, HX, MY, MX, true, kCxPR>(ss + (cy + HY) * kCxPR + 4 * lane + 4, wy, wx, wc, g);
+          *reinterpret_cast<float4*>(a.grad + (size_t)gy * n1 + gx) = make_float4(g[0], g[1], g[2], g[3]);
+        }
+      }
+      if (!interior) {
+        __syncthreads();                                     // the fix-up overwrites cells stored above
+        cx_fix_grad<HY, HX>(a, ss, ty0, tx0);
+      }
+    }
+    __syncthreads();                                         // seeds and this stage's buffers are free again
+  }
+  for (int o = 16; o; o >>= 1) dacc += __shfl_xor_sync(0xffffffffu, dacc, o);
+  if (lane == 0) red[warp] = dacc;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int w = 0; w < kCtThreads / 32; ++w) s += red[w];
+    a.part_loss[blockIdx.x] = s;
+  }
+}
+
+template <int HY, int HX, unsigned MY, unsigned MX>
+static cudaError_t launch_mat_cross_tma_t(const MatArgs& a, const CUtensorMap& mu, const CUtensorMap& mf, int n_sms, int* n_ctas,
+                                          cudaStream_t s) {
+  constexpr size_t smem = ct_smem_bytes<HY, HX>();
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(mat_cross_tma_kernel<HY, HX, MY, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int per_sm = smem * 2 <= 227 * 1024 ? 2 : 1;
+  const int n_tiles = ((a.n1 + kCxTX - 1) / kCxTX) * ((a.n0 + kCxTY - 1) / kCxTY);
+  int grid = n_sms * per_sm;
+  if (grid > n_tiles) grid = n_tiles;
+  *n_ctas = grid;
+  mat_cross_tma_kernel<HY, HX, MY, MX><<<grid, kCtThreads, smem, s>>>(a, mu, mf);
+  return cudaGetLastError();
+}
+static cudaError_t launch_mat_cross_tma(const MatArgs& a, int hy, int hx, unsigned my, unsigned mx, const CUtensorMap& mu,
+                                        const CUtensorMap& mf, int n_sms, int* n_ctas, cudaStream_t s) {
+#define X(A, B, C, D) if (hy == A && hx == B && (my & ~C) == 0 && (mx & ~D) == 0) return launch_mat_cross_tma_t<A, B, C, D>(a, mu, mf, n_sms, n_ctas, s);
+  TDB_CROSS_SHAPES(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+// 2-D fp32 tensor map over a row-major [n0][n1] array with a [box_y][box_x] box, no swizzle, zero fill out of range
+typedef CUresult (*tdb_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bool make_map_2d(CUtensorMap* map, const float* ptr, int n0, int n1, int box_y, int box_x) {
+  static tdb_encode_tiled_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<tdb_encode_tiled_fn>(f);
+  }
+  if (!fn) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)n1, (cuuint64_t)n0};
+  const cuuint64_t gstr[1] = {(cuuint64_t)n1 * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)box_x, (cuuint32_t)box_y};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 __global__ void __launch_bounds__(kMatThreads) mat_residual_adjoint_kernel(const MatArgs a) {
   extern __shared__ __align__(16) float sm[];
   const int hy = a.hy, hx = a.hx;
@@ -949,6 +1232,11 @@ struct tdb200_mat_plan {
   int cx_hy = 0, cx_hx = 0;                // cross kernel: reach and non-zero offset masks of the composite stencil
   unsigned cx_my = 0, cx_mx = 0;
   bool cross = false;
+  bool tma = false;                        // persistent TMA variant of the cross kernel (single forcing buffer)
+  CUtensorMap map_u{}, map_f{};
+  const float* map_u_ptr = nullptr;
+  const float* map_f_ptr = nullptr;
+  int n_sms = 148;
   int n_ctas = 0;
   int n_bc_slots = 0;
   int n_slots = 0;
@@ -1083,6 +1371,8 @@ int tdb200_mat_plan_create(const tdb200_mat_desc* desc, const tdb200_mat_field* 
       p->cx_hy = hy; p->cx_hx = hx; p->cx_my = my; p->cx_mx = mx;
       p->cross = tdb::mat_cross_supported(hy, hx, my, mx) && desc->n1 % 4 == 0 && !getenv("TDB200_MAT_NO_CROSS");
       if (!p->cross && !p->l1_regs) a.lin1 = 0;           // neither specialised kernel applies
+      p->tma = p->cross && n_fbuf <= 1 && !getenv("TDB200_MAT_NO_TMA");
+      cudaDeviceGetAttribute(&p->n_sms, cudaDevAttrMultiProcessorCount, device);
     }
     a.edge_y = ey; a.edge_x = ex;
   }
@@ -1176,7 +1466,22 @@ static int mat_run(tdb200_mat_plan* p, const float* u, float* grad, float* op_ou
     auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     const bool vec_ok = aligned16(u) && aligned16(grad) && aligned16(a.l1_fbuf[0]) && aligned16(a.l1_fbuf[1]);
     if (p->cross && !vec_ok && !p->l1_regs) return mat_invalid("mat-mode tensors must be 16-byte aligned");
-    if (p->cross && vec_ok) {
+    bool tma = p->tma && vec_ok;
+    if (tma) {                                             // tensor maps: re-encoded only when a pointer changes
+      const int uy = tdb::kCxTY + 4 * p->cx_hy, ry = tdb::kCxTY + 2 * p->cx_hy;
+      if (p->map_u_ptr != u) {
+        tma = tdb::make_map_2d(&p->map_u, u, a.n0, a.n1, uy, tdb::kCxPU);
+        p->map_u_ptr = tma ? u : nullptr;
+      }
+      if (tma && a.l1_fbuf[0] && p->map_f_ptr != a.l1_fbuf[0]) {
+        tma = tdb::make_map_2d(&p->map_f, a.l1_fbuf[0], a.n0, a.n1, ry, tdb::kCxPR);
+        p->map_f_ptr = tma ? a.l1_fbuf[0] : nullptr;
+      }
+    }
+    if (tma) {
+      MCU(tdb::launch_mat_cross_tma(a, p->cx_hy, p->cx_hx, p->cx_my, p->cx_mx, p->map_u, a.l1_fbuf[0] ? p->map_f : p->map_u,
+                                    p->n_sms, &n_ctas, s));
+    } else if (p->cross && vec_ok) {
       MCU(tdb::launch_mat_cross(a, p->cx_hy, p->cx_hx, p->cx_my, p->cx_mx, s));
       n_ctas = tdb::mat_cross_ctas(a);
     } else {
@@ -1223,7 +1528,7 @@ int32_t tdb200_mat_plan_launches_per_call(const tdb200_mat_plan* p) { return p ?
 
 int32_t tdb200_mat_plan_kernel_kind(const tdb200_mat_plan* p) {
   if (!p || !p->args.lin1) return 0;
-  return p->cross ? 2 : 1;
+  return p->cross ? (p->tma ? 3 : 2) : 1;
 }
 
 void tdb200_mat_plan_destroy(tdb200_mat_plan* p) {

@@ -284,7 +284,7 @@ class MatPlan:
         self._push_bcs()
         self.out_size = int(self.lib.tdb200_mat_plan_out_size(handle))
         self.launches_per_call = int(self.lib.tdb200_mat_plan_launches_per_call(handle))
-        self.kernel_kind = ('generic', 'register-tap', 'cross-vec4')[int(self.lib.tdb200_mat_plan_kernel_kind(handle))]
+        self.kernel_kind = ('generic', 'register-tap', 'cross-vec4', 'cross-tma')[int(self.lib.tdb200_mat_plan_kernel_kind(handle))]
         self.n_cells = n0 * n1
 
     def _push_bcs(self):
