@@ -53,6 +53,7 @@ struct MatArgs {
   float l1_fconst;                         // lin1: sum of the constant forcing terms
   const float* l1_fbuf[2];                 // lin1: up to two forcing buffers (absolute pointers, set per call)
   float cx_wy[9], cx_wx[9], cx_wc;         // cross kernel: weights by offset (index offset + reach), merged centre
+  unsigned int* tile_ctr;                  // persistent kernel: dynamic tile counter (zero on entry)
   int frc_begin[TDB200_MAX_COLS + 1];      // forcing terms of equation e
   float frc_const[kMatMaxForcing];
   long long frc_buf[kMatMaxForcing];       // coefficient buffer offset, -1: constant only
@@ -311,6 +312,87 @@ __device__ __forceinline__ void cx_apply(const float* __restrict__ c, const floa
   }
 }
 
+// in-domain cells of the seed region whose stencil rows are special: (a) whole special rows, warp-uniform;
+// (b) special columns of the remaining rows, compact enumeration
+template <int HY, int HX>
+__device__ __forceinline__ void cx_fix_seeds(const MatArgs& a, const float* __restrict__ us, float* __restrict__ ss,
+                                             int ty0, int tx0, float& lacc) {
+  constexpr int RY = kCxTY + 2 * HY;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = a.n0, n1 = a.n1, zy = a.edge_y, zx = a.edge_x;
+  const float* __restrict__ f0 = a.l1_fbuf[0];
+  const float* __restrict__ f1 = a.l1_fbuf[1];
+  const float fc0 = a.l1_fconst, scale2 = 2.f * a.eq_scale[0];
+  auto special_seed = [&](int ly, int lx) {                // (ly, lx): seed-region coordinates
+    const int gy = ty0 - HY + ly, gx = tx0 - 4 + lx;
+    const size_t cell = (size_t)gy * n1 + gx;
+    float res = fc0;
+    if (f0) res += __ldg(f0 + cell);
+    if (f1) res += __ldg(f1 + cell);
+    for (int t = 0; t < a.n_lin; ++t)
+      res = fmaf(a.lin_c[t], field_value(a, a.fld[a.lin_q[t]], us, kCxPU, 0, ly + HY, lx + 4, gy, gx), res);
+    if (ly >= HY && ly < HY + kCxTY && lx >= 4 && lx < 4 + kCxTX) lacc = fmaf(res, res, lacc);
+    ss[ly * kCxPR + lx] = scale2 * res;
+  };
+  for (int ly = warp; ly < RY; ly += (int)(blockDim.x >> 5)) {
+    const int gy = ty0 - HY + ly;
+    if (gy < 0 || gy >= n0 || (gy >= zy && gy < n0 - zy)) continue;
+    for (int lx = 4 - HX + lane; lx < 4 + kCxTX + HX; lx += 32) {
+      const int gx = tx0 - 4 + lx;
+      if (gx >= 0 && gx < n1) special_seed(ly, lx);
+    }
+  }
+  for (int k = tid; k < RY * 2 * zx; k += (int)blockDim.x) {
+    const int ly = k / (2 * zx), ci = k - ly * (2 * zx);
+    const int gy = ty0 - HY + ly, gx = ci < zx ? ci : n1 - 2 * zx + ci;
+    const int lx = gx - (tx0 - 4);
+    if (gy >= zy && gy < n0 - zy && lx >= 4 - HX && lx < 4 + kCxTX + HX) special_seed(ly, lx);
+  }
+}
+
+// cells of the tile whose transposed stencil gathers from a special row
+template <int HY, int HX>
+__device__ __forceinline__ void cx_fix_grad(const MatArgs& a, const float* __restrict__ ss, int ty0, int tx0) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = a.n0, n1 = a.n1;
+  const int zy3 = a.edge_y + HY, zx3 = a.edge_x + HX;
+  auto special_grad = [&](int cy, int cx) {
+    const int gy = ty0 + cy, gx = tx0 + cx;
+    const float* sc = ss + (cy + HY) * kCxPR + cx + 4;
+    float g = 0.f;
+    for (int t = 0; t < a.n_lin; ++t) {
+      const tdb200_mat_field& f = a.fld[a.lin_q[t]];
+      float s = 0.f;
+      if (f.order == 0) s = sc[0];
+      else if (f.axis == 0) {
+        for (int m = -f.half_width; m <= f.half_width; ++m) {
+          const int yy = gy + m;
+          if (yy >= 0 && yy < n0) s = fmaf(band_coef(a.band, f, n0, yy, -m), sc[m * kCxPR], s);
+        }
+      } else {
+        for (int m = -f.half_width; m <= f.half_width; ++m) {
+          const int xx = gx + m;
+          if (xx >= 0 && xx < n1) s = fmaf(band_coef(a.band, f, n1, xx, -m), sc[m], s);
+        }
+      }
+      g = fmaf(a.lin_c[t], s, g);
+    }
+    a.grad[(size_t)gy * n1 + gx] = g;
+  };
+  for (int cy = warp; cy < kCxTY; cy += (int)(blockDim.x >> 5)) {
+    const int gy = ty0 + cy;
+    if (gy >= n0 || (gy >= zy3 && gy < n0 - zy3)) continue;
+    for (int cx = lane; cx < kCxTX; cx += 32)
+      if (tx0 + cx < n1) special_grad(cy, cx);
+  }
+  for (int k = tid; k < kCxTY * 2 * zx3; k += (int)blockDim.x) {
+    const int cy = k / (2 * zx3), ci = k - cy * (2 * zx3);
+    const int gy = ty0 + cy, gx = ci < zx3 ? ci : n1 - 2 * zx3 + ci;
+    const int cx = gx - tx0;
+    if (gy < n0 && gy >= zy3 && gy < n0 - zy3 && cx >= 0 && cx < kCxTX) special_grad(cy, cx);
+  }
+}
+
 template <int HY, int HX, unsigned MY, unsigned MX, bool INTERIOR>
 __device__ __forceinline__ float mat_cross_tile(const MatArgs& a, float* __restrict__ us, float* __restrict__ ss,
                                                 int ty0, int tx0) {
@@ -383,33 +465,7 @@ __device__ __forceinline__ float mat_cross_tile(const MatArgs& a, float* __restr
   }
   if (!INTERIOR) {
     __syncthreads();
-    // fix-up: in-domain cells of the seed region whose stencil rows are special.  (a) whole special rows,
-    // warp-uniform; (b) special columns of the remaining rows, compact enumeration
-    auto special_seed = [&](int ly, int lx) {                // (ly, lx): seed-region coordinates
-      const int gy = ty0 - HY + ly, gx = tx0 - 4 + lx;
-      const size_t cell = (size_t)gy * n1 + gx;
-      float res = fc0;
-      if (f0) res += __ldg(f0 + cell);
-      if (f1) res += __ldg(f1 + cell);
-      for (int t = 0; t < a.n_lin; ++t)
-        res = fmaf(a.lin_c[t], field_value(a, a.fld[a.lin_q[t]], us, kCxPU, 0, ly + HY, lx + 4, gy, gx), res);
-      if (ly >= HY && ly < HY + kCxTY && lx >= 4 && lx < 4 + kCxTX) lacc = fmaf(res, res, lacc);
-      ss[ly * kCxPR + lx] = scale2 * res;
-    };
-    for (int ly = warp; ly < RY; ly += 8) {
-      const int gy = ty0 - HY + ly;
-      if (gy < 0 || gy >= n0 || (gy >= zy && gy < n0 - zy)) continue;
-      for (int lx = 4 - HX + lane; lx < 4 + kCxTX + HX; lx += 32) {
-        const int gx = tx0 - 4 + lx;
-        if (gx >= 0 && gx < n1) special_seed(ly, lx);
-      }
-    }
-    for (int k = tid; k < RY * 2 * zx; k += 256) {
-      const int ly = k / (2 * zx), ci = k - ly * (2 * zx);
-      const int gy = ty0 - HY + ly, gx = ci < zx ? ci : n1 - 2 * zx + ci;
-      const int lx = gx - (tx0 - 4);
-      if (gy >= zy && gy < n0 - zy && lx >= 4 - HX && lx < 4 + kCxTX + HX) special_seed(ly, lx);
-    }
+    cx_fix_seeds<HY, HX>(a, us, ss, ty0, tx0, lacc);
   }
   __syncthreads();
   if (!a.grad) return lacc;
@@ -425,42 +481,7 @@ __device__ __forceinline__ float mat_cross_tile(const MatArgs& a, float* __restr
   }
   if (!INTERIOR) {
     __syncthreads();                                         // the fix-up overwrites cells stored above
-    const int zy3 = zy + HY, zx3 = zx + HX;                  // cells that gather from a special row
-    auto special_grad = [&](int cy, int cx) {
-      const int gy = ty0 + cy, gx = tx0 + cx;
-      const float* sc = ss + (cy + HY) * kCxPR + cx + 4;
-      float g = 0.f;
-      for (int t = 0; t < a.n_lin; ++t) {
-        const tdb200_mat_field& f = a.fld[a.lin_q[t]];
-        float s = 0.f;
-        if (f.order == 0) s = sc[0];
-        else if (f.axis == 0) {
-          for (int m = -f.half_width; m <= f.half_width; ++m) {
-            const int yy = gy + m;
-            if (yy >= 0 && yy < n0) s = fmaf(band_coef(a.band, f, n0, yy, -m), sc[m * kCxPR], s);
-          }
-        } else {
-          for (int m = -f.half_width; m <= f.half_width; ++m) {
-            const int xx = gx + m;
-            if (xx >= 0 && xx < n1) s = fmaf(band_coef(a.band, f, n1, xx, -m), sc[m], s);
-          }
-        }
-        g = fmaf(a.lin_c[t], s, g);
-      }
-      a.grad[(size_t)gy * n1 + gx] = g;
-    };
-    for (int cy = warp; cy < kCxTY; cy += 8) {
-      const int gy = ty0 + cy;
-      if (gy >= n0 || (gy >= zy3 && gy < n0 - zy3)) continue;
-      for (int cx = lane; cx < kCxTX; cx += 32)
-        if (tx0 + cx < n1) special_grad(cy, cx);
-    }
-    for (int k = tid; k < kCxTY * 2 * zx3; k += 256) {
-      const int cy = k / (2 * zx3), ci = k - cy * (2 * zx3);
-      const int gy = ty0 + cy, gx = ci < zx3 ? ci : n1 - 2 * zx3 + ci;
-      const int cx = gx - tx0;
-      if (gy < n0 && gy >= zy3 && gy < n0 - zy3 && cx >= 0 && cx < kCxTX && gx >= 0) special_grad(cy, cx);
-    }
+    cx_fix_grad<HY, HX>(a, ss, ty0, tx0);
   }
   return lacc;
 }
@@ -526,7 +547,7 @@ static int mat_cross_ctas(const MatArgs& a) {
 // stages tile t+1 (the u box with both halos and the forcing box with one halo, out-of-range elements zero
 // filled by the TMA unit) with two cp.async.bulk.tensor.2d loads completing on an mbarrier while all threads work
 // on tile t: the HBM stream never stops, nothing is staged through registers and no thread computes a load address.
-constexpr int kCtThreads = 256;
+constexpr int kCtThreads = 512, kCtWarps = kCtThreads / 32;
 
 __device__ __forceinline__ uint32_t ct_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ct_mbar_init(uint64_t* bar, uint32_t count) {
@@ -546,87 +567,6 @@ __device__ __forceinline__ void ct_mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void ct_tma_load_2d(float* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                :: "r"(ct_smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(ct_smem_u32(bar)) : "memory");
-}
-
-// in-domain cells of the seed region whose stencil rows are special: (a) whole special rows, warp-uniform;
-// (b) special columns of the remaining rows, compact enumeration
-template <int HY, int HX>
-__device__ __forceinline__ void cx_fix_seeds(const MatArgs& a, const float* __restrict__ us, float* __restrict__ ss,
-                                             int ty0, int tx0, float& lacc) {
-  constexpr int RY = kCxTY + 2 * HY;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n0 = a.n0, n1 = a.n1, zy = a.edge_y, zx = a.edge_x;
-  const float* __restrict__ f0 = a.l1_fbuf[0];
-  const float* __restrict__ f1 = a.l1_fbuf[1];
-  const float fc0 = a.l1_fconst, scale2 = 2.f * a.eq_scale[0];
-  auto special_seed = [&](int ly, int lx) {                // (ly, lx): seed-region coordinates
-    const int gy = ty0 - HY + ly, gx = tx0 - 4 + lx;
-    const size_t cell = (size_t)gy * n1 + gx;
-    float res = fc0;
-    if (f0) res += __ldg(f0 + cell);
-    if (f1) res += __ldg(f1 + cell);
-    for (int t = 0; t < a.n_lin; ++t)
-      res = fmaf(a.lin_c[t], field_value(a, a.fld[a.lin_q[t]], us, kCxPU, 0, ly + HY, lx + 4, gy, gx), res);
-    if (ly >= HY && ly < HY + kCxTY && lx >= 4 && lx < 4 + kCxTX) lacc = fmaf(res, res, lacc);
-    ss[ly * kCxPR + lx] = scale2 * res;
-  };
-  for (int ly = warp; ly < RY; ly += 8) {
-    const int gy = ty0 - HY + ly;
-    if (gy < 0 || gy >= n0 || (gy >= zy && gy < n0 - zy)) continue;
-    for (int lx = 4 - HX + lane; lx < 4 + kCxTX + HX; lx += 32) {
-      const int gx = tx0 - 4 + lx;
-      if (gx >= 0 && gx < n1) special_seed(ly, lx);
-    }
-  }
-  for (int k = tid; k < RY * 2 * zx; k += kCtThreads) {
-    const int ly = k / (2 * zx), ci = k - ly * (2 * zx);
-    const int gy = ty0 - HY + ly, gx = ci < zx ? ci : n1 - 2 * zx + ci;
-    const int lx = gx - (tx0 - 4);
-    if (gy >= zy && gy < n0 - zy && lx >= 4 - HX && lx < 4 + kCxTX + HX) special_seed(ly, lx);
-  }
-}
-
-// cells of the tile whose transposed stencil gathers from a special row
-template <int HY, int HX>
-__device__ __forceinline__ void cx_fix_grad(const MatArgs& a, const float* __restrict__ ss, int ty0, int tx0) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n0 = a.n0, n1 = a.n1;
-  const int zy3 = a.edge_y + HY, zx3 = a.edge_x + HX;
-  auto special_grad = [&](int cy, int cx) {
-    const int gy = ty0 + cy, gx = tx0 + cx;
-    const float* sc = ss + (cy + HY) * kCxPR + cx + 4;
-    float g = 0.f;
-    for (int t = 0; t < a.n_lin; ++t) {
-      const tdb200_mat_field& f = a.fld[a.lin_q[t]];
-      float s = 0.f;
-      if (f.order == 0) s = sc[0];
-      else if (f.axis == 0) {
-        for (int m = -f.half_width; m <= f.half_width; ++m) {
-          const int yy = gy + m;
-          if (yy >= 0 && yy < n0) s = fmaf(band_coef(a.band, f, n0, yy, -m), sc[m * kCxPR], s);
-        }
-      } else {
-        for (int m = -f.half_width; m <= f.half_width; ++m) {
-          const int xx = gx + m;
-          if (xx >= 0 && xx < n1) s = fmaf(band_coef(a.band, f, n1, xx, -m), sc[m], s);
-        }
-      }
-      g = fmaf(a.lin_c[t], s, g);
-    }
-    a.grad[(size_t)gy * n1 + gx] = g;
-  };
-  for (int cy = warp; cy < kCxTY; cy += 8) {
-    const int gy = ty0 + cy;
-    if (gy >= n0 || (gy >= zy3 && gy < n0 - zy3)) continue;
-    for (int cx = lane; cx < kCxTX; cx += 32)
-      if (tx0 + cx < n1) special_grad(cy, cx);
-  }
-  for (int k = tid; k < kCxTY * 2 * zx3; k += kCtThreads) {
-    const int cy = k / (2 * zx3), ci = k - cy * (2 * zx3);
-    const int gy = ty0 + cy, gx = ci < zx3 ? ci : n1 - 2 * zx3 + ci;
-    const int cx = gx - tx0;
-    if (gy < n0 && gy >= zy3 && gy < n0 - zy3 && cx >= 0 && cx < kCxTX) special_grad(cy, cx);
-  }
 }
 
 // per stage: u box [UY][PU] then forcing box [RY][PR]; both sub-buffers start 128-byte aligned (TMA destination)
@@ -677,46 +617,66 @@ __global__ void __launch_bounds__(kCtThreads, 2) mat_cross_tma_kernel(const MatA
   const float wc = a.cx_wc, fc0 = a.l1_fconst, scale2 = 2.f * a.eq_scale[0];
   const int zy = a.edge_y, zx = a.edge_x;
   double dacc = 0.0;
+  // this thread's items of the residual pass (seed-region row, float4 group): fixed for the whole kernel
+  int off_u[N2], off_s[N2], lyq[N2];
+  bool core[N2];
+#pragma unroll
+  for (int k = 0; k < N2; ++k) {
+    const int idx = tid + kCtThreads * k;
+    const int ly = idx / kCxQR, q = idx - ly * kCxQR;
+    off_u[k] = idx < RY * kCxQR ? (ly + HY) * kCxPU + 4 * q + 4 : -1;
+    off_s[k] = ly * kCxPR + 4 * q;
+    lyq[k] = (ly << 8) | q;
+    core[k] = ly >= HY && ly < HY + kCxTY && q >= 1 && q <= kCxTX / 4;
+  }
+  // dynamic tile scheduler: the first tile of a CTA is its block index, further tiles come from a global counter
+  // (boundary tiles cost more than interior tiles); thread 0 publishes {tile, ty0, tx0, interior} of each stage
+  __shared__ int4 tile_s[2];
   uint32_t phase[2] = {0u, 0u};
-  int tile = blockIdx.x, st = 0;
-  if (tid == 0 && tile < n_tiles) stage_tile(tile, 0);
-  for (; tile < n_tiles; tile += gridDim.x, st ^= 1) {
-    if (tid == 0 && tile + (int)gridDim.x < n_tiles) stage_tile(tile + gridDim.x, st ^ 1);
-    const float* us = base + st * ct_stage_floats<HY, HX>();
-    const float* fs = us + ct_u_floats<HY, HX>();
+  auto publish = [&](int tile, int st) {                     // one thread
     const int ty0 = (tile / tiles_x) * kCxTY, tx0 = (tile % tiles_x) * kCxTX;
     const bool interior = ty0 - 2 * HY >= zy && ty0 + kCxTY + 2 * HY <= n0 - zy && tx0 - 8 >= zx && tx0 + kCxTX + 8 <= n1 - zx;
+    tile_s[st] = make_int4(tile, ty0, tx0, interior ? 1 : 0);
+    if (tile < n_tiles) stage_tile(tile, st);
+  };
+  if (tid == 0) publish(blockIdx.x, 0);
+  __syncthreads();
+  for (int st = 0;; st ^= 1) {
+    const int4 ti = tile_s[st];
+    if (ti.x >= n_tiles) break;
+    if (tid == 0) publish((int)gridDim.x + (int)atomicAdd(a.tile_ctr, 1u), st ^ 1);   // read after this iteration's barriers
+    const float* us = base + st * ct_stage_floats<HY, HX>();
+    const float* fs = us + ct_u_floats<HY, HX>();
+    const int ty0 = ti.y, tx0 = ti.z;
+    const bool interior = ti.w != 0;
     ct_mbar_wait(bars + st, phase[st]);
     phase[st] ^= 1u;
     float lacc = 0.f;
     // ---- residual seeds on tile + halo ----
 #pragma unroll
     for (int k = 0; k < N2; ++k) {
-      const int idx = tid + kCtThreads * k;
-      if (idx < RY * kCxQR) {
-        const int ly = idx / kCxQR, q = idx - ly * kCxQR;
+      if (off_u[k] >= 0) {
         float r[4] = {fc0, fc0, fc0, fc0};
         if (has_f) {
-          const float4 fv = *reinterpret_cast<const float4*>(fs + ly * kCxPR + 4 * q);
+          const float4 fv = *reinterpret_cast<const float4*>(fs + off_s[k]);
           r[0] += fv.x; r[1] += fv.y; r[2] += fv.z; r[3] += fv.w;
         }
-        cx_apply<HY, HX, MY, MX, false, kCxPU>(us + (ly + HY) * kCxPU + 4 * q + 4, wy, wx, wc, r);
-        const bool core = ly >= HY && ly < HY + kCxTY && q >= 1 && q <= kCxTX / 4;
+        cx_apply<HY, HX, MY, MX, false, kCxPU>(us + off_u[k], wy, wx, wc, r);
         float sd[4];
         if (interior) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { sd[i] = scale2 * r[i]; if (core) lacc = fmaf(r[i], r[i], lacc); }
+          for (int i = 0; i < 4; ++i) { sd[i] = scale2 * r[i]; if (core[k]) lacc = fmaf(r[i], r[i], lacc); }
         } else {
-          const int gy = ty0 - HY + ly, gx = tx0 - 4 + 4 * q;
+          const int gy = ty0 - HY + (lyq[k] >> 8), gx = tx0 - 4 + 4 * (lyq[k] & 255);
           const bool rowreg = gy >= zy && gy < n0 - zy;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const bool reg = rowreg && gx + i >= zx && gx + i < n1 - zx;   // regular interior row of the operators
             sd[i] = reg ? scale2 * r[i] : 0.f;
-            if (core && reg) lacc = fmaf(r[i], r[i], lacc);
+            if (core[k] && reg) lacc = fmaf(r[i], r[i], lacc);
           }
         }
-        *reinterpret_cast<float4*>(ss + ly * kCxPR + 4 * q) = make_float4(sd[0], sd[1], sd[2], sd[3]);
+        *reinterpret_cast<float4*>(ss + off_s[k]) = make_float4(sd[0], sd[1], sd[2], sd[3]);
       }
     }
     if (!interior) {                                         // CTA-uniform
@@ -728,8 +688,8 @@ __global__ void __launch_bounds__(kCtThreads, 2) mat_cross_tma_kernel(const MatA
     // ---- transposed stencil -> gradient of the tile ----
     if (a.grad) {
 #pragma unroll
-      for (int i = 0; i < kCxTY / 8; ++i) {
-        const int cy = warp + 8 * i, gy = ty0 + cy, gx = tx0 + 4 * lane;
+      for (int i = 0; i < kCxTY / kCtWarps; ++i) {
+        const int cy = warp + kCtWarps * i, gy = ty0 + cy, gx = tx0 + 4 * lane;
         if (gy < n0 && gx < n1) {
           float g[4] = {0.f, 0.f, 0.f, 0.f};
           cx_apply<HY, HX, MY, MX, true, kCxPR>(ss + (cy + HY) * kCxPR + 4 * lane + 4, wy, wx, wc, g);
@@ -1030,6 +990,7 @@ struct MatBcArgs {
   const double* slot_len;
   float* out;
   unsigned int* ticket;                    // zero on entry, reset by the finalizing block
+  unsigned int* tile_ctr;                  // tile scheduler counter of the persistent kernel, reset likewise
 };
 
 __device__ float global_field(const MatBcArgs& a, const tdb200_mat_field& f, int cell) {
@@ -1153,7 +1114,7 @@ __global__ void __launch_bounds__(128) mat_bc_kernel(const MatBcArgs a) {
   if (sh_ticket != gridDim.x - 1) return;
   // last block: every other block's slot sums are visible
   __threadfence();
-  if (threadIdx.x == 0) *a.ticket = 0u;
+  if (threadIdx.x == 0) { *a.ticket = 0u; *a.tile_ctr = 0u; }
   mat_finalize_block(a.part_loss, a.n_ctas, a.n_eq, a.n_cells, a.slot_sum, a.n_bc_slots, a.slot_lambda, a.slot_len, a.out);
 }
 
@@ -1194,7 +1155,8 @@ __device__ void mat_finalize_block(const double* __restrict__ part_loss, int n_c
 __global__ void mat_finalize_kernel(const double* __restrict__ part_loss, int n_ctas, int n_eq, double n_cells,
                                     double* __restrict__ bc_sum, int n_bc_slots,
                                     const double* __restrict__ slot_lambda, const double* __restrict__ slot_len,
-                                    float* __restrict__ out) {
+                                    float* __restrict__ out, unsigned int* tile_ctr) {
+  if (threadIdx.x == 0) *tile_ctr = 0u;
   mat_finalize_block(part_loss, n_ctas, n_eq, n_cells, bc_sum, n_bc_slots, slot_lambda, slot_len, out);
 }
 
@@ -1441,8 +1403,8 @@ int tdb200_mat_plan_set_bcs(tdb200_mat_plan* p, int32_t n_bcs, const tdb200_mat_
   MCU(cudaMemcpy(p->d_slot_len, slot_len, sizeof(double) * n_slots, cudaMemcpyHostToDevice));
   MCU(cudaMalloc(&p->d_bc_sum, sizeof(double) * (p->n_bc_slots > 0 ? p->n_bc_slots : 1)));
   MCU(cudaMemset(p->d_bc_sum, 0, sizeof(double) * (p->n_bc_slots > 0 ? p->n_bc_slots : 1)));
-  if (!p->d_ticket) MCU(cudaMalloc(&p->d_ticket, sizeof(unsigned int)));
-  MCU(cudaMemset(p->d_ticket, 0, sizeof(unsigned int)));
+  if (!p->d_ticket) MCU(cudaMalloc(&p->d_ticket, 2 * sizeof(unsigned int)));   // [finalize ticket, tile counter]
+  MCU(cudaMemset(p->d_ticket, 0, 2 * sizeof(unsigned int)));
   for (int e = 0; e < n_eq; ++e) p->args.eq_scale[e] = (float)(slot_lambda[e] / slot_len[e]);
   tdb::MatBcArgs& b = p->bc;
   b.bcs = p->d_bcs; b.n_bcs = n_bcs; b.bc_row_begin = p->d_bc_row_begin; b.cells = cells_dev; b.targets = targets_dev;
@@ -1458,7 +1420,7 @@ static int mat_run(tdb200_mat_plan* p, const float* u, float* grad, float* op_ou
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   MCU(cudaSetDevice(p->device));
   tdb::MatArgs a = p->args;
-  a.u = u; a.grad = grad; a.op_out = op_out;
+  a.u = u; a.grad = grad; a.op_out = op_out; a.tile_ctr = p->d_ticket + 1;
   int n_ctas = p->n_ctas;
   if (a.lin1 && !op_out) {
     // specialised kernels (loss + gradient, or loss only); per-cell operator values go through the generic kernel
@@ -1500,14 +1462,14 @@ static int mat_run(tdb200_mat_plan* p, const float* u, float* grad, float* op_ou
     b.u = u; b.grad = grad; b.bval_out = bval_out;
     b.part_loss = p->d_part_loss; b.n_ctas = n_ctas; b.n_bc_slots = p->n_bc_slots;
     b.n_cells = (double)p->desc.n0 * (double)p->desc.n1;
-    b.slot_lambda = p->d_slot_lambda; b.slot_len = p->d_slot_len; b.out = out; b.ticket = p->d_ticket;
+    b.slot_lambda = p->d_slot_lambda; b.slot_len = p->d_slot_len; b.out = out; b.ticket = p->d_ticket; b.tile_ctr = p->d_ticket + 1;
     const int blocks = (int)((p->n_bc_rows + 127) / 128);
     tdb::mat_bc_kernel<<<blocks < 1184 ? blocks : 1184, 128, 0, s>>>(b);
     MCU(cudaGetLastError());
   } else {
     tdb::mat_finalize_kernel<<<1, 256, 0, s>>>(p->d_part_loss, n_ctas, p->desc.n_eq,
                                               (double)p->desc.n0 * (double)p->desc.n1, p->d_bc_sum, p->n_bc_slots,
-                                              p->d_slot_lambda, p->d_slot_len, out);
+                                              p->d_slot_lambda, p->d_slot_len, out, p->d_ticket + 1);
     MCU(cudaGetLastError());
   }
   return TDB200_OK;
