@@ -187,7 +187,7 @@ int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_s
   p->grid = tiles < p->n_sms ? (tiles > 0 ? tiles : 1) : p->n_sms;
   {  // can the interior segment run on the tensor cores?
     const tdb200_segment& s0 = segments[0];
-    bool ok = L >= 3 && L - 2 <= 2 && net->widths[1] <= 104 && net->widths[L] <= tdb::kMaxOut;
+    bool ok = L >= 3 && L - 2 <= 2 && net->widths[1] <= 104 && net->widths[L] <= tdb::jet_tc_max_out() && net->widths[0] <= 4;
     for (int l = 2; l < L; ++l) ok = ok && net->widths[l] == net->widths[1];
     for (int i = 0; i < 3; ++i) p->tc_sig[i] = i < s0.n_dirs ? s0.dir_order[i] : 0;
     ok = ok && s0.identity && s0.K == 1 && s0.n_dirs <= 3 && s0.n_groups > 0 &&

@@ -82,6 +82,7 @@ cudaError_t launch_pack_tc_images(const PackArgs& a, float* img, cudaStream_t s)
 bool jet_tc_supports(int o0, int o1, int o2);
 int jet_tc_points_per_tile(int o0, int o1, int o2);
 int jet_tc_partial_rows();
+int jet_tc_max_out();
 cudaError_t launch_jet_tc(const JetArgs& a, const float* wimg, int o0, int o1, int o2, int grid, cudaStream_t s);
 
 // tanh and its derivatives as functions of a = tanh(z):  f1 = 1 - a^2, f_{k+1} = d f_k / dz

@@ -5,32 +5,43 @@
 // tcgen05.mma.kind::tf32 with fp32 accumulators in TMEM, in the 3xTF32 split (hi*hi + hi*lo + lo*hi).
 //
 // Orientation: D[neuron, (point, channel)] = W . Y^T, i.e. accumulator lanes are neurons and columns are the
-// (point, jet-channel) pairs of the tile.  A thread that owns lane n therefore sees every jet channel of every
-// point for its neuron, so the tanh-jet rule and its adjoint are thread-local TMEM -> registers -> smem epilogues.
-//   forward      D[n,(pc)]  = sum_k W[n,k]   Y[(pc),k]     A = W image   (smem, K-major), B = activations (K-major)
-//   backward     D[k,(pc)]  = sum_n W^T[k,n] gZ[(pc),n]    A = W^T image (smem, K-major), B = gZ (K-major)
-//   weight grad dW[n,k]    += sum_pc gZ[n,(pc)] Y[(pc),k]   A = gZ straight from the epilogue registers into TMEM
-//                                                          (tcgen05.st), B = Y (smem, MN-major); dW stays in TMEM
-//                                                          for the whole kernel and is flushed once per CTA.
-// K-major operands use the canonical 128-byte swizzle ([k-block of 32][row][32 floats], 16-byte chunks XOR row);
-// the MN-major tf32 operand needs the 32-byte-base variant (SWIZZLE_128B_BASE32B: 4-row atoms, 32-byte chunks).
+// (point, jet-channel) pairs of the tile (64 columns = 4 column parts of 16).  A thread that owns lane n sees
+// every jet channel of its points for its neuron, so the tanh-jet rule and its adjoint are thread-local
+// TMEM -> registers -> shared-memory epilogues, and what a thread writes for the next GEMM is a run of 16
+// consecutive (point, channel) columns of its own row:
+//   forward      D[n,(pc)]  = sum_k W[n,k]   Y[k,(pc)]      A = W image   (smem, K-major SW128)
+//                                                           B = Y image   [k rows][(pc) contiguous], read MN-major
+//   backward     D[k,(pc)]  = sum_n W^T[k,n] gZ[n,(pc)]     A = W^T image (smem, K-major SW128)
+//                                                           B = gZ image  [n rows][(pc) contiguous], read MN-major
+//   weight grad  dW[n,k]   += sum_pc gZ[n,(pc)] Y[k,(pc)]   A = gZ in TMEM (tcgen05.st from the epilogue registers)
+//                                                           B = Y image   [k rows][(pc) contiguous], K-major SW128
+// so every epilogue store is a 16-byte vector store.  MN-major tf32 operands use the 32-byte-base 128-byte swizzle
+// (SWIZZLE_128B_BASE32B: 32-byte chunks XOR (row & 3)), K-major operands the canonical one (16-byte chunks XOR
+// (row & 7)).  The dW accumulators stay in TMEM for the whole kernel and are flushed once per CTA; pre-activation
+// jets are kept in registers between the forward and the backward sweep, nothing goes to HBM.
+// Measured (profiles/microbench/mma_probe.cu): an M = 128 tf32 MMA with both operands in shared memory costs
+// ~37 + N/4 cycles (the 4 KB A read dominates), with A in TMEM ~N/2 + 3; hence N = 64 and not less.
 #include "common.cuh"
 
 namespace tdb {
 
 constexpr int kTcThreads = 512;                  // 16 warps: 4 lane windows x 4 column parts
 constexpr int kTcParts = 4;
-constexpr int kTcCols = 48;                      // (point, channel) columns per tile = MMA N
+constexpr int kTcPC = 16;                        // columns per part
+constexpr int kTcCols = kTcParts * kTcPC;        // (point, channel) columns per tile = MMA N
 constexpr int kTcWRows = 104;                    // rows of the weight image (neurons padded to 8)
-constexpr int kTcActBlock = kTcCols * 32;        // floats per k-block of an activation operand
-constexpr int kTcActFloats = 4 * kTcActBlock;    // 6144 floats = 24 KB
 constexpr int kTcWBlock = kTcWRows * 32;
 constexpr int kTcWFloats = 4 * kTcWBlock;        // 13312 floats = 52 KB
-constexpr int kTcMaxMma = 2;                     // W x W layers: Z_l, dW_l and the operands all stay in TMEM
-constexpr int kTcSavePitch = 104;
-// TMEM columns: Z_1 | Z_2 (forward accumulators, kept for the backward sweep) | D_bwd | gZ hi | gZ lo (A operands
-// of the weight-gradient MMA) | dW slots (112 columns each)
-constexpr uint32_t kTmZ = 0, kTmDb = 96, kTmAHi = 144, kTmALo = 192, kTmDw = 240, kTmDwCols = 112;
+constexpr int kTcActBlock = 104 * 32;            // MN-major activation operand: [2 blocks of 32 columns][104 K rows][32]
+constexpr int kTcActFloats = 2 * kTcActBlock;    // 6656 floats = 26 KB
+constexpr int kTcYwRows = 112;                   // K-major operand of the weight-gradient GEMM: [2 blocks][112 rows][32]
+constexpr int kTcYwBlock = kTcYwRows * 32;
+constexpr int kTcYwFloats = 2 * kTcYwBlock;      // 7168 floats = 28 KB
+constexpr int kTcMaxMma = 2;                     // W x W layers (their dW accumulators live in TMEM)
+constexpr int kTcMaxOut = 4;                     // network outputs served by this kernel
+// TMEM columns: D (forward / backward-data accumulator) | gZ hi | gZ lo (A operands of the weight-gradient MMA) |
+// dW slots (112 columns each)
+constexpr uint32_t kTmD = 0, kTmAHi = 64, kTmALo = 128, kTmDw = 192, kTmDwCols = 112;
 
 // float offset of element (row, k) inside a swizzled operand buffer with `rows` rows per k-block
 __host__ __device__ __forceinline__ int sw_off(int row, int k, int rows) {
@@ -187,18 +198,42 @@ __device__ __forceinline__ void split_store(float* hi_buf, float* lo_buf, int of
   lo_buf[off] = y - h;
 }
 
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      :: "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+         "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+         "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+         "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
+         "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])) : "memory");
+}
+
+__device__ __forceinline__ void split16(const float* v, float* hi, float* lo) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    uint32_t hb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v[j]));
+    hi[j] = __uint_as_float(hb);
+    lo[j] = v[j] - hi[j];
+  }
+}
+__device__ __forceinline__ void st4(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
 // ------------------------------------------------------------------------------------------------
-// MMA issue helpers (one thread).  All operand buffers are 1024-byte aligned.
+// MMA issue helpers.  Called by every lane of one warp (warp-uniform control flow keeps the descriptors in uniform
+// registers); each tcgen05.mma itself is issued by the elected lane.  All operand buffers are 1024-byte aligned.
 // ------------------------------------------------------------------------------------------------
-// The issue helpers are called by every lane of one warp (warp-uniform control flow keeps the descriptors in
-// uniform registers); each tcgen05.mma itself is issued by the elected lane.
-// D[128 x 48] (+)= A(W image, K-major) . B(act, K-major), 3xTF32.  KS = K-steps of 8 (compile time).
+// D[128 x 64] = A(weight image, K-major SW128) . B(activation image [K rows][64 columns], MN-major BASE32B), 3xTF32
 template <int KS>
-__device__ __forceinline__ void issue_forward(uint32_t d_tmem, const float* w_hi, const float* w_lo,
-                                              const float* b_hi, const float* b_lo) {
-  constexpr uint32_t idesc = umma_idesc(128, kTcCols, 0, 0);
+__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, const float* w_hi, const float* w_lo,
+                                           const float* b_hi, const float* b_lo) {
+  constexpr uint32_t idesc = umma_idesc(128, kTcCols, 0, 1);
   const uint64_t dwh = umma_desc(smem_u32(w_hi), 16, 1024), dwl = umma_desc(smem_u32(w_lo), 16, 1024);
-  const uint64_t dbh = umma_desc(smem_u32(b_hi), 16, 1024), dbl = umma_desc(smem_u32(b_lo), 16, 1024);
+  // MN blocks of 32 columns at LBO = one block; 8 K rows = two 4-row swizzle atoms (SBO = 512 B)
+  const uint64_t dbh = umma_desc(smem_u32(b_hi), kTcActBlock * 4, 512, 1), dbl = umma_desc(smem_u32(b_lo), kTcActBlock * 4, 512, 1);
   const bool leader = elect_one();
 #pragma unroll
   for (int pass = 0; pass < 3; ++pass) {
@@ -207,90 +242,64 @@ __device__ __forceinline__ void issue_forward(uint32_t d_tmem, const float* w_hi
 #pragma unroll
     for (int s = 0; s < KS; ++s) {
       const uint64_t ao = ((uint64_t)(s >> 2) * kTcWBlock * 4 + (uint64_t)(s & 3) * 32) >> 4;
-      const uint64_t bo = ((uint64_t)(s >> 2) * kTcActBlock * 4 + (uint64_t)(s & 3) * 32) >> 4;
+      const uint64_t bo = ((uint64_t)s * 1024) >> 4;
       if (leader) umma_tf32(d_tmem, A + ao, B + bo, idesc, (pass | s) ? 1u : 0u);
     }
   }
 }
-__device__ __forceinline__ void issue_forward_any(uint32_t d_tmem, const float* w_hi, const float* w_lo,
-                                                  const float* b_hi, const float* b_lo, int ksteps) {
-  if (ksteps == 13) issue_forward<13>(d_tmem, w_hi, w_lo, b_hi, b_lo);
-  else if (ksteps <= 4) issue_forward<4>(d_tmem, w_hi, w_lo, b_hi, b_lo);     // zero-padded images: extra steps add 0
-  else if (ksteps <= 8) issue_forward<8>(d_tmem, w_hi, w_lo, b_hi, b_lo);
-  else issue_forward<13>(d_tmem, w_hi, w_lo, b_hi, b_lo);
+__device__ __forceinline__ void issue_gemm_any(uint32_t d_tmem, const float* w_hi, const float* w_lo,
+                                               const float* b_hi, const float* b_lo, int ksteps) {
+  if (ksteps <= 4) issue_gemm<4>(d_tmem, w_hi, w_lo, b_hi, b_lo);             // zero-padded images: extra steps add 0
+  else if (ksteps <= 8) issue_gemm<8>(d_tmem, w_hi, w_lo, b_hi, b_lo);
+  else issue_gemm<13>(d_tmem, w_hi, w_lo, b_hi, b_lo);
 }
-// dW[128 (n) x 112 (k)] += A(gZ in TMEM: lanes n, columns (pc)) . B(Y in smem read MN-major: N = k, K = (pc))
+// dW[128 (n) x 112 (k)] += A(gZ in TMEM: lanes n, columns (pc)) . B(Y image [k rows][64 columns], K-major SW128)
 __device__ __forceinline__ void issue_wgrad(uint32_t d_tmem, uint32_t a_hi_tmem, uint32_t a_lo_tmem,
                                             const float* y_hi, const float* y_lo, uint32_t accumulate) {
-  constexpr uint32_t idesc = umma_idesc(128, 112, 0, 1);
-  // 8 (pc) rows = two 4-row swizzle atoms (SBO = 512 B); MN blocks of 32 k at LBO = one k-block
-  const uint64_t dyh = umma_desc(smem_u32(y_hi), kTcActBlock * 4, 512, 1), dyl = umma_desc(smem_u32(y_lo), kTcActBlock * 4, 512, 1);
+  constexpr uint32_t idesc = umma_idesc(128, 112, 0, 0);
+  const uint64_t dyh = umma_desc(smem_u32(y_hi), 16, 1024), dyl = umma_desc(smem_u32(y_lo), 16, 1024);
   const bool leader = elect_one();
 #pragma unroll
   for (int pass = 0; pass < 3; ++pass) {
     const uint32_t A = pass == 0 ? a_lo_tmem : a_hi_tmem;
     const uint64_t B = pass == 1 ? dyl : dyh;
 #pragma unroll
-    for (int s = 0; s < kTcCols / 8; ++s)
-      if (leader) umma_tf32_ts(d_tmem, A + (uint32_t)s * 8, B + (uint64_t)(s * 1024 >> 4), idesc, (pass | s) ? 1u : accumulate);
+    for (int s = 0; s < kTcCols / 8; ++s) {
+      const uint64_t bo = ((uint64_t)(s >> 2) * kTcYwBlock * 4 + (uint64_t)(s & 3) * 32) >> 4;
+      if (leader) umma_tf32_ts(d_tmem, A + (uint32_t)s * 8, B + bo, idesc, (pass | s) ? 1u : accumulate);
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // small device helpers
 // ------------------------------------------------------------------------------------------------
-// tanh with ~1e-7 absolute error: odd polynomial near 0 (Cephes tanhf), 1 - 2 / (exp(2|x|) + 1) elsewhere
-__device__ __forceinline__ float tanh_acc(float x) {
-  const float ax = fabsf(x);
-  if (ax < 0.625f) {
-    const float s = x * x;
-    const float p = ((((-5.70498872745e-3f * s + 2.06390887954e-2f) * s - 5.37397155531e-2f) * s +
-                      1.33314422036e-1f) * s - 3.33332819422e-1f);
-    return fmaf(x * s, p, x);
-  }
-  const float e = __expf(2.f * ax);
-  return copysignf(1.f - __fdividef(2.f, e + 1.f), x);
+// tanh(x) = 1 - 2 / (exp(2x) + 1): two MUFU ops, absolute error ~1e-7 over the whole range (the jets only ever
+// use tanh through a, 1 - a^2, ...: absolute, not relative, accuracy is what the residual sees)
+__device__ __forceinline__ float tanh_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+  return fmaf(-2.f, r, 1.f);
 }
 
-__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float* v) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
+// warp-wide sums of 16 per-lane values: afterwards the lane pair (2q, 2q + 1) holds the total of column
+// c(q) = bit-reversed-ish index 8*b4 + 4*b3 + 2*b2 + b1 of the lane number (16 shuffles)
+__device__ __forceinline__ float warp_multi_reduce16(float* v, int lane) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// 16 consecutive columns of this warp's lane window (a part owns at most 12 of them)
-__device__ __forceinline__ void tmem_ld16w(uint32_t taddr, float* v) {
-  tmem_ld8_nowait(taddr, v);
-  tmem_ld8_nowait(taddr + 8, v + 8);
-  tmem_ld_wait();
-}
-// exactly C (compile time, <= 24) columns
-template <int C>
-__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const float* v) {
-  int c = 0;
-#pragma unroll
-  for (; c + 4 <= C; c += 4) tmem_st4(taddr + c, v + c);
-  if (C & 2) { tmem_st2(taddr + c, v + c); c += 2; }
-  if (C & 1) tmem_st1(taddr + c, v[c]);
-}
-
-// warp-wide sum of 32 per-lane values: afterwards lane L holds the total of v[L] over the warp (31 shuffles)
-__device__ __forceinline__ float warp_multi_reduce32(float* v, int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
+  for (int off = 16, cnt = 8; off >= 2; off >>= 1, cnt >>= 1) {
     const bool up = (lane & off) != 0;
 #pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float keep = up ? v[i + off] : v[i];
-      const float send = up ? v[i] : v[i + off];
+    for (int i = 0; i < cnt; ++i) {
+      const float keep = up ? v[i + cnt] : v[i];
+      const float send = up ? v[i] : v[i + cnt];
       v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
     }
   }
-  return v[0];
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+__device__ __forceinline__ int reduce16_col(int lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
 // bulk (TMA, 1-D) copy of one weight image pair into shared memory, completion on an mbarrier
@@ -307,24 +316,24 @@ __device__ __forceinline__ void bulk_load_image(float* dst, const float* src, ui
 // ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
+constexpr int kTcMaxTerms = 48, kTcMaxFactors = 96;   // operator program cached in shared memory
+constexpr int kTcMaxPts = 32;                         // points per tile (J = 2)
 struct TcSmem {
-  float *w_hi, *w_lo, *a_hi, *a_lo, *b_hi, *b_lo;
-  float *xS, *uS, *guS, *uP, *wlS, *cgS;
+  float *w_hi, *w_lo, *act_hi, *act_lo, *yw_hi, *yw_lo;
+  float *xS, *uS, *guS, *uP, *cgS;
   tdb200_term* termS;
   tdb200_factor* facS;
   tdb200_segment* segS;
   float* scaleS;          // [32] lambda / len per slot
-  double* lossT;          // [kTcCols][TDB200_MAX_COLS] per-point-thread loss accumulators (no atomics)
-  double* lossS;
+  double* lossT;          // [kTcMaxPts][TDB200_MAX_COLS] per-point-thread loss accumulators (no atomics)
   uint64_t *bar, *wbar, *gbar;
   uint32_t* tmem_ptr;
 };
-constexpr int kTcMaxTerms = 48, kTcMaxFactors = 96;   // operator program cached in shared memory
-constexpr size_t kTcSmemBytes = (size_t)(2 * kTcWFloats + 4 * kTcActFloats) * 4 + 1024 /*align*/ +
-                                (2 * kTcCols * 4 + 2 * kMaxOut * kTcCols + 4 * kMaxOut * kTcCols +
-                                 kMaxOut * kTcSavePitch + kMaxCParams) * 4 + 32 * 8 + 64 +
-                                kTcMaxTerms * sizeof(tdb200_term) + kTcMaxFactors * sizeof(tdb200_factor) + 16 +
-                                sizeof(tdb200_segment) + 32 * 4 + kTcCols * TDB200_MAX_COLS * 8 + 32;
+constexpr size_t kTcSmemBytes =
+    (size_t)(2 * kTcWFloats + 2 * kTcActFloats + 2 * kTcYwFloats) * 4 + 1024 /*align*/ +
+    (2 * kTcMaxPts * 4 + 2 * kTcMaxOut * kTcCols + 4 * kTcMaxOut * kTcCols + kMaxCParams) * 4 + 64 + 64 +
+    kTcMaxTerms * sizeof(tdb200_term) + kTcMaxFactors * sizeof(tdb200_factor) + 16 + sizeof(tdb200_segment) + 32 * 4 +
+    kTcMaxPts * TDB200_MAX_COLS * 8 + 64;
 
 size_t jet_tc_smem_bytes() { return kTcSmemBytes; }
 
@@ -333,10 +342,10 @@ template <int O0, int O1, int O2, int NMMA>
 __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, const float* __restrict__ wimg) {
   constexpr int J = 1 + O0 + O1 + O2;
   constexpr int ND = (O0 > 0) + (O1 > 0) + (O2 > 0);
-  constexpr int PH = 12 / J;                   // points per column part
+  constexpr int PH = kTcPC / J;                // points per column part
   constexpr int P = kTcParts * PH;             // points per tile
-  constexpr int C = PH * J;                    // columns per part (<= 12)
-  constexpr int n_mma = NMMA;                  // W x W layers (1 or 2)
+  constexpr int C = PH * J;                    // used columns per part (<= 16)
+  constexpr int JD = J > 1 ? J - 1 : 1;        // derivative channels per point
   constexpr int ORD[3] = {O0, O1, O2};
   extern __shared__ uint8_t smem_raw_tc[];
   TcSmem sm;
@@ -345,18 +354,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
     float* f = reinterpret_cast<float*>(base);
     sm.w_hi = f; f += kTcWFloats;
     sm.w_lo = f; f += kTcWFloats;
-    sm.a_hi = f; f += kTcActFloats;
-    sm.a_lo = f; f += kTcActFloats;
-    sm.b_hi = f; f += kTcActFloats;
-    sm.b_lo = f; f += kTcActFloats;
-    sm.xS = f; f += 2 * kTcCols * 4;                   // double buffered: the next tile's points are prefetched
-    sm.uS = f; f += kMaxOut * kTcCols;
-    sm.guS = f; f += kMaxOut * kTcCols;
-    sm.uP = f; f += 4 * kMaxOut * kTcCols;
-    sm.wlS = f; f += kMaxOut * kTcSavePitch;
+    sm.act_hi = f; f += kTcActFloats;
+    sm.act_lo = f; f += kTcActFloats;
+    sm.yw_hi = f; f += kTcYwFloats;
+    sm.yw_lo = f; f += kTcYwFloats;
+    sm.xS = f; f += 2 * kTcMaxPts * 4;                 // double buffered: the next tile's points are prefetched
+    sm.uS = f; f += kTcMaxOut * kTcCols;
+    sm.guS = f; f += kTcMaxOut * kTcCols;
+    sm.uP = f; f += 4 * kTcMaxOut * kTcCols;
     sm.cgS = f; f += kMaxCParams;
-    sm.lossS = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(f) + 15) & ~uintptr_t(15));
-    sm.bar = reinterpret_cast<uint64_t*>(sm.lossS + 32);
+    sm.bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(f) + 15) & ~uintptr_t(15));
     sm.wbar = sm.bar + 1;
     sm.gbar = sm.bar + 2;
     sm.tmem_ptr = reinterpret_cast<uint32_t*>(sm.bar + 3);
@@ -368,27 +375,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = (warp & 3) * 32 + lane;                 // neuron = TMEM lane owned by this thread
-  const int half = warp >> 2;                           // which column part (0..3) of the tile this thread owns
+  const int part = warp >> 2;                           // which column part (0..3) of the tile this thread owns
   const int L = a.n_layers, W = a.widths[1], n_out = a.widths[L], d = a.d;
   const int ksteps = (W + 7) / 8;
   const bool live = n < W;
-  const int col0 = half * C;                            // first (point, channel) column of this thread
+  const int col0 = part * kTcPC;                        // first (point, channel) column of this thread
   // one gradient-partial row per column part: a single owner thread per address -> bit-reproducible
-  float* const my_grad = a.part_grad + ((size_t)blockIdx.x * kTcParts + half) * a.n_params_pad;
+  float* const my_grad = a.part_grad + ((size_t)blockIdx.x * kTcParts + part) * a.n_params_pad;
+  // where this thread's 16 columns live in the operand images (floats)
+  const int actA = (part >> 1) * kTcActBlock + n * 32 + ((((part & 1) * 2) ^ (n & 3)) << 3);       // columns 0..7
+  const int actB = (part >> 1) * kTcActBlock + n * 32 + ((((part & 1) * 2 + 1) ^ (n & 3)) << 3);   // columns 8..15
+  int ywq[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) ywq[q] = (part >> 1) * kTcYwBlock + n * 32 + ((((part & 1) * 4 + q) ^ (n & 7)) << 2);
 
   // ---- one-time setup --------------------------------------------------------------------------------
   for (int i = tid; i < kTcParts * a.n_params_pad; i += kTcThreads)
     a.part_grad[(size_t)blockIdx.x * kTcParts * a.n_params_pad + i] = 0.f;
-  for (int i = tid; i < 4 * kTcActFloats; i += kTcThreads) sm.a_hi[i] = 0.f;      // pad rows / columns stay zero
-  if (tid < 32) sm.lossS[tid] = 0.0;
+  for (int i = tid; i < 2 * kTcActFloats + 2 * kTcYwFloats; i += kTcThreads) sm.act_hi[i] = 0.f;   // pad rows / columns stay zero
   if (tid < kMaxCParams) sm.cgS[tid] = 0.f;
-  for (int i = tid; i < n_out * W; i += kTcThreads) sm.wlS[(i / W) * kTcSavePitch + i % W] = a.arena[a.w_off[L - 1] + i];
   for (int i = tid; i < min(kTcMaxTerms, a.n_terms); i += kTcThreads) sm.termS[i] = a.terms[i];
   for (int i = tid; i < min(kTcMaxFactors, a.n_factors); i += kTcThreads) sm.facS[i] = a.factors[i];
   for (int i = tid; i < (int)(sizeof(tdb200_segment) / 4); i += kTcThreads)
     reinterpret_cast<uint32_t*>(sm.segS)[i] = reinterpret_cast<const uint32_t*>(a.segs)[i];
   if (tid < a.n_slots) sm.scaleS[tid] = a.slot_scale[tid];
-  for (int i = tid; i < kTcCols * TDB200_MAX_COLS; i += kTcThreads) sm.lossT[i] = 0.0;
+  for (int i = tid; i < kTcMaxPts * TDB200_MAX_COLS; i += kTcThreads) sm.lossT[i] = 0.0;
   if (tid == 0) { mbar_init(sm.bar, 1); mbar_init(sm.wbar, 1); mbar_init(sm.gbar, 1); }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(sm.tmem_ptr)) : "memory");
@@ -400,33 +411,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
   tc_fence_after();
   const uint32_t tmem = *sm.tmem_ptr;
   const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);    // this warp's lane window
-  {  // the gZ operand columns of TMEM must hold zeros where no (point, channel) column exists
-    const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (half == 0)
-      for (uint32_t c = kTmAHi; c < kTmDw; c += 8) { tmem_st4(t_lane + c, z8); tmem_st4(t_lane + c + 4, z8); }
-    tmem_st_wait();
-  }
   long long tacc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) tacc[i] = 0;
   long long tlast = clock64();
 #define TMARK(i) do { if (a.dbg) { const long long tn_ = clock64(); tacc[i] += tn_ - tlast; tlast = tn_; } } while (0)
   uint32_t phase = 0, wphase = 0, gphase = 0;           // wphase is only used by warp 0
-  bool wgrad_pending = false;                           // weight-gradient MMAs still reading TMEM A / Y operand
+  bool wgrad_pending = false;                           // weight-gradient MMAs still reading TMEM A / the Y image
   uint32_t dw_started = 0;
-  // per-layer parameters this thread needs all the time
-  float bias[3] = {0.f, 0.f, 0.f}, w0[4] = {0.f, 0.f, 0.f, 0.f}, wl[kMaxOut];
-  if (live) {
-    for (int l = 0; l <= n_mma; ++l) bias[l] = a.arena[a.b_off[l] + n];
-    for (int ax = 0; ax < d; ++ax) w0[ax] = a.arena[a.w_off[0] + n * d + ax];
-  }
+  // per-layer parameters this thread needs all the time, and its gradient accumulators (flushed once per CTA)
+  float bias[NMMA + 1], w0[4] = {0.f, 0.f, 0.f, 0.f}, wl[kTcMaxOut];
+  float db_acc[NMMA + 1], dw0_acc[4] = {0.f, 0.f, 0.f, 0.f}, dwl_acc[kTcMaxOut], dbl_acc = 0.f;
 #pragma unroll
-  for (int v = 0; v < kMaxOut; ++v) wl[v] = (live && v < n_out) ? a.arena[a.w_off[L - 1] + v * W + n] : 0.f;
+  for (int l = 0; l <= NMMA; ++l) { bias[l] = live ? a.arena[a.b_off[l] + n] : 0.f; db_acc[l] = 0.f; }
+  if (live)
+    for (int ax = 0; ax < d; ++ax) w0[ax] = a.arena[a.w_off[0] + n * d + ax];
+#pragma unroll
+  for (int v = 0; v < kTcMaxOut; ++v) { wl[v] = (live && v < n_out) ? a.arena[a.w_off[L - 1] + v * W + n] : 0.f; dwl_acc[v] = 0.f; }
 
   const tdb200_segment& sg = *sm.segS;                  // shared-memory copy (set up above, visible after the sync)
   const int ncols = sg.n_cols;
   int dir_axis[3] = {0, 0, 0};
   for (int i = 0; i < ND; ++i) dir_axis[i] = sg.dir_axis[i];
+  float w0d[3];                                         // first-layer weight along each jet direction
+#pragma unroll
+  for (int i = 0; i < 3; ++i) w0d[i] = i < ND ? w0[dir_axis[i]] : 0.f;
 
   if (tid == 0) bulk_load_image(sm.w_hi, wimg, sm.wbar);          // W_1 for the first tile
 
@@ -443,114 +452,128 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  // Y_l of this thread's columns from the saved tanh values and pre-activation jets
+  auto jets_from_saved = [&](const float* as_l, const float (*zd_l)[JD], bool first, float* y) {
+#pragma unroll
+    for (int p = 0; p < PH; ++p) {
+      const TanhF f(as_l[p]);
+      y[p * J] = as_l[p];
+      int c = 1;
+#pragma unroll
+      for (int i = 0; i < ND; ++i) {
+        float z[4] = {0.f, 0.f, 0.f, 0.f}, yy[4];
+        if (first) z[0] = w0d[i];
+        else {
+#pragma unroll
+          for (int k = 0; k < ORD[i]; ++k) z[k] = zd_l[p][c - 1 + k];
+        }
+        tanh_jet_fwd(f, z, ORD[i], yy);
+#pragma unroll
+        for (int k = 0; k < ORD[i]; ++k) y[p * J + c + k] = yy[k];
+        c += ORD[i];
+      }
+    }
+#pragma unroll
+    for (int j = C; j < 16; ++j) y[j] = 0.f;
+  };
+  auto store_act = [&](const float* v) {                // 16 columns -> MN-major operand image (hi / lo)
+    float hi[16], lo[16];
+    split16(v, hi, lo);
+    st4(sm.act_hi + actA, hi); st4(sm.act_hi + actA + 4, hi + 4); st4(sm.act_hi + actB, hi + 8); st4(sm.act_hi + actB + 4, hi + 12);
+    st4(sm.act_lo + actA, lo); st4(sm.act_lo + actA + 4, lo + 4); st4(sm.act_lo + actB, lo + 8); st4(sm.act_lo + actB + 4, lo + 12);
+  };
+
   load_points(blockIdx.x, sm.xS);
   int xbuf = 0;
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const long long g_first = (long long)tile * P;
     const int p_valid = (int)min((long long)P, sg.n_groups - g_first);
-    float* const xcur = sm.xS + xbuf * kTcCols * 4;
+    float* const xcur = sm.xS + xbuf * kTcMaxPts * 4;
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();                                    // this tile's points (loaded one tile ahead) are visible
-    if (tile + (int)gridDim.x < a.n_tiles) load_points(tile + gridDim.x, sm.xS + (xbuf ^ 1) * kTcCols * 4);
+    if (tile + (int)gridDim.x < a.n_tiles) load_points(tile + gridDim.x, sm.xS + (xbuf ^ 1) * kTcMaxPts * 4);
     xbuf ^= 1;
+    if (tid < p_valid && sg.tgt_off >= 0)               // warm L1 for the operator phase of this tile
+      asm volatile("prefetch.global.L1 [%0];" :: "l"(a.targets + sg.tgt_off + (g_first + tid) * ncols) : "memory");
     TMARK(0);
 
-    float yk[NMMA + 1][12];                             // outputs of tanh layers 0..n_mma for this thread's columns
+    float as[NMMA + 1][PH];                             // tanh values of layers 0..NMMA for this thread's points
+    float zd[NMMA > 0 ? NMMA : 1][PH][JD];              // pre-activation derivative channels of layers 1..NMMA
+    float y[16];
 
     // ---- layer 0 (K = d): thread-local ----------------------------------------------------------------
 #pragma unroll
     for (int p = 0; p < PH; ++p) {
       float z0 = bias[0];
-      for (int ax = 0; ax < d; ++ax) z0 = fmaf(w0[ax], xcur[(half * PH + p) * 4 + ax], z0);
-      const float av = tanh_acc(z0);
-      const TanhF f(av);
-      yk[0][p * J] = av;
-      int c = 1;
-#pragma unroll
-      for (int i = 0; i < ND; ++i) {
-        float z[4] = {w0[dir_axis[i]], 0.f, 0.f, 0.f}, y[4];
-        tanh_jet_fwd(f, z, ORD[i], y);
-#pragma unroll
-        for (int k = 0; k < ORD[i]; ++k) yk[0][p * J + c + k] = y[k];
-        c += ORD[i];
-      }
+      for (int ax = 0; ax < d; ++ax) z0 = fmaf(w0[ax], xcur[(part * PH + p) * 4 + ax], z0);
+      as[0][p] = tanh_fast(z0);
     }
-    if (wgrad_pending) { mbar_wait(sm.gbar, gphase); gphase ^= 1; wgrad_pending = false; }   // Y operand is free again
-    if (live) {
-#pragma unroll
-      for (int j = 0; j < C; ++j) split_store(sm.a_hi, sm.a_lo, sw_off(col0 + j, n, kTcCols), yk[0][j]);
-    }
+    jets_from_saved(as[0], nullptr, true, y);
+    if (live) store_act(y);
 
     // ---- W x W layers: tensor-core GEMM + thread-local tanh-jet epilogue ------------------------------
 #pragma unroll
-    for (int l = 1; l <= n_mma; ++l) {
+    for (int l = 1; l <= NMMA; ++l) {
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
       TMARK(1);
       if (warp == 0) {
         mbar_wait(sm.wbar, wphase); wphase ^= 1;        // W_l image has landed
-        TMARK(2);
         tc_fence_after();
-        issue_forward_any(tmem + kTmZ + 48u * (uint32_t)(l - 1), sm.w_hi, sm.w_lo, sm.a_hi, sm.a_lo, ksteps);
+        issue_gemm_any(tmem + kTmD, sm.w_hi, sm.w_lo, sm.act_hi, sm.act_lo, ksteps);
         if (elect_one()) umma_commit(sm.bar);
         __syncwarp();
-        TMARK(3);
+        TMARK(2);
       }
       mbar_wait(sm.bar, phase);
       phase ^= 1;
       tc_fence_after();
-      TMARK(4);
-      // next image (W_{l+1}, or W_{n_mma}^T for the backward sweep) streams in behind the epilogue
-      if (tid == 0)
-        bulk_load_image(sm.w_hi, wimg + (size_t)(l < n_mma ? l : n_mma - 1) * 4 * kTcWFloats + (l < n_mma ? 0 : 2 * kTcWFloats), sm.wbar);
+      TMARK(3);
+      // next image (W_{l+1}, or W_NMMA^T for the backward sweep, or W_1 again) streams in behind the epilogue
+      if (tid == 0) {
+        const float* nxt = l < NMMA ? wimg + (size_t)l * 4 * kTcWFloats
+                                    : (a.do_grad ? wimg + (size_t)(NMMA - 1) * 4 * kTcWFloats + 2 * kTcWFloats : wimg);
+        bulk_load_image(sm.w_hi, nxt, sm.wbar);
+      }
       float z[16];
-      tmem_ld16w(t_lane + kTmZ + 48u * (uint32_t)(l - 1) + (uint32_t)col0, z);
+      tmem_ld16(t_lane + kTmD + (uint32_t)col0, z);
 #pragma unroll
       for (int p = 0; p < PH; ++p) {
-        const float av = tanh_acc(z[p * J] + bias[l]);
-        const TanhF f(av);
-        yk[l][p * J] = av;
-        int c = 1;
+        as[l][p] = tanh_fast(z[p * J] + bias[l]);
 #pragma unroll
-        for (int i = 0; i < ND; ++i) {
-          float y[4];
-          tanh_jet_fwd(f, z + p * J + c, ORD[i], y);
-#pragma unroll
-          for (int k = 0; k < ORD[i]; ++k) yk[l][p * J + c + k] = y[k];
-          c += ORD[i];
-        }
+        for (int k = 0; k < J - 1; ++k) zd[l - 1][p][k] = z[p * J + 1 + k];
       }
-      if (live && l < n_mma) {
-#pragma unroll
-        for (int j = 0; j < C; ++j) split_store(sm.a_hi, sm.a_lo, sw_off(col0 + j, n, kTcCols), yk[l][j]);
-      }
+      jets_from_saved(as[l], zd[l - 1], false, y);
+      if (live && l < NMMA) store_act(y);
     }
 
-    TMARK(5);
+    TMARK(4);
     // ---- last layer: u[v][col] = sum_n Wl[v][n] y[n][col]  (warp multi-value reduction, fixed order) ------
     for (int v = 0; v < n_out; ++v) {
-      float t32[32];
+      float t16[16];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) t32[j] = (j < C && live) ? wl[v] * yk[n_mma][j] : 0.f;
-      const float tot = warp_multi_reduce32(t32, lane);
-      if (lane < C) sm.uP[((warp & 3) * kMaxOut + v) * kTcCols + col0 + lane] = tot;
+      for (int j = 0; j < 16; ++j) t16[j] = wl[v] * y[j];          // wl is zero in dead lanes
+      const float tot = warp_multi_reduce16(t16, lane);
+      if ((lane & 1) == 0) sm.uP[((warp & 3) * kTcMaxOut + v) * kTcCols + col0 + reduce16_col(lane)] = tot;
     }
     __syncthreads();
-    for (int idx = tid; idx < n_out * kTcParts * C; idx += kTcThreads) {
-      const int v = idx / (kTcParts * C), r = idx - v * (kTcParts * C);
-      float s = (r % J) == 0 ? a.arena[a.b_off[L - 1] + v] : 0.f;
+    for (int idx = tid; idx < n_out * kTcCols; idx += kTcThreads) {
+      const int v = idx / kTcCols, r = idx - v * kTcCols;
+      const int jc = r & (kTcPC - 1);
+      float s = (jc < C && jc % J == 0) ? a.arena[a.b_off[L - 1] + v] : 0.f;
 #pragma unroll
-      for (int w = 0; w < 4; ++w) s += sm.uP[(w * kMaxOut + v) * kTcCols + r];
-      sm.uS[v * kTcCols + r] = s;
-      sm.guS[v * kTcCols + r] = 0.f;
+      for (int w = 0; w < 4; ++w) s += sm.uP[(w * kTcMaxOut + v) * kTcCols + r];
+      sm.uS[idx] = s;
+      sm.guS[idx] = 0.f;
     }
     __syncthreads();
 
-    TMARK(6);
+    TMARK(5);
     // ---- operator terms, residual, loss, adjoint seeds (one thread per point) -------------------------
     if (tid < p_valid) {
       const int p = tid;
+      const int pc = (p / PH) * kTcPC + (p % PH) * J;   // first column of this point
       const long long row = g_first + p;
       for (int col = 0; col < ncols; ++col) {
         float val = 0.f;
@@ -560,7 +583,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
                                                                : a.arena[a.n_net_params + tm.idx];
           for (int fi = tm.fac_begin; fi < tm.fac_end; ++fi) {
             const tdb200_factor fc = sm.facS[fi];
-            prod *= pow_i(sm.uS[fc.var * kTcCols + p * J + fc.chan], fc.ipow, fc.pow);
+            prod *= pow_i(sm.uS[fc.var * kTcCols + pc + fc.chan], fc.ipow, fc.pow);
           }
           val += prod;
         }
@@ -578,14 +601,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
           float full = 1.f;
           for (int fi = tm.fac_begin; fi < tm.fac_end; ++fi) {
             const tdb200_factor fc = sm.facS[fi];
-            const float x = sm.uS[fc.var * kTcCols + p * J + fc.chan];
-            float part = seed * cf * dpow_i(x, fc.ipow, fc.pow);
+            const float x = sm.uS[fc.var * kTcCols + pc + fc.chan];
+            float part_ = seed * cf * dpow_i(x, fc.ipow, fc.pow);
             for (int fj = tm.fac_begin; fj < tm.fac_end; ++fj) {
               if (fj == fi) continue;
               const tdb200_factor fo = sm.facS[fj];
-              part *= pow_i(sm.uS[fo.var * kTcCols + p * J + fo.chan], fo.ipow, fo.pow);
+              part_ *= pow_i(sm.uS[fo.var * kTcCols + pc + fo.chan], fo.ipow, fo.pow);
             }
-            sm.guS[fc.var * kTcCols + p * J + fc.chan] += part;
+            sm.guS[fc.var * kTcCols + pc + fc.chan] += part_;
             full *= pow_i(x, fc.ipow, fc.pow);
           }
           if (tm.kind == 2) atomicAdd(&sm.cgS[tm.idx], seed * full);
@@ -593,18 +616,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       }
     }
     __syncthreads();
-    if (!a.do_grad) {
-      // forward-only evaluation: the image prefetched for the backward sweep is not needed; fetch W_1 instead
-      if (warp == 0) { mbar_wait(sm.wbar, wphase); wphase ^= 1; __syncwarp(); if (tid == 0) bulk_load_image(sm.w_hi, wimg, sm.wbar); }
-      continue;
-    }
+    if (!a.do_grad) continue;
 
-    TMARK(7);
-    // ---- backward of the last layer: dWl, dbl; gY of the last tanh layer ---------------------------------
-    if (tid < n_out) {                                   // warp 0 -> part-0 row
+    TMARK(6);
+    // ---- backward of the last layer: dWl, dbl accumulators; gY of the last tanh layer ----------------------
+    if (tid < n_out) {
       float s = 0.f;
-      for (int p = 0; p < P; ++p) s += sm.guS[tid * kTcCols + p * J];
-      atomicAdd(my_grad + a.b_off[L - 1] + tid, s);
+      for (int p = 0; p < P; ++p) s += sm.guS[tid * kTcCols + (p / PH) * kTcPC + (p % PH) * J];
+      dbl_acc += s;
     }
     float gy[16];
 #pragma unroll
@@ -612,129 +631,140 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
     for (int v = 0; v < n_out; ++v) {
       float s = 0.f;
 #pragma unroll
-      for (int j = 0; j < C; ++j) {
-        const float g = sm.guS[v * kTcCols + col0 + j];
-        s = fmaf(g, yk[n_mma][j], s);
-        gy[j] = fmaf(wl[v], g, gy[j]);
+      for (int q = 0; q < 4; ++q) {
+        const float4 g4 = *reinterpret_cast<const float4*>(sm.guS + v * kTcCols + col0 + 4 * q);
+        const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          s = fmaf(g[i], y[4 * q + i], s);
+          gy[4 * q + i] = fmaf(wl[v], g[i], gy[4 * q + i]);
+        }
       }
-      if (live) atomicAdd(my_grad + a.w_off[L - 1] + v * W + n, s);
+#pragma unroll
+      for (int vv = 0; vv < kTcMaxOut; ++vv) if (vv == v) dwl_acc[vv] += s;
     }
 
-    // ---- backward sweep over the tanh layers t = n_mma .. 0 ------------------------------------------
+    // ---- backward sweep over the tanh layers t = NMMA .. 0 ------------------------------------------
 #pragma unroll
-    for (int t = n_mma; t >= 0; --t) {
-      float z[16];
-      if (t > 0) tmem_ld16w(t_lane + kTmZ + 48u * (uint32_t)(t - 1) + (uint32_t)col0, z);
-      if (t < n_mma) tmem_ld16w(t_lane + kTmDb + (uint32_t)col0, gy);
-      float gz[12];
-      float db = 0.f, dw0[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int t = NMMA; t >= 0; --t) {
+      if (t < NMMA) tmem_ld16(t_lane + kTmD + (uint32_t)col0, gy);
+      float gz[16];
+      float db = 0.f;
 #pragma unroll
       for (int p = 0; p < PH; ++p) {
-        const float av = yk[t][p * J];
-        const TanhF f(av);
+        const TanhF f(as[t][p]);
         float g0 = gy[p * J] * f.f1;
         int c = 1;
 #pragma unroll
         for (int i = 0; i < ND; ++i) {
           float zz[4] = {0.f, 0.f, 0.f, 0.f}, gg[4];
-          if (t == 0) zz[0] = w0[dir_axis[i]];
+          if (t == 0) zz[0] = w0d[i];
           else {
 #pragma unroll
-            for (int k = 0; k < ORD[i]; ++k) zz[k] = z[p * J + c + k];
+            for (int k = 0; k < ORD[i]; ++k) zz[k] = zd[t > 0 ? t - 1 : 0][p][c - 1 + k];
           }
           g0 += tanh_jet_bwd(f, zz, gy + p * J + c, ORD[i], gg);
-          if (t == 0) dw0[dir_axis[i]] += gg[0];
+          if (t == 0) {
+#pragma unroll
+            for (int ax = 0; ax < 4; ++ax) if (ax == dir_axis[i]) dw0_acc[ax] += gg[0];
+          }
 #pragma unroll
           for (int k = 0; k < ORD[i]; ++k) gz[p * J + c + k] = gg[k];
           c += ORD[i];
         }
         gz[p * J] = g0;
         db += g0;
-        if (t == 0)
-          for (int ax = 0; ax < d; ++ax) dw0[ax] = fmaf(g0, xcur[(half * PH + p) * 4 + ax], dw0[ax]);
+        if (t == 0) {
+#pragma unroll
+          for (int ax = 0; ax < 4; ++ax) if (ax < d) dw0_acc[ax] = fmaf(g0, xcur[(part * PH + p) * 4 + ax], dw0_acc[ax]);
+        }
       }
-      if (live) atomicAdd(my_grad + a.b_off[t] + n, db);
-      if (t == 0) {
-        if (live) for (int ax = 0; ax < d; ++ax) atomicAdd(my_grad + a.w_off[0] + n * d + ax, dw0[ax]);
-        break;
-      }
+      db_acc[t] += db;
+      if (t == 0) break;
+#pragma unroll
+      for (int j = C; j < 16; ++j) gz[j] = 0.f;
       // gZ -> shared memory (B operand of the backward-data GEMM) and TMEM (A operand of the weight-gradient GEMM);
-      // Y_{t-1} -> shared memory as the MN-major B operand of the weight-gradient GEMM.  All hi / lo tf32 pairs.
+      // Y_{t-1} -> shared memory as the K-major B operand of the weight-gradient GEMM.  All hi / lo tf32 pairs.
+      float yp[16];
+      jets_from_saved(as[t - 1], zd[t > 1 ? t - 2 : 0], t == 1, yp);
       if (wgrad_pending) { mbar_wait(sm.gbar, gphase); gphase ^= 1; wgrad_pending = false; tc_fence_after(); }
       {
-        float ghi[12], glo[12];
+        float hi[16], lo[16];
+        if (!live) {
 #pragma unroll
-        for (int j = 0; j < C; ++j) {
-          const float g = live ? gz[j] : 0.f;
-          uint32_t hb;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(g));
-          ghi[j] = __uint_as_float(hb);
-          glo[j] = g - ghi[j];
+          for (int j = 0; j < 16; ++j) gz[j] = 0.f;
         }
+        split16(gz, hi, lo);
         if (live) {
-#pragma unroll
-          for (int j = 0; j < C; ++j) {
-            const int o = sw_off(col0 + j, n, kTcCols);
-            sm.b_hi[o] = ghi[j];
-            sm.b_lo[o] = glo[j];
-            split_store(sm.a_hi, sm.a_lo, sw_off_mn(col0 + j, n, kTcCols), yk[t - 1][j]);
-          }
+          st4(sm.act_hi + actA, hi); st4(sm.act_hi + actA + 4, hi + 4); st4(sm.act_hi + actB, hi + 8); st4(sm.act_hi + actB + 4, hi + 12);
+          st4(sm.act_lo + actA, lo); st4(sm.act_lo + actA + 4, lo + 4); st4(sm.act_lo + actB, lo + 8); st4(sm.act_lo + actB + 4, lo + 12);
         }
-        tmem_st_cols<C>(t_lane + kTmAHi + (uint32_t)col0, ghi);
-        tmem_st_cols<C>(t_lane + kTmALo + (uint32_t)col0, glo);
+        tmem_st16(t_lane + kTmAHi + (uint32_t)col0, hi);
+        tmem_st16(t_lane + kTmALo + (uint32_t)col0, lo);
+        if (live) {
+          split16(yp, hi, lo);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { st4(sm.yw_hi + ywq[q], hi + 4 * q); st4(sm.yw_lo + ywq[q], lo + 4 * q); }
+        }
         tmem_st_wait();
       }
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
-      TMARK(8);
+      TMARK(7);
       if (warp == 0) {
         mbar_wait(sm.wbar, wphase); wphase ^= 1;        // W_t^T image has landed
-        TMARK(9);
         tc_fence_after();
-        issue_forward_any(tmem + kTmDb, sm.w_hi, sm.w_lo, sm.b_hi, sm.b_lo, ksteps);   // A = W_t^T image
+        issue_gemm_any(tmem + kTmD, sm.w_hi, sm.w_lo, sm.act_hi, sm.act_lo, ksteps);   // A = W_t^T image
         if (elect_one()) umma_commit(sm.bar);
         __syncwarp();
         // the weight gradient is not on the critical path: it runs behind the next adjoint epilogue
-        issue_wgrad(tmem + kTmDw + (uint32_t)(t - 1) * kTmDwCols, tmem + kTmAHi, tmem + kTmALo, sm.a_hi, sm.a_lo,
-                    dw_started);
+        issue_wgrad(tmem + kTmDw + (uint32_t)(t - 1) * kTmDwCols, tmem + kTmAHi, tmem + kTmALo, sm.yw_hi, sm.yw_lo, dw_started);
         if (elect_one()) umma_commit(sm.gbar);
         __syncwarp();
-        TMARK(10);
+        TMARK(8);
       }
       wgrad_pending = true;
       mbar_wait(sm.bar, phase);
       phase ^= 1;
       tc_fence_after();
-      TMARK(11);
+      TMARK(9);
       if (tid == 0) {                                   // next image: W_{t-1}^T, or W_1 for the next tile
         const float* nxt = t > 1 ? wimg + (size_t)(t - 2) * 4 * kTcWFloats + 2 * kTcWFloats : wimg;
         bulk_load_image(sm.w_hi, nxt, sm.wbar);
       }
     }
     dw_started = 1;
-    tc_fence_before();
-    __syncthreads();
-    TMARK(12);
+    TMARK(10);
   }
   if (a.dbg && tid == 0)
     for (int i = 0; i < 16; ++i) a.dbg[(size_t)blockIdx.x * 16 + i] = tacc[i];
 
-  // ---- flush: dW accumulators (TMEM) and per-CTA scalars ----------------------------------------------
+  // ---- flush: per-thread accumulators, dW accumulators (TMEM), per-CTA scalars --------------------------
   if (warp == 0) { mbar_wait(sm.wbar, wphase); wphase ^= 1; }   // drain the last prefetch before exiting
   if (wgrad_pending) { mbar_wait(sm.gbar, gphase); gphase ^= 1; wgrad_pending = false; }
   __syncthreads();
   tc_fence_after();
-  if (a.do_grad && dw_started) {
-    float* row0 = a.part_grad + (size_t)blockIdx.x * kTcParts * a.n_params_pad;   // dW lives in the part-0 row
-    for (int t = 1; t <= n_mma; ++t) {
-      float* dst = row0 + a.w_off[t];
-      for (int k0 = half * 32; k0 < half * 32 + 32 && k0 < (int)kTmDwCols; k0 += 8) {
-        float v[8];
-        tmem_ld8(t_lane + kTmDw + (uint32_t)(t - 1) * kTmDwCols + (uint32_t)k0, v);
-        if (live)
-          for (int j = 0; j < 8; ++j)
-            if (k0 + j < W) dst[(size_t)n * W + k0 + j] = v[j];
+  if (a.do_grad) {
+    if (live) {
+#pragma unroll
+      for (int l = 0; l <= NMMA; ++l) my_grad[a.b_off[l] + n] = db_acc[l];
+      for (int ax = 0; ax < d; ++ax) my_grad[a.w_off[0] + n * d + ax] = dw0_acc[ax];
+#pragma unroll
+      for (int v = 0; v < kTcMaxOut; ++v) if (v < n_out) my_grad[a.w_off[L - 1] + v * W + n] = dwl_acc[v];
+    }
+    if (tid < n_out) my_grad[a.b_off[L - 1] + tid] = dbl_acc;     // warp 0 -> part-0 row
+    if (dw_started) {
+      float* row0 = a.part_grad + (size_t)blockIdx.x * kTcParts * a.n_params_pad;   // dW lives in the part-0 row
+      for (int t = 1; t <= NMMA; ++t) {
+        float* dst = row0 + a.w_off[t];
+        for (int k0 = part * 32; k0 < part * 32 + 32 && k0 < (int)kTmDwCols; k0 += 16) {
+          float v[16];
+          tmem_ld16(t_lane + kTmDw + (uint32_t)(t - 1) * kTmDwCols + (uint32_t)k0, v);
+          if (live)
+            for (int j = 0; j < 16; ++j)
+              if (k0 + j < W) dst[(size_t)n * W + k0 + j] = v[j];
+        }
       }
     }
   }
@@ -745,7 +775,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
         for (int p = 0; p < P; ++p) s += sm.lossT[p * TDB200_MAX_COLS + col];
     a.part_loss[(size_t)blockIdx.x * a.n_slots + tid] = s;
   }
-  if (a.do_grad && tid < a.n_cparams) my_grad[a.n_net_params + tid] = sm.cgS[tid];   // warp 0 -> half-0 row
+  if (a.do_grad && tid < a.n_cparams) my_grad[a.n_net_params + tid] = sm.cgS[tid];   // warp 0 -> part-0 row
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
@@ -778,8 +808,9 @@ bool jet_tc_supports(int o0, int o1, int o2) {
 #undef X
   return false;
 }
-int jet_tc_points_per_tile(int o0, int o1, int o2) { return kTcParts * (12 / (1 + o0 + o1 + o2)); }
+int jet_tc_points_per_tile(int o0, int o1, int o2) { return kTcParts * (kTcPC / (1 + o0 + o1 + o2)); }
 int jet_tc_partial_rows() { return kTcParts; }
+int jet_tc_max_out() { return kTcMaxOut; }
 
 cudaError_t launch_jet_tc(const JetArgs& a, const float* wimg, int o0, int o1, int o2, int grid, cudaStream_t s) {
   const int n_mma = a.n_layers - 2;
