@@ -8,7 +8,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 LIB_DIR = os.path.join(PKG, 'lib')
-LIB = os.path.join(LIB_DIR, 'libtedeous_b200.so')
+LIB = os.environ.get('TDB200_LIB') or os.path.join(LIB_DIR, 'libtedeous_b200.so')   # TDB200_LIB: use a prebuilt variant
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '--use_fast_math=false', '-Xptxas', '-v']
 
@@ -18,6 +18,8 @@ def sources():
 
 
 def needs_build() -> bool:
+    if os.environ.get('TDB200_LIB'):
+        return False
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
@@ -32,7 +34,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIB_DIR, exist_ok=True)
     def compile_one(src):
         obj = os.path.join(LIB_DIR, os.path.basename(src)[:-3] + '.o')
-        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != '--use_fast_math=false'] + \
+        extra = ['-DTDB_TC_TIMING'] if os.environ.get('TDB200_TC_TIMING_BUILD') else []
+        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != '--use_fast_math=false'] + extra + \
               ['-I', os.path.join(ROOT, 'include'), '-I', os.path.join(PKG, 'csrc'), '-c', src, '-o', obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or res.returncode != 0:

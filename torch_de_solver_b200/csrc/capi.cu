@@ -350,7 +350,7 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
       cudaFree(dbg);
       const int tiles_per_cta = (p->tc_tiles + p->tc_grid - 1) / p->tc_grid;
       fprintf(stderr, "[tdb200 tc timing] cycles per tile (thread 0 of CTA 0, %d tiles):", tiles_per_cta);
-      for (int i = 0; i < 13; ++i) fprintf(stderr, " p%d=%lld", i, h[i] / tiles_per_cta);
+      for (int i = 0; i < 16; ++i) fprintf(stderr, " p%d=%lld", i, h[i] / tiles_per_cta);
       fprintf(stderr, "\n");
     }
     grad_rows = tdb::jet_tc_partial_rows() * p->tc_grid;

@@ -138,9 +138,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        : "=r"(done) : "r"(addr), "r"(parity), "r"(20000u) : "memory");   // suspend-time hint: sleep, do not spin
   } while (!done);
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -318,9 +318,12 @@ __device__ __forceinline__ void bulk_load_image(float* dst, const float* src, ui
 // ------------------------------------------------------------------------------------------------
 constexpr int kTcMaxTerms = 48, kTcMaxFactors = 96;   // operator program cached in shared memory
 constexpr int kTcMaxPts = 32;                         // points per tile (J = 2)
+// float offsets of the big buffers from the 1024-byte aligned base (compile-time: addresses fold into immediates)
+constexpr int kOffWHi = 0, kOffWLo = kTcWFloats, kOffActHi = 2 * kTcWFloats, kOffActLo = kOffActHi + kTcActFloats,
+              kOffYwHi = kOffActLo + kTcActFloats, kOffYwLo = kOffYwHi + kTcYwFloats, kOffX = kOffYwLo + kTcYwFloats,
+              kOffU = kOffX + 2 * kTcMaxPts * 4, kOffGu = kOffU + kTcMaxOut * kTcCols, kOffUP = kOffGu + kTcMaxOut * kTcCols,
+              kOffCg = kOffUP + 4 * kTcMaxOut * kTcCols, kOffEnd = kOffCg + (kMaxCParams + 3) / 4 * 4;
 struct TcSmem {
-  float *w_hi, *w_lo, *act_hi, *act_lo, *yw_hi, *yw_lo;
-  float *xS, *uS, *guS, *uP, *cgS;
   tdb200_term* termS;
   tdb200_factor* facS;
   tdb200_segment* segS;
@@ -348,30 +351,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
   constexpr int JD = J > 1 ? J - 1 : 1;        // derivative channels per point
   constexpr int ORD[3] = {O0, O1, O2};
   extern __shared__ uint8_t smem_raw_tc[];
+  // align inside the shared window with pointer arithmetic on the __shared__ symbol itself: a round trip through
+  // uintptr_t would turn every later access into a generic LD / ST
+  const uint32_t s0_ = smem_u32(smem_raw_tc);
+  float* const sbase = reinterpret_cast<float*>(smem_raw_tc + (((s0_ + 1023u) & ~1023u) - s0_));
   TcSmem sm;
   {
-    uintptr_t base = (reinterpret_cast<uintptr_t>(smem_raw_tc) + 1023) & ~uintptr_t(1023);
-    float* f = reinterpret_cast<float*>(base);
-    sm.w_hi = f; f += kTcWFloats;
-    sm.w_lo = f; f += kTcWFloats;
-    sm.act_hi = f; f += kTcActFloats;
-    sm.act_lo = f; f += kTcActFloats;
-    sm.yw_hi = f; f += kTcYwFloats;
-    sm.yw_lo = f; f += kTcYwFloats;
-    sm.xS = f; f += 2 * kTcMaxPts * 4;                 // double buffered: the next tile's points are prefetched
-    sm.uS = f; f += kTcMaxOut * kTcCols;
-    sm.guS = f; f += kTcMaxOut * kTcCols;
-    sm.uP = f; f += 4 * kTcMaxOut * kTcCols;
-    sm.cgS = f; f += kMaxCParams;
-    sm.bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(f) + 15) & ~uintptr_t(15));
+    // kOffEnd is a multiple of 4 floats and sbase is 1024-byte aligned: everything below is 16-byte aligned
+    uint8_t* q = reinterpret_cast<uint8_t*>(sbase + kOffEnd);
+    sm.bar = reinterpret_cast<uint64_t*>(q); q += 32;
     sm.wbar = sm.bar + 1;
     sm.gbar = sm.bar + 2;
     sm.tmem_ptr = reinterpret_cast<uint32_t*>(sm.bar + 3);
-    sm.termS = reinterpret_cast<tdb200_term*>((reinterpret_cast<uintptr_t>(sm.tmem_ptr + 2) + 15) & ~uintptr_t(15));
-    sm.facS = reinterpret_cast<tdb200_factor*>(sm.termS + kTcMaxTerms);
-    sm.segS = reinterpret_cast<tdb200_segment*>(sm.facS + kTcMaxFactors);
-    sm.scaleS = reinterpret_cast<float*>(sm.segS + 1);
-    sm.lossT = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sm.scaleS + 32) + 15) & ~uintptr_t(15));
+    sm.termS = reinterpret_cast<tdb200_term*>(q); q += (kTcMaxTerms * sizeof(tdb200_term) + 15) / 16 * 16;
+    sm.facS = reinterpret_cast<tdb200_factor*>(q); q += (kTcMaxFactors * sizeof(tdb200_factor) + 15) / 16 * 16;
+    sm.segS = reinterpret_cast<tdb200_segment*>(q); q += (sizeof(tdb200_segment) + 15) / 16 * 16;
+    sm.scaleS = reinterpret_cast<float*>(q); q += 32 * 4;
+    sm.lossT = reinterpret_cast<double*>(q);
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = (warp & 3) * 32 + lane;                 // neuron = TMEM lane owned by this thread
@@ -392,8 +388,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
   // ---- one-time setup --------------------------------------------------------------------------------
   for (int i = tid; i < kTcParts * a.n_params_pad; i += kTcThreads)
     a.part_grad[(size_t)blockIdx.x * kTcParts * a.n_params_pad + i] = 0.f;
-  for (int i = tid; i < 2 * kTcActFloats + 2 * kTcYwFloats; i += kTcThreads) sm.act_hi[i] = 0.f;   // pad rows / columns stay zero
-  if (tid < kMaxCParams) sm.cgS[tid] = 0.f;
+  for (int i = tid; i < 2 * kTcActFloats + 2 * kTcYwFloats; i += kTcThreads) (sbase + kOffActHi)[i] = 0.f;   // pad rows / columns stay zero
+  if (tid < kMaxCParams) (sbase + kOffCg)[tid] = 0.f;
+  for (int i = tid; i < 2 * kTcMaxPts * 4; i += kTcThreads) (sbase + kOffX)[i] = 0.f;      // axes >= d stay zero
   for (int i = tid; i < min(kTcMaxTerms, a.n_terms); i += kTcThreads) sm.termS[i] = a.terms[i];
   for (int i = tid; i < min(kTcMaxFactors, a.n_factors); i += kTcThreads) sm.facS[i] = a.factors[i];
   for (int i = tid; i < (int)(sizeof(tdb200_segment) / 4); i += kTcThreads)
@@ -411,17 +408,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
   tc_fence_after();
   const uint32_t tmem = *sm.tmem_ptr;
   const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);    // this warp's lane window
+#ifdef TDB_TC_TIMING
   long long tacc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) tacc[i] = 0;
   long long tlast = clock64();
+#endif
+#ifdef TDB_TC_TIMING       // phase timers: build with TDB200_TC_TIMING_BUILD=1 (adds ~6 % instructions)
 #define TMARK(i) do { if (a.dbg) { const long long tn_ = clock64(); tacc[i] += tn_ - tlast; tlast = tn_; } } while (0)
+#else
+#define TMARK(i) do { } while (0)
+#endif
   uint32_t phase = 0, wphase = 0, gphase = 0;           // wphase is only used by warp 0
   bool wgrad_pending = false;                           // weight-gradient MMAs still reading TMEM A / the Y image
   uint32_t dw_started = 0;
   // per-layer parameters this thread needs all the time, and its gradient accumulators (flushed once per CTA)
   float bias[NMMA + 1], w0[4] = {0.f, 0.f, 0.f, 0.f}, wl[kTcMaxOut];
-  float db_acc[NMMA + 1], dw0_acc[4] = {0.f, 0.f, 0.f, 0.f}, dwl_acc[kTcMaxOut], dbl_acc = 0.f;
+  float db_acc[NMMA + 1], dw0_acc[4] = {0.f, 0.f, 0.f, 0.f}, dw0_dir[3] = {0.f, 0.f, 0.f}, dwl_acc[kTcMaxOut], dbl_acc = 0.f;
 #pragma unroll
   for (int l = 0; l <= NMMA; ++l) { bias[l] = live ? a.arena[a.b_off[l] + n] : 0.f; db_acc[l] = 0.f; }
   if (live)
@@ -437,7 +440,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
 #pragma unroll
   for (int i = 0; i < 3; ++i) w0d[i] = i < ND ? w0[dir_axis[i]] : 0.f;
 
-  if (tid == 0) bulk_load_image(sm.w_hi, wimg, sm.wbar);          // W_1 for the first tile
+  if (tid == 0) bulk_load_image((sbase + kOffWHi), wimg, sm.wbar);          // W_1 for the first tile
 
   auto load_points = [&](int tile_idx, float* dst) {
     const long long gf = (long long)tile_idx * P;
@@ -479,19 +482,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
   auto store_act = [&](const float* v) {                // 16 columns -> MN-major operand image (hi / lo)
     float hi[16], lo[16];
     split16(v, hi, lo);
-    st4(sm.act_hi + actA, hi); st4(sm.act_hi + actA + 4, hi + 4); st4(sm.act_hi + actB, hi + 8); st4(sm.act_hi + actB + 4, hi + 12);
-    st4(sm.act_lo + actA, lo); st4(sm.act_lo + actA + 4, lo + 4); st4(sm.act_lo + actB, lo + 8); st4(sm.act_lo + actB + 4, lo + 12);
+    st4((sbase + kOffActHi) + actA, hi); st4((sbase + kOffActHi) + actA + 4, hi + 4); st4((sbase + kOffActHi) + actB, hi + 8); st4((sbase + kOffActHi) + actB + 4, hi + 12);
+    st4((sbase + kOffActLo) + actA, lo); st4((sbase + kOffActLo) + actA + 4, lo + 4); st4((sbase + kOffActLo) + actB, lo + 8); st4((sbase + kOffActLo) + actB + 4, lo + 12);
   };
 
-  load_points(blockIdx.x, sm.xS);
+  load_points(blockIdx.x, (sbase + kOffX));
   int xbuf = 0;
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const long long g_first = (long long)tile * P;
     const int p_valid = (int)min((long long)P, sg.n_groups - g_first);
-    float* const xcur = sm.xS + xbuf * kTcMaxPts * 4;
+    float* const xcur = (sbase + kOffX) + xbuf * kTcMaxPts * 4;
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();                                    // this tile's points (loaded one tile ahead) are visible
-    if (tile + (int)gridDim.x < a.n_tiles) load_points(tile + gridDim.x, sm.xS + (xbuf ^ 1) * kTcMaxPts * 4);
+    if (tile + (int)gridDim.x < a.n_tiles) load_points(tile + gridDim.x, (sbase + kOffX) + (xbuf ^ 1) * kTcMaxPts * 4);
     xbuf ^= 1;
     if (tid < p_valid && sg.tgt_off >= 0)               // warm L1 for the operator phase of this tile
       asm volatile("prefetch.global.L1 [%0];" :: "l"(a.targets + sg.tgt_off + (g_first + tid) * ncols) : "memory");
@@ -504,9 +507,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
     // ---- layer 0 (K = d): thread-local ----------------------------------------------------------------
 #pragma unroll
     for (int p = 0; p < PH; ++p) {
-      float z0 = bias[0];
-      for (int ax = 0; ax < d; ++ax) z0 = fmaf(w0[ax], xcur[(part * PH + p) * 4 + ax], z0);
-      as[0][p] = tanh_fast(z0);
+      const float4 x4 = *reinterpret_cast<const float4*>(xcur + (part * PH + p) * 4);   // unused axes hold 0
+      as[0][p] = tanh_fast(fmaf(w0[0], x4.x, fmaf(w0[1], x4.y, fmaf(w0[2], x4.z, fmaf(w0[3], x4.w, bias[0])))));
     }
     jets_from_saved(as[0], nullptr, true, y);
     if (live) store_act(y);
@@ -521,7 +523,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       if (warp == 0) {
         mbar_wait(sm.wbar, wphase); wphase ^= 1;        // W_l image has landed
         tc_fence_after();
-        issue_gemm_any(tmem + kTmD, sm.w_hi, sm.w_lo, sm.act_hi, sm.act_lo, ksteps);
+        issue_gemm_any(tmem + kTmD, (sbase + kOffWHi), (sbase + kOffWLo), (sbase + kOffActHi), (sbase + kOffActLo), ksteps);
         if (elect_one()) umma_commit(sm.bar);
         __syncwarp();
         TMARK(2);
@@ -534,7 +536,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       if (tid == 0) {
         const float* nxt = l < NMMA ? wimg + (size_t)l * 4 * kTcWFloats
                                     : (a.do_grad ? wimg + (size_t)(NMMA - 1) * 4 * kTcWFloats + 2 * kTcWFloats : wimg);
-        bulk_load_image(sm.w_hi, nxt, sm.wbar);
+        bulk_load_image((sbase + kOffWHi), nxt, sm.wbar);
       }
       float z[16];
       tmem_ld16(t_lane + kTmD + (uint32_t)col0, z);
@@ -555,7 +557,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
 #pragma unroll
       for (int j = 0; j < 16; ++j) t16[j] = wl[v] * y[j];          // wl is zero in dead lanes
       const float tot = warp_multi_reduce16(t16, lane);
-      if ((lane & 1) == 0) sm.uP[((warp & 3) * kTcMaxOut + v) * kTcCols + col0 + reduce16_col(lane)] = tot;
+      if ((lane & 1) == 0) (sbase + kOffUP)[((warp & 3) * kTcMaxOut + v) * kTcCols + col0 + reduce16_col(lane)] = tot;
     }
     __syncthreads();
     for (int idx = tid; idx < n_out * kTcCols; idx += kTcThreads) {
@@ -563,9 +565,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       const int jc = r & (kTcPC - 1);
       float s = (jc < C && jc % J == 0) ? a.arena[a.b_off[L - 1] + v] : 0.f;
 #pragma unroll
-      for (int w = 0; w < 4; ++w) s += sm.uP[(w * kTcMaxOut + v) * kTcCols + r];
-      sm.uS[idx] = s;
-      sm.guS[idx] = 0.f;
+      for (int w = 0; w < 4; ++w) s += (sbase + kOffUP)[(w * kTcMaxOut + v) * kTcCols + r];
+      (sbase + kOffU)[idx] = s;
+      (sbase + kOffGu)[idx] = 0.f;
     }
     __syncthreads();
 
@@ -583,15 +585,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
                                                                : a.arena[a.n_net_params + tm.idx];
           for (int fi = tm.fac_begin; fi < tm.fac_end; ++fi) {
             const tdb200_factor fc = sm.facS[fi];
-            prod *= pow_i(sm.uS[fc.var * kTcCols + pc + fc.chan], fc.ipow, fc.pow);
+            prod *= pow_i((sbase + kOffU)[fc.var * kTcCols + pc + fc.chan], fc.ipow, fc.pow);
           }
           val += prod;
         }
+        TMARK(11);
         if (a.fields) a.fields[sg.field_off + row * ncols + col] = val;
         const float tgt = sg.tgt_off >= 0 ? __ldg(a.targets + sg.tgt_off + row * ncols + col) : 0.f;
         const float res = val - tgt;
         const int slot = sg.col_slot[col];
         sm.lossT[p * TDB200_MAX_COLS + col] += (double)res * (double)res;
+        TMARK(12);
         if (!a.do_grad) continue;
         const float seed = 2.f * sm.scaleS[slot] * res;
         for (int t = sg.col_term_begin[col]; t < sg.col_term_end[col]; ++t) {
@@ -601,20 +605,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
           float full = 1.f;
           for (int fi = tm.fac_begin; fi < tm.fac_end; ++fi) {
             const tdb200_factor fc = sm.facS[fi];
-            const float x = sm.uS[fc.var * kTcCols + pc + fc.chan];
+            const float x = (sbase + kOffU)[fc.var * kTcCols + pc + fc.chan];
             float part_ = seed * cf * dpow_i(x, fc.ipow, fc.pow);
             for (int fj = tm.fac_begin; fj < tm.fac_end; ++fj) {
               if (fj == fi) continue;
               const tdb200_factor fo = sm.facS[fj];
-              part_ *= pow_i(sm.uS[fo.var * kTcCols + pc + fo.chan], fo.ipow, fo.pow);
+              part_ *= pow_i((sbase + kOffU)[fo.var * kTcCols + pc + fo.chan], fo.ipow, fo.pow);
             }
-            sm.guS[fc.var * kTcCols + pc + fc.chan] += part_;
+            (sbase + kOffGu)[fc.var * kTcCols + pc + fc.chan] += part_;
             full *= pow_i(x, fc.ipow, fc.pow);
           }
-          if (tm.kind == 2) atomicAdd(&sm.cgS[tm.idx], seed * full);
+          if (tm.kind == 2) atomicAdd(&(sbase + kOffCg)[tm.idx], seed * full);
         }
+        TMARK(13);
       }
     }
+    TMARK(14);
     __syncthreads();
     if (!a.do_grad) continue;
 
@@ -622,7 +628,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
     // ---- backward of the last layer: dWl, dbl accumulators; gY of the last tanh layer ----------------------
     if (tid < n_out) {
       float s = 0.f;
-      for (int p = 0; p < P; ++p) s += sm.guS[tid * kTcCols + (p / PH) * kTcPC + (p % PH) * J];
+      for (int p = 0; p < P; ++p) s += (sbase + kOffGu)[tid * kTcCols + (p / PH) * kTcPC + (p % PH) * J];
       dbl_acc += s;
     }
     float gy[16];
@@ -632,7 +638,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       float s = 0.f;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 g4 = *reinterpret_cast<const float4*>(sm.guS + v * kTcCols + col0 + 4 * q);
+        const float4 g4 = *reinterpret_cast<const float4*>((sbase + kOffGu) + v * kTcCols + col0 + 4 * q);
         const float g[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -664,10 +670,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
             for (int k = 0; k < ORD[i]; ++k) zz[k] = zd[t > 0 ? t - 1 : 0][p][c - 1 + k];
           }
           g0 += tanh_jet_bwd(f, zz, gy + p * J + c, ORD[i], gg);
-          if (t == 0) {
-#pragma unroll
-            for (int ax = 0; ax < 4; ++ax) if (ax == dir_axis[i]) dw0_acc[ax] += gg[0];
-          }
+          if (t == 0) dw0_dir[i] += gg[0];
 #pragma unroll
           for (int k = 0; k < ORD[i]; ++k) gz[p * J + c + k] = gg[k];
           c += ORD[i];
@@ -675,8 +678,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
         gz[p * J] = g0;
         db += g0;
         if (t == 0) {
-#pragma unroll
-          for (int ax = 0; ax < 4; ++ax) if (ax < d) dw0_acc[ax] = fmaf(g0, xcur[(part * PH + p) * 4 + ax], dw0_acc[ax]);
+          const float4 x4 = *reinterpret_cast<const float4*>(xcur + (part * PH + p) * 4);
+          dw0_acc[0] = fmaf(g0, x4.x, dw0_acc[0]); dw0_acc[1] = fmaf(g0, x4.y, dw0_acc[1]);
+          dw0_acc[2] = fmaf(g0, x4.z, dw0_acc[2]); dw0_acc[3] = fmaf(g0, x4.w, dw0_acc[3]);
         }
       }
       db_acc[t] += db;
@@ -696,15 +700,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
         }
         split16(gz, hi, lo);
         if (live) {
-          st4(sm.act_hi + actA, hi); st4(sm.act_hi + actA + 4, hi + 4); st4(sm.act_hi + actB, hi + 8); st4(sm.act_hi + actB + 4, hi + 12);
-          st4(sm.act_lo + actA, lo); st4(sm.act_lo + actA + 4, lo + 4); st4(sm.act_lo + actB, lo + 8); st4(sm.act_lo + actB + 4, lo + 12);
+          st4((sbase + kOffActHi) + actA, hi); st4((sbase + kOffActHi) + actA + 4, hi + 4); st4((sbase + kOffActHi) + actB, hi + 8); st4((sbase + kOffActHi) + actB + 4, hi + 12);
+          st4((sbase + kOffActLo) + actA, lo); st4((sbase + kOffActLo) + actA + 4, lo + 4); st4((sbase + kOffActLo) + actB, lo + 8); st4((sbase + kOffActLo) + actB + 4, lo + 12);
         }
         tmem_st16(t_lane + kTmAHi + (uint32_t)col0, hi);
         tmem_st16(t_lane + kTmALo + (uint32_t)col0, lo);
         if (live) {
           split16(yp, hi, lo);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) { st4(sm.yw_hi + ywq[q], hi + 4 * q); st4(sm.yw_lo + ywq[q], lo + 4 * q); }
+          for (int q = 0; q < 4; ++q) { st4((sbase + kOffYwHi) + ywq[q], hi + 4 * q); st4((sbase + kOffYwLo) + ywq[q], lo + 4 * q); }
         }
         tmem_st_wait();
       }
@@ -715,11 +719,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       if (warp == 0) {
         mbar_wait(sm.wbar, wphase); wphase ^= 1;        // W_t^T image has landed
         tc_fence_after();
-        issue_gemm_any(tmem + kTmD, sm.w_hi, sm.w_lo, sm.act_hi, sm.act_lo, ksteps);   // A = W_t^T image
+        issue_gemm_any(tmem + kTmD, (sbase + kOffWHi), (sbase + kOffWLo), (sbase + kOffActHi), (sbase + kOffActLo), ksteps);   // A = W_t^T image
         if (elect_one()) umma_commit(sm.bar);
         __syncwarp();
         // the weight gradient is not on the critical path: it runs behind the next adjoint epilogue
-        issue_wgrad(tmem + kTmDw + (uint32_t)(t - 1) * kTmDwCols, tmem + kTmAHi, tmem + kTmALo, sm.yw_hi, sm.yw_lo, dw_started);
+        issue_wgrad(tmem + kTmDw + (uint32_t)(t - 1) * kTmDwCols, tmem + kTmAHi, tmem + kTmALo, (sbase + kOffYwHi), (sbase + kOffYwLo), dw_started);
         if (elect_one()) umma_commit(sm.gbar);
         __syncwarp();
         TMARK(8);
@@ -731,14 +735,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       TMARK(9);
       if (tid == 0) {                                   // next image: W_{t-1}^T, or W_1 for the next tile
         const float* nxt = t > 1 ? wimg + (size_t)(t - 2) * 4 * kTcWFloats + 2 * kTcWFloats : wimg;
-        bulk_load_image(sm.w_hi, nxt, sm.wbar);
+        bulk_load_image((sbase + kOffWHi), nxt, sm.wbar);
       }
     }
     dw_started = 1;
     TMARK(10);
   }
+#ifdef TDB_TC_TIMING
   if (a.dbg && tid == 0)
     for (int i = 0; i < 16; ++i) a.dbg[(size_t)blockIdx.x * 16 + i] = tacc[i];
+#endif
 
   // ---- flush: per-thread accumulators, dW accumulators (TMEM), per-CTA scalars --------------------------
   if (warp == 0) { mbar_wait(sm.wbar, wphase); wphase ^= 1; }   // drain the last prefetch before exiting
@@ -749,6 +755,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
     if (live) {
 #pragma unroll
       for (int l = 0; l <= NMMA; ++l) my_grad[a.b_off[l] + n] = db_acc[l];
+      for (int i = 0; i < ND; ++i)                         // derivative-channel part of dW0, by jet direction
+        for (int ax = 0; ax < 4; ++ax) if (ax == dir_axis[i]) dw0_acc[ax] += dw0_dir[i];
       for (int ax = 0; ax < d; ++ax) my_grad[a.w_off[0] + n * d + ax] = dw0_acc[ax];
 #pragma unroll
       for (int v = 0; v < kTcMaxOut; ++v) if (v < n_out) my_grad[a.w_off[L - 1] + v * W + n] = dwl_acc[v];
@@ -775,7 +783,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
         for (int p = 0; p < P; ++p) s += sm.lossT[p * TDB200_MAX_COLS + col];
     a.part_loss[(size_t)blockIdx.x * a.n_slots + tid] = s;
   }
-  if (a.do_grad && tid < a.n_cparams) my_grad[a.n_net_params + tid] = sm.cgS[tid];   // warp 0 -> part-0 row
+  if (a.do_grad && tid < a.n_cparams) my_grad[a.n_net_params + tid] = (sbase + kOffCg)[tid];   // warp 0 -> part-0 row
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");

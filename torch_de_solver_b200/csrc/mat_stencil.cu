@@ -587,7 +587,8 @@ __global__ void __launch_bounds__(kCtThreads, 2) mat_cross_tma_kernel(const MatA
   constexpr int N2 = (RY * kCxQR + kCtThreads - 1) / kCtThreads;
   constexpr uint32_t kTxBytes = (uint32_t)((UY * kCxPU + RY * kCxPR) * sizeof(float));
   extern __shared__ uint8_t sm_ct_raw[];
-  float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sm_ct_raw) + 127) & ~uintptr_t(127));
+  const uint32_t s0_ = ct_smem_u32(sm_ct_raw);                 // align with pointer arithmetic on the __shared__ symbol:
+  float* base = reinterpret_cast<float*>(sm_ct_raw + (((s0_ + 127u) & ~127u) - s0_));   // keeps LDS / STS addressing
   float* ss = base + 2 * ct_stage_floats<HY, HX>();          // seeds [RY][PR]
   uint64_t* bars = reinterpret_cast<uint64_t*>(ss + ct_round32((size_t)RY * kCxPR));
   __shared__ double red[kCtThreads / 32];
