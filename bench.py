@@ -171,7 +171,7 @@ def run_b200(args):
     torch.set_default_device(dev)
 
     if WORKLOADS[args.workload].get('mat'):
-        return run_b200_mat(args, dev, tdb, problems)
+        return run_b200_mat(args, dev, tdb, problems, rank, world)
     spec, prob = make_problem(args.workload, tdb, world)
     net = problems.make_net(prob.net_layers, torch.float32, prob.init).to(dev)
     model = tdb.Model(net, prob.domain, prob.equation, prob.conditions)
@@ -289,16 +289,27 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def run_b200_mat(args, dev, tdb, problems):
-    """mat-mode workload (1 GPU): HBM-bound stencil kernel."""
+def run_b200_mat(args, dev, tdb, problems, rank=0, world=1):
+    """mat-mode workload: HBM-bound stencil kernel.  Several GPUs: slab decomposition along axis 0, weak scaling
+    (4096 rows per rank), 4 halo rows of u from each neighbour + one all-reduce of the loss terms per step."""
+    import torch.distributed as dist
+    from torch_de_solver_b200.mat import slab_rows
     spec = WORKLOADS[args.workload]
-    prob = getattr(problems, spec['fn'])(tdb, 'float32', **spec['kw'])
-    u = problems.make_mat_model(prob.mat_shape, torch.float32).to(dev).contiguous()
+    kw = dict(spec['kw'])
+    n1 = kw['n'] + 1
+    if world > 1:
+        kw['ny'] = kw['n']
+        kw['n'] = (kw['n'] + 1) * world - 1
+    prob = getattr(problems, spec['fn'])(tdb, 'float32', **kw)
+    n0 = kw['n'] + 1
+    r0, r1 = slab_rows(n0, rank, world)
+    u = problems.make_mat_model((prob.mat_shape[0], r1 - r0, n1), torch.float32, seed=rank).to(dev).contiguous()
     model = tdb.Model(u, prob.domain, prob.equation, prob.conditions)
-    model.compile('mat', **prob.compile_kwargs)
+    model.compile('mat', **prob.compile_kwargs, shard=(rank, world) if world > 1 else None)
     sol = model.solution_cls
     plan = sol._plan
-    n_cells = plan.n_cells
+    n_cells = plan.n_cells                         # global
+    n_local = plan.n_cells_local
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
     def timed(fn, steps):
@@ -309,16 +320,30 @@ def run_b200_mat(args, dev, tdb, problems):
         torch.cuda.synchronize(dev)
         return [e0.elapsed_time(e1) for e0, e1 in ev]
 
+    def reduce_max(ms_total):
+        if world > 1:
+            t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t)
+        return ms_total
+
     step = lambda: plan.loss_grad_raw(u)
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
     sampler = ClockSampler(dev.index or 0)
     sampler.start()
     t_wall = time.time()
     times = timed(step, args.steps)
+    if world > 1:
+        dist.barrier()
     clocks = sampler.stop()
-    ms = statistics.mean(times)
+    ms = reduce_max(sum(times)) / args.steps
+    # kernel-only time of the stencil kernel on this rank (roofline): the same launch without the exchange
+    ue = u if world == 1 else torch.zeros(plan.ir.shape_ext, dtype=torch.float32, device=dev)
+    kt = statistics.mean(timed(lambda: plan.loss_grad_ext(ue), max(5, min(args.steps, 20))))
     # e2e: forcing tensor + boundary targets from pinned host memory every step, loss terms read back
     host_in = [plan._coeffs.detach().cpu().pin_memory(), plan._targets.detach().cpu().pin_memory()]
     dev_in = [plan._coeffs, plan._targets]
@@ -335,29 +360,42 @@ def run_b200_mat(args, dev, tdb, problems):
     for _ in range(3):
         step_e2e()
     torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
     e2e_steps = max(3, min(args.steps, 20))
-    e2e_ms = statistics.mean(timed(step_e2e, e2e_steps))
+    e2e_ms = reduce_max(sum(timed(step_e2e, e2e_steps))) / e2e_steps
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
     peaks, peak_src = load_peaks()
-    achieved = n_cells * MAT_BYTES_PER_CELL / (ms * 1e-3) / 1e9
+    achieved = n_local * MAT_BYTES_PER_CELL / (kt * 1e-3) / 1e9
     torch.set_default_device('cpu')
-    cpu = cpu_baseline(args.workload) if not args.no_cpu_baseline else None
+    cpu = cpu_baseline(args.workload) if (not args.no_cpu_baseline and world == 1) else None
     line = {
-        'metric': METRIC, 'value': n_cells / (ms * 1e-3), 'unit': UNIT, 'n_gpus': 1, 'steps': args.steps,
+        'metric': METRIC, 'value': n_cells / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': args.workload, 'description': spec['desc'], 'cells': n_cells, 'mode': 'mat',
-                   'l2': 'flushed between timed steps (256 MB write)', 'parallelism': 'single GPU'},
+        'config': {'workload': args.workload, 'description': spec['desc'], 'cells': n_cells, 'cells_per_gpu': n_local,
+                   'mode': 'mat', 'kernel': plan.kernel_kind,
+                   'l2': 'flushed between timed steps (256 MB write)',
+                   'parallelism': 'single GPU' if world == 1 else
+                                  f'{world} row slabs, {plan.ir.halo}-row halo exchange + all-reduce of the loss terms'},
         'e2e': {'value': n_cells / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': sum(t.numel() * 4 for t in host_in),
                 'd2h_bytes_per_step': host_out.numel() * 4, 'ms_per_step': e2e_ms},
         'gpu_launches': args.steps * plan.launches_per_call,
         'clocks': clocks,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                      'frac': achieved / peaks['hbm_gbs'], 'traffic': None,
-                     'bytes_per_cell': MAT_BYTES_PER_CELL, 'peak_source': f'MEASURED_PEAKS.json [{peak_src}] hbm_gbs'},
+                     'bytes_per_cell': MAT_BYTES_PER_CELL, 'kernel_ms': kt,
+                     'peak_source': f'MEASURED_PEAKS.json [{peak_src}] hbm_gbs; achieved = cells per GPU * 12 B / '
+                                    f'time of the two launches of one step (stencil + boundary/finalize) on rank 0'},
         'cpu_baseline': cpu,
         'wall_s': time.time() - t_wall,
     }
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -161,6 +161,11 @@ int tdb200_mat_plan_set_bcs(tdb200_mat_plan* plan, int32_t n_bcs, const tdb200_m
                             const int32_t* cells_dev, const float* targets_dev, int32_t n_slots,
                             const double* slot_lambda, const double* slot_len);
 
+/* Slab decomposition over several GPUs: the plan is built on this rank's rows plus 2 * reach halo rows
+ * on each interior side; only rows [row_lo, row_hi) of that extended slab enter the loss (slot_len is the global
+ * count, so the per-rank outputs add up), gradients of the halo rows are not meaningful.  Default: all rows. */
+int tdb200_mat_plan_set_row_window(tdb200_mat_plan* plan, int32_t row_lo, int32_t row_hi);
+
 /* out_dev[0] = loss, [1] = loss_normalized, [2 + s] = slot mean squares (n_eq + n_bc_slots);
  * grad_dev [n_var, n0, n1] = d loss / d u. */
 int tdb200_mat_loss_grad(tdb200_mat_plan* plan, const float* u_dev, float* grad_dev, float* out_dev,

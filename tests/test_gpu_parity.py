@@ -260,6 +260,41 @@ def test_mat_specialised_kernels_agree(case, cuda_default, monkeypatch):
         assert np.abs(grad - ref_grad).max() <= 2e-4 * np.abs(ref_grad).max(), tag
 
 
+@pytest.mark.parametrize('case,world', [('poisson_p2_200x260', 2), ('poisson_p2_200x260', 3), ('heat_p2_96x128', 2),
+                                        ('poisson_p3_72x136', 2)])
+def test_mat_slab_plans_add_up(case, world, cuda_default):
+    """Slab decomposition on one GPU: the plans of ranks 0..world-1 (extended slabs, loss window, boundary rows of the
+    owned block) evaluated one after the other give partial loss terms that add up to, and gradient slabs that
+    concatenate to, the single-plan result.  (The halo exchange itself is covered by the gloo test on the CPU.)"""
+    kind, p, shape = case.split('_')
+    n0, n1 = (int(x) for x in shape.split('x'))
+    dp = int(p[1])
+    if kind == 'poisson':
+        prob = problems.poisson_mat(tdb, 'float32', n=n0 - 1, ny=n1 - 1, derivative_points=dp)
+    else:
+        prob = problems.heat_mat(tdb, 'float32', n=n0 - 1, nt=n1 - 1, derivative_points=dp)
+    u = torch.as_tensor(np.random.default_rng(5).random(prob.mat_shape, dtype=np.float32)).to('cuda:0').contiguous()
+    model = tdb.Model(u.clone(), prob.domain, prob.equation, prob.conditions)
+    model.compile('mat', **prob.compile_kwargs)
+    ref_out, ref_grad = model.solution_cls._plan.loss_grad_raw(u)
+    outs, grads = [], []
+    for rank in range(world):
+        from torch_de_solver_b200.mat import slab_rows
+        r0, r1 = slab_rows(n0, rank, world)
+        m = tdb.Model(u[:, r0:r1].contiguous(), prob.domain, prob.equation, prob.conditions)
+        m.compile('mat', **prob.compile_kwargs, shard=(rank, world))
+        plan = m.solution_cls._plan
+        e0, e1 = plan.ir.ext
+        out, grad = plan.loss_grad_ext(u[:, e0:e1].contiguous())
+        assert tuple(grad.shape) == (1, r1 - r0, n1)
+        outs.append(out.double())
+        grads.append(grad)
+    out = torch.stack(outs).sum(0)
+    np.testing.assert_allclose(out.cpu().numpy(), ref_out.double().cpu().numpy(), rtol=2e-5)
+    grad = torch.cat(grads, 1)
+    assert float((grad - ref_grad).abs().max()) <= 2e-4 * float(ref_grad.abs().max())
+
+
 def test_repeatable_and_param_update(cuda_default):
     """Two calls give bit-identical results (fixed reduction order); weights are re-read every call."""
     g = load_golden('burgers_NN_small', 'float64')

@@ -253,21 +253,24 @@ __device__ __forceinline__ void issue_gemm_any(uint32_t d_tmem, const float* w_h
   else if (ksteps <= 8) issue_gemm<8>(d_tmem, w_hi, w_lo, b_hi, b_lo);
   else issue_gemm<13>(d_tmem, w_hi, w_lo, b_hi, b_lo);
 }
-// dW[128 (n) x 112 (k)] += A(gZ in TMEM: lanes n, columns (pc)) . B(Y image [k rows][64 columns], K-major SW128)
-__device__ __forceinline__ void issue_wgrad(uint32_t d_tmem, uint32_t a_hi_tmem, uint32_t a_lo_tmem,
-                                            const float* y_hi, const float* y_lo, uint32_t accumulate) {
+// dW[128 (n) x 112 (k)] += A(gZ in TMEM: lanes n, columns (pc)) . B(Y image [k rows][64 columns], K-major SW128):
+// MMAs [I0, I1) of the 24 of one weight-gradient GEMM (index = pass * 8 + K-step).  The issue of a tcgen05.mma
+// blocks while the (short) MMA queue is full, so the issuing warp feeds the 24 MMAs in small portions between the
+// pieces of its own epilogue instead of falling ~1400 cycles behind the other warps.
+template <int I0, int I1>
+__device__ __forceinline__ void issue_wgrad_range(uint32_t d_tmem, uint32_t a_hi_tmem, uint32_t a_lo_tmem,
+                                                  const float* y_hi, const float* y_lo, uint32_t accumulate) {
+  if (I0 >= I1) return;
   constexpr uint32_t idesc = umma_idesc(128, 112, 0, 0);
   const uint64_t dyh = umma_desc(smem_u32(y_hi), 16, 1024), dyl = umma_desc(smem_u32(y_lo), 16, 1024);
   const bool leader = elect_one();
 #pragma unroll
-  for (int pass = 0; pass < 3; ++pass) {
+  for (int i = I0; i < I1; ++i) {
+    const int pass = i >> 3, s = i & 7;
     const uint32_t A = pass == 0 ? a_lo_tmem : a_hi_tmem;
     const uint64_t B = pass == 1 ? dyl : dyh;
-#pragma unroll
-    for (int s = 0; s < kTcCols / 8; ++s) {
-      const uint64_t bo = ((uint64_t)(s >> 2) * kTcYwBlock * 4 + (uint64_t)(s & 3) * 32) >> 4;
-      if (leader) umma_tf32_ts(d_tmem, A + (uint32_t)s * 8, B + bo, idesc, (pass | s) ? 1u : accumulate);
-    }
+    const uint64_t bo = ((uint64_t)(s >> 2) * kTcYwBlock * 4 + (uint64_t)(s & 3) * 32) >> 4;
+    if (leader) umma_tf32_ts(d_tmem, A + (uint32_t)s * 8, B + bo, idesc, i ? 1u : accumulate);
   }
 }
 
@@ -329,6 +332,8 @@ struct TcSmem {
   tdb200_segment* segS;
   float* scaleS;          // [32] lambda / len per slot
   double* lossT;          // [kTcMaxPts][TDB200_MAX_COLS] per-point-thread loss accumulators (no atomics)
+  int4* recS;             // [kTcMaxTerms] pre-decoded terms (<= 2 live factors, integer powers <= 3), see below
+  int* fastS;             // 1: every term of the segment has a record
   uint64_t *bar, *wbar, *gbar;
   uint32_t* tmem_ptr;
 };
@@ -336,7 +341,7 @@ constexpr size_t kTcSmemBytes =
     (size_t)(2 * kTcWFloats + 2 * kTcActFloats + 2 * kTcYwFloats) * 4 + 1024 /*align*/ +
     (2 * kTcMaxPts * 4 + 2 * kTcMaxOut * kTcCols + 4 * kTcMaxOut * kTcCols + kMaxCParams) * 4 + 64 + 64 +
     kTcMaxTerms * sizeof(tdb200_term) + kTcMaxFactors * sizeof(tdb200_factor) + 16 + sizeof(tdb200_segment) + 32 * 4 +
-    kTcMaxPts * TDB200_MAX_COLS * 8 + 64;
+    kTcMaxPts * TDB200_MAX_COLS * 8 + 64 + kTcMaxTerms * 16 + 16;
 
 size_t jet_tc_smem_bytes() { return kTcSmemBytes; }
 
@@ -367,7 +372,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
     sm.facS = reinterpret_cast<tdb200_factor*>(q); q += (kTcMaxFactors * sizeof(tdb200_factor) + 15) / 16 * 16;
     sm.segS = reinterpret_cast<tdb200_segment*>(q); q += (sizeof(tdb200_segment) + 15) / 16 * 16;
     sm.scaleS = reinterpret_cast<float*>(q); q += 32 * 4;
-    sm.lossT = reinterpret_cast<double*>(q);
+    sm.lossT = reinterpret_cast<double*>(q); q += kTcMaxPts * TDB200_MAX_COLS * 8;
+    sm.recS = reinterpret_cast<int4*>(q); q += kTcMaxTerms * 16;
+    sm.fastS = reinterpret_cast<int*>(q);
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = (warp & 3) * 32 + lane;                 // neuron = TMEM lane owned by this thread
@@ -407,6 +414,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *sm.tmem_ptr;
+  // pre-decode the operator program: term -> {coeff bits | buffer index, kind, u offsets of <= 2 live factors, powers}
+  if (tid == 0) *sm.fastS = 1;
+  __syncthreads();
+  if (tid < min(kTcMaxTerms, a.n_terms) && tid < sm.segS->col_term_end[sm.segS->n_cols - 1]) {
+    const tdb200_term tm = sm.termS[tid];
+    int off[2] = {0xFFFF, 0xFFFF}, ipw[2] = {0, 0}, nf = 0;
+    bool ok = tm.kind == 0 || (tm.idx >= 0 && tm.idx < 0x7fffffffLL);
+    for (int fi = tm.fac_begin; fi < tm.fac_end; ++fi) {
+      const tdb200_factor fc = sm.facS[fi];
+      if (fc.ipow == 0) continue;                       // x^0: contributes 1 and no derivative
+      if (fc.ipow < 0 || fc.ipow > 3 || nf == 2) { ok = false; break; }
+      off[nf] = fc.var * kTcCols + fc.chan;
+      ipw[nf] = fc.ipow;
+      ++nf;
+    }
+    if (ok) sm.recS[tid] = make_int4(tm.kind == 0 ? __float_as_int(tm.coeff) : (int)tm.idx, tm.kind, off[0] | (off[1] << 16),
+                                     ipw[0] | (ipw[1] << 8));
+    else *sm.fastS = 0;
+  }
+  __syncthreads();
+  const bool fast_op = *sm.fastS != 0;
   const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);    // this warp's lane window
 #ifdef TDB_TC_TIMING
   long long tacc[16];
@@ -573,7 +601,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
 
     TMARK(5);
     // ---- operator terms, residual, loss, adjoint seeds (one thread per point) -------------------------
-    if (tid < p_valid) {
+    if (tid < p_valid && fast_op) {
+      // pre-decoded terms: no factor loops, powers by selection
+      const int p = tid;
+      const int pc = (p / PH) * kTcPC + (p % PH) * J;   // first column of this point
+      const long long row = g_first + p;
+      const float* u = (sbase + kOffU) + pc;
+      float* gu = (sbase + kOffGu) + pc;
+      auto pw = [](float x, int i) { const float x2 = x * x; return i == 1 ? x : i == 2 ? x2 : i == 3 ? x2 * x : 1.f; };
+      auto dpw = [](float x, int i) { return i == 1 ? 1.f : i == 2 ? 2.f * x : i == 3 ? 3.f * x * x : 0.f; };
+      for (int col = 0; col < ncols; ++col) {
+        const int tb = sg.col_term_begin[col], te = sg.col_term_end[col];
+        float val = 0.f;
+        for (int t = tb; t < te; ++t) {
+          const int4 r = sm.recS[t];
+          const float cf = r.y == 0 ? __int_as_float(r.x) : r.y == 1 ? __ldg(a.coeffs + r.x + row) : a.arena[a.n_net_params + r.x];
+          const int o0 = r.z & 0xFFFF, o1 = (r.z >> 16) & 0xFFFF;
+          const float x0 = o0 != 0xFFFF ? u[o0] : 1.f, x1 = o1 != 0xFFFF ? u[o1] : 1.f;
+          val = fmaf(cf * pw(x0, r.w & 255), pw(x1, r.w >> 8), val);
+        }
+        if (a.fields) a.fields[sg.field_off + row * ncols + col] = val;
+        const float tgt = sg.tgt_off >= 0 ? __ldg(a.targets + sg.tgt_off + row * ncols + col) : 0.f;
+        const float res = val - tgt;
+        sm.lossT[p * TDB200_MAX_COLS + col] += (double)res * (double)res;
+        if (!a.do_grad) continue;
+        const float seed = 2.f * sm.scaleS[sg.col_slot[col]] * res;
+        for (int t = tb; t < te; ++t) {
+          const int4 r = sm.recS[t];
+          const float cf = r.y == 0 ? __int_as_float(r.x) : r.y == 1 ? __ldg(a.coeffs + r.x + row) : a.arena[a.n_net_params + r.x];
+          const int o0 = r.z & 0xFFFF, o1 = (r.z >> 16) & 0xFFFF;
+          const float x0 = o0 != 0xFFFF ? u[o0] : 1.f, x1 = o1 != 0xFFFF ? u[o1] : 1.f;
+          const float p0 = pw(x0, r.w & 255), p1 = pw(x1, r.w >> 8), sc = seed * cf;
+          if (o0 != 0xFFFF) gu[o0] += sc * dpw(x0, r.w & 255) * p1;
+          if (o1 != 0xFFFF) gu[o1] += sc * p0 * dpw(x1, r.w >> 8);
+          if (r.y == 2) atomicAdd(&(sbase + kOffCg)[r.x], seed * p0 * p1);
+        }
+      }
+    } else     if (tid < p_valid) {
       const int p = tid;
       const int pc = (p / PH) * kTcPC + (p % PH) * J;   // first column of this point
       const long long row = g_first + p;
@@ -651,13 +715,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
     }
 
     // ---- backward sweep over the tanh layers t = NMMA .. 0 ------------------------------------------
+    // The weight-gradient GEMM of layer t + 1 is issued by warp 0 in 2 PH portions during the epilogue of layer t.
 #pragma unroll
     for (int t = NMMA; t >= 0; --t) {
       if (t < NMMA) tmem_ld16(t_lane + kTmD + (uint32_t)col0, gy);
+      const uint32_t wg_d = tmem + kTmDw + (uint32_t)t * kTmDwCols;       // dW slot of layer t + 1
       float gz[16];
       float db = 0.f;
 #pragma unroll
       for (int p = 0; p < PH; ++p) {
+        if (t < NMMA && warp == 0) {
+          if (p == 0) issue_wgrad_range<0, 24 * 1 / (2 * PH)>(wg_d, tmem + kTmAHi, tmem + kTmALo, sbase + kOffYwHi, sbase + kOffYwLo, dw_started);
+          if (p == 1) issue_wgrad_range<24 * 2 / (2 * PH), 24 * 3 / (2 * PH)>(wg_d, tmem + kTmAHi, tmem + kTmALo, sbase + kOffYwHi, sbase + kOffYwLo, dw_started);
+          if (p == 2) issue_wgrad_range<24 * 4 / (2 * PH), 24 * 5 / (2 * PH)>(wg_d, tmem + kTmAHi, tmem + kTmALo, sbase + kOffYwHi, sbase + kOffYwLo, dw_started);
+          if (p == 3) issue_wgrad_range<24 * 6 / (2 * PH), 24 * 7 / (2 * PH)>(wg_d, tmem + kTmAHi, tmem + kTmALo, sbase + kOffYwHi, sbase + kOffYwLo, dw_started);
+          if (p == 4) issue_wgrad_range<24 * 8 / (2 * PH), 24 * 9 / (2 * PH)>(wg_d, tmem + kTmAHi, tmem + kTmALo, sbase + kOffYwHi, sbase + kOffYwLo, dw_started);
+          if (p == 5) issue_wgrad_range<24 * 10 / (2 * PH), 24 * 11 / (2 * PH)>(wg_d, tmem + kTmAHi, tmem + kTmALo, sbase + kOffYwHi, sbase + kOffYwLo, dw_started);
+          if (p == 6) issue_wgrad_range<24 * 12 / (2 * PH), 24 * 13 / (2 * PH)>(wg_d, tmem + kTmAHi, tmem + kTmALo, sbase + kOffYwHi, sbase + kOffYwLo, dw_started);
+          if (p == 7) issue_wgrad_range<24 * 14 / (2 * PH), 24 * 15 / (2 * PH)>(wg_d, tmem + kTmAHi, tmem + kTmALo, sbase + kOffYwHi, sbase + kOffYwLo, dw_started);
+        }
         const TanhF f(as[t][p]);
         float g0 = gy[p * J] * f.f1;
         int c = 1;
@@ -682,6 +758,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
           dw0_acc[0] = fmaf(g0, x4.x, dw0_acc[0]); dw0_acc[1] = fmaf(g0, x4.y, dw0_acc[1]);
           dw0_acc[2] = fmaf(g0, x4.z, dw0_acc[2]); dw0_acc[3] = fmaf(g0, x4.w, dw0_acc[3]);
         }
+        if (t < NMMA && warp == 0) {
+          if (p == 0) issue_wgrad_range<24 * 1 / (2 * PH), 24 * 2 / (2 * PH)>(wg_d, tmem + kTmAHi, tmem + kTmALo, sbase + kOffYwHi, sbase + kOffYwLo, dw_started);
+          if (p == 1) issue_wgrad_range<24 * 3 / (2 * PH), 24 * 4 / (2 * PH)>(wg_d, tmem + kTmAHi, tmem + kTmALo, sbase + kOffYwHi, sbase + kOffYwLo, dw_started);
+          if (p == 2) issue_wgrad_range<24 * 5 / (2 * PH), 24 * 6 / (2 * PH)>(wg_d, tmem + kTmAHi, tmem + kTmALo, sbase + kOffYwHi, sbase + kOffYwLo, dw_started);
+          if (p == 3) issue_wgrad_range<24 * 7 / (2 * PH), 24 * 8 / (2 * PH)>(wg_d, tmem + kTmAHi, tmem + kTmALo, sbase + kOffYwHi, sbase + kOffYwLo, dw_started);
+          if (p == 4) issue_wgrad_range<24 * 9 / (2 * PH), 24 * 10 / (2 * PH)>(wg_d, tmem + kTmAHi, tmem + kTmALo, sbase + kOffYwHi, sbase + kOffYwLo, dw_started);
+          if (p == 5) issue_wgrad_range<24 * 11 / (2 * PH), 24 * 12 / (2 * PH)>(wg_d, tmem + kTmAHi, tmem + kTmALo, sbase + kOffYwHi, sbase + kOffYwLo, dw_started);
+          if (p == 6) issue_wgrad_range<24 * 13 / (2 * PH), 24 * 14 / (2 * PH)>(wg_d, tmem + kTmAHi, tmem + kTmALo, sbase + kOffYwHi, sbase + kOffYwLo, dw_started);
+          if (p == 7) issue_wgrad_range<24 * 15 / (2 * PH), 24 * 16 / (2 * PH)>(wg_d, tmem + kTmAHi, tmem + kTmALo, sbase + kOffYwHi, sbase + kOffYwLo, dw_started);
+        }
+      }
+      if (t < NMMA) {
+        if (warp == 0) {
+          if (PH > 8) issue_wgrad_range<24 * 16 / (2 * PH), 24>(wg_d, tmem + kTmAHi, tmem + kTmALo, sbase + kOffYwHi, sbase + kOffYwLo, dw_started);
+          if (elect_one()) umma_commit(sm.gbar);
+          __syncwarp();
+        }
+        wgrad_pending = true;
       }
       db_acc[t] += db;
       if (t == 0) break;
@@ -722,13 +816,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
         issue_gemm_any(tmem + kTmD, (sbase + kOffWHi), (sbase + kOffWLo), (sbase + kOffActHi), (sbase + kOffActLo), ksteps);   // A = W_t^T image
         if (elect_one()) umma_commit(sm.bar);
         __syncwarp();
-        // the weight gradient is not on the critical path: it runs behind the next adjoint epilogue
-        issue_wgrad(tmem + kTmDw + (uint32_t)(t - 1) * kTmDwCols, tmem + kTmAHi, tmem + kTmALo, (sbase + kOffYwHi), (sbase + kOffYwLo), dw_started);
-        if (elect_one()) umma_commit(sm.gbar);
-        __syncwarp();
         TMARK(8);
       }
-      wgrad_pending = true;
       mbar_wait(sm.bar, phase);
       phase ^= 1;
       tc_fence_after();

@@ -54,6 +54,8 @@ struct MatArgs {
   const float* l1_fbuf[2];                 // lin1: up to two forcing buffers (absolute pointers, set per call)
   float cx_wy[9], cx_wx[9], cx_wc;         // cross kernel: weights by offset (index offset + reach), merged centre
   unsigned int* tile_ctr;                  // persistent kernel: dynamic tile counter (zero on entry)
+  int row_lo, row_hi;                      // rows whose residuals enter the loss (slab decomposition: the owned rows of
+                                           // an extended slab; seeds are still formed on the halo rows around them)
   int frc_begin[TDB200_MAX_COLS + 1];      // forcing terms of equation e
   float frc_const[kMatMaxForcing];
   long long frc_buf[kMatMaxForcing];       // coefficient buffer offset, -1: constant only
@@ -171,7 +173,7 @@ __device__ __forceinline__ float mat_lin1_tile(const MatArgs& a, float* __restri
               for (int t = 0; t < a.n_lin; ++t)
                 res = fmaf(a.lin_c[t], field_value(a, a.fld[a.lin_q[t]], us, kL1PU, 0, ly + hy, lx + hx, gy, gx), res);
             }
-            if (ly >= hy && ly < hy + kL1TY && lx >= hx && lx < hx + kL1TX) lacc = fmaf(res, res, lacc);
+            if (ly >= hy && ly < hy + kL1TY && lx >= hx && lx < hx + kL1TX && gy >= a.row_lo && gy < a.row_hi) lacc = fmaf(res, res, lacc);
             seed = scale2 * res;
           }
           ss[ly * kL1PR + lx] = seed;
@@ -331,7 +333,7 @@ __device__ __forceinline__ void cx_fix_seeds(const MatArgs& a, const float* __re
     if (f1) res += __ldg(f1 + cell);
     for (int t = 0; t < a.n_lin; ++t)
       res = fmaf(a.lin_c[t], field_value(a, a.fld[a.lin_q[t]], us, kCxPU, 0, ly + HY, lx + 4, gy, gx), res);
-    if (ly >= HY && ly < HY + kCxTY && lx >= 4 && lx < 4 + kCxTX) lacc = fmaf(res, res, lacc);
+    if (ly >= HY && ly < HY + kCxTY && lx >= 4 && lx < 4 + kCxTX && gy >= a.row_lo && gy < a.row_hi) lacc = fmaf(res, res, lacc);
     ss[ly * kCxPR + lx] = scale2 * res;
   };
   for (int ly = warp; ly < RY; ly += (int)(blockDim.x >> 5)) {
@@ -445,7 +447,8 @@ __device__ __forceinline__ float mat_cross_tile(const MatArgs& a, float* __restr
       const int ly = idx / kCxQR, q = idx - ly * kCxQR;
       float r[4] = {fv[k].x + fc0, fv[k].y + fc0, fv[k].z + fc0, fv[k].w + fc0};
       cx_apply<HY, HX, MY, MX, false, kCxPU>(us + (ly + HY) * kCxPU + 4 * q + 4, wy, wx, wc, r);
-      const bool core = ly >= HY && ly < HY + kCxTY && q >= 1 && q <= kCxTX / 4;
+      const bool core = ly >= HY && ly < HY + kCxTY && q >= 1 && q <= kCxTX / 4 && ty0 - HY + ly >= a.row_lo &&
+                        ty0 - HY + ly < a.row_hi;
       float sd[4];
       if (INTERIOR) {
 #pragma unroll
@@ -650,6 +653,8 @@ __global__ void __launch_bounds__(kCtThreads, 2) mat_cross_tma_kernel(const MatA
     const float* fs = us + ct_u_floats<HY, HX>();
     const int ty0 = ti.y, tx0 = ti.z;
     const bool interior = ti.w != 0;
+    const bool rows_in = ty0 >= a.row_lo && ty0 + kCxTY <= a.row_hi;      // tile entirely inside the loss window
+    auto in_win = [&](int ly) { const int gy = ty0 - HY + ly; return gy >= a.row_lo && gy < a.row_hi; };
     ct_mbar_wait(bars + st, phase[st]);
     phase[st] ^= 1u;
     float lacc = 0.f;
@@ -666,7 +671,7 @@ __global__ void __launch_bounds__(kCtThreads, 2) mat_cross_tma_kernel(const MatA
         float sd[4];
         if (interior) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { sd[i] = scale2 * r[i]; if (core[k]) lacc = fmaf(r[i], r[i], lacc); }
+          for (int i = 0; i < 4; ++i) { sd[i] = scale2 * r[i]; if (core[k] && (rows_in || in_win(lyq[k] >> 8))) lacc = fmaf(r[i], r[i], lacc); }
         } else {
           const int gy = ty0 - HY + (lyq[k] >> 8), gx = tx0 - 4 + 4 * (lyq[k] & 255);
           const bool rowreg = gy >= zy && gy < n0 - zy;
@@ -674,7 +679,7 @@ __global__ void __launch_bounds__(kCtThreads, 2) mat_cross_tma_kernel(const MatA
           for (int i = 0; i < 4; ++i) {
             const bool reg = rowreg && gx + i >= zx && gx + i < n1 - zx;   // regular interior row of the operators
             sd[i] = reg ? scale2 * r[i] : 0.f;
-            if (core[k] && reg) lacc = fmaf(r[i], r[i], lacc);
+            if (core[k] && reg && (rows_in || in_win(lyq[k] >> 8))) lacc = fmaf(r[i], r[i], lacc);
           }
         }
         *reinterpret_cast<float4*>(ss + off_s[k]) = make_float4(sd[0], sd[1], sd[2], sd[3]);
@@ -805,7 +810,7 @@ __global__ void __launch_bounds__(kMatThreads) mat_residual_adjoint_kernel(const
       const int ly = idx / rx, lx = idx - ly * rx;
       const int gy = ty0 - hy + ly, gx = tx0 - hx + lx;
       const size_t cell = (size_t)gy * a.n1 + gx;
-      const bool core = ly >= hy && ly < hy + kMatTY && lx >= hx && lx < hx + kMatTX;
+      const bool core = ly >= hy && ly < hy + kMatTY && lx >= hx && lx < hx + kMatTX && gy >= a.row_lo && gy < a.row_hi;
       const float* uc = us + (ly + hy) * ux + lx + hx;
       for (int e = 0; e < a.n_eq; ++e) {
         float res = 0.f;
@@ -869,7 +874,7 @@ __global__ void __launch_bounds__(kMatThreads) mat_residual_adjoint_kernel(const
       for (int q = 0; q < kMatMaxFields; ++q)
         if (q < a.n_fields) F[q] = field_value(a, a.fld[q], us, ux, uplane, ly + hy, lx + hx, gy, gx);
       const size_t cell = (size_t)gy * a.n1 + gx;
-      const bool core = ly >= hy && ly < hy + kMatTY && lx >= hx && lx < hx + kMatTX;
+      const bool core = ly >= hy && ly < hy + kMatTY && lx >= hx && lx < hx + kMatTX && gy >= a.row_lo && gy < a.row_hi;
       for (int e = 0; e < a.n_eq; ++e) {
         float res = 0.f;
         for (int t = a.eq_term_begin[e]; t < a.eq_term_end[e]; ++t) {
@@ -1134,7 +1139,7 @@ __device__ void mat_finalize_block(const double* __restrict__ part_loss, int n_c
     if (threadIdx.x == 0) {
       double t = 0.0;
       for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) t += sh[w];
-      mse[e] = t / n_cells;
+      mse[e] = t / slot_len[e];          // global cell count (slab decomposition: partial sums add across ranks)
     }
     __syncthreads();
   }
@@ -1356,6 +1361,7 @@ int tdb200_mat_plan_create(const tdb200_mat_desc* desc, const tdb200_mat_field* 
     MCU(cudaMalloc(&p->d_part_loss, sizeof(double) * (size_t)(p->n_ctas > l1 ? p->n_ctas : l1) * desc->n_eq));
   }
   a.band = p->d_band; a.terms = p->d_terms; a.factors = p->d_factors; a.part_loss = p->d_part_loss;
+  a.row_lo = 0; a.row_hi = desc->n0;
   tdb::MatBcArgs& b = p->bc;
   b.n_var = desc->n_var; b.n0 = desc->n0; b.n1 = desc->n1; b.n_fields = desc->n_fields; b.n_eq = desc->n_eq;
   b.band = p->d_band; b.terms = p->d_terms; b.factors = p->d_factors;
@@ -1488,6 +1494,14 @@ int tdb200_mat_eval_fields(tdb200_mat_plan* p, const float* u_dev, float* op_dev
 
 int64_t tdb200_mat_plan_out_size(const tdb200_mat_plan* p) { return p ? 2 + p->n_slots : 0; }
 int32_t tdb200_mat_plan_launches_per_call(const tdb200_mat_plan* p) { return p ? 2 : 0; }
+
+int tdb200_mat_plan_set_row_window(tdb200_mat_plan* p, int32_t row_lo, int32_t row_hi) {
+  if (!p) return mat_invalid("null plan");
+  if (row_lo < 0 || row_hi > p->desc.n0 || row_lo >= row_hi) return mat_invalid("row window out of range");
+  p->args.row_lo = row_lo;
+  p->args.row_hi = row_hi;
+  return TDB200_OK;
+}
 
 int32_t tdb200_mat_plan_kernel_kind(const tdb200_mat_plan* p) {
   if (!p || !p->args.lin1) return 0;

@@ -125,32 +125,35 @@ def cell_indices(grid: torch.Tensor, bnd: torch.Tensor) -> torch.Tensor:
     return flat.to(torch.int32)
 
 
-class MatPlan:
-    """Owns one tdb200_mat_plan."""
+def slab_rows(n0: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block of grid rows (axis 0) owned by `rank`."""
+    return (n0 * rank) // world, (n0 * (rank + 1)) // world
 
-    def __init__(self, grid: torch.Tensor, prepared_operator: List[dict], bconds: List[dict], model: torch.Tensor,
-                 lambda_operator, lambda_bound, derivative_points: int = 2, shard=(0, 1), process_group=None):
-        if shard[1] > 1:
-            raise UnsupportedProblem('multi-GPU slab decomposition of mat mode is not implemented yet')
-        if grid.dim() != 3 or model.dim() != 3:
+
+class MatIR:
+    """Lowered mat-mode problem of one rank (host data only; `MatPlan` hands it to the C ABI, tests/mat_interp.py
+    evaluates it with dense fp64 operators).  With `shard = (rank, world)` the rank owns rows [r0, r1) of axis 0 and
+    works on the extended slab [e0, e1) = owned rows + 2 * reach halo rows towards every neighbour: residuals of the
+    halo rows next to the owned block are recomputed locally, so the only exchange per step is the 2 * reach rows of
+    `u` from each neighbour plus one all-reduce of the loss terms."""
+
+    def __init__(self, grid: torch.Tensor, prepared_operator: List[dict], bconds: List[dict], n_var: int,
+                 device, lambda_operator, lambda_bound, derivative_points: int = 2, shard=(0, 1)):
+        if grid.dim() != 3:
             raise UnsupportedProblem('the fused mat path supports 2-D grids ([2, N0, N1], model [n_eq, N0, N1])')
-        if model.dtype != torch.float32:
-            raise UnsupportedProblem('mat-mode model must be float32')
         if not bconds:
             raise UnsupportedProblem('a problem without boundary conditions has no finite loss in the reference')
-        self.lib = _native.load()
-        self.device = model.device
-        self.grid = grid
-        n_var, n0, n1 = model.shape
-        self.shape = (n_var, n0, n1)
+        rank, world = shard
+        self.shard = (int(rank), int(world))
+        self.device = device
+        n0, n1 = int(grid.shape[1]), int(grid.shape[2])
+        self.n0_global, self.n1, self.n_var = n0, n1, n_var
         n_eq = len(prepared_operator)
         p = derivative_points
         hs = step_h(grid)
-        dims = (n0, n1)
 
-        self._fields: List[Tuple[int, int, int]] = [(v, 0, 0) for v in range(n_var)]
-        terms, factors, coefs = [], [], []
-        coef_off = 0
+        self.fields: List[Tuple[int, int, int]] = [(v, 0, 0) for v in range(n_var)]
+        terms, factors, coefs_full = [], [], []
 
         def field_index(var, axes):
             axes = [a for a in axes if a is not None]
@@ -159,12 +162,11 @@ class MatPlan:
             if len(set(axes)) != 1:
                 raise UnsupportedProblem(f'mixed partial derivative {axes} is not supported by the fused mat path')
             key = (var, axes[0], len(axes))
-            if key not in self._fields:
-                self._fields.append(key)
-            return self._fields.index(key)
+            if key not in self.fields:
+                self.fields.append(key)
+            return self.fields.index(key)
 
         def add_terms(op: dict):
-            nonlocal coef_off
             begin = len(terms)
             for label, term in op.items():
                 dif = list(term.keys())[1]
@@ -183,22 +185,18 @@ class MatPlan:
                 if callable(c) and not isinstance(c, torch.Tensor):
                     c = c(grid)
                 if isinstance(c, torch.Tensor) and c.numel() > 1:
-                    c = torch.broadcast_to(c.to(self.device, torch.float32), (n0, n1)).reshape(-1)
-                    terms.append((0.0, 1, coef_off, fb, len(factors)))
-                    coefs.append(c)
-                    coef_off += c.numel()
+                    terms.append([0.0, 1, len(coefs_full), fb, len(factors)])       # idx = buffer number for now
+                    coefs_full.append(torch.broadcast_to(c.to(device, torch.float32), (n0, n1)))
                 else:
-                    terms.append((float(c), 0, 0, fb, len(factors)))
+                    terms.append([float(c), 0, 0, fb, len(factors)])
             return begin, len(terms)
 
-        eq_ranges = [add_terms(eq) for eq in prepared_operator]
+        self.eq_ranges = [add_terms(eq) for eq in prepared_operator]
 
-        # ---- boundary rows ----------------------------------------------------------------------------
+        # ---- boundary rows (global), operator terms of the conditions --------------------------------
         self.bnd_types: List[str] = []
         type_len: Dict[str, int] = {}
-        bc_rows, cells, targets = [], [], []
-        cell_off = tgt_off = 0
-        self._bc_layout = []                       # (type index, offset in type column, n) per condition
+        bc_global = []
         for bc in bconds:
             kind = bc['type']
             if kind not in self.bnd_types:
@@ -214,78 +212,183 @@ class MatPlan:
                 if K > 4:
                     raise UnsupportedProblem('periodic condition with more than 4 sides')
                 n = sides[0].numel()
-                cidx = torch.stack(sides, 1).reshape(-1)
+                cidx = torch.stack(sides, 1)                        # [n, K]
                 sign = [1.0] + [-1.0] * (K - 1) + [0.0] * (4 - K)
-                tgt = torch.zeros(n, dtype=torch.float32, device=self.device)
+                tgt = torch.zeros(n, dtype=torch.float32, device=device)
             else:
-                cidx = cell_indices(grid, bc['bnd'])
-                n, K = cidx.numel(), 1
+                cidx = cell_indices(grid, bc['bnd']).reshape(-1, 1)
+                n, K = cidx.shape[0], 1
                 sign = [1.0, 0.0, 0.0, 0.0]
-                tgt = bc['bval'].reshape(-1).to(self.device, torch.float32)
+                tgt = bc['bval'].reshape(-1).to(device, torch.float32)
                 if tgt.numel() != n:
                     raise ValueError(f'{tgt.numel()} target values for {n} boundary points')
             tb = te = 0
             if bop is not None:
                 tb, te = add_terms(bop)
-            bc_rows.append((n, cell_off, tgt_off, K, int(bc['var']), slot, tb, te, sign))
-            self._bc_layout.append((slot, type_len[kind], n))
-            cells.append(cidx)
-            targets.append(tgt)
-            cell_off += n * K
-            tgt_off += n
+            bc_global.append(dict(cells=cidx.to(torch.int64), tgt=tgt, K=K, var=int(bc['var']), slot=slot, tb=tb, te=te,
+                                  sign=sign, type_off=type_len[kind]))
             type_len[kind] += n
         self.type_len = [type_len[t] for t in self.bnd_types]
         max_len = max(self.type_len)
         self.n_eq = n_eq
         self.n_slots = n_eq + len(self.bnd_types)
-        self.slot_len = [n0 * n1] * n_eq + [max_len] * len(self.bnd_types)
+        self.slot_len = [n0 * n1] * n_eq + [max_len] * len(self.bnd_types)        # global counts
         self.slot_lambda = _lambda_list(lambda_operator, n_eq, 'lambda_operator') + \
             _lambda_list(lambda_bound, len(self.bnd_types), 'lambda_bound')
 
-        # ---- bands for every derivative field ------------------------------------------------------------
-        if len(self._fields) > 12:
+        # ---- rows of this rank ---------------------------------------------------------------------------
+        if len(self.fields) > 12:
             raise UnsupportedProblem('more than 12 distinct derivative fields')
-        fld = np.zeros(len(self._fields), FIELD_DTYPE)
+        self.reach0 = max([order * (p - 1) for (_, axis, order) in self.fields if order > 0 and axis == 0] + [0])
+        self.halo = 2 * self.reach0
+        r0, r1 = slab_rows(n0, rank, world)
+        if world > 1 and (r1 - r0) < max(self.halo, 1):
+            raise UnsupportedProblem(f'{n0} grid rows are too few for {world} ranks (halo {self.halo})')
+        e0, e1 = (max(0, r0 - self.halo), min(n0, r1 + self.halo)) if world > 1 else (0, n0)
+        self.rows, self.ext = (r0, r1), (e0, e1)
+        n_ext = e1 - e0
+        self.shape = (n_var, r1 - r0, n1)                                        # the model tensor of this rank
+        self.shape_ext = (n_var, n_ext, n1)
+        self.n_cells = n0 * n1
+        self.n_cells_local = (r1 - r0) * n1
+
+        # coefficient buffers: the extended slab of every per-cell tensor
+        for t in terms:
+            if t[1] == 1:
+                t[2] = t[2] * n_ext * n1                                         # buffer number -> float offset
+        self.coeffs = (torch.cat([c[e0:e1].reshape(-1) for c in coefs_full]).contiguous() if coefs_full
+                       else torch.zeros(1, device=device))
+
+        # boundary rows owned by this rank, cells as flat indices into the extended slab
+        bc_rows, cells, targets = [], [], []
+        self.bc_layout = []                        # (type index, offset in type column, n) per condition (unsharded)
+        cell_off = tgt_off = 0
+        for b in bc_global:
+            c = b['cells']
+            i0 = c // n1
+            own = (i0[:, 0] >= r0) & (i0[:, 0] < r1)
+            if world > 1 and b['K'] > 1:
+                inside = ((i0 >= e0) & (i0 < e1)).all(1)
+                if not bool((inside | ~own).all()):
+                    raise UnsupportedProblem('a periodic condition couples rows of different ranks')
+            c = c[own] - e0 * n1
+            tgt = b['tgt'][own.to(b['tgt'].device)]
+            n = int(c.shape[0])
+            bc_rows.append((n, cell_off, tgt_off, b['K'], b['var'], b['slot'], b['tb'], b['te'], b['sign']))
+            self.bc_layout.append((b['slot'], b['type_off'], n))
+            cells.append(c.reshape(-1))
+            targets.append(tgt)
+            cell_off += n * b['K']
+            tgt_off += n
+
+        # ---- bands for every derivative field (on the extended slab along axis 0) -----------------------
+        dims = (n_ext, n1)
+        fld = np.zeros(len(self.fields), FIELD_DTYPE)
         band = [np.zeros(1, np.float32)]
         off = 1
-        for q, (var, axis, order) in enumerate(self._fields):
+        for q, (var, axis, order) in enumerate(self.fields):
             fld[q]['var'], fld[q]['axis'], fld[q]['order'] = var, axis, order
             if order > 0:
                 bnd_arr, b, E = derivative_band(dims[axis], p, order, hs[axis])
                 fld[q]['half_width'], fld[q]['n_edge'], fld[q]['coef_off'] = b, E, off
                 band.append(bnd_arr)
                 off += bnd_arr.size
-        band = np.concatenate(band).astype(np.float32)
-
-        self._terms = np.array(terms, dtype=TERM_DTYPE) if terms else np.zeros(0, TERM_DTYPE)
-        self._factors = np.array(factors, dtype=FACTOR_DTYPE) if factors else np.zeros(0, FACTOR_DTYPE)
-        desc = _native.MatDesc(n_eq, n_var, n0, n1, len(self._fields))
-        eb = np.array([r[0] for r in eq_ranges], np.int32)
-        ee = np.array([r[1] for r in eq_ranges], np.int32)
-        handle = C.c_void_p()
-        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        _native.check(self.lib.tdb200_mat_plan_create(
-            C.byref(desc), _native.np_ptr(fld), band.size, _native.np_ptr(band), _native.np_ptr(eb), _native.np_ptr(ee),
-            len(self._terms), _native.np_ptr(self._terms), len(self._factors), _native.np_ptr(self._factors),
-            dev_index, C.byref(handle)), 'tdb200_mat_plan_create')
-        self.handle = handle
-        self._coeffs = torch.cat(coefs).contiguous() if coefs else torch.zeros(1, device=self.device)
-        _native.check(self.lib.tdb200_mat_plan_set_coeffs(handle, self._coeffs.data_ptr(), self._coeffs.numel()),
-                      'tdb200_mat_plan_set_coeffs')
-        self._bcs = np.zeros(len(bc_rows), _native.MAT_BC_DTYPE)
+        self.fld = fld
+        self.band = np.concatenate(band).astype(np.float32)
+        self.terms = np.array([tuple(t) for t in terms], dtype=TERM_DTYPE) if terms else np.zeros(0, TERM_DTYPE)
+        self.factors = np.array(factors, dtype=FACTOR_DTYPE) if factors else np.zeros(0, FACTOR_DTYPE)
+        self.bcs = np.zeros(len(bc_rows), _native.MAT_BC_DTYPE)
         for i, (n, co, to, K, var, slot, tb, te, sign) in enumerate(bc_rows):
-            r = self._bcs[i]
+            r = self.bcs[i]
             r['n_rows'], r['cell_off'], r['tgt_off'], r['K'], r['var'], r['slot'] = n, co, to, K, var, slot
             r['term_begin'], r['term_end'] = tb, te
             r['sign'][:] = sign
-        self._cells = torch.cat(cells).to(self.device, torch.int32).contiguous()
-        self._targets = torch.cat(targets).contiguous()
-        self.n_bc_rows = int(self._targets.numel())
+        self.cells = (torch.cat(cells) if cells else torch.zeros(0, dtype=torch.int64)).to(device, torch.int32).contiguous()
+        self.targets = (torch.cat(targets) if targets else torch.zeros(0, device=device)).contiguous()
+        self.n_bc_rows = int(self.targets.numel())
+
+
+def exchange_halos(u: torch.Tensor, ir: MatIR, group=None) -> torch.Tensor:
+    """[n_var, n_local, n1] -> the extended slab [n_var, n_ext, n1]: the owned rows plus `halo` rows received from each
+    neighbour (point-to-point; NCCL on GPUs, gloo in the CPU tests).  Single rank: returns `u` itself."""
+    rank, world = ir.shard
+    if world == 1:
+        return u
+    import torch.distributed as dist
+    (r0, r1), (e0, e1) = ir.rows, ir.ext
+    up, down = r0 - e0, e1 - r1                                 # halo rows above / below the owned block
+    ext = torch.empty(ir.shape_ext, dtype=u.dtype, device=u.device)
+    ext[:, up:up + (r1 - r0)] = u
+    ops, keep = [], []
+    if rank > 0:                                                # neighbour above needs my first rows, I need its last
+        send = u[:, :ir.halo].contiguous()
+        recv = torch.empty((u.shape[0], up, u.shape[2]), dtype=u.dtype, device=u.device)
+        ops += [dist.P2POp(dist.isend, send, rank - 1, group), dist.P2POp(dist.irecv, recv, rank - 1, group)]
+        keep.append((recv, slice(0, up)))
+    if rank < world - 1:
+        send = u[:, -ir.halo:].contiguous()
+        recv = torch.empty((u.shape[0], down, u.shape[2]), dtype=u.dtype, device=u.device)
+        ops += [dist.P2POp(dist.isend, send, rank + 1, group), dist.P2POp(dist.irecv, recv, rank + 1, group)]
+        keep.append((recv, slice(up + (r1 - r0), up + (r1 - r0) + down)))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    for recv, sl in keep:
+        ext[:, sl] = recv
+    return ext
+
+
+class MatPlan:
+    """Owns one tdb200_mat_plan (built from the `MatIR` of this rank)."""
+
+    def __init__(self, grid: torch.Tensor, prepared_operator: List[dict], bconds: List[dict], model: torch.Tensor,
+                 lambda_operator, lambda_bound, derivative_points: int = 2, shard=None, process_group=None):
+        if model.dim() != 3:
+            raise UnsupportedProblem('the fused mat path supports 2-D grids ([2, N0, N1], model [n_eq, N0, N1])')
+        if model.dtype != torch.float32:
+            raise UnsupportedProblem('mat-mode model must be float32')
+        shard = (0, 1) if shard is None else shard
+        self.lib = _native.load()
+        self.device = model.device
+        self.grid = grid
+        self._pg = process_group
+        ir = MatIR(grid, prepared_operator, bconds, int(model.shape[0]), model.device, lambda_operator, lambda_bound,
+                   derivative_points, shard)
+        self.ir = ir
+        if tuple(model.shape) != ir.shape:
+            raise UnsupportedProblem(f'rank {shard[0]} of {shard[1]} owns grid rows {ir.rows}: its model tensor must be '
+                                     f'{ir.shape}, got {tuple(model.shape)}')
+        self.shape, self.n_eq, self.n_slots = ir.shape, ir.n_eq, ir.n_slots
+        self.bnd_types, self.type_len = ir.bnd_types, ir.type_len
+        self.slot_len, self.slot_lambda = ir.slot_len, ir.slot_lambda
+        self._bc_layout = ir.bc_layout
+        n_var, n_ext, n1 = ir.shape_ext
+        desc = _native.MatDesc(ir.n_eq, n_var, n_ext, n1, len(ir.fields))
+        eb = np.array([r[0] for r in ir.eq_ranges], np.int32)
+        ee = np.array([r[1] for r in ir.eq_ranges], np.int32)
+        handle = C.c_void_p()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        _native.check(self.lib.tdb200_mat_plan_create(
+            C.byref(desc), _native.np_ptr(ir.fld), ir.band.size, _native.np_ptr(ir.band), _native.np_ptr(eb),
+            _native.np_ptr(ee), len(ir.terms), _native.np_ptr(ir.terms), len(ir.factors), _native.np_ptr(ir.factors),
+            dev_index, C.byref(handle)), 'tdb200_mat_plan_create')
+        self.handle = handle
+        self._coeffs = ir.coeffs
+        _native.check(self.lib.tdb200_mat_plan_set_coeffs(handle, self._coeffs.data_ptr(), self._coeffs.numel()),
+                      'tdb200_mat_plan_set_coeffs')
+        self._bcs, self._cells, self._targets = ir.bcs, ir.cells, ir.targets
+        if self._cells.numel() == 0:                      # keep valid device pointers for ranks without boundary rows
+            self._cells = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._targets = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.n_bc_rows = ir.n_bc_rows
         self._push_bcs()
+        if shard[1] > 1:
+            _native.check(self.lib.tdb200_mat_plan_set_row_window(handle, ir.rows[0] - ir.ext[0], ir.rows[1] - ir.ext[0]),
+                          'tdb200_mat_plan_set_row_window')
         self.out_size = int(self.lib.tdb200_mat_plan_out_size(handle))
         self.launches_per_call = int(self.lib.tdb200_mat_plan_launches_per_call(handle))
         self.kernel_kind = ('generic', 'register-tap', 'cross-vec4', 'cross-tma')[int(self.lib.tdb200_mat_plan_kernel_kind(handle))]
-        self.n_cells = n0 * n1
+        self.n_cells = ir.n_cells                          # global
+        self.n_cells_local = ir.n_cells_local
 
     def _push_bcs(self):
         lam = np.asarray(self.slot_lambda, np.float64)
@@ -302,17 +405,35 @@ class MatPlan:
         if tuple(u.shape) != self.shape or u.dtype != torch.float32 or not u.is_cuda or not u.is_contiguous():
             raise RuntimeError(f'mat-mode model must be a contiguous float32 CUDA tensor of shape {self.shape}')
 
-    def loss_grad_raw(self, u: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        self._check_model(u)
+    def loss_grad_ext(self, ue: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Kernel launch on this rank's extended slab (no communication): -> (partial out [2 + n_slots] of this rank,
+        d loss / d u of the owned rows)."""
+        if tuple(ue.shape) != self.ir.shape_ext or ue.dtype != torch.float32 or not ue.is_cuda or not ue.is_contiguous():
+            raise RuntimeError(f'extended slab must be a contiguous float32 CUDA tensor of shape {self.ir.shape_ext}')
         out = torch.empty(self.out_size, dtype=torch.float32, device=self.device)
-        grad = torch.empty(self.shape, dtype=torch.float32, device=self.device)
+        grad = torch.empty(self.ir.shape_ext, dtype=torch.float32, device=self.device)
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        _native.check(self.lib.tdb200_mat_loss_grad(self.handle, u.data_ptr(), grad.data_ptr(), out.data_ptr(),
+        _native.check(self.lib.tdb200_mat_loss_grad(self.handle, ue.data_ptr(), grad.data_ptr(), out.data_ptr(),
                                                     stream), 'tdb200_mat_loss_grad')
+        if self.ir.shard[1] > 1:
+            up = self.ir.rows[0] - self.ir.ext[0]
+            grad = grad[:, up:up + self.shape[1]].contiguous()
+        return out, grad
+
+    def loss_grad_raw(self, u: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """-> (out [2 + n_slots] summed over ranks, d loss / d u of this rank's rows).  Several ranks: halo rows from
+        the neighbours (point-to-point), then one all-reduce of the loss terms; the gradient stays sharded."""
+        self._check_model(u)
+        out, grad = self.loss_grad_ext(exchange_halos(u, self.ir, self._pg))
+        if self.ir.shard[1] > 1:
+            import torch.distributed as dist
+            dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self._pg)
         return out, grad
 
     def eval_fields(self, u: torch.Tensor):
         self._check_model(u)
+        if self.ir.shard[1] > 1:
+            raise UnsupportedProblem('per-point fields are not gathered across ranks')
         out = torch.empty(self.out_size, dtype=torch.float32, device=self.device)
         op = torch.empty(self.n_cells, self.n_eq, dtype=torch.float32, device=self.device)
         rows = torch.empty(max(self.n_bc_rows, 1), dtype=torch.float32, device=self.device)
