@@ -328,6 +328,14 @@ def run_b200_mat(args, dev, tdb, problems, rank=0, world=1):
         return ms_total
 
     step = lambda: plan.loss_grad_raw(u)
+    graphed = False
+    if not args.no_graph and world == 1:      # one CUDA graph per step (single rank; eager with collectives)
+        try:
+            step, _, _ = plan.capture(u)
+            graphed = True
+        except Exception as e:                # noqa: BLE001 - report and fall back to eager launches
+            sys.stderr.write(f'[bench] CUDA graph capture failed ({e}); timing eager launches\n')
+            step = lambda: plan.loss_grad_raw(u)
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize(dev)
@@ -377,7 +385,7 @@ def run_b200_mat(args, dev, tdb, problems, rank=0, world=1):
         'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': args.workload, 'description': spec['desc'], 'cells': n_cells, 'cells_per_gpu': n_local,
-                   'mode': 'mat', 'kernel': plan.kernel_kind,
+                   'mode': 'mat', 'kernel': plan.kernel_kind, 'cuda_graph': graphed,
                    'l2': 'flushed between timed steps (256 MB write)',
                    'parallelism': 'single GPU' if world == 1 else
                                   f'{world} row slabs, {plan.ir.halo}-row halo exchange + all-reduce of the loss terms'},
@@ -474,6 +482,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='wave_autograd_1e6', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='mat workload: time eager launches instead of a CUDA graph')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

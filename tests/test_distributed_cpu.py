@@ -109,6 +109,12 @@ def _mat_worker(rank, world, port, name, out_dir):
         assert tuple(u_local.shape) == ir.shape
         u_ext = exchange_halos(u_local, ir)                        # the product's own halo exchange (gloo here)
         assert torch.equal(u_ext, u[:, ir.ext[0]:ir.ext[1]])       # every halo row arrived from the right neighbour
+        if u.shape[0] == 1:                                        # in-place variant: the model is a view of the slab
+            ext = torch.zeros(ir.shape_ext, dtype=u.dtype)
+            up = r0 - ir.ext[0]
+            ext[:, up:up + (r1 - r0)] = u_local
+            assert exchange_halos(ext[:, up:up + (r1 - r0)], ir, None, ext) is ext
+            assert torch.equal(ext, u[:, ir.ext[0]:ir.ext[1]])
         out, grad = evaluate_mat_ir(ir, u_ext)
         dist.all_reduce(out, op=dist.ReduceOp.SUM)
         np.savez(os.path.join(out_dir, f'rank{rank}.npz'), out=out.numpy(), grad=grad.numpy(), rows=np.array(ir.rows))

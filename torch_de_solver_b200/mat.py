@@ -308,32 +308,38 @@ class MatIR:
         self.n_bc_rows = int(self.targets.numel())
 
 
-def exchange_halos(u: torch.Tensor, ir: MatIR, group=None) -> torch.Tensor:
+def exchange_halos(u: torch.Tensor, ir: MatIR, group=None, ext: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[n_var, n_local, n1] -> the extended slab [n_var, n_ext, n1]: the owned rows plus `halo` rows received from each
-    neighbour (point-to-point; NCCL on GPUs, gloo in the CPU tests).  Single rank: returns `u` itself."""
+    neighbour (one all-gather of the edge rows; NCCL on GPUs, gloo in the CPU tests).  Single rank: returns `u` itself.
+    If `ext` is given and `u` already is the view of its owned rows (MatPlan adopts the model tensor that way), only
+    the halo rows move."""
     rank, world = ir.shard
     if world == 1:
         return u
     import torch.distributed as dist
     (r0, r1), (e0, e1) = ir.rows, ir.ext
-    up, down = r0 - e0, e1 - r1                                 # halo rows above / below the owned block
-    ext = torch.empty(ir.shape_ext, dtype=u.dtype, device=u.device)
-    ext[:, up:up + (r1 - r0)] = u
-    ops, keep = [], []
-    if rank > 0:                                                # neighbour above needs my first rows, I need its last
-        send = u[:, :ir.halo].contiguous()
-        recv = torch.empty((u.shape[0], up, u.shape[2]), dtype=u.dtype, device=u.device)
-        ops += [dist.P2POp(dist.isend, send, rank - 1, group), dist.P2POp(dist.irecv, recv, rank - 1, group)]
-        keep.append((recv, slice(0, up)))
+    up, down, n = r0 - e0, e1 - r1, r1 - r0                     # halo rows above / below the owned block
+    in_place = ext is not None and u.data_ptr() == ext[:, up:up + n].data_ptr() and u.shape[0] == 1
+    if not in_place:
+        ext = torch.empty(ir.shape_ext, dtype=u.dtype, device=u.device)
+        ext[:, up:up + n] = u
+    # one all-gather of every rank's first / last `halo` owned rows (world * 2 * halo rows: ~1 MB at 8 ranks of a
+    # 4096-wide grid) instead of four point-to-point operations: a single collective launch per step
+    h = ir.halo
+    if h == 0:
+        return ext
+    mine = torch.stack([ext[:, up:up + h], ext[:, up + n - h:up + n]])          # [2, n_var, h, n1]
+    allh = torch.empty((world,) + tuple(mine.shape), dtype=u.dtype, device=u.device)
+    if u.is_cuda:
+        dist.all_gather_into_tensor(allh, mine.contiguous(), group=group)
+    else:
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine.contiguous(), group=group)
+        allh = torch.stack(parts)
+    if rank > 0:
+        ext[:, 0:up] = allh[rank - 1, 1]                       # last rows of the neighbour above
     if rank < world - 1:
-        send = u[:, -ir.halo:].contiguous()
-        recv = torch.empty((u.shape[0], down, u.shape[2]), dtype=u.dtype, device=u.device)
-        ops += [dist.P2POp(dist.isend, send, rank + 1, group), dist.P2POp(dist.irecv, recv, rank + 1, group)]
-        keep.append((recv, slice(up + (r1 - r0), up + (r1 - r0) + down)))
-    for req in dist.batch_isend_irecv(ops):
-        req.wait()
-    for recv, sl in keep:
-        ext[:, sl] = recv
+        ext[:, up + n:up + n + down] = allh[rank + 1, 0]       # first rows of the neighbour below
     return ext
 
 
@@ -389,6 +395,14 @@ class MatPlan:
         self.kernel_kind = ('generic', 'register-tap', 'cross-vec4', 'cross-tma')[int(self.lib.tdb200_mat_plan_kernel_kind(handle))]
         self.n_cells = ir.n_cells                          # global
         self.n_cells_local = ir.n_cells_local
+        # Several ranks, one field: the model tensor is adopted as the owned-row view of a persistent extended slab, so
+        # a step moves only the halo rows (optimisers update the view in place; `model.data` is re-pointed once here)
+        self._ext = None
+        if shard[1] > 1 and n_var == 1:
+            up = ir.rows[0] - ir.ext[0]
+            self._ext = torch.zeros(ir.shape_ext, dtype=torch.float32, device=self.device)
+            self._ext[:, up:up + ir.shape[1]] = model.detach()
+            model.data = self._ext[:, up:up + ir.shape[1]]
 
     def _push_bcs(self):
         lam = np.asarray(self.slot_lambda, np.float64)
@@ -424,11 +438,30 @@ class MatPlan:
         """-> (out [2 + n_slots] summed over ranks, d loss / d u of this rank's rows).  Several ranks: halo rows from
         the neighbours (point-to-point), then one all-reduce of the loss terms; the gradient stays sharded."""
         self._check_model(u)
-        out, grad = self.loss_grad_ext(exchange_halos(u, self.ir, self._pg))
+        out, grad = self.loss_grad_ext(exchange_halos(u, self.ir, self._pg, self._ext))
         if self.ir.shard[1] > 1:
             import torch.distributed as dist
             dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self._pg)
         return out, grad
+
+    def capture(self, u: torch.Tensor):
+        """CUDA graph of one step - halo exchange, the two kernel launches, all-reduce of the loss terms - for training
+        loops that are launch bound (a step is ~90 us of GPU work).  -> (replay callable, out, grad): `out` / `grad`
+        are static tensors refreshed by every replay; `u` must keep its storage (in-place optimiser updates do)."""
+        self._check_model(u)
+        if self.ir.shard[1] > 1:
+            raise UnsupportedProblem('CUDA-graph capture of the multi-rank step (collectives inside) is not enabled')
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):                          # warm-up outside the capture (attributes, tensor maps, NCCL)
+                self.loss_grad_raw(u)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out, grad = self.loss_grad_raw(u)
+        return graph.replay, out, grad
 
     def eval_fields(self, u: torch.Tensor):
         self._check_model(u)
