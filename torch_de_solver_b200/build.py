@@ -47,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return obj
 
     from concurrent.futures import ThreadPoolExecutor
-    with ThreadPoolExecutor(max_workers=4) as ex:      # one nvcc process per translation unit
+    with ThreadPoolExecutor(max_workers=8) as ex:      # one nvcc process per translation unit
         objs = list(ex.map(compile_one, sources()))
     cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-cudart', 'static']
     res = subprocess.run(cmd, capture_output=True, text=True)

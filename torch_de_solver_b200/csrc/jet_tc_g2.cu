@@ -1,0 +1,8 @@
+// tcgen05 path: instantiations of signature group 2 (see jet_tc_kernel.cuh; split for parallel compilation).
+#include "jet_tc_kernel.cuh"
+
+namespace tdb {
+
+TDB_TC_DEFINE_GROUP(launch_jet_tc_g2, TDB_TC_SIGS_G2)
+
+}  // namespace tdb
