@@ -296,7 +296,8 @@ constexpr int kTcMaxPts = 32;                         // points per tile (J = 2)
 constexpr int kOffWHi = 0, kOffWLo = kTcWFloats, kOffActHi = 2 * kTcWFloats, kOffActLo = kOffActHi + kTcActFloats,
               kOffYwHi = kOffActLo + kTcActFloats, kOffYwLo = kOffYwHi + kTcYwFloats, kOffX = kOffYwLo + kTcYwFloats,
               kOffU = kOffX + 2 * kTcMaxPts * 4, kOffGu = kOffU + kTcMaxOut * kTcCols, kOffUP = kOffGu + kTcMaxOut * kTcCols,
-              kOffCg = kOffUP + 4 * kTcMaxOut * kTcCols, kOffEnd = kOffCg + (kMaxCParams + 3) / 4 * 4;
+              kOffCg = kOffUP + 4 * kTcMaxOut * kTcCols, kOffBl = kOffCg + (kMaxCParams + 3) / 4 * 4,
+              kOffEnd = kOffBl + kTcMaxOut;                      // kOffBl: last-layer bias
 struct TcSmem {
   tdb200_term* termS;
   tdb200_factor* facS;
@@ -310,7 +311,7 @@ struct TcSmem {
 };
 constexpr size_t kTcSmemBytes =
     (size_t)(2 * kTcWFloats + 2 * kTcActFloats + 2 * kTcYwFloats) * 4 + 1024 /*align*/ +
-    (2 * kTcMaxPts * 4 + 2 * kTcMaxOut * kTcCols + 4 * kTcMaxOut * kTcCols + kMaxCParams) * 4 + 64 + 64 +
+    (2 * kTcMaxPts * 4 + 2 * kTcMaxOut * kTcCols + 4 * kTcMaxOut * kTcCols + kMaxCParams + kTcMaxOut) * 4 + 64 + 64 +
     kTcMaxTerms * sizeof(tdb200_term) + kTcMaxFactors * sizeof(tdb200_factor) + 16 + sizeof(tdb200_segment) + 32 * 4 +
     kTcMaxPts * TDB200_MAX_COLS * 8 + 64 + kTcMaxTerms * 16 + 16;
 
@@ -368,6 +369,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
   for (int i = tid; i < 2 * kTcActFloats + 2 * kTcYwFloats; i += kTcThreads) (sbase + kOffActHi)[i] = 0.f;   // pad rows / columns stay zero
   if (tid < kMaxCParams) (sbase + kOffCg)[tid] = 0.f;
   for (int i = tid; i < 2 * kTcMaxPts * 4; i += kTcThreads) (sbase + kOffX)[i] = 0.f;      // axes >= d stay zero
+  for (int i = tid; i < kTcMaxOut * kTcCols; i += kTcThreads) (sbase + kOffGu)[i] = 0.f;   // pad columns stay zero
+  if (tid < kTcMaxOut) (sbase + kOffBl)[tid] = tid < n_out ? a.arena[a.b_off[L - 1] + tid] : 0.f;
   for (int i = tid; i < min(kTcMaxTerms, a.n_terms); i += kTcThreads) sm.termS[i] = a.terms[i];
   for (int i = tid; i < min(kTcMaxFactors, a.n_factors); i += kTcThreads) sm.facS[i] = a.factors[i];
   for (int i = tid; i < (int)(sizeof(tdb200_segment) / 4); i += kTcThreads)
@@ -564,16 +567,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       if ((lane & 1) == 0) (sbase + kOffUP)[((warp & 3) * kTcMaxOut + v) * kTcCols + col0 + reduce16_col(lane)] = tot;
     }
     __syncthreads();
-    for (int idx = tid; idx < n_out * kTcCols; idx += kTcThreads) {
-      const int v = idx / kTcCols, r = idx - v * kTcCols;
-      const int jc = r & (kTcPC - 1);
-      float s = (jc < C && jc % J == 0) ? a.arena[a.b_off[L - 1] + v] : 0.f;
+    // the point threads finish the reduction for their own point (4 lane-window partials + bias) and clear its seeds
+    if (tid < P) {
+      const int pc = (tid / PH) * kTcPC + (tid % PH) * J;
+      for (int v = 0; v < n_out; ++v) {
+        const float bl = (sbase + kOffBl)[v];
 #pragma unroll
-      for (int w = 0; w < 4; ++w) s += (sbase + kOffUP)[(w * kTcMaxOut + v) * kTcCols + r];
-      (sbase + kOffU)[idx] = s;
-      (sbase + kOffGu)[idx] = 0.f;
+        for (int c = 0; c < J; ++c) {
+          float sacc = c == 0 ? bl : 0.f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) sacc += (sbase + kOffUP)[(w * kTcMaxOut + v) * kTcCols + pc + c];
+          (sbase + kOffU)[v * kTcCols + pc + c] = sacc;
+          (sbase + kOffGu)[v * kTcCols + pc + c] = 0.f;
+        }
+      }
     }
-    __syncthreads();
 
     TMARK(5);
     // ---- operator terms, residual, loss, adjoint seeds (one thread per point) -------------------------
