@@ -567,21 +567,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
       if ((lane & 1) == 0) (sbase + kOffUP)[((warp & 3) * kTcMaxOut + v) * kTcCols + col0 + reduce16_col(lane)] = tot;
     }
     __syncthreads();
-    // the point threads finish the reduction for their own point (4 lane-window partials + bias) and clear its seeds
-    if (tid < P) {
-      const int pc = (tid / PH) * kTcPC + (tid % PH) * J;
-      for (int v = 0; v < n_out; ++v) {
-        const float bl = (sbase + kOffBl)[v];
+    for (int idx = tid; idx < n_out * kTcCols; idx += kTcThreads) {
+      const int v = idx / kTcCols, r = idx - v * kTcCols;
+      const int jc = r & (kTcPC - 1);
+      float s = (jc < C && jc % J == 0) ? (sbase + kOffBl)[v] : 0.f;
 #pragma unroll
-        for (int c = 0; c < J; ++c) {
-          float sacc = c == 0 ? bl : 0.f;
-#pragma unroll
-          for (int w = 0; w < 4; ++w) sacc += (sbase + kOffUP)[(w * kTcMaxOut + v) * kTcCols + pc + c];
-          (sbase + kOffU)[v * kTcCols + pc + c] = sacc;
-          (sbase + kOffGu)[v * kTcCols + pc + c] = 0.f;
-        }
-      }
+      for (int w = 0; w < 4; ++w) s += (sbase + kOffUP)[(w * kTcMaxOut + v) * kTcCols + r];
+      (sbase + kOffU)[idx] = s;
+      (sbase + kOffGu)[idx] = 0.f;
     }
+    __syncthreads();
 
     TMARK(5);
     // ---- operator terms, residual, loss, adjoint seeds (one thread per point) -------------------------
