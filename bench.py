@@ -52,6 +52,9 @@ WORKLOADS = {
                              desc="Poisson 2D mode 'mat', 4096x4096 grid, u_xx + u_yy - f, Dirichlet edges"),
 }
 MAT_BYTES_PER_CELL = 12      # read u, read the forcing tensor, write d loss / d u (fp32) - SURVEY 8d
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+# captures (profiles/r01_ncu_jet_tc.md, profiles/r01_ncu_mat.md); None where no capture exists
+NCU_TRAFFIC_BYTES = {'wave_autograd_1e6': 8.58e6 + 4.80e6, 'poisson_mat_4096': 134.42e6 + 38.08e6}
 
 
 def flop_per_point(layers, J):
@@ -74,7 +77,7 @@ class ClockSampler:
             f = tempfile.NamedTemporaryFile('w', suffix='.csv', delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-i', str(self.idx), '-lms', '100'], stdout=f, stderr=subprocess.DEVNULL)
+                                          '-i', str(self.idx), '-lms', '50'], stdout=f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -89,7 +92,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         try:
-            for line in open(self.path):
+            lines = list(open(self.path))
+            if not lines:                   # region shorter than the sampler's start-up: one query right after the load
+                lines = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i',
+                                        str(self.idx)], capture_output=True, text=True, timeout=10).stdout.splitlines()
+            for line in lines:
                 c = [x.strip() for x in line.split(',')]
                 if len(c) < 9:
                     continue
@@ -200,13 +207,13 @@ def run_b200(args):
         torch.cuda.synchronize(dev)
         return [e0.elapsed_time(e1) for e0, e1 in ev]
 
+    sampler = ClockSampler(local)           # started before the warm-up: nvidia-smi needs ~0.2 s to deliver samples
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_resident()
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     t_wall = time.time()
     times = timed(step_resident, args.steps)
     torch.cuda.synchronize(dev)
@@ -277,7 +284,8 @@ def run_b200(args):
         'gpu_launches': args.steps * plan.launches_per_call,
         'clocks': clocks,
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                     'frac': achieved / peak if peak else None, 'traffic': None,
+                     'frac': achieved / peak if peak else None,
+                     'traffic': NCU_TRAFFIC_BYTES.get(args.workload) if world == 1 else None,
                      'flop_per_point': fpp,
                      'peak_source': f'cuBLAS TF32 8192^3 measured live = {tf32:.1f} TFLOP/s, / 3 for 3xTF32 '
                                     f'(MEASURED_PEAKS.json [{peak_src}] bf16 = {peaks.get("bf16_tflops")})'},
@@ -336,13 +344,13 @@ def run_b200_mat(args, dev, tdb, problems, rank=0, world=1):
         except Exception as e:                # noqa: BLE001 - report and fall back to eager launches
             sys.stderr.write(f'[bench] CUDA graph capture failed ({e}); timing eager launches\n')
             step = lambda: plan.loss_grad_raw(u)
+    sampler = ClockSampler(dev.index or 0)  # started before the warm-up: nvidia-smi needs ~0.2 s to deliver samples
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(dev.index or 0)
-    sampler.start()
     t_wall = time.time()
     times = timed(step, args.steps)
     if world > 1:
@@ -394,7 +402,8 @@ def run_b200_mat(args, dev, tdb, problems, rank=0, world=1):
         'gpu_launches': args.steps * plan.launches_per_call,
         'clocks': clocks,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                     'frac': achieved / peaks['hbm_gbs'], 'traffic': None,
+                     'frac': achieved / peaks['hbm_gbs'],
+                     'traffic': NCU_TRAFFIC_BYTES.get(args.workload) if world == 1 else None,
                      'bytes_per_cell': MAT_BYTES_PER_CELL, 'kernel_ms': kt,
                      'peak_source': f'MEASURED_PEAKS.json [{peak_src}] hbm_gbs; achieved = cells per GPU * 12 B / '
                                     f'time of the two launches of one step (stencil + boundary/finalize) on rank 0'},
