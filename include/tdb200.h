@@ -96,6 +96,11 @@ int tdb200_plan_set_points(tdb200_plan* plan, const float* pts_dev, int64_t n_pt
 /* Per-slot lambda and 1/len (global row count of the slot): scale = lambda/len enters the gradient. */
 int tdb200_plan_set_slots(tdb200_plan* plan, const double* slot_lambda, const double* slot_len);
 
+/* Causal loss (tedeous/losses.py:137-182): optional per-row weights w_r of the interior operator rows (segment 0,
+ * device pointer, n_groups floats, not differentiated): the operator part of the loss becomes sum_r w_r * res_r^2 *
+ * lambda / len.  NULL switches the weights off. */
+int tdb200_plan_set_row_weights(tdb200_plan* plan, const float* weights_dev);
+
 /* Choose the kernel implementation: 0 = auto, 1 = SIMT fp32, 2 = tcgen05 3xTF32 (errors if unsupported). */
 int tdb200_plan_set_impl(tdb200_plan* plan, int32_t impl);
 

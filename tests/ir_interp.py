@@ -26,8 +26,9 @@ def _jets(model, pts, jet):
     return torch.stack(chans, 1)
 
 
-def evaluate_ir(ir: ProblemIR, model, dtype=torch.float64):
-    """-> (loss, loss_normalized, slot_mse list, fields per segment)"""
+def evaluate_ir(ir: ProblemIR, model, dtype=torch.float64, tol=0):
+    """-> (loss, loss_normalized, slot_mse list, fields per segment).  tol != 0: causal weights on the rows of
+    segment 0 (what Solution._causal_weights feeds the kernels; tedeous/losses.py:137-182), lambda_operator unused."""
     sums = [torch.zeros((), dtype=dtype) for _ in range(ir.n_slots)]
     fields = []
     for s in ir.segments:
@@ -56,9 +57,16 @@ def evaluate_ir(ir: ProblemIR, model, dtype=torch.float64):
         vals = torch.stack(cols, 1)
         fields.append(vals)
         res = vals - (s.targets.to(dtype) if s.targets is not None else 0.)
+        w = 1.
+        if tol != 0 and s is ir.segments[0]:
+            with torch.no_grad():
+                n_t = ir.n_t if n % ir.n_t == 0 else n
+                r2 = (vals.detach() ** 2).sum(1).reshape(n_t, -1)
+                w = torch.exp(-tol * (torch.cumsum(r2, 0) - r2)).reshape(-1)
         for ci, slot in enumerate(s.slots):
-            sums[slot] = sums[slot] + (res[:, ci] ** 2).sum()
+            sums[slot] = sums[slot] + (w * res[:, ci] ** 2).sum()
     mse = [sm / ln for sm, ln in zip(sums, ir.slot_len)]
-    loss = sum(l * m for l, m in zip(ir.slot_lambda, mse))
+    lam = [1. if (tol != 0 and i < ir.n_eq) else l for i, l in enumerate(ir.slot_lambda)]
+    loss = sum(l * m for l, m in zip(lam, mse))
     loss_n = sum(mse)
     return loss, loss_n, mse, fields

@@ -59,7 +59,7 @@ def make_mat_model(shape, dtype=torch.float32, seed=0) -> torch.Tensor:
 
 
 # --- config 1: Burgers (examples/examples_burgers/example_burgers_1d.py:35-80) ----------------------------
-def burgers(api, dtype='float32', n=100, mode='NN', layers=(2, 100, 100, 100, 1), h=0.001, n0=None):
+def burgers(api, dtype='float32', n=100, mode='NN', layers=(2, 100, 100, 100, 1), h=0.001, n0=None, tol=0):
     mu = 0.01 / math.pi
     dom = api.Domain()
     dom.variable('x', [-1, 1], n0 or n, dtype=dtype)
@@ -77,6 +77,8 @@ def burgers(api, dtype='float32', n=100, mode='NN', layers=(2, 100, 100, 100, 1)
     kw = dict(lambda_operator=1, lambda_bound=10)
     if mode == 'NN':
         kw['h'] = h
+    if tol:
+        kw['tol'] = tol                 # causal loss (tedeous/losses.py:137-182)
     return Problem(f'burgers_{mode}', dom, bc, eq, mode, list(layers), kw)
 
 
@@ -311,6 +313,8 @@ ZOO: Dict[str, Callable] = {
     'burgers_NN_cfg1': lambda api, dt: burgers(api, dt, n=100, mode='NN'),
     'burgers_NN_small': lambda api, dt: burgers(api, dt, n=24, mode='NN', layers=(2, 32, 32, 1)),
     'burgers_autograd_4h': lambda api, dt: burgers(api, dt, n=40, mode='autograd', layers=(2, 100, 100, 100, 100, 1)),
+    'burgers_autograd_causal': lambda api, dt: burgers(api, dt, n=30, mode='autograd', layers=(2, 32, 32, 1), tol=2.0),
+    'burgers_NN_causal': lambda api, dt: burgers(api, dt, n=20, mode='NN', layers=(2, 32, 32, 1), tol=2.0),
     'wave_autograd': lambda api, dt: wave(api, dt, n=40, mode='autograd'),
     'wave_NN': lambda api, dt: wave(api, dt, n=20, mode='NN', layers=(2, 32, 32, 1)),
     'kdv_autograd': lambda api, dt: kdv(api, dt, nx=30, nt=30, mode='autograd'),

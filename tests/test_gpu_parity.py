@@ -53,7 +53,8 @@ def test_loss_and_gradient_match_reference(name, cuda_default):
     gn = np.linalg.norm(g['grad'])
     assert abs(np.linalg.norm(grad) - gn) <= GRADNORM_RTOL * gn
     assert np.linalg.norm(grad - g['grad']) <= GRADVEC_RTOL * gn
-    np.testing.assert_allclose(sol.op_mse.cpu().numpy(), g['op_mse'], rtol=5e-4)
+    if not prob.compile_kwargs.get('tol', 0):      # causal loss: the slot sums are weighted, the fixture's are not
+        np.testing.assert_allclose(sol.op_mse.cpu().numpy(), g['op_mse'], rtol=5e-4)
     # NN-mode one-sided boundary stencils are literal fp32 differences (3u - 4u + u) / 2h: cancellation noise
     np.testing.assert_allclose(sol.bval_mse.cpu().numpy(), g['bval_mse'], rtol=1e-3 if prob.mode == 'NN' else 1e-4)
     assert sol.bval_keys == [str(k) for k in g['bval_keys']]
@@ -107,11 +108,12 @@ def test_tensor_core_path_matches_reference(name, cuda_default):
     gn = np.linalg.norm(g['grad'])
     assert abs(np.linalg.norm(grad) - gn) <= GRADNORM_RTOL * gn
     assert np.linalg.norm(grad - g['grad']) <= GRADVEC_RTOL * gn
-    np.testing.assert_allclose(sol.op_mse.cpu().numpy(), g['op_mse'], rtol=5e-4)
+    if not prob.compile_kwargs.get('tol', 0):
+        np.testing.assert_allclose(sol.op_mse.cpu().numpy(), g['op_mse'], rtol=5e-4)
     # and against the SIMT fp32 kernel on the same inputs
     prob2, net2, sol2 = fused(name, g['weights'], impl=1)
-    ref = sol2._plan.loss_grad().double()
-    out = sol._plan.loss_grad().double()
+    ref = sol2._run_plan()[0].double()            # (_run_plan refreshes the causal row weights when tol != 0)
+    out = sol._run_plan()[0].double()
     assert float(out[0]) == pytest.approx(float(ref[0]), rel=2e-6)
     k = 2 + sol._n_slots
     assert float((out[k:] - ref[k:]).norm()) <= 2e-5 * float(ref[k:].norm())

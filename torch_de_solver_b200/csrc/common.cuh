@@ -49,6 +49,7 @@ struct JetArgs {
   float* scratch;                      // [gridDim.x][scratch_per_cta] saved activations (L2 resident)
   long long scratch_per_cta;
   float* fields;                       // optional per-row operator values
+  const float* row_weight;             // optional per-row loss weights of segment 0 (causal loss, losses.py:137-182)
   int do_grad;
   long long* dbg;                      // optional [gridDim.x][16] phase cycle counters (TDB200_TC_TIMING=1)
 };

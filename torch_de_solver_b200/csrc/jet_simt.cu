@@ -375,8 +375,9 @@ __global__ void __launch_bounds__(kThreads, 1) jet_simt_kernel(const JetArgs a) 
         const float tgt = sg.tgt_off >= 0 ? __ldg(a.targets + sg.tgt_off + row * ncols + col) : 0.f;
         const float res = val - tgt;
         const int slot = sg.col_slot[col];
-        atomicAdd(&sm.lossS[slot], (double)res * (double)res);
-        sm.rS[col * G + g] = 2.f * __ldg(a.slot_scale + slot) * res;
+        const float rw = (a.row_weight && seg_i == 0) ? __ldg(a.row_weight + row) : 1.f;   // causal-loss weight (no grad)
+        atomicAdd(&sm.lossS[slot], (double)rw * (double)res * (double)res);
+        sm.rS[col * G + g] = 2.f * __ldg(a.slot_scale + slot) * rw * res;
       }
       if (a.do_grad) {
         for (int col = 0; col < ncols; ++col) {

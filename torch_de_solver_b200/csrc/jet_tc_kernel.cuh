@@ -602,9 +602,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
         if (a.fields) a.fields[sg.field_off + row * ncols + col] = val;
         const float tgt = sg.tgt_off >= 0 ? __ldg(a.targets + sg.tgt_off + row * ncols + col) : 0.f;
         const float res = val - tgt;
-        sm.lossT[p * TDB200_MAX_COLS + col] += (double)res * (double)res;
+        const float rw = a.row_weight ? __ldg(a.row_weight + row) : 1.f;        // causal-loss weight (no grad)
+        sm.lossT[p * TDB200_MAX_COLS + col] += (double)rw * (double)res * (double)res;
         if (!a.do_grad) continue;
-        const float seed = 2.f * sm.scaleS[sg.col_slot[col]] * res;
+        const float seed = 2.f * sm.scaleS[sg.col_slot[col]] * rw * res;
         for (int t = tb; t < te; ++t) {
           const int4 r = sm.recS[t];
           const float cf = r.y == 0 ? __int_as_float(r.x) : r.y == 1 ? __ldg(a.coeffs + r.x + row) : a.arena[a.n_net_params + r.x];

@@ -506,6 +506,8 @@ def lower_problem(mode: str, grid: torch.Tensor, prepared_operator: List[dict], 
     ir = ProblemIR(mode, d, net, segments, n_eq, bnd_types,
                    [n_interior] * n_eq + [max_len] * len(bnd_types), lam_op + lam_b, n_interior)
     ir.type_len = [type_len[t] for t in bnd_types]
+    # time slices of the causal loss: unique values of column 0 of the interior rows (tedeous/solution.py:51-57)
+    ir.n_t = int(torch.unique(pts[:, 0]).numel())
     for s in ir.segments:
         s.n_groups_global = s.n_groups
     if shard[1] > 1:

@@ -76,6 +76,14 @@ class FusedPlan:
         _native.check(self.lib.tdb200_plan_set_slots(self.handle, _native.np_ptr(lam), _native.np_ptr(ln)),
                       'tdb200_plan_set_slots')
 
+    def set_row_weights(self, w: Optional[torch.Tensor]):
+        """Per-row loss weights of the interior operator rows (causal loss); None switches them off."""
+        self._row_w = None if w is None else w.detach().to(self.device, torch.float32).contiguous()
+        if self._row_w is not None and self._row_w.numel() != self.ir.segments[0].n_groups:
+            raise ValueError('one weight per interior operator row expected')
+        _native.check(self.lib.tdb200_plan_set_row_weights(
+            self.handle, None if self._row_w is None else self._row_w.data_ptr()), 'tdb200_plan_set_row_weights')
+
     def set_impl(self, impl: int):
         _native.check(self.lib.tdb200_plan_set_impl(self.handle, impl), 'tdb200_plan_set_impl')
         self.launches_per_call = int(self.lib.tdb200_plan_launches_per_call(self.handle))
@@ -144,8 +152,10 @@ class Solution:
                  impl: int = 0):
         if weak_form not in (None, []):
             raise UnsupportedProblem('weak-form loss is not implemented by the fused path (SURVEY 8 a11)')
-        if tol != 0:
-            raise UnsupportedProblem('causal loss (tol != 0) is not implemented by the fused path yet (SURVEY 8 a10)')
+        if tol != 0 and mode == 'mat':
+            raise UnsupportedProblem('causal loss (tol != 0) is implemented for modes NN / autograd only (SURVEY 8 a10)')
+        if tol != 0 and shard is not None and shard[1] > 1:
+            raise UnsupportedProblem('causal loss needs the prefix sums of all time slices: not sharded over ranks')
         if batch_size is not None and mode != 'NN':
             raise UnsupportedProblem('mini-batching is not implemented by the fused path; shard points over '
                                      'GPUs instead')
@@ -222,15 +232,34 @@ class Solution:
         """-> (out [2 + n_slots (+ n_params)], flat gradient)."""
         if self.mode == 'mat':
             return self._plan.loss_grad_raw(self.model)
+        if self.tol != 0:
+            self._causal_weights()
         out = self._plan.loss_grad()
         if self._shard[1] > 1:
             import torch.distributed as dist
             dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self._pg)
         return out, out[2 + self._n_slots:]
 
+    def _causal_weights(self):
+        """Causal loss (tedeous/losses.py:137-182): w[t, j] = exp(-tol * sum_{s < t} res[s, j]) with
+        res = sum_eq op^2 reshaped to [n_t, N / n_t] (column 0 of the grid is the slowest coordinate), not
+        differentiated.  One forward-only launch yields op; the weights then enter the fused loss + gradient launch
+        as per-row factors (`tdb200_plan_set_row_weights`); lambda_operator is not used by this loss."""
+        self._plan.set_row_weights(None)
+        fields, _ = self._plan.eval_fields()
+        seg = self._ir.segments[0]
+        n, ncols = seg.n_groups, len(seg.cols)
+        op = fields[:n * ncols].reshape(n, ncols)
+        n_t = self._ir.n_t
+        if n % n_t:
+            n_t = n                                            # the reference's fallback (losses.py:162-165)
+        res = (op * op).sum(1).reshape(n_t, -1)
+        w = torch.exp(-float(self.tol) * (torch.cumsum(res, 0) - res))
+        self._plan.set_row_weights(w.reshape(-1))
+
     def _sync_lambdas(self):
         n_eq = self._n_slots - len(self.bval_keys)
-        lam_op = lambda_prepare(torch.empty(1, n_eq), self.lambda_operator).reshape(-1).tolist()
+        lam_op = lambda_prepare(torch.empty(1, n_eq), 1 if self.tol != 0 else self.lambda_operator).reshape(-1).tolist()
         lam_b = lambda_prepare(torch.empty(1, len(self.bval_keys)), self.lambda_bound).reshape(-1).tolist()
         lam = [float(x) for x in lam_op + lam_b]
         if len(lam) != self._n_slots:
