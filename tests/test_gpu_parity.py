@@ -230,7 +230,7 @@ def test_mat_large_grid_properties(n, amp, gtol, cuda_default):
 @pytest.mark.parametrize('case', ['poisson_p2_64x64', 'poisson_p2_40x132', 'poisson_p2_200x260', 'poisson_p3_72x136',
                                   'heat_p2_96x128', 'heat_p2_33x260'])
 def test_mat_specialised_kernels_agree(case, cuda_default, monkeypatch):
-    """The persistent TMA kernel, the vectorised cross-stencil kernel, the register-tap kernel and the generic tiled kernel evaluate the same
+    """The register-marching kernel, the persistent TMA kernel, the vectorised cross-stencil kernel, the register-tap kernel and the generic tiled kernel evaluate the same
     loss and gradient (interior tiles, all four kinds of boundary tiles, partial tiles)."""
     kind, p, shape = case.split('_')
     n0, n1 = (int(x) for x in shape.split('x'))
@@ -241,22 +241,28 @@ def test_mat_specialised_kernels_agree(case, cuda_default, monkeypatch):
         prob = problems.heat_mat(tdb, 'float32', n=n0 - 1, nt=n1 - 1, derivative_points=dp)
     u = torch.as_tensor(np.random.default_rng(3).random(prob.mat_shape, dtype=np.float32)).to('cuda:0').contiguous()
     res = {}
-    for tag, env in (('cross-tma', None), ('cross-vec4', 'TDB200_MAT_NO_TMA'), ('register-tap', 'TDB200_MAT_NO_CROSS'),
-                     ('generic', 'TDB200_MAT_NO_LIN1')):
-        for e in ('TDB200_MAT_NO_TMA', 'TDB200_MAT_NO_CROSS', 'TDB200_MAT_NO_LIN1'):
+    all_env = ('TDB200_MAT_NO_MARCH', 'TDB200_MAT_NO_TMA', 'TDB200_MAT_NO_CROSS', 'TDB200_MAT_NO_LIN1')
+    for tag, envs in (('cross-march', ()), ('cross-tma', all_env[:1]), ('cross-vec4', all_env[:2]),
+                      ('register-tap', all_env[2:3]), ('generic', all_env[3:])):
+        for e in all_env:
             monkeypatch.delenv(e, raising=False)
-        if env:
-            monkeypatch.setenv(env, '1')
+        for e in envs:
+            monkeypatch.setenv(e, '1')
         model = tdb.Model(u.clone(), prob.domain, prob.equation, prob.conditions)
         model.compile('mat', **prob.compile_kwargs)
         plan = model.solution_cls._plan
-        assert plan.kernel_kind == ('generic' if (dp == 3 and tag == 'register-tap') else tag)   # p = 3: > 16 taps
+        expect = tag
+        if dp == 3 and tag == 'register-tap':
+            expect = 'generic'                               # p = 3: > 16 taps
+        if dp == 3 and tag == 'cross-march':
+            expect = 'cross-tma'                             # p = 3: reach 4 keeps too many rows in registers
+        assert plan.kernel_kind == expect
         out, grad = plan.loss_grad_raw(u)
         out2, grad2 = plan.loss_grad_raw(u)                  # the fused finalize step re-arms itself
         assert torch.equal(grad, grad2) and float(out[0]) == pytest.approx(float(out2[0]), rel=1e-6)
         res[tag] = (out.double().cpu().numpy(), grad.double().cpu().numpy())
     ref_out, ref_grad = res['generic']
-    for tag in ('cross-tma', 'cross-vec4', 'register-tap'):
+    for tag in ('cross-march', 'cross-tma', 'cross-vec4', 'register-tap'):
         out, grad = res[tag]
         np.testing.assert_allclose(out, ref_out, rtol=2e-5)
         assert np.abs(grad - ref_grad).max() <= 2e-4 * np.abs(ref_grad).max(), tag

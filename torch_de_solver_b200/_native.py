@@ -34,6 +34,7 @@ EXPORTS = [
     'tdb200_loss_grad', 'tdb200_eval_fields', 'tdb200_plan_destroy',
     'tdb200_mat_plan_create', 'tdb200_mat_plan_set_coeffs', 'tdb200_mat_plan_set_bcs', 'tdb200_mat_loss_grad', 'tdb200_mat_eval_fields',
     'tdb200_mat_plan_out_size', 'tdb200_mat_plan_launches_per_call', 'tdb200_mat_plan_kernel_kind', 'tdb200_mat_plan_set_row_window',
+    'tdb200_mat_plan_set_timing', 'tdb200_mat_plan_stencil_ms',
     'tdb200_mat_plan_destroy',
     'tdb200_last_error', 'tdb200_version',
 ]
@@ -64,6 +65,8 @@ def load():
     lib.tdb200_plan_launches_per_call.argtypes = [vp]
     lib.tdb200_mat_plan_launches_per_call.argtypes = [vp]
     lib.tdb200_mat_plan_kernel_kind.argtypes = [vp]
+    lib.tdb200_mat_plan_set_timing.argtypes = [vp, i32]
+    lib.tdb200_mat_plan_stencil_ms.argtypes = [vp, vp]
     lib.tdb200_mat_plan_set_row_window.argtypes = [vp, i32, i32]
     lib.tdb200_loss_grad.argtypes = [vp, vp, vp, vp]
     lib.tdb200_eval_fields.argtypes = [vp, vp, vp, vp, vp]

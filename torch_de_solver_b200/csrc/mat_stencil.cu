@@ -769,6 +769,326 @@ static bool make_map_2d(CUtensorMap* map, const float* ptr, int n0, int n1, int 
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// ---- register-marching cross-stencil kernel ---------------------------------------------------------------
+// BASELINE config 4 (Poisson 4096 x 4096), second generation.  No shared-memory tiles, no block barriers, no 2-D halo:
+// every WARP owns a column strip (32 lanes x float4 = 128 loaded columns, the inner 28 lanes = 112 columns are its
+// output) and marches down a chunk of rows.  The last 2 HY + 1 + P rows of u, the last 2 HY + 1 rows of residual seeds
+// and the forcing rows in flight live in REGISTERS (rings indexed at compile time: the row loop is unrolled by the
+// ring length); x-neighbours come from the two adjacent lanes by warp shuffles.  Per row and thread: two 16-byte
+// global loads (u, f) issued P rows ahead of their use (the HBM stream is kept full by register prefetch rather than
+// by occupancy), <= 8 shuffles, ~45 FMAs, one 16-byte store.  Seeds of cells whose stencil rows are special (one-sided
+// rows near the domain edge) are zero here; `mat_march_edge_kernel` adds their loss and gradient contributions.
+constexpr int kMwWarps = 8, kMwThreads = kMwWarps * 32;
+constexpr int kMwOutLanes = 28, kMwOutW = 4 * kMwOutLanes;   // lanes 2..29 own output columns
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// r[i] += sum_dx wx[dx] * row[x_i + dx] (REV: row[x_i - dx]) for the 4 cells of a thread; neighbours by shuffle
+template <int H, unsigned M, bool REV>
+__device__ __forceinline__ void mw_xtaps(const float4 c, const float* wx, float* r) {
+  if (M == 0) return;
+  float w[12];
+  w[4] = c.x; w[5] = c.y; w[6] = c.z; w[7] = c.w;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    bool need_l = false, need_r = false;
+#pragma unroll
+    for (int dx = -H; dx <= H; ++dx) {
+      if (dx == 0 || !(M & (1u << (dx + H)))) continue;
+      const int d = REV ? -dx : dx;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (4 + i + d == e) need_l = true;
+        if (4 + i + d == 8 + e) need_r = true;
+      }
+    }
+    w[e] = need_l ? __shfl_up_sync(kFullMask, w[4 + e], 1) : 0.f;
+    w[8 + e] = need_r ? __shfl_down_sync(kFullMask, w[4 + e], 1) : 0.f;
+  }
+#pragma unroll
+  for (int dx = -H; dx <= H; ++dx) {
+    if (dx == 0 || !(M & (1u << (dx + H)))) continue;
+    const float wgt = wx[dx + H];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = fmaf(wgt, w[4 + i + (REV ? -dx : dx)], r[i]);
+  }
+}
+
+// Cells near the domain edge.  The FRAME = cells within edge + reach of the domain edge, enumerated band by band (top
+// and bottom rows at full width, then the left / right columns of the rows between).  Phase A (the leading CTAs of the
+// mat_march_kernel launch): residual of every frame cell whose stencil rows are special (not "regular"), evaluated from
+// u with the banded operators -> loss partial + compact seed buffer.  Phase B (mat_march_edge_kernel, after the march
+// launch, before the boundary rows): every frame cell gathers coef(row of the special neighbour, this cell) * seed over
+// its special in-domain neighbours and adds it to the gradient the march kernel wrote (regular rows only).  Each
+// gradient cell has one owner: bit-reproducible.  All fields of a march-kernel plan have half_width <= 2.
+constexpr int kMwMaxHw = 2;
+struct MwFrame {
+  int n0, n1, zy, zx, top, bot, mid, left, right;
+  int n_band, total;                                         // < 2^31: the frame is a few rows / columns wide
+  __device__ __forceinline__ MwFrame(const MatArgs& a, int zy3, int zx3) {
+    n0 = a.n0; n1 = a.n1; zy = a.edge_y; zx = a.edge_x;
+    top = min(zy3, n0); bot = min(zy3, n0 - top); mid = n0 - top - bot;
+    left = min(zx3, n1); right = min(zx3, n1 - left);
+    n_band = (top + bot) * n1; total = n_band + mid * (left + right);
+  }
+  __device__ __forceinline__ bool regular(int gy, int gx) const { return gy >= zy && gy < n0 - zy && gx >= zx && gx < n1 - zx; }
+  __device__ __forceinline__ void cell(int idx, int& gy, int& gx) const {
+    if (idx < n_band) {
+      const int i = idx / n1;
+      gx = idx - i * n1;
+      gy = i < top ? i : n0 - bot + (i - top);
+    } else {
+      const int k = idx - n_band;
+      const int i = k / (left + right), c = k - i * (left + right);
+      gy = top + i;
+      gx = c < left ? c : n1 - right + (c - left);
+    }
+  }
+  __device__ __forceinline__ int index(int gy, int gx) const {              // (gy, gx) must be a frame cell
+    if (gy < top) return gy * n1 + gx;
+    if (gy >= n0 - bot) return (top + gy - (n0 - bot)) * n1 + gx;
+    return n_band + (gy - top) * (left + right) + (gx < left ? gx : left + gx - (n1 - right));
+  }
+};
+
+__device__ __forceinline__ float mw_edge_residual(const MatArgs& a, int gy, int gx) {
+  const int n0 = a.n0, n1 = a.n1;
+  float res = a.l1_fconst;
+  if (a.l1_fbuf[0]) res += __ldg(a.l1_fbuf[0] + (size_t)gy * n1 + gx);
+#pragma unroll 2
+  for (int t = 0; t < a.n_lin; ++t) {
+    const tdb200_mat_field& f = a.fld[a.lin_q[t]];
+    float v;
+    if (f.order == 0) {
+      v = __ldg(a.u + (size_t)gy * n1 + gx);
+    } else {
+      float uv[2 * kMwMaxHw + 1], cv[2 * kMwMaxHw + 1];
+#pragma unroll
+      for (int m = -kMwMaxHw; m <= kMwMaxHw; ++m) {        // independent loads first
+        const int yy = f.axis == 0 ? gy + m : gy, xx = f.axis == 0 ? gx : gx + m;
+        const bool ok = m >= -f.half_width && m <= f.half_width && yy >= 0 && yy < n0 && xx >= 0 && xx < n1;
+        uv[m + kMwMaxHw] = ok ? __ldg(a.u + (size_t)yy * n1 + xx) : 0.f;
+        cv[m + kMwMaxHw] = ok ? band_coef(a.band, f, f.axis == 0 ? n0 : n1, f.axis == 0 ? gy : gx, m) : 0.f;
+      }
+      v = 0.f;
+#pragma unroll
+      for (int m = 0; m <= 2 * kMwMaxHw; ++m) v = fmaf(cv[m], uv[m], v);
+    }
+    res = fmaf(a.lin_c[t], v, res);
+  }
+  return res;
+}
+
+// phase A, run by the first `n_blocks` CTAs of the march launch
+__device__ __forceinline__ double mw_edge_seeds(const MatArgs& a, int zy3, int zx3, float* __restrict__ es, int block, int n_blocks) {
+  const MwFrame fr(a, zy3, zx3);
+  const float scale2 = 2.f * a.eq_scale[0];
+  double dacc = 0.0;
+  for (int idx = block * (int)blockDim.x + (int)threadIdx.x; idx < fr.total; idx += n_blocks * (int)blockDim.x) {
+    int gy, gx;
+    fr.cell(idx, gy, gx);
+    float seed = 0.f;
+    if (!fr.regular(gy, gx)) {
+      const float res = mw_edge_residual(a, gy, gx);
+      if (gy >= a.row_lo && gy < a.row_hi) dacc += (double)res * (double)res;
+      seed = scale2 * res;
+    }
+    es[idx] = seed;
+  }
+  return dacc;
+}
+
+// phase B
+__global__ void __launch_bounds__(128) mat_march_edge_kernel(const MatArgs a, const int zy3, const int zx3,
+                                                             const float* __restrict__ es) {
+  const MwFrame fr(a, zy3, zx3);
+  const int n0 = a.n0, n1 = a.n1;
+  for (int idx = (int)(blockIdx.x * blockDim.x + threadIdx.x); idx < fr.total; idx += (int)(gridDim.x * blockDim.x)) {
+    int gy, gx;
+    fr.cell(idx, gy, gx);
+    float g = 0.f;
+#pragma unroll 2
+    for (int t = 0; t < a.n_lin; ++t) {
+      const tdb200_mat_field& f = a.fld[a.lin_q[t]];
+      float sacc = 0.f;
+      if (f.order == 0) {
+        sacc = es[idx];                                      // zero for regular cells
+      } else {
+        float sv[2 * kMwMaxHw + 1], cv[2 * kMwMaxHw + 1];
+#pragma unroll
+        for (int m = -kMwMaxHw; m <= kMwMaxHw; ++m) {
+          const int yy = f.axis == 0 ? gy + m : gy, xx = f.axis == 0 ? gx : gx + m;
+          const bool ok = m >= -f.half_width && m <= f.half_width && yy >= 0 && yy < n0 && xx >= 0 && xx < n1 &&
+                          !fr.regular(yy, xx);
+          sv[m + kMwMaxHw] = ok ? __ldg(es + fr.index(yy, xx)) : 0.f;
+          cv[m + kMwMaxHw] = ok ? band_coef(a.band, f, f.axis == 0 ? n0 : n1, f.axis == 0 ? yy : xx, -m) : 0.f;
+        }
+#pragma unroll
+        for (int m = 0; m <= 2 * kMwMaxHw; ++m) sacc = fmaf(cv[m], sv[m], sacc);
+      }
+      g = fmaf(a.lin_c[t], sacc, g);
+    }
+    if (g != 0.f) a.grad[(size_t)gy * n1 + gx] += g;
+  }
+}
+
+template <int HY, int HX, unsigned MY, unsigned MX, int P>
+__global__ void __launch_bounds__(kMwThreads, 2) mat_march_kernel(const MatArgs a, const int ch, const int n_strips,
+                                                                  const int n_items, const int n_edge_blocks,
+                                                                  float* __restrict__ edge_seeds) {
+  constexpr int R = 2 * HY + 1 + P;                          // ring length = unroll factor of the row loop
+  __shared__ double red[kMwWarps];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = a.n0, n1 = a.n1;
+  const int item = (int)blockIdx.x * kMwWarps + warp;
+  const int first_edge_block = (int)gridDim.x - n_edge_blocks;
+  double dacc = 0.0;
+  if ((int)blockIdx.x >= first_edge_block) {                 // phase A of the edge treatment: the trailing CTAs fill the
+    dacc = mw_edge_seeds(a, a.edge_y + HY, a.edge_x + HX, edge_seeds, (int)blockIdx.x - first_edge_block, n_edge_blocks);   // tail
+  } else if (item < n_items) {                               // warp-uniform
+    const int chunk = item / n_strips, strip = item - chunk * n_strips;
+    const int y0 = chunk * ch, y1 = min(y0 + ch, n0);
+    const int x = strip * kMwOutW - 8 + 4 * lane;            // column of this thread's first element
+    const bool col_ok = x >= 0 && x < n1;                    // n1 % 4 == 0: the float4 is entirely inside or outside
+    const bool own = col_ok && lane >= 2 && lane < 2 + kMwOutLanes;
+    const bool f_ok = col_ok && lane >= 1 && lane <= 30 && a.l1_fbuf[0] != nullptr;
+    const bool do_grad = a.grad != nullptr;
+    const int zy = a.edge_y, zx = a.edge_x;
+    const float scale2 = 2.f * a.eq_scale[0], fc0 = a.l1_fconst, wc = a.cx_wc;
+    float wy[2 * HY + 1], wx[2 * HX + 1], sm2[4], lm[4];
+#pragma unroll
+    for (int i = 0; i <= 2 * HY; ++i) wy[i] = a.cx_wy[i];
+#pragma unroll
+    for (int i = 0; i <= 2 * HX; ++i) wx[i] = a.cx_wx[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const bool reg = x + i >= zx && x + i < n1 - zx;       // regular column of the operators
+      sm2[i] = reg ? scale2 : 0.f;
+      lm[i] = (reg && own) ? 1.f : 0.f;
+    }
+    const int loss_lo = max(y0, a.row_lo), loss_hi = min(y1, a.row_hi);
+    const int ybase = y0 - 2 * HY;                           // first row of u this warp loads
+    const int load_hi = min(y1 + 2 * HY, n0), f_lo = max(y0 - HY, 0), f_hi = min(y1 + HY, n0);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 u[R], s[R], fr[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) u[i] = s[i] = fr[i] = zero4;
+    const float* pu = a.u + (ptrdiff_t)ybase * n1 + x;                      // u row loaded at step j: ybase + j
+    const float* pf = a.l1_fbuf[0] + (ptrdiff_t)(ybase - HY) * n1 + x;      // forcing row loaded at step j: ybase - HY + j
+    float* pg = a.grad + (ptrdiff_t)(ybase - P - 2 * HY) * n1 + x;          // gradient row stored at step j
+    const int steps = (y1 - y0) + 4 * HY + P;
+    for (int jb = 0; jb < steps; jb += R) {
+      float lacc = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < R; ++jj) {
+        const int j = jb + jj;
+        // (1) issue the loads of this step; they are consumed P steps from now
+        {
+          const int yl = ybase + j, yf = yl - HY;
+          u[jj] = (col_ok && yl >= 0 && yl < load_hi) ? __ldg(reinterpret_cast<const float4*>(pu)) : zero4;
+          fr[jj] = (f_ok && yf >= f_lo && yf < f_hi) ? __ldg(reinterpret_cast<const float4*>(pf)) : zero4;
+          pu += n1; pf += n1;
+        }
+        // (2) residual row yr: centre = the u row loaded at step j - P - HY, forcing loaded at step j - P
+        {
+          const int yr = ybase + j - P - HY;
+          const float4 c = u[(jj + 2 * R - P - HY) % R], fv = fr[(jj + R - P) % R];
+          float r[4] = {fc0 + fv.x, fc0 + fv.y, fc0 + fv.z, fc0 + fv.w};
+          r[0] = fmaf(wc, c.x, r[0]); r[1] = fmaf(wc, c.y, r[1]); r[2] = fmaf(wc, c.z, r[2]); r[3] = fmaf(wc, c.w, r[3]);
+#pragma unroll
+          for (int dy = -HY; dy <= HY; ++dy) {
+            if (dy == 0 || !(MY & (1u << (dy + HY)))) continue;
+            const float wgt = wy[dy + HY];
+            const float4 v = u[(jj + 2 * R - P - HY + dy) % R];
+            r[0] = fmaf(wgt, v.x, r[0]); r[1] = fmaf(wgt, v.y, r[1]); r[2] = fmaf(wgt, v.z, r[2]); r[3] = fmaf(wgt, v.w, r[3]);
+          }
+          mw_xtaps<HX, MX, false>(c, wx, r);
+          const bool rowreg = yr >= zy && yr < n0 - zy;      // regular row of the operators (warp-uniform)
+          if (rowreg && yr >= loss_lo && yr < loss_hi) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) lacc = fmaf(lm[i] * r[i], r[i], lacc);
+          }
+          s[jj] = rowreg ? make_float4(sm2[0] * r[0], sm2[1] * r[1], sm2[2] * r[2], sm2[3] * r[3]) : zero4;
+        }
+        // (3) gradient row yg = yr - HY: transposed stencil on the seed rows formed at steps j - 2 HY .. j
+        if (do_grad) {
+          const int yg = ybase + j - P - 2 * HY;
+          const float4 c = s[(jj + R - HY) % R];
+          float g[4] = {wc * c.x, wc * c.y, wc * c.z, wc * c.w};
+#pragma unroll
+          for (int dy = -HY; dy <= HY; ++dy) {
+            if (dy == 0 || !(MY & (1u << (dy + HY)))) continue;
+            const float wgt = wy[dy + HY];
+            const float4 v = s[(jj + 2 * R - HY - dy) % R];   // seed row yg - dy
+            g[0] = fmaf(wgt, v.x, g[0]); g[1] = fmaf(wgt, v.y, g[1]); g[2] = fmaf(wgt, v.z, g[2]); g[3] = fmaf(wgt, v.w, g[3]);
+          }
+          mw_xtaps<HX, MX, true>(c, wx, g);
+          if (own && yg >= y0 && yg < y1) *reinterpret_cast<float4*>(pg) = make_float4(g[0], g[1], g[2], g[3]);
+          pg += n1;
+        }
+      }
+      dacc += (double)lacc;
+    }
+  }
+  for (int o = 16; o; o >>= 1) dacc += __shfl_xor_sync(kFullMask, dacc, o);
+  if (lane == 0) red[warp] = dacc;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kMwWarps; ++w) t += red[w];
+    a.part_loss[blockIdx.x] = t;
+  }
+}
+
+constexpr int kMwEdgeBlocks = 148;                           // phase A CTAs (256 threads) = phase B CTAs x 2 (128 threads)
+// rows per chunk: every SM gets ~16 warps in a single wave (the y-halo of a chunk costs 4 HY extra row loads)
+static int mat_march_chunk(const MatArgs& a, int n_sms) {
+  const int n_strips = (a.n1 + kMwOutW - 1) / kMwOutW;
+  const long long slots = (long long)n_sms * 2 * kMwWarps;
+  long long ch = ((long long)a.n0 * n_strips + slots - 1) / slots;
+  ch = (ch + 7) / 8 * 8;
+  if (ch < 32) ch = 32;
+  return (int)ch;
+}
+static int mat_march_ctas(const MatArgs& a, int n_sms) {         // loss partials written by the march launch
+  const int ch = mat_march_chunk(a, n_sms), n_strips = (a.n1 + kMwOutW - 1) / kMwOutW;
+  const int n_items = n_strips * ((a.n0 + ch - 1) / ch);
+  return kMwEdgeBlocks + (n_items + kMwWarps - 1) / kMwWarps;
+}
+static size_t mat_march_frame_cells(const MatArgs& a, int hy, int hx) {
+  const int zy3 = a.edge_y + hy, zx3 = a.edge_x + hx;
+  const int top = zy3 < a.n0 ? zy3 : a.n0, bot = zy3 < a.n0 - top ? zy3 : a.n0 - top, mid = a.n0 - top - bot;
+  const int left = zx3 < a.n1 ? zx3 : a.n1, right = zx3 < a.n1 - left ? zx3 : a.n1 - left;
+  return (size_t)(top + bot) * a.n1 + (size_t)mid * (left + right);
+}
+template <int HY, int HX, unsigned MY, unsigned MX>
+static cudaError_t launch_mat_march_t(const MatArgs& a, int n_sms, float* edge_seeds, cudaEvent_t after_stencil, cudaStream_t s) {
+  const int ch = mat_march_chunk(a, n_sms), n_strips = (a.n1 + kMwOutW - 1) / kMwOutW;
+  const int n_items = n_strips * ((a.n0 + ch - 1) / ch);
+  const int grid = kMwEdgeBlocks + (n_items + kMwWarps - 1) / kMwWarps;
+  mat_march_kernel<HY, HX, MY, MX, 3><<<grid, kMwThreads, 0, s>>>(a, ch, n_strips, n_items, kMwEdgeBlocks, edge_seeds);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && after_stencil) e = cudaEventRecord(after_stencil, s);
+  if (e != cudaSuccess || !a.grad) return e;
+  mat_march_edge_kernel<<<2 * kMwEdgeBlocks, 128, 0, s>>>(a, a.edge_y + HY, a.edge_x + HX, edge_seeds);
+  return cudaGetLastError();
+}
+// instantiated for the cross shapes with reach <= 2 (wider stencils keep too many rows in registers)
+#define TDB_MARCH_SHAPES(X) \
+  X(2, 2, 0x11u, 0x11u) X(1, 2, 0x5u, 0x11u) X(2, 1, 0x11u, 0x5u) X(1, 1, 0x5u, 0x5u) X(2, 0, 0x11u, 0x0u) X(0, 2, 0x0u, 0x11u)
+static bool mat_march_supported(int hy, int hx, unsigned my, unsigned mx) {
+#define X(A, B, C, D) if (hy == A && hx == B && (my & ~C) == 0 && (mx & ~D) == 0) return true;
+  TDB_MARCH_SHAPES(X)
+#undef X
+  return false;
+}
+static cudaError_t launch_mat_march(const MatArgs& a, int hy, int hx, unsigned my, unsigned mx, int n_sms, float* edge_seeds,
+                                    cudaEvent_t after_stencil, cudaStream_t s) {
+#define X(A, B, C, D) if (hy == A && hx == B && (my & ~C) == 0 && (mx & ~D) == 0) return launch_mat_march_t<A, B, C, D>(a, n_sms, edge_seeds, after_stencil, s);
+  TDB_MARCH_SHAPES(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
 __global__ void __launch_bounds__(kMatThreads) mat_residual_adjoint_kernel(const MatArgs a) {
   extern __shared__ __align__(16) float sm[];
   const int hy = a.hy, hx = a.hx;
@@ -1201,6 +1521,10 @@ struct tdb200_mat_plan {
   unsigned cx_my = 0, cx_mx = 0;
   bool cross = false;
   bool tma = false;                        // persistent TMA variant of the cross kernel (single forcing buffer)
+  bool march = false;                      // register-marching variant (reach <= 2, single forcing buffer)
+  float* d_edge_seed = nullptr;            // march kernel: compact seeds of the frame cells with special stencil rows
+  bool timing = false;                     // measurement aid: CUDA events around the stencil kernel launch
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   CUtensorMap map_u{}, map_f{};
   const float* map_u_ptr = nullptr;
   const float* map_f_ptr = nullptr;
@@ -1340,6 +1664,8 @@ int tdb200_mat_plan_create(const tdb200_mat_desc* desc, const tdb200_mat_field* 
       p->cross = tdb::mat_cross_supported(hy, hx, my, mx) && desc->n1 % 4 == 0 && !getenv("TDB200_MAT_NO_CROSS");
       if (!p->cross && !p->l1_regs) a.lin1 = 0;           // neither specialised kernel applies
       p->tma = p->cross && n_fbuf <= 1 && !getenv("TDB200_MAT_NO_TMA");
+      p->march = p->cross && n_fbuf <= 1 && tdb::mat_march_supported(hy, hx, my, mx) && !getenv("TDB200_MAT_NO_MARCH") &&
+                 (long long)(desc->n0 + 64) * desc->n1 < (1ll << 31);      // the kernel uses 32-bit element offsets
       cudaDeviceGetAttribute(&p->n_sms, cudaDevAttrMultiProcessorCount, device);
     }
     a.edge_y = ey; a.edge_x = ex;
@@ -1357,7 +1683,12 @@ int tdb200_mat_plan_create(const tdb200_mat_desc* desc, const tdb200_mat_field* 
   MCU(cudaMalloc(&p->d_factors, sizeof(tdb200_factor) * (n_factors > 0 ? n_factors : 1)));
   if (n_factors) MCU(cudaMemcpy(p->d_factors, factors, sizeof(tdb200_factor) * n_factors, cudaMemcpyHostToDevice));
   {
-    const int l1 = a.lin1 ? tdb::mat_lin1_ctas(a) : 0;   // (the cross kernel uses the same tiling)
+    int l1 = a.lin1 ? tdb::mat_lin1_ctas(a) : 0;         // (the cross kernel uses the same tiling)
+    if (p->march) {
+      const int m = tdb::mat_march_ctas(a, p->n_sms);
+      l1 = m > l1 ? m : l1;
+      MCU(cudaMalloc(&p->d_edge_seed, sizeof(float) * (tdb::mat_march_frame_cells(a, hy, hx) + 1)));
+    }
     MCU(cudaMalloc(&p->d_part_loss, sizeof(double) * (size_t)(p->n_ctas > l1 ? p->n_ctas : l1) * desc->n_eq));
   }
   a.band = p->d_band; a.terms = p->d_terms; a.factors = p->d_factors; a.part_loss = p->d_part_loss;
@@ -1429,13 +1760,15 @@ static int mat_run(tdb200_mat_plan* p, const float* u, float* grad, float* op_ou
   tdb::MatArgs a = p->args;
   a.u = u; a.grad = grad; a.op_out = op_out; a.tile_ctr = p->d_ticket + 1;
   int n_ctas = p->n_ctas;
+  if (p->timing) MCU(cudaEventRecord(p->ev0, s));
+  bool ev1_done = false;
   if (a.lin1 && !op_out) {
     // specialised kernels (loss + gradient, or loss only); per-cell operator values go through the generic kernel
     for (int i = 0; i < 2; ++i) a.l1_fbuf[i] = i < p->l1_n_fbuf ? a.coeffs + p->l1_fbuf_off[i] : nullptr;
     auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     const bool vec_ok = aligned16(u) && aligned16(grad) && aligned16(a.l1_fbuf[0]) && aligned16(a.l1_fbuf[1]);
     if (p->cross && !vec_ok && !p->l1_regs) return mat_invalid("mat-mode tensors must be 16-byte aligned");
-    bool tma = p->tma && vec_ok;
+    bool tma = p->tma && vec_ok && !p->march;
     if (tma) {                                             // tensor maps: re-encoded only when a pointer changes
       const int uy = tdb::kCxTY + 4 * p->cx_hy, ry = tdb::kCxTY + 2 * p->cx_hy;
       if (p->map_u_ptr != u) {
@@ -1447,7 +1780,12 @@ static int mat_run(tdb200_mat_plan* p, const float* u, float* grad, float* op_ou
         p->map_f_ptr = tma ? a.l1_fbuf[0] : nullptr;
       }
     }
-    if (tma) {
+    if (p->march && vec_ok) {
+      MCU(tdb::launch_mat_march(a, p->cx_hy, p->cx_hx, p->cx_my, p->cx_mx, p->n_sms, p->d_edge_seed,
+                                p->timing ? p->ev1 : nullptr, s));
+      ev1_done = true;
+      n_ctas = tdb::mat_march_ctas(a, p->n_sms);
+    } else if (tma) {
       MCU(tdb::launch_mat_cross_tma(a, p->cx_hy, p->cx_hx, p->cx_my, p->cx_mx, p->map_u, a.l1_fbuf[0] ? p->map_f : p->map_u,
                                     p->n_sms, &n_ctas, s));
     } else if (p->cross && vec_ok) {
@@ -1462,6 +1800,7 @@ static int mat_run(tdb200_mat_plan* p, const float* u, float* grad, float* op_ou
     tdb::mat_residual_adjoint_kernel<<<grid, tdb::kMatThreads, p->smem, s>>>(a);
     MCU(cudaGetLastError());
   }
+  if (p->timing && !ev1_done) MCU(cudaEventRecord(p->ev1, s));
   // boundary rows; the last block to finish reduces the loss partials and assembles the loss (and re-zeroes the
   // slot sums and its ticket for the next call)
   if (p->n_bc_rows > 0) {
@@ -1493,7 +1832,7 @@ int tdb200_mat_eval_fields(tdb200_mat_plan* p, const float* u_dev, float* op_dev
 }
 
 int64_t tdb200_mat_plan_out_size(const tdb200_mat_plan* p) { return p ? 2 + p->n_slots : 0; }
-int32_t tdb200_mat_plan_launches_per_call(const tdb200_mat_plan* p) { return p ? 2 : 0; }
+int32_t tdb200_mat_plan_launches_per_call(const tdb200_mat_plan* p) { return p ? (p->args.lin1 && p->march ? 3 : 2) : 0; }
 
 int tdb200_mat_plan_set_row_window(tdb200_mat_plan* p, int32_t row_lo, int32_t row_hi) {
   if (!p) return mat_invalid("null plan");
@@ -1503,9 +1842,25 @@ int tdb200_mat_plan_set_row_window(tdb200_mat_plan* p, int32_t row_lo, int32_t r
   return TDB200_OK;
 }
 
+int tdb200_mat_plan_set_timing(tdb200_mat_plan* p, int32_t on) {
+  if (!p) return mat_invalid("null plan");
+  MCU(cudaSetDevice(p->device));
+  if (on && !p->ev0) { MCU(cudaEventCreate(&p->ev0)); MCU(cudaEventCreate(&p->ev1)); }
+  p->timing = on != 0;
+  return TDB200_OK;
+}
+
+int tdb200_mat_plan_stencil_ms(tdb200_mat_plan* p, float* ms_out) {
+  if (!p || !ms_out) return mat_invalid("null argument");
+  if (!p->ev0) return mat_invalid("tdb200_mat_plan_set_timing was not called");
+  MCU(cudaEventSynchronize(p->ev1));
+  MCU(cudaEventElapsedTime(ms_out, p->ev0, p->ev1));
+  return TDB200_OK;
+}
+
 int32_t tdb200_mat_plan_kernel_kind(const tdb200_mat_plan* p) {
   if (!p || !p->args.lin1) return 0;
-  return p->cross ? (p->tma ? 3 : 2) : 1;
+  return p->cross ? (p->march ? 4 : p->tma ? 3 : 2) : 1;
 }
 
 void tdb200_mat_plan_destroy(tdb200_mat_plan* p) {
@@ -1513,7 +1868,8 @@ void tdb200_mat_plan_destroy(tdb200_mat_plan* p) {
   cudaSetDevice(p->device);
   cudaFree(p->d_band); cudaFree(p->d_terms); cudaFree(p->d_factors); cudaFree(p->d_bcs); cudaFree(p->d_bc_row_begin);
   cudaFree(p->d_slot_scale); cudaFree(p->d_slot_lambda); cudaFree(p->d_slot_len); cudaFree(p->d_part_loss);
-  cudaFree(p->d_bc_sum); cudaFree(p->d_ticket);
+  cudaFree(p->d_bc_sum); cudaFree(p->d_ticket); cudaFree(p->d_edge_seed);
+  if (p->ev0) { cudaEventDestroy(p->ev0); cudaEventDestroy(p->ev1); }
   delete p;
 }
 

@@ -392,7 +392,7 @@ class MatPlan:
                           'tdb200_mat_plan_set_row_window')
         self.out_size = int(self.lib.tdb200_mat_plan_out_size(handle))
         self.launches_per_call = int(self.lib.tdb200_mat_plan_launches_per_call(handle))
-        self.kernel_kind = ('generic', 'register-tap', 'cross-vec4', 'cross-tma')[int(self.lib.tdb200_mat_plan_kernel_kind(handle))]
+        self.kernel_kind = ('generic', 'register-tap', 'cross-vec4', 'cross-tma', 'cross-march')[int(self.lib.tdb200_mat_plan_kernel_kind(handle))]
         self.n_cells = ir.n_cells                          # global
         self.n_cells_local = ir.n_cells_local
         # Several ranks, one field: the model tensor is adopted as the owned-row view of a persistent extended slab, so
@@ -433,6 +433,17 @@ class MatPlan:
             up = self.ir.rows[0] - self.ir.ext[0]
             grad = grad[:, up:up + self.shape[1]].contiguous()
         return out, grad
+
+    def set_timing(self, on: bool):
+        """Measurement aid: CUDA events around the stencil-kernel launch of every following eager call."""
+        _native.check(self.lib.tdb200_mat_plan_set_timing(self.handle, 1 if on else 0), 'tdb200_mat_plan_set_timing')
+
+    def stencil_ms(self) -> float:
+        """Duration of the stencil kernel of the last eager call made with timing on (waits for it)."""
+        import ctypes
+        ms = ctypes.c_float(0.0)
+        _native.check(self.lib.tdb200_mat_plan_stencil_ms(self.handle, ctypes.byref(ms)), 'tdb200_mat_plan_stencil_ms')
+        return float(ms.value)
 
     def loss_grad_raw(self, u: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """-> (out [2 + n_slots] summed over ranks, d loss / d u of this rank's rows).  Several ranks: halo rows from
