@@ -54,7 +54,7 @@ WORKLOADS = {
 MAT_BYTES_PER_CELL = 12      # read u, read the forcing tensor, write d loss / d u (fp32) - SURVEY 8d
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
 # captures (profiles/r01_ncu_jet_tc.md, profiles/r01_ncu_mat.md); None where no capture exists
-NCU_TRAFFIC_BYTES = {'wave_autograd_1e6': 8.58e6 + 4.80e6, 'poisson_mat_4096': 134.42e6 + 38.08e6}
+NCU_TRAFFIC_BYTES = {'wave_autograd_1e6': 8.57e6 + 5.14e6, 'poisson_mat_4096': 148.05e6 + 38.67e6}
 
 
 def flop_per_point(layers, J):
@@ -359,16 +359,10 @@ def run_b200_mat(args, dev, tdb, problems, rank=0, world=1):
     ms = reduce_max(sum(times)) / args.steps
     # kernel-only time of the stencil kernel on this rank (roofline): the same launch without the exchange
     ue = u if world == 1 else torch.zeros(plan.ir.shape_ext, dtype=torch.float32, device=dev)
-    # dominant (stencil) kernel alone: CUDA events recorded by the library around that launch, on the launching stream,
-    # L2 flushed before every launch
-    plan.set_timing(True)
-    kts = []
-    for _ in range(max(5, min(args.steps, 20))):
-        flush.zero_()
-        plan.loss_grad_ext(ue)
-        kts.append(plan.stencil_ms())
-    plan.set_timing(False)
-    kt = statistics.mean(kts)
+    # dominant (stencil) kernel alone: CUDA events recorded by the library on the launching stream around back-to-back
+    # launches of that kernel (inputs + output = 192 MiB per launch > L2, so launches do not feed each other from cache)
+    flush.zero_()
+    kt = statistics.mean(plan.time_stencil(ue, 10) for _ in range(max(3, min(args.steps, 10))))
     # e2e: forcing tensor + boundary targets from pinned host memory every step, loss terms read back
     host_in = [plan._coeffs.detach().cpu().pin_memory(), plan._targets.detach().cpu().pin_memory()]
     dev_in = [plan._coeffs, plan._targets]
@@ -416,8 +410,9 @@ def run_b200_mat(args, dev, tdb, problems, rank=0, world=1):
                      'bytes_per_cell': MAT_BYTES_PER_CELL, 'kernel_ms': kt, 'kernel': 'mat stencil kernel (' + plan.kernel_kind + ')',
                      'step_frac': n_local * MAT_BYTES_PER_CELL / (ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
                      'peak_source': f'MEASURED_PEAKS.json [{peak_src}] hbm_gbs; achieved = cells per GPU * 12 B / mean '
-                                    f'duration of the stencil kernel launch alone (CUDA events on its stream, L2 flushed '
-                                    f'before each launch); step_frac = the same bytes / the whole step (all launches)'},
+                                    f'duration of the stencil kernel launch alone (CUDA events on its stream around 10 back-to-back '
+                                    f'launches; working set 192 MiB > L2); step_frac = the same bytes / the whole step '
+                                    f'(all launches, L2 flushed between steps)'},
         'cpu_baseline': cpu,
         'wall_s': time.time() - t_wall,
     }

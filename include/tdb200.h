@@ -101,6 +101,13 @@ int tdb200_plan_set_slots(tdb200_plan* plan, const double* slot_lambda, const do
  * lambda / len.  NULL switches the weights off. */
 int tdb200_plan_set_row_weights(tdb200_plan* plan, const float* weights_dev);
 
+/* Vector-Jacobian product mode: with seeds (device pointer, tdb200_plan_n_fields floats, the layout tdb200_eval_fields
+ * writes) the gradient part of tdb200_loss_grad's output becomes sum_fields seed * d field / d theta - the backward of
+ * any differentiable function of the per-point fields (weak-form loss tedeous/losses.py:184-228 and eval.py:195-221,
+ * the Operator / Bounds seams of eval.py used directly).  The loss terms of that call are those of the plain loss.
+ * NULL switches back to the loss gradient. */
+int tdb200_plan_set_field_seeds(tdb200_plan* plan, const float* seeds_dev);
+
 /* Choose the kernel implementation: 0 = auto, 1 = SIMT fp32, 2 = tcgen05 3xTF32 (errors if unsupported). */
 int tdb200_plan_set_impl(tdb200_plan* plan, int32_t impl);
 
@@ -191,6 +198,12 @@ int32_t tdb200_mat_plan_kernel_kind(const tdb200_mat_plan* plan);
  * waits for the last pair and returns the elapsed milliseconds.  Leave it off when capturing a CUDA graph. */
 int tdb200_mat_plan_set_timing(tdb200_mat_plan* plan, int32_t on);
 int tdb200_mat_plan_stencil_ms(tdb200_mat_plan* plan, float* ms_out);
+/* Measurement aid: `iters` back-to-back launches of the residual (stencil) kernel(s) alone - no boundary rows, no
+ * finalize - between two CUDA events on `stream`; *ms_out = mean milliseconds per launch (synchronises).  The working
+ * set of BASELINE config 4 (u + forcing + gradient = 192 MiB) exceeds the 126 MB L2, so consecutive launches do not
+ * feed each other from cache. */
+int tdb200_mat_time_stencil(tdb200_mat_plan* plan, const float* u_dev, float* grad_dev, int32_t iters, float* ms_out,
+                            void* stream);
 void tdb200_mat_plan_destroy(tdb200_mat_plan* plan);
 
 const char* tdb200_last_error(void);

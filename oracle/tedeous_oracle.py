@@ -247,6 +247,26 @@ class MatDerivative:
 
 
 # ------------------------------------------------------------------------------------------------
+def integration(func, grid, power=2):
+    """eval.py:13-52, restated loop for loop: trapezoid rule along the last grid column inside runs of equal values
+    of the column before it (one run when the grid has a single column), integrand raised to `power`."""
+    column = -1 if grid.shape[-1] == 1 else -2
+    marker = grid[0][column]
+    index, result, u = [0], [], 0.
+    for i in range(1, len(grid)):
+        if grid[i][column] == marker or column == -1:
+            u = u + (grid[i][-1] - grid[i - 1][-1]).item() * (func[i] ** power + func[i - 1] ** power) / 2
+        else:
+            result.append(u)
+            marker = grid[i][column]
+            index.append(i)
+            u = 0.
+    if column == -1:
+        return u, 0.
+    result.append(u)
+    return result, grid[index, :-1]
+
+
 # the problem object: Solution.evaluate
 # ------------------------------------------------------------------------------------------------
 class OracleSolution:
@@ -254,8 +274,9 @@ class OracleSolution:
     bval_length like tedeous.solution.Solution."""
 
     def __init__(self, grid, equations, bconds, model, mode, lambda_operator, lambda_bound, h=0.001,
-                 inner_order='1', boundary_order='2', derivative_points=2, tol=0):
+                 inner_order='1', boundary_order='2', derivative_points=2, tol=0, weak_form=None):
         self.grid, self.model, self.mode = grid, model, mode
+        self.weak_form = weak_form
         self.h, self.inner_order, self.boundary_order = h, inner_order, boundary_order
         self.lambda_operator, self.lambda_bound, self.tol = lambda_operator, lambda_bound, tol
         eqs = equations if isinstance(equations, list) else [equations]
@@ -386,8 +407,34 @@ class OracleSolution:
         return bval, tval, keys, [len(vals[k]) for k in keys]
 
     # -- loss (losses.py:84-182) -----------------------------------------------------------------------
+    def _weak_operator(self, op):
+        """eval.py:195-221: every equation column times the test functions, then one `integration` pass per grid
+        column (each pass squares its integrand again - the reference's default power=2)."""
+        pts = self.grid_central if self.mode == 'NN' else self.grid
+        sols = []
+        for i in range(op.shape[-1]):
+            sol = op[:, i]
+            for func in self.weak_form:
+                sol = sol * func(pts).reshape(-1)
+            g = torch.clone(pts)
+            for _ in range(pts.shape[-1]):
+                sol, g = integration(sol, g)
+            sols.append(sol.reshape(-1, 1))
+        return sols[0] if len(sols) == 1 else torch.cat(sols).reshape(1, -1)
+
     def evaluate(self):
         self.op = self.operator_compute()
+        if self.weak_form not in (None, []):                      # losses.py:184-228
+            self.op = self._weak_operator(self.op)
+            self.bval, self.true_bval, self.bval_keys, self.bval_length = self.apply_bcs()
+            dtype = self.op.dtype
+            lam_op = lambda_prepare(self.op, self.lambda_operator).to(dtype)
+            lam_b = lambda_prepare(self.bval, self.lambda_bound).to(dtype)
+            bdiff = torch.mean((self.bval - self.true_bval) ** 2, 0)
+            self.loss = self.op @ lam_op.T + bdiff @ lam_b.T
+            with torch.no_grad():
+                self.loss_normalized = self.op @ torch.ones_like(lam_op).T + bdiff @ torch.ones_like(lam_b).T
+            return self.loss, self.loss_normalized
         self.bval, self.true_bval, self.bval_keys, self.bval_length = self.apply_bcs()
         dtype = self.op.dtype
         lam_op = lambda_prepare(self.op, self.lambda_operator).to(dtype)

@@ -11,6 +11,6 @@ ncu --set full --clock-control none --import-source on -k regex:jet_tc -s 2 -c 1
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${R}_ncu_tc.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:jet_simt -s 2 -c 1 -o gpurun_out/${R}_jet_simt \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --workload ns_autograd_1e6 > gpurun_out/${R}_ncu_simt.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:mat_cross_tma -s 2 -c 1 -o gpurun_out/${R}_mat \
+ncu --set full --clock-control none --import-source on -k regex:mat_march_kernel -s 2 -c 1 -o gpurun_out/${R}_mat \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph --workload poisson_mat_4096 > gpurun_out/${R}_ncu_mat.log 2>&1
 ls -la gpurun_out

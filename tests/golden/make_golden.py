@@ -57,7 +57,7 @@ def run_case(name, dtype):
                 if not torch.equal(torch.cat(list(sub.values())), bc['bnd']):
                     raise SystemExit(f'{name}: subset order != bnd order under PYTHONHASHSEED='
                                      f'{os.environ.get("PYTHONHASHSEED")}; pick another seed')
-    sol = Solution(grid, eq_cls, model, prob.mode, None, kw['lambda_operator'], kw['lambda_bound'],
+    sol = Solution(grid, eq_cls, model, prob.mode, kw.get('weak_form'), kw['lambda_operator'], kw['lambda_bound'],
                    tol=kw.get('tol', 0), derivative_points=kw.get('derivative_points', 2))
     if kw.get('tol', 0) != 0 and dtype == 'float64':
         # The reference's causal loss cannot run in fp64 as shipped: losses.py:176-180 multiplies an fp32
@@ -78,7 +78,7 @@ def run_case(name, dtype):
     op = sol.op.detach()
     out = dict(
         weights=weights, loss=float(loss), loss_normalized=float(loss_n),
-        op_mse=torch.mean(op ** 2, 0).double().numpy(),
+        op_mse=(op if kw.get('weak_form') else torch.mean(op ** 2, 0)).reshape(-1).double().numpy(),
         bval_mse=torch.mean((sol.bval - sol.true_bval) ** 2, 0).detach().double().numpy(),
         bval=sol.bval.detach().double().numpy(), true_bval=sol.true_bval.detach().double().numpy(),
         bval_keys=np.array(sol.bval_keys), bval_length=np.array(sol.bval_length),

@@ -47,7 +47,8 @@ def oracle_solution(prob, grid, bconds, model):
     kw = prob.compile_kwargs
     return orc.OracleSolution(grid, prob.equation.equation_lst, bconds, model, prob.mode,
                               kw['lambda_operator'], kw['lambda_bound'], h=kw.get('h', 0.001),
-                              derivative_points=kw.get('derivative_points', 2), tol=kw.get('tol', 0))
+                              derivative_points=kw.get('derivative_points', 2), tol=kw.get('tol', 0),
+                              weak_form=kw.get('weak_form'))
 
 
 def oracle_eval(name, dtype, weights=None):

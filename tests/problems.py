@@ -308,7 +308,44 @@ def kdv_mat(api, dtype='float32', n=24, derivative_points=2):
                    mat_shape=(1, n + 1, n + 1))
 
 
+# --- weak form (examples/examples_lotka_volterra/example_weak_LotkaVolterra.py:26-121) ---------------------
+def lotka_weak(api, dtype='float32', n=40, mode='NN', layers=(1, 32, 32, 2)):
+    alpha, beta, delta, gamma, x0, y0, tmax = 20., 20., 20., 20., 4., 2., 1.
+    dom = api.Domain()
+    dom.variable('t', [0, tmax], n, dtype=dtype)
+    h = tmax / n
+    bc = api.Conditions()
+    bc.dirichlet({'t': 0}, value=x0, var=0)
+    bc.dirichlet({'t': 0}, value=y0, var=1)
+    eq = api.Equation()
+    eq.add({'dx/dt': {'coeff': 1, 'term': [0], 'pow': 1, 'var': [0]},
+            '-x*alpha': {'coeff': -alpha, 'term': [None], 'pow': 1, 'var': [0]},
+            '+beta*x*y': {'coeff': beta, 'term': [[None], [None]], 'pow': [1, 1], 'var': [0, 1]}})
+    eq.add({'dy/dt': {'coeff': 1, 'term': [0], 'pow': 1, 'var': [1]},
+            '+y*delta': {'coeff': delta, 'term': [None], 'pow': 1, 'var': [1]},
+            '-gamma*x*y': {'coeff': -gamma, 'term': [[None], [None]], 'pow': [1, 1], 'var': [0, 1]}})
+
+    def v(grid):
+        return (0.5 + 0.5 * torch.sin(grid[:, 0])) * (2 / h) ** 0.5 / 10
+    kw = dict(lambda_operator=1, lambda_bound=100, weak_form=[v])
+    if mode == 'NN':
+        kw['h'] = h
+    return Problem(f'lotka_weak_{mode}', dom, bc, eq, mode, list(layers), kw)
+
+
+def wave_weak(api, dtype='float32', n=16):
+    """2-D grid: two nested integration passes (eval.py:13-52 squares the integrand in each of them)."""
+    prob = wave(api, dtype, n=n, mode='autograd', layers=(2, 32, 32, 1))
+    prob.compile_kwargs = dict(prob.compile_kwargs)
+    prob.compile_kwargs['weak_form'] = [lambda grid: 0.5 + 0.25 * torch.sin(3 * grid[:, 0]) * torch.cos(2 * grid[:, 1])]
+    prob.name = 'wave_weak_autograd'
+    return prob
+
+
 ZOO: Dict[str, Callable] = {
+    'lotka_weak_NN': lambda api, dt: lotka_weak(api, dt, mode='NN'),
+    'lotka_weak_autograd': lambda api, dt: lotka_weak(api, dt, mode='autograd'),
+    'wave_weak_autograd': lambda api, dt: wave_weak(api, dt),
     # name -> (builder, kwargs).  Sizes chosen so the reference itself preprocesses them in seconds.
     'burgers_NN_cfg1': lambda api, dt: burgers(api, dt, n=100, mode='NN'),
     'burgers_NN_small': lambda api, dt: burgers(api, dt, n=24, mode='NN', layers=(2, 32, 32, 1)),

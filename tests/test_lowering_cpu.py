@@ -12,7 +12,8 @@ from torch_de_solver_b200.input_preprocessing import Operator_bcond_preproc
 from torch_de_solver_b200.plan import lower_problem, flatten, points_per_tile
 from torch_de_solver_b200.solution import deepcopy_equation
 
-NET_CASES = sorted(k for k in problems.ZOO if 'mat' not in k)
+NET_CASES = sorted(k for k in problems.ZOO if 'mat' not in k and 'weak' not in k)
+WEAK_CASES = sorted(k for k in problems.ZOO if 'weak' in k)
 
 
 def lower(name, dtype='float64', nn_interior='jet', shard=(0, 1), weights=None):
@@ -83,3 +84,55 @@ def test_flatten_layout():
     # forcing term is a per-row buffer
     assert (flat.terms['kind'] == 1).sum() == 1
     assert points_per_tile(6, 1) == 20 and points_per_tile(4, 1) == 32 and points_per_tile(1, 3) == 120
+
+
+@pytest.mark.parametrize('name', WEAK_CASES)
+def test_weak_form_matches_reference(name):
+    """Weak-form loss (losses.py:184-228): the per-point fields of the lowered IR, the product's vectorised nested
+    integration (torch_de_solver_b200.losses) and the boundary MSE reproduce the reference's loss and gradient."""
+    from torch_de_solver_b200.losses import Losses, weak_operator
+    g, prob, model, ir = lower(name)
+    _, _, _, fields = evaluate_ir(ir, model)
+    kw = prob.compile_kwargs
+    wop = weak_operator(fields[0], ir.interior_points, kw['weak_form'])
+    n_types, max_len = len(ir.bnd_types), max(ir.type_len)
+    bval = torch.zeros(max_len, n_types, dtype=torch.float64)
+    tval = torch.zeros_like(bval)
+    for s, f in zip(ir.segments[1:], fields[1:]):
+        col = s.slots[0] - ir.n_eq
+        bval = bval.index_put((s.row_index, torch.full_like(s.row_index, col)), f[:, 0])
+        tval[s.row_index, col] = s.targets.reshape(-1).double()
+    loss, loss_n = Losses(prob.mode, kw['weak_form'], None, 0).compute(wop, bval, tval, kw['lambda_operator'], kw['lambda_bound'])
+    grads = torch.autograd.grad(loss.sum(), list(model.parameters()))
+    grad = torch.cat([x.reshape(-1) for x in grads]).numpy()
+    exact = prob.mode == 'autograd'
+    assert tuple(loss.shape) == (1, 1)                     # the reference's shape for this loss
+    assert float(loss) == pytest.approx(float(g['loss']), rel=1e-10 if exact else 2e-4)
+    assert float(loss_n) == pytest.approx(float(g['loss_normalized']), rel=1e-10 if exact else 2e-4)
+    np.testing.assert_allclose(wop.detach().reshape(-1).numpy(), g['op_mse'], rtol=1e-9 if exact else 2e-3)
+    gn = np.linalg.norm(g['grad'])
+    assert np.linalg.norm(grad - g['grad']) <= (1e-9 if exact else 5e-4) * gn
+
+
+@pytest.mark.parametrize('d', [1, 2, 3])
+def test_vectorised_integration_equals_the_reference_loop(d):
+    """torch_de_solver_b200.losses.integration against the loop-for-loop restatement in the oracle (eval.py:13-52),
+    including runs of one row and a ragged run structure."""
+    from oracle import tedeous_oracle as orc
+    from torch_de_solver_b200.losses import integration
+    torch.manual_seed(d)
+    axes = [torch.linspace(0, 1, n, dtype=torch.float64) ** 1.3 for n in (5, 4, 6)[:d]]
+    grid = torch.cartesian_prod(*axes).reshape(-1, d)
+    if d > 1:
+        keep = torch.ones(len(grid), dtype=torch.bool)
+        keep[3] = keep[7] = False                          # ragged runs
+        keep[-6:-1] = False                                # a run of a single row
+        grid = grid[keep]
+    f = torch.randn(len(grid), dtype=torch.float64)
+    want, wgrid = orc.integration(f, grid)
+    got, ggrid = integration(f, grid)
+    if d == 1:
+        assert float(got) == pytest.approx(float(want), rel=1e-12)
+    else:
+        np.testing.assert_allclose(got.numpy(), np.array([float(x) for x in want]), rtol=1e-12, atol=1e-15)
+        assert torch.equal(ggrid, wgrid)

@@ -29,12 +29,12 @@ MAT_BC_DTYPE = np.dtype([('n_rows', '<i8'), ('cell_off', '<i8'), ('tgt_off', '<i
                         align=True)
 
 EXPORTS = [
-    'tdb200_plan_create', 'tdb200_plan_set_points', 'tdb200_plan_set_slots', 'tdb200_plan_set_impl', 'tdb200_plan_set_row_weights',
+    'tdb200_plan_create', 'tdb200_plan_set_points', 'tdb200_plan_set_slots', 'tdb200_plan_set_impl', 'tdb200_plan_set_row_weights', 'tdb200_plan_set_field_seeds',
     'tdb200_plan_out_size', 'tdb200_plan_n_params', 'tdb200_plan_n_fields', 'tdb200_plan_launches_per_call',
     'tdb200_loss_grad', 'tdb200_eval_fields', 'tdb200_plan_destroy',
     'tdb200_mat_plan_create', 'tdb200_mat_plan_set_coeffs', 'tdb200_mat_plan_set_bcs', 'tdb200_mat_loss_grad', 'tdb200_mat_eval_fields',
     'tdb200_mat_plan_out_size', 'tdb200_mat_plan_launches_per_call', 'tdb200_mat_plan_kernel_kind', 'tdb200_mat_plan_set_row_window',
-    'tdb200_mat_plan_set_timing', 'tdb200_mat_plan_stencil_ms',
+    'tdb200_mat_plan_set_timing', 'tdb200_mat_plan_stencil_ms', 'tdb200_mat_time_stencil',
     'tdb200_mat_plan_destroy',
     'tdb200_last_error', 'tdb200_version',
 ]
@@ -59,6 +59,7 @@ def load():
     lib.tdb200_plan_set_slots.argtypes = [vp, vp, vp]
     lib.tdb200_plan_set_impl.argtypes = [vp, i32]
     lib.tdb200_plan_set_row_weights.argtypes = [vp, vp]
+    lib.tdb200_plan_set_field_seeds.argtypes = [vp, vp]
     for name in ('tdb200_plan_out_size', 'tdb200_plan_n_params', 'tdb200_plan_n_fields', 'tdb200_mat_plan_out_size'):
         getattr(lib, name).argtypes = [vp]
         getattr(lib, name).restype = i64
@@ -67,6 +68,7 @@ def load():
     lib.tdb200_mat_plan_kernel_kind.argtypes = [vp]
     lib.tdb200_mat_plan_set_timing.argtypes = [vp, i32]
     lib.tdb200_mat_plan_stencil_ms.argtypes = [vp, vp]
+    lib.tdb200_mat_time_stencil.argtypes = [vp, vp, vp, i32, vp, vp]
     lib.tdb200_mat_plan_set_row_window.argtypes = [vp, i32, i32]
     lib.tdb200_loss_grad.argtypes = [vp, vp, vp, vp]
     lib.tdb200_eval_fields.argtypes = [vp, vp, vp, vp, vp]

@@ -289,6 +289,12 @@ int tdb200_plan_set_row_weights(tdb200_plan* p, const float* weights_dev) {
   return TDB200_OK;
 }
 
+int tdb200_plan_set_field_seeds(tdb200_plan* p, const float* seeds_dev) {
+  if (!p) return fail(TDB200_ERR_INVALID, "null plan");
+  p->args.field_seed = seeds_dev;                        // NULL: loss gradient (default)
+  return TDB200_OK;
+}
+
 int tdb200_plan_set_impl(tdb200_plan* p, int32_t impl) {
   if (!p) return fail(TDB200_ERR_INVALID, "null plan");
   if (impl < 0 || impl > 2) return fail(TDB200_ERR_INVALID, "impl must be 0 (auto), 1 (SIMT) or 2 (tcgen05)");

@@ -50,6 +50,8 @@ struct JetArgs {
   long long scratch_per_cta;
   float* fields;                       // optional per-row operator values
   const float* row_weight;             // optional per-row loss weights of segment 0 (causal loss, losses.py:137-182)
+  const float* field_seed;             // optional cotangents of every field value (layout of `fields`): the gradient
+                                       // becomes the vector-Jacobian product sum seed * d field / d theta
   int do_grad;
   long long* dbg;                      // optional [gridDim.x][16] phase cycle counters (TDB200_TC_TIMING=1)
 };

@@ -377,7 +377,8 @@ __global__ void __launch_bounds__(kThreads, 1) jet_simt_kernel(const JetArgs a) 
         const int slot = sg.col_slot[col];
         const float rw = (a.row_weight && seg_i == 0) ? __ldg(a.row_weight + row) : 1.f;   // causal-loss weight (no grad)
         atomicAdd(&sm.lossS[slot], (double)rw * (double)res * (double)res);
-        sm.rS[col * G + g] = 2.f * __ldg(a.slot_scale + slot) * rw * res;
+        sm.rS[col * G + g] = a.field_seed ? __ldg(a.field_seed + sg.field_off + row * ncols + col)
+                                          : 2.f * __ldg(a.slot_scale + slot) * rw * res;
       }
       if (a.do_grad) {
         for (int col = 0; col < ncols; ++col) {

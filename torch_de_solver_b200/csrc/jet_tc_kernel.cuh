@@ -605,7 +605,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
         const float rw = a.row_weight ? __ldg(a.row_weight + row) : 1.f;        // causal-loss weight (no grad)
         sm.lossT[p * TDB200_MAX_COLS + col] += (double)rw * (double)res * (double)res;
         if (!a.do_grad) continue;
-        const float seed = 2.f * sm.scaleS[sg.col_slot[col]] * rw * res;
+        const float seed = a.field_seed ? __ldg(a.field_seed + sg.field_off + row * ncols + col)
+                                        : 2.f * sm.scaleS[sg.col_slot[col]] * rw * res;
         for (int t = tb; t < te; ++t) {
           const int4 r = sm.recS[t];
           const float cf = r.y == 0 ? __int_as_float(r.x) : r.y == 1 ? __ldg(a.coeffs + r.x + row) : a.arena[a.n_net_params + r.x];
@@ -641,7 +642,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
         sm.lossT[p * TDB200_MAX_COLS + col] += (double)res * (double)res;
         TMARK(12);
         if (!a.do_grad) continue;
-        const float seed = 2.f * sm.scaleS[slot] * res;
+        const float seed = a.field_seed ? __ldg(a.field_seed + sg.field_off + row * ncols + col) : 2.f * sm.scaleS[slot] * res;
         for (int t = sg.col_term_begin[col]; t < sg.col_term_end[col]; ++t) {
           const tdb200_term tm = sm.termS[t];
           const float cf = tm.kind == 0 ? tm.coeff : tm.kind == 1 ? __ldg(a.coeffs + tm.idx + row)

@@ -1061,14 +1061,15 @@ static size_t mat_march_frame_cells(const MatArgs& a, int hy, int hx) {
   return (size_t)(top + bot) * a.n1 + (size_t)mid * (left + right);
 }
 template <int HY, int HX, unsigned MY, unsigned MX>
-static cudaError_t launch_mat_march_t(const MatArgs& a, int n_sms, float* edge_seeds, cudaEvent_t after_stencil, cudaStream_t s) {
+static cudaError_t launch_mat_march_t(const MatArgs& a, int n_sms, float* edge_seeds, cudaEvent_t after_stencil, bool main_only,
+                                      cudaStream_t s) {
   const int ch = mat_march_chunk(a, n_sms), n_strips = (a.n1 + kMwOutW - 1) / kMwOutW;
   const int n_items = n_strips * ((a.n0 + ch - 1) / ch);
   const int grid = kMwEdgeBlocks + (n_items + kMwWarps - 1) / kMwWarps;
   mat_march_kernel<HY, HX, MY, MX, 3><<<grid, kMwThreads, 0, s>>>(a, ch, n_strips, n_items, kMwEdgeBlocks, edge_seeds);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess && after_stencil) e = cudaEventRecord(after_stencil, s);
-  if (e != cudaSuccess || !a.grad) return e;
+  if (e != cudaSuccess || !a.grad || main_only) return e;
   mat_march_edge_kernel<<<2 * kMwEdgeBlocks, 128, 0, s>>>(a, a.edge_y + HY, a.edge_x + HX, edge_seeds);
   return cudaGetLastError();
 }
@@ -1082,8 +1083,8 @@ static bool mat_march_supported(int hy, int hx, unsigned my, unsigned mx) {
   return false;
 }
 static cudaError_t launch_mat_march(const MatArgs& a, int hy, int hx, unsigned my, unsigned mx, int n_sms, float* edge_seeds,
-                                    cudaEvent_t after_stencil, cudaStream_t s) {
-#define X(A, B, C, D) if (hy == A && hx == B && (my & ~C) == 0 && (mx & ~D) == 0) return launch_mat_march_t<A, B, C, D>(a, n_sms, edge_seeds, after_stencil, s);
+                                    cudaEvent_t after_stencil, bool main_only, cudaStream_t s) {
+#define X(A, B, C, D) if (hy == A && hx == B && (my & ~C) == 0 && (mx & ~D) == 0) return launch_mat_march_t<A, B, C, D>(a, n_sms, edge_seeds, after_stencil, main_only, s);
   TDB_MARCH_SHAPES(X)
 #undef X
   return cudaErrorInvalidValue;
@@ -1751,16 +1752,10 @@ int tdb200_mat_plan_set_bcs(tdb200_mat_plan* p, int32_t n_bcs, const tdb200_mat_
   return TDB200_OK;
 }
 
-static int mat_run(tdb200_mat_plan* p, const float* u, float* grad, float* op_out, float* bval_out, float* out,
-                   void* stream) {
-  if (!p || !u || !out) return mat_invalid("null argument");
-  if (!p->bcs_set) return mat_invalid("tdb200_mat_plan_set_bcs was not called");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  MCU(cudaSetDevice(p->device));
-  tdb::MatArgs a = p->args;
-  a.u = u; a.grad = grad; a.op_out = op_out; a.tile_ctr = p->d_ticket + 1;
+// the residual (stencil) launch(es) of one call; *n_ctas = number of loss partials they write
+static int mat_stencil(tdb200_mat_plan* p, tdb::MatArgs& a, const float* u, float* grad, float* op_out, int* n_ctas_out,
+                       cudaEvent_t after_stencil, bool main_only, cudaStream_t s) {
   int n_ctas = p->n_ctas;
-  if (p->timing) MCU(cudaEventRecord(p->ev0, s));
   bool ev1_done = false;
   if (a.lin1 && !op_out) {
     // specialised kernels (loss + gradient, or loss only); per-cell operator values go through the generic kernel
@@ -1781,8 +1776,7 @@ static int mat_run(tdb200_mat_plan* p, const float* u, float* grad, float* op_ou
       }
     }
     if (p->march && vec_ok) {
-      MCU(tdb::launch_mat_march(a, p->cx_hy, p->cx_hx, p->cx_my, p->cx_mx, p->n_sms, p->d_edge_seed,
-                                p->timing ? p->ev1 : nullptr, s));
+      MCU(tdb::launch_mat_march(a, p->cx_hy, p->cx_hx, p->cx_my, p->cx_mx, p->n_sms, p->d_edge_seed, after_stencil, main_only, s));
       ev1_done = true;
       n_ctas = tdb::mat_march_ctas(a, p->n_sms);
     } else if (tma) {
@@ -1800,7 +1794,25 @@ static int mat_run(tdb200_mat_plan* p, const float* u, float* grad, float* op_ou
     tdb::mat_residual_adjoint_kernel<<<grid, tdb::kMatThreads, p->smem, s>>>(a);
     MCU(cudaGetLastError());
   }
-  if (p->timing && !ev1_done) MCU(cudaEventRecord(p->ev1, s));
+  if (after_stencil && !ev1_done) MCU(cudaEventRecord(after_stencil, s));
+  *n_ctas_out = n_ctas;
+  return TDB200_OK;
+}
+
+static int mat_run(tdb200_mat_plan* p, const float* u, float* grad, float* op_out, float* bval_out, float* out,
+                   void* stream) {
+  if (!p || !u || !out) return mat_invalid("null argument");
+  if (!p->bcs_set) return mat_invalid("tdb200_mat_plan_set_bcs was not called");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MCU(cudaSetDevice(p->device));
+  tdb::MatArgs a = p->args;
+  a.u = u; a.grad = grad; a.op_out = op_out; a.tile_ctr = p->d_ticket + 1;
+  int n_ctas = p->n_ctas;
+  if (p->timing) MCU(cudaEventRecord(p->ev0, s));
+  {
+    const int rc = mat_stencil(p, a, u, grad, op_out, &n_ctas, p->timing ? p->ev1 : nullptr, false, s);
+    if (rc != TDB200_OK) return rc;
+  }
   // boundary rows; the last block to finish reduces the loss partials and assembles the loss (and re-zeroes the
   // slot sums and its ticket for the next call)
   if (p->n_bc_rows > 0) {
@@ -1847,6 +1859,29 @@ int tdb200_mat_plan_set_timing(tdb200_mat_plan* p, int32_t on) {
   MCU(cudaSetDevice(p->device));
   if (on && !p->ev0) { MCU(cudaEventCreate(&p->ev0)); MCU(cudaEventCreate(&p->ev1)); }
   p->timing = on != 0;
+  return TDB200_OK;
+}
+
+int tdb200_mat_time_stencil(tdb200_mat_plan* p, const float* u, float* grad, int32_t iters, float* ms_out, void* stream) {
+  if (!p || !u || !grad || !ms_out || iters < 1) return mat_invalid("bad argument");
+  if (!p->bcs_set) return mat_invalid("tdb200_mat_plan_set_bcs was not called");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MCU(cudaSetDevice(p->device));
+  if (!p->ev0) { MCU(cudaEventCreate(&p->ev0)); MCU(cudaEventCreate(&p->ev1)); }
+  tdb::MatArgs a = p->args;
+  a.u = u; a.grad = grad; a.op_out = nullptr; a.tile_ctr = p->d_ticket + 1;
+  int n_ctas = 0;
+  MCU(cudaEventRecord(p->ev0, s));
+  for (int i = 0; i < iters; ++i) {
+    const int rc = mat_stencil(p, a, u, grad, nullptr, &n_ctas, nullptr, true, s);
+    if (rc != TDB200_OK) return rc;
+    if (p->tma && !p->march) MCU(cudaMemsetAsync(p->d_ticket + 1, 0, sizeof(unsigned int), s));   // re-arm the tile counter
+  }
+  MCU(cudaEventRecord(p->ev1, s));
+  MCU(cudaEventSynchronize(p->ev1));
+  float ms = 0.f;
+  MCU(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+  *ms_out = ms / (float)iters;
   return TDB200_OK;
 }
 

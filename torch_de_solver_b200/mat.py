@@ -438,6 +438,16 @@ class MatPlan:
         """Measurement aid: CUDA events around the stencil-kernel launch of every following eager call."""
         _native.check(self.lib.tdb200_mat_plan_set_timing(self.handle, 1 if on else 0), 'tdb200_mat_plan_set_timing')
 
+    def time_stencil(self, ue: torch.Tensor, iters: int = 10) -> float:
+        """Mean duration (ms) of `iters` back-to-back launches of the stencil kernel alone on the extended slab."""
+        import ctypes
+        grad = torch.empty(self.ir.shape_ext, dtype=torch.float32, device=self.device)
+        ms = ctypes.c_float(0.0)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _native.check(self.lib.tdb200_mat_time_stencil(self.handle, ue.data_ptr(), grad.data_ptr(), int(iters),
+                                                       ctypes.byref(ms), stream), 'tdb200_mat_time_stencil')
+        return float(ms.value)
+
     def stencil_ms(self) -> float:
         """Duration of the stencil kernel of the last eager call made with timing on (waits for it)."""
         import ctypes

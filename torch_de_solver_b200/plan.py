@@ -157,6 +157,9 @@ def parse_operator(op: dict, rows: torch.Tensor, coeff_rows: Optional[Callable] 
         for spec, pw, var in zip(specs, pows, vars_):
             if callable(pw):
                 raise UnsupportedProblem(f"term {label!r}: callable 'pow' is not supported by the fused path")
+            if isinstance(var, (list, tuple)) and len(var) == 1:
+                var = var[0]     # 'var': [0] next to a scalar 'pow' (example_weak_LotkaVolterra.py:59-64): equation_unify
+                                 # wraps it once more and the reference indexes model(grid)[:, [0]] with the list
             facs.append(FactorIR(int(var), _pure_axes(spec), float(pw)))
         coeff = term['coeff']
         if isinstance(coeff, tuple):          # reference NN-prepared form (callable, grid)
@@ -508,6 +511,7 @@ def lower_problem(mode: str, grid: torch.Tensor, prepared_operator: List[dict], 
     ir.type_len = [type_len[t] for t in bnd_types]
     # time slices of the causal loss: unique values of column 0 of the interior rows (tedeous/solution.py:51-57)
     ir.n_t = int(torch.unique(pts[:, 0]).numel())
+    ir.interior_points = pts             # rows of the operator residual (NN mode: the central points), weak form
     for s in ir.segments:
         s.n_groups_global = s.n_groups
     if shard[1] > 1:

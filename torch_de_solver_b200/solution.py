@@ -84,6 +84,19 @@ class FusedPlan:
         _native.check(self.lib.tdb200_plan_set_row_weights(
             self.handle, None if self._row_w is None else self._row_w.data_ptr()), 'tdb200_plan_set_row_weights')
 
+    def vjp(self, seeds: torch.Tensor) -> torch.Tensor:
+        """Vector-Jacobian product: sum_fields seeds * d field / d theta -> flat [n_params] (parameter order of the
+        gradient).  `seeds` has the layout of `eval_fields()[0]`; one fused launch in seed mode."""
+        seeds = seeds.detach().to(self.device, torch.float32).contiguous()
+        if seeds.numel() != max(self.n_fields, 1):
+            raise ValueError(f'expected {self.n_fields} field cotangents, got {seeds.numel()}')
+        _native.check(self.lib.tdb200_plan_set_field_seeds(self.handle, seeds.data_ptr()), 'tdb200_plan_set_field_seeds')
+        try:
+            out = self.loss_grad()
+        finally:
+            _native.check(self.lib.tdb200_plan_set_field_seeds(self.handle, None), 'tdb200_plan_set_field_seeds')
+        return out[self.out_size - self.n_params:]
+
     def set_impl(self, impl: int):
         _native.check(self.lib.tdb200_plan_set_impl(self.handle, impl), 'tdb200_plan_set_impl')
         self.launches_per_call = int(self.lib.tdb200_plan_launches_per_call(self.handle))
@@ -143,6 +156,28 @@ class _FusedLoss(torch.autograd.Function):
         return (None, *grads)
 
 
+class _FusedFields(torch.autograd.Function):
+    """fields = plan.eval_fields(params) (flat, every per-point operator / boundary value); backward = one fused launch
+    in vector-Jacobian mode.  Makes any torch function of the per-point fields differentiable w.r.t. the network."""
+
+    @staticmethod
+    def forward(ctx, plan, *params):
+        fields, _ = plan.eval_fields()
+        ctx.plan = plan
+        ctx.shapes = [p.shape for p in params]
+        return fields
+
+    @staticmethod
+    def backward(ctx, g):
+        flat = ctx.plan.vjp(g)
+        grads, off = [], 0
+        for shp in ctx.shapes:
+            n = int(np.prod(shp)) if len(shp) else 1
+            grads.append(flat[off:off + n].view(shp))
+            off += n
+        return (None, *grads)
+
+
 class Solution:
     """Same constructor and public attributes as tedeous.solution.Solution."""
 
@@ -150,8 +185,11 @@ class Solution:
                  lambda_bound, tol: float = 0, derivative_points: int = 2, batch_size: int = None,
                  shard: Optional[Tuple[int, int]] = None, process_group=None, nn_interior: str = 'jet',
                  impl: int = 0):
-        if weak_form not in (None, []):
-            raise UnsupportedProblem('weak-form loss is not implemented by the fused path (SURVEY 8 a11)')
+        weak = weak_form not in (None, [])
+        if weak and mode == 'mat':
+            raise UnsupportedProblem('weak-form loss is implemented for modes NN / autograd only (SURVEY 8 a11)')
+        if weak and (tol != 0 or (shard is not None and shard[1] > 1)):
+            raise UnsupportedProblem('weak-form loss: no causal weights, not sharded over ranks')
         if tol != 0 and mode == 'mat':
             raise UnsupportedProblem('causal loss (tol != 0) is implemented for modes NN / autograd only (SURVEY 8 a10)')
         if tol != 0 and shard is not None and shard[1] > 1:
@@ -267,8 +305,27 @@ class Solution:
         if lam != list(self._plan.slot_lambda):
             self._plan.set_lambdas(lam)
 
+    def _evaluate_weak(self, save_graph: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Weak-form loss (tedeous/losses.py:184-228 over eval.py:195-221): per-point fields from a forward launch,
+        the nested integrals as a few device ops, the parameter gradient by the fused kernel in seed mode."""
+        from .losses import Losses, weak_operator
+        self._fields_cache = None
+        grad = save_graph and torch.is_grad_enabled()
+        op, bval, tval = self._fields_differentiable() if grad else self._fields()
+        self._fields_cache = (op.detach(), bval.detach(), tval)
+        wop = weak_operator(op, self._ir.interior_points, self.weak_form)
+        n_eq = self._n_slots - len(self.bval_keys)
+        loss, loss_n = Losses(self.mode, self.weak_form, None, 0).compute(
+            wop, bval, tval, self.lambda_operator, self.lambda_bound, save_graph)
+        self.loss, self.loss_normalized = loss, loss_n.detach()
+        self.lambda_operator = lambda_prepare(torch.empty(1, n_eq), self.lambda_operator).to(torch.float32)
+        self.lambda_bound = lambda_prepare(torch.empty(1, len(self.bval_keys)), self.lambda_bound).to(torch.float32)
+        return self.loss, self.loss_normalized
+
     def evaluate(self, save_graph: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
         """One loss evaluation (tedeous/solution.py:129-168)."""
+        if self.weak_form not in (None, []):
+            return self._evaluate_weak(save_graph)
         self._sync_lambdas()
         self._fields_cache = None
         if self.mode == 'mat':
@@ -312,6 +369,15 @@ class Solution:
                 self._fields_cache = _assemble_fields(self._plan)
         return self._fields_cache
 
+    def _fields_differentiable(self):
+        """(op, bval, true_bval) with op / bval attached to the autograd graph of the network parameters."""
+        if self.mode == 'mat':
+            raise UnsupportedProblem('differentiable per-point fields are implemented for modes NN / autograd')
+        if self._shard[1] > 1:
+            raise UnsupportedProblem('per-point fields are not gathered across ranks')
+        params = self._plan.ir.net.param_tensors()
+        return _assemble_fields(self._plan, _FusedFields.apply(self._plan, *params))
+
     @property
     def op(self) -> torch.Tensor:
         return self._fields()[0]
@@ -325,10 +391,12 @@ class Solution:
         return self._fields()[2]
 
 
-def _assemble_fields(plan: FusedPlan):
-    """op [N, n_eq], bval / true_bval [max_len, n_types] zero padded (eval.py:55-87)."""
+def _assemble_fields(plan: FusedPlan, fields: Optional[torch.Tensor] = None):
+    """op [N, n_eq], bval / true_bval [max_len, n_types] zero padded (eval.py:55-87).  `fields`: an already evaluated
+    (possibly differentiable) flat field vector; default: one forward launch."""
     ir = plan.ir
-    fields, _ = plan.eval_fields()
+    if fields is None:
+        fields, _ = plan.eval_fields()
     seg_rec = plan.flat.seg
     n_types = len(ir.bnd_types)
     max_len = max(ir.type_len)
@@ -343,7 +411,7 @@ def _assemble_fields(plan: FusedPlan):
         else:
             col = s.slots[0] - ir.n_eq
             idx = s.row_index.to(plan.device)
-            bval[idx, col] = vals[:, 0]
+            bval = bval.index_put((idx, torch.full_like(idx, col)), vals[:, 0])      # out of place: keeps the graph
             tval[idx, col] = s.targets.reshape(-1).to(device=plan.device, dtype=torch.float32)
     return op, bval, tval
 
