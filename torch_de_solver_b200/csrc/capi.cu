@@ -77,6 +77,8 @@ struct tdb200_plan {
   int tc_tiles = 0, tc_grid = 0;
   int tc_sig[3] = {0, 0, 0};
   int simt_rest_tiles = 0, simt_rest_grid = 0;
+  cudaStream_t side = nullptr;             // boundary-row launch running next to the tcgen05 launch (fork / join by events)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int* d_seg_tile_begin_tc = nullptr;
   int* d_seg_tile_begin_rest = nullptr;
   float* wimg = nullptr;
@@ -355,7 +357,34 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
     long long* dbg = nullptr;
     if (getenv("TDB200_TC_TIMING")) { cudaMalloc(&dbg, sizeof(long long) * 16 * p->tc_grid); }
     tc.dbg = dbg;
-    CU(tdb::launch_jet_tc(tc, p->wimg, p->tc_sig[0], p->tc_sig[1], p->tc_sig[2], p->tc_grid, s));
+    // The boundary rows (SIMT kernel, a few tiles of ~170 us each) run NEXT TO the tcgen05 launch on a side stream, on
+    // SMs the persistent tcgen05 grid leaves free, when few CTAs finish them within the tcgen05 launch's own time.
+    int side_ctas = 0;
+    if (p->simt_rest_tiles > 0 && p->tc_grid == p->n_sms && !dbg && !getenv("TDB200_NO_OVERLAP")) {
+      const double tc_us = 25.0 + 15.0 * ((p->tc_tiles + p->tc_grid - 1) / p->tc_grid);
+      const int k = (int)ceil(p->simt_rest_tiles * 170.0 / tc_us);
+      if (k <= p->n_sms / 8) side_ctas = k < 1 ? 1 : k;
+    }
+    const int tc_grid = p->tc_grid - side_ctas;
+    grad_rows = tdb::jet_tc_partial_rows() * tc_grid;
+    loss_rows = tc_grid;
+    tdb::JetArgs rest = call;
+    rest.seg_tile_begin = p->d_seg_tile_begin_rest;
+    rest.n_tiles = p->simt_rest_tiles;
+    rest.part_grad = p->part_grad + (size_t)grad_rows * a.n_params_pad;
+    rest.part_loss = p->part_loss + (size_t)loss_rows * p->n_slots;
+    if (side_ctas) {
+      if (!p->side) {
+        CU(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+      }
+      CU(cudaEventRecord(p->ev_fork, s));
+      CU(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+      CU(tdb::launch_jet_simt(rest, side_ctas, p->side));       // enqueued first: its CTAs take their SMs first
+      CU(cudaEventRecord(p->ev_join, p->side));
+    }
+    CU(tdb::launch_jet_tc(tc, p->wimg, p->tc_sig[0], p->tc_sig[1], p->tc_sig[2], tc_grid, s));
     if (dbg) {
       std::vector<long long> h(16 * p->tc_grid);
       cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -365,14 +394,11 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
       for (int i = 0; i < 16; ++i) fprintf(stderr, " p%d=%lld", i, h[i] / tiles_per_cta);
       fprintf(stderr, "\n");
     }
-    grad_rows = tdb::jet_tc_partial_rows() * p->tc_grid;
-    loss_rows = p->tc_grid;
-    if (p->simt_rest_tiles > 0) {
-      tdb::JetArgs rest = call;
-      rest.seg_tile_begin = p->d_seg_tile_begin_rest;
-      rest.n_tiles = p->simt_rest_tiles;
-      rest.part_grad = p->part_grad + (size_t)grad_rows * a.n_params_pad;
-      rest.part_loss = p->part_loss + (size_t)loss_rows * p->n_slots;
+    if (side_ctas) {
+      CU(cudaStreamWaitEvent(s, p->ev_join, 0));
+      grad_rows += side_ctas;
+      loss_rows += side_ctas;
+    } else if (p->simt_rest_tiles > 0) {
       CU(tdb::launch_jet_simt(rest, p->simt_rest_grid, s));
       grad_rows += p->simt_rest_grid;
       loss_rows += p->simt_rest_grid;
@@ -406,6 +432,7 @@ void tdb200_plan_destroy(tdb200_plan* p) {
   cudaFree(p->d_comb); cudaFree(p->d_slot_scale); cudaFree(p->d_slot_lambda); cudaFree(p->d_slot_len);
   cudaFree(p->arena); cudaFree(p->arena_t); cudaFree(p->img_f); cudaFree(p->img_b);
   cudaFree(p->d_seg_tile_begin_tc); cudaFree(p->d_seg_tile_begin_rest); cudaFree(p->wimg); cudaFree(p->tc_scratch); cudaFree(p->part_grad); cudaFree(p->part_loss); cudaFree(p->scratch);
+  if (p->side) { cudaStreamDestroy(p->side); cudaEventDestroy(p->ev_fork); cudaEventDestroy(p->ev_join); }
   delete p;
 }
 

@@ -556,25 +556,36 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part_grad, int 
                                        float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_params) {
+    // fixed summation order (row 0, 1, 2, ...); the loads of 8 rows are issued together
     float s = 0.f;
-    for (int c = 0; c < n_grad_rows; ++c) s += part_grad[(size_t)c * n_params_pad + i];
+    int c = 0;
+    for (; c + 8 <= n_grad_rows; c += 8) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __ldg(part_grad + (size_t)(c + k) * n_params_pad + i);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += v[k];
+    }
+    for (; c < n_grad_rows; ++c) s += __ldg(part_grad + (size_t)c * n_params_pad + i);
     out[2 + n_slots + i] = s;
   }
-  if (blockIdx.x == 0 && threadIdx.x < 32) {
-    double loss = 0.0, lossn = 0.0;
-    for (int s = threadIdx.x; s < n_slots; s += 32) {
+  if (blockIdx.x == gridDim.x - 1) {
+    // loss terms: one warp per slot (lanes stride the rows, then a fixed shuffle tree); warp 0 assembles the loss
+    __shared__ double mse_s[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    for (int sl = warp; sl < n_slots; sl += n_warps) {
       double acc = 0.0;
-      for (int c = 0; c < n_loss_rows; ++c) acc += part_loss[(size_t)c * n_slots + s];
-      const double mse = acc / slot_len[s];
-      out[2 + s] = (float)mse;
-      loss += slot_lambda[s] * mse;
-      lossn += mse;
+      for (int c = lane; c < n_loss_rows; c += 32) acc += part_loss[(size_t)c * n_slots + sl];
+      for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) { mse_s[sl] = acc / slot_len[sl]; out[2 + sl] = (float)mse_s[sl]; }
     }
-    for (int o = 16; o; o >>= 1) {
-      loss += __shfl_xor_sync(0xffffffffu, loss, o);
-      lossn += __shfl_xor_sync(0xffffffffu, lossn, o);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double loss = 0.0, lossn = 0.0;
+      for (int sl = 0; sl < n_slots; ++sl) { loss += slot_lambda[sl] * mse_s[sl]; lossn += mse_s[sl]; }
+      out[0] = (float)loss;
+      out[1] = (float)lossn;
     }
-    if (threadIdx.x == 0) { out[0] = (float)loss; out[1] = (float)lossn; }
   }
 }
 
