@@ -77,6 +77,8 @@ struct tdb200_plan {
   int tc_tiles = 0, tc_grid = 0;
   int tc_sig[3] = {0, 0, 0};
   int simt_rest_tiles = 0, simt_rest_grid = 0;
+  struct TcExtra { int seg, sig[3], tiles, grid; };      // boundary segments that also run on tcgen05 (identity rows)
+  std::vector<TcExtra> tc_extra;
   cudaStream_t side = nullptr;             // boundary-row launch running next to the tcgen05 launch (fork / join by events)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int* d_seg_tile_begin_tc = nullptr;
@@ -204,7 +206,30 @@ int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_s
       p->tc_grid = p->tc_tiles < p->n_sms ? p->tc_tiles : p->n_sms;
       std::vector<int> tb(n_segments + 1, p->tc_tiles), rb(n_segments + 1, 0);
       tb[0] = 0;
-      for (int s = 1; s <= n_segments; ++s) rb[s] = p->seg_tile_begin[s] - p->seg_tile_begin[1];
+      // boundary segments made of identity rows (Dirichlet values, autograd-mode operator conditions) take the tcgen05
+      // kernel too - one small launch each on the side stream; periodic / finite-difference groups stay on the SIMT kernel
+      int n_factors_max = 0;
+      for (int s = 1; s < n_segments; ++s) {
+        const tdb200_segment& sg = segments[s];
+        int sig[3];
+        for (int i = 0; i < 3; ++i) sig[i] = i < sg.n_dirs ? sg.dir_order[i] : 0;
+        bool eok = sg.identity && sg.K == 1 && sg.n_dirs <= 3 && sg.n_groups > 0 && sg.n_cols >= 1 &&
+                   tdb::jet_tc_supports(sig[0], sig[1], sig[2]) && sg.col_term_end[sg.n_cols - 1] <= 48 &&
+                   !getenv("TDB200_NO_TC_BOUNDARY");
+        if (eok)
+          for (int t = sg.col_term_begin[0]; t < sg.col_term_end[sg.n_cols - 1]; ++t) eok = eok && terms[t].fac_end <= 96;
+        const int simt_tiles = p->seg_tile_begin[s + 1] - p->seg_tile_begin[s];
+        if (eok) {
+          const int Pe = tdb::jet_tc_points_per_tile(sig[0], sig[1], sig[2]);
+          tdb200_plan::TcExtra e{};
+          e.seg = s; e.sig[0] = sig[0]; e.sig[1] = sig[1]; e.sig[2] = sig[2];
+          e.tiles = (int)((sg.n_groups + Pe - 1) / Pe);
+          e.grid = e.tiles < 16 ? e.tiles : 16;                  // most CTAs a call gives it (partial rows are sized for it)
+          p->tc_extra.push_back(e);
+        }
+        rb[s + 1] = rb[s] + (eok ? 0 : simt_tiles);
+      }
+      (void)n_factors_max;
       p->simt_rest_tiles = rb[n_segments];
       p->simt_rest_grid = p->simt_rest_tiles < p->n_sms ? p->simt_rest_tiles : p->n_sms;
       if ((rc = upload(&p->d_seg_tile_begin_tc, tb.data(), tb.size()))) { tdb200_plan_destroy(p); return rc; }
@@ -218,6 +243,7 @@ int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_s
   }
   p->grad_rows = p->grid + tdb::jet_tc_partial_rows() * p->tc_grid + p->simt_rest_grid;
   p->loss_rows = p->grid + p->tc_grid + p->simt_rest_grid;
+  for (const auto& e : p->tc_extra) { p->grad_rows += tdb::jet_tc_partial_rows() * e.grid; p->loss_rows += e.grid; }
   if ((rc = upload<float>(&p->arena, nullptr, a.n_params_pad))) { tdb200_plan_destroy(p); return rc; }
   if ((rc = upload<float>(&p->arena_t, nullptr, a.n_params_pad))) { tdb200_plan_destroy(p); return rc; }
   {
@@ -316,7 +342,7 @@ static bool use_tc(const tdb200_plan* p) {
 int32_t tdb200_plan_launches_per_call(const tdb200_plan* p) {
   if (!p) return 0;
   if (!use_tc(p)) return 3;
-  return 4 + (p->simt_rest_tiles > 0 ? 1 : 0);
+  return 4 + (int)p->tc_extra.size() + (p->simt_rest_tiles > 0 ? 1 : 0);
 }
 
 static int run(tdb200_plan* p, const float* const* params, float* fields, float* out, int do_grad, void* stream) {
@@ -357,23 +383,40 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
     long long* dbg = nullptr;
     if (getenv("TDB200_TC_TIMING")) { cudaMalloc(&dbg, sizeof(long long) * 16 * p->tc_grid); }
     tc.dbg = dbg;
-    // The boundary rows (SIMT kernel, a few tiles of ~170 us each) run NEXT TO the tcgen05 launch on a side stream, on
-    // SMs the persistent tcgen05 grid leaves free, when few CTAs finish them within the tcgen05 launch's own time.
-    int side_ctas = 0;
-    if (p->simt_rest_tiles > 0 && p->tc_grid == p->n_sms && !dbg && !getenv("TDB200_NO_OVERLAP")) {
-      const double tc_us = 25.0 + 15.0 * ((p->tc_tiles + p->tc_grid - 1) / p->tc_grid);
-      const int k = (int)ceil(p->simt_rest_tiles * 170.0 / tc_us);
-      if (k <= p->n_sms / 8) side_ctas = k < 1 ? 1 : k;
+    // The boundary rows run NEXT TO the interior tcgen05 launch, on a side stream and on SMs the persistent interior
+    // grid leaves free: small tcgen05 launches for the identity segments, then the SIMT kernel for the rest (a few tiles
+    // of ~170 us each) when few CTAs finish it within the interior launch's own time.
+    const double tc_us = 25.0 + 15.0 * ((p->tc_tiles + p->tc_grid - 1) / p->tc_grid);
+    const bool may_fork = p->tc_grid == p->n_sms && !dbg && !getenv("TDB200_NO_OVERLAP");
+    int rest_ctas = p->simt_rest_grid, reserve = 0, extra_cap = 16;
+    bool fork = false;
+    if (may_fork) {
+      // fewest side CTAs that still finish inside the interior launch's own time (every reserved SM is taken from it)
+      auto extras_us = [&](int g) {
+        double us = 0.0;
+        for (const auto& e : p->tc_extra) { const int ge = e.grid < g ? e.grid : g; us += 30.0 + 15.0 * ((e.tiles + ge - 1) / ge); }
+        return us;
+      };
+      int g = 1;
+      while (g < 4 && extras_us(g) > 0.9 * tc_us) ++g;
+      const double side_us = extras_us(g);
+      if (!p->tc_extra.empty()) { extra_cap = g; reserve = g; }
+      if (p->simt_rest_tiles > 0) {
+        const double left = tc_us - side_us > 50.0 ? tc_us - side_us : 50.0;
+        int k = (int)ceil(p->simt_rest_tiles * 170.0 / left);
+        k = k < 1 ? 1 : k;
+        if (k <= p->n_sms / 8) { rest_ctas = k; reserve = k > reserve ? k : reserve; fork = true; }
+        else fork = false;                                      // too much SIMT work to hide: everything in stream order
+      } else {
+        fork = !p->tc_extra.empty();
+      }
+      if (!fork) { reserve = 0; extra_cap = 16; }
     }
-    const int tc_grid = p->tc_grid - side_ctas;
+    const int tc_grid = p->tc_grid - reserve;
     grad_rows = tdb::jet_tc_partial_rows() * tc_grid;
     loss_rows = tc_grid;
-    tdb::JetArgs rest = call;
-    rest.seg_tile_begin = p->d_seg_tile_begin_rest;
-    rest.n_tiles = p->simt_rest_tiles;
-    rest.part_grad = p->part_grad + (size_t)grad_rows * a.n_params_pad;
-    rest.part_loss = p->part_loss + (size_t)loss_rows * p->n_slots;
-    if (side_ctas) {
+    cudaStream_t ss = s;
+    if (fork) {
       if (!p->side) {
         CU(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
@@ -381,7 +424,38 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
       }
       CU(cudaEventRecord(p->ev_fork, s));
       CU(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
-      CU(tdb::launch_jet_simt(rest, side_ctas, p->side));       // enqueued first: its CTAs take their SMs first
+      ss = p->side;
+    }
+    int side_grad_rows = 0, side_loss_rows = 0;                  // rows of the side launches follow the interior rows
+    auto launch_side = [&]() -> int {
+      for (const auto& e : p->tc_extra) {
+        tdb::JetArgs x = call;
+        x.segs = a.segs + e.seg;
+        x.n_tiles = e.tiles;
+        x.row_weight = nullptr;
+        x.dbg = nullptr;
+        x.part_grad = p->part_grad + (size_t)(grad_rows + side_grad_rows) * a.n_params_pad;
+        x.part_loss = p->part_loss + (size_t)(loss_rows + side_loss_rows) * p->n_slots;
+        const int ge = e.grid < extra_cap ? e.grid : extra_cap;
+        CU(tdb::launch_jet_tc(x, p->wimg, e.sig[0], e.sig[1], e.sig[2], ge, ss));
+        side_grad_rows += tdb::jet_tc_partial_rows() * ge;
+        side_loss_rows += ge;
+      }
+      if (p->simt_rest_tiles > 0) {
+        tdb::JetArgs rest = call;
+        rest.seg_tile_begin = p->d_seg_tile_begin_rest;
+        rest.n_tiles = p->simt_rest_tiles;
+        rest.part_grad = p->part_grad + (size_t)(grad_rows + side_grad_rows) * a.n_params_pad;
+        rest.part_loss = p->part_loss + (size_t)(loss_rows + side_loss_rows) * p->n_slots;
+        CU(tdb::launch_jet_simt(rest, rest_ctas, ss));
+        side_grad_rows += rest_ctas;
+        side_loss_rows += rest_ctas;
+      }
+      return TDB200_OK;
+    };
+    if (fork) {                                                 // enqueued first: the side CTAs take their SMs first
+      const int rc = launch_side();
+      if (rc != TDB200_OK) return rc;
       CU(cudaEventRecord(p->ev_join, p->side));
     }
     CU(tdb::launch_jet_tc(tc, p->wimg, p->tc_sig[0], p->tc_sig[1], p->tc_sig[2], tc_grid, s));
@@ -394,15 +468,14 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
       for (int i = 0; i < 16; ++i) fprintf(stderr, " p%d=%lld", i, h[i] / tiles_per_cta);
       fprintf(stderr, "\n");
     }
-    if (side_ctas) {
+    if (fork) {
       CU(cudaStreamWaitEvent(s, p->ev_join, 0));
-      grad_rows += side_ctas;
-      loss_rows += side_ctas;
-    } else if (p->simt_rest_tiles > 0) {
-      CU(tdb::launch_jet_simt(rest, p->simt_rest_grid, s));
-      grad_rows += p->simt_rest_grid;
-      loss_rows += p->simt_rest_grid;
+    } else {
+      const int rc = launch_side();
+      if (rc != TDB200_OK) return rc;
     }
+    grad_rows += side_grad_rows;
+    loss_rows += side_loss_rows;
   } else {
     CU(tdb::launch_jet_simt(call, p->grid, s));
   }

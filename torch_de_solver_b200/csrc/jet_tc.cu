@@ -44,7 +44,10 @@ bool jet_tc_supports(int o0, int o1, int o2) {
 #undef X
   return false;
 }
-int jet_tc_points_per_tile(int o0, int o1, int o2) { return kTcParts * (kTcPC / (1 + o0 + o1 + o2)); }
+int jet_tc_points_per_tile(int o0, int o1, int o2) {
+  const int ph = kTcPC / (1 + o0 + o1 + o2);
+  return kTcParts * (ph > kTcMaxPts / kTcParts ? kTcMaxPts / kTcParts : ph);
+}
 int jet_tc_partial_rows() { return kTcParts; }
 int jet_tc_max_out() { return kTcMaxOut; }
 

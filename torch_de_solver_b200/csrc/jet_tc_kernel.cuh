@@ -321,7 +321,8 @@ template <int O0, int O1, int O2, int NMMA>
 __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, const float* __restrict__ wimg) {
   constexpr int J = 1 + O0 + O1 + O2;
   constexpr int ND = (O0 > 0) + (O1 > 0) + (O2 > 0);
-  constexpr int PH = kTcPC / J;                // points per column part
+  constexpr int PH = kTcPC / J > kTcMaxPts / kTcParts ? kTcMaxPts / kTcParts : kTcPC / J;   // points per column part
+                                               // (J = 1: capped by the per-tile point tables, 8 of 16 columns used)
   constexpr int P = kTcParts * PH;             // points per tile
   constexpr int C = PH * J;                    // used columns per part (<= 16)
   constexpr int JD = J > 1 ? J - 1 : 1;        // derivative channels per point
