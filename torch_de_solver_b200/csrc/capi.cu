@@ -208,14 +208,17 @@ int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_s
       tb[0] = 0;
       // boundary segments made of identity rows (Dirichlet values, autograd-mode operator conditions) take the tcgen05
       // kernel too - one small launch each on the side stream; periodic / finite-difference groups stay on the SIMT kernel
-      int n_factors_max = 0;
+      // ... when the interior launch is short (< ~1 ms): there the ~170 us SIMT boundary tile is the critical path.  Next
+      // to a long interior launch one SIMT CTA hides all boundary rows, and the tcgen05 side launches measured 4 % slower
+      // (wave, 10^6 points: 8.25 -> 8.57 ms).
+      const double tc_us_plan = 25.0 + 15.0 * ((p->tc_tiles + p->tc_grid - 1) / p->tc_grid);
+      const bool tc_boundary = tc_us_plan < 1000.0 && !getenv("TDB200_NO_TC_BOUNDARY");
       for (int s = 1; s < n_segments; ++s) {
         const tdb200_segment& sg = segments[s];
         int sig[3];
         for (int i = 0; i < 3; ++i) sig[i] = i < sg.n_dirs ? sg.dir_order[i] : 0;
         bool eok = sg.identity && sg.K == 1 && sg.n_dirs <= 3 && sg.n_groups > 0 && sg.n_cols >= 1 &&
-                   tdb::jet_tc_supports(sig[0], sig[1], sig[2]) && sg.col_term_end[sg.n_cols - 1] <= 48 &&
-                   !getenv("TDB200_NO_TC_BOUNDARY");
+                   tdb::jet_tc_supports(sig[0], sig[1], sig[2]) && sg.col_term_end[sg.n_cols - 1] <= 48 && tc_boundary;
         if (eok)
           for (int t = sg.col_term_begin[0]; t < sg.col_term_end[sg.n_cols - 1]; ++t) eok = eok && terms[t].fac_end <= 96;
         const int simt_tiles = p->seg_tile_begin[s + 1] - p->seg_tile_begin[s];
@@ -229,7 +232,6 @@ int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_s
         }
         rb[s + 1] = rb[s] + (eok ? 0 : simt_tiles);
       }
-      (void)n_factors_max;
       p->simt_rest_tiles = rb[n_segments];
       p->simt_rest_grid = p->simt_rest_tiles < p->n_sms ? p->simt_rest_tiles : p->n_sms;
       if ((rc = upload(&p->d_seg_tile_begin_tc, tb.data(), tb.size()))) { tdb200_plan_destroy(p); return rc; }
