@@ -191,7 +191,8 @@ int32_t tdb200_mat_plan_launches_per_call(const tdb200_mat_plan* plan);
 /* Which residual kernel tdb200_mat_loss_grad launches: 0 = generic tiled kernel (any operator), 1 = register-tap
  * kernel (one linear constant-coefficient equation), 2 = vectorised cross-stencil kernel (1 + n1 % 4 == 0),
  * 3 = persistent TMA-pipelined cross-stencil kernel (2 + at most one forcing buffer), 4 = register-marching
- * cross-stencil kernel (3 + stencil reach <= 2; followed by a small edge-frame launch). */
+ * cross-stencil kernel (3 + stencil reach <= 2; the edge frame is completed by the boundary launch, or by a small
+ * launch of its own when some boundary row is not a value row on a frame cell). */
 int32_t tdb200_mat_plan_kernel_kind(const tdb200_mat_plan* plan);
 /* Measurement aid (bench.py roofline): with timing on, every eager tdb200_mat_loss_grad / tdb200_mat_eval_fields call
  * records CUDA events on its stream around the launch of the residual (stencil) kernel alone; tdb200_mat_plan_stencil_ms

@@ -1445,6 +1445,99 @@ __global__ void __launch_bounds__(128) mat_bc_kernel(const MatBcArgs a) {
   mat_finalize_block(a.part_loss, a.n_ctas, a.n_eq, a.n_cells, a.slot_sum, a.n_bc_slots, a.slot_lambda, a.slot_len, a.out);
 }
 
+// Edge frame + boundary rows in ONE launch (register-marching plans whose boundary rows are all value rows on frame
+// cells).  Blocks [0, n_frame_blocks): one thread per frame cell adds (a) phase B of the edge treatment - coef * seed
+// over the special neighbours - and (b) the adjoint of every boundary row that touches the cell, found through a
+// cell -> (condition, row, k) CSR built on the host, to the gradient the stencil kernel stored: one owner per gradient
+// cell, fixed summation order, no atomics.  The remaining blocks reduce the boundary residuals into the loss slots.
+// The last block to finish assembles the loss as mat_bc_kernel does.
+struct MwEdgeBc {
+  int zy3, zx3, n_frame_blocks;
+  const float* es;                        // compact seeds written by phase A (previous launch)
+  const int* csr_off;                     // [frame cells + 1]
+  const int4* csr_ent;                    // {condition, row in the condition, k, unused}
+};
+__global__ void __launch_bounds__(128) mat_edge_bc_kernel(const MatBcArgs a, const MatArgs m, const MwEdgeBc e) {
+  __shared__ double sh_slot[32];
+  __shared__ unsigned int sh_ticket;
+  if (threadIdx.x < 32) sh_slot[threadIdx.x] = 0.0;
+  __syncthreads();
+  const size_t N = (size_t)a.n0 * a.n1;
+  auto row_residual = [&](const tdb200_mat_bc& bc, long long r) {
+    float val = 0.f;
+    for (int k = 0; k < bc.K; ++k) val += bc.sign[k] * __ldg(a.u + (size_t)bc.var * N + a.cells[bc.cell_off + r * bc.K + k]);
+    return val - a.targets[bc.tgt_off + r];
+  };
+  if ((int)blockIdx.x < e.n_frame_blocks) {
+    if (m.grad) {
+      const MwFrame fr(m, e.zy3, e.zx3);
+      const int n0 = m.n0, n1 = m.n1;
+      for (int idx = (int)(blockIdx.x * blockDim.x + threadIdx.x); idx < fr.total; idx += e.n_frame_blocks * (int)blockDim.x) {
+        int gy, gx;
+        fr.cell(idx, gy, gx);
+        float g = 0.f;
+#pragma unroll 2
+        for (int t = 0; t < m.n_lin; ++t) {
+          const tdb200_mat_field& f = m.fld[m.lin_q[t]];
+          float sacc = 0.f;
+          if (f.order == 0) {
+            sacc = __ldg(e.es + idx);                        // zero for regular cells
+          } else {
+            float sv[2 * kMwMaxHw + 1], cv[2 * kMwMaxHw + 1];
+#pragma unroll
+            for (int mm = -kMwMaxHw; mm <= kMwMaxHw; ++mm) {
+              const int yy = f.axis == 0 ? gy + mm : gy, xx = f.axis == 0 ? gx : gx + mm;
+              const bool ok = mm >= -f.half_width && mm <= f.half_width && yy >= 0 && yy < n0 && xx >= 0 && xx < n1 &&
+                              !fr.regular(yy, xx);
+              sv[mm + kMwMaxHw] = ok ? __ldg(e.es + fr.index(yy, xx)) : 0.f;
+              cv[mm + kMwMaxHw] = ok ? band_coef(m.band, f, f.axis == 0 ? n0 : n1, f.axis == 0 ? yy : xx, -mm) : 0.f;
+            }
+#pragma unroll
+            for (int mm = 0; mm <= 2 * kMwMaxHw; ++mm) sacc = fmaf(cv[mm], sv[mm], sacc);
+          }
+          g = fmaf(m.lin_c[t], sacc, g);
+        }
+        const int e0 = __ldg(e.csr_off + idx), e1 = __ldg(e.csr_off + idx + 1);
+        for (int q = e0; q < e1; ++q) {                      // boundary rows that touch this cell, in row order
+          const int4 en = __ldg(e.csr_ent + q);
+          const tdb200_mat_bc bc = a.bcs[en.x];
+          g = fmaf(2.f * a.slot_scale[bc.slot] * bc.sign[en.z], row_residual(bc, en.y), g);
+        }
+        if (g != 0.f) m.grad[(size_t)gy * n1 + gx] += g;
+      }
+    }
+  } else {
+    const long long total = a.bc_row_begin[a.n_bcs];
+    const long long stride = (long long)((int)gridDim.x - e.n_frame_blocks) * blockDim.x;
+    for (long long row = (long long)((int)blockIdx.x - e.n_frame_blocks) * blockDim.x + threadIdx.x; row < total; row += stride) {
+      int bi = 0;
+      while (row >= a.bc_row_begin[bi + 1]) ++bi;
+      const tdb200_mat_bc bc = a.bcs[bi];
+      const float res = row_residual(bc, row - a.bc_row_begin[bi]);
+      const unsigned act = __activemask();
+      double sq = (double)res * (double)res;
+      const int slot0 = __shfl_sync(act, bc.slot, __ffs(act) - 1);
+      if (act == 0xffffffffu && __all_sync(act, bc.slot == slot0)) {      // one shared-memory atomic per warp
+        for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(act, sq, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sh_slot[slot0], sq);
+      } else {
+        atomicAdd(&sh_slot[bc.slot], sq);
+      }
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < a.n_bc_slots && sh_slot[threadIdx.x] != 0.0) atomicAdd(a.slot_sum + threadIdx.x, sh_slot[threadIdx.x]);
+  if (!a.out) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) sh_ticket = atomicAdd(a.ticket, 1u);
+  __syncthreads();
+  if (sh_ticket != gridDim.x - 1) return;
+  __threadfence();
+  if (threadIdx.x == 0) { *a.ticket = 0u; *a.tile_ctr = 0u; }
+  mat_finalize_block(a.part_loss, a.n_ctas, a.n_eq, a.n_cells, a.slot_sum, a.n_bc_slots, a.slot_lambda, a.slot_len, a.out);
+}
+
 // ordered reduction of the per-CTA loss partials + loss assembly, by one block of any size <= 256
 __device__ void mat_finalize_block(const double* __restrict__ part_loss, int n_ctas, int n_eq, double n_cells,
                                    double* __restrict__ bc_sum, int n_bc_slots, const double* __restrict__ slot_lambda,
@@ -1524,6 +1617,10 @@ struct tdb200_mat_plan {
   bool tma = false;                        // persistent TMA variant of the cross kernel (single forcing buffer)
   bool march = false;                      // register-marching variant (reach <= 2, single forcing buffer)
   float* d_edge_seed = nullptr;            // march kernel: compact seeds of the frame cells with special stencil rows
+  bool edge_bc = false;                    // march plans: edge frame + boundary rows in one launch (value rows on frame cells)
+  int* d_csr_off = nullptr;                // frame cell -> boundary rows touching it
+  int4* d_csr_ent = nullptr;
+  int n_frame_blocks = 0;
   bool timing = false;                     // measurement aid: CUDA events around the stencil kernel launch
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   CUtensorMap map_u{}, map_f{};
@@ -1745,6 +1842,71 @@ int tdb200_mat_plan_set_bcs(tdb200_mat_plan* p, int32_t n_bcs, const tdb200_mat_
   if (!p->d_ticket) MCU(cudaMalloc(&p->d_ticket, 2 * sizeof(unsigned int)));   // [finalize ticket, tile counter]
   MCU(cudaMemset(p->d_ticket, 0, 2 * sizeof(unsigned int)));
   for (int e = 0; e < n_eq; ++e) p->args.eq_scale[e] = (float)(slot_lambda[e] / slot_len[e]);
+  {  // register-marching plans: can the edge frame and the boundary rows share one launch?  (every row a value row -
+     // Dirichlet / periodic values - and every cell it touches a frame cell: then the adjoint of the rows is gathered per
+     // frame cell through a cell -> row CSR instead of scattered with atomics after the edge launch)
+    p->edge_bc = false;
+    cudaFree(p->d_csr_off); cudaFree(p->d_csr_ent);
+    p->d_csr_off = nullptr; p->d_csr_ent = nullptr;
+    bool ok = p->march && p->args.lin1 && p->desc.n_var == 1 && !getenv("TDB200_MAT_NO_EDGE_BC");
+    long long n_cells_total = 0;
+    for (int i = 0; i < n_bcs && ok; ++i) {
+      ok = bcs[i].term_begin == bcs[i].term_end && bcs[i].var == 0;
+      n_cells_total += bcs[i].n_rows * bcs[i].K;
+    }
+    if (ok && n_cells_total > 0 && n_cells_total < (1ll << 24)) {
+      const tdb::MatArgs& a = p->args;
+      const int n0 = a.n0, n1 = a.n1, zy3 = a.edge_y + p->cx_hy, zx3 = a.edge_x + p->cx_hx;
+      const int top = zy3 < n0 ? zy3 : n0, bot = zy3 < n0 - top ? zy3 : n0 - top, mid = n0 - top - bot;
+      const int left = zx3 < n1 ? zx3 : n1, right = zx3 < n1 - left ? zx3 : n1 - left;
+      const long long n_band = (long long)(top + bot) * n1, total = n_band + (long long)mid * (left + right);
+      auto frame_index = [&](int gy, int gx) -> long long {
+        if (gy < top) return (long long)gy * n1 + gx;
+        if (gy >= n0 - bot) return (long long)(top + gy - (n0 - bot)) * n1 + gx;
+        if (gx < left) return n_band + (long long)(gy - top) * (left + right) + gx;
+        if (gx >= n1 - right) return n_band + (long long)(gy - top) * (left + right) + left + gx - (n1 - right);
+        return -1;
+      };
+      std::vector<int> cells((size_t)n_cells_total);
+      // the cells of condition i start at bcs[i].cell_off: copy the used range of cells_dev
+      long long lo = -1, hi = 0;
+      for (int i = 0; i < n_bcs; ++i) {
+        if (lo < 0 || bcs[i].cell_off < lo) lo = bcs[i].cell_off;
+        const long long end = bcs[i].cell_off + bcs[i].n_rows * bcs[i].K;
+        hi = end > hi ? end : hi;
+      }
+      std::vector<int> host((size_t)(hi - lo));
+      MCU(cudaMemcpy(host.data(), cells_dev + lo, sizeof(int) * host.size(), cudaMemcpyDeviceToHost));
+      std::vector<int> count((size_t)total + 1, 0);
+      for (int i = 0; i < n_bcs && ok; ++i)
+        for (long long r = 0; r < bcs[i].n_rows && ok; ++r)
+          for (int k = 0; k < bcs[i].K; ++k) {
+            const int cell = host[(size_t)(bcs[i].cell_off - lo + r * bcs[i].K + k)];
+            const long long fi = (cell >= 0 && cell < n0 * n1) ? frame_index(cell / n1, cell % n1) : -1;
+            if (fi < 0) { ok = false; break; }
+            ++count[(size_t)fi + 1];
+          }
+      if (ok) {
+        for (size_t c = 0; c < (size_t)total; ++c) count[c + 1] += count[c];
+        std::vector<int4> ent((size_t)count[(size_t)total]);
+        std::vector<int> fill(count.begin(), count.end() - 1);
+        for (int i = 0; i < n_bcs; ++i)                       // condition-major, row-major: a fixed summation order per cell
+          for (long long r = 0; r < bcs[i].n_rows; ++r)
+            for (int k = 0; k < bcs[i].K; ++k) {
+              const int cell = host[(size_t)(bcs[i].cell_off - lo + r * bcs[i].K + k)];
+              const long long fi = frame_index(cell / n1, cell % n1);
+              ent[(size_t)fill[(size_t)fi]++] = make_int4(i, (int)r, k, 0);
+            }
+        MCU(cudaMalloc(&p->d_csr_off, sizeof(int) * count.size()));
+        MCU(cudaMemcpy(p->d_csr_off, count.data(), sizeof(int) * count.size(), cudaMemcpyHostToDevice));
+        MCU(cudaMalloc(&p->d_csr_ent, sizeof(int4) * (ent.size() > 0 ? ent.size() : 1)));
+        if (!ent.empty()) MCU(cudaMemcpy(p->d_csr_ent, ent.data(), sizeof(int4) * ent.size(), cudaMemcpyHostToDevice));
+        const long long fb = (total + 127) / 128;
+        p->n_frame_blocks = (int)(fb < 1 ? 1 : fb > 592 ? 592 : fb);
+        p->edge_bc = true;
+      }
+    }
+  }
   tdb::MatBcArgs& b = p->bc;
   b.bcs = p->d_bcs; b.n_bcs = n_bcs; b.bc_row_begin = p->d_bc_row_begin; b.cells = cells_dev; b.targets = targets_dev;
   b.slot_scale = p->d_slot_scale; b.slot_sum = p->d_bc_sum;
@@ -1754,7 +1916,8 @@ int tdb200_mat_plan_set_bcs(tdb200_mat_plan* p, int32_t n_bcs, const tdb200_mat_
 
 // the residual (stencil) launch(es) of one call; *n_ctas = number of loss partials they write
 static int mat_stencil(tdb200_mat_plan* p, tdb::MatArgs& a, const float* u, float* grad, float* op_out, int* n_ctas_out,
-                       cudaEvent_t after_stencil, bool main_only, cudaStream_t s) {
+                       cudaEvent_t after_stencil, bool main_only, cudaStream_t s, bool* ran_march = nullptr) {
+  if (ran_march) *ran_march = false;
   int n_ctas = p->n_ctas;
   bool ev1_done = false;
   if (a.lin1 && !op_out) {
@@ -1776,7 +1939,9 @@ static int mat_stencil(tdb200_mat_plan* p, tdb::MatArgs& a, const float* u, floa
       }
     }
     if (p->march && vec_ok) {
-      MCU(tdb::launch_mat_march(a, p->cx_hy, p->cx_hx, p->cx_my, p->cx_mx, p->n_sms, p->d_edge_seed, after_stencil, main_only, s));
+      MCU(tdb::launch_mat_march(a, p->cx_hy, p->cx_hx, p->cx_my, p->cx_mx, p->n_sms, p->d_edge_seed, after_stencil,
+                                main_only || p->edge_bc, s));
+      if (ran_march) *ran_march = true;
       ev1_done = true;
       n_ctas = tdb::mat_march_ctas(a, p->n_sms);
     } else if (tma) {
@@ -1809,12 +1974,14 @@ static int mat_run(tdb200_mat_plan* p, const float* u, float* grad, float* op_ou
   a.u = u; a.grad = grad; a.op_out = op_out; a.tile_ctr = p->d_ticket + 1;
   int n_ctas = p->n_ctas;
   if (p->timing) MCU(cudaEventRecord(p->ev0, s));
+  bool ran_march = false;
   {
-    const int rc = mat_stencil(p, a, u, grad, op_out, &n_ctas, p->timing ? p->ev1 : nullptr, false, s);
+    const int rc = mat_stencil(p, a, u, grad, op_out, &n_ctas, p->timing ? p->ev1 : nullptr, false, s, &ran_march);
     if (rc != TDB200_OK) return rc;
   }
   // boundary rows; the last block to finish reduces the loss partials and assembles the loss (and re-zeroes the
   // slot sums and its ticket for the next call)
+  const bool merged = p->edge_bc && ran_march && p->n_bc_rows > 0;
   if (p->n_bc_rows > 0) {
     tdb::MatBcArgs b = p->bc;
     b.u = u; b.grad = grad; b.bval_out = bval_out;
@@ -1822,7 +1989,14 @@ static int mat_run(tdb200_mat_plan* p, const float* u, float* grad, float* op_ou
     b.n_cells = (double)p->desc.n0 * (double)p->desc.n1;
     b.slot_lambda = p->d_slot_lambda; b.slot_len = p->d_slot_len; b.out = out; b.ticket = p->d_ticket; b.tile_ctr = p->d_ticket + 1;
     const int blocks = (int)((p->n_bc_rows + 127) / 128);
-    tdb::mat_bc_kernel<<<blocks < 1184 ? blocks : 1184, 128, 0, s>>>(b);
+    if (merged) {
+      tdb::MwEdgeBc eb{};
+      eb.zy3 = a.edge_y + p->cx_hy; eb.zx3 = a.edge_x + p->cx_hx; eb.n_frame_blocks = p->n_frame_blocks;
+      eb.es = p->d_edge_seed; eb.csr_off = p->d_csr_off; eb.csr_ent = p->d_csr_ent;
+      tdb::mat_edge_bc_kernel<<<p->n_frame_blocks + (blocks < 1184 ? blocks : 1184), 128, 0, s>>>(b, a, eb);
+    } else {
+      tdb::mat_bc_kernel<<<blocks < 1184 ? blocks : 1184, 128, 0, s>>>(b);
+    }
     MCU(cudaGetLastError());
   } else {
     tdb::mat_finalize_kernel<<<1, 256, 0, s>>>(p->d_part_loss, n_ctas, p->desc.n_eq,
@@ -1844,7 +2018,7 @@ int tdb200_mat_eval_fields(tdb200_mat_plan* p, const float* u_dev, float* op_dev
 }
 
 int64_t tdb200_mat_plan_out_size(const tdb200_mat_plan* p) { return p ? 2 + p->n_slots : 0; }
-int32_t tdb200_mat_plan_launches_per_call(const tdb200_mat_plan* p) { return p ? (p->args.lin1 && p->march ? 3 : 2) : 0; }
+int32_t tdb200_mat_plan_launches_per_call(const tdb200_mat_plan* p) { return p ? (p->args.lin1 && p->march && !p->edge_bc ? 3 : 2) : 0; }
 
 int tdb200_mat_plan_set_row_window(tdb200_mat_plan* p, int32_t row_lo, int32_t row_hi) {
   if (!p) return mat_invalid("null plan");
@@ -1903,7 +2077,7 @@ void tdb200_mat_plan_destroy(tdb200_mat_plan* p) {
   cudaSetDevice(p->device);
   cudaFree(p->d_band); cudaFree(p->d_terms); cudaFree(p->d_factors); cudaFree(p->d_bcs); cudaFree(p->d_bc_row_begin);
   cudaFree(p->d_slot_scale); cudaFree(p->d_slot_lambda); cudaFree(p->d_slot_len); cudaFree(p->d_part_loss);
-  cudaFree(p->d_bc_sum); cudaFree(p->d_ticket); cudaFree(p->d_edge_seed);
+  cudaFree(p->d_bc_sum); cudaFree(p->d_ticket); cudaFree(p->d_edge_seed); cudaFree(p->d_csr_off); cudaFree(p->d_csr_ent);
   if (p->ev0) { cudaEventDestroy(p->ev0); cudaEventDestroy(p->ev1); }
   delete p;
 }
