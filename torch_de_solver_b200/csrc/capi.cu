@@ -204,6 +204,10 @@ int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_s
       const int P = tdb::jet_tc_points_per_tile(p->tc_sig[0], p->tc_sig[1], p->tc_sig[2]);
       p->tc_tiles = (int)((s0.n_groups + P - 1) / P);
       p->tc_grid = p->tc_tiles < p->n_sms ? p->tc_tiles : p->n_sms;
+      if (getenv("TDB200_TC_GRID")) {                       // experiment knob: fewer persistent CTAs (contention studies)
+        const int g = atoi(getenv("TDB200_TC_GRID"));
+        if (g >= 1 && g < p->tc_grid) p->tc_grid = g;
+      }
       std::vector<int> tb(n_segments + 1, p->tc_tiles), rb(n_segments + 1, 0);
       tb[0] = 0;
       // boundary segments made of identity rows (Dirichlet values, autograd-mode operator conditions) take the tcgen05
