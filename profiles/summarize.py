@@ -38,7 +38,13 @@ def launches(name):
     unit = rows[1][hdr.index('Metric Unit')]
     with open(os.path.join(PR, f'{R}_launches_{name}.md'), 'w') as f:
         f.write(f'# {R}: launches of `python bench.py` ({name}) under `ncu --metrics gpu__time_duration.sum`\n\n')
-        f.write('Cold-cache, serialised timings: compare shares, not absolutes.\n\n| kernel | launches | total | share |\n|---|---|---|---|\n')
+        f.write('Cold-cache, serialised timings: compare shares, not absolutes.\n\n')
+        if name == 'wave':
+            f.write('NOTE: in the real step `jet_simt_kernel` (all boundary rows, ONE CTA, side stream) runs CONCURRENTLY with '
+                    '`jet_tc_kernel` (147 CTAs) and ends before it (DESIGN 3.4); ncu serialises the two launches, so the '
+                    'share below is its duration on one SM, not a share of the step.  With `TDB200_NO_OVERLAP=1` the same '
+                    'rows take ~0.19 ms on 32 CTAs after the interior launch (2 % of the step).\n\n')
+        f.write('| kernel | launches | total | share |\n|---|---|---|---|\n')
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f'| `{k}` | {n} | {t:.1f} {unit} | {100 * t / tot:.1f} % |\n')
     shutil.copy(src, os.path.join(PR, f'{R}_launches_{name}.csv'))
