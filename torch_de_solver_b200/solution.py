@@ -296,10 +296,24 @@ class Solution:
         self._plan.set_row_weights(w.reshape(-1))
 
     def _sync_lambdas(self):
+        """Push lambda_operator / lambda_bound to the plan when they changed (callbacks such as AdaptiveLambda assign new
+        tensors).  Reading a device tensor back is a host sync, so unchanged objects (same identity and version counter)
+        are not looked at again: the steady-state step has no sync before the launch."""
+        key = tuple((id(x), getattr(x, '_version', None)) for x in (self.lambda_operator, self.lambda_bound))
+        if key == getattr(self, '_lam_key', None):
+            return
+        self._lam_key = key
         n_eq = self._n_slots - len(self.bval_keys)
-        lam_op = lambda_prepare(torch.empty(1, n_eq), 1 if self.tol != 0 else self.lambda_operator).reshape(-1).tolist()
-        lam_b = lambda_prepare(torch.empty(1, len(self.bval_keys)), self.lambda_bound).reshape(-1).tolist()
-        lam = [float(x) for x in lam_op + lam_b]
+
+        def as_list(lam, n):
+            if isinstance(lam, torch.Tensor):
+                return [float(x) for x in lam.detach().reshape(-1).cpu().tolist()]
+            if isinstance(lam, (int, float)):
+                return [float(lam)] * n
+            return [float(x) for x in lam]
+        lam_op = as_list(1 if self.tol != 0 else self.lambda_operator, n_eq)
+        lam_b = as_list(self.lambda_bound, len(self.bval_keys))
+        lam = lam_op + lam_b
         if len(lam) != self._n_slots:
             raise ValueError(f'expected {self._n_slots} lambdas, got {len(lam)}')
         if lam != list(self._plan.slot_lambda):
@@ -342,8 +356,10 @@ class Solution:
         self.loss_normalized = self._last_out[1:2].clone()
         n_eq = self._n_slots - len(self.bval_keys)
         dt = torch.float32
-        self.lambda_operator = lambda_prepare(torch.empty(1, n_eq), self.lambda_operator).to(dt)
-        self.lambda_bound = lambda_prepare(torch.empty(1, len(self.bval_keys)), self.lambda_bound).to(dt)
+        if not isinstance(self.lambda_operator, torch.Tensor) or self.lambda_operator.dtype != dt:
+            self.lambda_operator = lambda_prepare(torch.empty(1, n_eq), self.lambda_operator).to(dt)
+        if not isinstance(self.lambda_bound, torch.Tensor) or self.lambda_bound.dtype != dt:
+            self.lambda_bound = lambda_prepare(torch.empty(1, len(self.bval_keys)), self.lambda_bound).to(dt)
         return self.loss, self.loss_normalized
 
     # per-column mean squares of the last evaluation (the natural partial results)
