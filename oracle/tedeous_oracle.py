@@ -8,7 +8,8 @@ residual-loss hot path, TEDEouS v0.4.11:
     Derivative_NN/_autograd/_mat tedeous/derivative.py:18-323
     Finite_diffs                tedeous/finite_diffs.py:9-268
     Points_type                 tedeous/points_type.py:40-157
-    Losses                      tedeous/losses.py:38-182, 230-263
+    Losses                      tedeous/losses.py:38-263 (default, causal and weak-form losses)
+    integration / weak residual tedeous/eval.py:13-52, 195-221
     lambda_prepare / unify      tedeous/input_preprocessing.py:14-81, 239-264, 319-408, 553-575
 
 The arithmetic of the reference lives in torch (requirements.txt:6 `torch >= 2.0`, unpinned; torch

@@ -142,3 +142,53 @@ def test_mat_slabs_reduce_to_single_rank_result(name, world, tmp_path):
     assert float(ref_out[0]) == pytest.approx(float(g['loss']), rel=1e-6)
     gn = np.linalg.norm(g['grad'])
     assert np.linalg.norm(grad.reshape(-1) - g['grad']) <= 1e-6 * gn
+
+
+# ---- causal loss over ranks: prefix sums of the time slices cross the rank boundary ------------------------------------
+def test_causal_weights_over_two_ranks(tmp_path):
+    """burgers_autograd_causal has 31 time slices of 31 rows: two ranks cannot own whole slices -> explicit error; the
+    weights of a 2-rank run on a grid with an even number of slices equal the single-rank weights."""
+    from torch_de_solver_b200.solution import causal_row_weights
+    from torch_de_solver_b200.plan import UnsupportedProblem
+    g, prob, model, ir = lower('burgers_autograd_causal')
+    _, _, _, fields = evaluate_ir(ir, model)
+    res = (fields[0].detach() ** 2).sum(1)
+    tol = prob.compile_kwargs['tol']
+    w_ref = causal_row_weights(res, tol, ir.n_t, ir.n_interior)
+    m = ir.n_interior // ir.n_t
+    want = torch.exp(-tol * (torch.tril(torch.ones(ir.n_t, ir.n_t, dtype=torch.float64), -1) @ res.reshape(ir.n_t, m)))
+    np.testing.assert_allclose(w_ref.numpy(), want.reshape(-1).numpy(), rtol=1e-12)      # losses.py:167-171
+    with pytest.raises(UnsupportedProblem, match='split a time slice'):
+        causal_row_weights(res[:480], tol, ir.n_t, ir.n_interior, (0, 480), 2)
+    # a slice-aligned split: emulate two ranks owning 15 and 16 slices through the public function and gloo
+    world = 2
+    out = str(tmp_path / 'causal.npz')
+    # rows (n * rank) // world are slice aligned only for an even slice count: use the aligned helper below
+    mp.spawn(_causal_aligned_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    got = np.load(out)
+    np.testing.assert_allclose(got['w'], w_ref.numpy(), rtol=1e-12)
+    assert float(got['loss_op'][0]) == pytest.approx(float((w_ref * res).sum() / ir.n_interior), rel=1e-12)
+
+
+def _causal_aligned_worker(rank, world, port, out_path):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from torch_de_solver_b200.solution import causal_row_weights
+        g, prob, model, ir = lower('burgers_autograd_causal')    # every rank lowers the full problem, owns whole slices
+        _, _, _, fields = evaluate_ir(ir, model)
+        m = ir.n_interior // ir.n_t
+        cut = (ir.n_t // 2) * m
+        lo, hi = (0, cut) if rank == 0 else (cut, ir.n_interior)
+        res = (fields[0].detach() ** 2).sum(1)[lo:hi]
+        w = causal_row_weights(res, prob.compile_kwargs['tol'], ir.n_t, ir.n_interior, (lo, hi), world)
+        part = torch.zeros(ir.n_interior, dtype=torch.float64)
+        part[lo:hi] = w
+        dist.all_reduce(part)
+        loss_part = (w * res).sum().reshape(1) / ir.n_interior
+        dist.all_reduce(loss_part)
+        if rank == 0:
+            np.savez(out_path, w=part.numpy(), loss_op=loss_part.numpy())
+    finally:
+        dist.destroy_process_group()

@@ -134,6 +134,35 @@ class FusedPlan:
             pass
 
 
+def causal_row_weights(res_rows: torch.Tensor, tol: float, n_t: int, n_global: int, shard_range=None, world: int = 1,
+                       group=None) -> torch.Tensor:
+    """No-grad weights of the causal loss (tedeous/losses.py:160-171) for this rank's block of interior rows.
+
+    res_rows [n_local] = sum over equations of op^2 for the rows [lo, hi) = `shard_range` of the global row order (grid
+    column 0 slowest).  With M = n_global / n_t rows per time slice, w[t, j] = exp(-tol * sum_{s < t} res[s, j]): an
+    exclusive prefix sum over the time slices, column by column, instead of the reference's [n_t, n_t] triangular
+    matmul.  Several ranks own whole time slices each; the prefix of a rank starts from the column totals of the ranks
+    below it: one all-gather of M floats per rank."""
+    if n_global % n_t:
+        n_t = n_global                                     # the reference's fallback (losses.py:162-165): one row per slice
+    m = n_global // n_t
+    lo, hi = shard_range if shard_range is not None else (0, res_rows.numel())
+    if world > 1 and (lo % m or hi % m):
+        raise UnsupportedProblem(f'causal loss over {world} ranks: rows [{lo}, {hi}) of this rank split a time slice of '
+                                 f'{m} rows; choose a grid whose number of time slices ({n_t}) is a multiple of the ranks')
+    res = res_rows.detach().reshape(-1, m)
+    excl = torch.cumsum(res, 0) - res
+    if world > 1:
+        import torch.distributed as dist
+        tot = res.sum(0).contiguous()
+        parts = [torch.empty_like(tot) for _ in range(world)]
+        dist.all_gather(parts, tot, group=group)
+        rank = dist.get_rank(group)
+        if rank > 0:
+            excl = excl + torch.stack(parts[:rank]).sum(0)
+    return torch.exp(-float(tol) * excl).reshape(-1)
+
+
 class _FusedLoss(torch.autograd.Function):
     """loss = plan(params); backward returns the gradient the same launch already produced."""
 
@@ -192,8 +221,6 @@ class Solution:
             raise UnsupportedProblem('weak-form loss: no causal weights, not sharded over ranks')
         if tol != 0 and mode == 'mat':
             raise UnsupportedProblem('causal loss (tol != 0) is implemented for modes NN / autograd only (SURVEY 8 a10)')
-        if tol != 0 and shard is not None and shard[1] > 1:
-            raise UnsupportedProblem('causal loss needs the prefix sums of all time slices: not sharded over ranks')
         if batch_size is not None and mode != 'NN':
             raise UnsupportedProblem('mini-batching is not implemented by the fused path; shard points over '
                                      'GPUs instead')
@@ -288,12 +315,9 @@ class Solution:
         seg = self._ir.segments[0]
         n, ncols = seg.n_groups, len(seg.cols)
         op = fields[:n * ncols].reshape(n, ncols)
-        n_t = self._ir.n_t
-        if n % n_t:
-            n_t = n                                            # the reference's fallback (losses.py:162-165)
-        res = (op * op).sum(1).reshape(n_t, -1)
-        w = torch.exp(-float(self.tol) * (torch.cumsum(res, 0) - res))
-        self._plan.set_row_weights(w.reshape(-1))
+        w = causal_row_weights((op * op).sum(1), self.tol, self._ir.n_t, self._ir.n_interior,
+                               getattr(seg, 'shard_range', None), self._shard[1], self._pg)
+        self._plan.set_row_weights(w)
 
     def _sync_lambdas(self):
         """Push lambda_operator / lambda_bound to the plan when they changed (callbacks such as AdaptiveLambda assign new
