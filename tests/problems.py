@@ -51,6 +51,11 @@ def make_mat_model(shape, dtype=torch.float32, seed=0) -> torch.Tensor:
     """mat-mode "model" = the solution values on the grid ([n_eq, N0, N1], tedeous/models.py:198-226).  The
     default all-ones tensor has zero derivatives everywhere, so tests use a smooth field plus noise."""
     torch.manual_seed(seed)
+    if len(shape) == 2:          # 1-D grid
+        n_eq, n0 = shape
+        x = torch.linspace(0, 1, n0)
+        base = torch.stack([torch.sin(3 * x + k) for k in range(n_eq)])
+        return (base + 0.05 * torch.rand(shape)).to(dtype)
     n_eq, n0, n1 = shape
     x = torch.linspace(0, 1, n0)[:, None]
     y = torch.linspace(0, 1, n1)[None, :]
@@ -200,6 +205,9 @@ def legendre_ode(api, dtype='float32', n=40, mode='autograd', layers=(1, 32, 32,
     kw = dict(lambda_operator=1, lambda_bound=10)
     if mode == 'NN':
         kw['h'] = h
+    if mode == 'mat':           # 1-D grid, model [1, n + 1] (examples/examples_legendre/example_ODE_Legendre_matrix.py)
+        return Problem('legendre_mat', dom, bc, eq, 'mat', [], dict(lambda_operator=1, lambda_bound=10, derivative_points=2),
+                       mat_shape=(1, n + 1))
     return Problem(f'legendre_{mode}', dom, bc, eq, mode, list(layers), kw)
 
 
@@ -359,6 +367,7 @@ ZOO: Dict[str, Callable] = {
     'navier_stokes_autograd': lambda api, dt: navier_stokes(api, dt, n=8),
     'legendre_autograd': lambda api, dt: legendre_ode(api, dt, mode='autograd'),
     'legendre_NN': lambda api, dt: legendre_ode(api, dt, mode='NN'),
+    'legendre_mat_1d': lambda api, dt: legendre_ode(api, dt, n=48, mode='mat'),
     'nonlinear_mix_autograd': lambda api, dt: nonlinear_mix(api, dt, mode='autograd'),
     'nonlinear_mix_NN': lambda api, dt: nonlinear_mix(api, dt, mode='NN'),
     'poisson_mat_p2': lambda api, dt: poisson_mat(api, dt, n=32, derivative_points=2),

@@ -59,3 +59,19 @@ def test_cell_indices():
     assert idx.tolist() == [1 * 9 + 0, 4 * 9 + 6, 0 * 9 + 8]
     with pytest.raises(ValueError):
         cell_indices(grid, torch.tensor([[0.3, 0.0]]))
+
+
+def test_one_dimensional_grid_is_lifted():
+    """1-D mat-mode grids ([1, N0], the ODE examples) are lowered as [N0, 1] grids with a dummy second axis: the dense
+    fp64 interpretation of the lowered problem reproduces the reference's loss and gradient."""
+    import numpy as np
+    from mat_interp import evaluate_mat_ir
+    from test_distributed_cpu import _mat_ir
+    g, ir, u = _mat_ir('legendre_mat_1d', (0, 1))
+    assert ir.lifted and ir.shape_ext[2] == 1
+    out, grad = evaluate_mat_ir(ir, u.unsqueeze(-1))
+    # (the lowering divides by the fp32 grid step the fp32 reference computes, derivative.py:229-247; h = 1/48 is not a
+    # binary fraction, so the fp64 fixture differs at the 1e-8 level)
+    assert float(out[0]) == pytest.approx(float(g['loss']), rel=1e-6)
+    gref = g['grad']
+    assert np.linalg.norm(grad.reshape(-1).numpy() - gref) <= 1e-6 * np.linalg.norm(gref)

@@ -101,7 +101,7 @@ def step_h(grid: torch.Tensor) -> List[float]:
     hs = []
     for c in _axis_coords(grid):
         u = torch.unique(c.float())
-        hs.append(float(abs(u[1] - u[0])))
+        hs.append(float(abs(u[1] - u[0])) if u.numel() > 1 else 1.0)     # (dummy axis of a lifted 1-D grid: unused)
     return hs
 
 
@@ -113,6 +113,9 @@ def cell_indices(grid: torch.Tensor, bnd: torch.Tensor) -> torch.Tensor:
     flat = torch.zeros(bnd.shape[0], dtype=torch.int64, device=bnd.device)
     for a, coords in enumerate(axes):
         c = coords.float()
+        if c.numel() == 1 or a >= bnd.shape[1]:            # dummy axis of a lifted 1-D grid
+            flat = flat * shape[a]
+            continue
         x = bnd[:, a].float()
         order = torch.argsort(c)
         cs = c[order]
@@ -139,8 +142,13 @@ class MatIR:
 
     def __init__(self, grid: torch.Tensor, prepared_operator: List[dict], bconds: List[dict], n_var: int,
                  device, lambda_operator, lambda_bound, derivative_points: int = 2, shard=(0, 1)):
+        self.lifted = grid.dim() == 2                      # 1-D grid [1, N0] -> [2, N0, 1] with a dummy second axis
+        grid_user = grid                                   # what callable coefficients are evaluated on (derivative.py:319)
+        if self.lifted:
+            x = grid[0].reshape(-1, 1)
+            grid = torch.stack([x, torch.zeros_like(x)])
         if grid.dim() != 3:
-            raise UnsupportedProblem('the fused mat path supports 2-D grids ([2, N0, N1], model [n_eq, N0, N1])')
+            raise UnsupportedProblem('the fused mat path supports 1-D and 2-D grids ([d, N0(, N1)], model [n_eq, N0(, N1)])')
         if not bconds:
             raise UnsupportedProblem('a problem without boundary conditions has no finite loss in the reference')
         rank, world = shard
@@ -183,10 +191,13 @@ class MatIR:
                 if isinstance(c, torch.nn.Parameter):
                     raise UnsupportedProblem('trainable coefficients in mat mode')
                 if callable(c) and not isinstance(c, torch.Tensor):
-                    c = c(grid)
+                    c = c(grid_user)
                 if isinstance(c, torch.Tensor) and c.numel() > 1:
                     terms.append([0.0, 1, len(coefs_full), fb, len(factors)])       # idx = buffer number for now
-                    coefs_full.append(torch.broadcast_to(c.to(device, torch.float32), (n0, n1)))
+                    c = c.to(device, torch.float32)
+                    if self.lifted:                                                 # [1, N0] / [N0] values of a 1-D grid
+                        c = c.reshape(-1, 1) if c.numel() == n0 else c
+                    coefs_full.append(torch.broadcast_to(c, (n0, n1)))
                 else:
                     terms.append([float(c), 0, 0, fb, len(factors)])
             return begin, len(terms)
@@ -348,8 +359,15 @@ class MatPlan:
 
     def __init__(self, grid: torch.Tensor, prepared_operator: List[dict], bconds: List[dict], model: torch.Tensor,
                  lambda_operator, lambda_bound, derivative_points: int = 2, shard=None, process_group=None):
+        # 1-D grids ([1, N0], model [n_eq, N0]: the ODE examples, example_ODE_Legendre_matrix.py, example_LV_mat.py) run as
+        # [N0, 1] grids with a dummy second axis - same memory, no derivative field along it
+        self._lift = grid.dim() == 2 and model.dim() == 2
+        if self._lift:
+            if shard is not None and shard[1] > 1:
+                raise UnsupportedProblem('1-D mat-mode grids are not sharded over ranks')
+            model = model.detach().unsqueeze(-1)          # (MatIR lifts the grid the same way)
         if model.dim() != 3:
-            raise UnsupportedProblem('the fused mat path supports 2-D grids ([2, N0, N1], model [n_eq, N0, N1])')
+            raise UnsupportedProblem('the fused mat path supports 1-D and 2-D grids ([d, N0(, N1)], model [n_eq, N0(, N1)])')
         if model.dtype != torch.float32:
             raise UnsupportedProblem('mat-mode model must be float32')
         shard = (0, 1) if shard is None else shard
@@ -416,6 +434,8 @@ class MatPlan:
         self._push_bcs()
 
     def _check_model(self, u):
+        if self._lift and tuple(u.shape) == self.shape[:2]:
+            return
         if tuple(u.shape) != self.shape or u.dtype != torch.float32 or not u.is_cuda or not u.is_contiguous():
             raise RuntimeError(f'mat-mode model must be a contiguous float32 CUDA tensor of shape {self.shape}')
 
@@ -459,6 +479,9 @@ class MatPlan:
         """-> (out [2 + n_slots] summed over ranks, d loss / d u of this rank's rows).  Several ranks: halo rows from
         the neighbours (point-to-point), then one all-reduce of the loss terms; the gradient stays sharded."""
         self._check_model(u)
+        if self._lift and u.dim() == 2:
+            out, grad = self.loss_grad_ext(u.unsqueeze(-1))
+            return out, grad.squeeze(-1)
         out, grad = self.loss_grad_ext(exchange_halos(u, self.ir, self._pg, self._ext))
         if self.ir.shard[1] > 1:
             import torch.distributed as dist
