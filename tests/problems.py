@@ -333,6 +333,10 @@ def lotka_weak(api, dtype='float32', n=40, mode='NN', layers=(1, 32, 32, 2)):
             '+y*delta': {'coeff': delta, 'term': [None], 'pow': 1, 'var': [1]},
             '-gamma*x*y': {'coeff': -gamma, 'term': [[None], [None]], 'pow': [1, 1], 'var': [0, 1]}})
 
+    if mode == 'mat':           # examples/examples_lotka_volterra/example_LV_mat.py: 1-D grid, two fields
+        return Problem('lotka_mat', dom, bc, eq, 'mat', [], dict(lambda_operator=1, lambda_bound=100, derivative_points=2),
+                       mat_shape=(2, n + 1))
+
     def v(grid):
         return (0.5 + 0.5 * torch.sin(grid[:, 0])) * (2 / h) ** 0.5 / 10
     kw = dict(lambda_operator=1, lambda_bound=100, weak_form=[v])
@@ -368,6 +372,7 @@ ZOO: Dict[str, Callable] = {
     'legendre_autograd': lambda api, dt: legendre_ode(api, dt, mode='autograd'),
     'legendre_NN': lambda api, dt: legendre_ode(api, dt, mode='NN'),
     'legendre_mat_1d': lambda api, dt: legendre_ode(api, dt, n=48, mode='mat'),
+    'lotka_mat_1d': lambda api, dt: lotka_weak(api, dt, n=64, mode='mat'),
     'nonlinear_mix_autograd': lambda api, dt: nonlinear_mix(api, dt, mode='autograd'),
     'nonlinear_mix_NN': lambda api, dt: nonlinear_mix(api, dt, mode='NN'),
     'poisson_mat_p2': lambda api, dt: poisson_mat(api, dt, n=32, derivative_points=2),

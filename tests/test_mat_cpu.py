@@ -61,13 +61,14 @@ def test_cell_indices():
         cell_indices(grid, torch.tensor([[0.3, 0.0]]))
 
 
-def test_one_dimensional_grid_is_lifted():
+@pytest.mark.parametrize('name', ['legendre_mat_1d', 'lotka_mat_1d'])
+def test_one_dimensional_grid_is_lifted(name):
     """1-D mat-mode grids ([1, N0], the ODE examples) are lowered as [N0, 1] grids with a dummy second axis: the dense
     fp64 interpretation of the lowered problem reproduces the reference's loss and gradient."""
     import numpy as np
     from mat_interp import evaluate_mat_ir
     from test_distributed_cpu import _mat_ir
-    g, ir, u = _mat_ir('legendre_mat_1d', (0, 1))
+    g, ir, u = _mat_ir(name, (0, 1))
     assert ir.lifted and ir.shape_ext[2] == 1
     out, grad = evaluate_mat_ir(ir, u.unsqueeze(-1))
     # (the lowering divides by the fp32 grid step the fp32 reference computes, derivative.py:229-247; h = 1/48 is not a

@@ -180,6 +180,8 @@ class MatIR:
                 dif = list(term.keys())[1]
                 fb = len(factors)
                 for spec, pw, var in zip(term[dif], term['pow'], term['var']):
+                    if isinstance(var, (list, tuple)) and len(var) == 1:
+                        var = var[0]         # 'var': [0] next to a scalar 'pow' (equation_unify wraps it once more)
                     if callable(pw):
                         raise UnsupportedProblem("callable 'pow' is not supported by the fused path")
                     spec = [] if spec == [None] else spec
@@ -525,6 +527,10 @@ class MatPlan:
             bval[base:base + n, slot] = rows[off:off + n]
             tval[base:base + n, slot] = self._targets[off:off + n]
             off += n
+        if self.shape[0] > 1:
+            # the reference forms every term as ones_like(model) * field (derivative.py:306): with n_var fields in the
+            # model the residual of an equation comes out n_var times, [n_var * N, n_eq] - reproduced for `Solution.op`
+            op = op.repeat(self.shape[0], 1)
         return op, bval, tval
 
     def __del__(self):
