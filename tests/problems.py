@@ -294,6 +294,31 @@ def heat_mat(api, dtype='float32', n=32, nt=32, derivative_points=2):
                    mat_shape=(1, n + 1, nt + 1))
 
 
+def schrodinger_mat(api, dtype='float32', n=20, nt=28, derivative_points=2):
+    """Two coupled fields on a 2-D grid in mat mode: u_t + 0.5 v_xx + (u^2 + v^2) v = 0, v_t - 0.5 u_xx - (u^2 + v^2) u = 0
+    (examples/examples_schrodinger/example_schrodinger_matrix.py pattern: products of powers across fields)."""
+    dom = api.Domain()
+    dom.variable('x', [-2, 2], n, dtype=dtype)
+    dom.variable('t', [0, 1], nt, dtype=dtype)
+    bc = api.Conditions()
+    bc.dirichlet({'x': [-2, 2], 't': 0}, value=lambda g: 2 / torch.cosh(g[:, 0]), var=0)
+    bc.dirichlet({'x': [-2, 2], 't': 0}, value=0., var=1)
+    bc.periodic([{'x': -2, 't': [0, 1]}, {'x': 2, 't': [0, 1]}], var=0)
+    bc.periodic([{'x': -2, 't': [0, 1]}, {'x': 2, 't': [0, 1]}], var=1)
+    eq = api.Equation()
+    eq.add({'du/dt': {'coeff': 1, 'term': [1], 'pow': 1, 'var': 0},
+            '1/2*d2v/dx2': {'coeff': 0.5, 'term': [0, 0], 'pow': 1, 'var': 1},
+            'v*u**2': {'coeff': 1, 'term': [[None], [None]], 'pow': [1, 2], 'var': [1, 0]},
+            'v**3': {'coeff': 1, 'term': [None], 'pow': 3, 'var': 1}})
+    eq.add({'dv/dt': {'coeff': 1, 'term': [1], 'pow': 1, 'var': 1},
+            '-1/2*d2u/dx2': {'coeff': -0.5, 'term': [0, 0], 'pow': 1, 'var': 0},
+            '-u*v**2': {'coeff': -1, 'term': [[None], [None]], 'pow': [1, 2], 'var': [0, 1]},
+            '-u**3': {'coeff': -1, 'term': [None], 'pow': 3, 'var': 0}})
+    return Problem('schrodinger_mat', dom, bc, eq, 'mat', [],
+                   dict(lambda_operator=1, lambda_bound=[5., 7.], derivative_points=derivative_points),
+                   mat_shape=(2, n + 1, nt + 1))
+
+
 def kdv_mat(api, dtype='float32', n=24, derivative_points=2):
     """Nonlinear mat-mode operator with 3rd derivative, periodic + operator conditions
     (examples/examples_korteweg_de_vries/example_KdV_matrix.py pattern)."""
@@ -378,6 +403,7 @@ ZOO: Dict[str, Callable] = {
     'poisson_mat_p2': lambda api, dt: poisson_mat(api, dt, n=32, derivative_points=2),
     'poisson_mat_p3': lambda api, dt: poisson_mat(api, dt, n=24, derivative_points=3),
     'kdv_mat_p2': lambda api, dt: kdv_mat(api, dt, n=24, derivative_points=2),
+    'schrodinger_mat_p2': lambda api, dt: schrodinger_mat(api, dt),
     # grids with n1 % 4 == 0: served by the vectorised cross-stencil kernel (one tile, every cell next to an edge)
     'poisson_mat_p2_rect': lambda api, dt: poisson_mat(api, dt, n=40, ny=63, derivative_points=2),
     'poisson_mat_p3_rect': lambda api, dt: poisson_mat(api, dt, n=24, ny=43, derivative_points=3),
