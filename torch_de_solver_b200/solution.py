@@ -221,9 +221,14 @@ class Solution:
             raise UnsupportedProblem('weak-form loss: no causal weights, not sharded over ranks')
         if tol != 0 and mode == 'mat':
             raise UnsupportedProblem('causal loss (tol != 0) is implemented for modes NN / autograd only (SURVEY 8 a10)')
-        if batch_size is not None and mode != 'NN':
-            raise UnsupportedProblem('mini-batching is not implemented by the fused path; shard points over '
-                                     'GPUs instead')
+        if batch_size is not None:
+            # The reference draws shuffled mini-batches of the points (eval.py:124-141: DataLoader(shuffle=True) with its own
+            # generator) - a stochastic estimate of the same loss.  The fused path evaluates EVERY point each step (the
+            # expectation of that estimate; at 10^8 points/s a batch of 32 is pure launch latency), and says so once.
+            import warnings
+            warnings.warn('batch_size is ignored by the fused path: every collocation point is evaluated on every step '
+                          '(the full-batch loss, i.e. the expectation of the reference\'s shuffled mini-batch loss)',
+                          stacklevel=2)
         self.grid = check_device(grid)
         _require_cuda(self.grid, 'grid')
         self.mode = mode
