@@ -1037,7 +1037,11 @@ __global__ void __launch_bounds__(kMwThreads, 2) mat_march_kernel(const MatArgs 
   }
 }
 
-constexpr int kMwEdgeBlocks = 148;                           // phase A CTAs (256 threads) = phase B CTAs x 2 (128 threads)
+static int mw_edge_blocks() {                                  // phase A CTAs (256 threads); phase B uses twice as many of 128
+  static const int n = getenv("TDB200_MARCH_EDGE_BLOCKS") ? atoi(getenv("TDB200_MARCH_EDGE_BLOCKS")) : 148;
+  return n < 1 ? 1 : n > 592 ? 592 : n;
+}
+#define kMwEdgeBlocks mw_edge_blocks()
 // rows per chunk: every SM gets ~16 warps in a single wave (the y-halo of a chunk costs 4 HY extra row loads)
 static int mat_march_chunk(const MatArgs& a, int n_sms) {
   const int n_strips = (a.n1 + kMwOutW - 1) / kMwOutW;
