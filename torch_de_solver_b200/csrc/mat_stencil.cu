@@ -771,7 +771,7 @@ static bool make_map_2d(CUtensorMap* map, const float* ptr, int n0, int n1, int 
 
 // ---- register-marching cross-stencil kernel ---------------------------------------------------------------
 // BASELINE config 4 (Poisson 4096 x 4096), second generation.  No shared-memory tiles, no block barriers, no 2-D halo:
-// every WARP owns a column strip (32 lanes x float4 = 128 loaded columns, the inner 28 lanes = 112 columns are its
+// every WARP owns a column strip (32 lanes x float4 = 128 loaded columns, the inner 30 lanes = 120 columns are its
 // output) and marches down a chunk of rows.  The last 2 HY + 1 + P rows of u, the last 2 HY + 1 rows of residual seeds
 // and the forcing rows in flight live in REGISTERS (rings indexed at compile time: the row loop is unrolled by the
 // ring length); x-neighbours come from the two adjacent lanes by warp shuffles.  Per row and thread: two 16-byte
@@ -779,7 +779,8 @@ static bool make_map_2d(CUtensorMap* map, const float* ptr, int n0, int n1, int 
 // by occupancy), <= 8 shuffles, ~45 FMAs, one 16-byte store.  Seeds of cells whose stencil rows are special (one-sided
 // rows near the domain edge) are zero here; `mat_march_edge_kernel` adds their loss and gradient contributions.
 constexpr int kMwWarps = 8, kMwThreads = kMwWarps * 32;
-constexpr int kMwOutLanes = 28, kMwOutW = 4 * kMwOutLanes;   // lanes 2..29 own output columns
+constexpr int kMwOutLanes = 30, kMwOutW = 4 * kMwOutLanes;   // lanes 1..30 own output columns: the composite stencil reaches
+// 2 HX <= 4 columns = ONE float4 lane to each side (lanes 0 / 31 hold u and the two seed columns next to the strip)
 constexpr unsigned kFullMask = 0xffffffffu;
 
 // r[i] += sum_dx wx[dx] * row[x_i + dx] (REV: row[x_i - dx]) for the 4 cells of a thread; neighbours by shuffle
@@ -947,10 +948,10 @@ __global__ void __launch_bounds__(kMwThreads, 2) mat_march_kernel(const MatArgs 
   } else if (item < n_items) {                               // warp-uniform
     const int chunk = item / n_strips, strip = item - chunk * n_strips;
     const int y0 = chunk * ch, y1 = min(y0 + ch, n0);
-    const int x = strip * kMwOutW - 8 + 4 * lane;            // column of this thread's first element
+    const int x = strip * kMwOutW - 4 + 4 * lane;            // column of this thread's first element
     const bool col_ok = x >= 0 && x < n1;                    // n1 % 4 == 0: the float4 is entirely inside or outside
-    const bool own = col_ok && lane >= 2 && lane < 2 + kMwOutLanes;
-    const bool f_ok = col_ok && lane >= 1 && lane <= 30 && a.l1_fbuf[0] != nullptr;
+    const bool own = col_ok && lane >= 1 && lane < 1 + kMwOutLanes;
+    const bool f_ok = col_ok && a.l1_fbuf[0] != nullptr;
     const bool do_grad = a.grad != nullptr;
     const int zy = a.edge_y, zx = a.edge_x;
     // The stencil weights are read from the kernel parameters where they are used (constant-bank operands of the FFMAs,
@@ -1037,11 +1038,8 @@ __global__ void __launch_bounds__(kMwThreads, 2) mat_march_kernel(const MatArgs 
   }
 }
 
-static int mw_edge_blocks() {                                  // phase A CTAs (256 threads); phase B uses twice as many of 128
-  static const int n = getenv("TDB200_MARCH_EDGE_BLOCKS") ? atoi(getenv("TDB200_MARCH_EDGE_BLOCKS")) : 148;
-  return n < 1 ? 1 : n > 592 ? 592 : n;
-}
-#define kMwEdgeBlocks mw_edge_blocks()
+constexpr int kMwEdgeBlocks = 296;                           // phase A CTAs (256 threads: one frame cell per thread at 4096^2;
+                                                             // measured 148 -> 296: 62.7 -> 61.5 us per step)
 // rows per chunk: every SM gets ~16 warps in a single wave (the y-halo of a chunk costs 4 HY extra row loads)
 static int mat_march_chunk(const MatArgs& a, int n_sms) {
   const int n_strips = (a.n1 + kMwOutW - 1) / kMwOutW;
@@ -1074,7 +1072,7 @@ static cudaError_t launch_mat_march_t(const MatArgs& a, int n_sms, float* edge_s
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess && after_stencil) e = cudaEventRecord(after_stencil, s);
   if (e != cudaSuccess || !a.grad || main_only) return e;
-  mat_march_edge_kernel<<<2 * kMwEdgeBlocks, 128, 0, s>>>(a, a.edge_y + HY, a.edge_x + HX, edge_seeds);
+  mat_march_edge_kernel<<<kMwEdgeBlocks, 128, 0, s>>>(a, a.edge_y + HY, a.edge_x + HX, edge_seeds);
   return cudaGetLastError();
 }
 // instantiated for the cross shapes with reach <= 2 (wider stencils keep too many rows in registers)
