@@ -54,7 +54,7 @@ WORKLOADS = {
 MAT_BYTES_PER_CELL = 12      # read u, read the forcing tensor, write d loss / d u (fp32) - SURVEY 8d
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
 # captures (profiles/r01_ncu_jet_tc.md, profiles/r01_ncu_mat.md); None where no capture exists
-NCU_TRAFFIC_BYTES = {'wave_autograd_1e6': 8.57e6 + 5.14e6, 'poisson_mat_4096': 147.94e6 + 36.34e6}
+NCU_TRAFFIC_BYTES = {'wave_autograd_1e6': 8.57e6 + 5.14e6, 'poisson_mat_4096': 147.86e6 + 35.75e6}
 
 
 def flop_per_point(layers, J):
