@@ -462,3 +462,22 @@ def test_vector_jacobian_product_of_fields(name, cuda_default):
     # and the plain loss path is untouched by the seed-mode call
     loss, _ = sol.evaluate()
     assert float(loss) == pytest.approx(float(g['loss']), rel=LOSS_RTOL)
+
+
+def test_mat_stencil_timing_entry_points(cuda_default):
+    """Measurement aids of the C ABI (bench.py roofline): events around the stencil kernel of an eager call, and
+    back-to-back launches of the stencil kernel alone; neither changes the results of later calls."""
+    prob = problems.poisson_mat(tdb, 'float32', n=255, ny=255, derivative_points=2)
+    u = problems.make_mat_model(prob.mat_shape, torch.float32).to('cuda:0').contiguous()
+    model = tdb.Model(u, prob.domain, prob.equation, prob.conditions)
+    model.compile('mat', **prob.compile_kwargs)
+    plan = model.solution_cls._plan
+    assert plan.kernel_kind == 'cross-march' and plan.launches_per_call == 2
+    out0, grad0 = plan.loss_grad_raw(u)
+    plan.set_timing(True)
+    plan.loss_grad_raw(u)
+    assert 0.0 < plan.stencil_ms() < 50.0
+    plan.set_timing(False)
+    assert 0.0 < plan.time_stencil(u, 5) < 50.0
+    out1, grad1 = plan.loss_grad_raw(u)
+    assert torch.equal(grad0, grad1) and float(out0[0]) == pytest.approx(float(out1[0]), rel=1e-6)
