@@ -481,3 +481,26 @@ def test_mat_stencil_timing_entry_points(cuda_default):
     assert 0.0 < plan.time_stencil(u, 5) < 50.0
     out1, grad1 = plan.loss_grad_raw(u)
     assert torch.equal(grad0, grad1) and float(out0[0]) == pytest.approx(float(out1[0]), rel=1e-6)
+
+
+def test_lambda_changes_are_picked_up(cuda_default):
+    """Callbacks replace or modify lambda_operator / lambda_bound between steps (AdaptiveLambda): new objects, new
+    values of the same kind and in-place updates must all reach the plan (the steady state re-reads nothing)."""
+    g = load_golden('burgers_NN_small', 'float64')
+    prob, net, sol = fused('burgers_NN_small', g['weights'])
+
+    def check(lam_op, lam_b):
+        loss, _ = sol.evaluate()
+        want = float(sol.op_mse.sum()) * lam_op + float(sol.bval_mse.sum()) * lam_b
+        assert float(loss) == pytest.approx(want, rel=1e-5)
+
+    check(1.0, 10.0)
+    sol.lambda_bound = 3.0
+    check(1.0, 3.0)
+    for v in (7.0, 9.0, 11.0):                       # fresh tensors: a recycled id must not look unchanged
+        sol.lambda_bound = torch.tensor([[v]], device='cuda:0')
+        check(1.0, v)
+    sol.lambda_bound.mul_(2.0)                       # in place
+    check(1.0, 22.0)
+    sol.lambda_operator = torch.tensor([[0.5]], device='cuda:0')
+    check(0.5, 22.0)

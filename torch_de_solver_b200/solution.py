@@ -328,10 +328,12 @@ class Solution:
         """Push lambda_operator / lambda_bound to the plan when they changed (callbacks such as AdaptiveLambda assign new
         tensors).  Reading a device tensor back is a host sync, so unchanged objects (same identity and version counter)
         are not looked at again: the steady-state step has no sync before the launch."""
-        key = tuple((id(x), getattr(x, '_version', None)) for x in (self.lambda_operator, self.lambda_bound))
-        if key == getattr(self, '_lam_key', None):
+        objs = (self.lambda_operator, self.lambda_bound)
+        vers = tuple(getattr(x, '_version', None) for x in objs)
+        seen = getattr(self, '_lam_seen', None)               # holds references: an id cannot be recycled while cached
+        if seen is not None and all(a is b for a, b in zip(seen[0], objs)) and seen[1] == vers:
             return
-        self._lam_key = key
+        self._lam_seen = (objs, vers)
         n_eq = self._n_slots - len(self.bval_keys)
 
         def as_list(lam, n):
