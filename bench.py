@@ -195,6 +195,14 @@ def run_b200(args):
             dist.all_reduce(out)
         return out
 
+    graphed = False
+    if world == 1 and n_local < 100_000 and not args.no_graph:      # launch-bound sizes: one CUDA graph per step
+        try:
+            step_resident, _ = plan.capture()
+            graphed = True
+        except Exception as e:                # noqa: BLE001 - report and time eager launches
+            sys.stderr.write(f'[bench] CUDA graph capture failed ({e}); timing eager launches\n')
+
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
 
     def timed(fn, steps):
@@ -278,6 +286,7 @@ def run_b200(args):
         'config': {'workload': args.workload, 'description': spec['desc'], 'points_per_gpu': n_local,
                    'points_total': n_global, 'mlp': list(prob.net_layers), 'mode': prob.mode,
                    'jet_channels': spec['J'], 'kernel': 'simt-fp32' if plan.launches_per_call == 3 else 'tcgen05-3xtf32 (interior) + simt-fp32 (boundary rows)',
+                   'cuda_graph': graphed,
                    'l2': 'flushed between timed steps (256 MB write)', 'parallelism': f'dp{world} (points sharded)'},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': e2e_ms / e2e_steps},

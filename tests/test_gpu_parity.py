@@ -504,3 +504,20 @@ def test_lambda_changes_are_picked_up(cuda_default):
     check(1.0, 22.0)
     sol.lambda_operator = torch.tensor([[0.5]], device='cuda:0')
     check(0.5, 22.0)
+
+
+def test_graph_captured_step_matches_eager(cuda_default):
+    """FusedPlan.capture(): the replayed graph (fork / join of the boundary launches included) returns the eager result
+    and follows in-place parameter updates."""
+    g = load_golden('burgers_NN_cfg1', 'float64')
+    prob, net, sol = fused('burgers_NN_cfg1', g['weights'])
+    eager = sol._plan.loss_grad().clone()
+    replay, out = sol._plan.capture()
+    replay()
+    assert torch.equal(out, eager)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(1.01)
+    replay()
+    assert torch.equal(out, sol._plan.loss_grad())
+    assert not torch.equal(out, eager)

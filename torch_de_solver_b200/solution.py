@@ -117,6 +117,23 @@ class FusedPlan:
                       'tdb200_loss_grad')
         return out
 
+    def capture(self):
+        """CUDA graph of one loss + gradient call (pack, interior and boundary launches with their fork / join, reduction)
+        for steps that are launch bound (BASELINE config 1: ~0.15 ms of GPU work in 8 launches).  -> (replay callable,
+        out): `out` is a static [2 + n_slots + n_params] tensor refreshed by every replay; the parameter tensors must
+        keep their storage (in-place optimiser updates do)."""
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):                          # warm-up outside the capture (function attributes, side stream)
+                self.loss_grad()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self.loss_grad()
+        return graph.replay, out
+
     def eval_fields(self) -> Tuple[torch.Tensor, torch.Tensor]:
         fields = torch.empty(max(self.n_fields, 1), dtype=torch.float32, device=self.device)
         out = torch.empty(self.out_size, dtype=torch.float32, device=self.device)
