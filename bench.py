@@ -1,17 +1,22 @@
 #!/usr/bin/env python
 """Benchmark of the residual-loss hot path: collocation points per second for one loss + gradient step.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME] [--no-configs]
 
 * A *step* is one evaluation of loss and the full parameter gradient over every collocation point
   (`Solution.evaluate(); loss.backward()` in the reference, one `tdb200_loss_grad` call here), plus the NCCL
   all-reduce of the [loss terms | gradient] vector when N > 1.
-* Default workload = BASELINE.json configs[1]: wave equation 1D+t, mode 'autograd' (2nd-order jets), 10^6
-  collocation points per GPU, tanh MLP 2-100-100-100-1.  Scaling is weak: every rank holds 10^6 points.
+* The top-level line is BASELINE.json's metric configuration: **Burgers 1D, mode 'NN', 101 x 101 grid, tanh MLP
+  2-100-100-100-1** (configs[0], `burgers_NN_cfg1`).  Scaling is weak: with N ranks the grid has 101 N x 101 nodes
+  and every rank holds a 101 x 101 block of it.
+* The other BASELINE configs are measured in the same run, each with its own `value` / `e2e` / `roofline` /
+  `cpu_baseline`, under the extra key `configs` (wave 10^6, Burgers NN 10^6, KdV 1.25 10^6 per GPU = 10^7 over 8,
+  Navier-Stokes 1.25 10^6 per GPU = 10^7 over 8, Poisson mat 4096^2 per GPU).  `--workload NAME` measures one
+  workload only (top level), `--no-configs` skips the extra ones.
 * `value` is timed with inputs resident in HBM; `e2e` goes through the public API (`Solution.evaluate` +
-  `loss.backward()`) with the step's point set copied from pinned host memory and the result read back.
-* `--impl reference` times the CPU port of the reference's algorithm (oracle/tedeous_oracle.py, torch CPU,
-  all host threads) on a bounded sample of the same workload.
+  `loss.backward()`) with the step's inputs copied from pinned host memory and the result read back.
+* `--impl reference` times the reference's own CPU implementation (`oracle/_ref`: the unmodified TEDEouS package,
+  installed by oracle/make_ref.py; falls back to the oracle port when it is absent) with every host thread.
 
 One JSON line on stdout (rank 0).
 """
@@ -22,7 +27,6 @@ import statistics
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -32,33 +36,63 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
-METRIC = 'collocation pts/s for loss+grad step'
+METRIC = 'collocation pts/s for loss+grad step (Burgers 1D, NN mode)'
 UNIT = 'pts/s'
+HEADLINE = 'burgers_NN_cfg1'
+MLP3 = (2, 100, 100, 100, 1)
 
-# algorithmic FLOPs per point: 3 (fwd, bwd-data, bwd-weight) * J jet channels * 2 * sum(in*out)  
+# name: builder in tests/problems.py, kwargs of the single-GPU problem, jet channels J, description.
+# `axis0` names the kwarg of the slowest (sharded) axis: with N ranks it grows to (n + 1) N - 1 intervals.
 WORKLOADS = {
-    # name: (builder name in tests/problems.py, kwargs, J, description)
-    'wave_autograd_1e6': dict(fn='wave', kw=dict(n=999, mode='autograd', layers=(2, 100, 100, 100, 1)), J=5,
-                              desc='wave 1D+t autograd, 1000x1000 pts/GPU, MLP 2-100-100-100-1'),
-    'burgers_NN_cfg1': dict(fn='burgers', kw=dict(n=100, mode='NN', layers=(2, 100, 100, 100, 1)), J=4,
-                            desc='Burgers 1D NN mode, 101x101 grid (9801 central pts), MLP 2-100-100-100-1'),
-    'burgers_autograd_1e6': dict(fn='burgers', kw=dict(n=999, mode='autograd', layers=(2, 100, 100, 100, 1)), J=4,
-                                 desc='Burgers 1D autograd, 1000x1000 pts/GPU'),
-    'kdv_autograd_1e6': dict(fn='kdv', kw=dict(nx=999, nt=999, mode='autograd', layers=(2, 100, 100, 100, 1)), J=5,
-                             desc='KdV periodic autograd, 1000x1000 pts/GPU'),
-    'ns_autograd_1e6': dict(fn='navier_stokes', kw=dict(n=99, layers=(3, 100, 100, 100, 100, 100, 100, 3)), J=6,
-                            desc='Navier-Stokes 2D+t autograd, 100^3 pts/GPU, MLP 3-100x6-3'),
+    'burgers_NN_cfg1': dict(fn='burgers', kw=dict(n=100, mode='NN', layers=MLP3), J=4, axis0='n0',
+                            desc='Burgers 1D NN mode (h = 0.001), 101x101 grid per GPU (9801 central pts), MLP 2-100-100-100-1'),
+    'wave_autograd_1e6': dict(fn='wave', kw=dict(n=999, mode='autograd', layers=MLP3), J=5, axis0='n0',
+                              desc='wave 1D+t autograd, 1000x1000 pts per GPU, MLP 2-100-100-100-1'),
+    'burgers_NN_1e6': dict(fn='burgers', kw=dict(n=999, mode='NN', layers=MLP3), J=4, axis0='n0',
+                           desc='Burgers 1D NN mode (h = 0.001), 1000x1000 grid per GPU (998x998 central pts)'),
+    'burgers_autograd_1e6': dict(fn='burgers', kw=dict(n=999, mode='autograd', layers=MLP3), J=4, axis0='n0',
+                                 desc='Burgers 1D autograd, 1000x1000 pts per GPU'),
+    'kdv_autograd_1e7over8': dict(fn='kdv', kw=dict(nx=1249, nt=999, mode='autograd', layers=MLP3), J=5, axis0='nx',
+                                  desc='KdV periodic autograd, 1250x1000 pts per GPU (10^4 x 10^3 = 10^7 over 8 GPUs)'),
+    'ns_autograd_1e7over8': dict(fn='navier_stokes', kw=dict(n=214, n0=26, layers=(3, 100, 100, 100, 100, 100, 100, 3)),
+                                 J=6, axis0='n0',
+                                 desc='Navier-Stokes 2D+t autograd, 27x215x215 pts per GPU (216x215x215 = 10^7 over 8 GPUs), MLP 3-100x6-3'),
+    'ns_autograd_1e6': dict(fn='navier_stokes', kw=dict(n=99, layers=(3, 100, 100, 100, 100, 100, 100, 3)), J=6, axis0='n0',
+                            desc='Navier-Stokes 2D+t autograd, 100^3 pts per GPU, MLP 3-100x6-3'),
     'poisson_mat_4096': dict(fn='poisson_mat', kw=dict(n=4095, derivative_points=2), J=0, mat=True,
-                             desc="Poisson 2D mode 'mat', 4096x4096 grid, u_xx + u_yy - f, Dirichlet edges"),
+                             desc="Poisson 2D mode 'mat', 4096x4096 grid per GPU, u_xx + u_yy - f, Dirichlet edges"),
 }
+EXTRA_CONFIGS = ['wave_autograd_1e6', 'burgers_NN_1e6', 'kdv_autograd_1e7over8', 'ns_autograd_1e7over8', 'poisson_mat_4096']
 MAT_BYTES_PER_CELL = 12      # read u, read the forcing tensor, write d loss / d u (fp32) - SURVEY 8d
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
-# captures (profiles/r01_ncu_jet_tc.md, profiles/r01_ncu_mat.md); None where no capture exists
-NCU_TRAFFIC_BYTES = {'wave_autograd_1e6': 8.57e6 + 5.14e6, 'poisson_mat_4096': 147.86e6 + 35.75e6}
+
+# bounded CPU samples of the same operators for the reference arm (the reference's cost per point is flat in N,
+# BASELINE.md 2); config 1 is timed at its full size
+CPU_SAMPLE = {
+    'burgers_NN_cfg1': dict(fn='burgers', kw=dict(n=100, mode='NN', layers=MLP3)),
+    'wave_autograd_1e6': dict(fn='wave', kw=dict(n=315, mode='autograd', layers=MLP3)),
+    'burgers_NN_1e6': dict(fn='burgers', kw=dict(n=140, mode='NN', layers=MLP3)),
+    'burgers_autograd_1e6': dict(fn='burgers', kw=dict(n=315, mode='autograd', layers=MLP3)),
+    'kdv_autograd_1e7over8': dict(fn='kdv', kw=dict(nx=199, nt=199, mode='autograd', layers=MLP3)),
+    'ns_autograd_1e7over8': dict(fn='navier_stokes', kw=dict(n=20, layers=(3, 100, 100, 100, 100, 100, 100, 3))),
+    'ns_autograd_1e6': dict(fn='navier_stokes', kw=dict(n=20, layers=(3, 100, 100, 100, 100, 100, 100, 3))),
+    'poisson_mat_4096': dict(fn='poisson_mat', kw=dict(n=255, derivative_points=2)),
+}
 
 
 def flop_per_point(layers, J):
+    """Algorithmic FLOPs per point: 3 (fwd, bwd-data, bwd-weight) * J jet channels * 2 * sum(in*out)  (SURVEY 8d)."""
     return 3 * J * 2 * sum(a * b for a, b in zip(layers[:-1], layers[1:]))
+
+
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the workload's dominant kernel, from the committed
+    `ncu --set full` captures: profiles/ncu_traffic.json, written by profiles/summarize.py next to the summaries."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+            rec = json.load(f).get(workload)
+        return None if rec is None else float(rec['bytes'])
+    except Exception:                       # noqa: BLE001 - no capture: the key stays null
+        return None
 
 
 class ClockSampler:
@@ -146,40 +180,83 @@ def measure_tf32_tflops(device, seconds=1.0):
     return best
 
 
-def make_problem(workload, api, world):
-    """The workload with `world` times more nodes along the first axis (weak scaling: every rank keeps the
-    single-GPU number of points)."""
-    import problems
+def workload_kwargs(workload, world):
+    """kwargs of the problem with `world` times more nodes along the first (sharded) axis: weak scaling, every rank
+    keeps the single-GPU number of points."""
     spec = WORKLOADS[workload]
     kw = dict(spec['kw'])
-    if world > 1:
-        if 'nx' in kw:
-            kw['nx'] = (kw['nx'] + 1) * world - 1
-        else:
-            kw['n0'] = (kw['n'] + 1) * world - 1
-    return spec, getattr(problems, spec['fn'])(api, 'float32', **kw)
+    if world > 1 and not spec.get('mat'):
+        base = kw.get(spec['axis0']) or kw['n']
+        kw[spec['axis0']] = (base + 1) * world - 1
+    return spec, kw
+
+
+def common_config(workload, world):
+    """The part of `config` both arms print (the driver compares it)."""
+    spec = WORKLOADS[workload]
+    return {'workload': workload, 'description': spec['desc'], 'scaling_rule': 'weak: the grid grows along axis 0 with the '
+            'number of GPUs, every rank holds the single-GPU block', 'n_gpus': world}
+
+
+class Ctx:
+    """Per-process state shared by the measurements of one run."""
+
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.args = args
+        self.dist = dist
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.local = int(os.environ.get('LOCAL_RANK', '0'))
+        if args.gpus > 1 and self.world != args.gpus:
+            raise SystemExit(f'--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={self.world})')
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device('cuda', self.local)
+        if self.world > 1:
+            dist.init_process_group('nccl', device_id=self.dev)
+        self.flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=self.dev)   # > 126 MB L2
+        self.peaks, self.peak_src = load_peaks()
+        self._tf32 = None
+
+    def tf32(self):
+        if self._tf32 is None:
+            torch.set_default_device('cpu')
+            self._tf32 = measure_tf32_tflops(self.dev)
+        return self._tf32
+
+    def timed(self, fn, steps):
+        """CUDA-event time of every step on the launching (current) stream, L2 flushed between steps."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for e0, e1 in ev:
+            self.flush.zero_()
+            e0.record()
+            fn()
+            e1.record()
+        torch.cuda.synchronize(self.dev)
+        return [e0.elapsed_time(e1) for e0, e1 in ev]
+
+    def barrier(self):
+        torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            self.dist.barrier()
+
+    def max_over_ranks(self, x):
+        if self.world > 1:
+            t = torch.tensor([x], device=self.dev, dtype=torch.float64)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            return float(t)
+        return x
 
 
 # ----------------------------------------------------------------------------------------------------
-def run_b200(args):
-    import torch.distributed as dist
+def measure_nn(ctx, workload, steps, warmup, with_cpu):
+    """One NN / autograd workload -> dict (value, ms_per_step, e2e, roofline, gpu_launches, config, clocks...)."""
     import torch_de_solver_b200 as tdb
     import problems
-
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    if args.gpus > 1 and world != args.gpus:
-        raise SystemExit(f'--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})')
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+    args, dev, world, rank = ctx.args, ctx.dev, ctx.world, ctx.rank
     torch.set_default_device(dev)
-
-    if WORKLOADS[args.workload].get('mat'):
-        return run_b200_mat(args, dev, tdb, problems, rank, world)
-    spec, prob = make_problem(args.workload, tdb, world)
+    spec, kw = workload_kwargs(workload, world)
+    prob = getattr(problems, spec['fn'])(tdb, 'float32', **kw)
     net = problems.make_net(prob.net_layers, torch.float32, prob.init).to(dev)
     model = tdb.Model(net, prob.domain, prob.equation, prob.conditions)
     model.compile(prob.mode, **prob.compile_kwargs, shard=(rank, world) if world > 1 else None)
@@ -190,50 +267,27 @@ def run_b200(args):
     params = list(net.parameters())
 
     def step_resident():
-        out = plan.loss_grad()
-        if world > 1:
-            dist.all_reduce(out)
-        return out
+        return sol._run_plan()[0]               # launches + (N > 1) the all-reduce of [loss terms | gradient]
 
     graphed = False
-    if world == 1 and n_local < 100_000 and not args.no_graph:      # launch-bound sizes: one CUDA graph per step
+    if n_local < 100_000 and not args.no_graph:          # launch-bound sizes: one CUDA graph per step
         try:
-            step_resident, _ = plan.capture()
+            step_resident, _ = sol.capture_step()
             graphed = True
         except Exception as e:                # noqa: BLE001 - report and time eager launches
-            sys.stderr.write(f'[bench] CUDA graph capture failed ({e}); timing eager launches\n')
+            sys.stderr.write(f'[bench] {workload}: CUDA graph capture failed ({e}); timing eager launches\n')
+            step_resident = lambda: sol._run_plan()[0]
 
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
-
-    def timed(fn, steps):
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        for e0, e1 in ev:
-            flush.zero_()
-            e0.record()
-            fn()
-            e1.record()
-        torch.cuda.synchronize(dev)
-        return [e0.elapsed_time(e1) for e0, e1 in ev]
-
-    sampler = ClockSampler(local)           # started before the warm-up: nvidia-smi needs ~0.2 s to deliver samples
+    sampler = ClockSampler(ctx.local)         # started before the warm-up: nvidia-smi needs ~0.2 s to deliver samples
     sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step_resident()
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
+    ctx.barrier()
     t_wall = time.time()
-    times = timed(step_resident, args.steps)
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
+    times = ctx.timed(step_resident, steps)
+    ctx.barrier()
     clocks = sampler.stop()
-    total_ms = sum(times)
-    if world > 1:
-        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t)
-    ms_per_step = total_ms / args.steps
+    ms_per_step = ctx.max_over_ranks(sum(times)) / steps
     value = n_global / (ms_per_step * 1e-3)
 
     # ---- end to end through the public API, host buffers ----------------------------------------------
@@ -255,63 +309,52 @@ def run_b200(args):
 
     for _ in range(3):
         step_e2e()
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    e2e_steps = max(3, min(args.steps, 20))
-    e2e_times = timed(step_e2e, e2e_steps)
-    e2e_ms = sum(e2e_times)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t)
-    e2e_value = n_global / (e2e_ms / e2e_steps * 1e-3)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    peaks, peak_src = load_peaks()
+    ctx.barrier()
+    e2e_steps = max(3, min(steps, 20))
+    e2e_ms = ctx.max_over_ranks(sum(ctx.timed(step_e2e, e2e_steps))) / e2e_steps
+    ctx.barrier()
+    e2e_value = n_global / (e2e_ms * 1e-3)
+    launches = plan.launches_per_call
+    tc = launches != 3
+    del sol, model, plan
     torch.set_default_device('cpu')
-    tf32 = measure_tf32_tflops(dev)
+    if rank != 0:
+        return None
+    tf32 = ctx.tf32()
     fpp = flop_per_point(prob.net_layers, spec['J'])
     achieved = (n_local / (statistics.mean(times) * 1e-3)) * fpp / 1e12
     peak = tf32 / 3.0
-    cpu = cpu_baseline(args.workload) if not args.no_cpu_baseline else None
-    line = {
-        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-        'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32' if plan.launches_per_call == 3 else 'tf32x3 (fp32 accumulate)', 'data': 'synthetic',
-        'config': {'workload': args.workload, 'description': spec['desc'], 'points_per_gpu': n_local,
-                   'points_total': n_global, 'mlp': list(prob.net_layers), 'mode': prob.mode,
-                   'jet_channels': spec['J'], 'kernel': 'simt-fp32' if plan.launches_per_call == 3 else 'tcgen05-3xtf32 (interior) + simt-fp32 (boundary rows)',
-                   'cuda_graph': graphed,
-                   'l2': 'flushed between timed steps (256 MB write)', 'parallelism': f'dp{world} (points sharded)'},
+    cfg = common_config(workload, world)
+    cfg.update({'points_per_gpu': n_local, 'points_total': n_global, 'mlp': list(prob.net_layers), 'mode': prob.mode,
+                'jet_channels': spec['J'],
+                'kernel': ('tcgen05-3xtf32 (interior) + simt-fp32 (boundary rows)' if tc else 'simt-fp32'),
+                'cuda_graph': graphed, 'l2': 'flushed between timed steps (256 MB write)',
+                'parallelism': f'dp{world} (points sharded, one all-reduce of [loss terms | gradient] per step)'})
+    return {
+        'value': value, 'unit': UNIT, 'ms_per_step': ms_per_step, 'steps': steps, 'warmup': max(warmup, 3),
+        'dtype': 'tf32x3 (fp32 accumulate)' if tc else 'f32', 'config': cfg,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                'ms_per_step': e2e_ms / e2e_steps},
-        'gpu_launches': args.steps * plan.launches_per_call,
-        'clocks': clocks,
+                'ms_per_step': e2e_ms},
+        'gpu_launches': steps * launches, 'clocks': clocks,
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                      'frac': achieved / peak if peak else None,
-                     'traffic': NCU_TRAFFIC_BYTES.get(args.workload) if world == 1 else None,
-                     'flop_per_point': fpp,
+                     'traffic': ncu_traffic(workload) if world == 1 else None, 'flop_per_point': fpp,
                      'peak_source': f'cuBLAS TF32 8192^3 measured live = {tf32:.1f} TFLOP/s, / 3 for 3xTF32 '
-                                    f'(MEASURED_PEAKS.json [{peak_src}] bf16 = {peaks.get("bf16_tflops")})'},
-        'cpu_baseline': cpu,
+                                    f'(MEASURED_PEAKS.json [{ctx.peak_src}] bf16 = {ctx.peaks.get("bf16_tflops")})'},
+        'cpu_baseline': cpu_baseline(workload) if with_cpu else None,
         'wall_s': time.time() - t_wall,
     }
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
 
 
-def run_b200_mat(args, dev, tdb, problems, rank=0, world=1):
+def measure_mat(ctx, workload, steps, warmup, with_cpu):
     """mat-mode workload: HBM-bound stencil kernel.  Several GPUs: slab decomposition along axis 0, weak scaling
-    (4096 rows per rank), 4 halo rows of u from each neighbour + one all-reduce of the loss terms per step."""
-    import torch.distributed as dist
+    (4096 rows per rank), halo rows of u from each neighbour + one all-reduce of the loss terms per step."""
+    import torch_de_solver_b200 as tdb
+    import problems
     from torch_de_solver_b200.mat import slab_rows
-    spec = WORKLOADS[args.workload]
+    args, dev, world, rank = ctx.args, ctx.dev, ctx.world, ctx.rank
+    torch.set_default_device(dev)
+    spec = WORKLOADS[workload]
     kw = dict(spec['kw'])
     n1 = kw['n'] + 1
     if world > 1:
@@ -327,128 +370,162 @@ def run_b200_mat(args, dev, tdb, problems, rank=0, world=1):
     plan = sol._plan
     n_cells = plan.n_cells                         # global
     n_local = plan.n_cells_local
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
-
-    def timed(fn, steps):
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        for e0, e1 in ev:
-            flush.zero_()
-            e0.record(); fn(); e1.record()
-        torch.cuda.synchronize(dev)
-        return [e0.elapsed_time(e1) for e0, e1 in ev]
-
-    def reduce_max(ms_total):
-        if world > 1:
-            t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t)
-        return ms_total
 
     step = lambda: plan.loss_grad_raw(u)
     graphed = False
-    if not args.no_graph and world == 1:      # one CUDA graph per step (single rank; eager with collectives)
+    if not args.no_graph:                     # one CUDA graph per step (halo exchange and all-reduce included)
         try:
             step, _, _ = plan.capture(u)
             graphed = True
         except Exception as e:                # noqa: BLE001 - report and fall back to eager launches
-            sys.stderr.write(f'[bench] CUDA graph capture failed ({e}); timing eager launches\n')
+            sys.stderr.write(f'[bench] {workload}: CUDA graph capture failed ({e}); timing eager launches\n')
             step = lambda: plan.loss_grad_raw(u)
-    sampler = ClockSampler(dev.index or 0)  # started before the warm-up: nvidia-smi needs ~0.2 s to deliver samples
+    sampler = ClockSampler(ctx.local)
     sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step()
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
+    ctx.barrier()
     t_wall = time.time()
-    times = timed(step, args.steps)
-    if world > 1:
-        dist.barrier()
+    times = ctx.timed(step, steps)
+    ctx.barrier()
     clocks = sampler.stop()
-    ms = reduce_max(sum(times)) / args.steps
-    # kernel-only time of the stencil kernel on this rank (roofline): the same launch without the exchange
-    ue = u if world == 1 else torch.zeros(plan.ir.shape_ext, dtype=torch.float32, device=dev)
+    ms = ctx.max_over_ranks(sum(times)) / steps
     # dominant (stencil) kernel alone: CUDA events recorded by the library on the launching stream around back-to-back
     # launches of that kernel (inputs + output = 192 MiB per launch > L2, so launches do not feed each other from cache)
-    flush.zero_()
-    kt = statistics.mean(plan.time_stencil(ue, 10) for _ in range(max(3, min(args.steps, 10))))
-    # e2e: forcing tensor + boundary targets from pinned host memory every step, loss terms read back
-    host_in = [plan._coeffs.detach().cpu().pin_memory(), plan._targets.detach().cpu().pin_memory()]
-    dev_in = [plan._coeffs, plan._targets]
+    ue = u if world == 1 else torch.zeros(plan.ir.shape_ext, dtype=torch.float32, device=dev)
+    ctx.flush.zero_()
+    kt = statistics.mean(plan.time_stencil(ue, 10) for _ in range(max(3, min(steps, 10))))
+    # e2e through Solution.evaluate + backward: the step's inputs - the grid values u (the quantity a mat-mode optimiser
+    # updates) and the boundary targets - come from pinned host memory, the loss terms are read back.  The forcing tensor
+    # is static problem data: the reference's own step reads it from a resident tensor (tedeous/derivative.py:319-320),
+    # so it is uploaded once, not per step.
+    host_in = [u.detach().cpu().pin_memory(), plan._targets.detach().cpu().pin_memory()]
+    dev_in = [u, plan._targets]
     host_out = torch.empty(plan.out_size, dtype=torch.float32, device='cpu').pin_memory()
     u.requires_grad_()
 
     def step_e2e():
-        for h, d in zip(host_in, dev_in):
-            d.copy_(h, non_blocking=True)
+        with torch.no_grad():
+            for h, d in zip(host_in, dev_in):
+                d.copy_(h, non_blocking=True)
         u.grad = None
         loss, _ = sol.evaluate()
         loss.backward()
         host_out.copy_(sol._last_out, non_blocking=True)
     for _ in range(3):
         step_e2e()
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    e2e_steps = max(3, min(args.steps, 20))
-    e2e_ms = reduce_max(sum(timed(step_e2e, e2e_steps))) / e2e_steps
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    peaks, peak_src = load_peaks()
-    achieved = n_local * MAT_BYTES_PER_CELL / (kt * 1e-3) / 1e9
+    ctx.barrier()
+    e2e_steps = max(3, min(steps, 20))
+    e2e_ms = ctx.max_over_ranks(sum(ctx.timed(step_e2e, e2e_steps))) / e2e_steps
+    ctx.barrier()
+    launches, kind, halo = plan.launches_per_call, plan.kernel_kind, plan.ir.halo
+    h2d = sum(t.numel() * 4 for t in host_in)
+    d2h = host_out.numel() * 4
+    del sol, model, plan, u, ue
     torch.set_default_device('cpu')
-    cpu = cpu_baseline(args.workload) if (not args.no_cpu_baseline and world == 1) else None
-    line = {
-        'metric': METRIC, 'value': n_cells / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-        'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': args.workload, 'description': spec['desc'], 'cells': n_cells, 'cells_per_gpu': n_local,
-                   'mode': 'mat', 'kernel': plan.kernel_kind, 'cuda_graph': graphed,
-                   'l2': 'flushed between timed steps (256 MB write)',
-                   'parallelism': 'single GPU' if world == 1 else
-                                  f'{world} row slabs, {plan.ir.halo}-row halo exchange + all-reduce of the loss terms'},
-        'e2e': {'value': n_cells / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': sum(t.numel() * 4 for t in host_in),
-                'd2h_bytes_per_step': host_out.numel() * 4, 'ms_per_step': e2e_ms},
-        'gpu_launches': args.steps * plan.launches_per_call,
-        'clocks': clocks,
+    if rank != 0:
+        return None
+    peaks = ctx.peaks
+    achieved = n_local * MAT_BYTES_PER_CELL / (kt * 1e-3) / 1e9
+    cfg = common_config(workload, world)
+    cfg.update({'cells': n_cells, 'cells_per_gpu': n_local, 'mode': 'mat', 'kernel': kind, 'cuda_graph': graphed,
+                'l2': 'flushed between timed steps (256 MB write)',
+                'parallelism': 'single GPU' if world == 1 else
+                               f'{world} row slabs, {halo}-row halo exchange + all-reduce of the loss terms'})
+    return {
+        'value': n_cells / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'steps': steps, 'warmup': max(warmup, 3),
+        'dtype': 'f32', 'config': cfg,
+        'e2e': {'value': n_cells / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'ms_per_step': e2e_ms,
+                'note': 'u and the boundary targets are uploaded every step; the forcing tensor is static problem data '
+                        '(resident in the reference too, tedeous/derivative.py:319-320)'},
+        'gpu_launches': steps * launches, 'clocks': clocks,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                      'frac': achieved / peaks['hbm_gbs'],
-                     'traffic': NCU_TRAFFIC_BYTES.get(args.workload) if world == 1 else None,
-                     'bytes_per_cell': MAT_BYTES_PER_CELL, 'kernel_ms': kt, 'kernel': 'mat stencil kernel (' + plan.kernel_kind + ')',
+                     'traffic': ncu_traffic(workload) if world == 1 else None,
+                     'bytes_per_cell': MAT_BYTES_PER_CELL, 'kernel_ms': kt, 'kernel': 'mat stencil kernel (' + kind + ')',
                      'step_frac': n_local * MAT_BYTES_PER_CELL / (ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
-                     'peak_source': f'MEASURED_PEAKS.json [{peak_src}] hbm_gbs; achieved = cells per GPU * 12 B / mean '
-                                    f'duration of the stencil kernel launch alone (CUDA events on its stream around 10 back-to-back '
-                                    f'launches; working set 192 MiB > L2); step_frac = the same bytes / the whole step '
-                                    f'(all launches, L2 flushed between steps)'},
-        'cpu_baseline': cpu,
+                     'peak_source': f'MEASURED_PEAKS.json [{ctx.peak_src}] hbm_gbs; achieved = cells per GPU * 12 B / mean '
+                                    f'duration of the stencil kernel launch alone (CUDA events on its stream around 10 '
+                                    f'back-to-back launches; working set 192 MiB > L2); step_frac = the same bytes / the '
+                                    f'whole step (all launches, L2 flushed between steps)'},
+        'cpu_baseline': cpu_baseline(workload) if with_cpu else None,
         'wall_s': time.time() - t_wall,
     }
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+
+
+def measure(ctx, workload, steps, warmup, with_cpu):
+    fn = measure_mat if WORKLOADS[workload].get('mat') else measure_nn
+    return fn(ctx, workload, steps, warmup, with_cpu)
+
+
+def run_b200(args):
+    ctx = Ctx(args)
+    with_cpu = not args.no_cpu_baseline and ctx.world == 1
+    head = measure(ctx, args.workload, args.steps, args.warmup, with_cpu)
+    configs = {}
+    if args.workload == HEADLINE and not args.no_configs:
+        for name in EXTRA_CONFIGS:
+            try:
+                res = measure(ctx, name, max(5, min(args.steps, 20)), max(3, min(args.warmup, 5)), with_cpu)
+            except Exception as e:            # noqa: BLE001 - one failing extra config must not lose the headline line
+                if ctx.world > 1:
+                    raise                     # ranks must stay in step: fail loudly
+                res = {'error': f'{type(e).__name__}: {e}'}
+            gc_collect()
+            if ctx.rank == 0:
+                configs[name] = res
+    if ctx.rank == 0:
+        line = {'metric': METRIC, 'value': head['value'], 'unit': UNIT, 'n_gpus': ctx.world, 'steps': args.steps,
+                'warmup': max(args.warmup, 3), 'ms_per_step': head['ms_per_step'], 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': head['dtype'], 'data': 'synthetic',
+                'config': head['config'], 'e2e': head['e2e'], 'gpu_launches': head['gpu_launches'],
+                'clocks': head['clocks'], 'roofline': head['roofline'], 'cpu_baseline': head['cpu_baseline'],
+                'wall_s': head['wall_s']}
+        if configs:
+            line['configs'] = configs
+        print(json.dumps(line))
+    if ctx.world > 1:
+        ctx.dist.destroy_process_group()
+
+
+def gc_collect():
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
 
 
 # ----------------------------------------------------------------------------------------------------
-CPU_SAMPLE = {   # bounded CPU samples of the same operators (reference cost is flat in N)
-    'wave_autograd_1e6': dict(fn='wave', kw=dict(n=315, mode='autograd', layers=(2, 100, 100, 100, 1))),
-    'burgers_NN_cfg1': dict(fn='burgers', kw=dict(n=100, mode='NN', layers=(2, 100, 100, 100, 1))),
-    'burgers_autograd_1e6': dict(fn='burgers', kw=dict(n=315, mode='autograd', layers=(2, 100, 100, 100, 1))),
-    'kdv_autograd_1e6': dict(fn='kdv', kw=dict(nx=199, nt=199, mode='autograd', layers=(2, 100, 100, 100, 1))),
-    'ns_autograd_1e6': dict(fn='navier_stokes', kw=dict(n=20, layers=(3, 100, 100, 100, 100, 100, 100, 3))),
-    'poisson_mat_4096': dict(fn='poisson_mat', kw=dict(n=255, derivative_points=2)),
-}
+def _reference_solution(prob, grid, bconds, net):
+    """The reference's own objects (oracle/_ref, unmodified TEDEouS): what Model.compile builds, tedeous/model.py:96-113."""
+    from tedeous.input_preprocessing import Operator_bcond_preproc
+    from tedeous.solution import Solution
+    kw = prob.compile_kwargs
+    eq_cls = Operator_bcond_preproc(grid, prob.equation.equation_lst, bconds, h=kw.get('h', 0.001),
+                                    inner_order='1', boundary_order='2').set_strategy(prob.mode)
+    return Solution(grid, eq_cls, net, prob.mode, kw.get('weak_form'), kw['lambda_operator'], kw['lambda_bound'],
+                    tol=kw.get('tol', 0), derivative_points=kw.get('derivative_points', 2))
 
 
 def cpu_step_time(workload, steps=3, warmup=1):
-    """Times the oracle port (same call pattern as the reference) on the host cores."""
+    """Times `loss, _ = Solution.evaluate(); loss.backward()` (tedeous/solution.py:129-168, closure.py:49-64) on the
+    host cores: the installed reference (oracle/_ref) when present, else the oracle port of the same call pattern.
+    -> (points, [seconds per step], sample description, kind, threads)."""
     import problems
-    import torch_de_solver_b200 as tdb
-    from oracle import tedeous_oracle as orc
+    from oracle import make_ref
     torch.set_default_device('cpu')
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)            # torchrun exports OMP_NUM_THREADS=1: use every host core regardless
     spec = CPU_SAMPLE[workload]
-    prob = getattr(problems, spec['fn'])(tdb, 'float32', **spec['kw'])
+    kind = 'reference' if make_ref.available() else 'port'
+    if kind == 'reference':
+        make_ref.import_reference()
+        from tedeous import data as api
+        from tedeous.device import solver_device
+        solver_device('cpu')
+    else:
+        import torch_de_solver_b200 as api
+    prob = getattr(problems, spec['fn'])(api, 'float32', **spec['kw'])
     grid = prob.domain.build(prob.mode)
     bconds = prob.conditions.build(prob.domain.variable_dict)
     kw = prob.compile_kwargs
@@ -458,40 +535,59 @@ def cpu_step_time(workload, steps=3, warmup=1):
     else:
         net = problems.make_net(prob.net_layers, torch.float32, prob.init)
         params = list(net.parameters())
-    sol = orc.OracleSolution(grid, prob.equation.equation_lst, bconds, net, prob.mode, kw['lambda_operator'],
-                             kw['lambda_bound'], h=kw.get('h', 0.001),
-                             derivative_points=kw.get('derivative_points', 2))
+    if kind == 'reference':
+        sol = _reference_solution(prob, grid, bconds, net)
+
+        def one_step():
+            for p in params:
+                p.grad = None
+            loss, _ = sol.evaluate()
+            loss.backward()
+    else:
+        from oracle import tedeous_oracle as orc
+        sol = orc.OracleSolution(grid, prob.equation.equation_lst, bconds, net, prob.mode, kw['lambda_operator'],
+                                 kw['lambda_bound'], h=kw.get('h', 0.001),
+                                 derivative_points=kw.get('derivative_points', 2))
+        one_step = lambda: orc.loss_and_grad(sol, params)
     ts = []
-    for i in range(warmup + steps):
+    for _ in range(warmup + steps):
         t0 = time.perf_counter()
-        orc.loss_and_grad(sol, params)
+        one_step()
         ts.append(time.perf_counter() - t0)
     n = sol.op.shape[0]
-    return n, ts[warmup:], f"{spec['fn']} {spec['kw']} -> {n} operator points"
+    what = 'unmodified TEDEouS 0.4.11 (oracle/_ref)' if kind == 'reference' else 'oracle port (oracle/_ref absent)'
+    sample = (f"{spec['fn']} {spec['kw']} -> {n} operator points; {what}; torch {torch.__version__} CPU, "
+              f'{threads} threads (os.cpu_count()={os.cpu_count()})')
+    return n, ts[warmup:], sample, kind, threads
 
 
 def cpu_baseline(workload):
-    n, ts, sample = cpu_step_time(workload)
-    return {'value': n / min(ts), 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-            'sample': sample + f'; min of {len(ts)} steps after 1 warm-up; torch {torch.__version__} CPU, '
-                               f'os.cpu_count()={os.cpu_count()}'}
+    try:
+        n, ts, sample, kind, threads = cpu_step_time(workload)
+    except Exception as e:                    # noqa: BLE001
+        return {'error': f'{type(e).__name__}: {e}'}
+    return {'value': n / min(ts), 'unit': UNIT, 'cores': threads, 'kind': kind,
+            'sample': sample + f'; min of {len(ts)} steps after 1 warm-up'}
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    n, ts, sample = cpu_step_time(args.workload, steps=max(1, min(args.steps, 5)), warmup=min(max(args.warmup, 1), 2))
+    world = int(os.environ.get('WORLD_SIZE', str(args.gpus)))
+    full = args.workload == HEADLINE           # the headline config is small enough for the reference at full size
+    steps = args.steps if full else max(1, min(args.steps, 5))
+    warmup = args.warmup if full else min(max(args.warmup, 1), 2)
+    n, ts, sample, kind, threads = cpu_step_time(args.workload, steps=steps, warmup=warmup)
     ms = statistics.mean(ts) * 1e3
     val = n / (ms * 1e-3)
-    spec = WORKLOADS[args.workload]
+    cfg = common_config(args.workload, world)
+    cfg['sample'] = sample
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
-        'steps': len(ts), 'warmup': min(max(args.warmup, 1), 2), 'ms_per_step': ms, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': args.workload, 'description': spec['desc'], 'sample': sample},
-        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-                         'sample': sample},
+        'steps': len(ts), 'warmup': warmup, 'ms_per_step': ms, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'kind': kind, 'sample': sample},
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -504,9 +600,10 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='wave_autograd_1e6', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default=HEADLINE, choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-graph', action='store_true', help='mat workload: time eager launches instead of a CUDA graph')
+    ap.add_argument('--no-configs', action='store_true', help='headline workload only (skip the `configs` key)')
+    ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of a CUDA graph')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

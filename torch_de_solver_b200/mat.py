@@ -495,8 +495,6 @@ class MatPlan:
         loops that are launch bound (a step is ~90 us of GPU work).  -> (replay callable, out, grad): `out` / `grad`
         are static tensors refreshed by every replay; `u` must keep its storage (in-place optimiser updates do)."""
         self._check_model(u)
-        if self.ir.shard[1] > 1:
-            raise UnsupportedProblem('CUDA-graph capture of the multi-rank step (collectives inside) is not enabled')
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):

@@ -192,6 +192,7 @@ class _FusedLoss(torch.autograd.Function):
         return out[0:1].clone()
 
     @staticmethod
+    @torch.autograd.function.once_differentiable        # the gradient is a constant of the launch: no double backward
     def backward(ctx, g):
         flat = ctx.flat_grad.reshape(-1) * g
         grads, off = [], 0
@@ -214,6 +215,7 @@ class _FusedFields(torch.autograd.Function):
         return fields
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g):
         flat = ctx.plan.vjp(g)
         grads, off = [], 0
@@ -326,6 +328,32 @@ class Solution:
             import torch.distributed as dist
             dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self._pg)
         return out, out[2 + self._n_slots:]
+
+    def capture_step(self):
+        """CUDA graph of one whole loss + gradient step as `_run_plan` enqueues it: parameter packing, the interior and
+        boundary launches with their fork / join, the reduction and - over several ranks - the NCCL all-reduce of the
+        [loss terms | gradient] vector (mat mode: halo exchange, the kernel launches, all-reduce of the loss terms).
+        -> (replay, out): `out` is a static tensor refreshed by every replay; parameter tensors must keep their storage
+        (in-place optimiser updates do).  Steps that are launch bound (BASELINE config 1) replay as one graph launch."""
+        if self.tol != 0 or self.weak_form not in (None, []):
+            raise UnsupportedProblem('graph capture of the causal / weak-form step is not provided')
+        if self.mode == 'mat':
+            replay, out, self._graph_grad = self._plan.capture(self.model)
+            return replay, out
+        dev = self.grid.device
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(3):                          # warm-up outside the capture (function attributes, NCCL)
+                self._run_plan()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self._run_plan()[0]
+        self._graph = graph                             # keeps the graph (and its private pool) alive
+        return graph.replay, out
 
     def _causal_weights(self):
         """Causal loss (tedeous/losses.py:137-182): w[t, j] = exp(-tol * sum_{s < t} res[s, j]) with
