@@ -21,6 +21,7 @@
 One JSON line on stdout (rank 0).
 """
 import argparse
+import contextlib
 import json
 import os
 import statistics
@@ -563,7 +564,8 @@ def cpu_step_time(workload, steps=3, warmup=1):
 
 def cpu_baseline(workload):
     try:
-        n, ts, sample, kind, threads = cpu_step_time(workload)
+        with contextlib.redirect_stdout(sys.stderr):       # the reference prints ("Default cpu processor is used.")
+            n, ts, sample, kind, threads = cpu_step_time(workload)
     except Exception as e:                    # noqa: BLE001
         return {'error': f'{type(e).__name__}: {e}'}
     return {'value': n / min(ts), 'unit': UNIT, 'cores': threads, 'kind': kind,
@@ -578,7 +580,8 @@ def run_reference(args):
     full = args.workload == HEADLINE           # the headline config is small enough for the reference at full size
     steps = args.steps if full else max(1, min(args.steps, 5))
     warmup = args.warmup if full else min(max(args.warmup, 1), 2)
-    n, ts, sample, kind, threads = cpu_step_time(args.workload, steps=steps, warmup=warmup)
+    with contextlib.redirect_stdout(sys.stderr):           # stdout carries exactly one JSON line
+        n, ts, sample, kind, threads = cpu_step_time(args.workload, steps=steps, warmup=warmup)
     ms = statistics.mean(ts) * 1e3
     val = n / (ms * 1e-3)
     cfg = common_config(args.workload, world)
