@@ -122,6 +122,32 @@ def test_tensor_core_path_matches_reference(name, cuda_default):
     assert torch.equal(a, b)                      # fixed accumulation order: bit-reproducible
 
 
+@pytest.mark.parametrize('name', NET_CASES)
+def test_streamed_tensor_core_path_matches_reference(name, cuda_default):
+    """impl=3: jet_tcs_kernel (fused forward / backward-data on tcgen05, two tiles in flight, any depth) +
+    wgrad_gemm_kernel (weight gradients of the W x W layers from the streamed Y / gZ rows)."""
+    g = load_golden(name, 'float64')
+    prob, net, sol = fused(name, g['weights'], impl=3)
+    assert sol._plan.launches_per_call >= 5
+    loss, loss_n = sol.evaluate()
+    loss.backward()
+    grad = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).double().cpu().numpy()
+    assert float(loss) == pytest.approx(float(g['loss']), rel=LOSS_RTOL)
+    gn = np.linalg.norm(g['grad'])
+    assert abs(np.linalg.norm(grad) - gn) <= GRADNORM_RTOL * gn
+    assert np.linalg.norm(grad - g['grad']) <= GRADVEC_RTOL * gn
+    if not prob.compile_kwargs.get('tol', 0):
+        np.testing.assert_allclose(sol.op_mse.cpu().numpy(), g['op_mse'], rtol=5e-4)
+    prob2, net2, sol2 = fused(name, g['weights'], impl=1)
+    ref = sol2._run_plan()[0].double()
+    out = sol._run_plan()[0].double()
+    assert float(out[0]) == pytest.approx(float(ref[0]), rel=2e-6)
+    k = 2 + sol._n_slots
+    assert float((out[k:] - ref[k:]).norm()) <= 2e-5 * float(ref[k:].norm())
+    a, b = sol._plan.loss_grad(), sol._plan.loss_grad()
+    assert torch.equal(a, b)                      # fixed accumulation order: bit-reproducible
+
+
 def test_tensor_core_path_refuses_unsupported_net(cuda_default):
     g = load_golden('burgers_autograd_4h', 'float64')
     with pytest.raises(RuntimeError, match='tcgen05 path needs'):

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "jet_tcs.cuh"
 
 namespace {
 thread_local std::string g_err;
@@ -87,6 +88,15 @@ struct tdb200_plan {
   float* tc_scratch = nullptr;
   long long tc_scratch_per_cta = 0;
   int grad_rows = 0, loss_rows = 0;   // allocated rows of the partial buffers
+  // streamed tensor-core path (jet_tcs_kernel + wgrad_gemm_kernel): any number of W x W layers
+  bool tcs_eligible = false;
+  int* d_seg_tile_begin_rest_all = nullptr;    // every segment but the interior one on the SIMT kernel
+  int simt_rest_all_tiles = 0;
+  float* tcs_ys = nullptr;                     // streamed Y_l / gZ_t rows of one chunk
+  float* tcs_gs = nullptr;
+  float* tcs_zsave = nullptr;
+  long long tcs_stream_stride = 0;             // floats per layer array
+  int tcs_chunk_tiles = 0;
 };
 
 static int points_per_tile(int J, int K) {
@@ -191,7 +201,7 @@ int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_s
   p->grid = tiles < p->n_sms ? (tiles > 0 ? tiles : 1) : p->n_sms;
   {  // can the interior segment run on the tensor cores?
     const tdb200_segment& s0 = segments[0];
-    bool ok = L >= 3 && L - 2 <= 2 && net->widths[1] <= 104 && net->widths[L] <= tdb::jet_tc_max_out() && net->widths[0] <= 4;
+    bool ok = L >= 3 && net->widths[1] <= 104 && net->widths[L] <= tdb::jet_tc_max_out() && net->widths[0] <= 4;
     for (int l = 2; l < L; ++l) ok = ok && net->widths[l] == net->widths[1];
     for (int i = 0; i < 3; ++i) p->tc_sig[i] = i < s0.n_dirs ? s0.dir_order[i] : 0;
     ok = ok && s0.identity && s0.K == 1 && s0.n_dirs <= 3 && s0.n_groups > 0 &&
@@ -199,7 +209,8 @@ int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_s
          s0.col_term_end[s0.n_cols - 1] <= 48 && n_terms >= 0;
     if (ok)   // every factor of the interior segment must sit in the first 96 entries (cached in shared memory)
       for (int t = 0; t < s0.col_term_end[s0.n_cols - 1]; ++t) ok = ok && terms[t].fac_end <= 96;
-    p->tc_eligible = ok;
+    p->tcs_eligible = ok;                      // streamed path: any depth
+    p->tc_eligible = ok && L - 2 <= 2;         // dW accumulators of <= 2 W x W layers fit TMEM next to D and gZ
     if (ok) {
       const int P = tdb::jet_tc_points_per_tile(p->tc_sig[0], p->tc_sig[1], p->tc_sig[2]);
       p->tc_tiles = (int)((s0.n_groups + P - 1) / P);
@@ -208,15 +219,18 @@ int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_s
         const int g = atoi(getenv("TDB200_TC_GRID"));
         if (g >= 1 && g < p->tc_grid) p->tc_grid = g;
       }
-      std::vector<int> tb(n_segments + 1, p->tc_tiles), rb(n_segments + 1, 0);
+      std::vector<int> tb(n_segments + 1, p->tc_tiles), rb(n_segments + 1, 0), ra(n_segments + 1, 0);
       tb[0] = 0;
+      for (int s = 1; s < n_segments; ++s) ra[s + 1] = ra[s] + p->seg_tile_begin[s + 1] - p->seg_tile_begin[s];
+      p->simt_rest_all_tiles = ra[n_segments];
+      if ((rc = upload(&p->d_seg_tile_begin_rest_all, ra.data(), ra.size()))) { tdb200_plan_destroy(p); return rc; }
       // boundary segments made of identity rows (Dirichlet values, autograd-mode operator conditions) take the tcgen05
       // kernel too - one small launch each on the side stream; periodic / finite-difference groups stay on the SIMT kernel
       // ... when the interior launch is short (< ~1 ms): there the ~170 us SIMT boundary tile is the critical path.  Next
       // to a long interior launch one SIMT CTA hides all boundary rows, and the tcgen05 side launches measured 4 % slower
       // (wave, 10^6 points: 8.25 -> 8.57 ms).
       const double tc_us_plan = 25.0 + 15.0 * ((p->tc_tiles + p->tc_grid - 1) / p->tc_grid);
-      const bool tc_boundary = tc_us_plan < 1000.0 && !getenv("TDB200_NO_TC_BOUNDARY");
+      const bool tc_boundary = p->tc_eligible && tc_us_plan < 1000.0 && !getenv("TDB200_NO_TC_BOUNDARY");
       for (int s = 1; s < n_segments; ++s) {
         const tdb200_segment& sg = segments[s];
         int sig[3];
@@ -247,8 +261,8 @@ int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_s
       if ((rc = upload<float>(&p->tc_scratch, nullptr, (size_t)p->tc_grid * p->tc_scratch_per_cta))) { tdb200_plan_destroy(p); return rc; }
     }
   }
-  p->grad_rows = p->grid + tdb::jet_tc_partial_rows() * p->tc_grid + p->simt_rest_grid;
-  p->loss_rows = p->grid + p->tc_grid + p->simt_rest_grid;
+  p->grad_rows = p->grid + tdb::jet_tc_partial_rows() * p->tc_grid + p->simt_rest_grid + (p->tcs_eligible ? 2 * p->n_sms : 0);
+  p->loss_rows = p->grid + p->tc_grid + p->simt_rest_grid + (p->tcs_eligible ? p->n_sms : 0);
   for (const auto& e : p->tc_extra) { p->grad_rows += tdb::jet_tc_partial_rows() * e.grid; p->loss_rows += e.grid; }
   if ((rc = upload<float>(&p->arena, nullptr, a.n_params_pad))) { tdb200_plan_destroy(p); return rc; }
   if ((rc = upload<float>(&p->arena_t, nullptr, a.n_params_pad))) { tdb200_plan_destroy(p); return rc; }
@@ -331,7 +345,9 @@ int tdb200_plan_set_field_seeds(tdb200_plan* p, const float* seeds_dev) {
 
 int tdb200_plan_set_impl(tdb200_plan* p, int32_t impl) {
   if (!p) return fail(TDB200_ERR_INVALID, "null plan");
-  if (impl < 0 || impl > 2) return fail(TDB200_ERR_INVALID, "impl must be 0 (auto), 1 (SIMT) or 2 (tcgen05)");
+  if (impl < 0 || impl > 3) return fail(TDB200_ERR_INVALID, "impl must be 0 (auto), 1 (SIMT), 2 (tcgen05, dW in TMEM) or 3 (tcgen05, streamed dW)");
+  if (impl == 3 && !p->tcs_eligible)
+    return fail(TDB200_ERR_INVALID, "streamed tcgen05 path needs equal hidden widths <= 104, >= 1 W x W layer and an identity interior segment with pure partials along <= 3 axes");
   if (impl == 2 && !p->tc_eligible)
     return fail(TDB200_ERR_INVALID, "tcgen05 path needs equal hidden widths <= 104, 1 or 2 W x W layers and an identity interior segment with pure partials along <= 3 axes");
   p->impl = impl;
@@ -341,12 +357,44 @@ int tdb200_plan_set_impl(tdb200_plan* p, int32_t impl) {
 int64_t tdb200_plan_out_size(const tdb200_plan* p) { return p ? 2 + p->n_slots + p->args.n_params : 0; }
 int64_t tdb200_plan_n_params(const tdb200_plan* p) { return p ? p->args.n_params : 0; }
 int64_t tdb200_plan_n_fields(const tdb200_plan* p) { return p ? p->n_fields : 0; }
+static bool use_tcs(const tdb200_plan* p) {
+  if (!p->tcs_eligible || p->impl == 1 || p->impl == 2) return false;
+  if (p->impl == 3) return true;
+  if (getenv("TDB200_AUTO_TCS")) return atoi(getenv("TDB200_AUTO_TCS")) != 0 && p->segs[0].n_groups >= 4096;
+  return !p->tc_eligible && p->segs[0].n_groups >= 4096;        // deeper nets: the only tensor-core path
+}
 static bool use_tc(const tdb200_plan* p) {
-  if (!p->tc_eligible || p->impl == 1) return false;
+  if (!p->tc_eligible || p->impl == 1 || use_tcs(p)) return false;
   return p->impl == 2 || p->segs[0].n_groups >= 4096;
+}
+static int tcs_chunks(const tdb200_plan* p) {
+  return p->tcs_chunk_tiles > 0 ? (p->tc_tiles + p->tcs_chunk_tiles - 1) / p->tcs_chunk_tiles : 1;
+}
+// stream / scratch buffers of the streamed path, sized on first use (never inside a stream capture: warm up first)
+static int ensure_tcs_buffers(tdb200_plan* p) {
+  if (p->tcs_ys) return TDB200_OK;
+  const tdb::JetArgs& a = p->args;
+  const int NM = a.n_layers - 2, Wp = (a.widths[1] + 3) / 4 * 4;
+  const int P = tdb::jet_tc_points_per_tile(p->tc_sig[0], p->tc_sig[1], p->tc_sig[2]);
+  const int J = 1 + p->tc_sig[0] + p->tc_sig[1] + p->tc_sig[2];
+  const double budget = (getenv("TDB200_TCS_SCRATCH_MB") ? atof(getenv("TDB200_TCS_SCRATCH_MB")) : 8192.0) * 1048576.0;
+  const double per_tile = (double)P * J * Wp * 4.0 * 2.0 * NM;
+  long long ct = (long long)(budget / per_tile);
+  const int pairs = 2 * p->n_sms;
+  ct = ct / pairs * pairs;
+  if (ct < pairs) ct = pairs;
+  if (ct > p->tc_tiles) ct = p->tc_tiles;
+  p->tcs_chunk_tiles = (int)ct;
+  p->tcs_stream_stride = (long long)ct * P * J * Wp;
+  int rc;
+  if ((rc = upload<float>(&p->tcs_ys, nullptr, (size_t)p->tcs_stream_stride * NM))) return rc;
+  if ((rc = upload<float>(&p->tcs_gs, nullptr, (size_t)p->tcs_stream_stride * NM))) return rc;
+  if ((rc = upload<float>(&p->tcs_zsave, nullptr, (size_t)p->n_sms * 2 * NM * 512 * 16))) return rc;
+  return TDB200_OK;
 }
 int32_t tdb200_plan_launches_per_call(const tdb200_plan* p) {
   if (!p) return 0;
+  if (use_tcs(p)) return 3 + 2 * tcs_chunks(p) + (p->simt_rest_all_tiles > 0 ? 1 : 0);
   if (!use_tc(p)) return 3;
   return 4 + (int)p->tc_extra.size() + (p->simt_rest_tiles > 0 ? 1 : 0);
 }
@@ -379,7 +427,84 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
   call.fields = fields;
   call.do_grad = do_grad;
   int grad_rows = p->grid, loss_rows = p->grid;
-  if (use_tc(p)) {
+  if (use_tcs(p)) {
+    { const int rc = ensure_tcs_buffers(p); if (rc != TDB200_OK) return rc; }
+    CU(tdb::launch_pack_tc_images(pk, p->wimg, s));
+    const int NM = a.n_layers - 2, Wp = (a.widths[1] + 3) / 4 * 4;
+    const int P = tdb::jet_tc_points_per_tile(p->tc_sig[0], p->tc_sig[1], p->tc_sig[2]);
+    const int J = 1 + p->tc_sig[0] + p->tc_sig[1] + p->tc_sig[2];
+    // boundary rows: SIMT kernel on a side stream, on the SMs the persistent interior grid leaves free
+    const double tcs_us = 30.0 + 9.0 * ((p->tc_tiles + p->tc_grid - 1) / p->tc_grid) * (1.0 + 0.5 * NM);
+    int rest_ctas = p->simt_rest_all_tiles < p->n_sms ? p->simt_rest_all_tiles : p->n_sms, reserve = 0;
+    bool fork = false;
+    if (p->simt_rest_all_tiles > 0 && p->tc_grid == p->n_sms && !getenv("TDB200_NO_OVERLAP")) {
+      int k = (int)ceil(p->simt_rest_all_tiles * 170.0 / (tcs_us > 50.0 ? tcs_us : 50.0));
+      k = k < 1 ? 1 : k;
+      if (k <= p->n_sms / 8) { rest_ctas = k; reserve = k; fork = true; }
+    }
+    const int gA = p->tc_grid - reserve;
+    const int gG = gA;
+    const int rowsA = tdb::jet_tc_partial_rows() * gA;
+    grad_rows = rowsA + (do_grad ? gG : 0);
+    loss_rows = gA;
+    cudaStream_t ss = s;
+    if (fork) {
+      if (!p->side) {
+        CU(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+      }
+      CU(cudaEventRecord(p->ev_fork, s));
+      CU(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+      ss = p->side;
+    }
+    auto launch_rest = [&]() -> int {
+      if (p->simt_rest_all_tiles > 0) {
+        tdb::JetArgs rest = call;
+        rest.seg_tile_begin = p->d_seg_tile_begin_rest_all;
+        rest.n_tiles = p->simt_rest_all_tiles;
+        rest.part_grad = p->part_grad + (size_t)grad_rows * a.n_params_pad;
+        rest.part_loss = p->part_loss + (size_t)loss_rows * p->n_slots;
+        CU(tdb::launch_jet_simt(rest, rest_ctas, ss));
+      }
+      return TDB200_OK;
+    };
+    if (fork) {
+      const int rc = launch_rest();
+      if (rc != TDB200_OK) return rc;
+      CU(cudaEventRecord(p->ev_join, p->side));
+    }
+    tdb::JetArgs tc = call;
+    tc.seg_tile_begin = p->d_seg_tile_begin_tc;
+    tdb::TcsArgs xa{};
+    xa.wimg = p->wimg; xa.ys = p->tcs_ys; xa.gs = p->tcs_gs; xa.stream_stride = p->tcs_stream_stride;
+    xa.zsave = p->tcs_zsave; xa.Wp = Wp;
+    tdb::WgradArgs wa{};
+    wa.gs = p->tcs_gs; wa.ys = p->tcs_ys; wa.stream_stride = p->tcs_stream_stride;
+    wa.W = a.widths[1]; wa.Wp = Wp; wa.n_mma = NM; wa.splits = gG / NM > 0 ? gG / NM : 1;
+    wa.part = p->part_grad + (size_t)rowsA * a.n_params_pad; wa.n_params_pad = a.n_params_pad;
+    for (int t = 1; t <= NM; ++t) wa.w_off[t - 1] = a.w_off[t];
+    if (gG < NM) return fail(TDB200_ERR_INVALID, "streamed tcgen05 path: fewer CTAs than W x W layers");
+    int chunk = 0;
+    for (int t0 = 0; t0 < p->tc_tiles; t0 += p->tcs_chunk_tiles, ++chunk) {
+      const int t1 = t0 + p->tcs_chunk_tiles < p->tc_tiles ? t0 + p->tcs_chunk_tiles : p->tc_tiles;
+      xa.tile0 = t0; xa.tile1 = t1; xa.zero_partials = chunk == 0;
+      CU(tdb::launch_jet_tcs(tc, xa, p->tc_sig[0], p->tc_sig[1], p->tc_sig[2], gA, s));
+      if (do_grad) {
+        long long r1 = (long long)t1 * P; if (r1 > p->segs[0].n_groups) r1 = p->segs[0].n_groups;
+        wa.rows = (r1 - (long long)t0 * P) * J;
+        wa.accumulate = chunk > 0;
+        CU(tdb::launch_wgrad_gemm(wa, gG, s));
+      }
+    }
+    if (fork) {
+      CU(cudaStreamWaitEvent(s, p->ev_join, 0));
+    } else {
+      const int rc = launch_rest();
+      if (rc != TDB200_OK) return rc;
+    }
+    if (p->simt_rest_all_tiles > 0) { grad_rows += rest_ctas; loss_rows += rest_ctas; }
+  } else if (use_tc(p)) {
     CU(tdb::launch_pack_tc_images(pk, p->wimg, s));
     tdb::JetArgs tc = call;
     tc.seg_tile_begin = p->d_seg_tile_begin_tc;
@@ -510,7 +635,7 @@ void tdb200_plan_destroy(tdb200_plan* p) {
   cudaFree(p->d_segs); cudaFree(p->d_seg_tile_begin); cudaFree(p->d_terms); cudaFree(p->d_factors);
   cudaFree(p->d_comb); cudaFree(p->d_slot_scale); cudaFree(p->d_slot_lambda); cudaFree(p->d_slot_len);
   cudaFree(p->arena); cudaFree(p->arena_t); cudaFree(p->img_f); cudaFree(p->img_b);
-  cudaFree(p->d_seg_tile_begin_tc); cudaFree(p->d_seg_tile_begin_rest); cudaFree(p->wimg); cudaFree(p->tc_scratch); cudaFree(p->part_grad); cudaFree(p->part_loss); cudaFree(p->scratch);
+  cudaFree(p->d_seg_tile_begin_tc); cudaFree(p->d_seg_tile_begin_rest); cudaFree(p->d_seg_tile_begin_rest_all); cudaFree(p->tcs_ys); cudaFree(p->tcs_gs); cudaFree(p->tcs_zsave); cudaFree(p->wimg); cudaFree(p->tc_scratch); cudaFree(p->part_grad); cudaFree(p->part_loss); cudaFree(p->scratch);
   if (p->side) { cudaStreamDestroy(p->side); cudaEventDestroy(p->ev_fork); cudaEventDestroy(p->ev_join); }
   delete p;
 }

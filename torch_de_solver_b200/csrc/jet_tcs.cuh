@@ -1,0 +1,43 @@
+// Streamed tensor-core path ("tcs"): argument blocks shared by jet_tcs_kernel.cuh, wgrad_gemm.cu and capi.cu.
+#pragma once
+#include "common.cuh"
+
+namespace tdb {
+
+constexpr int kTcsMaxMma = TDB200_MAX_LAYERS - 2;   // W x W layers the streamed path handles
+
+// jet_tcs_kernel: fused forward + operator + backward-data over the tiles [tile0, tile1) of the interior segment.
+struct TcsArgs {
+  const float* wimg;            // weight images, layout of pack_tc_images_kernel
+  float* ys;                    // Y_l rows of the chunk, l = 0..n_mma-1: [l][rows][Wp] (input of W x W layer l + 1)
+  float* gs;                    // gZ_t rows, t = 1..n_mma at index t - 1
+  long long stream_stride;      // floats between two layers' arrays
+  float* zsave;                 // per CTA [2 slots][n_mma][512 threads][16]: pre-activation jets (L2-resident scratch)
+  int tile0, tile1;             // tiles of this launch (chunk)
+  int Wp;                       // row pitch of the streams (W rounded up to 4)
+  int zero_partials;            // 1: first chunk of a call (partial rows start from zero), 0: accumulate
+};
+
+// wgrad_gemm_kernel
+struct WgradArgs {
+  const float* gs;
+  const float* ys;
+  long long stream_stride;
+  long long rows;               // rows of this chunk
+  int W, Wp, n_mma, splits;     // CTAs: blockIdx = split * n_mma + layer
+  float* part;                  // gradient partial rows of this kernel: [grid][n_params_pad]
+  int n_params_pad;
+  int w_off[kTcsMaxMma];        // offset of W_{t} (t = 1..n_mma at index t - 1) in the flat gradient
+  int accumulate;               // 0: first chunk (overwrite), 1: add
+};
+
+size_t jet_tcs_smem_bytes();
+int jet_tcs_threads();
+cudaError_t launch_jet_tcs(const JetArgs& a, const TcsArgs& x, int o0, int o1, int o2, int grid, cudaStream_t s);
+cudaError_t launch_jet_tcs_g0(const JetArgs& a, const TcsArgs& x, int o0, int o1, int o2, int grid, cudaStream_t s);
+cudaError_t launch_jet_tcs_g1(const JetArgs& a, const TcsArgs& x, int o0, int o1, int o2, int grid, cudaStream_t s);
+cudaError_t launch_jet_tcs_g2(const JetArgs& a, const TcsArgs& x, int o0, int o1, int o2, int grid, cudaStream_t s);
+cudaError_t launch_jet_tcs_g3(const JetArgs& a, const TcsArgs& x, int o0, int o1, int o2, int grid, cudaStream_t s);
+cudaError_t launch_wgrad_gemm(const WgradArgs& a, int grid, cudaStream_t s);
+
+}  // namespace tdb

@@ -1,0 +1,628 @@
+// Streamed tensor-core path ("tcs"): fused Taylor-jet MLP forward + operator + backward-data kernel for nets with ANY
+// number of W x W layers (1 .. 14), warp-specialised, two tiles in flight per CTA.
+//
+// Same orientation, operand images and 3xTF32 GEMMs as jet_tc_kernel.cuh (D[neuron, (point, channel)] = W . Y, lanes are
+// neurons, the tanh-jet rule and its adjoint are thread-local epilogues).  What is different:
+//   * the weight gradients of the W x W layers are NOT formed here: every epilogue streams its Y_l / gZ_t rows
+//     ([(point, channel) row][neuron], fp32, coalesced) to HBM and wgrad_gemm.cu contracts them afterwards.  Without the
+//     dW accumulators TMEM holds only the two D accumulators (256 of 512 columns), without the weight-gradient operand
+//     image shared memory has room for the operand images of TWO tiles, and nothing limits the depth of the net.
+//   * pre-activation jets saved for the backward sweep live in an L2-resident per-CTA scratch (64 bytes per thread, tile
+//     slot and layer, written / read as one coalesced 2 KB run per warp) instead of registers, so no per-tile state
+//     crosses an MMA wait in registers and the 16 epilogue warps alternate between the two tile slots: the GEMM of one
+//     slot runs behind the epilogue of the other.
+//   * warp 16 issues every tcgen05.mma and streams the weight images (two K halves, each reloaded as soon as the last
+//     MMA that reads it has retired); the epilogue warps hand over operand images with mbarriers (no CTA-wide barrier
+//     between an epilogue and its GEMM).
+#pragma once
+#include "jet_tc_kernel.cuh"
+#include "jet_tcs.cuh"
+
+namespace tdb {
+
+constexpr int kTsEpi = 512;                       // epilogue threads (16 warps: 4 lane windows x 4 column parts)
+constexpr int kTsThreads = kTsEpi + 32;           // + the MMA / weight-streaming warp
+constexpr int kTsHalfFloats = 2 * kTcWBlock;      // one K half (2 k-blocks) of a hi or lo weight image
+constexpr int kSOffW = 0, kSOffAct = 2 * kTcWFloats, kSOffX = kSOffAct + 4 * kTcActFloats,
+              kSOffU = kSOffX + 4 * kTcMaxPts * 4, kSOffGu = kSOffU + kTcMaxOut * kTcCols,
+              kSOffUP = kSOffGu + kTcMaxOut * kTcCols, kSOffCg = kSOffUP + 4 * kTcMaxOut * kTcCols,
+              kSOffBl = kSOffCg + (kMaxCParams + 3) / 4 * 4, kSOffEnd = kSOffBl + kTcMaxOut;
+constexpr size_t kTsSmemBytes =
+    (size_t)kSOffEnd * 4 + 1024 /*align*/ + 128 /*barriers*/ + kTcMaxTerms * sizeof(tdb200_term) +
+    kTcMaxFactors * sizeof(tdb200_factor) + 16 + sizeof(tdb200_segment) + 16 + 32 * 4 + kTcMaxPts * TDB200_MAX_COLS * 8 +
+    kTcMaxTerms * 16 + 64;
+
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+// K-steps [s0, s1) of one 3xTF32 layer GEMM (see issue_gemm in jet_tc_kernel.cuh); `first` clears the accumulator
+__device__ __forceinline__ void issue_gemm_steps(uint32_t d_tmem, const float* w_hi, const float* w_lo, const float* b_hi,
+                                                 int s0, int s1, bool leader) {
+  constexpr uint32_t idesc128 = umma_idesc(128, 2 * kTcCols, 0, 1), idesc64 = umma_idesc(128, kTcCols, 0, 1);
+  const uint64_t dwh = umma_desc(smem_u32(w_hi), 16, 1024), dwl = umma_desc(smem_u32(w_lo), 16, 1024);
+  const uint64_t dbh = umma_desc(smem_u32(b_hi), kTcActBlock * 4, 512, 1);
+  for (int s = s0; s < s1; ++s) {
+    const uint64_t ao = ((uint64_t)(s >> 2) * kTcWBlock * 4 + (uint64_t)(s & 3) * 32) >> 4;
+    const uint64_t bo = ((uint64_t)s * 1024) >> 4;
+    if (leader) {
+      umma_tf32(d_tmem, dwh + ao, dbh + bo, idesc128, s ? 1u : 0u);
+      umma_tf32(d_tmem, dwl + ao, dbh + bo, idesc64, 1u);
+    }
+  }
+}
+// one K half (k-blocks 2h, 2h + 1 of the hi and of the lo image) of a weight image pair -> shared memory
+__device__ __forceinline__ void bulk_load_half(float* dst, const float* src, int h, uint64_t* bar) {
+  constexpr uint32_t kBytes = kTsHalfFloats * 4, kChunk = 6656;       // 26624 = 4 x 6656
+  const uint32_t b = smem_u32(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(2 * kBytes) : "memory");
+#pragma unroll
+  for (int img = 0; img < 2; ++img) {
+    const uint32_t off = (uint32_t)img * kTcWFloats * 4 + (uint32_t)h * kBytes;
+    for (uint32_t o = 0; o < kBytes; o += kChunk)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   :: "r"(smem_u32(dst) + off + o), "l"(reinterpret_cast<const char*>(src) + off + o), "r"(kChunk), "r"(b)
+                   : "memory");
+  }
+}
+
+template <int O0, int O1, int O2>
+__global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a, const TcsArgs x) {
+  constexpr int J = 1 + O0 + O1 + O2;
+  constexpr int ND = (O0 > 0) + (O1 > 0) + (O2 > 0);
+  constexpr int PH = kTcPC / J > kTcMaxPts / kTcParts ? kTcMaxPts / kTcParts : kTcPC / J;   // points per column part
+  constexpr int P = kTcParts * PH;             // points per tile
+  constexpr int C = PH * J;                    // used columns per part (<= 16)
+  constexpr int ORD[3] = {O0, O1, O2};
+  extern __shared__ uint8_t smem_raw_ts[];
+  const uint32_t s0_ = smem_u32(smem_raw_ts);
+  float* const sbase = reinterpret_cast<float*>(smem_raw_ts + (((s0_ + 1023u) & ~1023u) - s0_));
+  uint64_t* bars;
+  uint32_t* tmem_ptr;
+  tdb200_term* termS; tdb200_factor* facS; tdb200_segment* segS; float* scaleS; double* lossT; int4* recS; int* fastS;
+  {
+    uint8_t* q = reinterpret_cast<uint8_t*>(sbase + kSOffEnd);
+    bars = reinterpret_cast<uint64_t*>(q); q += 96;
+    tmem_ptr = reinterpret_cast<uint32_t*>(q); q += 32;
+    termS = reinterpret_cast<tdb200_term*>(q); q += (kTcMaxTerms * sizeof(tdb200_term) + 15) / 16 * 16;
+    facS = reinterpret_cast<tdb200_factor*>(q); q += (kTcMaxFactors * sizeof(tdb200_factor) + 15) / 16 * 16;
+    segS = reinterpret_cast<tdb200_segment*>(q); q += (sizeof(tdb200_segment) + 15) / 16 * 16;
+    scaleS = reinterpret_cast<float*>(q); q += 32 * 4;
+    lossT = reinterpret_cast<double*>(q); q += kTcMaxPts * TDB200_MAX_COLS * 8;
+    recS = reinterpret_cast<int4*>(q); q += kTcMaxTerms * 16;
+    fastS = reinterpret_cast<int*>(q);
+  }
+  uint64_t* const act_full = bars;             // [2] epilogue warps (16 arrivals) -> MMA warp: operand image of the slot is ready
+  uint64_t* const d_full = bars + 2;           // [2] MMA warp (tcgen05.commit) -> epilogue warps: accumulator of the slot is ready
+  uint64_t* const w_full = bars + 4;           // [2] bulk copies -> MMA warp: K half of the weight image has landed
+  uint64_t* const w_free = bars + 6;           // [2] MMA warp (tcgen05.commit): every MMA reading the K half has retired
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool is_mma_warp = warp == kTsEpi / 32;
+  const int n = (warp & 3) * 32 + lane;                 // neuron = TMEM lane owned by this thread
+  const int part = (warp >> 2) & 3;                     // column part (0..3) of the tile this thread owns
+  const int L = a.n_layers, W = a.widths[1], n_out = a.widths[L], d = a.d, NM = L - 2;
+  const int ksteps = (W + 7) / 8;
+  const bool live = n < W;
+  const int col0 = part * kTcPC;
+  const int G = gridDim.x;
+  const int my_tiles = x.tile0 + (int)blockIdx.x < x.tile1 ? (x.tile1 - x.tile0 - (int)blockIdx.x + G - 1) / G : 0;
+  const int iters = (my_tiles + 1) / 2;
+  const int n_kinds = a.do_grad ? 2 * NM : NM;
+  float* const my_grad = a.part_grad + ((size_t)blockIdx.x * kTcParts + part) * a.n_params_pad;
+
+  // ---- one-time setup --------------------------------------------------------------------------------
+  if (x.zero_partials)
+    for (int i = tid; i < kTcParts * a.n_params_pad; i += kTsThreads)
+      a.part_grad[(size_t)blockIdx.x * kTcParts * a.n_params_pad + i] = 0.f;
+  for (int i = tid; i < 4 * kTcActFloats; i += kTsThreads) (sbase + kSOffAct)[i] = 0.f;    // pad rows / columns stay zero
+  if (tid < kMaxCParams) (sbase + kSOffCg)[tid] = 0.f;
+  for (int i = tid; i < 4 * kTcMaxPts * 4; i += kTsThreads) (sbase + kSOffX)[i] = 0.f;     // axes >= d stay zero
+  for (int i = tid; i < kTcMaxOut * kTcCols; i += kTsThreads) (sbase + kSOffGu)[i] = 0.f;
+  if (tid < kTcMaxOut) (sbase + kSOffBl)[tid] = tid < n_out ? a.arena[a.b_off[L - 1] + tid] : 0.f;
+  for (int i = tid; i < min(kTcMaxTerms, a.n_terms); i += kTsThreads) termS[i] = a.terms[i];
+  for (int i = tid; i < min(kTcMaxFactors, a.n_factors); i += kTsThreads) facS[i] = a.factors[i];
+  for (int i = tid; i < (int)(sizeof(tdb200_segment) / 4); i += kTsThreads)
+    reinterpret_cast<uint32_t*>(segS)[i] = reinterpret_cast<const uint32_t*>(a.segs)[i];
+  if (tid < a.n_slots) scaleS[tid] = a.slot_scale[tid];
+  for (int i = tid; i < kTcMaxPts * TDB200_MAX_COLS; i += kTsThreads) lossT[i] = 0.0;
+  if (tid == 0) {
+    mbar_init(act_full, 16); mbar_init(act_full + 1, 16);
+    for (int i = 2; i < 8; ++i) mbar_init(bars + i, 1);
+    *fastS = 1;
+  }
+  if (is_mma_warp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" :: "r"(smem_u32(tmem_ptr)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  if (tid < min(kTcMaxTerms, a.n_terms) && tid < segS->col_term_end[segS->n_cols - 1]) {
+    const tdb200_term tm = termS[tid];
+    int off[2] = {0xFFFF, 0xFFFF}, ipw[2] = {0, 0}, nf = 0;
+    bool ok = tm.kind == 0 || (tm.idx >= 0 && tm.idx < 0x7fffffffLL);
+    for (int fi = tm.fac_begin; fi < tm.fac_end; ++fi) {
+      const tdb200_factor fc = facS[fi];
+      if (fc.ipow == 0) continue;
+      if (fc.ipow < 0 || fc.ipow > 3 || nf == 2) { ok = false; break; }
+      off[nf] = fc.var * kTcCols + fc.chan;
+      ipw[nf] = fc.ipow;
+      ++nf;
+    }
+    if (ok) recS[tid] = make_int4(tm.kind == 0 ? __float_as_int(tm.coeff) : (int)tm.idx, tm.kind, off[0] | (off[1] << 16),
+                                  ipw[0] | (ipw[1] << 8));
+    else *fastS = 0;
+  }
+  __syncthreads();
+
+  // =====================================================================================================
+  // MMA / weight-streaming warp
+  // =====================================================================================================
+  if (is_mma_warp) {
+    const bool leader = elect_one();
+    float* const wbuf = sbase + kSOffW;
+    auto image_of = [&](int kind) -> const float* {     // kinds 0..NM-1: W_1..W_NM; NM..2NM-1: W_NM^T..W_1^T
+      return kind < NM ? x.wimg + (size_t)kind * 4 * kTcWFloats
+                       : x.wimg + (size_t)(2 * NM - 1 - kind) * 4 * kTcWFloats + 2 * kTcWFloats;
+    };
+    uint32_t act_ph = 0, wfull_ph = 0, wfree_ph = 0;    // one parity bit per slot / half
+    if (iters > 0 && leader) { bulk_load_half(wbuf, image_of(0), 0, w_full); bulk_load_half(wbuf, image_of(0), 1, w_full + 1); }
+    __syncwarp();
+    for (int it = 0; it < iters; ++it) {
+      const int nslots = (2 * it + 1 < my_tiles) ? 2 : 1;
+      for (int kind = 0; kind < n_kinds; ++kind) {
+        for (int slot = 0; slot < nslots; ++slot) {
+          mbar_wait(act_full + slot, (act_ph >> slot) & 1); act_ph ^= 1u << slot;
+          tc_fence_after();
+          const float* b_hi = sbase + kSOffAct + slot * 2 * kTcActFloats;
+          const uint32_t dt = tmem + (uint32_t)slot * 2 * kTcCols;
+          if (slot == 0) { mbar_wait(w_full, wfull_ph & 1); wfull_ph ^= 1; }
+          issue_gemm_steps(dt, wbuf, wbuf + kTcWFloats, b_hi, 0, ksteps < 8 ? ksteps : 8, leader);
+          if (slot == nslots - 1 && leader) umma_commit(w_free);
+          if (slot == 0) { mbar_wait(w_full + 1, (wfull_ph >> 1) & 1); wfull_ph ^= 2; }
+          issue_gemm_steps(dt, wbuf, wbuf + kTcWFloats, b_hi, 8, ksteps, leader);
+          if (leader) umma_commit(d_full + slot);
+          if (slot == nslots - 1 && leader) umma_commit(w_free + 1);
+          __syncwarp();
+        }
+        const int next = kind + 1 < n_kinds ? kind + 1 : (it + 1 < iters ? 0 : -1);
+        if (next >= 0) {
+          mbar_wait(w_free, wfree_ph & 1); wfree_ph ^= 1;
+          if (leader) bulk_load_half(wbuf, image_of(next), 0, w_full);
+          mbar_wait(w_free + 1, (wfree_ph >> 1) & 1); wfree_ph ^= 2;
+          if (leader) bulk_load_half(wbuf, image_of(next), 1, w_full + 1);
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ===================================================================================================
+    // epilogue warps
+    // ===================================================================================================
+    const bool fast_op = *fastS != 0;
+    const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);    // this warp's lane window
+    const int actA = (part >> 1) * kTcActBlock + n * 32 + ((((part & 1) * 2) ^ (n & 3)) << 3);       // columns 0..7
+    const int actB = (part >> 1) * kTcActBlock + n * 32 + ((((part & 1) * 2 + 1) ^ (n & 3)) << 3);   // columns 8..15
+    float w0[4] = {0.f, 0.f, 0.f, 0.f}, wl[kTcMaxOut];
+    float dw0_acc[4] = {0.f, 0.f, 0.f, 0.f}, dw0_dir[3] = {0.f, 0.f, 0.f}, dwl_acc[kTcMaxOut], dbl_acc = 0.f;
+    float db_acc[kTcsMaxMma + 1];                        // indexed by a runtime layer: lives in local memory (one
+#pragma unroll                                           // access per layer and tile)
+    for (int l = 0; l <= kTcsMaxMma; ++l) db_acc[l] = 0.f;
+    const float bias0 = live ? a.arena[a.b_off[0] + n] : 0.f;
+    if (live)
+      for (int ax = 0; ax < d; ++ax) w0[ax] = a.arena[a.w_off[0] + n * d + ax];
+#pragma unroll
+    for (int v = 0; v < kTcMaxOut; ++v) { wl[v] = (live && v < n_out) ? a.arena[a.w_off[L - 1] + v * W + n] : 0.f; dwl_acc[v] = 0.f; }
+    const tdb200_segment& sg = *segS;
+    const int ncols = sg.n_cols;
+    int dir_axis[3] = {0, 0, 0};
+    for (int i = 0; i < ND; ++i) dir_axis[i] = sg.dir_axis[i];
+    float w0d[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) w0d[i] = i < ND ? w0[dir_axis[i]] : 0.f;
+    const long long row0 = (long long)x.tile0 * P * J;   // first stream row of this chunk
+    uint32_t d_ph = 0;                                   // parity bit per slot of d_full
+
+    auto xbuf_of = [&](int slot, int it) { return sbase + kSOffX + (slot * 2 + (it & 1)) * kTcMaxPts * 4; };
+    auto tile_of = [&](int it, int slot) { return x.tile0 + (int)blockIdx.x + (2 * it + slot) * G; };
+    auto load_points = [&](int it) {                     // points of both slots of iteration `it` (asynchronous)
+      for (int slot = 0; slot < 2; ++slot) {
+        const int tile = tile_of(it, slot);
+        if (tile >= x.tile1) break;
+        float* dst = xbuf_of(slot, it);
+        const long long gf = (long long)tile * P;
+        const int pv = (int)min((long long)P, sg.n_groups - gf);
+        for (int i = tid; i < P * d; i += kTsEpi) {
+          const int p = i / d, ax = i - p * d;
+          if (p < pv)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dst + p * 4 + ax)),
+                         "l"(a.pts + (size_t)(sg.pts_off + gf + p) * d + ax) : "memory");
+          else
+            dst[p * 4 + ax] = 0.f;
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // tanh-jet rule of this thread's PH points: z (value channel already biased) -> y
+    auto jets_fwd = [&](const float* z, bool first, float* y) {
+#pragma unroll
+      for (int p = 0; p < PH; ++p) {
+        const float av = tanh_fast(z[p * J]);
+        const TanhF f(av);
+        y[p * J] = av;
+        int c = 1;
+#pragma unroll
+        for (int i = 0; i < ND; ++i) {
+          float zz[4] = {0.f, 0.f, 0.f, 0.f}, yy[4];
+          if (first) zz[0] = w0d[i];
+          else {
+#pragma unroll
+            for (int k = 0; k < ORD[i]; ++k) zz[k] = z[p * J + c + k];
+          }
+          tanh_jet_fwd(f, zz, ORD[i], yy);
+#pragma unroll
+          for (int k = 0; k < ORD[i]; ++k) y[p * J + c + k] = yy[k];
+          c += ORD[i];
+        }
+      }
+#pragma unroll
+      for (int j = C; j < 16; ++j) y[j] = 0.f;
+    };
+    // adjoint: gy -> gz (pre-activation cotangents); returns the sum of the value-channel cotangents (bias gradient)
+    auto jets_bwd = [&](const float* z, bool first, const float* gy, float* gz, float* g0_out) -> float {
+      float db = 0.f;
+#pragma unroll
+      for (int p = 0; p < PH; ++p) {
+        const TanhF f(tanh_fast(z[p * J]));
+        float g0 = gy[p * J] * f.f1;
+        int c = 1;
+#pragma unroll
+        for (int i = 0; i < ND; ++i) {
+          float zz[4] = {0.f, 0.f, 0.f, 0.f}, gg[4];
+          if (first) zz[0] = w0d[i];
+          else {
+#pragma unroll
+            for (int k = 0; k < ORD[i]; ++k) zz[k] = z[p * J + c + k];
+          }
+          g0 += tanh_jet_bwd(f, zz, gy + p * J + c, ORD[i], gg);
+          if (first) dw0_dir[i] += gg[0];
+#pragma unroll
+          for (int k = 0; k < ORD[i]; ++k) gz[p * J + c + k] = gg[k];
+          c += ORD[i];
+        }
+        gz[p * J] = g0;
+        if (g0_out) g0_out[p] = g0;
+        db += g0;
+      }
+#pragma unroll
+      for (int j = C; j < 16; ++j) gz[j] = 0.f;
+      return db;
+    };
+    auto store_act = [&](int slot, const float* v) {      // 16 columns -> MN-major operand image (hi / lo) of the slot
+      float hi[16], lo[16];
+      split16(v, hi, lo);
+      float* const ah = sbase + kSOffAct + slot * 2 * kTcActFloats;
+      float* const al = ah + kTcActFloats;
+      st4(ah + actA, hi); st4(ah + actA + 4, hi + 4); st4(ah + actB, hi + 8); st4(ah + actB + 4, hi + 12);
+      st4(al + actA, lo); st4(al + actA + 4, lo + 4); st4(al + actB, lo + 8); st4(al + actB + 4, lo + 12);
+    };
+    // rows (point, channel) of this thread's columns -> stream array of one layer (coalesced over the 32 neurons of a warp)
+    auto stream_rows = [&](float* arr, int tile, const float* v) {
+      if (n >= x.Wp) return;
+      const long long pt0 = (long long)tile * P + part * PH;
+      float* dst = arr + (size_t)(pt0 * J - row0) * x.Wp + n;
+#pragma unroll
+      for (int j = 0; j < C; ++j)
+        if (pt0 + j / J < sg.n_groups) __stcs(dst + (size_t)j * x.Wp, v[j]);
+    };
+    auto hand_over = [&](int slot) {                      // operand image of the slot is complete (this warp's part)
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(act_full + slot);
+    };
+    auto wait_d = [&](int slot) {
+      mbar_wait(d_full + slot, (d_ph >> slot) & 1);
+      d_ph ^= 1u << slot;
+      tc_fence_after();
+    };
+    auto load_d = [&](int slot, float* v) {               // accumulator halves of the N = 128 + N = 64 MMA pair
+      float v2[16];
+      const uint32_t base = t_lane + (uint32_t)slot * 2 * kTcCols + (uint32_t)col0;
+      tmem_ld16(base, v);
+      tmem_ld16(base + kTcCols, v2);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] += v2[j];
+    };
+    auto zsave_ptr = [&](int slot, int l) {                // saved jets of W x W layer l (1..NM)
+      return reinterpret_cast<float4*>(x.zsave + ((((size_t)blockIdx.x * 2 + slot) * NM + (l - 1)) * kTsEpi + tid) * 16);
+    };
+
+    if (iters > 0) load_points(0);
+    for (int it = 0; it < iters; ++it) {
+      const int nslots = (2 * it + 1 < my_tiles) ? 2 : 1;
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      epi_sync();                                         // this iteration's points are visible
+      if (it + 1 < iters) load_points(it + 1);
+
+      // ---- layer 0 (K = d): thread-local ---------------------------------------------------------------
+      for (int slot = 0; slot < nslots; ++slot) {
+        const float* xs = xbuf_of(slot, it);
+        float z[16], y[16];
+#pragma unroll
+        for (int p = 0; p < PH; ++p) {
+          const float4 x4 = *reinterpret_cast<const float4*>(xs + (part * PH + p) * 4);
+          z[p * J] = fmaf(w0[0], x4.x, fmaf(w0[1], x4.y, fmaf(w0[2], x4.z, fmaf(w0[3], x4.w, bias0))));
+        }
+        jets_fwd(z, true, y);
+        if (live) store_act(slot, y);
+        if (a.do_grad) stream_rows(x.ys, tile_of(it, slot), y);
+        hand_over(slot);
+      }
+      // ---- W x W layers 1 .. NM - 1: GEMM (MMA warp) + tanh-jet epilogue --------------------------------
+      for (int l = 1; l < NM; ++l) {
+        const float bl = live ? __ldg(a.arena + a.b_off[l] + n) : 0.f;
+        for (int slot = 0; slot < nslots; ++slot) {
+          float z[16], y[16];
+          wait_d(slot);
+          load_d(slot, z);
+#pragma unroll
+          for (int p = 0; p < PH; ++p) z[p * J] += bl;
+          if (a.do_grad) {
+            float4* zs = zsave_ptr(slot, l);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) zs[q] = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
+          }
+          jets_fwd(z, false, y);
+          if (live) store_act(slot, y);
+          if (a.do_grad) stream_rows(x.ys + (size_t)l * x.stream_stride, tile_of(it, slot), y);
+          hand_over(slot);
+        }
+      }
+      // ---- layer NM epilogue, last layer, operator, adjoint seeds, backward of layers L-1 and NM -----------
+      const float bNM = live ? __ldg(a.arena + a.b_off[NM] + n) : 0.f;
+      for (int slot = 0; slot < nslots; ++slot) {
+        const int tile = tile_of(it, slot);
+        const long long g_first = (long long)tile * P;
+        const int p_valid = (int)min((long long)P, sg.n_groups - g_first);
+        float z[16], y[16];
+        wait_d(slot);
+        load_d(slot, z);
+#pragma unroll
+        for (int p = 0; p < PH; ++p) z[p * J] += bNM;
+        jets_fwd(z, false, y);
+        for (int v = 0; v < n_out; ++v) {
+          float t16[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) t16[j] = wl[v] * y[j];          // wl is zero in dead lanes
+          const float tot = warp_multi_reduce16(t16, lane);
+          if ((lane & 1) == 0) (sbase + kSOffUP)[((warp & 3) * kTcMaxOut + v) * kTcCols + col0 + reduce16_col(lane)] = tot;
+        }
+        epi_sync();
+        for (int idx = tid; idx < n_out * kTcCols; idx += kTsEpi) {
+          const int v = idx / kTcCols, r = idx - v * kTcCols;
+          const int jc = r & (kTcPC - 1);
+          float s = (jc < C && jc % J == 0) ? (sbase + kSOffBl)[v] : 0.f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) s += (sbase + kSOffUP)[(w * kTcMaxOut + v) * kTcCols + r];
+          (sbase + kSOffU)[idx] = s;
+          (sbase + kSOffGu)[idx] = 0.f;
+        }
+        epi_sync();
+        if (tid < p_valid && fast_op) {
+          const int p = tid;
+          const int pc = (p / PH) * kTcPC + (p % PH) * J;
+          const long long row = g_first + p;
+          const float* u = (sbase + kSOffU) + pc;
+          float* gu = (sbase + kSOffGu) + pc;
+          auto pw = [](float xx, int i) { const float x2 = xx * xx; return i == 1 ? xx : i == 2 ? x2 : i == 3 ? x2 * xx : 1.f; };
+          auto dpw = [](float xx, int i) { return i == 1 ? 1.f : i == 2 ? 2.f * xx : i == 3 ? 3.f * xx * xx : 0.f; };
+          for (int col = 0; col < ncols; ++col) {
+            const int tb = sg.col_term_begin[col], te = sg.col_term_end[col];
+            float val = 0.f;
+            for (int t = tb; t < te; ++t) {
+              const int4 r = recS[t];
+              const float cf = r.y == 0 ? __int_as_float(r.x) : r.y == 1 ? __ldg(a.coeffs + r.x + row) : a.arena[a.n_net_params + r.x];
+              const int o0 = r.z & 0xFFFF, o1 = (r.z >> 16) & 0xFFFF;
+              const float x0 = o0 != 0xFFFF ? u[o0] : 1.f, x1 = o1 != 0xFFFF ? u[o1] : 1.f;
+              val = fmaf(cf * pw(x0, r.w & 255), pw(x1, r.w >> 8), val);
+            }
+            if (a.fields) a.fields[sg.field_off + row * ncols + col] = val;
+            const float tgt = sg.tgt_off >= 0 ? __ldg(a.targets + sg.tgt_off + row * ncols + col) : 0.f;
+            const float res = val - tgt;
+            const float rw = a.row_weight ? __ldg(a.row_weight + row) : 1.f;        // causal-loss weight (no grad)
+            lossT[p * TDB200_MAX_COLS + col] += (double)rw * (double)res * (double)res;
+            if (!a.do_grad) continue;
+            const float seed = a.field_seed ? __ldg(a.field_seed + sg.field_off + row * ncols + col)
+                                            : 2.f * scaleS[sg.col_slot[col]] * rw * res;
+            for (int t = tb; t < te; ++t) {
+              const int4 r = recS[t];
+              const float cf = r.y == 0 ? __int_as_float(r.x) : r.y == 1 ? __ldg(a.coeffs + r.x + row) : a.arena[a.n_net_params + r.x];
+              const int o0 = r.z & 0xFFFF, o1 = (r.z >> 16) & 0xFFFF;
+              const float x0 = o0 != 0xFFFF ? u[o0] : 1.f, x1 = o1 != 0xFFFF ? u[o1] : 1.f;
+              const float p0 = pw(x0, r.w & 255), p1 = pw(x1, r.w >> 8), sc = seed * cf;
+              if (o0 != 0xFFFF) gu[o0] += sc * dpw(x0, r.w & 255) * p1;
+              if (o1 != 0xFFFF) gu[o1] += sc * p0 * dpw(x1, r.w >> 8);
+              if (r.y == 2) atomicAdd(&(sbase + kSOffCg)[r.x], seed * p0 * p1);
+            }
+          }
+        } else if (tid < p_valid) {
+          const int p = tid;
+          const int pc = (p / PH) * kTcPC + (p % PH) * J;
+          const long long row = g_first + p;
+          for (int col = 0; col < ncols; ++col) {
+            float val = 0.f;
+            for (int t = sg.col_term_begin[col]; t < sg.col_term_end[col]; ++t) {
+              const tdb200_term tm = termS[t];
+              float prod = tm.kind == 0 ? tm.coeff : tm.kind == 1 ? __ldg(a.coeffs + tm.idx + row)
+                                                                   : a.arena[a.n_net_params + tm.idx];
+              for (int fi = tm.fac_begin; fi < tm.fac_end; ++fi) {
+                const tdb200_factor fc = facS[fi];
+                prod *= pow_i((sbase + kSOffU)[fc.var * kTcCols + pc + fc.chan], fc.ipow, fc.pow);
+              }
+              val += prod;
+            }
+            if (a.fields) a.fields[sg.field_off + row * ncols + col] = val;
+            const float tgt = sg.tgt_off >= 0 ? __ldg(a.targets + sg.tgt_off + row * ncols + col) : 0.f;
+            const float res = val - tgt;
+            const float rw = a.row_weight ? __ldg(a.row_weight + row) : 1.f;
+            lossT[p * TDB200_MAX_COLS + col] += (double)rw * (double)res * (double)res;
+            if (!a.do_grad) continue;
+            const float seed = a.field_seed ? __ldg(a.field_seed + sg.field_off + row * ncols + col)
+                                            : 2.f * scaleS[sg.col_slot[col]] * rw * res;
+            for (int t = sg.col_term_begin[col]; t < sg.col_term_end[col]; ++t) {
+              const tdb200_term tm = termS[t];
+              const float cf = tm.kind == 0 ? tm.coeff : tm.kind == 1 ? __ldg(a.coeffs + tm.idx + row)
+                                                                       : a.arena[a.n_net_params + tm.idx];
+              float full = 1.f;
+              for (int fi = tm.fac_begin; fi < tm.fac_end; ++fi) {
+                const tdb200_factor fc = facS[fi];
+                const float xx = (sbase + kSOffU)[fc.var * kTcCols + pc + fc.chan];
+                float part_ = seed * cf * dpow_i(xx, fc.ipow, fc.pow);
+                for (int fj = tm.fac_begin; fj < tm.fac_end; ++fj) {
+                  if (fj == fi) continue;
+                  const tdb200_factor fo = facS[fj];
+                  part_ *= pow_i((sbase + kSOffU)[fo.var * kTcCols + pc + fo.chan], fo.ipow, fo.pow);
+                }
+                (sbase + kSOffGu)[fc.var * kTcCols + pc + fc.chan] += part_;
+                full *= pow_i(xx, fc.ipow, fc.pow);
+              }
+              if (tm.kind == 2) atomicAdd(&(sbase + kSOffCg)[tm.idx], seed * full);
+            }
+          }
+        }
+        epi_sync();
+        if (!a.do_grad) continue;
+        // backward of the last layer: dWl, dbl; gY of tanh layer NM
+        if (tid < n_out) {
+          float s = 0.f;
+          for (int p = 0; p < P; ++p) s += (sbase + kSOffGu)[tid * kTcCols + (p / PH) * kTcPC + (p % PH) * J];
+          dbl_acc += s;
+        }
+        float gy[16], gz[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) gy[j] = 0.f;
+        for (int v = 0; v < n_out; ++v) {
+          float s = 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 g4 = *reinterpret_cast<const float4*>((sbase + kSOffGu) + v * kTcCols + col0 + 4 * q);
+            const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              s = fmaf(g[i], y[4 * q + i], s);
+              gy[4 * q + i] = fmaf(wl[v], g[i], gy[4 * q + i]);
+            }
+          }
+#pragma unroll
+          for (int vv = 0; vv < kTcMaxOut; ++vv) if (vv == v) dwl_acc[vv] += s;
+        }
+        epi_sync();                                       // everybody has read Gu before the next slot clears it
+        db_acc[NM] += jets_bwd(z, false, gy, gz, nullptr);
+        if (!live) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) gz[j] = 0.f;
+        }
+        if (live) store_act(slot, gz);
+        stream_rows(x.gs + (size_t)(NM - 1) * x.stream_stride, tile, gz);
+        hand_over(slot);
+      }
+      if (!a.do_grad) continue;
+      // ---- backward sweep over the W x W layers NM - 1 .. 1 ---------------------------------------------------
+      for (int t = NM - 1; t >= 1; --t) {
+        for (int slot = 0; slot < nslots; ++slot) {
+          float z[16], gy[16], gz[16];
+          {
+            const float4* zs = zsave_ptr(slot, t);        // issued before the wait: the L2 latency hides behind the GEMM
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const float4 v4 = zs[q]; z[4 * q] = v4.x; z[4 * q + 1] = v4.y; z[4 * q + 2] = v4.z; z[4 * q + 3] = v4.w; }
+          }
+          wait_d(slot);
+          load_d(slot, gy);
+          db_acc[t] += jets_bwd(z, false, gy, gz, nullptr);
+          if (!live) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) gz[j] = 0.f;
+          }
+          if (live) store_act(slot, gz);
+          stream_rows(x.gs + (size_t)(t - 1) * x.stream_stride, tile_of(it, slot), gz);
+          hand_over(slot);
+        }
+      }
+      // ---- backward of layer 0 (thread-local) --------------------------------------------------------------
+      for (int slot = 0; slot < nslots; ++slot) {
+        const float* xs = xbuf_of(slot, it);
+        float z[16], gy[16], gz[16], g0[PH];
+        wait_d(slot);
+        load_d(slot, gy);
+#pragma unroll
+        for (int p = 0; p < PH; ++p) {
+          const float4 x4 = *reinterpret_cast<const float4*>(xs + (part * PH + p) * 4);
+          z[p * J] = fmaf(w0[0], x4.x, fmaf(w0[1], x4.y, fmaf(w0[2], x4.z, fmaf(w0[3], x4.w, bias0))));
+        }
+        db_acc[0] += jets_bwd(z, true, gy, gz, g0);
+#pragma unroll
+        for (int p = 0; p < PH; ++p) {
+          const float4 x4 = *reinterpret_cast<const float4*>(xs + (part * PH + p) * 4);
+          dw0_acc[0] = fmaf(g0[p], x4.x, dw0_acc[0]); dw0_acc[1] = fmaf(g0[p], x4.y, dw0_acc[1]);
+          dw0_acc[2] = fmaf(g0[p], x4.z, dw0_acc[2]); dw0_acc[3] = fmaf(g0[p], x4.w, dw0_acc[3]);
+        }
+      }
+    }
+
+    // ---- flush: per-thread accumulators, per-CTA scalars ----------------------------------------------------
+    epi_sync();
+    const bool acc = !x.zero_partials;
+    auto put = [&](float* q, float v) { *q = acc ? *q + v : v; };
+    if (a.do_grad) {
+      if (live) {
+        for (int l = 0; l <= NM; ++l) put(my_grad + a.b_off[l] + n, db_acc[l]);
+        for (int i = 0; i < ND; ++i)
+          for (int ax = 0; ax < 4; ++ax) if (ax == dir_axis[i]) dw0_acc[ax] += dw0_dir[i];
+        for (int ax = 0; ax < d; ++ax) put(my_grad + a.w_off[0] + n * d + ax, dw0_acc[ax]);
+#pragma unroll
+        for (int v = 0; v < kTcMaxOut; ++v) if (v < n_out) put(my_grad + a.w_off[L - 1] + v * W + n, dwl_acc[v]);
+      }
+      if (tid < n_out) put(my_grad + a.b_off[L - 1] + tid, dbl_acc);     // warp 0 -> part-0 row
+      if (tid < a.n_cparams) put(my_grad + a.n_net_params + tid, (sbase + kSOffCg)[tid]);
+    }
+    if (tid < a.n_slots) {
+      double s = 0.0;
+      for (int col = 0; col < ncols; ++col)
+        if (sg.col_slot[col] == tid)
+          for (int p = 0; p < P; ++p) s += lossT[p * TDB200_MAX_COLS + col];
+      double* q = a.part_loss + (size_t)blockIdx.x * a.n_slots + tid;
+      *q = acc ? *q + s : s;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (is_mma_warp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int O0, int O1, int O2>
+static cudaError_t launch_tcs_sig(const JetArgs& a, const TcsArgs& x, int grid, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(jet_tcs_kernel<O0, O1, O2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kTsSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  jet_tcs_kernel<O0, O1, O2><<<grid, kTsThreads, kTsSmemBytes, s>>>(a, x);
+  return cudaGetLastError();
+}
+
+#define TDB_TCS_DEFINE_GROUP(NAME, SIGS)                                                                        \
+  cudaError_t NAME(const JetArgs& a, const TcsArgs& x, int o0, int o1, int o2, int grid, cudaStream_t s) {      \
+    SIGS(TDB_TCS_GROUP_CASE)                                                                                    \
+    return cudaErrorInvalidValue;                                                                               \
+  }
+#define TDB_TCS_GROUP_CASE(A, B, Cc) \
+  if (o0 == A && o1 == B && o2 == Cc) return launch_tcs_sig<A, B, Cc>(a, x, grid, s);
+
+}  // namespace tdb
