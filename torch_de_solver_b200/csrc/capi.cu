@@ -90,7 +90,8 @@ struct tdb200_plan {
   int grad_rows = 0, loss_rows = 0;   // allocated rows of the partial buffers
   // streamed tensor-core path (jet_tcs_kernel + wgrad_gemm_kernel): any number of W x W layers
   bool tcs_eligible = false;
-  int* d_seg_tile_begin_rest_all = nullptr;    // every segment but the interior one on the SIMT kernel
+  std::vector<TcExtra> tcs_extra;              // boundary segments made of identity rows: streamed kernels too
+  int* d_seg_tile_begin_rest_all = nullptr;    // the remaining segments (periodic / finite-difference groups): SIMT kernel
   int simt_rest_all_tiles = 0;
   float* tcs_ys = nullptr;                     // streamed Y_l / gZ_t rows of one chunk
   float* tcs_gs = nullptr;
@@ -221,7 +222,25 @@ int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_s
       }
       std::vector<int> tb(n_segments + 1, p->tc_tiles), rb(n_segments + 1, 0), ra(n_segments + 1, 0);
       tb[0] = 0;
-      for (int s = 1; s < n_segments; ++s) ra[s + 1] = ra[s] + p->seg_tile_begin[s + 1] - p->seg_tile_begin[s];
+      for (int s = 1; s < n_segments; ++s) {
+        const tdb200_segment& sg = segments[s];
+        int sig[3];
+        for (int i = 0; i < 3; ++i) sig[i] = i < sg.n_dirs ? sg.dir_order[i] : 0;
+        bool eok = sg.identity && sg.K == 1 && sg.n_dirs <= 3 && sg.n_groups > 0 && sg.n_cols >= 1 &&
+                   tdb::jet_tc_supports(sig[0], sig[1], sig[2]) && sg.col_term_end[sg.n_cols - 1] <= 48 &&
+                   !getenv("TDB200_NO_TC_BOUNDARY");
+        if (eok)
+          for (int t = sg.col_term_begin[0]; t < sg.col_term_end[sg.n_cols - 1]; ++t) eok = eok && terms[t].fac_end <= 96;
+        if (eok) {
+          const int Pe = tdb::jet_tc_points_per_tile(sig[0], sig[1], sig[2]);
+          tdb200_plan::TcExtra e{};
+          e.seg = s; e.sig[0] = sig[0]; e.sig[1] = sig[1]; e.sig[2] = sig[2];
+          e.tiles = (int)((sg.n_groups + Pe - 1) / Pe);
+          e.grid = e.tiles < p->n_sms ? e.tiles : p->n_sms;
+          p->tcs_extra.push_back(e);
+        }
+        ra[s + 1] = ra[s] + (eok ? 0 : p->seg_tile_begin[s + 1] - p->seg_tile_begin[s]);
+      }
       p->simt_rest_all_tiles = ra[n_segments];
       if ((rc = upload(&p->d_seg_tile_begin_rest_all, ra.data(), ra.size()))) { tdb200_plan_destroy(p); return rc; }
       // boundary segments made of identity rows (Dirichlet values, autograd-mode operator conditions) take the tcgen05
@@ -378,14 +397,16 @@ static int ensure_tcs_buffers(tdb200_plan* p) {
   const int P = tdb::jet_tc_points_per_tile(p->tc_sig[0], p->tc_sig[1], p->tc_sig[2]);
   const int J = 1 + p->tc_sig[0] + p->tc_sig[1] + p->tc_sig[2];
   const double budget = (getenv("TDB200_TCS_SCRATCH_MB") ? atof(getenv("TDB200_TCS_SCRATCH_MB")) : 8192.0) * 1048576.0;
-  const double per_tile = (double)P * J * Wp * 4.0 * 2.0 * NM;
+  const int Q = (tdb::jet_tc_columns_per_part(p->tc_sig[0], p->tc_sig[1], p->tc_sig[2]) + 3) / 4;
+  const double per_tile = 4.0 * Q * Wp * 16.0 * 2.0 * NM;
   long long ct = (long long)(budget / per_tile);
   const int pairs = 2 * p->n_sms;
   ct = ct / pairs * pairs;
   if (ct < pairs) ct = pairs;
   if (ct > p->tc_tiles) ct = p->tc_tiles;
   p->tcs_chunk_tiles = (int)ct;
-  p->tcs_stream_stride = (long long)ct * P * J * Wp;
+  p->tcs_stream_stride = (long long)ct * 4 * Q * Wp * 4;
+  (void)P; (void)J;
   int rc;
   if ((rc = upload<float>(&p->tcs_ys, nullptr, (size_t)p->tcs_stream_stride * NM))) return rc;
   if ((rc = upload<float>(&p->tcs_gs, nullptr, (size_t)p->tcs_stream_stride * NM))) return rc;
@@ -394,7 +415,7 @@ static int ensure_tcs_buffers(tdb200_plan* p) {
 }
 int32_t tdb200_plan_launches_per_call(const tdb200_plan* p) {
   if (!p) return 0;
-  if (use_tcs(p)) return 3 + 2 * tcs_chunks(p) + (p->simt_rest_all_tiles > 0 ? 1 : 0);
+  if (use_tcs(p)) return 3 + 2 * tcs_chunks(p) + 2 * (int)p->tcs_extra.size() + (p->simt_rest_all_tiles > 0 ? 1 : 0);
   if (!use_tc(p)) return 3;
   return 4 + (int)p->tc_extra.size() + (p->simt_rest_tiles > 0 ? 1 : 0);
 }
@@ -431,8 +452,7 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
     { const int rc = ensure_tcs_buffers(p); if (rc != TDB200_OK) return rc; }
     CU(tdb::launch_pack_tc_images(pk, p->wimg, s));
     const int NM = a.n_layers - 2, Wp = (a.widths[1] + 3) / 4 * 4;
-    const int P = tdb::jet_tc_points_per_tile(p->tc_sig[0], p->tc_sig[1], p->tc_sig[2]);
-    const int J = 1 + p->tc_sig[0] + p->tc_sig[1] + p->tc_sig[2];
+    const int Q = (tdb::jet_tc_columns_per_part(p->tc_sig[0], p->tc_sig[1], p->tc_sig[2]) + 3) / 4;
     // boundary rows: SIMT kernel on a side stream, on the SMs the persistent interior grid leaves free
     const double tcs_us = 30.0 + 9.0 * ((p->tc_tiles + p->tc_grid - 1) / p->tc_grid) * (1.0 + 0.5 * NM);
     int rest_ctas = p->simt_rest_all_tiles < p->n_sms ? p->simt_rest_all_tiles : p->n_sms, reserve = 0;
@@ -476,12 +496,15 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
     }
     tdb::JetArgs tc = call;
     tc.seg_tile_begin = p->d_seg_tile_begin_tc;
+    long long* dbg = nullptr;
+    if (getenv("TDB200_TC_TIMING")) { cudaMalloc(&dbg, sizeof(long long) * 16 * p->tc_grid); cudaMemset(dbg, 0, sizeof(long long) * 16 * p->tc_grid); }
+    tc.dbg = dbg;
     tdb::TcsArgs xa{};
     xa.wimg = p->wimg; xa.ys = p->tcs_ys; xa.gs = p->tcs_gs; xa.stream_stride = p->tcs_stream_stride;
     xa.zsave = p->tcs_zsave; xa.Wp = Wp;
     tdb::WgradArgs wa{};
     wa.gs = p->tcs_gs; wa.ys = p->tcs_ys; wa.stream_stride = p->tcs_stream_stride;
-    wa.W = a.widths[1]; wa.Wp = Wp; wa.n_mma = NM; wa.splits = gG / NM > 0 ? gG / NM : 1;
+    wa.W = a.widths[1]; wa.Wp = Wp; wa.n_mma = NM; wa.kb = Q == 3 ? 24 : 32; wa.splits = gG / NM > 0 ? gG / NM : 1;
     wa.part = p->part_grad + (size_t)rowsA * a.n_params_pad; wa.n_params_pad = a.n_params_pad;
     for (int t = 1; t <= NM; ++t) wa.w_off[t - 1] = a.w_off[t];
     if (gG < NM) return fail(TDB200_ERR_INVALID, "streamed tcgen05 path: fewer CTAs than W x W layers");
@@ -491,9 +514,37 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
       xa.tile0 = t0; xa.tile1 = t1; xa.zero_partials = chunk == 0;
       CU(tdb::launch_jet_tcs(tc, xa, p->tc_sig[0], p->tc_sig[1], p->tc_sig[2], gA, s));
       if (do_grad) {
-        long long r1 = (long long)t1 * P; if (r1 > p->segs[0].n_groups) r1 = p->segs[0].n_groups;
-        wa.rows = (r1 - (long long)t0 * P) * J;
+        wa.total4 = (long long)(t1 - t0) * 4 * Q * Wp;
         wa.accumulate = chunk > 0;
+        CU(tdb::launch_wgrad_gemm(wa, gG, s));
+      }
+      if (dbg && chunk == 0) {
+        std::vector<long long> h(16 * p->tc_grid);
+        cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        const int tiles_per_cta = (t1 - t0 + gA - 1) / gA;
+        fprintf(stderr, "[tdb200 tcs timing] cycles per tile (CTA 0, %d tiles; 0-11 epilogue thread 0, 12-15 MMA warp):", tiles_per_cta);
+        for (int i = 0; i < 16; ++i) fprintf(stderr, " p%d=%lld", i, h[i] / tiles_per_cta);
+        fprintf(stderr, "\n");
+      }
+    }
+    if (dbg) cudaFree(dbg);
+    // boundary segments of identity rows: the same two kernels in stream order (the stream buffers are reused), adding
+    // to the partial rows of the interior launches
+    for (const auto& e : p->tcs_extra) {
+      const int Qe = (tdb::jet_tc_columns_per_part(e.sig[0], e.sig[1], e.sig[2]) + 3) / 4;
+      const long long need = (long long)e.tiles * 4 * Qe * Wp * 4;
+      if (need > p->tcs_stream_stride) return fail(TDB200_ERR_INVALID, "streamed tcgen05 path: a boundary segment exceeds the stream chunk");
+      tdb::JetArgs xe = call;
+      xe.segs = a.segs + e.seg;
+      xe.row_weight = nullptr;
+      xe.dbg = nullptr;
+      xa.tile0 = 0; xa.tile1 = e.tiles; xa.zero_partials = 0;
+      const int ge = e.grid < gA ? e.grid : gA;
+      CU(tdb::launch_jet_tcs(xe, xa, e.sig[0], e.sig[1], e.sig[2], ge, s));
+      if (do_grad) {
+        wa.total4 = (long long)e.tiles * 4 * Qe * Wp;
+        wa.kb = Qe == 3 ? 24 : 32;
+        wa.accumulate = 1;
         CU(tdb::launch_wgrad_gemm(wa, gG, s));
       }
     }

@@ -84,6 +84,7 @@ size_t jet_tc_smem_bytes();
 cudaError_t launch_pack_tc_images(const PackArgs& a, float* img, cudaStream_t s);
 bool jet_tc_supports(int o0, int o1, int o2);
 int jet_tc_points_per_tile(int o0, int o1, int o2);
+int jet_tc_columns_per_part(int o0, int o1, int o2);   // used (point, channel) columns of the 16 a thread owns
 int jet_tc_partial_rows();
 int jet_tc_max_out();
 cudaError_t launch_jet_tc(const JetArgs& a, const float* wimg, int o0, int o1, int o2, int grid, cudaStream_t s);

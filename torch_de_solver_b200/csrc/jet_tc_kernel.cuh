@@ -177,12 +177,14 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
          "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])) : "memory");
 }
 
+// tf32 value nearest to x, ties away from zero: the result of cvt.rna.tf32.f32 for every finite x, computed on the
+// integer ALU (the conversion instruction runs on the quarter-rate pipe and its latency showed up as the top stall of
+// the epilogues: 32 conversions per thread and layer)
+__device__ __forceinline__ float tf32_rna(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ void split16(const float* v, float* hi, float* lo) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    uint32_t hb;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v[j]));
-    hi[j] = __uint_as_float(hb);
+    hi[j] = tf32_rna(v[j]);
     lo[j] = v[j] - hi[j];
   }
 }

@@ -9,8 +9,9 @@ constexpr int kTcsMaxMma = TDB200_MAX_LAYERS - 2;   // W x W layers the streamed
 // jet_tcs_kernel: fused forward + operator + backward-data over the tiles [tile0, tile1) of the interior segment.
 struct TcsArgs {
   const float* wimg;            // weight images, layout of pack_tc_images_kernel
-  float* ys;                    // Y_l rows of the chunk, l = 0..n_mma-1: [l][rows][Wp] (input of W x W layer l + 1)
-  float* gs;                    // gZ_t rows, t = 1..n_mma at index t - 1
+  float* ys;                    // Y_l of the chunk, l = 0..n_mma-1 (input of W x W layer l + 1): per layer float4
+                                // [(tile * 4 + part) * Q + q][Wp neurons] = 4 consecutive (point, channel) columns
+  float* gs;                    // gZ_t, t = 1..n_mma at index t - 1, same layout
   long long stream_stride;      // floats between two layers' arrays
   float* zsave;                 // per CTA [2 slots][n_mma][512 threads][16]: pre-activation jets (L2-resident scratch)
   int tile0, tile1;             // tiles of this launch (chunk)
@@ -23,7 +24,8 @@ struct WgradArgs {
   const float* gs;
   const float* ys;
   long long stream_stride;
-  long long rows;               // rows of this chunk
+  long long total4;             // float4 per layer array of this chunk = tiles * 4 * Q * Wp
+  int kb;                       // K rows (stream columns) per pipeline stage: 24 or 32
   int W, Wp, n_mma, splits;     // CTAs: blockIdx = split * n_mma + layer
   float* part;                  // gradient partial rows of this kernel: [grid][n_params_pad]
   int n_params_pad;

@@ -21,14 +21,14 @@
 namespace tdb {
 
 constexpr int kTsEpi = 512;                       // epilogue threads (16 warps: 4 lane windows x 4 column parts)
-constexpr int kTsThreads = kTsEpi + 32;           // + the MMA / weight-streaming warp
+constexpr int kTsThreads = kTsEpi + 64;           // + the MMA / weight-streaming warp + the operator warp
 constexpr int kTsHalfFloats = 2 * kTcWBlock;      // one K half (2 k-blocks) of a hi or lo weight image
 constexpr int kSOffW = 0, kSOffAct = 2 * kTcWFloats, kSOffX = kSOffAct + 4 * kTcActFloats,
-              kSOffU = kSOffX + 4 * kTcMaxPts * 4, kSOffGu = kSOffU + kTcMaxOut * kTcCols,
-              kSOffUP = kSOffGu + kTcMaxOut * kTcCols, kSOffCg = kSOffUP + 4 * kTcMaxOut * kTcCols,
+              kSOffU = kSOffX + 4 * kTcMaxPts * 4, kSOffGu = kSOffU + 2 * kTcMaxOut * kTcCols,      // U, Gu: per slot
+              kSOffUP = kSOffGu + 2 * kTcMaxOut * kTcCols, kSOffCg = kSOffUP + 4 * kTcMaxOut * kTcCols,
               kSOffBl = kSOffCg + (kMaxCParams + 3) / 4 * 4, kSOffEnd = kSOffBl + kTcMaxOut;
 constexpr size_t kTsSmemBytes =
-    (size_t)kSOffEnd * 4 + 1024 /*align*/ + 128 /*barriers*/ + kTcMaxTerms * sizeof(tdb200_term) +
+    (size_t)kSOffEnd * 4 + 1024 /*align*/ + 160 /*barriers*/ + kTcMaxTerms * sizeof(tdb200_term) +
     kTcMaxFactors * sizeof(tdb200_factor) + 16 + sizeof(tdb200_segment) + 16 + 32 * 4 + kTcMaxPts * TDB200_MAX_COLS * 8 +
     kTcMaxTerms * 16 + 64;
 
@@ -36,17 +36,21 @@ __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 512;" :::
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
-// K-steps [s0, s1) of one 3xTF32 layer GEMM (see issue_gemm in jet_tc_kernel.cuh); `first` clears the accumulator
+// K-steps [s0, s1) of one 3xTF32 layer GEMM: D[:, 0:64] (+)= W_hi Y_hi + W_hi Y_lo + W_lo Y_hi, three N = 64 MMAs into ONE
+// accumulator (jet_tc_kernel.cuh issues an N = 128 + an N = 64 MMA and adds two halves in the epilogue: 25 % less tensor
+// time, but this kernel is bound by its epilogues and the tensor pipe has slack - a single tcgen05.ld and no adds).
 __device__ __forceinline__ void issue_gemm_steps(uint32_t d_tmem, const float* w_hi, const float* w_lo, const float* b_hi,
                                                  int s0, int s1, bool leader) {
-  constexpr uint32_t idesc128 = umma_idesc(128, 2 * kTcCols, 0, 1), idesc64 = umma_idesc(128, kTcCols, 0, 1);
+  constexpr uint32_t idesc64 = umma_idesc(128, kTcCols, 0, 1);
   const uint64_t dwh = umma_desc(smem_u32(w_hi), 16, 1024), dwl = umma_desc(smem_u32(w_lo), 16, 1024);
-  const uint64_t dbh = umma_desc(smem_u32(b_hi), kTcActBlock * 4, 512, 1);
+  const uint64_t dbh = umma_desc(smem_u32(b_hi), kTcActBlock * 4, 512, 1),
+                 dbl = umma_desc(smem_u32(b_hi + kTcActFloats), kTcActBlock * 4, 512, 1);
   for (int s = s0; s < s1; ++s) {
     const uint64_t ao = ((uint64_t)(s >> 2) * kTcWBlock * 4 + (uint64_t)(s & 3) * 32) >> 4;
     const uint64_t bo = ((uint64_t)s * 1024) >> 4;
     if (leader) {
-      umma_tf32(d_tmem, dwh + ao, dbh + bo, idesc128, s ? 1u : 0u);
+      umma_tf32(d_tmem, dwh + ao, dbh + bo, idesc64, s ? 1u : 0u);
+      umma_tf32(d_tmem, dwh + ao, dbl + bo, idesc64, 1u);
       umma_tf32(d_tmem, dwl + ao, dbh + bo, idesc64, 1u);
     }
   }
@@ -66,6 +70,12 @@ __device__ __forceinline__ void bulk_load_half(float* dst, const float* src, int
   }
 }
 
+#ifdef TDB_TC_TIMING       // phase timers: build with TDB200_TC_TIMING_BUILD=1, run with TDB200_TC_TIMING=1
+#define TSMARK(i) do { if (a.dbg) { const long long tn_ = clock64(); tacc[i] += tn_ - tlast; tlast = tn_; } } while (0)
+#else
+#define TSMARK(i) do { } while (0)
+#endif
+
 template <int O0, int O1, int O2>
 __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a, const TcsArgs x) {
   constexpr int J = 1 + O0 + O1 + O2;
@@ -73,6 +83,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
   constexpr int PH = kTcPC / J > kTcMaxPts / kTcParts ? kTcMaxPts / kTcParts : kTcPC / J;   // points per column part
   constexpr int P = kTcParts * PH;             // points per tile
   constexpr int C = PH * J;                    // used columns per part (<= 16)
+  constexpr int Q = (C + 3) / 4;               // float4 per thread, tile and layer in the streams
   constexpr int ORD[3] = {O0, O1, O2};
   extern __shared__ uint8_t smem_raw_ts[];
   const uint32_t s0_ = smem_u32(smem_raw_ts);
@@ -82,7 +93,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
   tdb200_term* termS; tdb200_factor* facS; tdb200_segment* segS; float* scaleS; double* lossT; int4* recS; int* fastS;
   {
     uint8_t* q = reinterpret_cast<uint8_t*>(sbase + kSOffEnd);
-    bars = reinterpret_cast<uint64_t*>(q); q += 96;
+    bars = reinterpret_cast<uint64_t*>(q); q += 128;
     tmem_ptr = reinterpret_cast<uint32_t*>(q); q += 32;
     termS = reinterpret_cast<tdb200_term*>(q); q += (kTcMaxTerms * sizeof(tdb200_term) + 15) / 16 * 16;
     facS = reinterpret_cast<tdb200_factor*>(q); q += (kTcMaxFactors * sizeof(tdb200_factor) + 15) / 16 * 16;
@@ -96,8 +107,17 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
   uint64_t* const d_full = bars + 2;           // [2] MMA warp (tcgen05.commit) -> epilogue warps: accumulator of the slot is ready
   uint64_t* const w_full = bars + 4;           // [2] bulk copies -> MMA warp: K half of the weight image has landed
   uint64_t* const w_free = bars + 6;           // [2] MMA warp (tcgen05.commit): every MMA reading the K half has retired
+  uint64_t* const op_req = bars + 8;           // [2] epilogue warps (16 arrivals) -> operator warp: last-layer partial sums are in UP
+  uint64_t* const op_done = bars + 10;         // [2] operator warp -> epilogue warps: adjoint seeds Gu of the slot are ready
+  uint64_t* const up_free = bars + 12;         // operator warp -> epilogue warps: UP has been consumed
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool is_mma_warp = warp == kTsEpi / 32;
+  const bool is_mma_warp = warp == kTsEpi / 32, is_op_warp = warp == kTsEpi / 32 + 1;
+#ifdef TDB_TC_TIMING
+  long long tacc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) tacc[i] = 0;
+  long long tlast = clock64();
+#endif
   const int n = (warp & 3) * 32 + lane;                 // neuron = TMEM lane owned by this thread
   const int part = (warp >> 2) & 3;                     // column part (0..3) of the tile this thread owns
   const int L = a.n_layers, W = a.widths[1], n_out = a.widths[L], d = a.d, NM = L - 2;
@@ -108,6 +128,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
   const int my_tiles = x.tile0 + (int)blockIdx.x < x.tile1 ? (x.tile1 - x.tile0 - (int)blockIdx.x + G - 1) / G : 0;
   const int iters = (my_tiles + 1) / 2;
   const int n_kinds = a.do_grad ? 2 * NM : NM;
+  auto tile_of = [&](int it, int slot) { return x.tile0 + (int)blockIdx.x + (2 * it + slot) * G; };
   float* const my_grad = a.part_grad + ((size_t)blockIdx.x * kTcParts + part) * a.n_params_pad;
 
   // ---- one-time setup --------------------------------------------------------------------------------
@@ -117,7 +138,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
   for (int i = tid; i < 4 * kTcActFloats; i += kTsThreads) (sbase + kSOffAct)[i] = 0.f;    // pad rows / columns stay zero
   if (tid < kMaxCParams) (sbase + kSOffCg)[tid] = 0.f;
   for (int i = tid; i < 4 * kTcMaxPts * 4; i += kTsThreads) (sbase + kSOffX)[i] = 0.f;     // axes >= d stay zero
-  for (int i = tid; i < kTcMaxOut * kTcCols; i += kTsThreads) (sbase + kSOffGu)[i] = 0.f;
+  for (int i = tid; i < 2 * kTcMaxOut * kTcCols; i += kTsThreads) (sbase + kSOffGu)[i] = 0.f;
   if (tid < kTcMaxOut) (sbase + kSOffBl)[tid] = tid < n_out ? a.arena[a.b_off[L - 1] + tid] : 0.f;
   for (int i = tid; i < min(kTcMaxTerms, a.n_terms); i += kTsThreads) termS[i] = a.terms[i];
   for (int i = tid; i < min(kTcMaxFactors, a.n_factors); i += kTsThreads) facS[i] = a.factors[i];
@@ -128,10 +149,12 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
   if (tid == 0) {
     mbar_init(act_full, 16); mbar_init(act_full + 1, 16);
     for (int i = 2; i < 8; ++i) mbar_init(bars + i, 1);
+    mbar_init(op_req, 16); mbar_init(op_req + 1, 16);
+    mbar_init(op_done, 1); mbar_init(op_done + 1, 1); mbar_init(up_free, 1);
     *fastS = 1;
   }
   if (is_mma_warp) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" :: "r"(smem_u32(tmem_ptr)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" :: "r"(smem_u32(tmem_ptr)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -175,18 +198,24 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
       const int nslots = (2 * it + 1 < my_tiles) ? 2 : 1;
       for (int kind = 0; kind < n_kinds; ++kind) {
         for (int slot = 0; slot < nslots; ++slot) {
+          TSMARK(15);
           mbar_wait(act_full + slot, (act_ph >> slot) & 1); act_ph ^= 1u << slot;
           tc_fence_after();
+          TSMARK(12);
           const float* b_hi = sbase + kSOffAct + slot * 2 * kTcActFloats;
-          const uint32_t dt = tmem + (uint32_t)slot * 2 * kTcCols;
+          const uint32_t dt = tmem + (uint32_t)slot * kTcCols;
           if (slot == 0) { mbar_wait(w_full, wfull_ph & 1); wfull_ph ^= 1; }
+          TSMARK(13);
           issue_gemm_steps(dt, wbuf, wbuf + kTcWFloats, b_hi, 0, ksteps < 8 ? ksteps : 8, leader);
           if (slot == nslots - 1 && leader) umma_commit(w_free);
+          TSMARK(14);
           if (slot == 0) { mbar_wait(w_full + 1, (wfull_ph >> 1) & 1); wfull_ph ^= 2; }
+          TSMARK(13);
           issue_gemm_steps(dt, wbuf, wbuf + kTcWFloats, b_hi, 8, ksteps, leader);
           if (leader) umma_commit(d_full + slot);
           if (slot == nslots - 1 && leader) umma_commit(w_free + 1);
           __syncwarp();
+          TSMARK(14);
         }
         const int next = kind + 1 < n_kinds ? kind + 1 : (it + 1 < iters ? 0 : -1);
         if (next >= 0) {
@@ -198,11 +227,128 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
         }
       }
     }
+#ifdef TDB_TC_TIMING
+    if (a.dbg && lane == 0)
+      for (int i = 12; i < 16; ++i) a.dbg[(size_t)blockIdx.x * 16 + i] = tacc[i];
+#endif
+  } else if (is_op_warp) {
+    // ===================================================================================================
+    // operator warp: last-layer sums -> u, operator terms, residual, loss, adjoint seeds (one lane per point)
+    // ===================================================================================================
+    const bool fast_op = *fastS != 0;
+    const tdb200_segment& sg = *segS;
+    const int ncols = sg.n_cols;
+    uint32_t req_ph = 0;
+    for (int it = 0; it < iters; ++it) {
+      const int nslots = (2 * it + 1 < my_tiles) ? 2 : 1;
+      for (int slot = 0; slot < nslots; ++slot) {
+        const int tile = tile_of(it, slot);
+        const long long g_first = (long long)tile * P;
+        const int p_valid = (int)min((long long)P, sg.n_groups - g_first);
+        float* const Us = sbase + kSOffU + slot * kTcMaxOut * kTcCols;
+        float* const Gus = sbase + kSOffGu + slot * kTcMaxOut * kTcCols;
+        mbar_wait(op_req + slot, (req_ph >> slot) & 1); req_ph ^= 1u << slot;
+        for (int idx = lane; idx < n_out * kTcCols; idx += 32) {
+          const int v = idx / kTcCols, r = idx - v * kTcCols;
+          const int jc = r & (kTcPC - 1);
+          float sacc = (jc < C && jc % J == 0) ? (sbase + kSOffBl)[v] : 0.f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) sacc += (sbase + kSOffUP)[(w * kTcMaxOut + v) * kTcCols + r];
+          Us[idx] = sacc;
+          Gus[idx] = 0.f;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(up_free);
+      if (lane < p_valid && fast_op) {
+        const int p = lane;
+        const int pc = (p / PH) * kTcPC + (p % PH) * J;
+        const long long row = g_first + p;
+        const float* u = Us + pc;
+        float* gu = Gus + pc;
+        auto pw = [](float xx, int i) { const float x2 = xx * xx; return i == 1 ? xx : i == 2 ? x2 : i == 3 ? x2 * xx : 1.f; };
+        auto dpw = [](float xx, int i) { return i == 1 ? 1.f : i == 2 ? 2.f * xx : i == 3 ? 3.f * xx * xx : 0.f; };
+        for (int col = 0; col < ncols; ++col) {
+          const int tb = sg.col_term_begin[col], te = sg.col_term_end[col];
+          float val = 0.f;
+          for (int t = tb; t < te; ++t) {
+            const int4 r = recS[t];
+            const float cf = r.y == 0 ? __int_as_float(r.x) : r.y == 1 ? __ldg(a.coeffs + r.x + row) : a.arena[a.n_net_params + r.x];
+            const int o0 = r.z & 0xFFFF, o1 = (r.z >> 16) & 0xFFFF;
+            const float x0 = o0 != 0xFFFF ? u[o0] : 1.f, x1 = o1 != 0xFFFF ? u[o1] : 1.f;
+            val = fmaf(cf * pw(x0, r.w & 255), pw(x1, r.w >> 8), val);
+          }
+          if (a.fields) a.fields[sg.field_off + row * ncols + col] = val;
+          const float tgt = sg.tgt_off >= 0 ? __ldg(a.targets + sg.tgt_off + row * ncols + col) : 0.f;
+          const float res = val - tgt;
+          const float rw = a.row_weight ? __ldg(a.row_weight + row) : 1.f;        // causal-loss weight (no grad)
+          lossT[p * TDB200_MAX_COLS + col] += (double)rw * (double)res * (double)res;
+          if (!a.do_grad) continue;
+          const float seed = a.field_seed ? __ldg(a.field_seed + sg.field_off + row * ncols + col)
+                                          : 2.f * scaleS[sg.col_slot[col]] * rw * res;
+          for (int t = tb; t < te; ++t) {
+            const int4 r = recS[t];
+            const float cf = r.y == 0 ? __int_as_float(r.x) : r.y == 1 ? __ldg(a.coeffs + r.x + row) : a.arena[a.n_net_params + r.x];
+            const int o0 = r.z & 0xFFFF, o1 = (r.z >> 16) & 0xFFFF;
+            const float x0 = o0 != 0xFFFF ? u[o0] : 1.f, x1 = o1 != 0xFFFF ? u[o1] : 1.f;
+            const float p0 = pw(x0, r.w & 255), p1 = pw(x1, r.w >> 8), sc = seed * cf;
+            if (o0 != 0xFFFF) gu[o0] += sc * dpw(x0, r.w & 255) * p1;
+            if (o1 != 0xFFFF) gu[o1] += sc * p0 * dpw(x1, r.w >> 8);
+            if (r.y == 2) atomicAdd(&(sbase + kSOffCg)[r.x], seed * p0 * p1);
+          }
+        }
+      } else if (lane < p_valid) {
+        const int p = lane;
+        const int pc = (p / PH) * kTcPC + (p % PH) * J;
+        const long long row = g_first + p;
+        for (int col = 0; col < ncols; ++col) {
+          float val = 0.f;
+          for (int t = sg.col_term_begin[col]; t < sg.col_term_end[col]; ++t) {
+            const tdb200_term tm = termS[t];
+            float prod = tm.kind == 0 ? tm.coeff : tm.kind == 1 ? __ldg(a.coeffs + tm.idx + row)
+                                                                 : a.arena[a.n_net_params + tm.idx];
+            for (int fi = tm.fac_begin; fi < tm.fac_end; ++fi) {
+              const tdb200_factor fc = facS[fi];
+              prod *= pow_i(Us[fc.var * kTcCols + pc + fc.chan], fc.ipow, fc.pow);
+            }
+            val += prod;
+          }
+          if (a.fields) a.fields[sg.field_off + row * ncols + col] = val;
+          const float tgt = sg.tgt_off >= 0 ? __ldg(a.targets + sg.tgt_off + row * ncols + col) : 0.f;
+          const float res = val - tgt;
+          const float rw = a.row_weight ? __ldg(a.row_weight + row) : 1.f;
+          lossT[p * TDB200_MAX_COLS + col] += (double)rw * (double)res * (double)res;
+          if (!a.do_grad) continue;
+          const float seed = a.field_seed ? __ldg(a.field_seed + sg.field_off + row * ncols + col)
+                                          : 2.f * scaleS[sg.col_slot[col]] * rw * res;
+          for (int t = sg.col_term_begin[col]; t < sg.col_term_end[col]; ++t) {
+            const tdb200_term tm = termS[t];
+            const float cf = tm.kind == 0 ? tm.coeff : tm.kind == 1 ? __ldg(a.coeffs + tm.idx + row)
+                                                                     : a.arena[a.n_net_params + tm.idx];
+            float full = 1.f;
+            for (int fi = tm.fac_begin; fi < tm.fac_end; ++fi) {
+              const tdb200_factor fc = facS[fi];
+              const float xx = Us[fc.var * kTcCols + pc + fc.chan];
+              float part_ = seed * cf * dpow_i(xx, fc.ipow, fc.pow);
+              for (int fj = tm.fac_begin; fj < tm.fac_end; ++fj) {
+                if (fj == fi) continue;
+                const tdb200_factor fo = facS[fj];
+                part_ *= pow_i(Us[fo.var * kTcCols + pc + fo.chan], fo.ipow, fo.pow);
+              }
+              Gus[fc.var * kTcCols + pc + fc.chan] += part_;
+              full *= pow_i(xx, fc.ipow, fc.pow);
+            }
+            if (tm.kind == 2) atomicAdd(&(sbase + kSOffCg)[tm.idx], seed * full);
+          }
+        }
+      }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(op_done + slot);
+      }
+    }
   } else {
     // ===================================================================================================
     // epilogue warps
     // ===================================================================================================
-    const bool fast_op = *fastS != 0;
     const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);    // this warp's lane window
     const int actA = (part >> 1) * kTcActBlock + n * 32 + ((((part & 1) * 2) ^ (n & 3)) << 3);       // columns 0..7
     const int actB = (part >> 1) * kTcActBlock + n * 32 + ((((part & 1) * 2 + 1) ^ (n & 3)) << 3);   // columns 8..15
@@ -223,11 +369,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
     float w0d[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) w0d[i] = i < ND ? w0[dir_axis[i]] : 0.f;
-    const long long row0 = (long long)x.tile0 * P * J;   // first stream row of this chunk
-    uint32_t d_ph = 0;                                   // parity bit per slot of d_full
+    uint32_t d_ph = 0, done_ph = 0, up_ph = 0;            // parity bits (per slot) of d_full, op_done; of up_free
 
     auto xbuf_of = [&](int slot, int it) { return sbase + kSOffX + (slot * 2 + (it & 1)) * kTcMaxPts * 4; };
-    auto tile_of = [&](int it, int slot) { return x.tile0 + (int)blockIdx.x + (2 * it + slot) * G; };
     auto load_points = [&](int it) {                     // points of both slots of iteration `it` (asynchronous)
       for (int slot = 0; slot < 2; ++slot) {
         const int tile = tile_of(it, slot);
@@ -309,14 +453,15 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
       st4(ah + actA, hi); st4(ah + actA + 4, hi + 4); st4(ah + actB, hi + 8); st4(ah + actB + 4, hi + 12);
       st4(al + actA, lo); st4(al + actA + 4, lo + 4); st4(al + actB, lo + 8); st4(al + actB + 4, lo + 12);
     };
-    // rows (point, channel) of this thread's columns -> stream array of one layer (coalesced over the 32 neurons of a warp)
+    // this thread's columns -> stream array of one layer: float4 q of (tile, part) at [((tile * 4 + part) * Q + q) * Wp + n],
+    // i.e. every warp store writes 512 contiguous bytes.  Which (point, channel) row a column is does not matter to the
+    // contraction over rows in wgrad_gemm_kernel as long as Y and gZ use the same order; pad columns and the columns of
+    // points beyond the segment carry gZ = 0.
     auto stream_rows = [&](float* arr, int tile, const float* v) {
       if (n >= x.Wp) return;
-      const long long pt0 = (long long)tile * P + part * PH;
-      float* dst = arr + (size_t)(pt0 * J - row0) * x.Wp + n;
+      float4* dst = reinterpret_cast<float4*>(arr) + ((size_t)(tile - x.tile0) * 4 + part) * (Q * x.Wp) + n;
 #pragma unroll
-      for (int j = 0; j < C; ++j)
-        if (pt0 + j / J < sg.n_groups) __stcs(dst + (size_t)j * x.Wp, v[j]);
+      for (int q = 0; q < Q; ++q) __stcs(dst + q * x.Wp, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
     };
     auto hand_over = [&](int slot) {                      // operand image of the slot is complete (this warp's part)
       fence_async_smem();
@@ -329,14 +474,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
       d_ph ^= 1u << slot;
       tc_fence_after();
     };
-    auto load_d = [&](int slot, float* v) {               // accumulator halves of the N = 128 + N = 64 MMA pair
-      float v2[16];
-      const uint32_t base = t_lane + (uint32_t)slot * 2 * kTcCols + (uint32_t)col0;
-      tmem_ld16(base, v);
-      tmem_ld16(base + kTcCols, v2);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] += v2[j];
-    };
+    auto load_d = [&](int slot, float* v) { tmem_ld16(t_lane + (uint32_t)slot * kTcCols + (uint32_t)col0, v); };
     auto zsave_ptr = [&](int slot, int l) {                // saved jets of W x W layer l (1..NM)
       return reinterpret_cast<float4*>(x.zsave + ((((size_t)blockIdx.x * 2 + slot) * NM + (l - 1)) * kTsEpi + tid) * 16);
     };
@@ -344,9 +482,11 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
     if (iters > 0) load_points(0);
     for (int it = 0; it < iters; ++it) {
       const int nslots = (2 * it + 1 < my_tiles) ? 2 : 1;
+      TSMARK(11);
       asm volatile("cp.async.wait_all;" ::: "memory");
       epi_sync();                                         // this iteration's points are visible
       if (it + 1 < iters) load_points(it + 1);
+      TSMARK(0);
 
       // ---- layer 0 (K = d): thread-local ---------------------------------------------------------------
       for (int slot = 0; slot < nslots; ++slot) {
@@ -361,6 +501,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
         if (live) store_act(slot, y);
         if (a.do_grad) stream_rows(x.ys, tile_of(it, slot), y);
         hand_over(slot);
+        TSMARK(1);
       }
       // ---- W x W layers 1 .. NM - 1: GEMM (MMA warp) + tanh-jet epilogue --------------------------------
       for (int l = 1; l < NM; ++l) {
@@ -368,6 +509,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
         for (int slot = 0; slot < nslots; ++slot) {
           float z[16], y[16];
           wait_d(slot);
+          TSMARK(2);
           load_d(slot, z);
 #pragma unroll
           for (int p = 0; p < PH; ++p) z[p * J] += bl;
@@ -380,20 +522,20 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
           if (live) store_act(slot, y);
           if (a.do_grad) stream_rows(x.ys + (size_t)l * x.stream_stride, tile_of(it, slot), y);
           hand_over(slot);
+          TSMARK(3);
         }
       }
-      // ---- layer NM epilogue, last layer, operator, adjoint seeds, backward of layers L-1 and NM -----------
+      // ---- layer NM epilogue + last layer (partial sums for the operator warp) ------------------------------------
       const float bNM = live ? __ldg(a.arena + a.b_off[NM] + n) : 0.f;
       for (int slot = 0; slot < nslots; ++slot) {
-        const int tile = tile_of(it, slot);
-        const long long g_first = (long long)tile * P;
-        const int p_valid = (int)min((long long)P, sg.n_groups - g_first);
         float z[16], y[16];
         wait_d(slot);
+        TSMARK(4);
         load_d(slot, z);
 #pragma unroll
         for (int p = 0; p < PH; ++p) z[p * J] += bNM;
         jets_fwd(z, false, y);
+        if (it > 0 || slot > 0) { mbar_wait(up_free, up_ph); up_ph ^= 1; }     // the operator warp has read the previous sums
         for (int v = 0; v < n_out; ++v) {
           float t16[16];
 #pragma unroll
@@ -401,126 +543,45 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
           const float tot = warp_multi_reduce16(t16, lane);
           if ((lane & 1) == 0) (sbase + kSOffUP)[((warp & 3) * kTcMaxOut + v) * kTcCols + col0 + reduce16_col(lane)] = tot;
         }
-        epi_sync();
-        for (int idx = tid; idx < n_out * kTcCols; idx += kTsEpi) {
-          const int v = idx / kTcCols, r = idx - v * kTcCols;
-          const int jc = r & (kTcPC - 1);
-          float s = (jc < C && jc % J == 0) ? (sbase + kSOffBl)[v] : 0.f;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(op_req + slot);
+        TSMARK(5);
+      }
+      if (!a.do_grad) continue;
+      // ---- backward of the last layer and of tanh layer NM (the operator warp has produced the adjoint seeds) ------
+      for (int slot = 0; slot < nslots; ++slot) {
+        const int tile = tile_of(it, slot);
+        const float* const Gus = sbase + kSOffGu + slot * kTcMaxOut * kTcCols;
+        float z[16], y[16];
+        load_d(slot, z);                                  // layer NM's pre-activations are still in the accumulator
 #pragma unroll
-          for (int w = 0; w < 4; ++w) s += (sbase + kSOffUP)[(w * kTcMaxOut + v) * kTcCols + r];
-          (sbase + kSOffU)[idx] = s;
-          (sbase + kSOffGu)[idx] = 0.f;
-        }
-        epi_sync();
-        if (tid < p_valid && fast_op) {
-          const int p = tid;
-          const int pc = (p / PH) * kTcPC + (p % PH) * J;
-          const long long row = g_first + p;
-          const float* u = (sbase + kSOffU) + pc;
-          float* gu = (sbase + kSOffGu) + pc;
-          auto pw = [](float xx, int i) { const float x2 = xx * xx; return i == 1 ? xx : i == 2 ? x2 : i == 3 ? x2 * xx : 1.f; };
-          auto dpw = [](float xx, int i) { return i == 1 ? 1.f : i == 2 ? 2.f * xx : i == 3 ? 3.f * xx * xx : 0.f; };
-          for (int col = 0; col < ncols; ++col) {
-            const int tb = sg.col_term_begin[col], te = sg.col_term_end[col];
-            float val = 0.f;
-            for (int t = tb; t < te; ++t) {
-              const int4 r = recS[t];
-              const float cf = r.y == 0 ? __int_as_float(r.x) : r.y == 1 ? __ldg(a.coeffs + r.x + row) : a.arena[a.n_net_params + r.x];
-              const int o0 = r.z & 0xFFFF, o1 = (r.z >> 16) & 0xFFFF;
-              const float x0 = o0 != 0xFFFF ? u[o0] : 1.f, x1 = o1 != 0xFFFF ? u[o1] : 1.f;
-              val = fmaf(cf * pw(x0, r.w & 255), pw(x1, r.w >> 8), val);
-            }
-            if (a.fields) a.fields[sg.field_off + row * ncols + col] = val;
-            const float tgt = sg.tgt_off >= 0 ? __ldg(a.targets + sg.tgt_off + row * ncols + col) : 0.f;
-            const float res = val - tgt;
-            const float rw = a.row_weight ? __ldg(a.row_weight + row) : 1.f;        // causal-loss weight (no grad)
-            lossT[p * TDB200_MAX_COLS + col] += (double)rw * (double)res * (double)res;
-            if (!a.do_grad) continue;
-            const float seed = a.field_seed ? __ldg(a.field_seed + sg.field_off + row * ncols + col)
-                                            : 2.f * scaleS[sg.col_slot[col]] * rw * res;
-            for (int t = tb; t < te; ++t) {
-              const int4 r = recS[t];
-              const float cf = r.y == 0 ? __int_as_float(r.x) : r.y == 1 ? __ldg(a.coeffs + r.x + row) : a.arena[a.n_net_params + r.x];
-              const int o0 = r.z & 0xFFFF, o1 = (r.z >> 16) & 0xFFFF;
-              const float x0 = o0 != 0xFFFF ? u[o0] : 1.f, x1 = o1 != 0xFFFF ? u[o1] : 1.f;
-              const float p0 = pw(x0, r.w & 255), p1 = pw(x1, r.w >> 8), sc = seed * cf;
-              if (o0 != 0xFFFF) gu[o0] += sc * dpw(x0, r.w & 255) * p1;
-              if (o1 != 0xFFFF) gu[o1] += sc * p0 * dpw(x1, r.w >> 8);
-              if (r.y == 2) atomicAdd(&(sbase + kSOffCg)[r.x], seed * p0 * p1);
-            }
-          }
-        } else if (tid < p_valid) {
-          const int p = tid;
-          const int pc = (p / PH) * kTcPC + (p % PH) * J;
-          const long long row = g_first + p;
-          for (int col = 0; col < ncols; ++col) {
-            float val = 0.f;
-            for (int t = sg.col_term_begin[col]; t < sg.col_term_end[col]; ++t) {
-              const tdb200_term tm = termS[t];
-              float prod = tm.kind == 0 ? tm.coeff : tm.kind == 1 ? __ldg(a.coeffs + tm.idx + row)
-                                                                   : a.arena[a.n_net_params + tm.idx];
-              for (int fi = tm.fac_begin; fi < tm.fac_end; ++fi) {
-                const tdb200_factor fc = facS[fi];
-                prod *= pow_i((sbase + kSOffU)[fc.var * kTcCols + pc + fc.chan], fc.ipow, fc.pow);
-              }
-              val += prod;
-            }
-            if (a.fields) a.fields[sg.field_off + row * ncols + col] = val;
-            const float tgt = sg.tgt_off >= 0 ? __ldg(a.targets + sg.tgt_off + row * ncols + col) : 0.f;
-            const float res = val - tgt;
-            const float rw = a.row_weight ? __ldg(a.row_weight + row) : 1.f;
-            lossT[p * TDB200_MAX_COLS + col] += (double)rw * (double)res * (double)res;
-            if (!a.do_grad) continue;
-            const float seed = a.field_seed ? __ldg(a.field_seed + sg.field_off + row * ncols + col)
-                                            : 2.f * scaleS[sg.col_slot[col]] * rw * res;
-            for (int t = sg.col_term_begin[col]; t < sg.col_term_end[col]; ++t) {
-              const tdb200_term tm = termS[t];
-              const float cf = tm.kind == 0 ? tm.coeff : tm.kind == 1 ? __ldg(a.coeffs + tm.idx + row)
-                                                                       : a.arena[a.n_net_params + tm.idx];
-              float full = 1.f;
-              for (int fi = tm.fac_begin; fi < tm.fac_end; ++fi) {
-                const tdb200_factor fc = facS[fi];
-                const float xx = (sbase + kSOffU)[fc.var * kTcCols + pc + fc.chan];
-                float part_ = seed * cf * dpow_i(xx, fc.ipow, fc.pow);
-                for (int fj = tm.fac_begin; fj < tm.fac_end; ++fj) {
-                  if (fj == fi) continue;
-                  const tdb200_factor fo = facS[fj];
-                  part_ *= pow_i((sbase + kSOffU)[fo.var * kTcCols + pc + fo.chan], fo.ipow, fo.pow);
-                }
-                (sbase + kSOffGu)[fc.var * kTcCols + pc + fc.chan] += part_;
-                full *= pow_i(xx, fc.ipow, fc.pow);
-              }
-              if (tm.kind == 2) atomicAdd(&(sbase + kSOffCg)[tm.idx], seed * full);
-            }
-          }
-        }
-        epi_sync();
-        if (!a.do_grad) continue;
-        // backward of the last layer: dWl, dbl; gY of tanh layer NM
+        for (int p = 0; p < PH; ++p) z[p * J] += bNM;
+        jets_fwd(z, false, y);
+        mbar_wait(op_done + slot, (done_ph >> slot) & 1); done_ph ^= 1u << slot;
+        TSMARK(6);
         if (tid < n_out) {
-          float s = 0.f;
-          for (int p = 0; p < P; ++p) s += (sbase + kSOffGu)[tid * kTcCols + (p / PH) * kTcPC + (p % PH) * J];
-          dbl_acc += s;
+          float sacc = 0.f;
+          for (int p = 0; p < P; ++p) sacc += Gus[tid * kTcCols + (p / PH) * kTcPC + (p % PH) * J];
+          dbl_acc += sacc;
         }
         float gy[16], gz[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) gy[j] = 0.f;
         for (int v = 0; v < n_out; ++v) {
-          float s = 0.f;
+          float sacc = 0.f;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 g4 = *reinterpret_cast<const float4*>((sbase + kSOffGu) + v * kTcCols + col0 + 4 * q);
+            const float4 g4 = *reinterpret_cast<const float4*>(Gus + v * kTcCols + col0 + 4 * q);
             const float g[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              s = fmaf(g[i], y[4 * q + i], s);
+              sacc = fmaf(g[i], y[4 * q + i], sacc);
               gy[4 * q + i] = fmaf(wl[v], g[i], gy[4 * q + i]);
             }
           }
 #pragma unroll
-          for (int vv = 0; vv < kTcMaxOut; ++vv) if (vv == v) dwl_acc[vv] += s;
+          for (int vv = 0; vv < kTcMaxOut; ++vv) if (vv == v) dwl_acc[vv] += sacc;
         }
-        epi_sync();                                       // everybody has read Gu before the next slot clears it
         db_acc[NM] += jets_bwd(z, false, gy, gz, nullptr);
         if (!live) {
 #pragma unroll
@@ -529,8 +590,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
         if (live) store_act(slot, gz);
         stream_rows(x.gs + (size_t)(NM - 1) * x.stream_stride, tile, gz);
         hand_over(slot);
+        TSMARK(7);
       }
-      if (!a.do_grad) continue;
       // ---- backward sweep over the W x W layers NM - 1 .. 1 ---------------------------------------------------
       for (int t = NM - 1; t >= 1; --t) {
         for (int slot = 0; slot < nslots; ++slot) {
@@ -541,6 +602,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
             for (int q = 0; q < 4; ++q) { const float4 v4 = zs[q]; z[4 * q] = v4.x; z[4 * q + 1] = v4.y; z[4 * q + 2] = v4.z; z[4 * q + 3] = v4.w; }
           }
           wait_d(slot);
+          TSMARK(8);
           load_d(slot, gy);
           db_acc[t] += jets_bwd(z, false, gy, gz, nullptr);
           if (!live) {
@@ -550,6 +612,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
           if (live) store_act(slot, gz);
           stream_rows(x.gs + (size_t)(t - 1) * x.stream_stride, tile_of(it, slot), gz);
           hand_over(slot);
+          TSMARK(9);
         }
       }
       // ---- backward of layer 0 (thread-local) --------------------------------------------------------------
@@ -557,6 +620,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
         const float* xs = xbuf_of(slot, it);
         float z[16], gy[16], gz[16], g0[PH];
         wait_d(slot);
+        TSMARK(10);
         load_d(slot, gy);
 #pragma unroll
         for (int p = 0; p < PH; ++p) {
@@ -573,8 +637,12 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
       }
     }
 
-    // ---- flush: per-thread accumulators, per-CTA scalars ----------------------------------------------------
-    epi_sync();
+    TSMARK(11);
+#ifdef TDB_TC_TIMING
+    if (a.dbg && tid == 0)
+      for (int i = 0; i < 12; ++i) a.dbg[(size_t)blockIdx.x * 16 + i] = tacc[i];
+#endif
+    // ---- flush: per-thread accumulators ----------------------------------------------------------------------
     const bool acc = !x.zero_partials;
     auto put = [&](float* q, float v) { *q = acc ? *q + v : v; };
     if (a.do_grad) {
@@ -587,20 +655,28 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
         for (int v = 0; v < kTcMaxOut; ++v) if (v < n_out) put(my_grad + a.w_off[L - 1] + v * W + n, dwl_acc[v]);
       }
       if (tid < n_out) put(my_grad + a.b_off[L - 1] + tid, dbl_acc);     // warp 0 -> part-0 row
-      if (tid < a.n_cparams) put(my_grad + a.n_net_params + tid, (sbase + kSOffCg)[tid]);
-    }
-    if (tid < a.n_slots) {
-      double s = 0.0;
-      for (int col = 0; col < ncols; ++col)
-        if (sg.col_slot[col] == tid)
-          for (int p = 0; p < P; ++p) s += lossT[p * TDB200_MAX_COLS + col];
-      double* q = a.part_loss + (size_t)blockIdx.x * a.n_slots + tid;
-      *q = acc ? *q + s : s;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (is_mma_warp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem) : "memory");
+  // ---- per-CTA scalars (accumulated by the operator warp) -----------------------------------------------------
+  {
+    const bool acc = !x.zero_partials;
+    const tdb200_segment& sg = *segS;
+    if (a.do_grad && tid < a.n_cparams) {
+      float* q = a.part_grad + (size_t)blockIdx.x * kTcParts * a.n_params_pad + a.n_net_params + tid;
+      *q = acc ? *q + (sbase + kSOffCg)[tid] : (sbase + kSOffCg)[tid];
+    }
+    if (tid < a.n_slots) {
+      double sacc = 0.0;
+      for (int col = 0; col < sg.n_cols; ++col)
+        if (sg.col_slot[col] == tid)
+          for (int p = 0; p < P; ++p) sacc += lossT[p * TDB200_MAX_COLS + col];
+      double* q = a.part_loss + (size_t)blockIdx.x * a.n_slots + tid;
+      *q = acc ? *q + sacc : sacc;
+    }
+  }
+  if (is_mma_warp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" :: "r"(tmem) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------

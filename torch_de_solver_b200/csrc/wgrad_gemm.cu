@@ -1,37 +1,53 @@
 // Weight-gradient GEMM of the streamed tensor-core path (jet_tcs_kernel.cuh):
-//     dW_t[n, k] = sum_r gZ_t[r, n] * Y_{t-1}[r, k]        r = (point, jet channel) rows of the chunk
-// for the W x W layers t = 1..n_mma.  The fused forward / backward kernel streams gZ_t and Y_{t-1} as fp32 row
-// arrays [rows][Wp] to HBM; this kernel is the split-K contraction over the rows: HBM-bound (2 * Wp * 4 bytes per
-// row and layer), tcgen05.mma.kind::tf32 in the 3xTF32 split with the accumulator in TMEM.
+//     dW_t[n, k] = sum_r gZ_t[r, n] * Y_{t-1}[r, k]        r = (point, jet channel) columns of the chunk's tiles
+// for the W x W layers t = 1..n_mma.  The fused forward / backward kernel streams gZ_t and Y_{t-1} to HBM as fp32
+// arrays of float4 [group of 4 columns][Wp neurons]; this kernel is the split-K contraction over the columns:
+// HBM-bound (2 * Wp * 4 bytes per column and layer), tcgen05.mma.kind::tf32 in the 3xTF32 split, accumulator in TMEM.
 //
-// One CTA = one (layer, row range).  Warps 0..7 stream the rows: coalesced 16-byte loads (one row = Wp / 4 lanes),
-// hi = cvt.rna.tf32, lo = x - hi, 16-byte stores into MN-major operand images (SWIZZLE_128B_BASE32B: [MN block of
-// 32][K rows][32 floats], 32-byte chunks XOR (row & 3)) of a 3-stage ring; warp 8 issues, per K-step of 8 rows,
-//     D[128 x 112] += gZ_hi^T Y_hi + gZ_hi^T Y_lo + gZ_lo^T Y_hi        (A = gZ image, B = Y image, both MN-major)
-// and releases the stage with tcgen05.commit.  The CTA's partial dW goes to its own row of the gradient partial
-// buffer (reduced in a fixed order by reduce_partials_kernel -> bit-reproducible).
+// One CTA = one (layer, range of stages); a stage = KB = 24 or 32 columns of both operands = two contiguous runs of
+// KB * Wp floats.  Three roles:
+//   * warp 9 (one lane): cp.async.bulk of the two runs of a stage into a 3-deep ring of raw buffers, completion on an
+//     mbarrier - the HBM stream is asynchronous and ~80 KB deep per SM, independent of the registers of the other warps;
+//   * warps 0..7: raw buffer -> operand images: hi = tf32 round-to-nearest (integer ALU), lo = x - hi, scalar stores
+//     (32 consecutive neurons per warp: conflict-free) into MN-major images (SWIZZLE_128B_BASE32B: [MN block of 32][K
+//     rows][32 floats], 32-byte chunks XOR (row & 3)), 2-deep ring;
+//   * warp 8 issues, per K-step of 8 rows,
+//         D[128 x 112] += gZ_hi^T Y_hi + gZ_hi^T Y_lo + gZ_lo^T Y_hi        (A = gZ image, B = Y image, both MN-major)
+//     and releases the image stage with tcgen05.commit.
+// The CTA's partial dW goes to its own row of the gradient partial buffer (reduced in a fixed order by
+// reduce_partials_kernel -> bit-reproducible).
 #include "jet_tc_kernel.cuh"
 #include "jet_tcs.cuh"
 
 namespace tdb {
 
-constexpr int kWgKB = 32;                          // rows (K) per stage
-constexpr int kWgStages = 3;
+constexpr int kWgKB = 32;                          // most rows (K) per stage
+constexpr int kWgRawStages = 3, kWgImgStages = 2;
 constexpr int kWgImg = 4 * kWgKB * 32;             // floats of one operand image: 4 MN blocks x 32 K rows x 32
-constexpr int kWgStageFloats = 4 * kWgImg;         // A hi, A lo, B hi, B lo = 64 KB
-constexpr int kWgLoaderWarps = 8;
-constexpr int kWgThreads = (kWgLoaderWarps + 1) * 32;
-constexpr size_t kWgSmemBytes = (size_t)kWgStages * kWgStageFloats * 4 + 1024 + 128;
+constexpr int kWgImgStageFloats = 4 * kWgImg;      // A hi, A lo, B hi, B lo = 64 KB
+constexpr int kWgRawOp = kWgKB * 104;              // floats of one operand of a raw stage (Wp <= 104)
+constexpr int kWgRawStageFloats = 2 * kWgRawOp;    // 26 KB
+constexpr int kWgConvWarps = 8;
+constexpr int kWgThreads = (kWgConvWarps + 2) * 32;
+constexpr size_t kWgSmemBytes =
+    (size_t)(kWgImgStages * kWgImgStageFloats + kWgRawStages * kWgRawStageFloats) * 4 + 1024 + 256;
+
+__device__ __forceinline__ void wg_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
 
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const WgradArgs a) {
   extern __shared__ uint8_t smem_raw_wg[];
   const uint32_t s0_ = smem_u32(smem_raw_wg);
   float* const sbase = reinterpret_cast<float*>(smem_raw_wg + (((s0_ + 1023u) & ~1023u) - s0_));
-  uint64_t* const bars = reinterpret_cast<uint64_t*>(sbase + kWgStages * kWgStageFloats);
-  uint64_t* const full = bars;                     // [stages] loader warps -> MMA warp
-  uint64_t* const empty = bars + kWgStages;        // [stages] MMA warp (tcgen05.commit) -> loader warps
-  uint64_t* const done = bars + 2 * kWgStages;
-  uint32_t* const tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 1);
+  float* const raw = sbase + kWgImgStages * kWgImgStageFloats;
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(raw + kWgRawStages * kWgRawStageFloats);
+  uint64_t* const raw_full = bars;                 // [3] bulk copies -> converters
+  uint64_t* const raw_empty = bars + 3;            // [3] converters (8 arrivals) -> producer
+  uint64_t* const img_full = bars + 6;             // [2] converters (8 arrivals) -> MMA warp
+  uint64_t* const img_empty = bars + 8;            // [2] MMA warp (tcgen05.commit) -> converters
+  uint64_t* const done = bars + 10;
+  uint32_t* const tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   const int layer = blockIdx.x % a.n_mma;          // 0-based: dW of W x W layer `layer + 1`
@@ -39,18 +55,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const WgradAr
   if (!a.accumulate)                               // first chunk of a call: the row holds nothing but this CTA's dW block
     for (int i = tid; i < a.n_params_pad; i += kWgThreads) a.part[(size_t)blockIdx.x * a.n_params_pad + i] = 0.f;
   if (split >= a.splits) return;                   // idle CTA: its partial row stays zero
-  const long long n_kb = (a.rows + kWgKB - 1) / kWgKB;
+  const int KB = a.kb, Wp = a.Wp;
+  const int F = KB * Wp / 4;                       // float4 per operand and stage
+  const long long n_kb = (a.total4 + F - 1) / F;
   const long long kb0 = n_kb * split / a.splits, kb1 = n_kb * (split + 1) / a.splits;
   const float* __restrict__ gs = a.gs + (size_t)layer * a.stream_stride;
   const float* __restrict__ ys = a.ys + (size_t)layer * a.stream_stride;
-  const int Wp = a.Wp, nq = Wp >> 2;               // float4 per row
 
-  for (int i = tid; i < kWgStages * kWgStageFloats; i += kWgThreads) sbase[i] = 0.f;     // MN pad (>= Wp) stays zero
+  // MN pad (neurons >= Wp) of the images stays zero
+  for (int i = tid; i < kWgImgStages * kWgImgStageFloats; i += kWgThreads) sbase[i] = 0.f;
   if (tid == 0) {
-    for (int s = 0; s < kWgStages; ++s) { mbar_init(full + s, kWgLoaderWarps); mbar_init(empty + s, 1); }
+    for (int s = 0; s < kWgRawStages; ++s) { mbar_init(raw_full + s, 1); mbar_init(raw_empty + s, kWgConvWarps); }
+    for (int s = 0; s < kWgImgStages; ++s) { mbar_init(img_full + s, kWgConvWarps); mbar_init(img_empty + s, 1); }
     mbar_init(done, 1);
   }
-  if (warp == kWgLoaderWarps) {
+  if (warp == kWgConvWarps) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" :: "r"(smem_u32(tmem_ptr)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -61,53 +80,74 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const WgradAr
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
 
-  if (warp < kWgLoaderWarps) {
-    // ---- loaders: warp w owns K rows 4w .. 4w + 3 of every stage --------------------------------------------
-    float4 g[4], y[4];
-    auto fetch = [&](long long kb) {
+  if (warp == kWgConvWarps + 1) {
+    // ---- producer: HBM -> raw ring ------------------------------------------------------------------------------
+    if (lane == 0) {
+      for (long long kb = kb0; kb < kb1; ++kb) {
+        const long long i = kb - kb0;
+        const int st = (int)(i % kWgRawStages);
+        const uint32_t use = (uint32_t)(i / kWgRawStages);
+        if (use > 0) mbar_wait(raw_empty + st, (use - 1) & 1);
+        const long long f0 = kb * F;
+        const long long nf = a.total4 - f0 < F ? a.total4 - f0 : F;            // float4 of this stage (tail: fewer)
+        const uint32_t bytes = (uint32_t)nf * 16u;
+        const uint32_t b = smem_u32(raw_full + st);
+        float* dst = raw + st * kWgRawStageFloats;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(2 * bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(smem_u32(dst)), "l"(gs + f0 * 4), "r"(bytes), "r"(b) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(smem_u32(dst + kWgRawOp)), "l"(ys + f0 * 4), "r"(bytes), "r"(b) : "memory");
+      }
+    }
+  } else if (warp < kWgConvWarps) {
+    // ---- converters: thread t owns the float4 t, t + 256, ... of every stage (same image positions every stage) ----
+    int off[4];                                     // image offset of element 0 of the float4 (element e: K row + e)
+    int c3[4];
+    bool own[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const long long r = kb * kWgKB + warp * 4 + i;
-        const bool ok = lane < nq && r < a.rows;
-        g[i] = ok ? __ldcs(reinterpret_cast<const float4*>(gs + (size_t)r * Wp) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-        y[i] = ok ? __ldcs(reinterpret_cast<const float4*>(ys + (size_t)r * Wp) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < 4; ++i) {
+      const int f = tid + 256 * i;
+      own[i] = f < F;
+      const int n = f % Wp, krow = 4 * (f / Wp);
+      off[i] = (n >> 5) * KB * 32 + krow * 32 + (n & 7);
+      c3[i] = (n & 31) >> 3;
+    }
+    auto put = [&](float* hi_img, float* lo_img, int i, const float4& v) {
+      const float xv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float h = tf32_rna(xv[e]);
+        const int o = off[i] + e * 32 + ((c3[i] ^ e) << 3);
+        hi_img[o] = h;
+        lo_img[o] = xv[e] - h;
       }
     };
-    auto put = [&](float* hi_img, float* lo_img, int krow, const float4& v) {
-      const float x[4] = {v.x, v.y, v.z, v.w};
-      float h[4], l[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t hb;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x[j]));
-        h[j] = __uint_as_float(hb);
-        l[j] = x[j] - h[j];
-      }
-      const int off = sw_off_mn(krow, 4 * lane, kWgKB);
-      st4(hi_img + off, h);
-      st4(lo_img + off, l);
-    };
-    if (kb0 < kb1) fetch(kb0);
     for (long long kb = kb0; kb < kb1; ++kb) {
       const long long i = kb - kb0;
-      const int stage = (int)(i % kWgStages);
-      const uint32_t use = (uint32_t)(i / kWgStages);           // how often this stage was filled before
-      if (use > 0) mbar_wait(empty + stage, (use - 1) & 1);     // ... and its (use)-th release by the MMA warp
-      float* const st = sbase + stage * kWgStageFloats;
+      const int rs = (int)(i % kWgRawStages), is = (int)(i % kWgImgStages);
+      const uint32_t ruse = (uint32_t)(i / kWgRawStages), iuse = (uint32_t)(i / kWgImgStages);
+      mbar_wait(raw_full + rs, ruse & 1);
+      const long long nf = a.total4 - kb * F < F ? a.total4 - kb * F : F;
+      const float4* r4 = reinterpret_cast<const float4*>(raw + rs * kWgRawStageFloats);
       float4 gc[4], yc[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { gc[q] = g[q]; yc[q] = y[q]; }
-      if (kb + 1 < kb1) fetch(kb + 1);              // next block's loads fly while this one is converted
-      if (lane < nq) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          put(st, st + kWgImg, warp * 4 + q, gc[q]);
-          put(st + 2 * kWgImg, st + 3 * kWgImg, warp * 4 + q, yc[q]);
-        }
+      for (int q = 0; q < 4; ++q) {
+        const bool ok = own[q] && tid + 256 * q < nf;
+        gc[q] = ok ? r4[tid + 256 * q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        yc[q] = ok ? r4[kWgRawOp / 4 + tid + 256 * q] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      if (iuse > 0) mbar_wait(img_empty + is, (iuse - 1) & 1);
+      float* const st = sbase + is * kWgImgStageFloats;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (own[q]) {
+          put(st, st + kWgImg, q, gc[q]);
+          put(st + 2 * kWgImg, st + 3 * kWgImg, q, yc[q]);
+        }
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(full + stage)) : "memory");
+      if (lane == 0) { wg_arrive(raw_empty + rs); wg_arrive(img_full + is); }   // raw stage consumed: refill it
     }
   } else {
     // ---- MMA warp ---------------------------------------------------------------------------------------------
@@ -116,15 +156,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const WgradAr
     uint32_t fph = 0;
     const bool leader = elect_one();
     for (long long kb = kb0; kb < kb1; ++kb) {
-      mbar_wait(full + stage, fph);
+      mbar_wait(img_full + stage, fph);
       tc_fence_after();
-      const float* st = sbase + stage * kWgStageFloats;
-      // MN blocks of 32 at LBO = one block (kWgKB rows x 128 B); 8 K rows = two 4-row swizzle atoms (SBO = 512 B)
-      const uint64_t ah = umma_desc(smem_u32(st), kWgKB * 128, 512, 1), al = umma_desc(smem_u32(st + kWgImg), kWgKB * 128, 512, 1);
-      const uint64_t bh = umma_desc(smem_u32(st + 2 * kWgImg), kWgKB * 128, 512, 1),
-                     bl = umma_desc(smem_u32(st + 3 * kWgImg), kWgKB * 128, 512, 1);
-#pragma unroll
-      for (int s = 0; s < kWgKB / 8; ++s) {
+      const float* st = sbase + stage * kWgImgStageFloats;
+      // MN blocks of 32 at LBO = one block (KB rows x 128 B); 8 K rows = two 4-row swizzle atoms (SBO = 512 B)
+      const uint64_t ah = umma_desc(smem_u32(st), KB * 128, 512, 1), al = umma_desc(smem_u32(st + kWgImg), KB * 128, 512, 1);
+      const uint64_t bh = umma_desc(smem_u32(st + 2 * kWgImg), KB * 128, 512, 1),
+                     bl = umma_desc(smem_u32(st + 3 * kWgImg), KB * 128, 512, 1);
+      for (int s = 0; s < KB / 8; ++s) {
         const uint64_t o = ((uint64_t)s * 1024) >> 4;
         if (leader) {
           umma_tf32(tmem, ah + o, bh + o, idesc, (kb > kb0 || s > 0) ? 1u : 0u);
@@ -132,18 +171,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const WgradAr
           umma_tf32(tmem, al + o, bh + o, idesc, 1u);
         }
       }
-      if (leader) umma_commit(empty + stage);
+      if (leader) umma_commit(img_empty + stage);
       __syncwarp();
-      if (++stage == kWgStages) { stage = 0; fph ^= 1; }
+      if (++stage == kWgImgStages) { stage = 0; fph ^= 1; }
     }
     if (leader) umma_commit(done);
     __syncwarp();
   }
 
-  // ---- epilogue: TMEM -> this CTA's partial row --------------------------------------------------------------
-  if (warp < kWgLoaderWarps) {
-    const int W = a.W, n = (warp & 3) * 32 + lane, half = warp >> 2;
-    float* const dst = a.part + (size_t)blockIdx.x * a.n_params_pad + a.w_off[layer];
+  // ---- epilogue: TMEM -> shared memory (transposition buffer) -> this CTA's partial row, coalesced -----------------
+  float* const tbuf = sbase;                       // [128][113] floats: the image stages are free by now
+  if (warp < kWgConvWarps) {
+    const int n = (warp & 3) * 32 + lane, half = warp >> 2;
     if (kb0 < kb1) {
       mbar_wait(done, 0);
       tc_fence_after();
@@ -155,19 +194,22 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const WgradAr
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = 0.f;
       }
-      if (n < W) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (k0 + j < W) {
-            float* q = dst + (size_t)n * W + k0 + j;
-            *q = a.accumulate ? *q + v[j] : v[j];
-          }
-      }
+      for (int j = 0; j < 16; ++j) tbuf[n * 113 + k0 + j] = v[j];
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kWgLoaderWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" :: "r"(tmem) : "memory");
+  {
+    const int W = a.W;
+    float* const dst = a.part + (size_t)blockIdx.x * a.n_params_pad + a.w_off[layer];
+    for (int i = tid; i < W * W; i += kWgThreads) {
+      const int n = i / W, k = i - n * W;
+      const float v = tbuf[n * 113 + k];
+      dst[i] = a.accumulate ? dst[i] + v : v;
+    }
+  }
+  if (warp == kWgConvWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" :: "r"(tmem) : "memory");
 }
 
 cudaError_t launch_wgrad_gemm(const WgradArgs& a, int grid, cudaStream_t s) {
