@@ -380,7 +380,8 @@ static bool use_tcs(const tdb200_plan* p) {
   if (!p->tcs_eligible || p->impl == 1 || p->impl == 2) return false;
   if (p->impl == 3) return true;
   if (getenv("TDB200_AUTO_TCS")) return atoi(getenv("TDB200_AUTO_TCS")) != 0 && p->segs[0].n_groups >= 4096;
-  return !p->tc_eligible && p->segs[0].n_groups >= 4096;        // deeper nets: the only tensor-core path
+  if (!p->tc_eligible) return p->segs[0].n_groups >= 4096;      // deeper nets: the only tensor-core path
+  return p->segs[0].n_groups >= 200000;                         // 1-2 W x W layers: faster than the TMEM-dW kernel on long launches
 }
 static bool use_tc(const tdb200_plan* p) {
   if (!p->tc_eligible || p->impl == 1 || use_tcs(p)) return false;

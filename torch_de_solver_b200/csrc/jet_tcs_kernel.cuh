@@ -21,7 +21,7 @@
 namespace tdb {
 
 constexpr int kTsEpi = 512;                       // epilogue threads (16 warps: 4 lane windows x 4 column parts)
-constexpr int kTsThreads = kTsEpi + 64;           // + the MMA / weight-streaming warp + the operator warp
+constexpr int kTsThreads = kTsEpi + 96;           // + the MMA / weight-streaming warp + one operator warp per tile slot
 constexpr int kTsHalfFloats = 2 * kTcWBlock;      // one K half (2 k-blocks) of a hi or lo weight image
 constexpr int kSOffW = 0, kSOffAct = 2 * kTcWFloats, kSOffX = kSOffAct + 4 * kTcActFloats,
               kSOffU = kSOffX + 4 * kTcMaxPts * 4, kSOffGu = kSOffU + 2 * kTcMaxOut * kTcCols,      // U, Gu: per slot
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
   uint64_t* const op_done = bars + 10;         // [2] operator warp -> epilogue warps: adjoint seeds Gu of the slot are ready
   uint64_t* const up_free = bars + 12;         // operator warp -> epilogue warps: UP has been consumed
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool is_mma_warp = warp == kTsEpi / 32, is_op_warp = warp == kTsEpi / 32 + 1;
+  const bool is_mma_warp = warp == kTsEpi / 32, is_op_warp = warp == kTsEpi / 32 + 1 || warp == kTsEpi / 32 + 2;
 #ifdef TDB_TC_TIMING
   long long tacc[16];
 #pragma unroll
@@ -233,21 +233,26 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
 #endif
   } else if (is_op_warp) {
     // ===================================================================================================
-    // operator warp: last-layer sums -> u, operator terms, residual, loss, adjoint seeds (one lane per point)
+    // operator warps (one per tile slot): last-layer sums -> u, operator terms, residual, loss, adjoint seeds (one lane
+    // per point)
     // ===================================================================================================
     const bool fast_op = *fastS != 0;
     const tdb200_segment& sg = *segS;
     const int ncols = sg.n_cols;
+    const int slot = warp - (kTsEpi / 32 + 1);
     uint32_t req_ph = 0;
+    double lacc[TDB200_MAX_COLS];                          // per-lane loss sums (runtime column index: local memory)
+#pragma unroll
+    for (int c = 0; c < TDB200_MAX_COLS; ++c) lacc[c] = 0.0;
     for (int it = 0; it < iters; ++it) {
       const int nslots = (2 * it + 1 < my_tiles) ? 2 : 1;
-      for (int slot = 0; slot < nslots; ++slot) {
+      if (slot < nslots) {
         const int tile = tile_of(it, slot);
         const long long g_first = (long long)tile * P;
         const int p_valid = (int)min((long long)P, sg.n_groups - g_first);
         float* const Us = sbase + kSOffU + slot * kTcMaxOut * kTcCols;
         float* const Gus = sbase + kSOffGu + slot * kTcMaxOut * kTcCols;
-        mbar_wait(op_req + slot, (req_ph >> slot) & 1); req_ph ^= 1u << slot;
+        mbar_wait(op_req + slot, req_ph); req_ph ^= 1;
         for (int idx = lane; idx < n_out * kTcCols; idx += 32) {
           const int v = idx / kTcCols, r = idx - v * kTcCols;
           const int jc = r & (kTcPC - 1);
@@ -281,7 +286,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
           const float tgt = sg.tgt_off >= 0 ? __ldg(a.targets + sg.tgt_off + row * ncols + col) : 0.f;
           const float res = val - tgt;
           const float rw = a.row_weight ? __ldg(a.row_weight + row) : 1.f;        // causal-loss weight (no grad)
-          lossT[p * TDB200_MAX_COLS + col] += (double)rw * (double)res * (double)res;
+          lacc[col] += (double)rw * (double)res * (double)res;
           if (!a.do_grad) continue;
           const float seed = a.field_seed ? __ldg(a.field_seed + sg.field_off + row * ncols + col)
                                           : 2.f * scaleS[sg.col_slot[col]] * rw * res;
@@ -316,7 +321,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
           const float tgt = sg.tgt_off >= 0 ? __ldg(a.targets + sg.tgt_off + row * ncols + col) : 0.f;
           const float res = val - tgt;
           const float rw = a.row_weight ? __ldg(a.row_weight + row) : 1.f;
-          lossT[p * TDB200_MAX_COLS + col] += (double)rw * (double)res * (double)res;
+          lacc[col] += (double)rw * (double)res * (double)res;
           if (!a.do_grad) continue;
           const float seed = a.field_seed ? __ldg(a.field_seed + sg.field_off + row * ncols + col)
                                           : 2.f * scaleS[sg.col_slot[col]] * rw * res;
@@ -345,6 +350,12 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
         if (lane == 0) mbar_arrive(op_done + slot);
       }
     }
+    if (slot == 0)
+      for (int c = 0; c < ncols; ++c) lossT[lane * TDB200_MAX_COLS + c] = lacc[c];
+    __syncwarp();
+    asm volatile("bar.sync 2, 64;" ::: "memory");         // the two operator warps: slot 0 stores, then slot 1 adds
+    if (slot == 1)
+      for (int c = 0; c < ncols; ++c) lossT[lane * TDB200_MAX_COLS + c] += lacc[c];
   } else {
     // ===================================================================================================
     // epilogue warps
@@ -445,13 +456,15 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
       for (int j = C; j < 16; ++j) gz[j] = 0.f;
       return db;
     };
-    auto store_act = [&](int slot, const float* v) {      // 16 columns -> MN-major operand image (hi / lo) of the slot
-      float hi[16], lo[16];
+    auto store_act = [&](int slot, const float* v) {      // used columns (Q float4) -> MN-major operand image (hi / lo) of the slot
+      float hi[16], lo[16];                               // (the pad columns of the images stay zero from the set-up)
       split16(v, hi, lo);
       float* const ah = sbase + kSOffAct + slot * 2 * kTcActFloats;
       float* const al = ah + kTcActFloats;
-      st4(ah + actA, hi); st4(ah + actA + 4, hi + 4); st4(ah + actB, hi + 8); st4(ah + actB + 4, hi + 12);
-      st4(al + actA, lo); st4(al + actA + 4, lo + 4); st4(al + actB, lo + 8); st4(al + actB + 4, lo + 12);
+      st4(ah + actA, hi); st4(al + actA, lo);
+      if (Q > 1) { st4(ah + actA + 4, hi + 4); st4(al + actA + 4, lo + 4); }
+      if (Q > 2) { st4(ah + actB, hi + 8); st4(al + actB, lo + 8); }
+      if (Q > 3) { st4(ah + actB + 4, hi + 12); st4(al + actB + 4, lo + 12); }
     };
     // this thread's columns -> stream array of one layer: float4 q of (tile, part) at [((tile * 4 + part) * Q + q) * Wp + n],
     // i.e. every warp store writes 512 contiguous bytes.  Which (point, channel) row a column is does not matter to the
