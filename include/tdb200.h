@@ -207,6 +207,20 @@ int tdb200_mat_time_stencil(tdb200_mat_plan* plan, const float* u_dev, float* gr
                             void* stream);
 void tdb200_mat_plan_destroy(tdb200_mat_plan* plan);
 
+/* ---- fused optimiser step --------------------------------------------------------------------------
+ * Replaces optimizer.step() of torch.optim.Adam / AdamW / SGD as tedeous/optimizers/optimizer.py:44-61 configures them
+ * (tedeous/model.py:174-191 drives it): one launch updates all `n_tensors` parameter tensors (device pointers, sizes in
+ * floats) in place from the flat gradient `grad_dev` (the gradient part of tdb200_loss_grad's output vector, or the
+ * gradient of tdb200_mat_loss_grad), plus a one-thread launch that advances the step counter - a fixed sequence that can
+ * follow tdb200_loss_grad inside one CUDA graph.  kind: 0 Adam (weight decay added to the gradient), 1 AdamW (decoupled),
+ * 2 SGD with momentum.  hyper_dev = [lr, beta1 (SGD: momentum), beta2, eps, weight_decay] and step_dev (steps taken so
+ * far) live in device memory so that schedulers can change lr between replays; m_dev / v_dev: n floats each (SGD: m_dev
+ * is the momentum buffer, v_dev unused).  Same arithmetic as torch's single-tensor implementation. */
+#define TDB200_OPT_MAX_TENSORS 40
+int tdb200_optimizer_step(int32_t kind, int32_t n_tensors, float* const* params_dev, const int64_t* sizes,
+                          const float* grad_dev, float* m_dev, float* v_dev, const float* hyper_dev, int32_t* step_dev,
+                          void* stream);
+
 const char* tdb200_last_error(void);
 int tdb200_version(void);
 

@@ -59,6 +59,16 @@ def run_case(name, dtype):
                                      f'{os.environ.get("PYTHONHASHSEED")}; pick another seed')
     sol = Solution(grid, eq_cls, model, prob.mode, kw.get('weak_form'), kw['lambda_operator'], kw['lambda_bound'],
                    tol=kw.get('tol', 0), derivative_points=kw.get('derivative_points', 2))
+    if prob.train_steps:
+        # trained-ish state: the reference's own step (closure.py:49-64) under torch.optim.Adam, lr 1e-3
+        opt = torch.optim.Adam(params, lr=1e-3)
+        for _ in range(prob.train_steps):
+            opt.zero_grad()
+            loss_t, _ = sol.evaluate()
+            loss_t.backward()
+            opt.step()
+        opt.zero_grad()
+        weights = torch.cat([p.detach().reshape(-1) for p in params]).double().numpy()
     if kw.get('tol', 0) != 0 and dtype == 'float64':
         # The reference's causal loss cannot run in fp64 as shipped: losses.py:176-180 multiplies an fp32
         # lambda_prepare(bval, 1) into the fp64 bval_diff ("expected scalar type Float but found Double").
@@ -92,7 +102,7 @@ def main():
     solver_device('cpu')
     names = sys.argv[1:] or list(problems.ZOO)
     for name in names:
-        for dtype in ('float32', 'float64'):
+        for dtype in (('float64',) if name in problems.LARGE else ('float32', 'float64')):
             out = run_case(name, dtype)
             path = os.path.join(HERE, f'{name}.{dtype}.npz')
             np.savez_compressed(path, **out)

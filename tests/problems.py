@@ -24,6 +24,7 @@ class Problem:
     compile_kwargs: Dict = field(default_factory=dict)
     init: str = 'default'            # 'default' (Kaiming-uniform) | 'xavier'
     mat_shape: tuple = ()
+    train_steps: int = 0             # fixture state: weights after this many reference Adam steps (lr 1e-3)
 
 
 def make_net(layers: List[int], dtype=torch.float32, init='default', seed=0) -> torch.nn.Sequential:
@@ -379,7 +380,49 @@ def wave_weak(api, dtype='float32', n=16):
     return prob
 
 
+# --- Robin conditions (examples/examples_poisson/example_poisson_2d_many_subdomains.py:46-75) ----------------
+def poisson_robin(api, dtype='float32', n=20, layers=(2, 32, 32, 1)):
+    """u_xx + u_yy = f on the unit square; u -/+ du/dn = g on the four edges as `robin` conditions (alpha * u +
+    beta * bop, the reference's quirk q5 included: tedeous/eval.py:357-388), autograd mode."""
+    dom = api.Domain()
+    dom.variable('x', [0, 1], n, dtype=dtype)
+    dom.variable('y', [0, 1], n, dtype=dtype)
+
+    def bop(func_coeff, deriv_coeff, axis):
+        return {'u': {'coeff': func_coeff, 'term': [None], 'pow': 1},
+                'du/dn': {'coeff': deriv_coeff, 'term': [axis], 'pow': 1}}
+    bc = api.Conditions()
+    bc.robin({'x': 0, 'y': [0, 1]}, operator=bop(1, -1, 0), value=lambda g: -g[:, 1])
+    bc.robin({'x': 1, 'y': [0, 1]}, operator=bop(1, 1, 0), value=lambda g: -g[:, 1])
+    bc.robin({'x': [0, 1], 'y': 0}, operator=bop(2, -0.5, 1), value=lambda g: torch.sin(g[:, 0]))
+    bc.robin({'x': [0, 1], 'y': 1}, operator=bop(1, 1, 1), value=0.25)
+    eq = api.Equation()
+    eq.add({
+        'd2u/dx2': {'coeff': 1, 'term': [0, 0], 'pow': 1},
+        'd2u/dy2': {'coeff': 1, 'term': [1, 1], 'pow': 1},
+        '-f': {'coeff': lambda g: -torch.sin(np.pi * g[:, 0]) * torch.cos(np.pi * g[:, 1]), 'term': [None], 'pow': 0},
+    })
+    return Problem('poisson_robin_autograd', dom, bc, eq, 'autograd', list(layers), dict(lambda_operator=1, lambda_bound=10),
+                   init='xavier_b')
+
+
+def trained(prob: Problem, steps: int) -> Problem:
+    prob.train_steps = steps
+    return prob
+
+
+# fixtures too large for the every-fixture CPU oracle sweep (tests/test_oracle_golden.py checks them in fp64 only)
+LARGE = ('wave_autograd_1e5', 'kdv_autograd_1e5', 'wave_autograd_3e5')
+
 ZOO: Dict[str, Callable] = {
+    'poisson_robin_autograd': lambda api, dt: poisson_robin(api, dt),
+    # ~10^5 points: the sizes at which the tensor-core kernels are chosen automatically (impl = 0)
+    'wave_autograd_1e5': lambda api, dt: wave(api, dt, n=315, mode='autograd'),
+    'kdv_autograd_1e5': lambda api, dt: kdv(api, dt, nx=399, nt=249, mode='autograd'),
+    'wave_autograd_3e5': lambda api, dt: wave(api, dt, n=547, mode='autograd'),
+    # trained-ish states: 200 Adam steps of the reference (residual cancellation is worst near convergence, SURVEY 8d)
+    'burgers_autograd_trained': lambda api, dt: trained(burgers(api, dt, n=40, mode='autograd'), 200),
+    'wave_autograd_trained': lambda api, dt: trained(wave(api, dt, n=40, mode='autograd'), 200),
     'lotka_weak_NN': lambda api, dt: lotka_weak(api, dt, mode='NN'),
     'lotka_weak_autograd': lambda api, dt: lotka_weak(api, dt, mode='autograd'),
     'wave_weak_autograd': lambda api, dt: wave_weak(api, dt),

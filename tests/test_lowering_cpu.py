@@ -136,3 +136,19 @@ def test_vectorised_integration_equals_the_reference_loop(d):
     else:
         np.testing.assert_allclose(got.numpy(), np.array([float(x) for x in want]), rtol=1e-12, atol=1e-15)
         assert torch.equal(ggrid, wgrid)
+
+
+def test_scheme_choose_equals_reference_table():
+    """Finite_diffs.scheme_choose against the committed output of the unmodified reference
+    (tests/golden/make_fd_table.py -> finite_diffs_table.json; tedeous/finite_diffs.py:244-268): identical shift
+    lists in the same order, weights equal to the last bit."""
+    import json
+    import os
+    from torch_de_solver_b200.finite_diffs import Finite_diffs
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'finite_diffs_table.json')
+    table = json.load(open(path))
+    assert len(table) > 1000
+    for c in table:
+        got = Finite_diffs(c['term'], c['nvars'], c['type']).scheme_choose(c['order'], h=c['h'])
+        assert got[0] == c['scheme'], c
+        assert got[1] == c['sign'], c

@@ -25,7 +25,7 @@ def test_oracle_matches_reference_fp64(name):
     assert np.linalg.norm(grad - g['grad']) <= 1e-9 * np.linalg.norm(g['grad'])
 
 
-@pytest.mark.parametrize('name', CASES)
+@pytest.mark.parametrize('name', [c for c in CASES if c not in problems.LARGE])
 def test_oracle_matches_reference_fp32(name):
     g = load_golden(name, 'float32')
     sol, loss, loss_n, grad = oracle_eval(name, 'float32', g['weights'])

@@ -35,7 +35,7 @@ EXPORTS = [
     'tdb200_mat_plan_create', 'tdb200_mat_plan_set_coeffs', 'tdb200_mat_plan_set_bcs', 'tdb200_mat_loss_grad', 'tdb200_mat_eval_fields',
     'tdb200_mat_plan_out_size', 'tdb200_mat_plan_launches_per_call', 'tdb200_mat_plan_kernel_kind', 'tdb200_mat_plan_set_row_window',
     'tdb200_mat_plan_set_timing', 'tdb200_mat_plan_stencil_ms', 'tdb200_mat_time_stencil',
-    'tdb200_mat_plan_destroy',
+    'tdb200_mat_plan_destroy', 'tdb200_optimizer_step',
     'tdb200_last_error', 'tdb200_version',
 ]
 
@@ -82,6 +82,7 @@ def load():
     lib.tdb200_mat_eval_fields.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.tdb200_mat_plan_destroy.argtypes = [vp]
     lib.tdb200_mat_plan_destroy.restype = None
+    lib.tdb200_optimizer_step.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     _lib = lib
     return lib
 

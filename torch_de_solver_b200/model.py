@@ -69,6 +69,24 @@ class Model:
                                      lambda_bound, tol, derivative_points, batch_size=self.batch_size,
                                      **fused_options)
 
+    def _fused_train_step(self, optimizer: Optimizer, mixed_precision: bool):
+        """The graph-captured training step (optimizers/fused.py) when the optimiser and the loss allow it: Adam / AdamW /
+        SGD without cosine restarts, default loss (no causal weights, no weak form).  TDB200_EAGER_TRAIN=1 keeps the eager
+        loop (torch optimiser + closure), which is also what every other configuration uses."""
+        import os
+        from .optimizers.fused import FusedOptimizer, TrainStep, _KIND
+        sol = self.solution_cls
+        if (optimizer.optimizer not in _KIND or mixed_precision or optimizer.cosine_scheduler_patience is not None
+                or sol.tol != 0 or sol.weak_form not in (None, []) or os.environ.get('TDB200_EAGER_TRAIN')
+                or getattr(sol, '_callable_coeffs', 'once') != 'once'):
+            return None
+        params = [sol.model] if sol.mode == 'mat' else sol._ir.net.param_tensors()
+        try:
+            opt = FusedOptimizer(optimizer.optimizer, params, **optimizer.params)
+            return TrainStep(sol, opt)
+        except (NotImplementedError, ValueError):
+            return None
+
     def train(self, optimizer: Optimizer, epochs: int, info_string_every: Union[int, None] = None,
               mixed_precision: bool = False, save_model: bool = False, model_name: Union[str, None] = None,
               callbacks: Union[List, None] = None):
@@ -82,7 +100,22 @@ class Model:
         self.min_loss, _ = self.solution_cls.evaluate()
         self.cur_loss = self.min_loss
         print('[{}] initial (min) loss is {}'.format(datetime.datetime.now(), self.min_loss.item()))
-        while self.t < epochs and self.stop_training is False:
+        fused = self._fused_train_step(optimizer, mixed_precision)
+        lr0, decays = (fused.opt.lr, 0) if fused is not None else (None, 0)
+        while fused is not None and self.t < epochs and self.stop_training is False:
+            # one CUDA-graph replay per epoch: pack -> kernels -> reduce -> [all-reduce] -> parameter update; the loss
+            # stays on the device (callbacks that read model.cur_loss synchronise, as they do in the reference)
+            callbacks.on_epoch_begin()
+            out = fused.step()
+            self.cur_loss = out[1:2] if self.normalized_loss_stop else out[0:1]
+            self.solution_cls.loss, self.solution_cls.loss_normalized = out[0:1], out[1:2]
+            self.solution_cls._last_out = out
+            if optimizer.gamma is not None and self.t % optimizer.decay_every == 0:
+                decays += 1
+                fused.opt.set_lr(lr0 * optimizer.gamma ** decays)
+            callbacks.on_epoch_end()
+            self.t += 1
+        while fused is None and self.t < epochs and self.stop_training is False:
             callbacks.on_epoch_begin()
             self.optimizer.zero_grad()
             self.optimizer.step(closure)

@@ -134,6 +134,24 @@ class FactorIR:
 class TermIR:
     coeff: object                # float | torch.Tensor (per row) | nn.Parameter
     factors: List[FactorIR]
+    coeff_fn: object = None      # (callable, rows) the per-row buffer was evaluated from (refresh_coeffs)
+    coeff_slice: object = None   # (lo, hi) rows kept by this rank
+
+
+def _check_coeff_callable(fn, label):
+    """A callable coefficient is evaluated into a buffer (at lowering, and again by `refresh_coeffs`): no gradient can
+    flow into state it closes over.  The reference re-evaluates it inside the autograd graph on every step
+    (tedeous/derivative.py:41-42, 114-115), so a closure over trainable tensors would silently train differently."""
+    cells = [c.cell_contents for c in (getattr(fn, '__closure__', None) or ()) if c is not None]
+    cells += list(getattr(fn, '__defaults__', None) or ())
+    if getattr(fn, '__self__', None) is not None:
+        cells.append(fn.__self__)
+    for obj in cells:
+        trainable = (isinstance(obj, torch.Tensor) and obj.requires_grad) or \
+                    (isinstance(obj, torch.nn.Module) and any(p.requires_grad for p in obj.parameters()))
+        if trainable:
+            raise UnsupportedProblem(f'term {label!r}: the callable coefficient closes over trainable state; pass the '
+                                     f'trainable quantity as an nn.Parameter coefficient (parameter_registr) instead')
 
 
 def _pure_axes(spec) -> Tuple[int, ...]:
@@ -162,11 +180,14 @@ def parse_operator(op: dict, rows: torch.Tensor, coeff_rows: Optional[Callable] 
                                  # wraps it once more and the reference indexes model(grid)[:, [0]] with the list
             facs.append(FactorIR(int(var), _pure_axes(spec), float(pw)))
         coeff = term['coeff']
+        coeff_fn = None
         if isinstance(coeff, tuple):          # reference NN-prepared form (callable, grid)
             coeff = coeff[0]
         if isinstance(coeff, torch.nn.Parameter):
             pass
         elif callable(coeff):
+            _check_coeff_callable(coeff, label)
+            coeff_fn = (coeff, rows)
             coeff = coeff(rows).reshape(-1).detach()
         elif isinstance(coeff, torch.Tensor):
             coeff = coeff.reshape(-1).detach()
@@ -179,7 +200,7 @@ def parse_operator(op: dict, rows: torch.Tensor, coeff_rows: Optional[Callable] 
         if isinstance(coeff, torch.Tensor) and not isinstance(coeff, torch.nn.Parameter) \
                 and coeff.numel() != rows.shape[0]:
             raise ValueError(f'term {label!r}: coefficient has {coeff.numel()} entries for {rows.shape[0]} rows')
-        terms.append(TermIR(coeff, facs))
+        terms.append(TermIR(coeff, facs, coeff_fn))
     return terms
 
 
@@ -553,6 +574,7 @@ def _shard_segments(ir: ProblemIR, rank: int, world: int) -> None:
             for t in terms:
                 if isinstance(t.coeff, torch.Tensor) and not isinstance(t.coeff, torch.nn.Parameter):
                     t.coeff = t.coeff[lo:hi].contiguous()
+                    t.coeff_slice = (lo, hi)
         s.shard_range = (lo, hi)
 
 
@@ -570,6 +592,7 @@ class FlatIR:
     coeffs: torch.Tensor             # float32
     n_fields: int
     cparam_index: Dict[int, int]
+    coeff_fns: list = None           # [(offset, numel, callable, rows, (lo, hi) | None)]: buffers of callable coefficients
 
 
 def flatten(ir: ProblemIR, device) -> FlatIR:
@@ -577,6 +600,7 @@ def flatten(ir: ProblemIR, device) -> FlatIR:
     terms, factors, comb = [], [], []
     pts, tgts, coefs = [], [], []
     pts_off = tgt_off = coef_off = field_off = 0
+    coeff_fns = []
     cparam_index = {id(p): i for i, p in enumerate(ir.net.coeff_params)}
     for si, s in enumerate(ir.segments):
         r = seg[si]
@@ -617,6 +641,8 @@ def flatten(ir: ProblemIR, device) -> FlatIR:
                     terms.append((0.0, COEFF_PARAM, cparam_index[id(t.coeff)], fb, len(factors)))
                 elif isinstance(t.coeff, torch.Tensor):
                     terms.append((0.0, COEFF_BUFFER, coef_off, fb, len(factors)))
+                    if t.coeff_fn is not None:
+                        coeff_fns.append((coef_off, t.coeff.numel(), t.coeff_fn[0], t.coeff_fn[1], t.coeff_slice))
                     coefs.append(t.coeff.reshape(-1).to(device=device, dtype=torch.float32))
                     coef_off += t.coeff.numel()
                 else:
@@ -631,4 +657,4 @@ def flatten(ir: ProblemIR, device) -> FlatIR:
     return FlatIR(seg, np.array(terms, dtype=TERM_DTYPE) if terms else np.zeros(0, TERM_DTYPE),
                   np.array(factors, dtype=FACTOR_DTYPE) if factors else np.zeros(0, FACTOR_DTYPE),
                   np.concatenate(comb).astype(np.float32) if comb else np.zeros(1, np.float32),
-                  torch.cat(pts).contiguous(), cat(tgts), cat(coefs), field_off, cparam_index)
+                  torch.cat(pts).contiguous(), cat(tgts), cat(coefs), field_off, cparam_index, coeff_fns)

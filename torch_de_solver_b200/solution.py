@@ -97,6 +97,16 @@ class FusedPlan:
             _native.check(self.lib.tdb200_plan_set_field_seeds(self.handle, None), 'tdb200_plan_set_field_seeds')
         return out[self.out_size - self.n_params:]
 
+    def refresh_coeffs(self):
+        """Re-evaluates every callable coefficient into its per-row buffer (the reference calls coeff(grid) on every
+        step, tedeous/derivative.py:41-42, 114-115; here they are evaluated at lowering and on request)."""
+        with torch.no_grad():
+            for off, n, fn, rows, sl in self.flat.coeff_fns or ():
+                vals = fn(rows).reshape(-1).detach()
+                if sl is not None:
+                    vals = vals[sl[0]:sl[1]]
+                self.flat.coeffs[off:off + n].copy_(vals.to(self.flat.coeffs.dtype))
+
     def set_impl(self, impl: int):
         _native.check(self.lib.tdb200_plan_set_impl(self.handle, impl), 'tdb200_plan_set_impl')
         self.launches_per_call = int(self.lib.tdb200_plan_launches_per_call(self.handle))
@@ -232,7 +242,13 @@ class Solution:
     def __init__(self, grid: torch.Tensor, equal_cls, model, mode: str, weak_form, lambda_operator,
                  lambda_bound, tol: float = 0, derivative_points: int = 2, batch_size: int = None,
                  shard: Optional[Tuple[int, int]] = None, process_group=None, nn_interior: str = 'jet',
-                 impl: int = 0):
+                 impl: int = 0, callable_coeffs: str = 'once'):
+        """Extensions after `batch_size`: shard / process_group (multi-GPU), nn_interior ('jet' | 'literal'), impl (kernel
+        choice), callable_coeffs: 'once' - callable coefficients are evaluated at lowering (and by `refresh_coeffs()`),
+        'every_step' - re-evaluated by every `evaluate()` like the reference does."""
+        if callable_coeffs not in ('once', 'every_step'):
+            raise ValueError("callable_coeffs must be 'once' or 'every_step'")
+        self._callable_coeffs = callable_coeffs
         weak = weak_form not in (None, [])
         if weak and mode == 'mat':
             raise UnsupportedProblem('weak-form loss is implemented for modes NN / autograd only (SURVEY 8 a11)')
@@ -412,8 +428,15 @@ class Solution:
         self.lambda_bound = lambda_prepare(torch.empty(1, len(self.bval_keys)), self.lambda_bound).to(torch.float32)
         return self.loss, self.loss_normalized
 
+    def refresh_coeffs(self) -> None:
+        """Re-evaluate callable coefficients (modes NN / autograd) into the plan's buffers."""
+        if self.mode != 'mat':
+            self._plan.refresh_coeffs()
+
     def evaluate(self, save_graph: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
         """One loss evaluation (tedeous/solution.py:129-168)."""
+        if self._callable_coeffs == 'every_step':
+            self.refresh_coeffs()
         if self.weak_form not in (None, []):
             return self._evaluate_weak(save_graph)
         self._sync_lambdas()
