@@ -273,7 +273,7 @@ def measure_nn(ctx, workload, steps, warmup, with_cpu):
     graphed = False
     if n_local < 100_000 and not args.no_graph:          # launch-bound sizes: one CUDA graph per step
         try:
-            step_resident, _ = sol.capture_step()
+            step_resident, sol._graph_out = sol.capture_step()
             graphed = True
         except Exception as e:                # noqa: BLE001 - report and time eager launches
             sys.stderr.write(f'[bench] {workload}: CUDA graph capture failed ({e}); timing eager launches\n')
@@ -292,21 +292,33 @@ def measure_nn(ctx, workload, steps, warmup, with_cpu):
     value = n_global / (ms_per_step * 1e-3)
 
     # ---- end to end through the public API, host buffers ----------------------------------------------
+    # every step: the step's inputs (points, targets, coefficient buffers) from pinned host memory, the call a user
+    # makes, the result vector back to pinned host memory.  The call is `Solution.evaluate(); loss.backward()` - or,
+    # where the step is launch bound and captured, the replay of `Solution.capture_step()` (what Model.train replays,
+    # with the optimiser update behind it).
     flat = plan.flat
     host_in = [t.detach().cpu().pin_memory() for t in (flat.points, flat.targets, flat.coeffs)]
     dev_in = [flat.points, flat.targets, flat.coeffs]
     host_out = torch.empty(plan.out_size, dtype=torch.float32, device='cpu').pin_memory()
     h2d = sum(t.numel() * 4 for t in host_in)
     d2h = host_out.numel() * 4
+    if graphed:
+        replay, g_out = step_resident, sol._graph_out
 
-    def step_e2e():
-        for h, d in zip(host_in, dev_in):
-            d.copy_(h, non_blocking=True)
-        for p in params:
-            p.grad = None
-        loss, _ = sol.evaluate()
-        loss.backward()
-        host_out.copy_(sol._last_out, non_blocking=True)
+        def step_e2e():
+            for h, d in zip(host_in, dev_in):
+                d.copy_(h, non_blocking=True)
+            replay()
+            host_out.copy_(g_out, non_blocking=True)
+    else:
+        def step_e2e():
+            for h, d in zip(host_in, dev_in):
+                d.copy_(h, non_blocking=True)
+            for p in params:
+                p.grad = None
+            loss, _ = sol.evaluate()
+            loss.backward()
+            host_out.copy_(sol._last_out, non_blocking=True)
 
     for _ in range(3):
         step_e2e()
@@ -315,8 +327,20 @@ def measure_nn(ctx, workload, steps, warmup, with_cpu):
     e2e_ms = ctx.max_over_ranks(sum(ctx.timed(step_e2e, e2e_steps))) / e2e_steps
     ctx.barrier()
     e2e_value = n_global / (e2e_ms * 1e-3)
+    # the whole training step as Model.train replays it (loss + gradient + fused Adam update), for the record
+    train_ms = None
+    if graphed and world == 1:
+        try:
+            from torch_de_solver_b200.optimizers.fused import FusedOptimizer, TrainStep
+            ts = TrainStep(sol, FusedOptimizer('Adam', sol._ir.net.param_tensors(), lr=1e-5))
+            for _ in range(3):
+                ts.step()
+            train_ms = sum(ctx.timed(ts.step, e2e_steps)) / e2e_steps
+        except Exception as e:                # noqa: BLE001
+            sys.stderr.write(f'[bench] {workload}: training-step graph failed ({e})\n')
+    kernel_path = plan.kernel_path
     launches = plan.launches_per_call
-    tc = launches != 3
+    tc = not kernel_path.startswith('simt')
     del sol, model, plan
     torch.set_default_device('cpu')
     if rank != 0:
@@ -328,14 +352,15 @@ def measure_nn(ctx, workload, steps, warmup, with_cpu):
     cfg = common_config(workload, world)
     cfg.update({'points_per_gpu': n_local, 'points_total': n_global, 'mlp': list(prob.net_layers), 'mode': prob.mode,
                 'jet_channels': spec['J'],
-                'kernel': ('tcgen05-3xtf32 (interior) + simt-fp32 (boundary rows)' if tc else 'simt-fp32'),
+                'kernel': kernel_path + (' (interior, identity boundary rows) + simt-fp32 (other boundary rows)' if tc else ''),
                 'cuda_graph': graphed, 'l2': 'flushed between timed steps (256 MB write)',
                 'parallelism': f'dp{world} (points sharded, one all-reduce of [loss terms | gradient] per step)'})
     return {
         'value': value, 'unit': UNIT, 'ms_per_step': ms_per_step, 'steps': steps, 'warmup': max(warmup, 3),
         'dtype': 'tf32x3 (fp32 accumulate)' if tc else 'f32', 'config': cfg,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                'ms_per_step': e2e_ms},
+                'ms_per_step': e2e_ms, 'call': 'Solution.capture_step() replay' if graphed else
+                'Solution.evaluate(); loss.backward()', 'train_step_ms': train_ms},
         'gpu_launches': steps * launches, 'clocks': clocks,
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                      'frac': achieved / peak if peak else None,

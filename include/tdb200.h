@@ -108,13 +108,17 @@ int tdb200_plan_set_row_weights(tdb200_plan* plan, const float* weights_dev);
  * NULL switches back to the loss gradient. */
 int tdb200_plan_set_field_seeds(tdb200_plan* plan, const float* seeds_dev);
 
-/* Choose the kernel implementation: 0 = auto, 1 = SIMT fp32, 2 = tcgen05 3xTF32 (errors if unsupported). */
+/* Choose the kernel implementation: 0 = auto, 1 = SIMT fp32, 2 = tcgen05 3xTF32 with the weight gradients of 1-2 W x W
+ * layers in TMEM, 3 = streamed tcgen05 3xTF32 pair, any depth (2 / 3: error if the net / operator is not served). */
 int tdb200_plan_set_impl(tdb200_plan* plan, int32_t impl);
 
 /* Number of floats of the output vector of tdb200_loss_grad: 2 + n_slots + n_params. */
 int64_t tdb200_plan_out_size(const tdb200_plan* plan);
 int64_t tdb200_plan_n_params(const tdb200_plan* plan);
 int64_t tdb200_plan_n_fields(const tdb200_plan* plan);
+/* Which kernels serve the interior segment with the current impl setting: 1 = fp32 SIMT jet kernel, 2 = tcgen05 kernel
+ * with the weight gradients in TMEM (1-2 W x W layers), 3 = streamed tcgen05 pair (jet_tcs_kernel + wgrad_gemm_kernel). */
+int32_t tdb200_plan_kernel_path(const tdb200_plan* plan);
 /* Kernel launches one tdb200_loss_grad call enqueues. */
 int32_t tdb200_plan_launches_per_call(const tdb200_plan* plan);
 

@@ -414,6 +414,10 @@ static int ensure_tcs_buffers(tdb200_plan* p) {
   if ((rc = upload<float>(&p->tcs_zsave, nullptr, (size_t)p->n_sms * 2 * NM * 512 * 16))) return rc;
   return TDB200_OK;
 }
+int32_t tdb200_plan_kernel_path(const tdb200_plan* p) {
+  if (!p) return 0;
+  return use_tcs(p) ? 3 : use_tc(p) ? 2 : 1;
+}
 int32_t tdb200_plan_launches_per_call(const tdb200_plan* p) {
   if (!p) return 0;
   if (use_tcs(p)) return 3 + 2 * tcs_chunks(p) + 2 * (int)p->tcs_extra.size() + (p->simt_rest_all_tiles > 0 ? 1 : 0);

@@ -107,6 +107,12 @@ class FusedPlan:
                     vals = vals[sl[0]:sl[1]]
                 self.flat.coeffs[off:off + n].copy_(vals.to(self.flat.coeffs.dtype))
 
+    @property
+    def kernel_path(self) -> str:
+        """Kernels serving the interior segment under the current impl setting."""
+        return {1: 'simt-fp32', 2: 'tcgen05-3xtf32 (dW in TMEM)', 3: 'tcgen05-3xtf32 streamed (jet_tcs + wgrad_gemm)'}[
+            int(self.lib.tdb200_plan_kernel_path(self.handle))]
+
     def set_impl(self, impl: int):
         _native.check(self.lib.tdb200_plan_set_impl(self.handle, impl), 'tdb200_plan_set_impl')
         self.launches_per_call = int(self.lib.tdb200_plan_launches_per_call(self.handle))
