@@ -51,7 +51,7 @@ int jet_tc_points_per_tile(int o0, int o1, int o2) {
 int jet_tc_columns_per_part(int o0, int o1, int o2) {
   return jet_tc_points_per_tile(o0, o1, o2) / kTcParts * (1 + o0 + o1 + o2);
 }
-int jet_tc_partial_rows() { return kTcParts; }
+int jet_tc_partial_rows() { return 1; }
 int jet_tc_max_out() { return kTcMaxOut; }
 
 TDB_TC_DEFINE_GROUP(launch_jet_tc_g0, TDB_TC_SIGS_G0)

@@ -357,8 +357,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
   const int ksteps = (W + 7) / 8;
   const bool live = n < W;
   const int col0 = part * kTcPC;                        // first (point, channel) column of this thread
-  // one gradient-partial row per column part: a single owner thread per address -> bit-reproducible
-  float* const my_grad = a.part_grad + ((size_t)blockIdx.x * kTcParts + part) * a.n_params_pad;
+  // one gradient-partial row per CTA: the four column parts are added up in shared memory in a fixed order at the end
+  // (a single owner thread per address -> bit-reproducible; the reduction kernel reads 4x fewer rows)
+  float* const my_grad = a.part_grad + (size_t)blockIdx.x * a.n_params_pad;
   // where this thread's 16 columns live in the operand images (floats)
   const int actA = (part >> 1) * kTcActBlock + n * 32 + ((((part & 1) * 2) ^ (n & 3)) << 3);       // columns 0..7
   const int actB = (part >> 1) * kTcActBlock + n * 32 + ((((part & 1) * 2 + 1) ^ (n & 3)) << 3);   // columns 8..15
@@ -367,8 +368,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
   for (int q = 0; q < 4; ++q) ywq[q] = (part >> 1) * kTcYwBlock + n * 32 + ((((part & 1) * 4 + q) ^ (n & 7)) << 2);
 
   // ---- one-time setup --------------------------------------------------------------------------------
-  for (int i = tid; i < kTcParts * a.n_params_pad; i += kTcThreads)
-    a.part_grad[(size_t)blockIdx.x * kTcParts * a.n_params_pad + i] = 0.f;
+  for (int i = tid; i < a.n_params_pad; i += kTcThreads) a.part_grad[(size_t)blockIdx.x * a.n_params_pad + i] = 0.f;
   for (int i = tid; i < 2 * kTcActFloats + 2 * kTcYwFloats; i += kTcThreads) (sbase + kOffActHi)[i] = 0.f;   // pad rows / columns stay zero
   if (tid < kMaxCParams) (sbase + kOffCg)[tid] = 0.f;
   for (int i = tid; i < 2 * kTcMaxPts * 4; i += kTcThreads) (sbase + kOffX)[i] = 0.f;      // axes >= d stay zero
@@ -831,18 +831,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
   __syncthreads();
   tc_fence_after();
   if (a.do_grad) {
-    if (live) {
+    // per-thread accumulators of the four column parts -> staging in the (now free) weight buffer -> part 0 adds them up
+    float* const stg = sbase + kOffWHi;                   // [4 parts][NMMA + 1 + 4 + kTcMaxOut][128]
+    constexpr int kRowsStg = NMMA + 1 + 4 + kTcMaxOut;
+    for (int i = 0; i < ND; ++i)                         // derivative-channel part of dW0, by jet direction
+      for (int ax = 0; ax < 4; ++ax) if (ax == dir_axis[i]) dw0_acc[ax] += dw0_dir[i];
+    {
+      float* mine = stg + (part * kRowsStg) * 128 + n;
 #pragma unroll
-      for (int l = 0; l <= NMMA; ++l) my_grad[a.b_off[l] + n] = db_acc[l];
-      for (int i = 0; i < ND; ++i)                         // derivative-channel part of dW0, by jet direction
-        for (int ax = 0; ax < 4; ++ax) if (ax == dir_axis[i]) dw0_acc[ax] += dw0_dir[i];
-      for (int ax = 0; ax < d; ++ax) my_grad[a.w_off[0] + n * d + ax] = dw0_acc[ax];
+      for (int l = 0; l <= NMMA; ++l) mine[l * 128] = db_acc[l];
 #pragma unroll
-      for (int v = 0; v < kTcMaxOut; ++v) if (v < n_out) my_grad[a.w_off[L - 1] + v * W + n] = dwl_acc[v];
+      for (int ax = 0; ax < 4; ++ax) mine[(NMMA + 1 + ax) * 128] = dw0_acc[ax];
+#pragma unroll
+      for (int v = 0; v < kTcMaxOut; ++v) mine[(NMMA + 5 + v) * 128] = dwl_acc[v];
     }
-    if (tid < n_out) my_grad[a.b_off[L - 1] + tid] = dbl_acc;     // warp 0 -> part-0 row
+    __syncthreads();
+    if (live && part == 0) {
+      auto total = [&](int r) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < kTcParts; ++q) t += stg[(q * kRowsStg + r) * 128 + n];
+        return t;
+      };
+#pragma unroll
+      for (int l = 0; l <= NMMA; ++l) my_grad[a.b_off[l] + n] = total(l);
+      for (int ax = 0; ax < d; ++ax) my_grad[a.w_off[0] + n * d + ax] = total(NMMA + 1 + ax);
+#pragma unroll
+      for (int v = 0; v < kTcMaxOut; ++v) if (v < n_out) my_grad[a.w_off[L - 1] + v * W + n] = total(NMMA + 5 + v);
+    }
+    if (tid < n_out) my_grad[a.b_off[L - 1] + tid] = dbl_acc;
     if (dw_started) {
-      float* row0 = a.part_grad + (size_t)blockIdx.x * kTcParts * a.n_params_pad;   // dW lives in the part-0 row
+      float* row0 = my_grad;
       for (int t = 1; t <= NMMA; ++t) {
         float* dst = row0 + a.w_off[t];
         for (int k0 = part * 32; k0 < part * 32 + 32 && k0 < (int)kTmDwCols; k0 += 16) {

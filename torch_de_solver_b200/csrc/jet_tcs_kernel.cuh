@@ -129,12 +129,11 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
   const int iters = (my_tiles + 1) / 2;
   const int n_kinds = a.do_grad ? 2 * NM : NM;
   auto tile_of = [&](int it, int slot) { return x.tile0 + (int)blockIdx.x + (2 * it + slot) * G; };
-  float* const my_grad = a.part_grad + ((size_t)blockIdx.x * kTcParts + part) * a.n_params_pad;
+  float* const my_grad = a.part_grad + (size_t)blockIdx.x * a.n_params_pad;    // one partial row per CTA
 
   // ---- one-time setup --------------------------------------------------------------------------------
   if (x.zero_partials)
-    for (int i = tid; i < kTcParts * a.n_params_pad; i += kTsThreads)
-      a.part_grad[(size_t)blockIdx.x * kTcParts * a.n_params_pad + i] = 0.f;
+    for (int i = tid; i < a.n_params_pad; i += kTsThreads) a.part_grad[(size_t)blockIdx.x * a.n_params_pad + i] = 0.f;
   for (int i = tid; i < 4 * kTcActFloats; i += kTsThreads) (sbase + kSOffAct)[i] = 0.f;    // pad rows / columns stay zero
   if (tid < kMaxCParams) (sbase + kSOffCg)[tid] = 0.f;
   for (int i = tid; i < 4 * kTcMaxPts * 4; i += kTsThreads) (sbase + kSOffX)[i] = 0.f;     // axes >= d stay zero
@@ -655,19 +654,33 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
     if (a.dbg && tid == 0)
       for (int i = 0; i < 12; ++i) a.dbg[(size_t)blockIdx.x * 16 + i] = tacc[i];
 #endif
-    // ---- flush: per-thread accumulators ----------------------------------------------------------------------
-    const bool acc = !x.zero_partials;
-    auto put = [&](float* q, float v) { *q = acc ? *q + v : v; };
+    // ---- flush: per-thread accumulators of the four column parts -> staging in the (now free) weight buffer; part 0
+    // adds them up in a fixed order into the CTA's partial row ----------------------------------------------------
     if (a.do_grad) {
-      if (live) {
-        for (int l = 0; l <= NM; ++l) put(my_grad + a.b_off[l] + n, db_acc[l]);
-        for (int i = 0; i < ND; ++i)
-          for (int ax = 0; ax < 4; ++ax) if (ax == dir_axis[i]) dw0_acc[ax] += dw0_dir[i];
-        for (int ax = 0; ax < d; ++ax) put(my_grad + a.w_off[0] + n * d + ax, dw0_acc[ax]);
+      float* const stg = sbase + kSOffW;                  // [4 parts][NM + 1 + 4 + kTcMaxOut][128]
+      const int rows_stg = NM + 1 + 4 + kTcMaxOut;
+      for (int i = 0; i < ND; ++i)
+        for (int ax = 0; ax < 4; ++ax) if (ax == dir_axis[i]) dw0_acc[ax] += dw0_dir[i];
+      float* mine = stg + (part * rows_stg) * 128 + n;
+      for (int l = 0; l <= NM; ++l) mine[l * 128] = db_acc[l];
 #pragma unroll
-        for (int v = 0; v < kTcMaxOut; ++v) if (v < n_out) put(my_grad + a.w_off[L - 1] + v * W + n, dwl_acc[v]);
+      for (int ax = 0; ax < 4; ++ax) mine[(NM + 1 + ax) * 128] = dw0_acc[ax];
+#pragma unroll
+      for (int v = 0; v < kTcMaxOut; ++v) mine[(NM + 5 + v) * 128] = dwl_acc[v];
+      epi_sync();
+      const bool acc = !x.zero_partials;
+      auto put = [&](float* q, int r) {
+        float t = 0.f;
+#pragma unroll
+        for (int qq = 0; qq < kTcParts; ++qq) t += stg[(qq * rows_stg + r) * 128 + n];
+        *q = acc ? *q + t : t;
+      };
+      if (live && part == 0) {
+        for (int l = 0; l <= NM; ++l) put(my_grad + a.b_off[l] + n, l);
+        for (int ax = 0; ax < d; ++ax) put(my_grad + a.w_off[0] + n * d + ax, NM + 1 + ax);
+        for (int v = 0; v < n_out; ++v) put(my_grad + a.w_off[L - 1] + v * W + n, NM + 5 + v);
       }
-      if (tid < n_out) put(my_grad + a.b_off[L - 1] + tid, dbl_acc);     // warp 0 -> part-0 row
+      if (tid < n_out) { float* q = my_grad + a.b_off[L - 1] + tid; *q = acc ? *q + dbl_acc : dbl_acc; }
     }
   }
   tc_fence_before();
@@ -677,7 +690,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
     const bool acc = !x.zero_partials;
     const tdb200_segment& sg = *segS;
     if (a.do_grad && tid < a.n_cparams) {
-      float* q = a.part_grad + (size_t)blockIdx.x * kTcParts * a.n_params_pad + a.n_net_params + tid;
+      float* q = my_grad + a.n_net_params + tid;
       *q = acc ? *q + (sbase + kSOffCg)[tid] : (sbase + kSOffCg)[tid];
     }
     if (tid < a.n_slots) {
