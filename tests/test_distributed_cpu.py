@@ -192,3 +192,31 @@ def _causal_aligned_worker(rank, world, port, out_path):
             np.savez(out_path, w=part.numpy(), loss_op=loss_part.numpy())
     finally:
         dist.destroy_process_group()
+
+
+def test_sharded_mat_refuses_boundary_operator_across_slab_interface():
+    """A boundary operator that differentiates along the sharded axis next to a slab interface would lose the part of
+    its adjoint that falls into the neighbour's rows (round-1 advisor finding): such problems raise instead of training
+    on a wrong gradient; the same operator at the domain edge (or on one rank) lowers fine."""
+    import torch_de_solver_b200 as tdb
+    from torch_de_solver_b200.input_preprocessing import Operator_bcond_preproc
+    from torch_de_solver_b200.mat import MatIR
+    from torch_de_solver_b200.plan import UnsupportedProblem
+
+    def lower(bnd, shard):
+        dom = tdb.Domain()
+        dom.variable('x', [0, 1], 16, dtype='float64')
+        dom.variable('t', [0, 1], 16, dtype='float64')
+        bc = tdb.Conditions()
+        bc.dirichlet({'x': 0, 't': [0, 1]}, value=0.)
+        bc.operator(bnd, operator={'du/dx': {'coeff': 1, 'term': [0], 'pow': 1}}, value=0.)
+        eq = tdb.Equation()
+        eq.add({'du/dt': {'coeff': 1, 'term': [1], 'pow': 1}, '-d2u/dx2': {'coeff': -1, 'term': [0, 0], 'pow': 1}})
+        grid = dom.build('mat')
+        e = Operator_bcond_preproc(grid, eq.equation_lst, bc.build(dom.variable_dict)).set_strategy('mat')
+        return MatIR(grid, e.operator_prepare(), e.bnd_prepare(), 1, 'cpu', 1, 10, 2, shard)
+
+    lower({'x': [0, 1], 't': 0}, (0, 1))                       # one rank: fine
+    lower({'x': 1, 't': [0, 1]}, (1, 2))                       # the operator rows sit at the domain edge: fine
+    with pytest.raises(UnsupportedProblem, match='slab interface'):
+        lower({'x': [0, 1], 't': 0}, (0, 2))

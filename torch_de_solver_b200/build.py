@@ -28,10 +28,29 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Builds under an exclusive file lock (one process per GPU under torchrun: every rank calls this at import) into a
+    private object directory and moves the finished library into place atomically, so no rank can dlopen a half-written
+    file.  A prebuilt library is used as it is when nvcc is not available (GPU boxes receive the built .so)."""
     if not force and not needs_build():
         return LIB
-    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    nvcc = shutil.which('nvcc') or ('/usr/local/cuda/bin/nvcc' if os.path.exists('/usr/local/cuda/bin/nvcc') else None)
+    if nvcc is None:
+        if os.path.exists(LIB):
+            return LIB                                 # sources look newer (fresh checkout) but there is no compiler here
+        raise RuntimeError('libtedeous_b200.so is not built and nvcc was not found')
     os.makedirs(LIB_DIR, exist_ok=True)
+    import fcntl
+    with open(os.path.join(LIB_DIR, '.lock'), 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():        # another rank built it while this one waited
+                return LIB
+            return _build_locked(nvcc, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(nvcc, verbose):
     def compile_one(src):
         obj = os.path.join(LIB_DIR, os.path.basename(src)[:-3] + '.o')
         extra = ['-DTDB_TC_TIMING'] if os.environ.get('TDB200_TC_TIMING_BUILD') else []
@@ -49,11 +68,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(max_workers=8) as ex:      # one nvcc process per translation unit
         objs = list(ex.map(compile_one, sources()))
-    cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-cudart', 'static']
+    tmp = LIB + f'.tmp{os.getpid()}'
+    cmd = [nvcc, '-shared', '-o', tmp] + objs + ['-cudart', 'static']
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError('link failed')
+    os.replace(tmp, LIB)
     return LIB
 
 

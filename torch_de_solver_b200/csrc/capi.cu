@@ -344,6 +344,10 @@ int tdb200_plan_set_slots(tdb200_plan* p, const double* slot_lambda, const doubl
     scale[s] = (float)(slot_lambda[s] / slot_len[s]);
   }
   CU(cudaSetDevice(p->device));
+  // launches of this plan run on caller streams that need not synchronise with the legacy default stream (torch pool
+  // streams, the plan's side stream): wait for everything in flight on the device before the tables change, so that no
+  // running kernel can read a mix of old and new scales (lambdas change rarely: AdaptiveLambda, every N epochs)
+  CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(p->d_slot_scale, scale.data(), p->n_slots * sizeof(float), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(p->d_slot_lambda, slot_lambda, p->n_slots * sizeof(double), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(p->d_slot_len, slot_len, p->n_slots * sizeof(double), cudaMemcpyHostToDevice));

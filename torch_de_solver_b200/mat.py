@@ -284,6 +284,17 @@ class MatIR:
                 inside = ((i0 >= e0) & (i0 < e1)).all(1)
                 if not bool((inside | ~own).all()):
                     raise UnsupportedProblem('a periodic condition couples rows of different ranks')
+            if world > 1 and b['te'] > b['tb']:
+                # a boundary operator that differentiates along the sharded axis reaches into the neighbour's rows: the part
+                # of its adjoint that falls there would be cut off (the neighbour never evaluates this row)
+                reach = max([self.fields[f[1]][2] * (p - 1) for t in terms[b['tb']:b['te']] for f in factors[t[3]:t[4]]
+                             if self.fields[f[1]][1] == 0 and self.fields[f[1]][2] > 0] + [0])
+                if reach > 0:
+                    rows_own = i0[own][:, 0]
+                    near = ((r0 > 0) & (rows_own < r0 + reach)) | ((r1 < n0) & (rows_own >= r1 - reach))
+                    if bool(near.any()):
+                        raise UnsupportedProblem('a boundary operator with a derivative along grid axis 0 sits within its '
+                                                 'stencil reach of a slab interface: its adjoint would cross ranks')
             c = c[own] - e0 * n1
             tgt = b['tgt'][own.to(b['tgt'].device)]
             n = int(c.shape[0])
