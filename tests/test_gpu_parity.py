@@ -700,3 +700,39 @@ def test_model_train_uses_graph_step_and_matches_eager(mode_name, cuda_default, 
     np.testing.assert_allclose(seen_f, seen_e, rtol=2e-4)
     assert seen_f[-1] < seen_f[0]
     assert float((w_e - w_f).norm()) <= 2e-5 * float(w_e.norm())
+
+
+def test_mini_batches_match_reference(cuda_default):
+    """batch_size in mode 'autograd' (tedeous/eval.py:124-141, 174-182): seven consecutive steps - five batches of the
+    first epoch (the last one ragged: 41 rows), a reshuffle, two of the next - against the fixture of the unmodified
+    reference (tests/golden/make_minibatch.py), with the same generator state as the reference's DataLoader."""
+    import os
+    from helpers import GOLDEN_DIR
+    g = dict(np.load(os.path.join(GOLDEN_DIR, 'minibatch_wave.npz')))
+    prob = problems.wave(tdb, 'float32', n=20, mode='autograd', layers=(2, 32, 32, 1))
+    net = problems.make_net(prob.net_layers, torch.float32, prob.init)
+    set_weights(list(net.parameters()), g['weights'])
+    net = net.to('cuda:0')
+    model = tdb.Model(net, prob.domain, prob.equation, prob.conditions, batch_size=100)
+    model.compile('autograd', **prob.compile_kwargs, batch_generator=torch.Generator())     # CPU generator, default seed
+    sol = model.solution_cls
+    assert sol.operator.n_batches == int(g['n_batches']) == 5
+    for i in range(7):
+        for p in net.parameters():
+            p.grad = None
+        loss, _ = sol.evaluate()
+        loss.backward()
+        grad = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).double().cpu().numpy()
+        assert float(loss) == pytest.approx(float(g['losses'][i]), rel=LOSS_RTOL), i
+        gn = np.linalg.norm(g['grads'][i])
+        assert np.linalg.norm(grad - g['grads'][i]) <= GRADVEC_RTOL * gn, i
+        assert sol.operator.current_batch_i == (i + 1) % 5
+    assert sol.save_op.shape[0] == 200                  # two batches into the second epoch
+    # NN mode: the reference's batches never reach the operator (q8) -> batch_size changes nothing
+    g2 = load_golden('burgers_NN_small', 'float64')
+    prob2 = problems.ZOO['burgers_NN_small'](tdb, 'float32')
+    net2 = problems.make_net(prob2.net_layers, torch.float32, prob2.init)
+    set_weights(list(net2.parameters()), g2['weights'])
+    m2 = tdb.Model(net2.to('cuda:0'), prob2.domain, prob2.equation, prob2.conditions, batch_size=64)
+    m2.compile('NN', **prob2.compile_kwargs)
+    assert float(m2.solution_cls.evaluate()[0]) == pytest.approx(float(g2['loss']), rel=LOSS_RTOL)

@@ -46,8 +46,8 @@ class Operator:
         self.grid = self._sol.grid
         self.model = self._sol.model
         self.mode = self._sol.mode
-        self.batch_size = None
-        self.n_batches = 1
+        self.batch_size = getattr(self._sol, 'batch_size', None)
+        self.n_batches = getattr(self._sol, 'n_batches', 1)
         self.current_batch_i = 0
 
     @classmethod

@@ -78,7 +78,7 @@ class Model:
         sol = self.solution_cls
         if (optimizer.optimizer not in _KIND or mixed_precision or optimizer.cosine_scheduler_patience is not None
                 or sol.tol != 0 or sol.weak_form not in (None, []) or os.environ.get('TDB200_EAGER_TRAIN')
-                or getattr(sol, '_callable_coeffs', 'once') != 'once'):
+                or getattr(sol, '_callable_coeffs', 'once') != 'once' or getattr(sol, '_batching', False)):
             return None
         params = [sol.model] if sol.mode == 'mat' else sol._ir.net.param_tensors()
         try:
@@ -118,9 +118,10 @@ class Model:
         while fused is None and self.t < epochs and self.stop_training is False:
             callbacks.on_epoch_begin()
             self.optimizer.zero_grad()
-            self.optimizer.step(closure)
-            if optimizer.gamma is not None and self.t % optimizer.decay_every == 0:
-                optimizer.scheduler.step()
+            for _ in range(self.solution_cls.operator.n_batches):       # one optimiser step per mini-batch (model.py:178-184)
+                self.optimizer.step(closure)
+                if optimizer.gamma is not None and self.t % optimizer.decay_every == 0:
+                    optimizer.scheduler.step()
             callbacks.on_epoch_end()
             self.t += 1
         callbacks.on_train_end()

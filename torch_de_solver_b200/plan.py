@@ -592,7 +592,7 @@ class FlatIR:
     coeffs: torch.Tensor             # float32
     n_fields: int
     cparam_index: Dict[int, int]
-    coeff_fns: list = None           # [(offset, numel, callable, rows, (lo, hi) | None)]: buffers of callable coefficients
+    coeff_fns: list = None           # [(offset, numel, callable, rows, (lo, hi) | None, segment)]: callable-coefficient buffers
 
 
 def flatten(ir: ProblemIR, device) -> FlatIR:
@@ -642,7 +642,7 @@ def flatten(ir: ProblemIR, device) -> FlatIR:
                 elif isinstance(t.coeff, torch.Tensor):
                     terms.append((0.0, COEFF_BUFFER, coef_off, fb, len(factors)))
                     if t.coeff_fn is not None:
-                        coeff_fns.append((coef_off, t.coeff.numel(), t.coeff_fn[0], t.coeff_fn[1], t.coeff_slice))
+                        coeff_fns.append((coef_off, t.coeff.numel(), t.coeff_fn[0], t.coeff_fn[1], t.coeff_slice, si))
                     coefs.append(t.coeff.reshape(-1).to(device=device, dtype=torch.float32))
                     coef_off += t.coeff.numel()
                 else:

@@ -101,7 +101,7 @@ class FusedPlan:
         """Re-evaluates every callable coefficient into its per-row buffer (the reference calls coeff(grid) on every
         step, tedeous/derivative.py:41-42, 114-115; here they are evaluated at lowering and on request)."""
         with torch.no_grad():
-            for off, n, fn, rows, sl in self.flat.coeff_fns or ():
+            for off, n, fn, rows, sl, _seg in self.flat.coeff_fns or ():
                 vals = fn(rows).reshape(-1).detach()
                 if sl is not None:
                     vals = vals[sl[0]:sl[1]]
@@ -112,6 +112,29 @@ class FusedPlan:
         """Kernels serving the interior segment under the current impl setting."""
         return {1: 'simt-fp32', 2: 'tcgen05-3xtf32 (dW in TMEM)', 3: 'tcgen05-3xtf32 streamed (jet_tcs + wgrad_gemm)'}[
             int(self.lib.tdb200_plan_kernel_path(self.handle))]
+
+    def set_interior_rows(self, pts: torch.Tensor, n_valid: int):
+        """Mini-batching (tedeous/eval.py:124-141, 174-182): replace the points of the interior segment by `pts` (as many rows
+        as the plan was built with; rows >= n_valid are padding with loss weight 0) and re-evaluate its callable
+        coefficients on them; the loss divides by n_valid."""
+        seg = self.ir.segments[0]
+        if pts.shape[0] != seg.n_groups:
+            raise ValueError('batch must have the plan\'s number of interior rows')
+        with torch.no_grad():
+            self.flat.points[:seg.n_groups].copy_(pts.to(self.flat.points.dtype))
+            for off, n, fn, rows, sl, sidx in self.flat.coeff_fns or ():
+                if sidx == 0:
+                    self.flat.coeffs[off:off + n].copy_(fn(pts).reshape(-1).detach().to(self.flat.coeffs.dtype))
+        n_eq = len(seg.cols)
+        if self.ir.slot_len[0] != n_valid:
+            self.ir.slot_len = [n_valid] * n_eq + list(self.ir.slot_len[n_eq:])
+            self.set_lambdas(self.ir.slot_lambda)
+            if n_valid < seg.n_groups:
+                w = torch.zeros(seg.n_groups, dtype=torch.float32, device=self.device)
+                w[:n_valid] = 1.0
+                self.set_row_weights(w)
+            else:
+                self.set_row_weights(None)
 
     def set_impl(self, impl: int):
         _native.check(self.lib.tdb200_plan_set_impl(self.handle, impl), 'tdb200_plan_set_impl')
@@ -248,10 +271,11 @@ class Solution:
     def __init__(self, grid: torch.Tensor, equal_cls, model, mode: str, weak_form, lambda_operator,
                  lambda_bound, tol: float = 0, derivative_points: int = 2, batch_size: int = None,
                  shard: Optional[Tuple[int, int]] = None, process_group=None, nn_interior: str = 'jet',
-                 impl: int = 0, callable_coeffs: str = 'once'):
+                 impl: int = 0, callable_coeffs: str = 'once', batch_generator: torch.Generator = None):
         """Extensions after `batch_size`: shard / process_group (multi-GPU), nn_interior ('jet' | 'literal'), impl (kernel
         choice), callable_coeffs: 'once' - callable coefficients are evaluated at lowering (and by `refresh_coeffs()`),
-        'every_step' - re-evaluated by every `evaluate()` like the reference does."""
+        'every_step' - re-evaluated by every `evaluate()` like the reference does; batch_generator: the generator of the
+        mini-batch shuffle (default, as in the reference: a fresh torch.Generator on the grid's device)."""
         if callable_coeffs not in ('once', 'every_step'):
             raise ValueError("callable_coeffs must be 'once' or 'every_step'")
         self._callable_coeffs = callable_coeffs
@@ -262,15 +286,19 @@ class Solution:
             raise UnsupportedProblem('weak-form loss: no causal weights, not sharded over ranks')
         if tol != 0 and mode == 'mat':
             raise UnsupportedProblem('causal loss (tol != 0) is implemented for modes NN / autograd only (SURVEY 8 a10)')
-        if batch_size is not None:
-            # The reference draws shuffled mini-batches of the points (eval.py:124-141: DataLoader(shuffle=True) with its own
-            # generator) - a stochastic estimate of the same loss.  The fused path evaluates EVERY point each step (the
-            # expectation of that estimate; at 10^8 points/s a batch of 32 is pure launch latency), and says so once.
-            import warnings
-            warnings.warn('batch_size is ignored by the fused path: every collocation point is evaluated on every step '
-                          '(the full-batch loss, i.e. the expectation of the reference\'s shuffled mini-batch loss)',
-                          stacklevel=2)
         self.grid = check_device(grid)
+        # Mini-batches (tedeous/eval.py:124-141, 174-182; solution.py:159-166): mode 'autograd' draws shuffled batches of the
+        # grid rows for the operator; in mode 'NN' the reference's batches never reach the operator (Derivative_NN ignores
+        # grid_points), so batch_size changes nothing there; mode 'mat' has no row batches to draw.
+        self._batching = False
+        if batch_size is not None:
+            if mode == 'mat':
+                raise UnsupportedProblem("batch_size in mode 'mat' (the reference would split the [d, N0, N1] grid tensor along "
+                                         "its coordinate axis)")
+            if weak or tol != 0 or (shard is not None and shard[1] > 1):
+                raise UnsupportedProblem('mini-batches with the weak-form / causal loss or over several ranks')
+            self._batching = mode == 'autograd' and int(batch_size) < self.grid.shape[0]
+        self._batch_generator = batch_generator
         _require_cuda(self.grid, 'grid')
         self.mode = mode
         self.weak_form = weak_form
@@ -278,7 +306,7 @@ class Solution:
         self.lambda_bound = lambda_bound
         self.tol = tol
         self.derivative_points = derivative_points
-        self.batch_size = None
+        self.batch_size = int(batch_size) if self._batching else None
         # objects of the reference's own Equation_{NN,autograd,mat} classes (or anything with .operator / .bconds)
         # are re-wrapped: only the raw term dicts and conditions are read from them
         from .input_preprocessing import _EquationBase, Operator_bcond_preproc
@@ -323,7 +351,15 @@ class Solution:
         self.model = model.to(self.grid.device)
         for p in self.model.parameters():
             _require_cuda(p, 'model parameter')
-        ir = lower_problem(self.mode, self.grid, self._prepared_operator, self.prepared_bconds, self.model,
+        grid_rows = self.grid
+        if self._batching:
+            grid_rows = self.grid[:self.batch_size]          # the plan's interior segment holds one batch of rows
+            for eq in self._prepared_operator:
+                for term in eq.values():
+                    c = term['coeff']
+                    if isinstance(c, torch.Tensor) and not isinstance(c, torch.nn.Parameter) and c.numel() == self.grid.shape[0]:
+                        raise UnsupportedProblem('per-point tensor coefficients with mini-batches (use a callable coefficient)')
+        ir = lower_problem(self.mode, grid_rows, self._prepared_operator, self.prepared_bconds, self.model,
                            self.lambda_operator, self.lambda_bound, h=self._h, inner_order=self._inner_order,
                            boundary_order=self._boundary_order, nn_interior=self._nn_interior,
                            shard=self._shard)
@@ -332,6 +368,39 @@ class Solution:
         self._n_slots = ir.n_slots
         self.bval_keys = list(ir.bnd_types)
         self.bval_length = list(ir.type_len)
+        if self._batching:
+            self._init_mini_batches()
+            self.current_batch_i = 0
+
+    # -- mini-batches (tedeous/eval.py:124-141) ----------------------------------------------------------------
+    @property
+    def n_batches(self) -> int:
+        n, b = self.grid.shape[0], self.batch_size
+        return (n + b - 1) // b if self._batching else 1
+
+    def _init_mini_batches(self):
+        """A fresh shuffle of the grid rows: what iter(DataLoader(grid, batch_size, shuffle=True, generator=g)) draws -
+        RandomSampler takes torch.randperm(n, generator=g) (same generator state -> same batches as the reference)."""
+        if self._batch_generator is None:
+            self._batch_generator = torch.Generator(device=self.grid.device)
+        g = self._batch_generator
+        perm = torch.randperm(self.grid.shape[0], generator=g, device=g.device).to(self.grid.device)
+        self._batches = list(perm.split(self.batch_size))
+        self._batch_next = 0
+
+    def _next_batch(self):
+        """Binds the next batch of rows to the plan (eval.py:174-182); after the last one the rows are reshuffled."""
+        idx = self._batches[self._batch_next]
+        self._batch_next += 1
+        wrapped = self._batch_next == len(self._batches)
+        if wrapped:
+            self._init_mini_batches()
+        n_valid = int(idx.numel())
+        rows = self.grid[idx]
+        if n_valid < self.batch_size:
+            rows = torch.cat([rows, rows[-1:].expand(self.batch_size - n_valid, -1)])
+        self._plan.set_interior_rows(rows, n_valid)
+        return n_valid, wrapped
 
     def _model_change(self, new_model) -> None:
         """Swap the model (Cache callback, tedeous/solution.py:109-127): rebuilds the plan's parameter view."""
@@ -447,6 +516,8 @@ class Solution:
             return self._evaluate_weak(save_graph)
         self._sync_lambdas()
         self._fields_cache = None
+        if self._batching:
+            n_valid, wrapped = self._next_batch()
         if self.mode == 'mat':
             params = [self.model]
         else:
@@ -465,6 +536,12 @@ class Solution:
             self.lambda_operator = lambda_prepare(torch.empty(1, n_eq), self.lambda_operator).to(dt)
         if not isinstance(self.lambda_bound, torch.Tensor) or self.lambda_bound.dtype != dt:
             self.lambda_bound = lambda_prepare(torch.empty(1, len(self.bval_keys)), self.lambda_bound).to(dt)
+        if self._batching:
+            # solution.py:159-166: the residual fields of the epoch's batches are concatenated in `save_op`
+            op = self._fields()[0][:n_valid].detach()
+            self.save_op = op if self.current_batch_i == 0 else torch.cat((self.save_op, op), 0)
+            self.current_batch_i = 0 if wrapped else self.current_batch_i + 1
+            self.operator.current_batch_i = self.current_batch_i
         return self.loss, self.loss_normalized
 
     # per-column mean squares of the last evaluation (the natural partial results)
