@@ -379,12 +379,18 @@ class Solution:
         return (n + b - 1) // b if self._batching else 1
 
     def _init_mini_batches(self):
-        """A fresh shuffle of the grid rows: what iter(DataLoader(grid, batch_size, shuffle=True, generator=g)) draws -
-        RandomSampler takes torch.randperm(n, generator=g) (same generator state -> same batches as the reference)."""
+        """A fresh shuffle of the grid rows, consuming the generator exactly like the reference's
+        iter(DataLoader(grid, batch_size, shuffle=True, generator=g)): one int64 (the iterator's base seed), then
+        RandomSampler's torch.randperm(n, generator=g) - plus the sampler's empty tail randperm when an epoch ends - so the
+        same generator state yields the same batches as the reference."""
         if self._batch_generator is None:
             self._batch_generator = torch.Generator(device=self.grid.device)
         g = self._batch_generator
-        perm = torch.randperm(self.grid.shape[0], generator=g, device=g.device).to(self.grid.device)
+        n = self.grid.shape[0]
+        if getattr(self, '_batches', None) is not None:
+            torch.randperm(n, generator=g, device=g.device)       # RandomSampler's tail draw when an epoch is exhausted
+        torch.empty((), dtype=torch.int64, device=g.device).random_(generator=g)   # the DataLoader iterator's base seed
+        perm = torch.randperm(n, generator=g, device=g.device).to(self.grid.device)
         self._batches = list(perm.split(self.batch_size))
         self._batch_next = 0
 
