@@ -108,6 +108,19 @@ int tdb200_plan_set_row_weights(tdb200_plan* plan, const float* weights_dev);
  * NULL switches back to the loss gradient. */
 int tdb200_plan_set_field_seeds(tdb200_plan* plan, const float* seeds_dev);
 
+/* Multi-GPU (collocation rows shard over ranks, one all-reduce of [loss terms | gradient] per step; the
+ * reference has no collectives).  tdb200_comm_unique_id fills 128 bytes (an ncclUniqueId) on one rank; the host hands them
+ * to every rank by its own means (torch.distributed broadcast, MPI, a file); tdb200_comm_create makes this rank's NCCL
+ * communicator (collective call: every rank, same id) - one per process is enough, plans borrow it with
+ * tdb200_plan_set_comm (NULL: none).  A plan with a communicator enqueues ncclAllReduce(SUM) of its output vector on the
+ * caller's stream right after the reduction kernel of tdb200_loss_grad / tdb200_eval_fields (graph-capturable).
+ * NCCL is loaded with dlopen at the first of these calls; tdb200_comm_destroy is never called implicitly. */
+typedef struct tdb200_comm tdb200_comm;
+int tdb200_comm_unique_id(void* id_out_128_bytes);
+int tdb200_comm_create(const void* unique_id_128_bytes, int32_t rank, int32_t world, int32_t device, tdb200_comm** out);
+void tdb200_comm_destroy(tdb200_comm* comm);
+int tdb200_plan_set_comm(tdb200_plan* plan, tdb200_comm* comm);
+
 /* Choose the kernel implementation: 0 = auto, 1 = SIMT fp32, 2 = tcgen05 3xTF32 with the weight gradients of 1-2 W x W
  * layers in TMEM, 3 = streamed tcgen05 3xTF32 pair, any depth (2 / 3: error if the net / operator is not served). */
 int tdb200_plan_set_impl(tdb200_plan* plan, int32_t impl);

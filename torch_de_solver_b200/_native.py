@@ -30,7 +30,7 @@ MAT_BC_DTYPE = np.dtype([('n_rows', '<i8'), ('cell_off', '<i8'), ('tgt_off', '<i
 
 EXPORTS = [
     'tdb200_plan_create', 'tdb200_plan_set_points', 'tdb200_plan_set_slots', 'tdb200_plan_set_impl', 'tdb200_plan_set_row_weights', 'tdb200_plan_set_field_seeds',
-    'tdb200_plan_out_size', 'tdb200_plan_n_params', 'tdb200_plan_n_fields', 'tdb200_plan_launches_per_call', 'tdb200_plan_kernel_path',
+    'tdb200_plan_out_size', 'tdb200_plan_n_params', 'tdb200_plan_n_fields', 'tdb200_plan_launches_per_call', 'tdb200_plan_kernel_path', 'tdb200_comm_unique_id', 'tdb200_comm_create', 'tdb200_comm_destroy', 'tdb200_plan_set_comm',
     'tdb200_loss_grad', 'tdb200_eval_fields', 'tdb200_plan_destroy',
     'tdb200_mat_plan_create', 'tdb200_mat_plan_set_coeffs', 'tdb200_mat_plan_set_bcs', 'tdb200_mat_loss_grad', 'tdb200_mat_eval_fields',
     'tdb200_mat_plan_out_size', 'tdb200_mat_plan_launches_per_call', 'tdb200_mat_plan_kernel_kind', 'tdb200_mat_plan_set_row_window',
@@ -65,6 +65,11 @@ def load():
         getattr(lib, name).restype = i64
     lib.tdb200_plan_launches_per_call.argtypes = [vp]
     lib.tdb200_plan_kernel_path.argtypes = [vp]
+    lib.tdb200_comm_unique_id.argtypes = [vp]
+    lib.tdb200_comm_create.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
+    lib.tdb200_comm_destroy.argtypes = [vp]
+    lib.tdb200_comm_destroy.restype = None
+    lib.tdb200_plan_set_comm.argtypes = [vp, vp]
     lib.tdb200_mat_plan_launches_per_call.argtypes = [vp]
     lib.tdb200_mat_plan_kernel_kind.argtypes = [vp]
     lib.tdb200_mat_plan_set_timing.argtypes = [vp, i32]

@@ -9,6 +9,12 @@
 #include "common.cuh"
 #include "jet_tcs.cuh"
 
+namespace tdb {
+int comm_create(const void* unique_id, int rank, int world, void** comm_out);
+int comm_all_reduce_sum(void* comm, float* buf, size_t n, cudaStream_t s);
+void comm_destroy(void* comm);
+}  // namespace tdb
+
 namespace {
 thread_local std::string g_err;
 int fail(int code, const std::string& msg) {
@@ -98,6 +104,7 @@ struct tdb200_plan {
   float* tcs_zsave = nullptr;
   long long tcs_stream_stride = 0;             // floats per layer array
   int tcs_chunk_tiles = 0;
+  void* comm = nullptr;                        // NCCL communicator of the plan (tdb200_plan_comm_init), or none
 };
 
 static int points_per_tile(int J, int K) {
@@ -363,6 +370,24 @@ int tdb200_plan_set_row_weights(tdb200_plan* p, const float* weights_dev) {
 int tdb200_plan_set_field_seeds(tdb200_plan* p, const float* seeds_dev) {
   if (!p) return fail(TDB200_ERR_INVALID, "null plan");
   p->args.field_seed = seeds_dev;                        // NULL: loss gradient (default)
+  return TDB200_OK;
+}
+
+int tdb200_comm_create(const void* unique_id, int32_t rank, int32_t world, int32_t device, tdb200_comm** out) {
+  if (!out || !unique_id || world < 1 || rank < 0 || rank >= world) return fail(TDB200_ERR_INVALID, "bad communicator arguments");
+  CU(cudaSetDevice(device));
+  void* c = nullptr;
+  const int rc = tdb::comm_create(unique_id, rank, world, &c);
+  if (rc != TDB200_OK) return rc;
+  *out = reinterpret_cast<tdb200_comm*>(c);
+  return TDB200_OK;
+}
+
+void tdb200_comm_destroy(tdb200_comm* comm) { tdb::comm_destroy(comm); }
+
+int tdb200_plan_set_comm(tdb200_plan* p, tdb200_comm* comm) {
+  if (!p) return fail(TDB200_ERR_INVALID, "null plan");
+  p->comm = comm;                                        // borrowed: the caller keeps the communicator alive
   return TDB200_OK;
 }
 
@@ -674,6 +699,10 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
     CU(tdb::launch_reduce_partials(p->part_grad, do_grad ? grad_rows : 0, p->part_loss, loss_rows,
                                    do_grad ? a.n_params : 0, a.n_params_pad, p->n_slots, p->d_slot_lambda,
                                    p->d_slot_len, out, s));
+    if (p->comm) {      // ranks hold row blocks with global denominators: the per-rank vectors simply add
+      const int rc = tdb::comm_all_reduce_sum(p->comm, out, (size_t)(2 + p->n_slots + (do_grad ? a.n_params : 0)), s);
+      if (rc != TDB200_OK) return rc;
+    }
   }
   return TDB200_OK;
 }

@@ -32,6 +32,28 @@ def _require_cuda(t: torch.Tensor, what: str):
                            "and has no CPU fallback - call solver_device('cuda') first")
 
 
+_LIB_COMMS = {}          # process group -> communicator handle; kept for the life of the process (never destroyed at exit)
+
+
+def library_comm(lib, device, rank: int, world: int, group=None):
+    import torch.distributed as dist
+    key = (id(group) if group is not None else 0, device.index)
+    if key not in _LIB_COMMS:
+        uid = torch.zeros(128, dtype=torch.uint8, device='cpu')
+        if rank == 0:
+            buf = (C.c_char * 128)()
+            _native.check(lib.tdb200_comm_unique_id(buf), 'tdb200_comm_unique_id')
+            uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        uid = uid.to(device)
+        dist.broadcast(uid, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = bytes(uid.cpu().numpy().tobytes())
+        handle = C.c_void_p()
+        dev_index = device.index if device.index is not None else torch.cuda.current_device()
+        _native.check(lib.tdb200_comm_create(raw, rank, world, dev_index, C.byref(handle)), 'tdb200_comm_create')
+        _LIB_COMMS[key] = handle
+    return _LIB_COMMS[key]
+
+
 class FusedPlan:
     """Owns one tdb200_plan (modes 'NN' / 'autograd') and the device buffers bound to it."""
 
@@ -112,6 +134,16 @@ class FusedPlan:
         """Kernels serving the interior segment under the current impl setting."""
         return {1: 'simt-fp32', 2: 'tcgen05-3xtf32 (dW in TMEM)', 3: 'tcgen05-3xtf32 streamed (jet_tcs + wgrad_gemm)'}[
             int(self.lib.tdb200_plan_kernel_path(self.handle))]
+
+    def comm_init(self, rank: int, world: int, group=None):
+        """Lends the plan this process's NCCL communicator under the C ABI (made once per process group: the 128-byte
+        unique id comes from rank 0 through torch.distributed); afterwards every loss_grad call all-reduces its output
+        inside the library."""
+        _native.check(self.lib.tdb200_plan_set_comm(self.handle, library_comm(self.lib, self.device, rank, world, group)),
+                      'tdb200_plan_set_comm')
+        self.has_comm = True
+
+    has_comm = False
 
     def set_interior_rows(self, pts: torch.Tensor, n_valid: int):
         """Mini-batching (tedeous/eval.py:124-141, 174-182): replace the points of the interior segment by `pts` (as many rows
@@ -271,11 +303,15 @@ class Solution:
     def __init__(self, grid: torch.Tensor, equal_cls, model, mode: str, weak_form, lambda_operator,
                  lambda_bound, tol: float = 0, derivative_points: int = 2, batch_size: int = None,
                  shard: Optional[Tuple[int, int]] = None, process_group=None, nn_interior: str = 'jet',
-                 impl: int = 0, callable_coeffs: str = 'once', batch_generator: torch.Generator = None):
+                 impl: int = 0, callable_coeffs: str = 'once', batch_generator: torch.Generator = None,
+                 collective: str = 'library'):
         """Extensions after `batch_size`: shard / process_group (multi-GPU), nn_interior ('jet' | 'literal'), impl (kernel
         choice), callable_coeffs: 'once' - callable coefficients are evaluated at lowering (and by `refresh_coeffs()`),
         'every_step' - re-evaluated by every `evaluate()` like the reference does; batch_generator: the generator of the
         mini-batch shuffle (default, as in the reference: a fresh torch.Generator on the grid's device)."""
+        if collective not in ('library', 'torch'):
+            raise ValueError("collective must be 'library' (NCCL inside libtedeous_b200.so) or 'torch' (torch.distributed)")
+        self._collective = collective if torch.cuda.is_available() else 'torch'
         if callable_coeffs not in ('once', 'every_step'):
             raise ValueError("callable_coeffs must be 'once' or 'every_step'")
         self._callable_coeffs = callable_coeffs
@@ -365,6 +401,10 @@ class Solution:
                            shard=self._shard)
         self._ir = ir
         self._plan = FusedPlan(ir, self.grid.device, impl=self._impl)
+        if self._shard[1] > 1 and self._collective == 'library' and self.tol == 0 and self.weak_form in (None, []):
+            # the all-reduce of [loss terms | gradient] moves under the C ABI (the causal loss keeps torch.distributed:
+            # its forward-only launch must not be reduced)
+            self._plan.comm_init(self._shard[0], self._shard[1], self._pg)
         self._n_slots = ir.n_slots
         self.bval_keys = list(ir.bnd_types)
         self.bval_length = list(ir.type_len)
@@ -421,7 +461,7 @@ class Solution:
         if self.tol != 0:
             self._causal_weights()
         out = self._plan.loss_grad()
-        if self._shard[1] > 1:
+        if self._shard[1] > 1 and not self._plan.has_comm:
             import torch.distributed as dist
             dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self._pg)
         return out, out[2 + self._n_slots:]
