@@ -589,7 +589,7 @@ def test_mat_stencil_timing_entry_points(cuda_default):
     model = tdb.Model(u, prob.domain, prob.equation, prob.conditions)
     model.compile('mat', **prob.compile_kwargs)
     plan = model.solution_cls._plan
-    assert plan.kernel_kind == 'cross-march' and plan.launches_per_call == 2
+    assert plan.kernel_kind == 'cross-march' and plan.launches_per_call in (1, 2)    # 1: the single-launch step
     out0, grad0 = plan.loss_grad_raw(u)
     plan.set_timing(True)
     plan.loss_grad_raw(u)

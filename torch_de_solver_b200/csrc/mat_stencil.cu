@@ -932,101 +932,114 @@ __global__ void __launch_bounds__(128) mat_march_edge_kernel(const MatArgs a, co
   }
 }
 
+// One march item (a warp's column strip over a chunk of rows) of the register-marching kernel; returns the warp lane's
+// share of the loss.  SKIP: gradient cells of the edge frame (rows < fzy from the top / bottom, columns < fzx from the
+// left / right) are NOT stored - the edge CTAs of mat_march_fused_kernel own them.
+template <int HY, int HX, unsigned MY, unsigned MX, int P, bool SKIP>
+__device__ __forceinline__ double mw_march_item(const MatArgs& a, const int ch, const int n_strips, const int item,
+                                                const int lane, const int fzy, const int fzx) {
+  constexpr int R = 2 * HY + 1 + P;                          // ring length = unroll factor of the row loop
+  const int n0 = a.n0, n1 = a.n1;
+  double dacc = 0.0;
+  const int chunk = item / n_strips, strip = item - chunk * n_strips;
+  const int y0 = chunk * ch, y1 = min(y0 + ch, n0);
+  const int x = strip * kMwOutW - 4 + 4 * lane;            // column of this thread's first element
+  const bool col_ok = x >= 0 && x < n1;                    // n1 % 4 == 0: the float4 is entirely inside or outside
+  const bool own = col_ok && lane >= 1 && lane < 1 + kMwOutLanes;
+  const bool frame_col = SKIP && (x < fzx || x >= n1 - fzx);     // fzx % 4 == 0: the float4 is entirely inside or outside the frame
+  const bool f_ok = col_ok && a.l1_fbuf[0] != nullptr;
+  const bool do_grad = a.grad != nullptr;
+  const int zy = a.edge_y, zx = a.edge_x;
+  // The stencil weights are read from the kernel parameters where they are used (constant-bank operands of the FFMAs,
+  // no registers): that pays for one more row of register prefetch (P = 4).
+  const float scale2 = 2.f * a.eq_scale[0];
+  float sm2[4], lm[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool reg = x + i >= zx && x + i < n1 - zx;       // regular column of the operators
+    sm2[i] = reg ? scale2 : 0.f;
+    lm[i] = (reg && own) ? 1.f : 0.f;
+  }
+  const int loss_lo = max(y0, a.row_lo), loss_hi = min(y1, a.row_hi);
+  const int ybase = y0 - 2 * HY;                           // first row of u this warp loads
+  const int load_hi = min(y1 + 2 * HY, n0), f_lo = max(y0 - HY, 0), f_hi = min(y1 + HY, n0);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 u[R], s[R], fr[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) u[i] = s[i] = fr[i] = zero4;
+  const float* pu = a.u + (ptrdiff_t)ybase * n1 + x;                      // u row loaded at step j: ybase + j
+  const float* pf = a.l1_fbuf[0] + (ptrdiff_t)(ybase - HY) * n1 + x;      // forcing row loaded at step j: ybase - HY + j
+  float* pg = a.grad + (ptrdiff_t)(ybase - P - 2 * HY) * n1 + x;          // gradient row stored at step j
+  const int steps = (y1 - y0) + 4 * HY + P;
+  for (int jb = 0; jb < steps; jb += R) {
+    float lacc = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) {
+      const int j = jb + jj;
+      // (1) issue the loads of this step; they are consumed P steps from now
+      {
+        const int yl = ybase + j, yf = yl - HY;
+        u[jj] = (col_ok && yl >= 0 && yl < load_hi) ? __ldg(reinterpret_cast<const float4*>(pu)) : zero4;
+        fr[jj] = (f_ok && yf >= f_lo && yf < f_hi) ? __ldg(reinterpret_cast<const float4*>(pf)) : zero4;
+        pu += n1; pf += n1;
+      }
+      // (2) residual row yr: centre = the u row loaded at step j - P - HY, forcing loaded at step j - P
+      {
+        const int yr = ybase + j - P - HY;
+        const float4 c = u[(jj + 2 * R - P - HY) % R], fv = fr[(jj + R - P) % R];
+        float r[4] = {a.l1_fconst + fv.x, a.l1_fconst + fv.y, a.l1_fconst + fv.z, a.l1_fconst + fv.w};
+        r[0] = fmaf(a.cx_wc, c.x, r[0]); r[1] = fmaf(a.cx_wc, c.y, r[1]); r[2] = fmaf(a.cx_wc, c.z, r[2]); r[3] = fmaf(a.cx_wc, c.w, r[3]);
+#pragma unroll
+        for (int dy = -HY; dy <= HY; ++dy) {
+          if (dy == 0 || !(MY & (1u << (dy + HY)))) continue;
+          const float wgt = a.cx_wy[dy + HY];
+          const float4 v = u[(jj + 2 * R - P - HY + dy) % R];
+          r[0] = fmaf(wgt, v.x, r[0]); r[1] = fmaf(wgt, v.y, r[1]); r[2] = fmaf(wgt, v.z, r[2]); r[3] = fmaf(wgt, v.w, r[3]);
+        }
+        mw_xtaps<HX, MX, false>(c, a.cx_wx, r);
+        const bool rowreg = yr >= zy && yr < n0 - zy;      // regular row of the operators (warp-uniform)
+        if (rowreg && yr >= loss_lo && yr < loss_hi) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) lacc = fmaf(lm[i] * r[i], r[i], lacc);
+        }
+        s[jj] = rowreg ? make_float4(sm2[0] * r[0], sm2[1] * r[1], sm2[2] * r[2], sm2[3] * r[3]) : zero4;
+      }
+      // (3) gradient row yg = yr - HY: transposed stencil on the seed rows formed at steps j - 2 HY .. j
+      if (do_grad) {
+        const int yg = ybase + j - P - 2 * HY;
+        const float4 c = s[(jj + R - HY) % R];
+        float g[4] = {a.cx_wc * c.x, a.cx_wc * c.y, a.cx_wc * c.z, a.cx_wc * c.w};
+#pragma unroll
+        for (int dy = -HY; dy <= HY; ++dy) {
+          if (dy == 0 || !(MY & (1u << (dy + HY)))) continue;
+          const float wgt = a.cx_wy[dy + HY];
+          const float4 v = s[(jj + 2 * R - HY - dy) % R];   // seed row yg - dy
+          g[0] = fmaf(wgt, v.x, g[0]); g[1] = fmaf(wgt, v.y, g[1]); g[2] = fmaf(wgt, v.z, g[2]); g[3] = fmaf(wgt, v.w, g[3]);
+        }
+        mw_xtaps<HX, MX, true>(c, a.cx_wx, g);
+        if (own && yg >= y0 && yg < y1 && !(SKIP && (frame_col || yg < fzy || yg >= n0 - fzy)))
+          *reinterpret_cast<float4*>(pg) = make_float4(g[0], g[1], g[2], g[3]);
+        pg += n1;
+      }
+    }
+    dacc += (double)lacc;
+  }
+  return dacc;
+}
+
 template <int HY, int HX, unsigned MY, unsigned MX, int P>
 __global__ void __launch_bounds__(kMwThreads, 2) mat_march_kernel(const MatArgs a, const int ch, const int n_strips,
                                                                   const int n_items, const int n_edge_blocks,
                                                                   float* __restrict__ edge_seeds) {
-  constexpr int R = 2 * HY + 1 + P;                          // ring length = unroll factor of the row loop
   __shared__ double red[kMwWarps];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n0 = a.n0, n1 = a.n1;
   const int item = (int)blockIdx.x * kMwWarps + warp;
   const int first_edge_block = (int)gridDim.x - n_edge_blocks;
   double dacc = 0.0;
   if ((int)blockIdx.x >= first_edge_block) {                 // phase A of the edge treatment: the trailing CTAs fill the
     dacc = mw_edge_seeds(a, a.edge_y + HY, a.edge_x + HX, edge_seeds, (int)blockIdx.x - first_edge_block, n_edge_blocks);   // tail
   } else if (item < n_items) {                               // warp-uniform
-    const int chunk = item / n_strips, strip = item - chunk * n_strips;
-    const int y0 = chunk * ch, y1 = min(y0 + ch, n0);
-    const int x = strip * kMwOutW - 4 + 4 * lane;            // column of this thread's first element
-    const bool col_ok = x >= 0 && x < n1;                    // n1 % 4 == 0: the float4 is entirely inside or outside
-    const bool own = col_ok && lane >= 1 && lane < 1 + kMwOutLanes;
-    const bool f_ok = col_ok && a.l1_fbuf[0] != nullptr;
-    const bool do_grad = a.grad != nullptr;
-    const int zy = a.edge_y, zx = a.edge_x;
-    // The stencil weights are read from the kernel parameters where they are used (constant-bank operands of the FFMAs,
-    // no registers): that pays for one more row of register prefetch (P = 4).
-    const float scale2 = 2.f * a.eq_scale[0];
-    float sm2[4], lm[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const bool reg = x + i >= zx && x + i < n1 - zx;       // regular column of the operators
-      sm2[i] = reg ? scale2 : 0.f;
-      lm[i] = (reg && own) ? 1.f : 0.f;
-    }
-    const int loss_lo = max(y0, a.row_lo), loss_hi = min(y1, a.row_hi);
-    const int ybase = y0 - 2 * HY;                           // first row of u this warp loads
-    const int load_hi = min(y1 + 2 * HY, n0), f_lo = max(y0 - HY, 0), f_hi = min(y1 + HY, n0);
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 u[R], s[R], fr[R];
-#pragma unroll
-    for (int i = 0; i < R; ++i) u[i] = s[i] = fr[i] = zero4;
-    const float* pu = a.u + (ptrdiff_t)ybase * n1 + x;                      // u row loaded at step j: ybase + j
-    const float* pf = a.l1_fbuf[0] + (ptrdiff_t)(ybase - HY) * n1 + x;      // forcing row loaded at step j: ybase - HY + j
-    float* pg = a.grad + (ptrdiff_t)(ybase - P - 2 * HY) * n1 + x;          // gradient row stored at step j
-    const int steps = (y1 - y0) + 4 * HY + P;
-    for (int jb = 0; jb < steps; jb += R) {
-      float lacc = 0.f;
-#pragma unroll
-      for (int jj = 0; jj < R; ++jj) {
-        const int j = jb + jj;
-        // (1) issue the loads of this step; they are consumed P steps from now
-        {
-          const int yl = ybase + j, yf = yl - HY;
-          u[jj] = (col_ok && yl >= 0 && yl < load_hi) ? __ldg(reinterpret_cast<const float4*>(pu)) : zero4;
-          fr[jj] = (f_ok && yf >= f_lo && yf < f_hi) ? __ldg(reinterpret_cast<const float4*>(pf)) : zero4;
-          pu += n1; pf += n1;
-        }
-        // (2) residual row yr: centre = the u row loaded at step j - P - HY, forcing loaded at step j - P
-        {
-          const int yr = ybase + j - P - HY;
-          const float4 c = u[(jj + 2 * R - P - HY) % R], fv = fr[(jj + R - P) % R];
-          float r[4] = {a.l1_fconst + fv.x, a.l1_fconst + fv.y, a.l1_fconst + fv.z, a.l1_fconst + fv.w};
-          r[0] = fmaf(a.cx_wc, c.x, r[0]); r[1] = fmaf(a.cx_wc, c.y, r[1]); r[2] = fmaf(a.cx_wc, c.z, r[2]); r[3] = fmaf(a.cx_wc, c.w, r[3]);
-#pragma unroll
-          for (int dy = -HY; dy <= HY; ++dy) {
-            if (dy == 0 || !(MY & (1u << (dy + HY)))) continue;
-            const float wgt = a.cx_wy[dy + HY];
-            const float4 v = u[(jj + 2 * R - P - HY + dy) % R];
-            r[0] = fmaf(wgt, v.x, r[0]); r[1] = fmaf(wgt, v.y, r[1]); r[2] = fmaf(wgt, v.z, r[2]); r[3] = fmaf(wgt, v.w, r[3]);
-          }
-          mw_xtaps<HX, MX, false>(c, a.cx_wx, r);
-          const bool rowreg = yr >= zy && yr < n0 - zy;      // regular row of the operators (warp-uniform)
-          if (rowreg && yr >= loss_lo && yr < loss_hi) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) lacc = fmaf(lm[i] * r[i], r[i], lacc);
-          }
-          s[jj] = rowreg ? make_float4(sm2[0] * r[0], sm2[1] * r[1], sm2[2] * r[2], sm2[3] * r[3]) : zero4;
-        }
-        // (3) gradient row yg = yr - HY: transposed stencil on the seed rows formed at steps j - 2 HY .. j
-        if (do_grad) {
-          const int yg = ybase + j - P - 2 * HY;
-          const float4 c = s[(jj + R - HY) % R];
-          float g[4] = {a.cx_wc * c.x, a.cx_wc * c.y, a.cx_wc * c.z, a.cx_wc * c.w};
-#pragma unroll
-          for (int dy = -HY; dy <= HY; ++dy) {
-            if (dy == 0 || !(MY & (1u << (dy + HY)))) continue;
-            const float wgt = a.cx_wy[dy + HY];
-            const float4 v = s[(jj + 2 * R - HY - dy) % R];   // seed row yg - dy
-            g[0] = fmaf(wgt, v.x, g[0]); g[1] = fmaf(wgt, v.y, g[1]); g[2] = fmaf(wgt, v.z, g[2]); g[3] = fmaf(wgt, v.w, g[3]);
-          }
-          mw_xtaps<HX, MX, true>(c, a.cx_wx, g);
-          if (own && yg >= y0 && yg < y1) *reinterpret_cast<float4*>(pg) = make_float4(g[0], g[1], g[2], g[3]);
-          pg += n1;
-        }
-      }
-      dacc += (double)lacc;
-    }
+    dacc = mw_march_item<HY, HX, MY, MX, P, false>(a, ch, n_strips, item, lane, 0, 0);
   }
   for (int o = 16; o; o >>= 1) dacc += __shfl_xor_sync(kFullMask, dacc, o);
   if (lane == 0) red[warp] = dacc;
@@ -1574,6 +1587,161 @@ __device__ void mat_finalize_block(const double* __restrict__ part_loss, int n_c
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// EXPERIMENT (opt-in with TDB200_MAT_FUSED=1; measured 68.7 us per step at 4096^2 against 59.7 us of the two-launch
+// schedule: the edge phases are multi-microsecond chains of dependent loads wherever they run, and the union of the
+// roles spills in the marching loop at 128 registers).
+// The whole mat-mode step in ONE launch (plans of mat_edge_bc_kernel: one linear constant-coefficient equation, every
+// boundary row a value row on a frame cell - BASELINE config 4).  The step used to be march launch (with phase A in its
+// tail) -> edge / boundary launch: 36 us of streaming followed by ~20 us of latency chains of two tiny grids.  Here the
+// first `n_edge_blocks` CTAs of the launch are EDGE CTAs, resident next to the marching CTAs from the start:
+//   A'  seeds 2 lambda / N * residual of every cell of the EXTENDED frame (frame + stencil reach), from u and the banded
+//       operators; loss of the cells with special rows (the marching warps count the regular ones);
+//   --  barrier among the edge CTAs (they are the first CTAs of the grid: co-resident, a spin on a counter is safe);
+//   B'  every frame cell gathers coef * seed over ALL its neighbours (regular rows included) plus the adjoint of the
+//       boundary rows that touch it (cell -> row CSR) and STORES its gradient: the frame cells belong to the edge CTAs
+//       alone, the marching warps skip them (mw_march_item<SKIP>), so nothing orders the two roles;
+//   C   boundary residuals -> loss slots.
+// The last CTA of the grid to finish assembles the loss.  One owner per gradient cell, fixed summation orders:
+// bit-reproducible like the two-launch schedule.
+template <int HY, int HX, unsigned MY, unsigned MX, int P>
+__global__ void __launch_bounds__(kMwThreads, 2) mat_march_fused_kernel(const MatArgs a, const int ch, const int n_strips,
+                                                                        const int n_items, const int n_edge_blocks,
+                                                                        float* __restrict__ es, const MatBcArgs b,
+                                                                        const MwEdgeBc e, unsigned int* edge_sync) {
+  __shared__ double red[kMwWarps];
+  __shared__ double sh_slot[32];
+  __shared__ unsigned int sh_ticket;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = a.n0, n1 = a.n1;
+  double dacc = 0.0;
+  if (tid < 32) sh_slot[tid] = 0.0;
+  __syncthreads();
+  {                                                                                           // A': every CTA takes a share
+    const MwFrame frx(a, e.zy3 + HY, e.zx3 + HX);
+    const float scale2 = 2.f * a.eq_scale[0];
+    for (int idx = (int)blockIdx.x * (int)blockDim.x + tid; idx < frx.total; idx += (int)gridDim.x * (int)blockDim.x) {
+      int gy, gx;
+      frx.cell(idx, gy, gx);
+      const float res = mw_edge_residual(a, gy, gx);
+      if (!frx.regular(gy, gx) && gy >= a.row_lo && gy < a.row_hi) dacc += (double)res * (double)res;
+      es[idx] = scale2 * res;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicAdd(edge_sync, 1u);
+  }
+  {                                                                                           // the marching work
+    const int item = (int)blockIdx.x * kMwWarps + warp;
+    if (item < n_items) dacc += mw_march_item<HY, HX, MY, MX, P, true>(a, ch, n_strips, item, lane, e.zy3, e.zx3);
+  }
+  {                                                                                           // B' + C: every CTA takes a share
+    const MwFrame frx(a, e.zy3 + HY, e.zx3 + HX), fr(a, e.zy3, e.zx3);
+    const int stride = (int)gridDim.x * (int)blockDim.x, first = (int)blockIdx.x * (int)blockDim.x + tid;
+    if (tid == 0)                                    // every CTA of the grid is resident (checked by the host) and did A'
+      while (atomicAdd(edge_sync, 0u) < gridDim.x) __nanosleep(100);   // before its march: no waiting in practice
+    __syncthreads();
+    __threadfence();
+    const size_t N = (size_t)n0 * n1;
+    auto row_residual = [&](const tdb200_mat_bc& bc, long long r) {
+      float val = 0.f;
+      for (int k = 0; k < bc.K; ++k) val += bc.sign[k] * __ldg(b.u + (size_t)bc.var * N + b.cells[bc.cell_off + r * bc.K + k]);
+      return val - b.targets[bc.tgt_off + r];
+    };
+    for (int idx = first; idx < fr.total; idx += stride) {                                    // B'
+      int gy, gx;
+      fr.cell(idx, gy, gx);
+      float g = 0.f;
+#pragma unroll 2
+      for (int t = 0; t < a.n_lin; ++t) {
+        const tdb200_mat_field& f = a.fld[a.lin_q[t]];
+        float sacc = 0.f;
+        if (f.order == 0) {
+          sacc = __ldcg(es + frx.index(gy, gx));
+        } else {
+          float sv[2 * kMwMaxHw + 1], cv[2 * kMwMaxHw + 1];
+#pragma unroll
+          for (int mm = -kMwMaxHw; mm <= kMwMaxHw; ++mm) {
+            const int yy = f.axis == 0 ? gy + mm : gy, xx = f.axis == 0 ? gx : gx + mm;
+            const bool ok = mm >= -f.half_width && mm <= f.half_width && yy >= 0 && yy < n0 && xx >= 0 && xx < n1;
+            sv[mm + kMwMaxHw] = ok ? __ldcg(es + frx.index(yy, xx)) : 0.f;
+            cv[mm + kMwMaxHw] = ok ? band_coef(a.band, f, f.axis == 0 ? n0 : n1, f.axis == 0 ? yy : xx, -mm) : 0.f;
+          }
+#pragma unroll
+          for (int mm = 0; mm <= 2 * kMwMaxHw; ++mm) sacc = fmaf(cv[mm], sv[mm], sacc);
+        }
+        g = fmaf(a.lin_c[t], sacc, g);
+      }
+      const int e0 = __ldg(e.csr_off + idx), e1 = __ldg(e.csr_off + idx + 1);
+      for (int q = e0; q < e1; ++q) {                      // boundary rows that touch this cell, in row order
+        const int4 en = __ldg(e.csr_ent + q);
+        const tdb200_mat_bc bc = b.bcs[en.x];
+        g = fmaf(2.f * b.slot_scale[bc.slot] * bc.sign[en.z], row_residual(bc, en.y), g);
+      }
+      a.grad[(size_t)gy * n1 + gx] = g;
+    }
+    const long long total = b.bc_row_begin[b.n_bcs];                                          // C
+    for (long long row = first; row < total; row += stride) {
+      int bi = 0;
+      while (row >= b.bc_row_begin[bi + 1]) ++bi;
+      const tdb200_mat_bc bc = b.bcs[bi];
+      const float res = row_residual(bc, row - b.bc_row_begin[bi]);
+      const unsigned act = __activemask();
+      double sq = (double)res * (double)res;
+      const int slot0 = __shfl_sync(act, bc.slot, __ffs(act) - 1);
+      if (act == 0xffffffffu && __all_sync(act, bc.slot == slot0)) {      // one shared-memory atomic per warp
+        for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(act, sq, o);
+        if (lane == 0) atomicAdd(&sh_slot[slot0], sq);
+      } else {
+        atomicAdd(&sh_slot[bc.slot], sq);
+      }
+    }
+  }
+  for (int o = 16; o; o >>= 1) dacc += __shfl_xor_sync(kFullMask, dacc, o);
+  if (lane == 0) red[warp] = dacc;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kMwWarps; ++w) t += red[w];
+    a.part_loss[blockIdx.x] = t;
+  }
+  if (tid < b.n_bc_slots && sh_slot[tid] != 0.0) atomicAdd(b.slot_sum + tid, sh_slot[tid]);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) sh_ticket = atomicAdd(b.ticket, 1u);
+  __syncthreads();
+  if (sh_ticket != gridDim.x - 1) return;
+  __threadfence();
+  if (tid == 0) { *b.ticket = 0u; *edge_sync = 0u; }
+  mat_finalize_block(a.part_loss, (int)gridDim.x, b.n_eq, b.n_cells, b.slot_sum, b.n_bc_slots, b.slot_lambda, b.slot_len, b.out);
+}
+
+constexpr int kMwFusedEdgeBlocks = 16;
+static int mat_march_fused_ctas(const MatArgs& a, int n_sms);        // 280 marching CTAs + 16 edge CTAs = 296 = 2 CTAs on each of the 148 SMs at 4096^2
+template <int HY, int HX, unsigned MY, unsigned MX>
+static cudaError_t launch_mat_march_fused_t(const MatArgs& a, int n_sms, float* es, const MatBcArgs& b, const MwEdgeBc& e,
+                                            unsigned int* edge_sync, int* n_ctas, cudaStream_t s) {
+  const int ch = mat_march_chunk(a, n_sms), n_strips = (a.n1 + kMwOutW - 1) / kMwOutW;
+  const int n_items = n_strips * ((a.n0 + ch - 1) / ch);
+  const int grid = kMwFusedEdgeBlocks + (n_items + kMwWarps - 1) / kMwWarps;
+  *n_ctas = grid;
+  mat_march_fused_kernel<HY, HX, MY, MX, 5><<<grid, kMwThreads, 0, s>>>(a, ch, n_strips, n_items, kMwFusedEdgeBlocks, es, b, e, edge_sync);
+  return cudaGetLastError();
+}
+static int mat_march_fused_ctas(const MatArgs& a, int n_sms) {
+  const int ch = mat_march_chunk(a, n_sms), n_strips = (a.n1 + kMwOutW - 1) / kMwOutW;
+  return kMwFusedEdgeBlocks + (n_strips * ((a.n0 + ch - 1) / ch) + kMwWarps - 1) / kMwWarps;
+}
+static cudaError_t launch_mat_march_fused(const MatArgs& a, int hy, int hx, unsigned my, unsigned mx, int n_sms, float* es,
+                                          const MatBcArgs& b, const MwEdgeBc& e, unsigned int* edge_sync, int* n_ctas,
+                                          cudaStream_t s) {
+#define X(A, B, C, D) if (hy == A && hx == B && (my & ~C) == 0 && (mx & ~D) == 0) return launch_mat_march_fused_t<A, B, C, D>(a, n_sms, es, b, e, edge_sync, n_ctas, s);
+  TDB_MARCH_SHAPES(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
 __global__ void mat_finalize_kernel(const double* __restrict__ part_loss, int n_ctas, int n_eq, double n_cells,
                                     double* __restrict__ bc_sum, int n_bc_slots,
                                     const double* __restrict__ slot_lambda, const double* __restrict__ slot_len,
@@ -1787,7 +1955,7 @@ int tdb200_mat_plan_create(const tdb200_mat_desc* desc, const tdb200_mat_field* 
     if (p->march) {
       const int m = tdb::mat_march_ctas(a, p->n_sms);
       l1 = m > l1 ? m : l1;
-      MCU(cudaMalloc(&p->d_edge_seed, sizeof(float) * (tdb::mat_march_frame_cells(a, hy, hx) + 1)));
+      MCU(cudaMalloc(&p->d_edge_seed, sizeof(float) * (tdb::mat_march_frame_cells(a, 2 * hy, 2 * hx) + 1)));   // extended frame
     }
     MCU(cudaMalloc(&p->d_part_loss, sizeof(double) * (size_t)(p->n_ctas > l1 ? p->n_ctas : l1) * desc->n_eq));
   }
@@ -1841,8 +2009,8 @@ int tdb200_mat_plan_set_bcs(tdb200_mat_plan* p, int32_t n_bcs, const tdb200_mat_
   MCU(cudaMemcpy(p->d_slot_len, slot_len, sizeof(double) * n_slots, cudaMemcpyHostToDevice));
   MCU(cudaMalloc(&p->d_bc_sum, sizeof(double) * (p->n_bc_slots > 0 ? p->n_bc_slots : 1)));
   MCU(cudaMemset(p->d_bc_sum, 0, sizeof(double) * (p->n_bc_slots > 0 ? p->n_bc_slots : 1)));
-  if (!p->d_ticket) MCU(cudaMalloc(&p->d_ticket, 2 * sizeof(unsigned int)));   // [finalize ticket, tile counter]
-  MCU(cudaMemset(p->d_ticket, 0, 2 * sizeof(unsigned int)));
+  if (!p->d_ticket) MCU(cudaMalloc(&p->d_ticket, 4 * sizeof(unsigned int)));   // [finalize ticket, tile counter, edge barrier]
+  MCU(cudaMemset(p->d_ticket, 0, 4 * sizeof(unsigned int)));
   for (int e = 0; e < n_eq; ++e) p->args.eq_scale[e] = (float)(slot_lambda[e] / slot_len[e]);
   {  // register-marching plans: can the edge frame and the boundary rows share one launch?  (every row a value row -
      // Dirichlet / periodic values - and every cell it touches a frame cell: then the adjoint of the rows is gathered per
@@ -1966,6 +2134,21 @@ static int mat_stencil(tdb200_mat_plan* p, tdb::MatArgs& a, const float* u, floa
   return TDB200_OK;
 }
 
+// single-launch step: a march plan whose boundary rows are value rows on frame cells, loss + gradient call, 16-byte
+// aligned tensors, frame columns a multiple of 4 wide (the marching warps skip whole float4s)
+static bool mat_fused_ok(const tdb200_mat_plan* p, const tdb::MatArgs& a, const float* u, const float* grad, const float* op_out,
+                         const float* bval_out) {
+  if (!(p->march && p->edge_bc && p->args.lin1 && grad && !op_out && !bval_out && p->n_bc_rows > 0)) return false;
+  if (!getenv("TDB200_MAT_FUSED")) return false;          // measured slower than the two-launch schedule (68.7 vs 59.7 us): opt-in
+  auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  const float* fb = p->l1_n_fbuf > 0 ? p->args.coeffs + p->l1_fbuf_off[0] : nullptr;
+  if (!aligned16(u) || !aligned16(grad) || !aligned16(fb)) return false;
+  const int zy3 = a.edge_y + p->cx_hy, zx3 = a.edge_x + p->cx_hx;
+  // the edge CTAs wait for every CTA of the grid: all of them must be resident at once (2 CTAs of 256 threads per SM)
+  if (tdb::mat_march_fused_ctas(a, p->n_sms) > 2 * p->n_sms) return false;
+  return zx3 % 4 == 0 && a.n1 % 4 == 0 && 2 * (zx3 + p->cx_hx) < a.n1 && 2 * (zy3 + p->cx_hy) < a.n0;
+}
+
 static int mat_run(tdb200_mat_plan* p, const float* u, float* grad, float* op_out, float* bval_out, float* out,
                    void* stream) {
   if (!p || !u || !out) return mat_invalid("null argument");
@@ -1977,6 +2160,24 @@ static int mat_run(tdb200_mat_plan* p, const float* u, float* grad, float* op_ou
   int n_ctas = p->n_ctas;
   if (p->timing) MCU(cudaEventRecord(p->ev0, s));
   bool ran_march = false;
+  if (mat_fused_ok(p, a, u, grad, op_out, bval_out)) {
+    // the whole step in one launch: marching CTAs + edge CTAs (seeds of the extended frame, frame gradient, boundary
+    // rows) + loss assembly by the last CTA
+    for (int i = 0; i < 2; ++i) a.l1_fbuf[i] = i < p->l1_n_fbuf ? a.coeffs + p->l1_fbuf_off[i] : nullptr;
+    tdb::MatBcArgs b = p->bc;
+    b.u = u; b.grad = grad; b.bval_out = nullptr;
+    b.part_loss = p->d_part_loss; b.n_bc_slots = p->n_bc_slots;
+    b.n_cells = (double)p->desc.n0 * (double)p->desc.n1;
+    b.slot_lambda = p->d_slot_lambda; b.slot_len = p->d_slot_len; b.out = out; b.ticket = p->d_ticket; b.tile_ctr = p->d_ticket + 1;
+    tdb::MwEdgeBc eb{};
+    eb.zy3 = a.edge_y + p->cx_hy; eb.zx3 = a.edge_x + p->cx_hx; eb.n_frame_blocks = 0;
+    eb.es = p->d_edge_seed; eb.csr_off = p->d_csr_off; eb.csr_ent = p->d_csr_ent;
+    MCU(tdb::launch_mat_march_fused(a, p->cx_hy, p->cx_hx, p->cx_my, p->cx_mx, p->n_sms, p->d_edge_seed, b, eb, p->d_ticket + 2,
+                                    &n_ctas, s));
+    b.n_ctas = n_ctas;
+    if (p->timing) MCU(cudaEventRecord(p->ev1, s));
+    return TDB200_OK;
+  }
   {
     const int rc = mat_stencil(p, a, u, grad, op_out, &n_ctas, p->timing ? p->ev1 : nullptr, false, s, &ran_march);
     if (rc != TDB200_OK) return rc;
@@ -2020,7 +2221,12 @@ int tdb200_mat_eval_fields(tdb200_mat_plan* p, const float* u_dev, float* op_dev
 }
 
 int64_t tdb200_mat_plan_out_size(const tdb200_mat_plan* p) { return p ? 2 + p->n_slots : 0; }
-int32_t tdb200_mat_plan_launches_per_call(const tdb200_mat_plan* p) { return p ? (p->args.lin1 && p->march && !p->edge_bc ? 3 : 2) : 0; }
+int32_t tdb200_mat_plan_launches_per_call(const tdb200_mat_plan* p) {
+  if (!p) return 0;
+  if (p->march && p->edge_bc && p->args.lin1 && getenv("TDB200_MAT_FUSED") && (p->args.edge_x + p->cx_hx) % 4 == 0 &&
+      tdb::mat_march_fused_ctas(p->args, p->n_sms) <= 2 * p->n_sms) return 1;
+  return p->args.lin1 && p->march && !p->edge_bc ? 3 : 2;
+}
 
 int tdb200_mat_plan_set_row_window(tdb200_mat_plan* p, int32_t row_lo, int32_t row_hi) {
   if (!p) return mat_invalid("null plan");
