@@ -39,11 +39,11 @@ def launches(name):
     with open(os.path.join(PR, f'{R}_launches_{name}.md'), 'w') as f:
         f.write(f'# {R}: launches of `python bench.py` ({name}) under `ncu --metrics gpu__time_duration.sum`\n\n')
         f.write('Cold-cache, serialised timings: compare shares, not absolutes.\n\n')
-        if name == 'wave':
-            f.write('NOTE: in the real step `jet_simt_kernel` (all boundary rows, ONE CTA, side stream) runs CONCURRENTLY with '
-                    '`jet_tc_kernel` (147 CTAs) and ends before it (DESIGN 3.4); ncu serialises the two launches, so the '
-                    'share below is its duration on one SM, not a share of the step.  With `TDB200_NO_OVERLAP=1` the same '
-                    'rows take ~0.19 ms on 32 CTAs after the interior launch (2 % of the step).\n\n')
+        if name in ('wave', 'bench'):
+            f.write('NOTE: in the real step the boundary-row launches on the side stream (`jet_simt_kernel` on a few CTAs, small '
+                    '`jet_tc_kernel` launches) run CONCURRENTLY with the interior launch and end before it (DESIGN 3.4); ncu '
+                    'serialises them, so their share below is not a share of the step.  The bench command measures every '
+                    'BASELINE config one after the other: kernels are listed over the whole run.\n\n')
         f.write('| kernel | launches | total | share |\n|---|---|---|---|\n')
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f'| `{k}` | {n} | {t:.1f} {unit} | {100 * t / tot:.1f} % |\n')
@@ -79,8 +79,35 @@ def full(name):
         f.write('\n## hottest source lines (warp-stall samples)\n\n```\n' + hot + '```\n')
 
 
-for n in ('wave', 'mat'):
+import json
+for n in ('wave', 'bench', 'mat'):
     launches(n)
-for n in ('jet_tc', 'jet_simt', 'mat'):
+for n in ('jet_tc', 'jet_simt', 'jet_tcs', 'jet_tcs_ns', 'wgrad', 'mat'):
     full(n)
+
+# dram traffic per launch of the dominant kernel of each bench workload, read by bench.py (roofline.traffic)
+traffic = {}
+for workload, reps in (('burgers_NN_cfg1', ['jet_tc']), ('wave_autograd_1e6', ['jet_tcs', 'wgrad']),
+                       ('ns_autograd_1e6', ['jet_tcs_ns']), ('poisson_mat_4096', ['mat'])):
+    tot, names = 0.0, []
+    for name in reps:
+        rep = os.path.join(GO, f'{R}_{name}.ncu-rep')
+        if not os.path.exists(rep):
+            tot = None
+            break
+        raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        hdr, units, vals = rows[0], rows[1], rows[2]
+        scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+        for key in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+            i = hdr.index(key)
+            tot += float(vals[i].replace(',', '')) * scale[units[i]]
+        names.append(vals[hdr.index('Kernel Name')].split('(')[0])
+    if tot is not None:
+        traffic[workload] = {'bytes': tot, 'kernels': names, 'source': f'profiles/{R}_ncu_*.md (ncu --set full, one launch each)'}
+if traffic:
+    path = os.path.join(PR, 'ncu_traffic.json')
+    old = json.load(open(path)) if os.path.exists(path) else {}
+    old.update(traffic)
+    json.dump(old, open(path, 'w'), indent=1)
 print('\n'.join(sorted(x for x in os.listdir(PR) if x.startswith(R))))
