@@ -15,6 +15,7 @@
 //     MMA that reads it has retired); the epilogue warps hand over operand images with mbarriers (no CTA-wide barrier
 //     between an epilogue and its GEMM).
 #pragma once
+#include <stdlib.h>
 #include "jet_tc_kernel.cuh"
 #include "jet_tcs.cuh"
 
@@ -22,7 +23,6 @@ namespace tdb {
 
 constexpr int kTsEpi = 512;                       // epilogue threads (16 warps: 4 lane windows x 4 column parts)
 constexpr int kTsThreads = kTsEpi + 96;           // + the MMA / weight-streaming warp + one operator warp per tile slot
-constexpr int kTsHalfFloats = 2 * kTcWBlock;      // one K half (2 k-blocks) of a hi or lo weight image
 constexpr int kSOffW = 0, kSOffAct = 2 * kTcWFloats, kSOffX = kSOffAct + 4 * kTcActFloats,
               kSOffU = kSOffX + 4 * kTcMaxPts * 4, kSOffGu = kSOffU + 2 * kTcMaxOut * kTcCols,      // U, Gu: per slot
               kSOffUP = kSOffGu + 2 * kTcMaxOut * kTcCols, kSOffCg = kSOffUP + 4 * kTcMaxOut * kTcCols,
@@ -55,14 +55,14 @@ __device__ __forceinline__ void issue_gemm_steps(uint32_t d_tmem, const float* w
     }
   }
 }
-// one K half (k-blocks 2h, 2h + 1 of the hi and of the lo image) of a weight image pair -> shared memory
-__device__ __forceinline__ void bulk_load_half(float* dst, const float* src, int h, uint64_t* bar) {
-  constexpr uint32_t kBytes = kTsHalfFloats * 4, kChunk = 6656;       // 26624 = 4 x 6656
+// one k-block (32 K values = 4 K-steps; hi and lo image) of a weight image pair -> shared memory
+__device__ __forceinline__ void bulk_load_kblock(float* dst, const float* src, int kb, uint64_t* bar) {
+  constexpr uint32_t kBytes = kTcWBlock * 4, kChunk = 6656;           // 13312 = 2 x 6656
   const uint32_t b = smem_u32(bar);
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(2 * kBytes) : "memory");
 #pragma unroll
   for (int img = 0; img < 2; ++img) {
-    const uint32_t off = (uint32_t)img * kTcWFloats * 4 + (uint32_t)h * kBytes;
+    const uint32_t off = (uint32_t)img * kTcWFloats * 4 + (uint32_t)kb * kBytes;
     for (uint32_t o = 0; o < kBytes; o += kChunk)
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                    :: "r"(smem_u32(dst) + off + o), "l"(reinterpret_cast<const char*>(src) + off + o), "r"(kChunk), "r"(b)
@@ -76,7 +76,7 @@ __device__ __forceinline__ void bulk_load_half(float* dst, const float* src, int
 #define TSMARK(i) do { } while (0)
 #endif
 
-template <int O0, int O1, int O2>
+template <int O0, int O1, int O2, bool TM>
 __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a, const TcsArgs x) {
   constexpr int J = 1 + O0 + O1 + O2;
   constexpr int ND = (O0 > 0) + (O1 > 0) + (O2 > 0);
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
   tdb200_term* termS; tdb200_factor* facS; tdb200_segment* segS; float* scaleS; double* lossT; int4* recS; int* fastS;
   {
     uint8_t* q = reinterpret_cast<uint8_t*>(sbase + kSOffEnd);
-    bars = reinterpret_cast<uint64_t*>(q); q += 128;
+    bars = reinterpret_cast<uint64_t*>(q); q += 160;
     tmem_ptr = reinterpret_cast<uint32_t*>(q); q += 32;
     termS = reinterpret_cast<tdb200_term*>(q); q += (kTcMaxTerms * sizeof(tdb200_term) + 15) / 16 * 16;
     facS = reinterpret_cast<tdb200_factor*>(q); q += (kTcMaxFactors * sizeof(tdb200_factor) + 15) / 16 * 16;
@@ -105,11 +105,11 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
   }
   uint64_t* const act_full = bars;             // [2] epilogue warps (16 arrivals) -> MMA warp: operand image of the slot is ready
   uint64_t* const d_full = bars + 2;           // [2] MMA warp (tcgen05.commit) -> epilogue warps: accumulator of the slot is ready
-  uint64_t* const w_full = bars + 4;           // [2] bulk copies -> MMA warp: K half of the weight image has landed
-  uint64_t* const w_free = bars + 6;           // [2] MMA warp (tcgen05.commit): every MMA reading the K half has retired
-  uint64_t* const op_req = bars + 8;           // [2] epilogue warps (16 arrivals) -> operator warp: last-layer partial sums are in UP
-  uint64_t* const op_done = bars + 10;         // [2] operator warp -> epilogue warps: adjoint seeds Gu of the slot are ready
-  uint64_t* const up_free = bars + 12;         // operator warp -> epilogue warps: UP has been consumed
+  uint64_t* const w_full = bars + 4;           // [4] bulk copies -> MMA warp: k-block of the weight image has landed
+  uint64_t* const w_free = bars + 8;           // [4] MMA warp (tcgen05.commit): every MMA reading the k-block has retired
+  uint64_t* const op_req = bars + 12;          // [2] epilogue warps (16 arrivals) -> operator warp: last-layer partial sums are in UP
+  uint64_t* const op_done = bars + 14;         // [2] operator warp -> epilogue warps: adjoint seeds Gu of the slot are ready
+  uint64_t* const up_free = bars + 16;         // operator warp -> epilogue warps: UP has been consumed
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool is_mma_warp = warp == kTsEpi / 32, is_op_warp = warp == kTsEpi / 32 + 1 || warp == kTsEpi / 32 + 2;
 #ifdef TDB_TC_TIMING
@@ -147,13 +147,13 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
   for (int i = tid; i < kTcMaxPts * TDB200_MAX_COLS; i += kTsThreads) lossT[i] = 0.0;
   if (tid == 0) {
     mbar_init(act_full, 16); mbar_init(act_full + 1, 16);
-    for (int i = 2; i < 8; ++i) mbar_init(bars + i, 1);
+    for (int i = 2; i < 12; ++i) mbar_init(bars + i, 1);
     mbar_init(op_req, 16); mbar_init(op_req + 1, 16);
     mbar_init(op_done, 1); mbar_init(op_done + 1, 1); mbar_init(up_free, 1);
     *fastS = 1;
   }
   if (is_mma_warp) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" :: "r"(smem_u32(tmem_ptr)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_ptr)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -190,8 +190,10 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
       return kind < NM ? x.wimg + (size_t)kind * 4 * kTcWFloats
                        : x.wimg + (size_t)(2 * NM - 1 - kind) * 4 * kTcWFloats + 2 * kTcWFloats;
     };
-    uint32_t act_ph = 0, wfull_ph = 0, wfree_ph = 0;    // one parity bit per slot / half
-    if (iters > 0 && leader) { bulk_load_half(wbuf, image_of(0), 0, w_full); bulk_load_half(wbuf, image_of(0), 1, w_full + 1); }
+    uint32_t act_ph = 0, wfull_ph = 0, wfree_ph = 0;    // one parity bit per slot / k-block
+    const int n_kb = (ksteps + 3) / 4;
+    if (iters > 0 && leader)
+      for (int kb = 0; kb < 4; ++kb) bulk_load_kblock(wbuf, image_of(0), kb, w_full + kb);
     __syncwarp();
     for (int it = 0; it < iters; ++it) {
       const int nslots = (2 * it + 1 < my_tiles) ? 2 : 1;
@@ -203,25 +205,24 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
           TSMARK(12);
           const float* b_hi = sbase + kSOffAct + slot * 2 * kTcActFloats;
           const uint32_t dt = tmem + (uint32_t)slot * kTcCols;
-          if (slot == 0) { mbar_wait(w_full, wfull_ph & 1); wfull_ph ^= 1; }
-          TSMARK(13);
-          issue_gemm_steps(dt, wbuf, wbuf + kTcWFloats, b_hi, 0, ksteps < 8 ? ksteps : 8, leader);
-          if (slot == nslots - 1 && leader) umma_commit(w_free);
-          TSMARK(14);
-          if (slot == 0) { mbar_wait(w_full + 1, (wfull_ph >> 1) & 1); wfull_ph ^= 2; }
-          TSMARK(13);
-          issue_gemm_steps(dt, wbuf, wbuf + kTcWFloats, b_hi, 8, ksteps, leader);
-          if (leader) umma_commit(d_full + slot);
-          if (slot == nslots - 1 && leader) umma_commit(w_free + 1);
+#pragma unroll 1
+          for (int kb = 0; kb < 4; ++kb) {
+            if (slot == 0) { mbar_wait(w_full + kb, (wfull_ph >> kb) & 1); wfull_ph ^= 1u << kb; }
+            TSMARK(13);
+            if (kb < n_kb) issue_gemm_steps(dt, wbuf, wbuf + kTcWFloats, b_hi, 4 * kb, ksteps < 4 * kb + 4 ? ksteps : 4 * kb + 4, leader);
+            if (kb == 3 && leader) umma_commit(d_full + slot);
+            if (slot == nslots - 1 && leader) umma_commit(w_free + kb);
+            TSMARK(14);
+          }
           __syncwarp();
-          TSMARK(14);
         }
         const int next = kind + 1 < n_kinds ? kind + 1 : (it + 1 < iters ? 0 : -1);
-        if (next >= 0) {
-          mbar_wait(w_free, wfree_ph & 1); wfree_ph ^= 1;
-          if (leader) bulk_load_half(wbuf, image_of(next), 0, w_full);
-          mbar_wait(w_free + 1, (wfree_ph >> 1) & 1); wfree_ph ^= 2;
-          if (leader) bulk_load_half(wbuf, image_of(next), 1, w_full + 1);
+        if (next >= 0) {                                  // every k-block is reloaded as soon as its last reader has retired
+#pragma unroll 1
+          for (int kb = 0; kb < 4; ++kb) {
+            mbar_wait(w_free + kb, (wfree_ph >> kb) & 1); wfree_ph ^= 1u << kb;
+            if (leader) bulk_load_kblock(wbuf, image_of(next), kb, w_full + kb);
+          }
           __syncwarp();
         }
       }
@@ -487,6 +488,10 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
       tc_fence_after();
     };
     auto load_d = [&](int slot, float* v) { tmem_ld16(t_lane + (uint32_t)slot * kTcCols + (uint32_t)col0, v); };
+    // Saved pre-activation jets of W x W layer l (1 .. NM - 1) for the backward sweep.  TM (nets with <= 4 W x W layers):
+    // TMEM columns 128 .. 511 hold six 64-column regions = three layers of both slots (one tcgen05.st / ld, no memory
+    // latency); deeper nets use the L2-resident scratch.  A compile-time choice: both paths in one kernel cost 30 registers.
+    auto zsave_tmem = [&](int slot, int l) { return t_lane + 2 * kTcCols + (uint32_t)(((l - 1) * 2 + slot) * kTcCols + col0); };
     auto zsave_ptr = [&](int slot, int l) {                // saved jets of W x W layer l (1..NM)
       return reinterpret_cast<float4*>(x.zsave + ((((size_t)blockIdx.x * 2 + slot) * NM + (l - 1)) * kTsEpi + tid) * 16);
     };
@@ -526,13 +531,18 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
 #pragma unroll
           for (int p = 0; p < PH; ++p) z[p * J] += bl;
           if (a.do_grad) {
-            float4* zs = zsave_ptr(slot, l);
+            if constexpr (TM) {
+              tmem_st16(zsave_tmem(slot, l), z);
+            } else {
+              float4* zs = zsave_ptr(slot, l);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) zs[q] = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
+              for (int q = 0; q < 4; ++q) zs[q] = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
+            }
           }
           jets_fwd(z, false, y);
           if (live) store_act(slot, y);
           if (a.do_grad) stream_rows(x.ys + (size_t)l * x.stream_stride, tile_of(it, slot), y);
+          if (TM && a.do_grad) tmem_st_wait();
           hand_over(slot);
           TSMARK(3);
         }
@@ -608,13 +618,14 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
       for (int t = NM - 1; t >= 1; --t) {
         for (int slot = 0; slot < nslots; ++slot) {
           float z[16], gy[16], gz[16];
-          {
+          if constexpr (!TM) {
             const float4* zs = zsave_ptr(slot, t);        // issued before the wait: the L2 latency hides behind the GEMM
 #pragma unroll
             for (int q = 0; q < 4; ++q) { const float4 v4 = zs[q]; z[4 * q] = v4.x; z[4 * q + 1] = v4.y; z[4 * q + 2] = v4.z; z[4 * q + 3] = v4.w; }
           }
           wait_d(slot);
           TSMARK(8);
+          if constexpr (TM) tmem_ld16(zsave_tmem(slot, t), z);
           load_d(slot, gy);
           db_acc[t] += jets_bwd(z, false, gy, gz, nullptr);
           if (!live) {
@@ -702,20 +713,20 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
       *q = acc ? *q + sacc : sacc;
     }
   }
-  if (is_mma_warp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" :: "r"(tmem) : "memory");
+  if (is_mma_warp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int O0, int O1, int O2>
+template <int O0, int O1, int O2, bool TM>
 static cudaError_t launch_tcs_sig(const JetArgs& a, const TcsArgs& x, int grid, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(jet_tcs_kernel<O0, O1, O2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(jet_tcs_kernel<O0, O1, O2, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kTsSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  jet_tcs_kernel<O0, O1, O2><<<grid, kTsThreads, kTsSmemBytes, s>>>(a, x);
+  jet_tcs_kernel<O0, O1, O2, TM><<<grid, kTsThreads, kTsSmemBytes, s>>>(a, x);
   return cudaGetLastError();
 }
 
@@ -724,7 +735,9 @@ static cudaError_t launch_tcs_sig(const JetArgs& a, const TcsArgs& x, int grid, 
     SIGS(TDB_TCS_GROUP_CASE)                                                                                    \
     return cudaErrorInvalidValue;                                                                               \
   }
-#define TDB_TCS_GROUP_CASE(A, B, Cc) \
-  if (o0 == A && o1 == B && o2 == Cc) return launch_tcs_sig<A, B, Cc>(a, x, grid, s);
+#define TDB_TCS_GROUP_CASE(A, B, Cc)                                                         \
+  if (o0 == A && o1 == B && o2 == Cc)                                                        \
+    return (a.n_layers - 2 <= 4 && !getenv("TDB200_TCS_NO_TM")) ? launch_tcs_sig<A, B, Cc, true>(a, x, grid, s)      \
+                                                                 : launch_tcs_sig<A, B, Cc, false>(a, x, grid, s);
 
 }  // namespace tdb

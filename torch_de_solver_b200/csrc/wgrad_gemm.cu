@@ -4,7 +4,7 @@
 // arrays of float4 [group of 4 columns][Wp neurons]; this kernel is the split-K contraction over the columns:
 // HBM-bound (2 * Wp * 4 bytes per column and layer), tcgen05.mma.kind::tf32 in the 3xTF32 split, accumulator in TMEM.
 //
-// One CTA = one (layer, range of stages); a stage = KB = 24 or 32 columns of both operands = two contiguous runs of
+// One CTA = one (layer, range of stages); a stage = KB = 32 columns of both operands = two contiguous runs of
 // KB * Wp floats.  Three roles:
 //   * warp 9 (one lane): cp.async.bulk of the two runs of a stage into a 3-deep ring of raw buffers, completion on an
 //     mbarrier - the HBM stream is asynchronous and ~80 KB deep per SM, independent of the registers of the other warps;
@@ -21,9 +21,10 @@
 
 namespace tdb {
 
-constexpr int kWgKB = 32;                          // most rows (K) per stage
+constexpr int kWgKB = 32;                          // rows (K) per stage: four K-steps (16-row stages with a 10-deep raw
+                                                   // ring measured slower: 2.32 vs 1.87 ms on the wave workload)
 constexpr int kWgRawStages = 3, kWgImgStages = 2;
-constexpr int kWgImg = 4 * kWgKB * 32;             // floats of one operand image: 4 MN blocks x 32 K rows x 32
+constexpr int kWgImg = 4 * kWgKB * 32;             // floats of one operand image: 4 MN blocks x 16 K rows x 32
 constexpr int kWgImgStageFloats = 4 * kWgImg;      // A hi, A lo, B hi, B lo = 64 KB
 constexpr int kWgRawOp = kWgKB * 104;              // floats of one operand of a raw stage (Wp <= 104)
 constexpr int kWgRawStageFloats = 2 * kWgRawOp;    // 26 KB
@@ -42,12 +43,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const WgradAr
   float* const sbase = reinterpret_cast<float*>(smem_raw_wg + (((s0_ + 1023u) & ~1023u) - s0_));
   float* const raw = sbase + kWgImgStages * kWgImgStageFloats;
   uint64_t* const bars = reinterpret_cast<uint64_t*>(raw + kWgRawStages * kWgRawStageFloats);
-  uint64_t* const raw_full = bars;                 // [3] bulk copies -> converters
-  uint64_t* const raw_empty = bars + 3;            // [3] converters (8 arrivals) -> producer
-  uint64_t* const img_full = bars + 6;             // [2] converters (8 arrivals) -> MMA warp
-  uint64_t* const img_empty = bars + 8;            // [2] MMA warp (tcgen05.commit) -> converters
-  uint64_t* const done = bars + 10;
-  uint32_t* const tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* const raw_full = bars;                                   // bulk copies -> converters
+  uint64_t* const raw_empty = bars + kWgRawStages;                   // converters (8 arrivals) -> producer
+  uint64_t* const img_full = bars + 2 * kWgRawStages;                // converters (8 arrivals) -> MMA warp
+  uint64_t* const img_empty = img_full + kWgImgStages;               // MMA warp (tcgen05.commit) -> converters
+  uint64_t* const done = img_empty + kWgImgStages;
+  uint32_t* const tmem_ptr = reinterpret_cast<uint32_t*>(done + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   const int layer = blockIdx.x % a.n_mma;          // 0-based: dW of W x W layer `layer + 1`
@@ -102,11 +103,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const WgradAr
     }
   } else if (warp < kWgConvWarps) {
     // ---- converters: thread t owns the float4 t, t + 256, ... of every stage (same image positions every stage) ----
-    int off[4];                                     // image offset of element 0 of the float4 (element e: K row + e)
-    int c3[4];
-    bool own[4];
+    constexpr int NQ = (kWgKB * 104 / 4 + 255) / 256;      // float4 per thread, operand and stage (4)
+    int off[NQ];                                    // image offset of element 0 of the float4 (element e: K row + e)
+    int c3[NQ];
+    bool own[NQ];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NQ; ++i) {
       const int f = tid + 256 * i;
       own[i] = f < F;
       const int n = f % Wp, krow = 4 * (f / Wp);
@@ -130,9 +132,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const WgradAr
       mbar_wait(raw_full + rs, ruse & 1);
       const long long nf = a.total4 - kb * F < F ? a.total4 - kb * F : F;
       const float4* r4 = reinterpret_cast<const float4*>(raw + rs * kWgRawStageFloats);
-      float4 gc[4], yc[4];
+      float4 gc[NQ], yc[NQ];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < NQ; ++q) {
         const bool ok = own[q] && tid + 256 * q < nf;
         gc[q] = ok ? r4[tid + 256 * q] : make_float4(0.f, 0.f, 0.f, 0.f);
         yc[q] = ok ? r4[kWgRawOp / 4 + tid + 256 * q] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const WgradAr
       if (iuse > 0) mbar_wait(img_empty + is, (iuse - 1) & 1);
       float* const st = sbase + is * kWgImgStageFloats;
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
+      for (int q = 0; q < NQ; ++q)
         if (own[q]) {
           put(st, st + kWgImg, q, gc[q]);
           put(st + 2 * kWgImg, st + 3 * kWgImg, q, yc[q]);
