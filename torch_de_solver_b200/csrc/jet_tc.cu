@@ -32,7 +32,7 @@ __global__ void pack_tc_images_kernel(PackArgs a, float* __restrict__ img) {
 }
 
 cudaError_t launch_pack_tc_images(const PackArgs& a, float* img, cudaStream_t s) {
-  pack_tc_images_kernel<<<32, 256, 0, s>>>(a, img);
+  pack_tc_images_kernel<<<148, 256, 0, s>>>(a, img);
   return cudaGetLastError();
 }
 

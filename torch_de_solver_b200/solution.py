@@ -32,6 +32,12 @@ def _require_cuda(t: torch.Tensor, what: str):
                            "and has no CPU fallback - call solver_device('cuda') first")
 
 
+def _dist_ready() -> bool:
+    """A sharded plan built outside a torch.distributed job (tests that add the shards up by hand) has no collective."""
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized()
+
+
 _LIB_COMMS = {}          # process group -> communicator handle; kept for the life of the process (never destroyed at exit)
 
 
@@ -401,7 +407,8 @@ class Solution:
                            shard=self._shard)
         self._ir = ir
         self._plan = FusedPlan(ir, self.grid.device, impl=self._impl)
-        if self._shard[1] > 1 and self._collective == 'library' and self.tol == 0 and self.weak_form in (None, []):
+        if (self._shard[1] > 1 and self._collective == 'library' and self.tol == 0 and self.weak_form in (None, [])
+                and _dist_ready()):
             # the all-reduce of [loss terms | gradient] moves under the C ABI (the causal loss keeps torch.distributed:
             # its forward-only launch must not be reduced)
             self._plan.comm_init(self._shard[0], self._shard[1], self._pg)
