@@ -488,10 +488,39 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
       tc_fence_after();
     };
     auto load_d = [&](int slot, float* v) { tmem_ld16(t_lane + (uint32_t)slot * kTcCols + (uint32_t)col0, v); };
-    // Saved pre-activation jets of W x W layer l (1 .. NM - 1) for the backward sweep.  TM (nets with <= 4 W x W layers):
-    // TMEM columns 128 .. 511 hold six 64-column regions = three layers of both slots (one tcgen05.st / ld, no memory
-    // latency); deeper nets use the L2-resident scratch.  A compile-time choice: both paths in one kernel cost 30 registers.
-    auto zsave_tmem = [&](int slot, int l) { return t_lane + 2 * kTcCols + (uint32_t)(((l - 1) * 2 + slot) * kTcCols + col0); };
+    // Saved pre-activation jets of W x W layer l (1 .. NM - 1) for the backward sweep.  TM ((NM - 1) * Q <= 12): TMEM
+    // columns 128 .. 511 hold one region of 4 parts x 4 Q columns (only the used columns) per saved layer and slot (a
+    // tcgen05.st / ld, no memory latency) - three layers of 64 columns, or the four layers of the Navier-Stokes net at 48;
+    // other nets use the L2-resident scratch.  A compile-time choice: both paths in one kernel cost 30 registers.
+    auto zsave_tmem = [&](int slot, int l) {
+      return t_lane + 2 * kTcCols + (uint32_t)(((l - 1) * 2 + slot) * (16 * Q) + part * (4 * Q));
+    };
+    auto zsave_tmem_st = [&](uint32_t addr, const float* v) {
+      if (Q == 4) { tmem_st16(addr, v); return; }
+      tmem_st4(addr, v);
+      if (Q > 1) tmem_st4(addr + 4, v + 4);
+      if (Q > 2) tmem_st4(addr + 8, v + 8);
+    };
+    auto zsave_tmem_ld = [&](uint32_t addr, float* v) {
+      if (Q == 4) { tmem_ld16(addr, v); return; }
+      if (Q >= 2) tmem_ld8(addr, v);
+      if (Q == 3) {
+        uint32_t r[4];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr + 8));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[8 + i] = __uint_as_float(r[i]);
+      }
+      if (Q == 1) {
+        uint32_t r[4];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+      }
+#pragma unroll
+      for (int j = 4 * Q; j < 16; ++j) v[j] = 0.f;
+    };
     auto zsave_ptr = [&](int slot, int l) {                // saved jets of W x W layer l (1..NM)
       return reinterpret_cast<float4*>(x.zsave + ((((size_t)blockIdx.x * 2 + slot) * NM + (l - 1)) * kTsEpi + tid) * 16);
     };
@@ -532,7 +561,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
           for (int p = 0; p < PH; ++p) z[p * J] += bl;
           if (a.do_grad) {
             if constexpr (TM) {
-              tmem_st16(zsave_tmem(slot, l), z);
+              zsave_tmem_st(zsave_tmem(slot, l), z);
             } else {
               float4* zs = zsave_ptr(slot, l);
 #pragma unroll
@@ -625,7 +654,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
           }
           wait_d(slot);
           TSMARK(8);
-          if constexpr (TM) tmem_ld16(zsave_tmem(slot, t), z);
+          if constexpr (TM) zsave_tmem_ld(zsave_tmem(slot, t), z);
           load_d(slot, gy);
           db_acc[t] += jets_bwd(z, false, gy, gz, nullptr);
           if (!live) {
@@ -737,7 +766,8 @@ static cudaError_t launch_tcs_sig(const JetArgs& a, const TcsArgs& x, int grid, 
   }
 #define TDB_TCS_GROUP_CASE(A, B, Cc)                                                         \
   if (o0 == A && o1 == B && o2 == Cc)                                                        \
-    return (a.n_layers - 2 <= 4 && !getenv("TDB200_TCS_NO_TM")) ? launch_tcs_sig<A, B, Cc, true>(a, x, grid, s)      \
-                                                                 : launch_tcs_sig<A, B, Cc, false>(a, x, grid, s);
+    return ((a.n_layers - 3) * ((jet_tc_columns_per_part(A, B, Cc) + 3) / 4) <= 12 && !getenv("TDB200_TCS_NO_TM"))  \
+               ? launch_tcs_sig<A, B, Cc, true>(a, x, grid, s)                                                        \
+               : launch_tcs_sig<A, B, Cc, false>(a, x, grid, s);
 
 }  // namespace tdb
