@@ -5,6 +5,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 #include "common.cuh"
 #include "jet_tcs.cuh"
@@ -531,7 +532,8 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
     tdb::JetArgs tc = call;
     tc.seg_tile_begin = p->d_seg_tile_begin_tc;
     long long* dbg = nullptr;
-    if (getenv("TDB200_TC_TIMING")) { cudaMalloc(&dbg, sizeof(long long) * 16 * p->tc_grid); cudaMemset(dbg, 0, sizeof(long long) * 16 * p->tc_grid); }
+    const size_t dbg_n = 16 * (size_t)p->tc_grid + 512;      // + event trace of one iteration of CTA 0 (TDB_TC_TIMING builds)
+    if (getenv("TDB200_TC_TIMING")) { cudaMalloc(&dbg, sizeof(long long) * dbg_n); cudaMemset(dbg, 0, sizeof(long long) * dbg_n); }
     tc.dbg = dbg;
     tdb::TcsArgs xa{};
     xa.wimg = p->wimg; xa.ys = p->tcs_ys; xa.gs = p->tcs_gs; xa.stream_stride = p->tcs_stream_stride;
@@ -559,6 +561,17 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
         fprintf(stderr, "[tdb200 tcs timing] cycles per tile (CTA 0, %d tiles; 0-11 epilogue thread 0, 12-15 MMA warp):", tiles_per_cta);
         for (int i = 0; i < 16; ++i) fprintf(stderr, " p%d=%lld", i, h[i] / tiles_per_cta);
         fprintf(stderr, "\n");
+        if (getenv("TDB200_TC_TRACE")) {                 // merged event list of iteration 40 of CTA 0: (cycle, role, mark)
+          std::vector<long long> tr(512);
+          cudaMemcpy(tr.data(), dbg + 16 * p->tc_grid, 512 * sizeof(long long), cudaMemcpyDeviceToHost);
+          std::vector<std::pair<long long, int>> ev;
+          for (int r = 0; r < 2; ++r)
+            for (int i = 0; i < 256; ++i)
+              if (tr[r * 256 + i]) ev.push_back({tr[r * 256 + i] >> 8, r * 1000 + (int)(tr[r * 256 + i] & 255)});
+          std::sort(ev.begin(), ev.end());
+          for (const auto& e : ev)
+            fprintf(stderr, "[tdb200 tcs trace] %8lld %s mark %d\n", e.first - ev[0].first, e.second >= 1000 ? "            mma" : "epi", e.second % 1000);
+        }
       }
     }
     if (dbg) cudaFree(dbg);

@@ -17,6 +17,7 @@ struct TcsArgs {
   int tile0, tile1;             // tiles of this launch (chunk)
   int Wp;                       // row pitch of the streams (W rounded up to 4)
   int zero_partials;            // 1: first chunk of a call (partial rows start from zero), 0: accumulate
+  int w_in_tmem;                // set by the launcher: weights as tensor-memory operands (tcgen05.cp), see jet_tcs_kernel.cuh
 };
 
 // wgrad_gemm_kernel

@@ -24,9 +24,10 @@ namespace tdb {
 constexpr int kTsEpi = 512;                       // epilogue threads (16 warps: 4 lane windows x 4 column parts)
 constexpr int kTsThreads = kTsEpi + 96;           // + the MMA / weight-streaming warp + one operator warp per tile slot
 constexpr int kSOffW = 0, kSOffAct = 2 * kTcWFloats, kSOffX = kSOffAct + 4 * kTcActFloats,
-              kSOffU = kSOffX + 4 * kTcMaxPts * 4, kSOffGu = kSOffU + 2 * kTcMaxOut * kTcCols,      // U, Gu: per slot
+              kSOffU = kSOffX + 6 * kTcMaxPts * 4, kSOffGu = kSOffU + 2 * kTcMaxOut * kTcCols,      // U, Gu: per slot
               kSOffUP = kSOffGu + 2 * kTcMaxOut * kTcCols, kSOffCg = kSOffUP + 4 * kTcMaxOut * kTcCols,
-              kSOffBl = kSOffCg + (kMaxCParams + 3) / 4 * 4, kSOffEnd = kSOffBl + kTcMaxOut;
+              kSOffBl = kSOffCg + (kMaxCParams + 3) / 4 * 4, kSOffDbl = kSOffBl + kTcMaxOut,      // Dbl: last-layer bias gradient per slot
+              kSOffEnd = kSOffDbl + 2 * kTcMaxOut;
 constexpr size_t kTsSmemBytes =
     (size_t)kSOffEnd * 4 + 1024 /*align*/ + 160 /*barriers*/ + kTcMaxTerms * sizeof(tdb200_term) +
     kTcMaxFactors * sizeof(tdb200_factor) + 16 + sizeof(tdb200_segment) + 16 + 32 * 4 + kTcMaxPts * TDB200_MAX_COLS * 8 +
@@ -39,20 +40,68 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // K-steps [s0, s1) of one 3xTF32 layer GEMM: D[:, 0:64] (+)= W_hi Y_hi + W_hi Y_lo + W_lo Y_hi, three N = 64 MMAs into ONE
 // accumulator (jet_tc_kernel.cuh issues an N = 128 + an N = 64 MMA and adds two halves in the epilogue: 25 % less tensor
 // time, but this kernel is bound by its epilogues and the tensor pipe has slack - a single tcgen05.ld and no adds).
-__device__ __forceinline__ void issue_gemm_steps(uint32_t d_tmem, const float* w_hi, const float* w_lo, const float* b_hi,
-                                                 int s0, int s1, bool leader) {
+//
+// w_tmem != 0: the weights are MMA operands out of TENSOR memory.  Each K-step of the hi / lo image (128 rows x 256 bits,
+// the K-major SWIZZLE_128B descriptor of the SS form - profiles/microbench/cp_probe.cu) is copied with tcgen05.cp to
+// columns w_tmem + 8 s / w_tmem + 104 + 8 s; tcgen05.cp and tcgen05.mma execute in issue order, so the copies of the NEXT
+// layer are issued right behind the last slot's MMAs of the current one and run while the tensor pipe would wait for the
+// epilogues; the MMAs then read only B (2 KB) from shared memory (event trace: 42 cycles per MMA against 60-85 for
+// shared-memory A operands next to the operand-image stores of the 16 epilogue warps).
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" :: "r"(taddr), "l"(sdesc) : "memory");
+}
+// One k-block (<= 4 K-steps, compile-time descriptor offsets: the issuing thread is a single instruction stream, and with
+// run-time offsets its ~25 dependent uniform-datapath instructions per K-step - not the tensor pipe - set the pace: the
+// event trace showed 110 cycles per MMA against 50 for the unrolled form).  awh / awl / bh / bl are the descriptors of the
+// k-block's first K-step.
+template <int NS>
+__device__ __forceinline__ void issue_kblock_steps(uint32_t d_tmem, uint64_t awh, uint64_t awl, uint64_t bh, uint64_t bl,
+                                                   bool first_kb, uint32_t wt) {
   constexpr uint32_t idesc64 = umma_idesc(128, kTcCols, 0, 1);
-  const uint64_t dwh = umma_desc(smem_u32(w_hi), 16, 1024), dwl = umma_desc(smem_u32(w_lo), 16, 1024);
-  const uint64_t dbh = umma_desc(smem_u32(b_hi), kTcActBlock * 4, 512, 1),
-                 dbl = umma_desc(smem_u32(b_hi + kTcActFloats), kTcActBlock * 4, 512, 1);
-  for (int s = s0; s < s1; ++s) {
-    const uint64_t ao = ((uint64_t)(s >> 2) * kTcWBlock * 4 + (uint64_t)(s & 3) * 32) >> 4;
-    const uint64_t bo = ((uint64_t)s * 1024) >> 4;
-    if (leader) {
-      umma_tf32(d_tmem, dwh + ao, dbh + bo, idesc64, s ? 1u : 0u);
-      umma_tf32(d_tmem, dwh + ao, dbl + bo, idesc64, 1u);
-      umma_tf32(d_tmem, dwl + ao, dbh + bo, idesc64, 1u);
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    const uint64_t ao = (uint64_t)(j * 32) >> 4, bo = (uint64_t)(j * 1024) >> 4;
+    const uint32_t acc0 = (first_kb && j == 0) ? 0u : 1u;
+    if (wt) {
+      const uint32_t th = wt + (uint32_t)j * 8, tl = th + kTcWRows;
+      umma_tf32_ts(d_tmem, th, bh + bo, idesc64, acc0);
+      umma_tf32_ts(d_tmem, th, bl + bo, idesc64, 1u);
+      umma_tf32_ts(d_tmem, tl, bh + bo, idesc64, 1u);
+    } else {
+      umma_tf32(d_tmem, awh + ao, bh + bo, idesc64, acc0);
+      umma_tf32(d_tmem, awh + ao, bl + bo, idesc64, 1u);
+      umma_tf32(d_tmem, awl + ao, bh + bo, idesc64, 1u);
     }
+  }
+}
+__device__ __forceinline__ void issue_gemm_kblock(uint32_t d_tmem, const float* w_hi, const float* w_lo, const float* b_hi,
+                                                  int kb, int nsteps, bool leader, uint32_t w_tmem) {
+  const uint64_t awh = umma_desc(smem_u32(w_hi) + (uint32_t)kb * kTcWBlock * 4, 16, 1024),
+                 awl = umma_desc(smem_u32(w_lo) + (uint32_t)kb * kTcWBlock * 4, 16, 1024);
+  const uint64_t bh = umma_desc(smem_u32(b_hi) + (uint32_t)kb * 4096, kTcActBlock * 4, 512, 1),
+                 bl = umma_desc(smem_u32(b_hi + kTcActFloats) + (uint32_t)kb * 4096, kTcActBlock * 4, 512, 1);
+  const uint32_t wt = w_tmem ? w_tmem + (uint32_t)kb * 32 : 0u;
+  if (leader) {
+    if (nsteps >= 4) issue_kblock_steps<4>(d_tmem, awh, awl, bh, bl, kb == 0, wt);
+    else if (nsteps == 3) issue_kblock_steps<3>(d_tmem, awh, awl, bh, bl, kb == 0, wt);
+    else if (nsteps == 2) issue_kblock_steps<2>(d_tmem, awh, awl, bh, bl, kb == 0, wt);
+    else if (nsteps == 1) issue_kblock_steps<1>(d_tmem, awh, awl, bh, bl, kb == 0, wt);
+  }
+}
+// k-block kb (nsteps K-steps) of the weight image pair in shared memory -> tensor memory columns w_tmem + 32 kb ...
+// (hi) and + 104 (lo)
+__device__ __forceinline__ void issue_weight_copy(uint32_t w_tmem, const float* w_hi, const float* w_lo, int kb, int nsteps,
+                                                  bool leader) {
+  const uint64_t awh = umma_desc(smem_u32(w_hi) + (uint32_t)kb * kTcWBlock * 4, 16, 1024),
+                 awl = umma_desc(smem_u32(w_lo) + (uint32_t)kb * kTcWBlock * 4, 16, 1024);
+  if (leader) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nsteps) {
+        const uint32_t th = w_tmem + (uint32_t)(kb * 4 + j) * 8;
+        tmem_cp_128x256b(th, awh + ((uint64_t)(j * 32) >> 4));
+        tmem_cp_128x256b(th + kTcWRows, awl + ((uint64_t)(j * 32) >> 4));
+      }
   }
 }
 // one k-block (32 K values = 4 K-steps; hi and lo image) of a weight image pair -> shared memory
@@ -71,7 +120,8 @@ __device__ __forceinline__ void bulk_load_kblock(float* dst, const float* src, i
 }
 
 #ifdef TDB_TC_TIMING       // phase timers: build with TDB200_TC_TIMING_BUILD=1, run with TDB200_TC_TIMING=1
-#define TSMARK(i) do { if (a.dbg) { const long long tn_ = clock64(); tacc[i] += tn_ - tlast; tlast = tn_; } } while (0)
+#define TSMARK(i) do { if (a.dbg) { const long long tn_ = clock64(); tacc[i] += tn_ - tlast; tlast = tn_; \
+    if (tr_on && tr_n < 256) tr_buf[tr_n++] = (tn_ << 8) | (i); } } while (0)
 #else
 #define TSMARK(i) do { } while (0)
 #endif
@@ -117,6 +167,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
 #pragma unroll
   for (int i = 0; i < 16; ++i) tacc[i] = 0;
   long long tlast = clock64();
+  bool tr_on = false;                                   // event trace of iteration 40 of CTA 0 (marks: see TSMARK calls)
+  int tr_n = 0;
+  long long* const tr_buf = a.dbg ? a.dbg + 16 * gridDim.x + (warp == kTsEpi / 32 ? 256 : 0) : nullptr;
 #endif
   const int n = (warp & 3) * 32 + lane;                 // neuron = TMEM lane owned by this thread
   const int part = (warp >> 2) & 3;                     // column part (0..3) of the tile this thread owns
@@ -136,7 +189,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
     for (int i = tid; i < a.n_params_pad; i += kTsThreads) a.part_grad[(size_t)blockIdx.x * a.n_params_pad + i] = 0.f;
   for (int i = tid; i < 4 * kTcActFloats; i += kTsThreads) (sbase + kSOffAct)[i] = 0.f;    // pad rows / columns stay zero
   if (tid < kMaxCParams) (sbase + kSOffCg)[tid] = 0.f;
-  for (int i = tid; i < 4 * kTcMaxPts * 4; i += kTsThreads) (sbase + kSOffX)[i] = 0.f;     // axes >= d stay zero
+  for (int i = tid; i < 6 * kTcMaxPts * 4; i += kTsThreads) (sbase + kSOffX)[i] = 0.f;     // axes >= d stay zero
   for (int i = tid; i < 2 * kTcMaxOut * kTcCols; i += kTsThreads) (sbase + kSOffGu)[i] = 0.f;
   if (tid < kTcMaxOut) (sbase + kSOffBl)[tid] = tid < n_out ? a.arena[a.b_off[L - 1] + tid] : 0.f;
   for (int i = tid; i < min(kTcMaxTerms, a.n_terms); i += kTsThreads) termS[i] = a.terms[i];
@@ -191,13 +244,69 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
                        : x.wimg + (size_t)(2 * NM - 1 - kind) * 4 * kTcWFloats + 2 * kTcWFloats;
     };
     uint32_t act_ph = 0, wfull_ph = 0, wfree_ph = 0;    // one parity bit per slot / k-block
+    const uint32_t w_tmem = x.w_in_tmem ? tmem + (512u - 2u * kTcWRows) : 0u;     // columns 304 .. 511: W hi | W lo
     const int n_kb = (ksteps + 3) / 4;
     if (iters > 0 && leader)
       for (int kb = 0; kb < 4; ++kb) bulk_load_kblock(wbuf, image_of(0), kb, w_full + kb);
     __syncwarp();
+    if (w_tmem) {
+      // ---- weights in tensor memory.  Invariant at the top of job g (= iteration x layer GEMM): the copies of image g are
+      // queued or done; shared memory holds nothing that is still needed.  Per job: slot 0's MMAs | request image g + 1
+      // (its predecessor's copies have retired by now) | slot 1's MMAs | copies of image g + 1 behind them.
+      const int total = iters * n_kinds;
+      auto copy_image = [&]() {
+#pragma unroll 1
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(w_full + kb, (wfull_ph >> kb) & 1); wfull_ph ^= 1u << kb;
+          tc_fence_after();
+          if (kb < n_kb) issue_weight_copy(w_tmem, wbuf, wbuf + kTcWFloats, kb, ksteps - 4 * kb, leader);
+          if (leader) umma_commit(w_free + kb);
+          __syncwarp();
+        }
+      };
+      if (total > 0) copy_image();
+      int g = 0;
+      for (int it = 0; it < iters; ++it) {
+        const int nslots = (2 * it + 1 < my_tiles) ? 2 : 1;
+#ifdef TDB_TC_TIMING
+        tr_on = a.dbg && blockIdx.x == 0 && it == 40 && lane == 0;
+#endif
+        for (int kind = 0; kind < n_kinds; ++kind, ++g) {
+          const int next = kind + 1 < n_kinds ? kind + 1 : 0;
+          for (int slot = 0; slot < nslots; ++slot) {
+            TSMARK(15);
+            mbar_wait(act_full + slot, (act_ph >> slot) & 1); act_ph ^= 1u << slot;
+            tc_fence_after();
+            TSMARK(12);
+            const float* b_hi = sbase + kSOffAct + slot * 2 * kTcActFloats;
+            const uint32_t dt = tmem + (uint32_t)slot * kTcCols;
+#pragma unroll 1
+            for (int kb = 0; kb < n_kb; ++kb)
+              issue_gemm_kblock(dt, wbuf, wbuf + kTcWFloats, b_hi, kb, ksteps - 4 * kb, leader, w_tmem);
+            if (leader) umma_commit(d_full + slot);
+            __syncwarp();
+            TSMARK(14);
+            if (slot == 0 && g + 1 < total) {
+#pragma unroll 1
+              for (int kb = 0; kb < 4; ++kb) {
+                mbar_wait(w_free + kb, (wfree_ph >> kb) & 1); wfree_ph ^= 1u << kb;
+                if (leader) bulk_load_kblock(wbuf, image_of(next), kb, w_full + kb);
+              }
+              __syncwarp();
+              TSMARK(13);
+            }
+          }
+          if (g + 1 < total) copy_image();
+        }
+      }
+    } else
     for (int it = 0; it < iters; ++it) {
       const int nslots = (2 * it + 1 < my_tiles) ? 2 : 1;
+#ifdef TDB_TC_TIMING
+      tr_on = a.dbg && blockIdx.x == 0 && it == 40 && lane == 0;
+#endif
       for (int kind = 0; kind < n_kinds; ++kind) {
+        const int next = kind + 1 < n_kinds ? kind + 1 : (it + 1 < iters ? 0 : -1);
         for (int slot = 0; slot < nslots; ++slot) {
           TSMARK(15);
           mbar_wait(act_full + slot, (act_ph >> slot) & 1); act_ph ^= 1u << slot;
@@ -205,25 +314,28 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
           TSMARK(12);
           const float* b_hi = sbase + kSOffAct + slot * 2 * kTcActFloats;
           const uint32_t dt = tmem + (uint32_t)slot * kTcCols;
+          const bool last_slot = slot == nslots - 1;     // the shared-memory k-block is free after the LAST slot has read it
 #pragma unroll 1
           for (int kb = 0; kb < 4; ++kb) {
             if (slot == 0) { mbar_wait(w_full + kb, (wfull_ph >> kb) & 1); wfull_ph ^= 1u << kb; }
             TSMARK(13);
-            if (kb < n_kb) issue_gemm_steps(dt, wbuf, wbuf + kTcWFloats, b_hi, 4 * kb, ksteps < 4 * kb + 4 ? ksteps : 4 * kb + 4, leader);
+            if (kb < n_kb) issue_gemm_kblock(dt, wbuf, wbuf + kTcWFloats, b_hi, kb, ksteps - 4 * kb, leader, 0u);
             if (kb == 3 && leader) umma_commit(d_full + slot);
-            if (slot == nslots - 1 && leader) umma_commit(w_free + kb);
+            if (last_slot && leader) umma_commit(w_free + kb);
+            // progressive reload: k-block kb - 1 of the NEXT image is requested as soon as its last reader has retired
+            // (the MMAs of k-block kb are queued behind it, so the wait does not starve the tensor pipe)
+            if (last_slot && kb > 0 && next >= 0) {
+              mbar_wait(w_free + kb - 1, (wfree_ph >> (kb - 1)) & 1); wfree_ph ^= 1u << (kb - 1);
+              if (leader) bulk_load_kblock(wbuf, image_of(next), kb - 1, w_full + kb - 1);
+            }
             TSMARK(14);
           }
           __syncwarp();
-        }
-        const int next = kind + 1 < n_kinds ? kind + 1 : (it + 1 < iters ? 0 : -1);
-        if (next >= 0) {                                  // every k-block is reloaded as soon as its last reader has retired
-#pragma unroll 1
-          for (int kb = 0; kb < 4; ++kb) {
-            mbar_wait(w_free + kb, (wfree_ph >> kb) & 1); wfree_ph ^= 1u << kb;
-            if (leader) bulk_load_kblock(wbuf, image_of(next), kb, w_full + kb);
+          if (last_slot && next >= 0) {
+            mbar_wait(w_free + 3, (wfree_ph >> 3) & 1); wfree_ph ^= 1u << 3;
+            if (leader) bulk_load_kblock(wbuf, image_of(next), 3, w_full + 3);
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
     }
@@ -244,6 +356,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
     double lacc[TDB200_MAX_COLS];                          // per-lane loss sums (runtime column index: local memory)
 #pragma unroll
     for (int c = 0; c < TDB200_MAX_COLS; ++c) lacc[c] = 0.0;
+    float dbl_lane[kTcMaxOut];                             // last-layer bias gradient: value-channel seeds of this lane's points
+#pragma unroll
+    for (int v = 0; v < kTcMaxOut; ++v) dbl_lane[v] = 0.f;
     for (int it = 0; it < iters; ++it) {
       const int nslots = (2 * it + 1 < my_tiles) ? 2 : 1;
       if (slot < nslots) {
@@ -346,9 +461,21 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
           }
         }
       }
+        if (a.do_grad && lane < p_valid) {
+          const int pc = (lane / PH) * kTcPC + (lane % PH) * J;
+#pragma unroll
+          for (int v = 0; v < kTcMaxOut; ++v) if (v < n_out) dbl_lane[v] += Gus[v * kTcCols + pc];
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(op_done + slot);
       }
+    }
+#pragma unroll
+    for (int v = 0; v < kTcMaxOut; ++v) {
+      float t = dbl_lane[v];
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+      if (lane == 0) (sbase + kSOffDbl)[slot * kTcMaxOut + v] = t;
     }
     if (slot == 0)
       for (int c = 0; c < ncols; ++c) lossT[lane * TDB200_MAX_COLS + c] = lacc[c];
@@ -364,7 +491,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
     const int actA = (part >> 1) * kTcActBlock + n * 32 + ((((part & 1) * 2) ^ (n & 3)) << 3);       // columns 0..7
     const int actB = (part >> 1) * kTcActBlock + n * 32 + ((((part & 1) * 2 + 1) ^ (n & 3)) << 3);   // columns 8..15
     float w0[4] = {0.f, 0.f, 0.f, 0.f}, wl[kTcMaxOut];
-    float dw0_acc[4] = {0.f, 0.f, 0.f, 0.f}, dw0_dir[3] = {0.f, 0.f, 0.f}, dwl_acc[kTcMaxOut], dbl_acc = 0.f;
+    float dw0_acc[4] = {0.f, 0.f, 0.f, 0.f}, dw0_dir[3] = {0.f, 0.f, 0.f}, dwl_acc[kTcMaxOut];
     float db_acc[kTcsMaxMma + 1];                        // indexed by a runtime layer: lives in local memory (one
 #pragma unroll                                           // access per layer and tile)
     for (int l = 0; l <= kTcsMaxMma; ++l) db_acc[l] = 0.f;
@@ -382,7 +509,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
     for (int i = 0; i < 3; ++i) w0d[i] = i < ND ? w0[dir_axis[i]] : 0.f;
     uint32_t d_ph = 0, done_ph = 0, up_ph = 0;            // parity bits (per slot) of d_full, op_done; of up_free
 
-    auto xbuf_of = [&](int slot, int it) { return sbase + kSOffX + (slot * 2 + (it & 1)) * kTcMaxPts * 4; };
+    auto xbuf_of = [&](int slot, int it) { return sbase + kSOffX + (slot * 3 + it % 3) * kTcMaxPts * 4; };   // three deep
     auto load_points = [&](int it) {                     // points of both slots of iteration `it` (asynchronous)
       for (int slot = 0; slot < 2; ++slot) {
         const int tile = tile_of(it, slot);
@@ -525,29 +652,37 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
       return reinterpret_cast<float4*>(x.zsave + ((((size_t)blockIdx.x * 2 + slot) * NM + (l - 1)) * kTsEpi + tid) * 16);
     };
 
+    // layer 0 (K = d) of the slot's tile of iteration it_: thread-local, then the operand image goes to the MMA warp
+    auto fwd0 = [&](int it_, int slot) {
+      const float* xs = xbuf_of(slot, it_);
+      float z[16], y[16];
+#pragma unroll
+      for (int p = 0; p < PH; ++p) {
+        const float4 x4 = *reinterpret_cast<const float4*>(xs + (part * PH + p) * 4);
+        z[p * J] = fmaf(w0[0], x4.x, fmaf(w0[1], x4.y, fmaf(w0[2], x4.z, fmaf(w0[3], x4.w, bias0))));
+      }
+      jets_fwd(z, true, y);
+      if (live) store_act(slot, y);
+      if (a.do_grad) stream_rows(x.ys, tile_of(it_, slot), y);
+      hand_over(slot);
+    };
+    // With the backward sweep, layer 0 of iteration it + 1 is computed in the TAIL of iteration it, right after the slot's
+    // last accumulator has been read (its GEMM then runs behind the thread-local backward of layer 0 and the other slot's
+    // tail instead of in front of an idle epilogue).  Forward-only launches keep it at the head of the iteration.
+    const bool pipelined = a.do_grad != 0;
     if (iters > 0) load_points(0);
     for (int it = 0; it < iters; ++it) {
       const int nslots = (2 * it + 1 < my_tiles) ? 2 : 1;
+#ifdef TDB_TC_TIMING
+      tr_on = a.dbg && blockIdx.x == 0 && it == 40 && tid == 0;
+#endif
       TSMARK(11);
-      asm volatile("cp.async.wait_all;" ::: "memory");
-      epi_sync();                                         // this iteration's points are visible
-      if (it + 1 < iters) load_points(it + 1);
-      TSMARK(0);
-
-      // ---- layer 0 (K = d): thread-local ---------------------------------------------------------------
-      for (int slot = 0; slot < nslots; ++slot) {
-        const float* xs = xbuf_of(slot, it);
-        float z[16], y[16];
-#pragma unroll
-        for (int p = 0; p < PH; ++p) {
-          const float4 x4 = *reinterpret_cast<const float4*>(xs + (part * PH + p) * 4);
-          z[p * J] = fmaf(w0[0], x4.x, fmaf(w0[1], x4.y, fmaf(w0[2], x4.z, fmaf(w0[3], x4.w, bias0))));
-        }
-        jets_fwd(z, true, y);
-        if (live) store_act(slot, y);
-        if (a.do_grad) stream_rows(x.ys, tile_of(it, slot), y);
-        hand_over(slot);
-        TSMARK(1);
+      if (it == 0 || !pipelined) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        epi_sync();                                       // this iteration's points are visible
+        if (it + 1 < iters) load_points(it + 1);
+        TSMARK(0);
+        for (int slot = 0; slot < nslots; ++slot) { fwd0(it, slot); TSMARK(1); }
       }
       // ---- W x W layers 1 .. NM - 1: GEMM (MMA warp) + tanh-jet epilogue --------------------------------
       for (int l = 1; l < NM; ++l) {
@@ -610,11 +745,6 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
         jets_fwd(z, false, y);
         mbar_wait(op_done + slot, (done_ph >> slot) & 1); done_ph ^= 1u << slot;
         TSMARK(6);
-        if (tid < n_out) {
-          float sacc = 0.f;
-          for (int p = 0; p < P; ++p) sacc += Gus[tid * kTcCols + (p / PH) * kTcPC + (p % PH) * J];
-          dbl_acc += sacc;
-        }
         float gy[16], gz[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) gy[j] = 0.f;
@@ -668,12 +798,21 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
         }
       }
       // ---- backward of layer 0 (thread-local) --------------------------------------------------------------
+      const bool has_next = it + 1 < iters;
+      const int nslots_next = (2 * it + 3 < my_tiles) ? 2 : 1;
+      if (has_next) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        epi_sync();                                       // points of iteration it + 1 are visible; buffer (it + 2) % 3 is free
+        if (it + 2 < iters) load_points(it + 2);
+        TSMARK(0);
+      }
       for (int slot = 0; slot < nslots; ++slot) {
         const float* xs = xbuf_of(slot, it);
         float z[16], gy[16], gz[16], g0[PH];
         wait_d(slot);
         TSMARK(10);
         load_d(slot, gy);
+        if (has_next && slot < nslots_next) { fwd0(it + 1, slot); TSMARK(1); }
 #pragma unroll
         for (int p = 0; p < PH; ++p) {
           const float4 x4 = *reinterpret_cast<const float4*>(xs + (part * PH + p) * 4);
@@ -720,7 +859,6 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
         for (int ax = 0; ax < d; ++ax) put(my_grad + a.w_off[0] + n * d + ax, NM + 1 + ax);
         for (int v = 0; v < n_out; ++v) put(my_grad + a.w_off[L - 1] + v * W + n, NM + 5 + v);
       }
-      if (tid < n_out) { float* q = my_grad + a.b_off[L - 1] + tid; *q = acc ? *q + dbl_acc : dbl_acc; }
     }
   }
   tc_fence_before();
@@ -729,6 +867,11 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
   {
     const bool acc = !x.zero_partials;
     const tdb200_segment& sg = *segS;
+    if (a.do_grad && tid < n_out) {
+      float* q = my_grad + a.b_off[L - 1] + tid;
+      const float t = (sbase + kSOffDbl)[tid] + (sbase + kSOffDbl)[kTcMaxOut + tid];
+      *q = acc ? *q + t : t;
+    }
     if (a.do_grad && tid < a.n_cparams) {
       float* q = my_grad + a.n_net_params + tid;
       *q = acc ? *q + (sbase + kSOffCg)[tid] : (sbase + kSOffCg)[tid];
@@ -764,10 +907,27 @@ static cudaError_t launch_tcs_sig(const JetArgs& a, const TcsArgs& x, int grid, 
     SIGS(TDB_TCS_GROUP_CASE)                                                                                    \
     return cudaErrorInvalidValue;                                                                               \
   }
+// Tensor-memory budget (512 columns): two 64-column accumulators | saved jets (TM variant: (NM - 1) layers x 2 slots x
+// 16 Q columns) | weights (columns 304 .. 511 when x.w_in_tmem).  Measured (wave / Burgers / Navier-Stokes, 10^6 points):
+// weights AND saved jets in tensor memory 6.96 / 5.26 ms (shared-memory weights 7.06 / 5.35); where both do not fit
+// ((W x W layers - 1) * Q > 5) the saved jets win: Navier-Stokes 25.4 ms with saved jets in TMEM + shared-memory weights,
+// 27.0 ms the other way round.  Nets too deep for either ((NM - 1) * Q > 12) keep their saved jets in the L2 scratch and the
+// weights in tensor memory.  TDB200_TCS_W_SMEM=1 / TDB200_TCS_NO_TM=1 force the shared-memory / scratch forms.
+inline bool tcs_pick(const JetArgs& a, int q, TcsArgs& x) {
+  const int regions = (a.n_layers - 3) * q;
+  const bool no_tm = getenv("TDB200_TCS_NO_TM") != nullptr, w_smem = getenv("TDB200_TCS_W_SMEM") != nullptr;
+  const bool both = regions * 32 <= 512 - 128 - 2 * kTcWRows;
+  if (!no_tm && !w_smem && both) { x.w_in_tmem = 1; return true; }
+  if (!no_tm && regions <= 12) { x.w_in_tmem = 0; return true; }
+  x.w_in_tmem = w_smem ? 0 : 1;
+  return false;
+}
 #define TDB_TCS_GROUP_CASE(A, B, Cc)                                                         \
-  if (o0 == A && o1 == B && o2 == Cc)                                                        \
-    return ((a.n_layers - 3) * ((jet_tc_columns_per_part(A, B, Cc) + 3) / 4) <= 12 && !getenv("TDB200_TCS_NO_TM"))  \
-               ? launch_tcs_sig<A, B, Cc, true>(a, x, grid, s)                                                        \
-               : launch_tcs_sig<A, B, Cc, false>(a, x, grid, s);
+  if (o0 == A && o1 == B && o2 == Cc) {                                                      \
+    TcsArgs xx = x;                                                                          \
+    return tcs_pick(a, (jet_tc_columns_per_part(A, B, Cc) + 3) / 4, xx)                      \
+               ? launch_tcs_sig<A, B, Cc, true>(a, xx, grid, s)                              \
+               : launch_tcs_sig<A, B, Cc, false>(a, xx, grid, s);                            \
+  }
 
 }  // namespace tdb
