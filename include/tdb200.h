@@ -148,6 +148,15 @@ int tdb200_loss_grad(tdb200_plan* plan, const float* const* params_dev, float* o
 int tdb200_eval_fields(tdb200_plan* plan, const float* const* params_dev, float* fields_dev, float* out_dev,
                        void* stream);
 
+/* Per-residual Jacobian rows (replaces the loop of one torch.autograd.grad per residual in
+ * tedeous/optimizers/ngd.py:57-77 `gram_factory.jacobian`): row r of rows_dev[n_groups(segment)][n_params_pad] becomes
+ * d field[r, col] / d params for the rows of one segment (0 = the interior operator rows, then the boundary segments in
+ * plan order) and one residual column; the first tdb200_plan_n_params floats of a row are in the order of the flat
+ * gradient, the pad is zero.  J v and J^T J are then dense products of this matrix.  fp32 SIMT kernel, one row per tile. */
+int64_t tdb200_plan_n_params_pad(const tdb200_plan* plan);
+int tdb200_jacobian_rows(tdb200_plan* plan, const float* const* params_dev, int32_t segment, int32_t col,
+                         float* rows_dev, void* stream);
+
 void tdb200_plan_destroy(tdb200_plan* plan);
 
 /* ---- mat mode (tedeous/derivative.py:135-323): grid-stencil residual + adjoint --------------------- */

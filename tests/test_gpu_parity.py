@@ -736,3 +736,88 @@ def test_mini_batches_match_reference(cuda_default):
     m2 = tdb.Model(net2.to('cuda:0'), prob2.domain, prob2.equation, prob2.conditions, batch_size=64)
     m2.compile('NN', **prob2.compile_kwargs)
     assert float(m2.solution_cls.evaluate()[0]) == pytest.approx(float(g2['loss']), rel=LOSS_RTOL)
+
+
+@pytest.mark.parametrize('name', ['kdv_autograd', 'navier_stokes_autograd', 'burgers_NN_small', 'wave_autograd'])
+def test_residual_jacobian_rows(name, cuda_default):
+    """per-residual Jacobian rows (tdb200_jacobian_rows) against torch autograd through the oracle - sampled
+    rows one by one (what NGD.gram_factory does, tedeous/optimizers/ngd.py:57-77), J^T c against one reverse sweep, and
+    J v against the directional derivative of the oracle's residuals."""
+    g = load_golden(name, 'float64')
+    prob, net, sol = fused(name, g['weights'])
+    j_op, j_bnd = sol.residual_jacobian()
+    op, bval = sol.op, sol.bval
+    assert j_op.shape == (op.numel(), sol._plan.n_params) and j_bnd.shape == (bval.numel(), sol._plan.n_params)
+    j_op, j_bnd = j_op.double().cpu(), j_bnd.double().cpu()
+    gen = torch.Generator(device='cpu').manual_seed(11)
+    rows_op = torch.randint(0, j_op.shape[0], (6,), generator=gen, device='cpu').tolist()
+    rows_b = torch.randint(0, j_bnd.shape[0], (6,), generator=gen, device='cpu').tolist()
+    c_op = torch.randn(j_op.shape[0], generator=gen, dtype=torch.float64, device='cpu')
+    c_b = torch.randn(j_bnd.shape[0], generator=gen, dtype=torch.float64, device='cpu')
+    v = torch.randn(j_op.shape[1], generator=gen, dtype=torch.float64, device='cpu')
+    jv_op, jv_b = sol.residual_jvp(v)
+    torch.set_default_device('cpu')
+    try:
+        osol, _, _, _ = oracle_eval(name, 'float64', g['weights'])
+        osol.evaluate()
+        params = list(osol.model.parameters())
+        r_op, r_b = osol.op.reshape(-1), (osol.bval - osol.true_bval).reshape(-1)
+
+        def flat_grad(scalar):
+            gs = torch.autograd.grad(scalar, params, retain_graph=True, allow_unused=True)
+            return torch.cat([torch.zeros_like(p).reshape(-1) if x is None else x.reshape(-1) for x, p in zip(gs, params)])
+        nn_mode = prob.mode == 'NN'
+        tol = 5e-3 if nn_mode else 2e-4
+        for r in rows_op:
+            ref = flat_grad(r_op[r])
+            assert torch.linalg.norm(j_op[r] - ref) <= tol * max(float(torch.linalg.norm(ref)), 1e-12)
+        for r in rows_b:
+            ref = flat_grad(r_b[r])
+            assert torch.linalg.norm(j_bnd[r] - ref) <= tol * float(torch.linalg.norm(ref)) + 1e-12
+        ref = flat_grad((c_op * r_op).sum() + (c_b * r_b).sum())
+        got = j_op.T @ c_op + j_bnd.T @ c_b
+        assert torch.linalg.norm(got - ref) <= tol * float(torch.linalg.norm(ref))
+        # J v: central difference of the oracle's residuals along v (fp64, step 1e-6)
+        base = [p.detach().clone() for p in params]
+
+        def residuals_at(eps):
+            off = 0
+            with torch.no_grad():
+                for p, b in zip(params, base):
+                    p.copy_(b + eps * v[off:off + p.numel()].reshape(p.shape))
+                    off += p.numel()
+            osol.evaluate()
+            return osol.op.reshape(-1).detach().clone(), (osol.bval - osol.true_bval).reshape(-1).detach().clone()
+        (a0, b0), (a1, b1) = residuals_at(-1e-6), residuals_at(1e-6)
+        fd_op, fd_b = (a1 - a0) / 2e-6, (b1 - b0) / 2e-6
+    finally:
+        torch.set_default_device('cuda:0')
+    assert torch.linalg.norm(jv_op.double().cpu() - fd_op) <= max(tol, 1e-3) * float(torch.linalg.norm(fd_op))
+    assert torch.linalg.norm(jv_b.double().cpu() - fd_b) <= max(tol, 1e-3) * float(torch.linalg.norm(fd_b)) + 1e-12
+    # the plain loss path is untouched
+    loss, _ = sol.evaluate()
+    assert float(loss) == pytest.approx(float(g['loss']), rel=LOSS_RTOL)
+
+
+def test_ngd_step_reduces_loss(cuda_default):
+    """Model.train with the natural-gradient optimiser (tedeous/optimizers/ngd.py) on the per-residual Jacobian rows of
+    the fused path: G = J^T J / n is symmetric and its pseudo-inverse solve reproduces right-hand sides in its range and three epochs reduce the loss (grid line search: never uphill)."""
+    prob = problems.ZOO['wave_autograd'](tdb, 'float32')
+    torch.manual_seed(3)
+    net = torch.nn.Sequential(torch.nn.Linear(2, 16), torch.nn.Tanh(), torch.nn.Linear(16, 16), torch.nn.Tanh(),
+                              torch.nn.Linear(16, 1)).to('cuda:0')
+    model = tdb.Model(net, prob.domain, prob.equation, prob.conditions)
+    model.compile(prob.mode, **prob.compile_kwargs)
+    sol = model.solution_cls
+    loss0, _ = sol.evaluate()
+    from torch_de_solver_b200.optimizers.ngd import NGD
+    j_op, j_bnd = sol.residual_jacobian()
+    G = NGD.gram(j_op) + NGD.gram(j_bnd)
+    assert torch.allclose(G, G.T, atol=1e-6 * float(G.abs().max()))
+    b = G @ torch.randn(G.shape[0], device=G.device)                  # a right-hand side in the range of G
+    x = NGD.pinv_solve(G.double(), b.double(), tol=1e-10 * float(torch.linalg.matrix_norm(G.double(), 2)))
+    assert torch.linalg.norm(G.double() @ x - b.double()) <= 1e-4 * torch.linalg.norm(b.double())
+    model.train(tdb.Optimizer('NGD', {'grid_steps_number': 20}), epochs=4, info_string_every=None)
+    loss1, _ = sol.evaluate()
+    print('NGD: loss', float(loss0), '->', float(loss1))
+    assert torch.isfinite(loss1).all() and float(loss1) < float(loss0)

@@ -31,7 +31,7 @@ MAT_BC_DTYPE = np.dtype([('n_rows', '<i8'), ('cell_off', '<i8'), ('tgt_off', '<i
 EXPORTS = [
     'tdb200_plan_create', 'tdb200_plan_set_points', 'tdb200_plan_set_slots', 'tdb200_plan_set_impl', 'tdb200_plan_set_row_weights', 'tdb200_plan_set_field_seeds',
     'tdb200_plan_out_size', 'tdb200_plan_n_params', 'tdb200_plan_n_fields', 'tdb200_plan_launches_per_call', 'tdb200_plan_kernel_path', 'tdb200_comm_unique_id', 'tdb200_comm_create', 'tdb200_comm_destroy', 'tdb200_plan_set_comm',
-    'tdb200_loss_grad', 'tdb200_eval_fields', 'tdb200_plan_destroy',
+    'tdb200_loss_grad', 'tdb200_eval_fields', 'tdb200_plan_n_params_pad', 'tdb200_jacobian_rows', 'tdb200_plan_destroy',
     'tdb200_mat_plan_create', 'tdb200_mat_plan_set_coeffs', 'tdb200_mat_plan_set_bcs', 'tdb200_mat_loss_grad', 'tdb200_mat_eval_fields',
     'tdb200_mat_plan_out_size', 'tdb200_mat_plan_launches_per_call', 'tdb200_mat_plan_kernel_kind', 'tdb200_mat_plan_set_row_window',
     'tdb200_mat_plan_set_timing', 'tdb200_mat_plan_stencil_ms', 'tdb200_mat_time_stencil',
@@ -60,7 +60,8 @@ def load():
     lib.tdb200_plan_set_impl.argtypes = [vp, i32]
     lib.tdb200_plan_set_row_weights.argtypes = [vp, vp]
     lib.tdb200_plan_set_field_seeds.argtypes = [vp, vp]
-    for name in ('tdb200_plan_out_size', 'tdb200_plan_n_params', 'tdb200_plan_n_fields', 'tdb200_mat_plan_out_size'):
+    for name in ('tdb200_plan_out_size', 'tdb200_plan_n_params', 'tdb200_plan_n_fields', 'tdb200_mat_plan_out_size',
+                 'tdb200_plan_n_params_pad'):
         getattr(lib, name).argtypes = [vp]
         getattr(lib, name).restype = i64
     lib.tdb200_plan_launches_per_call.argtypes = [vp]
@@ -78,6 +79,7 @@ def load():
     lib.tdb200_mat_plan_set_row_window.argtypes = [vp, i32, i32]
     lib.tdb200_loss_grad.argtypes = [vp, vp, vp, vp]
     lib.tdb200_eval_fields.argtypes = [vp, vp, vp, vp, vp]
+    lib.tdb200_jacobian_rows.argtypes = [vp, vp, i32, i32, vp, vp]
     lib.tdb200_plan_destroy.argtypes = [vp]
     lib.tdb200_plan_destroy.restype = None
     lib.tdb200_mat_plan_create.argtypes = [C.POINTER(MatDesc), vp, i32, vp, vp, vp, i32, vp, i32, vp, i32,

@@ -731,6 +731,43 @@ int tdb200_eval_fields(tdb200_plan* p, const float* const* params_dev, float* fi
   return run(p, params_dev, fields_dev, out_dev, 0, stream);
 }
 
+int64_t tdb200_plan_n_params_pad(const tdb200_plan* p) { return p ? p->args.n_params_pad : 0; }
+
+int tdb200_jacobian_rows(tdb200_plan* p, const float* const* params, int32_t segment, int32_t col, float* rows_dev,
+                         void* stream) {
+  if (!p || !params || !rows_dev) return fail(TDB200_ERR_INVALID, "null argument");
+  if (!p->pts) return fail(TDB200_ERR_INVALID, "tdb200_plan_set_points was not called");
+  if (segment < 0 || segment >= (int)p->segs.size()) return fail(TDB200_ERR_INVALID, "segment out of range");
+  if (col < 0 || col >= p->segs[segment].n_cols) return fail(TDB200_ERR_INVALID, "residual column out of range");
+  if (p->segs[segment].n_groups > 0x7fffffffLL) return fail(TDB200_ERR_INVALID, "too many rows");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CU(cudaSetDevice(p->device));
+  tdb::PackArgs pk{};
+  const tdb::JetArgs& a = p->args;
+  pk.n_layers = a.n_layers;
+  for (int l = 0; l <= a.n_layers; ++l) pk.widths[l] = a.widths[l];
+  for (int l = 0; l < a.n_layers; ++l) {
+    pk.w_off[l] = a.w_off[l];
+    pk.b_off[l] = a.b_off[l];
+    pk.W[l] = params[2 * l];
+    pk.b[l] = params[2 * l + 1];
+    if (!pk.W[l] || !pk.b[l]) return fail(TDB200_ERR_INVALID, "null parameter pointer");
+  }
+  pk.n_net_params = a.n_net_params;
+  pk.n_cparams = a.n_cparams;
+  for (int i = 0; i < a.n_cparams; ++i) pk.c[i] = params[2 * a.n_layers + i];
+  pk.arena = p->arena; pk.arena_t = p->arena_t; pk.img_f = p->img_f; pk.img_b = p->img_b;
+  CU(tdb::launch_pack_params(pk, s));
+  tdb::JetArgs call = a;
+  call.fields = nullptr; call.row_weight = nullptr; call.field_seed = nullptr; call.dbg = nullptr;
+  call.do_grad = 1;
+  call.jac_rows = rows_dev; call.jac_seg = segment; call.jac_col = col;
+  call.n_tiles = (int)p->segs[segment].n_groups;
+  if (call.n_tiles == 0) return TDB200_OK;
+  CU(tdb::launch_jet_simt(call, call.n_tiles < p->grid ? call.n_tiles : p->grid, s));
+  return TDB200_OK;
+}
+
 void tdb200_plan_destroy(tdb200_plan* p) {
   if (!p) return;
   cudaSetDevice(p->device);

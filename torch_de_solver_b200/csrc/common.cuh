@@ -53,6 +53,8 @@ struct JetArgs {
   const float* field_seed;             // optional cotangents of every field value (layout of `fields`): the gradient
                                        // becomes the vector-Jacobian product sum seed * d field / d theta
   int do_grad;
+  float* jac_rows;                     // Jacobian-rows mode of the SIMT kernel: [n_groups of segment jac_seg][n_params_pad]
+  int jac_seg, jac_col;
   long long* dbg;                      // optional [gridDim.x][16] phase cycle counters (TDB200_TC_TIMING=1)
 };
 

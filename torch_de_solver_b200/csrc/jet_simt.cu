@@ -211,12 +211,16 @@ __global__ void __launch_bounds__(kThreads, 1) jet_simt_kernel(const JetArgs a) 
   const int tid = threadIdx.x;
   const int L = a.n_layers;
   const int n_out = a.widths[L];
-  float* const my_grad = a.part_grad + (size_t)blockIdx.x * a.n_params_pad;
+  // Jacobian-rows mode (a.jac_rows != nullptr, tdb200_jacobian_rows): every tile holds ONE group of segment a.jac_seg and
+  // accumulates into its own output row, seeded with 1 on residual column a.jac_col: row r = d field[r, col] / d theta
+  // (the per-residual Jacobian the reference's NGD builds with one autograd.grad per point, optimizers/ngd.py:57-77).
+  const bool jac = a.jac_rows != nullptr;
+  float* my_grad = a.part_grad + (size_t)blockIdx.x * a.n_params_pad;
   float* const my_scratch = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;
   const size_t save_stride = (size_t)a.wmax * kRows;       // one saved [w][128] block
 
   // zero this CTA's partials
-  if (a.do_grad)
+  if (a.do_grad && !jac)
     for (int i = tid; i < a.n_params_pad; i += kThreads) my_grad[i] = 0.f;
   if (tid < 32) sm.lossS[tid] = 0.0;
   if (tid < kMaxCParams) sm.cgS[tid] = 0.f;
@@ -230,7 +234,8 @@ __global__ void __launch_bounds__(kThreads, 1) jet_simt_kernel(const JetArgs a) 
 
   int seg_i = 0;
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    while (tile >= a.seg_tile_begin[seg_i + 1]) ++seg_i;
+    if (jac) seg_i = a.jac_seg;
+    else while (tile >= a.seg_tile_begin[seg_i + 1]) ++seg_i;
     const tdb200_segment& sg = a.segs[seg_i];
     const int K = sg.K, M = sg.M, ncols = sg.n_cols, ndirs = sg.n_dirs;
     int J = 1;
@@ -241,8 +246,12 @@ __global__ void __launch_bounds__(kThreads, 1) jet_simt_kernel(const JetArgs a) 
     const int P = ((kRows / J) / step) * step;
     const int G = P / K;
     const int R = J * P;
-    const long long g_first = (long long)(tile - a.seg_tile_begin[seg_i]) * G;
-    const int g_valid = (int)min((long long)G, sg.n_groups - g_first);
+    const long long g_first = jac ? (long long)tile : (long long)(tile - a.seg_tile_begin[seg_i]) * G;
+    const int g_valid = jac ? 1 : (int)min((long long)G, sg.n_groups - g_first);
+    if (jac) {
+      my_grad = a.jac_rows + (size_t)tile * a.n_params_pad;
+      for (int i = tid; i < a.n_params_pad; i += kThreads) my_grad[i] = 0.f;      // visible after the barrier below
+    }
     const int p_valid = g_valid * K;
     const int d = a.d;
 
@@ -377,7 +386,8 @@ __global__ void __launch_bounds__(kThreads, 1) jet_simt_kernel(const JetArgs a) 
         const int slot = sg.col_slot[col];
         const float rw = (a.row_weight && seg_i == 0) ? __ldg(a.row_weight + row) : 1.f;   // causal-loss weight (no grad)
         atomicAdd(&sm.lossS[slot], (double)rw * (double)res * (double)res);
-        sm.rS[col * G + g] = a.field_seed ? __ldg(a.field_seed + sg.field_off + row * ncols + col)
+        sm.rS[col * G + g] = jac ? (col == a.jac_col ? 1.f : 0.f)
+                           : a.field_seed ? __ldg(a.field_seed + sg.field_off + row * ncols + col)
                                           : 2.f * __ldg(a.slot_scale + slot) * rw * res;
       }
       if (a.do_grad) {
@@ -526,12 +536,16 @@ __global__ void __launch_bounds__(kThreads, 1) jet_simt_kernel(const JetArgs a) 
       __syncthreads();
       float* tmp = cur; cur = oth; oth = tmp;
     }
+    if (jac) {                                              // coefficient-parameter entries of this row
+      __syncthreads();
+      if (tid < a.n_cparams) { my_grad[a.n_net_params + tid] = sm.cgS[tid]; sm.cgS[tid] = 0.f; }
+    }
   }
 
   // ---- flush per-CTA scalars ------------------------------------------------------------------------
   __syncthreads();
-  if (tid < a.n_slots) a.part_loss[(size_t)blockIdx.x * a.n_slots + tid] = sm.lossS[tid];
-  if (a.do_grad && tid < a.n_cparams) my_grad[a.n_net_params + tid] = sm.cgS[tid];
+  if (!jac && tid < a.n_slots) a.part_loss[(size_t)blockIdx.x * a.n_slots + tid] = sm.lossS[tid];
+  if (a.do_grad && !jac && tid < a.n_cparams) my_grad[a.n_net_params + tid] = sm.cgS[tid];
 }
 
 cudaError_t launch_jet_simt(const JetArgs& a, int grid, cudaStream_t s) {

@@ -1,13 +1,16 @@
-"""Name -> torch optimiser map (tedeous/optimizers/optimizer.py:12-73).  The optimisers themselves are
-torch's; PSO / CSO / NGD / NNCG are research optimisers outside the hot path and are not
-provided."""
+"""Name -> optimiser map (tedeous/optimizers/optimizer.py:12-73).  Adam / AdamW / SGD / LBFGS / RMSprop are torch's (the
+first three also have a fused CUDA-graph step, optimizers/fused.py); NGD runs on the per-residual Jacobian rows of the
+fused path (optimizers/ngd.py).  PSO / CSO / NNCG are research optimisers outside the hot path (SURVEY 2
+#13) and are not provided."""
 from typing import Union
 
 import torch
 from torch.optim.lr_scheduler import CosineAnnealingWarmRestarts, ExponentialLR
 
+from .ngd import NGD
+
 _TORCH = {'Adam': torch.optim.Adam, 'AdamW': torch.optim.AdamW, 'SGD': torch.optim.SGD,
-          'LBFGS': torch.optim.LBFGS, 'RMSprop': torch.optim.RMSprop}
+          'LBFGS': torch.optim.LBFGS, 'RMSprop': torch.optim.RMSprop, 'NGD': NGD}
 
 
 class Optimizer:

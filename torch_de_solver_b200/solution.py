@@ -219,6 +219,18 @@ class FusedPlan:
                                                   out.data_ptr(), stream), 'tdb200_eval_fields')
         return fields, out
 
+    def jacobian_rows(self, segment: int, col: int = 0) -> torch.Tensor:
+        """Per-residual Jacobian of one segment's residual column: [n_groups, n_params], row r = d field[r, col] / d theta
+        in the parameter order of the flat gradient (tdb200_jacobian_rows; the reference's NGD obtains these rows with
+        one torch.autograd.grad per residual, tedeous/optimizers/ngd.py:57-77)."""
+        n = self.ir.segments[segment].n_groups
+        pad = int(self.lib.tdb200_plan_n_params_pad(self.handle))
+        rows = torch.empty(max(n, 1), pad, dtype=torch.float32, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _native.check(self.lib.tdb200_jacobian_rows(self.handle, self._param_ptrs(), segment, col, rows.data_ptr(),
+                                                    stream), 'tdb200_jacobian_rows')
+        return rows[:n, :self.n_params]
+
     def __del__(self):
         try:
             if getattr(self, 'handle', None):
@@ -628,6 +640,36 @@ class Solution:
             raise UnsupportedProblem('per-point fields are not gathered across ranks')
         params = self._plan.ir.net.param_tensors()
         return _assemble_fields(self._plan, _FusedFields.apply(self._plan, *params))
+
+    def residual_jacobian(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(J_op [N * n_eq, P], J_bnd [max_len * n_types, P]): the Jacobians of `op.reshape(-1)` and of
+        `(bval - true_bval).reshape(-1)` with respect to the flat parameter vector (`parameters_to_vector` order; rows
+        of the zero padding of `bval` are zero) - what `NGD.gram_factory` (tedeous/optimizers/ngd.py:57-77) assembles
+        from one `autograd.grad` per residual.  One SIMT launch per (segment, residual column)."""
+        if self.mode == 'mat':
+            raise UnsupportedProblem('per-residual Jacobian rows are implemented for modes NN / autograd')
+        if self._shard[1] > 1:
+            raise UnsupportedProblem('per-residual Jacobian rows are not gathered across ranks')
+        if getattr(self, '_batching', False):
+            raise UnsupportedProblem('per-residual Jacobian rows with mini-batches')
+        plan, ir = self._plan, self._plan.ir
+        n_types, max_len, P = len(ir.bnd_types), max(ir.type_len), plan.n_params
+        j_op = None
+        j_bnd = torch.zeros(max_len, n_types, P, dtype=torch.float32, device=plan.device)
+        for si, s in enumerate(ir.segments):
+            if s.slots[0] < ir.n_eq:
+                cols = [plan.jacobian_rows(si, c) for c in range(len(s.cols))]
+                j_op = torch.stack(cols, dim=1).reshape(-1, P)               # row-major [N, n_eq] like op.reshape(-1)
+            else:
+                idx = s.row_index.to(plan.device)
+                j_bnd[idx, s.slots[0] - ir.n_eq] = plan.jacobian_rows(si, 0)
+        return j_op, j_bnd.reshape(-1, P)
+
+    def residual_jvp(self, v: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(J_op v, J_bnd v) for a flat parameter-space vector v: the directional derivative of every residual."""
+        j_op, j_bnd = self.residual_jacobian()
+        v = v.detach().to(j_op.device, torch.float32).reshape(-1)
+        return j_op @ v, j_bnd @ v
 
     @property
     def op(self) -> torch.Tensor:
