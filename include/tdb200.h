@@ -29,8 +29,8 @@ extern "C" {
 #define TDB200_MAX_DIRS 4
 #define TDB200_MAX_COLS 8
 #define TDB200_MAX_K 32
-#define TDB200_MAX_M 8
-#define TDB200_MAX_J 8
+#define TDB200_MAX_M 16
+#define TDB200_MAX_J 16
 #define TDB200_ROWS_PER_TILE 128
 
 typedef enum {
@@ -50,13 +50,17 @@ typedef struct {
   int64_t tgt_off;                       /* first float in `targets`, -1: zero targets */
   int64_t field_off;                     /* first float in the fields output */
   int32_t K, M, n_cols, n_dirs;
-  int32_t dir_axis[TDB200_MAX_DIRS];     /* jet directions: input axis ... */
+  int32_t dir_axis[TDB200_MAX_DIRS];     /* jet directions: input axis (-1: a general vector, see dir_vec) ... */
   int32_t dir_order[TDB200_MAX_DIRS];    /* ... and highest derivative order (1..4) */
   int32_t col_term_begin[TDB200_MAX_COLS];
   int32_t col_term_end[TDB200_MAX_COLS];
   int32_t col_slot[TDB200_MAX_COLS];     /* loss slot every residual column accumulates into */
   int32_t identity;
   int32_t comb_off;                      /* first float of this segment's [M][K*J] matrix in `comb` */
+  float dir_vec[TDB200_MAX_DIRS][4];     /* direction vectors (unit vector of dir_axis for a pure partial): channel k of
+                                            direction i is the k-th derivative ALONG dir_vec[i]; mixed partials such as
+                                            d2u/dxdy (tedeous/derivative.py:92-97 takes any axis list) are lowered on the
+                                            host to combinations of these (torch_de_solver_b200/plan.py lower_mixed) */
 } tdb200_segment;
 
 /* term = coeff * prod_f chan[f]^pow_f;  kind 0: immediate `coeff`, 1: per-row buffer coeffs[idx + row],

@@ -14,13 +14,14 @@ def _jets(model, pts, jet):
     out = model(pts)
     n_out = out.shape[1]
     chans = [out]
-    for axis, order in jet.dirs:
+    for i, (_, order) in enumerate(jet.dirs):
+        vec = torch.as_tensor(jet.vector(i, pts.shape[1]), dtype=pts.dtype)     # unit vector for a pure partial
         cur = out
         for _ in range(order):
             cols = []
             for v in range(n_out):
                 g, = torch.autograd.grad(cur[:, v].sum(), pts, create_graph=True)
-                cols.append(g[:, axis])
+                cols.append(g @ vec)
             cur = torch.stack(cols, 1)
             chans.append(cur)
     return torch.stack(chans, 1)

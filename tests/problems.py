@@ -406,6 +406,57 @@ def poisson_robin(api, dtype='float32', n=20, layers=(2, 32, 32, 1)):
                    init='xavier_b')
 
 
+# --- mixed partial derivatives (the reference differentiates along any axis list, tedeous/derivative.py:92-97) ---------
+def mixed_elliptic(api, dtype='float32', n=20, mode='autograd', layers=(2, 100, 100, 100, 1), h=0.01):
+    """u_xx + 1.5 u_xy + 2 u_yy - 0.5 u u_yx = f with a mixed-partial boundary operator: second-order mixed partials
+    next to the pure ones (directions x, y, x + y: the tensor-core signature (2, 2, 2))."""
+    dom = api.Domain()
+    dom.variable('x', [0, 1], n, dtype=dtype)
+    dom.variable('y', [0, 1], n, dtype=dtype)
+    bc = api.Conditions()
+    bc.dirichlet({'x': 0, 'y': [0, 1]}, value=lambda g: torch.sin(g[:, 1]))
+    bc.dirichlet({'x': 1, 'y': [0, 1]}, value=lambda g: torch.cos(g[:, 1]))
+    bc.dirichlet({'x': [0, 1], 'y': 0}, value=lambda g: g[:, 0])
+    if mode == 'autograd':
+        bc.operator({'x': [0, 1], 'y': 1}, operator={'d2u/dxdy': {'coeff': 1, 'term': [0, 1], 'pow': 1, 'var': 0},
+                                                     'u': {'coeff': 0.5, 'term': [None], 'pow': 1, 'var': 0}}, value=0.2)
+    else:
+        bc.dirichlet({'x': [0, 1], 'y': 1}, value=0.2)
+    eq = api.Equation()
+    eq.add({
+        'd2u/dx2': {'coeff': 1, 'term': [0, 0], 'pow': 1, 'var': 0},
+        'd2u/dxdy': {'coeff': 1.5, 'term': [0, 1], 'pow': 1, 'var': 0},
+        'd2u/dy2': {'coeff': 2, 'term': [1, 1], 'pow': 1, 'var': 0},
+        'u*d2u/dydx': {'coeff': -0.5, 'term': [[None], [1, 0]], 'pow': [1, 1], 'var': [0, 0]},
+        '-f': {'coeff': lambda g: -torch.sin(np.pi * g[:, 0]) * g[:, 1], 'term': [None], 'pow': 0},
+    })
+    kw = dict(lambda_operator=1, lambda_bound=10)
+    if mode == 'NN':
+        kw['h'] = h
+    return Problem(f'mixed_elliptic_{mode}', dom, bc, eq, mode, list(layers), kw, init='xavier_b')
+
+
+def mixed_bbm(api, dtype='float32', n=16, layers=(2, 32, 32, 1)):
+    """Benjamin-Bona-Mahony type equation u_t + u u_x - 0.05 u_xxt = 0: a THIRD-order mixed partial, and a second-order
+    mixed partial alone (u_xt, directions x + t and x - t), autograd mode."""
+    dom = api.Domain()
+    dom.variable('x', [0, 1], n, dtype=dtype)
+    dom.variable('t', [0, 1], n, dtype=dtype)
+    bc = api.Conditions()
+    bc.dirichlet({'x': [0, 1], 't': 0}, value=lambda g: torch.sin(np.pi * g[:, 0]))
+    bc.dirichlet({'x': 0, 't': [0, 1]}, value=0.)
+    bc.dirichlet({'x': 1, 't': [0, 1]}, value=0.)
+    eq = api.Equation()
+    eq.add({
+        'du/dt': {'coeff': 1, 'term': [1], 'pow': 1, 'var': 0},
+        'u*du/dx': {'coeff': 1, 'term': [[None], [0]], 'pow': [1, 1], 'var': [0, 0]},
+        '-0.05*d3u/dx2dt': {'coeff': -0.05, 'term': [0, 0, 1], 'pow': 1, 'var': 0},
+        '0.1*d2u/dxdt': {'coeff': 0.1, 'term': [0, 1], 'pow': 1, 'var': 0},
+    })
+    return Problem('mixed_bbm_autograd', dom, bc, eq, 'autograd', list(layers), dict(lambda_operator=1, lambda_bound=10),
+                   init='xavier_b')
+
+
 def trained(prob: Problem, steps: int) -> Problem:
     prob.train_steps = steps
     return prob
@@ -416,6 +467,9 @@ LARGE = ('wave_autograd_1e5', 'kdv_autograd_1e5', 'wave_autograd_3e5')
 
 ZOO: Dict[str, Callable] = {
     'poisson_robin_autograd': lambda api, dt: poisson_robin(api, dt),
+    'mixed_elliptic_autograd': lambda api, dt: mixed_elliptic(api, dt, mode='autograd'),
+    'mixed_elliptic_NN': lambda api, dt: mixed_elliptic(api, dt, n=16, mode='NN', layers=(2, 32, 32, 1)),
+    'mixed_bbm_autograd': lambda api, dt: mixed_bbm(api, dt),
     # ~10^5 points: the sizes at which the tensor-core kernels are chosen automatically (impl = 0)
     'wave_autograd_1e5': lambda api, dt: wave(api, dt, n=315, mode='autograd'),
     'kdv_autograd_1e5': lambda api, dt: kdv(api, dt, nx=399, nt=249, mode='autograd'),

@@ -156,7 +156,7 @@ int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_s
     int J = 1;
     if (sg.n_dirs < 0 || sg.n_dirs > TDB200_MAX_DIRS) { delete p; return fail(TDB200_ERR_INVALID, "n_dirs out of range"); }
     for (int i = 0; i < sg.n_dirs; ++i) {
-      if (sg.dir_order[i] < 1 || sg.dir_order[i] > 4 || sg.dir_axis[i] < 0 || sg.dir_axis[i] >= net->widths[0]) {
+      if (sg.dir_order[i] < 1 || sg.dir_order[i] > 4 || sg.dir_axis[i] < -1 || sg.dir_axis[i] >= net->widths[0]) {
         delete p; return fail(TDB200_ERR_INVALID, "bad jet direction");
       }
       J += sg.dir_order[i];

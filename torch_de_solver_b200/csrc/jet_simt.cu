@@ -202,6 +202,13 @@ __device__ __forceinline__ void gemm_wgrad_any(const float* g, const float* y, f
   else gemm_wgrad<8>(g, y, dst, Nd, Kd, R);
 }
 
+// first-order input of jet direction v after the first Linear layer: W0[n, :] . v (a column of W0 for a pure partial)
+__device__ __forceinline__ float dir_dot(const float* __restrict__ w0_row, const float* v, int d) {
+  float s = 0.f;
+  for (int ax = 0; ax < d; ++ax) s = fmaf(__ldg(w0_row + ax), v[ax], s);
+  return s;
+}
+
 // ------------------------------------------------------------------------------------------------
 // the fused kernel
 // ------------------------------------------------------------------------------------------------
@@ -283,7 +290,7 @@ __global__ void __launch_bounds__(kThreads, 1) jet_simt_kernel(const JetArgs a) 
           int c = 1;
           for (int i = 0; i < ndirs; ++i) {
             const int o = sg.dir_order[i];
-            float z[4] = {__ldg(W0 + n * d + sg.dir_axis[i]), 0.f, 0.f, 0.f}, y[4];
+            float z[4] = {dir_dot(W0 + n * d, sg.dir_vec[i], d), 0.f, 0.f, 0.f}, y[4];
             tanh_jet_fwd(f, z, o, y);
             for (int k = 0; k < o; ++k) {
               row[(c + k) * P + p] = y[k];
@@ -485,7 +492,7 @@ __global__ void __launch_bounds__(kThreads, 1) jet_simt_kernel(const JetArgs a) 
         for (int i = 0; i < ndirs; ++i) {
           const int o = sg.dir_order[i];
           float z[4] = {0.f, 0.f, 0.f, 0.f}, gy[4], gz[4];
-          if (t == 0) z[0] = __ldg(W0 + n * d + sg.dir_axis[i]);
+          if (t == 0) z[0] = dir_dot(W0 + n * d, sg.dir_vec[i], d);
           else for (int k = 0; k < o; ++k) z[k] = srow[(c + k) * P + p];
           for (int k = 0; k < o; ++k) gy[k] = row[(c + k) * P + p];
           g0 += tanh_jet_bwd(f, z, gy, o, gz);
@@ -511,8 +518,12 @@ __global__ void __launch_bounds__(kThreads, 1) jet_simt_kernel(const JetArgs a) 
           for (int p = 0; p < P; ++p) s = fmaf(row[p], sm.xS[p * 4 + ax], s);
           int c = 1;
           for (int i = 0; i < ndirs; ++i) {
-            if (sg.dir_axis[i] == ax)
-              for (int p = 0; p < P; ++p) s += row[c * P + p];
+            const float vx = sg.dir_vec[i][ax];                // d z1 / d W0[n][ax] = component ax of the direction
+            if (vx != 0.f) {
+              float sd = 0.f;
+              for (int p = 0; p < P; ++p) sd += row[c * P + p];
+              s = fmaf(vx, sd, s);
+            }
             c += sg.dir_order[i];
           }
           atomicAdd(my_grad + a.w_off[0] + idx, s);

@@ -448,11 +448,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
 
   const tdb200_segment& sg = *sm.segS;                  // shared-memory copy (set up above, visible after the sync)
   const int ncols = sg.n_cols;
-  int dir_axis[3] = {0, 0, 0};
-  for (int i = 0; i < ND; ++i) dir_axis[i] = sg.dir_axis[i];
   float w0d[3];                                         // first-layer weight along each jet direction
 #pragma unroll
-  for (int i = 0; i < 3; ++i) w0d[i] = i < ND ? w0[dir_axis[i]] : 0.f;
+  for (int i = 0; i < 3; ++i)
+    w0d[i] = i < ND ? fmaf(w0[0], sg.dir_vec[i][0], fmaf(w0[1], sg.dir_vec[i][1], fmaf(w0[2], sg.dir_vec[i][2], w0[3] * sg.dir_vec[i][3])))
+                      : 0.f;     // first-order input of direction i: W0[n, :] . v_i (column of W0 for a pure partial)
 
   if (tid == 0) bulk_load_image((sbase + kOffWHi), wimg, sm.wbar);          // W_1 for the first tile
 
@@ -845,7 +845,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_tc_kernel(const JetArgs a, 
     float* const stg = sbase + kOffWHi;                   // [4 parts][NMMA + 1 + 4 + kTcMaxOut][128]
     constexpr int kRowsStg = NMMA + 1 + 4 + kTcMaxOut;
     for (int i = 0; i < ND; ++i)                         // derivative-channel part of dW0, by jet direction
-      for (int ax = 0; ax < 4; ++ax) if (ax == dir_axis[i]) dw0_acc[ax] += dw0_dir[i];
+      for (int ax = 0; ax < 4; ++ax) dw0_acc[ax] = fmaf(dw0_dir[i], sg.dir_vec[i][ax], dw0_acc[ax]);
     {
       float* mine = stg + (part * kRowsStg) * 128 + n;
 #pragma unroll

@@ -502,11 +502,11 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
     for (int v = 0; v < kTcMaxOut; ++v) { wl[v] = (live && v < n_out) ? a.arena[a.w_off[L - 1] + v * W + n] : 0.f; dwl_acc[v] = 0.f; }
     const tdb200_segment& sg = *segS;
     const int ncols = sg.n_cols;
-    int dir_axis[3] = {0, 0, 0};
-    for (int i = 0; i < ND; ++i) dir_axis[i] = sg.dir_axis[i];
     float w0d[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) w0d[i] = i < ND ? w0[dir_axis[i]] : 0.f;
+    for (int i = 0; i < 3; ++i)
+      w0d[i] = i < ND ? fmaf(w0[0], sg.dir_vec[i][0], fmaf(w0[1], sg.dir_vec[i][1], fmaf(w0[2], sg.dir_vec[i][2], w0[3] * sg.dir_vec[i][3])))
+                        : 0.f;     // first-order input of direction i: W0[n, :] . v_i (column of W0 for a pure partial)
     uint32_t d_ph = 0, done_ph = 0, up_ph = 0;            // parity bits (per slot) of d_full, op_done; of up_free
 
     auto xbuf_of = [&](int slot, int it) { return sbase + kSOffX + (slot * 3 + it % 3) * kTcMaxPts * 4; };   // three deep
@@ -839,7 +839,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
       float* const stg = sbase + kSOffW;                  // [4 parts][NM + 1 + 4 + kTcMaxOut][128]
       const int rows_stg = NM + 1 + 4 + kTcMaxOut;
       for (int i = 0; i < ND; ++i)
-        for (int ax = 0; ax < 4; ++ax) if (ax == dir_axis[i]) dw0_acc[ax] += dw0_dir[i];
+        for (int ax = 0; ax < 4; ++ax) dw0_acc[ax] = fmaf(dw0_dir[i], sg.dir_vec[i][ax], dw0_acc[ax]);
       float* mine = stg + (part * rows_stg) * 128 + n;
       for (int l = 0; l <= NM; ++l) mine[l * 128] = db_acc[l];
 #pragma unroll

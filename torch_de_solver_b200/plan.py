@@ -36,8 +36,8 @@ MAX_DIRS = 4
 MAX_ORDER = 4
 MAX_COLS = 8
 MAX_K = 32
-MAX_M = 8
-MAX_J = 8
+MAX_M = 16
+MAX_J = 16
 ROWS_PER_TILE = 128          # (points x jet channels) rows a CTA tile holds; must match the kernel
 
 SEGMENT_DTYPE = np.dtype([
@@ -47,6 +47,7 @@ SEGMENT_DTYPE = np.dtype([
     ('col_term_begin', '<i4', (MAX_COLS,)), ('col_term_end', '<i4', (MAX_COLS,)),
     ('col_slot', '<i4', (MAX_COLS,)),
     ('identity', '<i4'), ('comb_off', '<i4'),
+    ('dir_vec', '<f4', (MAX_DIRS, 4)),
 ], align=True)
 
 TERM_DTYPE = np.dtype([
@@ -126,8 +127,9 @@ def net_spec(model: torch.nn.Module) -> NetSpec:
 @dataclass
 class FactorIR:
     var: int
-    axes: Tuple[int, ...]        # () = value, (0, 0) = d2/dx0^2
+    axes: Tuple[int, ...]        # () = value, (0, 0) = d2/dx0^2, (0, 1) = mixed partial (lowered by `lower_mixed`)
     pow: float
+    dirvec: Optional[Tuple[float, ...]] = None   # set by `lower_mixed`: derivative of order len(axes) ALONG this vector
 
 
 @dataclass
@@ -206,41 +208,165 @@ def parse_operator(op: dict, rows: torch.Tensor, coeff_rows: Optional[Callable] 
 
 @dataclass
 class JetSpec:
-    dirs: List[Tuple[int, int]]          # (axis, max order), sorted by axis
+    """Jet directions.  A direction is an input axis (int: d^k/dx_a^k) or a vector (tuple of d floats: the k-th
+    derivative ALONG that vector - mixed partials are linear combinations of those, see `lower_mixed`)."""
+    dirs: List[Tuple[object, int]]       # (axis | vector, max order): axes first (sorted), then vectors
 
     @property
     def J(self):
         return 1 + sum(o for _, o in self.dirs)
 
-    def channel(self, axes: Tuple[int, ...]) -> int:
+    def channel(self, f) -> int:
+        """Channel of a factor (FactorIR) or of a pure axes tuple."""
+        axes = f if isinstance(f, tuple) else f.axes
         if not axes:
             return 0
+        key = getattr(f, 'dirvec', None)
+        if key is None:
+            key = axes[0]
         base = 1
         for a, o in self.dirs:
-            if a == axes[0]:
+            if a == key:
                 return base + len(axes) - 1
             base += o
         raise KeyError(axes)
 
+    def vector(self, i: int, d: int) -> List[float]:
+        a = self.dirs[i][0]
+        return [float(x) for x in a] if isinstance(a, tuple) else [1.0 if ax == a else 0.0 for ax in range(d)]
+
 
 def jet_spec(term_lists: Sequence[List[TermIR]]) -> JetSpec:
-    order: Dict[int, int] = {}
+    """Directions and orders the (already `lower_mixed`-ed) terms need."""
+    order: Dict[object, int] = {}
     for terms in term_lists:
         for t in terms:
             for f in t.factors:
                 if not f.axes:
                     continue
-                if len(set(f.axes)) != 1:
-                    raise UnsupportedProblem(f'mixed partial derivative {list(f.axes)} is not supported by the '
-                                             'fused path (pure partials up to order 4 only)')
+                if f.dirvec is None and len(set(f.axes)) != 1:
+                    raise UnsupportedProblem(f'mixed partial derivative {list(f.axes)} reached the jet set unlowered')
                 if len(f.axes) > MAX_ORDER:
                     raise UnsupportedProblem(f'derivative order {len(f.axes)} > {MAX_ORDER}')
-                order[f.axes[0]] = max(order.get(f.axes[0], 0), len(f.axes))
-    dirs = sorted(order.items())
+                key = f.dirvec if f.dirvec is not None else f.axes[0]
+                order[key] = max(order.get(key, 0), len(f.axes))
+    dirs = sorted((k, o) for k, o in order.items() if not isinstance(k, tuple)) + \
+        sorted((k, o) for k, o in order.items() if isinstance(k, tuple))
     js = JetSpec(dirs)
     if len(dirs) > MAX_DIRS or js.J > MAX_J:
         raise UnsupportedProblem(f'jet set too large (J = {js.J}, {len(dirs)} directions)')
     return js
+
+
+def _mixed_plan(n: int, need_q: Sequence[int], have_a: int, have_b: int):
+    """Mixed partials of total order n along two axes a, b: d^n / da^(n-q) db^q = sum_j c_j D_{v_j}^n with directions
+    v = e_a, e_b or e_a + t e_b, because D_v^n = sum_k C(n, k) t^k d^n / da^(n-k) db^k.  Picks the cheapest set of
+    directions (fewest added jet channels given the pure orders `have_a`, `have_b` the operator needs anyway) whose rows
+    span every wanted unit vector e_q.  -> ([('a' | 'b' | t, ...)], {q: coefficients})."""
+    from itertools import combinations
+    from math import comb as binom
+    pool = ['a', 'b', 1.0, -1.0, 2.0, -2.0, 0.5]
+
+    def row(c):
+        if c == 'a':
+            return [1.0] + [0.0] * n
+        if c == 'b':
+            return [0.0] * n + [1.0]
+        return [binom(n, k) * c ** k for k in range(n + 1)]
+
+    def cost(c):
+        return max(0, n - have_a) if c == 'a' else max(0, n - have_b) if c == 'b' else n
+    best = None
+    for size in range(1, len(pool) + 1):
+        for sub in combinations(pool, size):
+            A = np.array([row(c) for c in sub], dtype=np.float64)            # [dirs, n + 1]
+            sol = {}
+            for q in need_q:
+                e = np.zeros(n + 1)
+                e[q] = 1.0
+                c, *_ = np.linalg.lstsq(A.T, e, rcond=None)
+                if np.abs(A.T @ c - e).max() > 1e-9:
+                    break
+                sol[q] = c
+            else:
+                k = (sum(cost(c) for c in sub), size)
+                if best is None or k < best[0]:
+                    best = (k, list(sub), sol)
+    if best is None:
+        raise UnsupportedProblem(f'no direction set for mixed partials of order {n}')
+    return best[1], best[2]
+
+
+def lower_mixed(term_lists: Sequence[List[TermIR]], d: int) -> List[List[TermIR]]:
+    """Rewrites every factor that is a MIXED partial (reference: any axis list, tedeous/derivative.py:92-97, e.g. [0, 1])
+    as a linear combination of pure directional derivatives of the same order (polarisation), so that the kernels only
+    ever propagate 1-D Taylor jets: a term `c * u_xy * rest` becomes `sum_j (c * c_j) * D_{v_j}^2 u * rest`.  Mixed
+    factors must enter with power 1 (a power of a sum is not a product of channels) and mix two axes."""
+    pure: Dict[int, int] = {}
+    mixed: Dict[Tuple[int, int, int], set] = {}
+    for terms in term_lists:
+        for t in terms:
+            for f in t.factors:
+                ax = sorted(set(f.axes))
+                if f.dirvec is not None:
+                    continue
+                if len(ax) == 1:
+                    pure[ax[0]] = max(pure.get(ax[0], 0), len(f.axes))
+                elif len(ax) == 2:
+                    if f.pow != 1.0:
+                        raise UnsupportedProblem(f'mixed partial {list(f.axes)} with power {f.pow} (power 1 only)')
+                    if len(f.axes) > MAX_ORDER:
+                        raise UnsupportedProblem(f'derivative order {len(f.axes)} > {MAX_ORDER}')
+                    mixed.setdefault((ax[0], ax[1], len(f.axes)), set()).add(sum(1 for x in f.axes if x == ax[1]))
+                elif len(ax) > 2:
+                    raise UnsupportedProblem(f'mixed partial {list(f.axes)} along more than two axes')
+    if not mixed:
+        return [list(terms) for terms in term_lists]
+    plans = {}
+    for (a, b, n), qs in sorted(mixed.items(), key=lambda kv: -kv[0][2]):      # highest order first: its directions
+        cands, sol = _mixed_plan(n, sorted(qs), pure.get(a, 0), pure.get(b, 0))  # serve the lower orders for free
+        vecs = []
+        for c in cands:
+            if c == 'a':
+                pure[a] = max(pure.get(a, 0), n)
+                vecs.append(a)
+            elif c == 'b':
+                pure[b] = max(pure.get(b, 0), n)
+                vecs.append(b)
+            else:
+                v = [0.0] * d
+                v[a], v[b] = 1.0, float(c)
+                vecs.append(tuple(v))
+        plans[(a, b, n)] = (vecs, sol)
+
+    def expand(t: TermIR) -> List[TermIR]:
+        for i, f in enumerate(t.factors):
+            ax = sorted(set(f.axes))
+            if len(ax) != 2 or f.dirvec is not None:
+                continue
+            n, q = len(f.axes), sum(1 for x in f.axes if x == ax[1])
+            vecs, sol = plans[(ax[0], ax[1], n)]
+            out = []
+            for v, c in zip(vecs, sol[q]):
+                if abs(c) < 1e-12:
+                    continue
+                nf = FactorIR(f.var, (v,) * n, 1.0) if isinstance(v, int) else FactorIR(f.var, tuple(f.axes), 1.0, dirvec=v)
+                facs = t.factors[:i] + [nf] + t.factors[i + 1:]
+                if isinstance(t.coeff, torch.nn.Parameter):
+                    if abs(c - 1.0) > 1e-12:
+                        raise UnsupportedProblem('mixed partial under a trainable coefficient')
+                    nt = TermIR(t.coeff, facs)
+                elif isinstance(t.coeff, torch.Tensor):
+                    fn = None
+                    if t.coeff_fn is not None:
+                        fn = (lambda rows, g=t.coeff_fn[0], c=float(c): c * g(rows), t.coeff_fn[1])
+                    nt = TermIR(t.coeff * float(c), facs, fn)
+                else:
+                    nt = TermIR(float(t.coeff) * float(c), facs)
+                out += expand(nt)                     # further mixed factors of the same term
+            return out
+        return [t]
+    return [[e for t in terms for e in expand(t)] for terms in term_lists]
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -432,8 +558,9 @@ def lower_problem(mode: str, grid: torch.Tensor, prepared_operator: List[dict], 
     if mode == 'NN' and nn_interior == 'literal':
         seg = _interior_literal_fd('operator', pts, cols, list(range(n_eq)), h)
     else:
+        cols = lower_mixed(cols, d)
         js = jet_spec(cols)
-        seg = SegmentIR('operator', pts, 1, js, None, lambda f, js=js: js.channel(f.axes), cols,
+        seg = SegmentIR('operator', pts, 1, js, None, lambda f, js=js: js.channel(f), cols,
                         list(range(n_eq)), None)
     segments.append(seg)
 
@@ -472,13 +599,14 @@ def lower_problem(mode: str, grid: torch.Tensor, prepared_operator: List[dict], 
                 terms = parse_operator(bop, sides[0])
                 if not _is_linear(terms) or any(isinstance(t.coeff, torch.Tensor) for t in terms):
                     raise UnsupportedProblem(f'{name}: periodic operator must be linear with constant coefficients')
+                terms, = lower_mixed([terms], d)
                 js = jet_spec([terms])
                 J = js.J
                 comb = np.zeros((J, K * J))
                 for k in range(K):
                     for c in range(J):
                         comb[c, k * J + c] = sign[k]
-                segments.append(SegmentIR(name, pts_g, K, js, comb, lambda f, js=js: js.channel(f.axes),
+                segments.append(SegmentIR(name, pts_g, K, js, comb, lambda f, js=js: js.channel(f),
                                           [terms], [slot], target.reshape(-1, 1),
                                           row_index=torch.arange(type_len[kind], type_len[kind] + n)))
             type_len[kind] += n
@@ -502,10 +630,10 @@ def lower_problem(mode: str, grid: torch.Tensor, prepared_operator: List[dict], 
             else:
                 terms = None
             if mode == 'autograd':
-                terms = terms or parse_operator(bop, bnd)
+                terms, = lower_mixed([terms or parse_operator(bop, bnd)], d)
                 js = jet_spec([terms])
                 segments.append(SegmentIR(name, bnd.contiguous(), 1, js, None,
-                                          lambda f, js=js: js.channel(f.axes), [terms], [slot],
+                                          lambda f, js=js: js.channel(f), [terms], [slot],
                                           target.reshape(-1, 1), row_index=torch.arange(base, base + n)))
             else:
                 _, names = ptype.bnd_types(bnd)
@@ -608,7 +736,8 @@ def flatten(ir: ProblemIR, device) -> FlatIR:
         r['n_groups'], r['pts_off'], r['K'], r['M'], r['n_cols'] = s.n_groups, pts_off, s.K, s.M, len(s.cols)
         r['n_dirs'] = len(s.jet.dirs)
         for i, (a, o) in enumerate(s.jet.dirs):
-            r['dir_axis'][i], r['dir_order'][i] = a, o
+            r['dir_axis'][i], r['dir_order'][i] = (-1 if isinstance(a, tuple) else a), o
+            r['dir_vec'][i][:ir.d] = s.jet.vector(i, ir.d)
         points_per_tile(J, s.K)                       # validates the tile shape
         if s.M > J * s.K:
             raise UnsupportedProblem(f'{s.name}: more virtual channels than evaluated jets')
