@@ -56,6 +56,16 @@ def evaluate_ir(ir: ProblemIR, model, dtype=torch.float64, tol=0):
                 val = val + prod
             cols.append(val)
         vals = torch.stack(cols, 1)
+        if s is ir.segments[0] and getattr(ir, 'host_terms', None):
+            # callable-'pow' terms: assembled from the factor columns as Solution._assemble_host does
+            eqs = [vals[:, e] for e in range(ir.n_eq)]
+            for e, coeff, chain in ir.host_terms:
+                der = 1.
+                for col, pw in chain:
+                    der = pw(der * vals[:, col]) if callable(pw) else der * vals[:, col] ** pw
+                c = coeff.to(dtype).reshape(-1) if isinstance(coeff, torch.Tensor) and coeff.numel() > 1 else coeff
+                eqs[e] = eqs[e] + c * der
+            vals = torch.stack(eqs, 1)
         fields.append(vals)
         res = vals - (s.targets.to(dtype) if s.targets is not None else 0.)
         w = 1.
@@ -64,7 +74,7 @@ def evaluate_ir(ir: ProblemIR, model, dtype=torch.float64, tol=0):
                 n_t = ir.n_t if n % ir.n_t == 0 else n
                 r2 = (vals.detach() ** 2).sum(1).reshape(n_t, -1)
                 w = torch.exp(-tol * (torch.cumsum(r2, 0) - r2)).reshape(-1)
-        for ci, slot in enumerate(s.slots):
+        for ci, slot in enumerate(s.slots[:vals.shape[1]]):
             sums[slot] = sums[slot] + (w * res[:, ci] ** 2).sum()
     mse = [sm / ln for sm, ln in zip(sums, ir.slot_len)]
     lam = [1. if (tol != 0 and i < ir.n_eq) else l for i, l in enumerate(ir.slot_lambda)]

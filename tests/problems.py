@@ -457,6 +457,32 @@ def mixed_bbm(api, dtype='float32', n=16, layers=(2, 32, 32, 1)):
                    init='xavier_b')
 
 
+# --- callable 'pow' (examples/examples_heat/example_heat_2d_long_time.py:94-99) ------------------------------------------
+def heat_callable_pow(api, dtype='float32', n=20, mode='autograd', layers=(2, 32, 32, 1), h=0.01):
+    """u_t - 0.05 u_xx + c(x, t) sin(3 u^2) + 0.3 tanh(u) u_x^2 = 0: a callable power on the value (the shipped example's
+    source term) and a chain of a callable and a numeric power over two factors (`der = pow_j(der * factor_j)`,
+    tedeous/derivative.py:52-55, 126-129)."""
+    dom = api.Domain()
+    dom.variable('x', [0, 1], n, dtype=dtype)
+    dom.variable('t', [0, 1], n, dtype=dtype)
+    bc = api.Conditions()
+    bc.dirichlet({'x': [0, 1], 't': 0}, value=lambda g: torch.sin(np.pi * g[:, 0]))
+    bc.dirichlet({'x': 0, 't': [0, 1]}, value=0.)
+    bc.dirichlet({'x': 1, 't': [0, 1]}, value=0.)
+    eq = api.Equation()
+    eq.add({
+        'du/dt': {'coeff': 1, 'term': [1], 'pow': 1, 'var': 0},
+        '-0.05*d2u/dx2': {'coeff': -0.05, 'term': [0, 0], 'pow': 1, 'var': 0},
+        'c*sin(3u^2)': {'coeff': lambda g: 1. + g[:, 0] * g[:, 1], 'term': [None], 'pow': lambda u: torch.sin(3. * u ** 2),
+                        'var': 0},
+        '0.3*tanh(u)*(du/dx)^2': {'coeff': 0.3, 'term': [[None], [0]], 'pow': [lambda z: torch.tanh(z), 2], 'var': [0, 0]},
+    })
+    kw = dict(lambda_operator=1, lambda_bound=10)
+    if mode == 'NN':
+        kw['h'] = h
+    return Problem(f'heat_callable_{mode}', dom, bc, eq, mode, list(layers), kw, init='xavier_b')
+
+
 def trained(prob: Problem, steps: int) -> Problem:
     prob.train_steps = steps
     return prob
@@ -470,6 +496,8 @@ ZOO: Dict[str, Callable] = {
     'mixed_elliptic_autograd': lambda api, dt: mixed_elliptic(api, dt, mode='autograd'),
     'mixed_elliptic_NN': lambda api, dt: mixed_elliptic(api, dt, n=16, mode='NN', layers=(2, 32, 32, 1)),
     'mixed_bbm_autograd': lambda api, dt: mixed_bbm(api, dt),
+    'heat_callable_autograd': lambda api, dt: heat_callable_pow(api, dt, mode='autograd'),
+    'heat_callable_NN': lambda api, dt: heat_callable_pow(api, dt, n=16, mode='NN'),
     # ~10^5 points: the sizes at which the tensor-core kernels are chosen automatically (impl = 0)
     'wave_autograd_1e5': lambda api, dt: wave(api, dt, n=315, mode='autograd'),
     'kdv_autograd_1e5': lambda api, dt: kdv(api, dt, nx=399, nt=249, mode='autograd'),

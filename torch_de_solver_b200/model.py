@@ -78,7 +78,8 @@ class Model:
         sol = self.solution_cls
         if (optimizer.optimizer not in _KIND or mixed_precision or optimizer.cosine_scheduler_patience is not None
                 or sol.tol != 0 or sol.weak_form not in (None, []) or os.environ.get('TDB200_EAGER_TRAIN')
-                or getattr(sol, '_callable_coeffs', 'once') != 'once' or getattr(sol, '_batching', False)):
+                or getattr(sol, '_callable_coeffs', 'once') != 'once' or getattr(sol, '_batching', False)
+                or getattr(sol, '_hybrid', False)):
             return None
         params = [sol.model] if sol.mode == 'mat' else sol._ir.net.param_tensors()
         try:

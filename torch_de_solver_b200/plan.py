@@ -138,6 +138,8 @@ class TermIR:
     factors: List[FactorIR]
     coeff_fn: object = None      # (callable, rows) the per-row buffer was evaluated from (refresh_coeffs)
     coeff_slice: object = None   # (lo, hi) rows kept by this rank
+    host_pows: object = None     # a callable 'pow' somewhere in the term: [pow_j (number | callable)] per factor; the term
+                                 # is then assembled by torch from per-point factor fields (`host_terms` of the IR)
 
 
 def _check_coeff_callable(fn, label):
@@ -163,7 +165,8 @@ def _pure_axes(spec) -> Tuple[int, ...]:
     return axes
 
 
-def parse_operator(op: dict, rows: torch.Tensor, coeff_rows: Optional[Callable] = None) -> List[TermIR]:
+def parse_operator(op: dict, rows: torch.Tensor, coeff_rows: Optional[Callable] = None,
+                   allow_host: bool = False) -> List[TermIR]:
     """Unified operator dict -> list of TermIR.  `rows` are the points the operator is evaluated at
     (callable coefficients are evaluated on them once); `coeff_rows(tensor)` maps a full-grid tensor
     coefficient onto `rows`."""
@@ -174,13 +177,14 @@ def parse_operator(op: dict, rows: torch.Tensor, coeff_rows: Optional[Callable] 
         if not isinstance(specs, list) or (specs and not isinstance(specs[0], list)):
             specs = [specs]
         facs = []
+        host = any(callable(pw) for pw in pows)
+        if host and not allow_host:
+            raise UnsupportedProblem(f"term {label!r}: callable 'pow' is supported in the equation operator only")
         for spec, pw, var in zip(specs, pows, vars_):
-            if callable(pw):
-                raise UnsupportedProblem(f"term {label!r}: callable 'pow' is not supported by the fused path")
             if isinstance(var, (list, tuple)) and len(var) == 1:
                 var = var[0]     # 'var': [0] next to a scalar 'pow' (example_weak_LotkaVolterra.py:59-64): equation_unify
                                  # wraps it once more and the reference indexes model(grid)[:, [0]] with the list
-            facs.append(FactorIR(int(var), _pure_axes(spec), float(pw)))
+            facs.append(FactorIR(int(var), _pure_axes(spec), 1.0 if host else float(pw)))
         coeff = term['coeff']
         coeff_fn = None
         if isinstance(coeff, tuple):          # reference NN-prepared form (callable, grid)
@@ -202,7 +206,7 @@ def parse_operator(op: dict, rows: torch.Tensor, coeff_rows: Optional[Callable] 
         if isinstance(coeff, torch.Tensor) and not isinstance(coeff, torch.nn.Parameter) \
                 and coeff.numel() != rows.shape[0]:
             raise ValueError(f'term {label!r}: coefficient has {coeff.numel()} entries for {rows.shape[0]} rows')
-        terms.append(TermIR(coeff, facs, coeff_fn))
+        terms.append(TermIR(coeff, facs, coeff_fn, host_pows=list(pows) if host else None))
     return terms
 
 
@@ -553,15 +557,43 @@ def lower_problem(mode: str, grid: torch.Tensor, prepared_operator: List[dict], 
         central = None
         pts = grid.contiguous()
         coeff_rows = None
-    cols = [parse_operator(eq, pts, coeff_rows) for eq in prepared_operator]
+    cols = [parse_operator(eq, pts, coeff_rows, allow_host=True) for eq in prepared_operator]
     n_interior = pts.shape[0]
+    # A callable 'pow' is an arbitrary torch function of the running product (tedeous/derivative.py:52-55, 126-129; shipped:
+    # examples/examples_heat/example_heat_2d_long_time.py:94-99): such terms leave the term table.  The kernel evaluates
+    # their factors as extra per-point field columns, torch applies the callables (autograd), and the parameter gradient
+    # comes back through the kernel in vector-Jacobian mode (Solution._evaluate_hybrid).
+    host_terms, extra_cols, extra_key = [], [], {}
+    for e, terms in enumerate(cols):
+        keep = []
+        for t in terms:
+            if t.host_pows is None:
+                keep.append(t)
+                continue
+            chain = []
+            for f, pw in zip(t.factors, t.host_pows):
+                key = (f.var, f.axes)
+                if key not in extra_key:
+                    extra_key[key] = n_eq + len(extra_cols)
+                    extra_cols.append([TermIR(1.0, [FactorIR(f.var, f.axes, 1.0)])])
+                chain.append((extra_key[key], pw))
+            host_terms.append((e, t.coeff, chain))
+        cols[e] = keep
+    if host_terms:
+        if nn_interior == 'literal' and mode == 'NN':
+            raise UnsupportedProblem("callable 'pow' with nn_interior='literal'")
+        if shard[1] > 1:
+            raise UnsupportedProblem("callable 'pow' sharded over ranks (the loss is assembled from per-point fields)")
+        if n_eq + len(extra_cols) > MAX_COLS:
+            raise UnsupportedProblem(f"callable 'pow': {n_eq} equations + {len(extra_cols)} factor fields > {MAX_COLS} columns")
+        cols = cols + extra_cols
     if mode == 'NN' and nn_interior == 'literal':
         seg = _interior_literal_fd('operator', pts, cols, list(range(n_eq)), h)
     else:
         cols = lower_mixed(cols, d)
         js = jet_spec(cols)
         seg = SegmentIR('operator', pts, 1, js, None, lambda f, js=js: js.channel(f), cols,
-                        list(range(n_eq)), None)
+                        list(range(n_eq)) + [0] * len(extra_cols), None)
     segments.append(seg)
 
     # ---- boundary rows ------------------------------------------------------------------------------
@@ -661,6 +693,7 @@ def lower_problem(mode: str, grid: torch.Tensor, prepared_operator: List[dict], 
     # time slices of the causal loss: unique values of column 0 of the interior rows (tedeous/solution.py:51-57)
     ir.n_t = int(torch.unique(pts[:, 0]).numel())
     ir.interior_points = pts             # rows of the operator residual (NN mode: the central points), weak form
+    ir.host_terms = host_terms           # [(equation, coeff, [(field column, pow | callable)])]: callable-'pow' terms
     for s in ir.segments:
         s.n_groups_global = s.n_groups
     if shard[1] > 1:

@@ -418,6 +418,8 @@ class Solution:
                            boundary_order=self._boundary_order, nn_interior=self._nn_interior,
                            shard=self._shard)
         self._ir = ir
+        if self._batching and ir.host_terms:
+            raise UnsupportedProblem("callable 'pow' with mini-batches")
         self._plan = FusedPlan(ir, self.grid.device, impl=self._impl)
         if (self._shard[1] > 1 and self._collective == 'library' and self.tol == 0 and self.weak_form in (None, [])
                 and _dist_ready()):
@@ -491,8 +493,8 @@ class Solution:
         [loss terms | gradient] vector (mat mode: halo exchange, the kernel launches, all-reduce of the loss terms).
         -> (replay, out): `out` is a static tensor refreshed by every replay; parameter tensors must keep their storage
         (in-place optimiser updates do).  Steps that are launch bound (BASELINE config 1) replay as one graph launch."""
-        if self.tol != 0 or self.weak_form not in (None, []):
-            raise UnsupportedProblem('graph capture of the causal / weak-form step is not provided')
+        if self.tol != 0 or self.weak_form not in (None, []) or self._hybrid:
+            raise UnsupportedProblem("graph capture of the causal / weak-form / callable-'pow' step is not provided")
         if self.mode == 'mat':
             replay, out, self._graph_grad = self._plan.capture(self.model)
             return replay, out
@@ -568,6 +570,47 @@ class Solution:
         self.lambda_bound = lambda_prepare(torch.empty(1, len(self.bval_keys)), self.lambda_bound).to(torch.float32)
         return self.loss, self.loss_normalized
 
+    # -- callable 'pow' (tedeous/derivative.py:52-55, 126-129) ---------------------------------------------------
+    @property
+    def _hybrid(self) -> bool:
+        return self.mode != 'mat' and bool(getattr(self._ir, 'host_terms', None))
+
+    def _assemble_host(self, op_ext: torch.Tensor) -> torch.Tensor:
+        """[N, n_eq + factor fields] from the kernel -> op [N, n_eq]: the callable-'pow' terms are evaluated by torch on
+        the factor columns exactly as the reference chains them (`der_term = pow_j(der_term * factor_j)` for a callable,
+        `der_term * factor_j ** pow_j` for a number) and added to their equation's column."""
+        n_eq = self._ir.n_eq
+        cols = [op_ext[:, e] for e in range(n_eq)]
+        for e, coeff, chain in self._ir.host_terms:
+            der = 1.
+            for col, pw in chain:
+                val = op_ext[:, col]
+                der = pw(der * val) if callable(pw) else der * val ** pw
+            c = coeff.to(op_ext.device).reshape(-1) if isinstance(coeff, torch.Tensor) and coeff.numel() > 1 else coeff
+            cols[e] = cols[e] + c * der
+        return torch.stack(cols, 1)
+
+    def _evaluate_hybrid(self, save_graph: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Default / causal loss of a problem with callable powers: per-point fields from a forward launch, the callables
+        and the loss formula as device ops under autograd, the parameter gradient by the fused kernel in seed mode."""
+        from .losses import Losses
+        self._fields_cache = None
+        grad = save_graph and torch.is_grad_enabled()
+        op, bval, tval = self._fields_differentiable() if grad else self._fields()
+        self._fields_cache = (op.detach(), bval.detach(), tval)
+        n_eq = self._n_slots - len(self.bval_keys)
+        n_t = None
+        if self.tol != 0:
+            n_t = int(torch.unique(self._ir.interior_points[:, 0]).numel())
+        loss, loss_n = Losses(self.mode, None, n_t, self.tol).compute(
+            op, bval, tval, self.lambda_operator, self.lambda_bound, save_graph)
+        self.loss, self.loss_normalized = loss.reshape(1), loss_n.detach().reshape(1)
+        self._last_out = torch.cat([self.loss.detach(), self.loss_normalized,
+                                    torch.mean(op.detach() ** 2, 0), torch.mean((bval.detach() - tval) ** 2, 0)])
+        self.lambda_operator = lambda_prepare(torch.empty(1, n_eq), self.lambda_operator).to(torch.float32)
+        self.lambda_bound = lambda_prepare(torch.empty(1, len(self.bval_keys)), self.lambda_bound).to(torch.float32)
+        return self.loss, self.loss_normalized
+
     def refresh_coeffs(self) -> None:
         """Re-evaluate callable coefficients (modes NN / autograd) into the plan's buffers."""
         if self.mode != 'mat':
@@ -579,6 +622,8 @@ class Solution:
             self.refresh_coeffs()
         if self.weak_form not in (None, []):
             return self._evaluate_weak(save_graph)
+        if self._hybrid:
+            return self._evaluate_hybrid(save_graph)
         self._sync_lambdas()
         self._fields_cache = None
         if self._batching:
@@ -629,7 +674,8 @@ class Solution:
             if self.mode == 'mat':
                 self._fields_cache = self._plan.eval_fields(self.model)
             else:
-                self._fields_cache = _assemble_fields(self._plan)
+                op, bval, tval = _assemble_fields(self._plan)
+                self._fields_cache = (self._assemble_host(op) if self._hybrid else op, bval, tval)
         return self._fields_cache
 
     def _fields_differentiable(self):
@@ -639,7 +685,8 @@ class Solution:
         if self._shard[1] > 1:
             raise UnsupportedProblem('per-point fields are not gathered across ranks')
         params = self._plan.ir.net.param_tensors()
-        return _assemble_fields(self._plan, _FusedFields.apply(self._plan, *params))
+        op, bval, tval = _assemble_fields(self._plan, _FusedFields.apply(self._plan, *params))
+        return (self._assemble_host(op) if self._hybrid else op), bval, tval
 
     def residual_jacobian(self) -> Tuple[torch.Tensor, torch.Tensor]:
         """(J_op [N * n_eq, P], J_bnd [max_len * n_types, P]): the Jacobians of `op.reshape(-1)` and of
@@ -652,6 +699,8 @@ class Solution:
             raise UnsupportedProblem('per-residual Jacobian rows are not gathered across ranks')
         if getattr(self, '_batching', False):
             raise UnsupportedProblem('per-residual Jacobian rows with mini-batches')
+        if self._hybrid:
+            raise UnsupportedProblem("per-residual Jacobian rows with callable 'pow' terms")
         plan, ir = self._plan, self._plan.ir
         n_types, max_len, P = len(ir.bnd_types), max(ir.type_len), plan.n_params
         j_op = None
