@@ -18,7 +18,13 @@ for name in names:
         set_weights(list(net.parameters()), g['weights'])
         net = net.to('cuda:0')
         model = tdb.Model(net, prob.domain, prob.equation, prob.conditions)
-        model.compile(prob.mode, **prob.compile_kwargs, impl=impl)
+        import os
+        kw = dict(prob.compile_kwargs)
+        if os.environ.get('LB'):
+            kw['lambda_bound'] = float(os.environ['LB'])
+        if os.environ.get('LO'):
+            kw['lambda_operator'] = float(os.environ['LO'])
+        model.compile(prob.mode, **kw, impl=impl)
         sol = model.solution_cls
         out = sol._run_plan()[0].double().cpu().numpy()
         torch.cuda.synchronize()

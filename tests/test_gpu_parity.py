@@ -154,13 +154,14 @@ def test_streamed_tensor_core_path_matches_reference(name, cuda_default):
 
 
 def test_auto_dispatch_reaches_tensor_cores(cuda_default):
-    """impl = 0 (what Model.compile does by default) at the sizes the benchmark runs: ~10^5 points take the tcgen05
-    kernel with TMEM-resident weight gradients, >= 2 10^5 points and deep nets the streamed pair; the numerics of these
-    fixtures are checked by test_loss_and_gradient_match_reference (fp64 goldens of the reference itself)."""
+    """impl = 0 (what Model.compile does by default) at the sizes the benchmark runs: from 4096 interior rows on the
+    streamed tensor-core pair serves every eligible net (value-row boundary segments inside the interior launch); the
+    numerics of these fixtures are checked by test_loss_and_gradient_match_reference (fp64 goldens of the reference)."""
     for name, lo in (('wave_autograd_1e5', 4), ('kdv_autograd_1e5', 4), ('wave_autograd_3e5', 5)):
         g = load_golden(name, 'float64')
         prob, net, sol = fused(name, g['weights'])
         assert sol._plan.launches_per_call >= lo, (name, sol._plan.launches_per_call)
+        assert sol._plan.kernel_path.startswith('tcgen05-3xtf32 streamed'), sol._plan.kernel_path
 
 
 def test_derivative_seam(cuda_default):

@@ -98,6 +98,10 @@ struct tdb200_plan {
   // streamed tensor-core path (jet_tcs_kernel + wgrad_gemm_kernel): any number of W x W layers
   bool tcs_eligible = false;
   std::vector<TcExtra> tcs_extra;              // boundary segments made of identity rows: streamed kernels too
+  // ... unless they ride in the interior launch (value rows: no derivative channels - Dirichlet / data conditions):
+  std::vector<int> tcs_mseg;                   // segments of the merged launch, interior first
+  std::vector<int> tcs_mseg_tile_begin;        // their first tiles (+ total)
+  int tcs_tiles = 0, tcs_term_end = 0, tcs_slot_base = 0;
   int* d_seg_tile_begin_rest_all = nullptr;    // the remaining segments (periodic / finite-difference groups): SIMT kernel
   int simt_rest_all_tiles = 0;
   float* tcs_ys = nullptr;                     // streamed Y_l / gZ_t rows of one chunk
@@ -230,6 +234,12 @@ int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_s
       }
       std::vector<int> tb(n_segments + 1, p->tc_tiles), rb(n_segments + 1, 0), ra(n_segments + 1, 0);
       tb[0] = 0;
+      p->tcs_mseg.assign(1, 0);
+      p->tcs_mseg_tile_begin.assign(1, 0);
+      p->tcs_tiles = p->tc_tiles;
+      p->tcs_term_end = s0.col_term_end[s0.n_cols - 1];
+      int slot_lo = s0.col_slot[0], slot_hi = s0.col_slot[0];
+      for (int c = 0; c < s0.n_cols; ++c) { slot_lo = std::min(slot_lo, s0.col_slot[c]); slot_hi = std::max(slot_hi, s0.col_slot[c]); }
       for (int s = 1; s < n_segments; ++s) {
         const tdb200_segment& sg = segments[s];
         int sig[3];
@@ -239,6 +249,24 @@ int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_s
                    !getenv("TDB200_NO_TC_BOUNDARY");
         if (eok)
           for (int t = sg.col_term_begin[0]; t < sg.col_term_end[sg.n_cols - 1]; ++t) eok = eok && terms[t].fac_end <= 96;
+        // value rows join the interior launch (same tile shape, their derivative channels are simply unused)
+        // ... when they are few: a value row costs a full jet tile slot there (Navier-Stokes at 10^6 points has 6 10^4
+        // boundary rows - 4x fewer tiles and no jet arithmetic in a launch of their own signature (0, 0, 0))
+        const long long merged_tiles = (sg.n_groups + P - 1) / P;
+        const bool few = (p->tcs_tiles - p->tc_tiles) + merged_tiles <= std::max<long long>(p->n_sms, p->tc_tiles / 128);
+        if (eok && sg.n_dirs == 0 && few && (int)p->tcs_mseg.size() < tdb::kTcsMaxSegs && !getenv("TDB200_TCS_NO_MERGE")) {
+          int lo = slot_lo, hi = slot_hi;
+          for (int c = 0; c < sg.n_cols; ++c) { lo = std::min(lo, sg.col_slot[c]); hi = std::max(hi, sg.col_slot[c]); }
+          if (hi - lo < TDB200_MAX_COLS) {
+            slot_lo = lo; slot_hi = hi;
+            p->tcs_mseg.push_back(s);
+            p->tcs_mseg_tile_begin.push_back(p->tcs_tiles);
+            p->tcs_tiles += (int)((sg.n_groups + P - 1) / P);
+            p->tcs_term_end = std::max(p->tcs_term_end, sg.col_term_end[sg.n_cols - 1]);
+            ra[s + 1] = ra[s];
+            continue;
+          }
+        }
         if (eok) {
           const int Pe = tdb::jet_tc_points_per_tile(sig[0], sig[1], sig[2]);
           tdb200_plan::TcExtra e{};
@@ -249,6 +277,8 @@ int tdb200_plan_create(const tdb200_net* net, int32_t n_segments, const tdb200_s
         }
         ra[s + 1] = ra[s] + (eok ? 0 : p->seg_tile_begin[s + 1] - p->seg_tile_begin[s]);
       }
+      p->tcs_mseg_tile_begin.push_back(p->tcs_tiles);
+      p->tcs_slot_base = slot_lo;
       p->simt_rest_all_tiles = ra[n_segments];
       if ((rc = upload(&p->d_seg_tile_begin_rest_all, ra.data(), ra.size()))) { tdb200_plan_destroy(p); return rc; }
       // boundary segments made of identity rows (Dirichlet values, autograd-mode operator conditions) take the tcgen05
@@ -410,15 +440,17 @@ static bool use_tcs(const tdb200_plan* p) {
   if (!p->tcs_eligible || p->impl == 1 || p->impl == 2) return false;
   if (p->impl == 3) return true;
   if (getenv("TDB200_AUTO_TCS")) return atoi(getenv("TDB200_AUTO_TCS")) != 0 && p->segs[0].n_groups >= 4096;
-  if (!p->tc_eligible) return p->segs[0].n_groups >= 4096;      // deeper nets: the only tensor-core path
-  return p->segs[0].n_groups >= 200000;                         // 1-2 W x W layers: faster than the TMEM-dW kernel on long launches
+  // >= 4096 rows.  Since the value-row boundary segments ride in the interior launch the pair also wins on short launches
+  // (BASELINE config 1, 9 801 + 303 points: 0.119 ms against 0.141 ms for the TMEM-dW kernel); TDB200_AUTO_TCS=0 or impl = 2
+  // select jet_tc_kernel.
+  return p->segs[0].n_groups >= 4096;
 }
 static bool use_tc(const tdb200_plan* p) {
   if (!p->tc_eligible || p->impl == 1 || use_tcs(p)) return false;
   return p->impl == 2 || p->segs[0].n_groups >= 4096;
 }
 static int tcs_chunks(const tdb200_plan* p) {
-  return p->tcs_chunk_tiles > 0 ? (p->tc_tiles + p->tcs_chunk_tiles - 1) / p->tcs_chunk_tiles : 1;
+  return p->tcs_chunk_tiles > 0 ? (p->tcs_tiles + p->tcs_chunk_tiles - 1) / p->tcs_chunk_tiles : 1;
 }
 // stream / scratch buffers of the streamed path, sized on first use (never inside a stream capture: warm up first)
 static int ensure_tcs_buffers(tdb200_plan* p) {
@@ -434,7 +466,7 @@ static int ensure_tcs_buffers(tdb200_plan* p) {
   const int pairs = 2 * p->n_sms;
   ct = ct / pairs * pairs;
   if (ct < pairs) ct = pairs;
-  if (ct > p->tc_tiles) ct = p->tc_tiles;
+  if (ct > p->tcs_tiles) ct = p->tcs_tiles;
   p->tcs_chunk_tiles = (int)ct;
   p->tcs_stream_stride = (long long)ct * 4 * Q * Wp * 4;
   (void)P; (void)J;
@@ -489,7 +521,7 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
     const int NM = a.n_layers - 2, Wp = (a.widths[1] + 3) / 4 * 4;
     const int Q = (tdb::jet_tc_columns_per_part(p->tc_sig[0], p->tc_sig[1], p->tc_sig[2]) + 3) / 4;
     // boundary rows: SIMT kernel on a side stream, on the SMs the persistent interior grid leaves free
-    const double tcs_us = 30.0 + 9.0 * ((p->tc_tiles + p->tc_grid - 1) / p->tc_grid) * (1.0 + 0.5 * NM);
+    const double tcs_us = 30.0 + 9.0 * ((p->tcs_tiles + p->tc_grid - 1) / p->tc_grid) * (1.0 + 0.5 * NM);
     int rest_ctas = p->simt_rest_all_tiles < p->n_sms ? p->simt_rest_all_tiles : p->n_sms, reserve = 0;
     bool fork = false;
     if (p->simt_rest_all_tiles > 0 && p->tc_grid == p->n_sms && !getenv("TDB200_NO_OVERLAP")) {
@@ -538,6 +570,11 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
     tdb::TcsArgs xa{};
     xa.wimg = p->wimg; xa.ys = p->tcs_ys; xa.gs = p->tcs_gs; xa.stream_stride = p->tcs_stream_stride;
     xa.zsave = p->tcs_zsave; xa.Wp = Wp;
+    xa.n_msegs = (int)p->tcs_mseg.size();
+    for (int m = 0; m < xa.n_msegs; ++m) { xa.mseg_index[m] = p->tcs_mseg[m]; xa.mseg_tile_begin[m] = p->tcs_mseg_tile_begin[m]; }
+    xa.mseg_tile_begin[xa.n_msegs] = p->tcs_tiles;
+    xa.term_end = p->tcs_term_end;
+    xa.slot_base = p->tcs_slot_base;
     tdb::WgradArgs wa{};
     wa.gs = p->tcs_gs; wa.ys = p->tcs_ys; wa.stream_stride = p->tcs_stream_stride;
     wa.W = a.widths[1]; wa.Wp = Wp; wa.n_mma = NM; wa.kb = 32; wa.splits = gG / NM > 0 ? gG / NM : 1;
@@ -545,8 +582,8 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
     for (int t = 1; t <= NM; ++t) wa.w_off[t - 1] = a.w_off[t];
     if (gG < NM) return fail(TDB200_ERR_INVALID, "streamed tcgen05 path: fewer CTAs than W x W layers");
     int chunk = 0;
-    for (int t0 = 0; t0 < p->tc_tiles; t0 += p->tcs_chunk_tiles, ++chunk) {
-      const int t1 = t0 + p->tcs_chunk_tiles < p->tc_tiles ? t0 + p->tcs_chunk_tiles : p->tc_tiles;
+    for (int t0 = 0; t0 < p->tcs_tiles; t0 += p->tcs_chunk_tiles, ++chunk) {
+      const int t1 = t0 + p->tcs_chunk_tiles < p->tcs_tiles ? t0 + p->tcs_chunk_tiles : p->tcs_tiles;
       xa.tile0 = t0; xa.tile1 = t1; xa.zero_partials = chunk == 0;
       CU(tdb::launch_jet_tcs(tc, xa, p->tc_sig[0], p->tc_sig[1], p->tc_sig[2], gA, s));
       if (do_grad) {
@@ -586,6 +623,10 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
       xe.row_weight = nullptr;
       xe.dbg = nullptr;
       xa.tile0 = 0; xa.tile1 = e.tiles; xa.zero_partials = 0;
+      xa.n_msegs = 1; xa.mseg_index[0] = 0; xa.mseg_tile_begin[0] = 0; xa.mseg_tile_begin[1] = e.tiles;
+      xa.term_end = p->segs[e.seg].col_term_end[p->segs[e.seg].n_cols - 1];
+      xa.slot_base = p->segs[e.seg].col_slot[0];
+      for (int c = 0; c < p->segs[e.seg].n_cols; ++c) xa.slot_base = std::min(xa.slot_base, p->segs[e.seg].col_slot[c]);
       const int ge = e.grid < gA ? e.grid : gA;
       CU(tdb::launch_jet_tcs(xe, xa, e.sig[0], e.sig[1], e.sig[2], ge, s));
       if (do_grad) {

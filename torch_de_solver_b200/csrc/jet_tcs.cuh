@@ -5,6 +5,7 @@
 namespace tdb {
 
 constexpr int kTcsMaxMma = TDB200_MAX_LAYERS - 2;   // W x W layers the streamed path handles
+constexpr int kTcsMaxSegs = 8;                      // segments one jet_tcs_kernel launch can cover
 
 // jet_tcs_kernel: fused forward + operator + backward-data over the tiles [tile0, tile1) of the interior segment.
 struct TcsArgs {
@@ -18,6 +19,15 @@ struct TcsArgs {
   int Wp;                       // row pitch of the streams (W rounded up to 4)
   int zero_partials;            // 1: first chunk of a call (partial rows start from zero), 0: accumulate
   int w_in_tmem;                // set by the launcher: weights as tensor-memory operands (tcgen05.cp), see jet_tcs_kernel.cuh
+  // Segments of this launch (a.segs is the plan's full segment array): segment mseg_index[m] owns the launch tiles
+  // [mseg_tile_begin[m], mseg_tile_begin[m + 1]).  m = 0 sets the jet signature; the others are identity segments WITHOUT
+  // derivative channels (Dirichlet / data value rows) or with the same directions, evaluated in the same tile shape - one
+  // launch instead of one small launch pair per boundary segment.
+  int n_msegs;
+  int mseg_tile_begin[kTcsMaxSegs + 1];
+  int mseg_index[kTcsMaxSegs];
+  int term_end;                 // terms [0, term_end) are pre-decoded for the operator warps (all segments of the launch)
+  int slot_base;                // loss slots of the launch lie in [slot_base, slot_base + TDB200_MAX_COLS)
 };
 
 // wgrad_gemm_kernel

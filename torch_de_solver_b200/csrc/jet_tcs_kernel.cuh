@@ -182,6 +182,13 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
   const int iters = (my_tiles + 1) / 2;
   const int n_kinds = a.do_grad ? 2 * NM : NM;
   auto tile_of = [&](int it, int slot) { return x.tile0 + (int)blockIdx.x + (2 * it + slot) * G; };
+  // launch tile -> (segment of the launch, tile inside that segment); segment 0 is the shared-memory copy
+  auto seg_of = [&](int tile, int& m, int& local) -> const tdb200_segment& {
+    m = 0;
+    while (m + 1 < x.n_msegs && tile >= x.mseg_tile_begin[m + 1]) ++m;
+    local = tile - x.mseg_tile_begin[m];
+    return m == 0 ? *segS : a.segs[x.mseg_index[m]];
+  };
   float* const my_grad = a.part_grad + (size_t)blockIdx.x * a.n_params_pad;    // one partial row per CTA
 
   // ---- one-time setup --------------------------------------------------------------------------------
@@ -195,7 +202,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
   for (int i = tid; i < min(kTcMaxTerms, a.n_terms); i += kTsThreads) termS[i] = a.terms[i];
   for (int i = tid; i < min(kTcMaxFactors, a.n_factors); i += kTsThreads) facS[i] = a.factors[i];
   for (int i = tid; i < (int)(sizeof(tdb200_segment) / 4); i += kTsThreads)
-    reinterpret_cast<uint32_t*>(segS)[i] = reinterpret_cast<const uint32_t*>(a.segs)[i];
+    reinterpret_cast<uint32_t*>(segS)[i] = reinterpret_cast<const uint32_t*>(a.segs + x.mseg_index[0])[i];
   if (tid < a.n_slots) scaleS[tid] = a.slot_scale[tid];
   for (int i = tid; i < kTcMaxPts * TDB200_MAX_COLS; i += kTsThreads) lossT[i] = 0.0;
   if (tid == 0) {
@@ -215,7 +222,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
-  if (tid < min(kTcMaxTerms, a.n_terms) && tid < segS->col_term_end[segS->n_cols - 1]) {
+  if (tid < min(kTcMaxTerms, a.n_terms) && tid < x.term_end) {
     const tdb200_term tm = termS[tid];
     int off[2] = {0xFFFF, 0xFFFF}, ipw[2] = {0, 0}, nf = 0;
     bool ok = tm.kind == 0 || (tm.idx >= 0 && tm.idx < 0x7fffffffLL);
@@ -349,8 +356,6 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
     // per point)
     // ===================================================================================================
     const bool fast_op = *fastS != 0;
-    const tdb200_segment& sg = *segS;
-    const int ncols = sg.n_cols;
     const int slot = warp - (kTsEpi / 32 + 1);
     uint32_t req_ph = 0;
     double lacc[TDB200_MAX_COLS];                          // per-lane loss sums (runtime column index: local memory)
@@ -362,8 +367,11 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
     for (int it = 0; it < iters; ++it) {
       const int nslots = (2 * it + 1 < my_tiles) ? 2 : 1;
       if (slot < nslots) {
-        const int tile = tile_of(it, slot);
-        const long long g_first = (long long)tile * P;
+        int mseg, ltile;
+        const tdb200_segment& sg = seg_of(tile_of(it, slot), mseg, ltile);
+        const int ncols = sg.n_cols;
+        const float* const row_w = mseg == 0 ? a.row_weight : nullptr;     // causal weights: interior rows only
+        const long long g_first = (long long)ltile * P;
         const int p_valid = (int)min((long long)P, sg.n_groups - g_first);
         float* const Us = sbase + kSOffU + slot * kTcMaxOut * kTcCols;
         float* const Gus = sbase + kSOffGu + slot * kTcMaxOut * kTcCols;
@@ -400,8 +408,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
           if (a.fields) a.fields[sg.field_off + row * ncols + col] = val;
           const float tgt = sg.tgt_off >= 0 ? __ldg(a.targets + sg.tgt_off + row * ncols + col) : 0.f;
           const float res = val - tgt;
-          const float rw = a.row_weight ? __ldg(a.row_weight + row) : 1.f;        // causal-loss weight (no grad)
-          lacc[col] += (double)rw * (double)res * (double)res;
+          const float rw = row_w ? __ldg(row_w + row) : 1.f;        // causal-loss weight (no grad)
+          lacc[sg.col_slot[col] - x.slot_base] += (double)rw * (double)res * (double)res;
           if (!a.do_grad) continue;
           const float seed = a.field_seed ? __ldg(a.field_seed + sg.field_off + row * ncols + col)
                                           : 2.f * scaleS[sg.col_slot[col]] * rw * res;
@@ -435,8 +443,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
           if (a.fields) a.fields[sg.field_off + row * ncols + col] = val;
           const float tgt = sg.tgt_off >= 0 ? __ldg(a.targets + sg.tgt_off + row * ncols + col) : 0.f;
           const float res = val - tgt;
-          const float rw = a.row_weight ? __ldg(a.row_weight + row) : 1.f;
-          lacc[col] += (double)rw * (double)res * (double)res;
+          const float rw = row_w ? __ldg(row_w + row) : 1.f;
+          lacc[sg.col_slot[col] - x.slot_base] += (double)rw * (double)res * (double)res;
           if (!a.do_grad) continue;
           const float seed = a.field_seed ? __ldg(a.field_seed + sg.field_off + row * ncols + col)
                                           : 2.f * scaleS[sg.col_slot[col]] * rw * res;
@@ -477,12 +485,12 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
       for (int off = 16; off >= 1; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
       if (lane == 0) (sbase + kSOffDbl)[slot * kTcMaxOut + v] = t;
     }
-    if (slot == 0)
-      for (int c = 0; c < ncols; ++c) lossT[lane * TDB200_MAX_COLS + c] = lacc[c];
+    if (slot == 0)                                         // per-lane sums by loss slot (relative to x.slot_base)
+      for (int c = 0; c < TDB200_MAX_COLS; ++c) lossT[lane * TDB200_MAX_COLS + c] = lacc[c];
     __syncwarp();
     asm volatile("bar.sync 2, 64;" ::: "memory");         // the two operator warps: slot 0 stores, then slot 1 adds
     if (slot == 1)
-      for (int c = 0; c < ncols; ++c) lossT[lane * TDB200_MAX_COLS + c] += lacc[c];
+      for (int c = 0; c < TDB200_MAX_COLS; ++c) lossT[lane * TDB200_MAX_COLS + c] += lacc[c];
   } else {
     // ===================================================================================================
     // epilogue warps
@@ -500,8 +508,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
       for (int ax = 0; ax < d; ++ax) w0[ax] = a.arena[a.w_off[0] + n * d + ax];
 #pragma unroll
     for (int v = 0; v < kTcMaxOut; ++v) { wl[v] = (live && v < n_out) ? a.arena[a.w_off[L - 1] + v * W + n] : 0.f; dwl_acc[v] = 0.f; }
-    const tdb200_segment& sg = *segS;
-    const int ncols = sg.n_cols;
+    const tdb200_segment& sg = *segS;                    // jet directions: those of the launch's first segment
     float w0d[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -515,13 +522,16 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
         const int tile = tile_of(it, slot);
         if (tile >= x.tile1) break;
         float* dst = xbuf_of(slot, it);
-        const long long gf = (long long)tile * P;
-        const int pv = (int)min((long long)P, sg.n_groups - gf);
+        int mseg, ltile;
+        const tdb200_segment& st = seg_of(tile, mseg, ltile);
+        const long long gf = (long long)ltile * P;
+        const int pv = (int)min((long long)P, st.n_groups - gf);
+        const float* const src = a.pts + (size_t)(st.pts_off + gf) * d;
         for (int i = tid; i < P * d; i += kTsEpi) {
           const int p = i / d, ax = i - p * d;
           if (p < pv)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dst + p * 4 + ax)),
-                         "l"(a.pts + (size_t)(sg.pts_off + gf + p) * d + ax) : "memory");
+                         "l"(src + (size_t)p * d + ax) : "memory");
           else
             dst[p * 4 + ax] = 0.f;
         }
@@ -866,7 +876,6 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
   // ---- per-CTA scalars (accumulated by the operator warp) -----------------------------------------------------
   {
     const bool acc = !x.zero_partials;
-    const tdb200_segment& sg = *segS;
     if (a.do_grad && tid < n_out) {
       float* q = my_grad + a.b_off[L - 1] + tid;
       const float t = (sbase + kSOffDbl)[tid] + (sbase + kSOffDbl)[kTcMaxOut + tid];
@@ -878,9 +887,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
     }
     if (tid < a.n_slots) {
       double sacc = 0.0;
-      for (int col = 0; col < sg.n_cols; ++col)
-        if (sg.col_slot[col] == tid)
-          for (int p = 0; p < P; ++p) sacc += lossT[p * TDB200_MAX_COLS + col];
+      const int rel = tid - x.slot_base;
+      if (rel >= 0 && rel < TDB200_MAX_COLS)
+        for (int p = 0; p < 32; ++p) sacc += lossT[p * TDB200_MAX_COLS + rel];
       double* q = a.part_loss + (size_t)blockIdx.x * a.n_slots + tid;
       *q = acc ? *q + sacc : sacc;
     }

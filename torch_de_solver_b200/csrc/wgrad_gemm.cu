@@ -4,7 +4,7 @@
 // arrays of float4 [group of 4 columns][Wp neurons]; this kernel is the split-K contraction over the columns:
 // HBM-bound (2 * Wp * 4 bytes per column and layer), tcgen05.mma.kind::tf32 in the 3xTF32 split, accumulator in TMEM.
 //
-// One CTA = one (layer, range of stages); a stage = KB = 32 columns of both operands = two contiguous runs of
+// One CTA = one (layer, every splits-th stage); a stage = KB = 32 columns of both operands = two contiguous runs of
 // KB * Wp floats.  Three roles:
 //   * warp 9 (one lane): cp.async.bulk of the two runs of a stage into a 3-deep ring of raw buffers, completion on an
 //     mbarrier - the HBM stream is asynchronous and ~80 KB deep per SM, independent of the registers of the other warps;
@@ -24,6 +24,7 @@ namespace tdb {
 constexpr int kWgKB = 32;                          // rows (K) per stage: four K-steps (16-row stages with a 10-deep raw
                                                    // ring measured slower: 2.32 vs 1.87 ms on the wave workload)
 constexpr int kWgRawStages = 3, kWgImgStages = 2;
+constexpr int kWgBlock = 4;                        // consecutive stages a CTA takes per round-robin turn
 constexpr int kWgImg = 4 * kWgKB * 32;             // floats of one operand image: 4 MN blocks x 16 K rows x 32
 constexpr int kWgImgStageFloats = 4 * kWgImg;      // A hi, A lo, B hi, B lo = 64 KB
 constexpr int kWgRawOp = kWgKB * 104;              // floats of one operand of a raw stage (Wp <= 104)
@@ -59,7 +60,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const WgradAr
   const int KB = a.kb, Wp = a.Wp;
   const int F = KB * Wp / 4;                       // float4 per operand and stage
   const long long n_kb = (a.total4 + F - 1) / F;
-  const long long kb0 = n_kb * split / a.splits, kb1 = n_kb * (split + 1) / a.splits;
+  // Stages are dealt out round-robin in small blocks, not as one contiguous range per CTA: the tensor
+  // core ADDS into its fp32 accumulator with truncation, so a long chain of same-signed products (the lambda-weighted
+  // boundary rows, which sit together at the end of a stream) drifts by ~2^-24 per MMA - measured 4e-5 on dW when one CTA
+  // took all of them.  Interleaved, every CTA sees an equal share of every part of the stream and the partial sums are
+  // combined in fp32 round-to-nearest by reduce_partials_kernel.  Each stage is still one contiguous 13 KB run per operand.
+  // (blocks of kWgBlock consecutive stages: neighbouring stages keep the DRAM pages of a CTA's reads together)
+  const long long n_blk = (n_kb + kWgBlock - 1) / kWgBlock;
+  const long long my_blk = split < n_blk ? (n_blk - split + a.splits - 1) / a.splits : 0;
+  long long cnt = 0;
+  if (my_blk > 0) {
+    const long long last = (long long)split + (my_blk - 1) * a.splits;          // this CTA's last block (may be partial)
+    const long long in_last = n_kb - last * kWgBlock < kWgBlock ? n_kb - last * kWgBlock : kWgBlock;
+    cnt = (my_blk - 1) * kWgBlock + in_last;
+  }
+  auto stage_of = [&](long long i) { return ((i / kWgBlock) * a.splits + split) * kWgBlock + i % kWgBlock; };
   const float* __restrict__ gs = a.gs + (size_t)layer * a.stream_stride;
   const float* __restrict__ ys = a.ys + (size_t)layer * a.stream_stride;
 
@@ -84,8 +99,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const WgradAr
   if (warp == kWgConvWarps + 1) {
     // ---- producer: HBM -> raw ring ------------------------------------------------------------------------------
     if (lane == 0) {
-      for (long long kb = kb0; kb < kb1; ++kb) {
-        const long long i = kb - kb0;
+      for (long long i = 0; i < cnt; ++i) {
+        const long long kb = stage_of(i);
         const int st = (int)(i % kWgRawStages);
         const uint32_t use = (uint32_t)(i / kWgRawStages);
         if (use > 0) mbar_wait(raw_empty + st, (use - 1) & 1);
@@ -125,8 +140,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const WgradAr
         lo_img[o] = xv[e] - h;
       }
     };
-    for (long long kb = kb0; kb < kb1; ++kb) {
-      const long long i = kb - kb0;
+    for (long long i = 0; i < cnt; ++i) {
+      const long long kb = stage_of(i);
       const int rs = (int)(i % kWgRawStages), is = (int)(i % kWgImgStages);
       const uint32_t ruse = (uint32_t)(i / kWgRawStages), iuse = (uint32_t)(i / kWgImgStages);
       mbar_wait(raw_full + rs, ruse & 1);
@@ -157,7 +172,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const WgradAr
     int stage = 0;
     uint32_t fph = 0;
     const bool leader = elect_one();
-    for (long long kb = kb0; kb < kb1; ++kb) {
+    for (long long i = 0; i < cnt; ++i) {
       mbar_wait(img_full + stage, fph);
       tc_fence_after();
       const float* st = sbase + stage * kWgImgStageFloats;
@@ -168,7 +183,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const WgradAr
       for (int s = 0; s < KB / 8; ++s) {
         const uint64_t o = ((uint64_t)s * 1024) >> 4;
         if (leader) {
-          umma_tf32(tmem, ah + o, bh + o, idesc, (kb > kb0 || s > 0) ? 1u : 0u);
+          umma_tf32(tmem, ah + o, bh + o, idesc, (i > 0 || s > 0) ? 1u : 0u);
           umma_tf32(tmem, ah + o, bl + o, idesc, 1u);
           umma_tf32(tmem, al + o, bh + o, idesc, 1u);
         }
@@ -185,13 +200,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const WgradAr
   float* const tbuf = sbase;                       // [128][113] floats: the image stages are free by now
   if (warp < kWgConvWarps) {
     const int n = (warp & 3) * 32 + lane, half = warp >> 2;
-    if (kb0 < kb1) {
+    if (cnt > 0) {
       mbar_wait(done, 0);
       tc_fence_after();
     }
     for (int k0 = half * 64; k0 < half * 64 + 64 && k0 < 112; k0 += 16) {
       float v[16];
-      if (kb0 < kb1) tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)k0, v);
+      if (cnt > 0) tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)k0, v);
       else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = 0.f;
