@@ -102,7 +102,7 @@ def test_tensor_core_path_matches_reference(name, cuda_default):
     """impl=2 forces the tcgen05 3xTF32 kernel for the interior segment (boundary segments stay on the SIMT kernel)."""
     g = load_golden(name, 'float64')
     prob, net, sol = fused(name, g['weights'], impl=2)
-    assert sol._plan.launches_per_call >= 4
+    assert sol._plan.launches_per_call >= 3
     loss, loss_n = sol.evaluate()
     loss.backward()
     grad = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).double().cpu().numpy()
@@ -131,7 +131,7 @@ def test_streamed_tensor_core_path_matches_reference(name, cuda_default):
     wgrad_gemm_kernel (weight gradients of the W x W layers from the streamed Y / gZ rows)."""
     g = load_golden(name, 'float64')
     prob, net, sol = fused(name, g['weights'], impl=3)
-    assert sol._plan.launches_per_call >= 5
+    assert sol._plan.launches_per_call >= 4
     loss, loss_n = sol.evaluate()
     loss.backward()
     grad = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).double().cpu().numpy()
@@ -157,7 +157,7 @@ def test_auto_dispatch_reaches_tensor_cores(cuda_default):
     """impl = 0 (what Model.compile does by default) at the sizes the benchmark runs: from 4096 interior rows on the
     streamed tensor-core pair serves every eligible net (value-row boundary segments inside the interior launch); the
     numerics of these fixtures are checked by test_loss_and_gradient_match_reference (fp64 goldens of the reference)."""
-    for name, lo in (('wave_autograd_1e5', 4), ('kdv_autograd_1e5', 4), ('wave_autograd_3e5', 5)):
+    for name, lo in (('wave_autograd_1e5', 4), ('kdv_autograd_1e5', 4), ('wave_autograd_3e5', 4)):
         g = load_golden(name, 'float64')
         prob, net, sol = fused(name, g['weights'])
         assert sol._plan.launches_per_call >= lo, (name, sol._plan.launches_per_call)

@@ -482,9 +482,9 @@ int32_t tdb200_plan_kernel_path(const tdb200_plan* p) {
 }
 int32_t tdb200_plan_launches_per_call(const tdb200_plan* p) {
   if (!p) return 0;
-  if (use_tcs(p)) return 3 + 2 * tcs_chunks(p) + 2 * (int)p->tcs_extra.size() + (p->simt_rest_all_tiles > 0 ? 1 : 0);
+  if (use_tcs(p)) return 2 + 2 * tcs_chunks(p) + 2 * (int)p->tcs_extra.size() + (p->simt_rest_all_tiles > 0 ? 1 : 0);
   if (!use_tc(p)) return 3;
-  return 4 + (int)p->tc_extra.size() + (p->simt_rest_tiles > 0 ? 1 : 0);
+  return 3 + (int)p->tc_extra.size() + (p->simt_rest_tiles > 0 ? 1 : 0);
 }
 
 static int run(tdb200_plan* p, const float* const* params, float* fields, float* out, int do_grad, void* stream) {
@@ -510,6 +510,7 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
   pk.arena_t = p->arena_t;
   pk.img_f = p->img_f;
   pk.img_b = p->img_b;
+  pk.wimg = (use_tcs(p) || use_tc(p)) ? p->wimg : nullptr;     // tensor-core weight images in the same launch
   CU(tdb::launch_pack_params(pk, s));
   tdb::JetArgs call = a;
   call.fields = fields;
@@ -517,7 +518,6 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
   int grad_rows = p->grid, loss_rows = p->grid;
   if (use_tcs(p)) {
     { const int rc = ensure_tcs_buffers(p); if (rc != TDB200_OK) return rc; }
-    CU(tdb::launch_pack_tc_images(pk, p->wimg, s));
     const int NM = a.n_layers - 2, Wp = (a.widths[1] + 3) / 4 * 4;
     const int Q = (tdb::jet_tc_columns_per_part(p->tc_sig[0], p->tc_sig[1], p->tc_sig[2]) + 3) / 4;
     // boundary rows: SIMT kernel on a side stream, on the SMs the persistent interior grid leaves free
@@ -644,7 +644,6 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
     }
     if (p->simt_rest_all_tiles > 0) { grad_rows += rest_ctas; loss_rows += rest_ctas; }
   } else if (use_tc(p)) {
-    CU(tdb::launch_pack_tc_images(pk, p->wimg, s));
     tdb::JetArgs tc = call;
     tc.seg_tile_begin = p->d_seg_tile_begin_tc;
     tc.n_tiles = p->tc_tiles;

@@ -58,6 +58,15 @@ struct JetArgs {
   long long* dbg;                      // optional [gridDim.x][16] phase cycle counters (TDB200_TC_TIMING=1)
 };
 
+// tensor-core weight images (jet_tc_kernel.cuh): K-major SWIZZLE_128B, [4 k-blocks][104 rows][32 floats] per image
+constexpr int kTcWRows = 104;                    // rows of the weight image (neurons padded to 8)
+constexpr int kTcWBlock = kTcWRows * 32;
+constexpr int kTcWFloats = 4 * kTcWBlock;        // 13312 floats = 52 KB
+// float offset of element (row, k) inside a swizzled operand buffer with `rows` rows per k-block
+__host__ __device__ __forceinline__ int sw_off(int row, int k, int rows) {
+  return (k >> 5) * rows * 32 + row * 32 + ((((k & 31) >> 2) ^ (row & 7)) << 2) + (k & 3);
+}
+
 struct PackArgs {
   int n_layers;
   int widths[TDB200_MAX_LAYERS + 1];
@@ -72,6 +81,8 @@ struct PackArgs {
   float* arena_t;
   float* img_f;
   float* img_b;
+  float* wimg;                         // optional: hi / lo tensor-core images of the W x W layers, written by the same
+                                       // launch (layout of pack_tc_images_kernel; one launch less per step)
 };
 
 // host-side launchers (jet_simt.cu)

@@ -38,6 +38,15 @@ __global__ void pack_params_kernel(PackArgs a) {
       const int tb = (in + 7) / 8 <= 4 ? 4 : (in + 7) / 8 <= 8 ? 8 : (in + 7) / 8 <= 13 ? 13 : 16;
       a.img_f[(size_t)l * kMaxW * kWLd + k * kWLd + (n / tf) * 16 + n % tf] = w;
       a.img_b[(size_t)l * kMaxW * kWLd + n * kWLd + (k / tb) * 16 + k % tb] = w;
+      if (a.wimg && l >= 1 && l <= a.n_layers - 2) {        // tensor-core images: W hi | W lo | W^T hi | W^T lo
+        float* hi = a.wimg + (size_t)(l - 1) * 4 * kTcWFloats;
+        const float h = __uint_as_float((__float_as_uint(w) + 0x1000u) & 0xFFFFE000u);      // tf32, round to nearest
+        const int o = sw_off(n, k, kTcWRows), ot = sw_off(k, n, kTcWRows);
+        hi[o] = h;
+        hi[kTcWFloats + o] = w - h;
+        hi[2 * kTcWFloats + ot] = h;
+        hi[3 * kTcWFloats + ot] = w - h;
+      }
     }
     for (int i = tid; i < out; i += nth) a.arena[a.b_off[l] + i] = a.b[l][i];
   }

@@ -30,9 +30,6 @@ constexpr int kTcThreads = 512;                  // 16 warps: 4 lane windows x 4
 constexpr int kTcParts = 4;
 constexpr int kTcPC = 16;                        // columns per part
 constexpr int kTcCols = kTcParts * kTcPC;        // (point, channel) columns per tile = MMA N
-constexpr int kTcWRows = 104;                    // rows of the weight image (neurons padded to 8)
-constexpr int kTcWBlock = kTcWRows * 32;
-constexpr int kTcWFloats = 4 * kTcWBlock;        // 13312 floats = 52 KB
 constexpr int kTcActBlock = 104 * 32;            // MN-major activation operand: [2 blocks of 32 columns][104 K rows][32]
 constexpr int kTcActFloats = 2 * kTcActBlock;    // 6656 floats = 26 KB
 constexpr int kTcYwRows = 112;                   // K-major operand of the weight-gradient GEMM: [2 blocks][112 rows][32]
@@ -44,10 +41,6 @@ constexpr int kTcMaxOut = 4;                     // network outputs served by th
 // gZ lo (A operands of the weight-gradient MMA) | dW slots (112 columns each)
 constexpr uint32_t kTmD = 0, kTmAHi = 128, kTmALo = 192, kTmDw = 256, kTmDwCols = 112;
 
-// float offset of element (row, k) inside a swizzled operand buffer with `rows` rows per k-block
-__host__ __device__ __forceinline__ int sw_off(int row, int k, int rows) {
-  return (k >> 5) * rows * 32 + row * 32 + ((((k & 31) >> 2) ^ (row & 7)) << 2) + (k & 3);
-}
 
 // float offset of element (K-row r, MN index k) of an MN-major tf32 operand (SWIZZLE_128B_BASE32B)
 __host__ __device__ __forceinline__ int sw_off_mn(int r, int k, int rows) {
