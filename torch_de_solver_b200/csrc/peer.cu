@@ -1,0 +1,260 @@
+// Peer-memory exchange for sharded mat mode (SURVEY 8e "direct peer loads over NVLink"): the halo rows of the slab
+// decomposition and the handful of loss terms move between the GPUs of one box through CUDA-IPC mapped buffers, written
+// and read by two tiny kernels of our own - no collective library call on the step's critical path.
+//
+// Every rank owns one exchange block (cudaMalloc, exported with cudaIpcGetMemHandle, mapped by every other rank):
+//     [ flags | loss inbox [2 parities][world][kPeerMaxLoss] | halo inbox [2 parities][2 sides][halo floats] ]
+// PUSH model: data and flags are WRITTEN into the receiver's block (posted NVLink stores), every wait polls LOCAL memory
+// (the first version pulled: remote polls and dependent remote loads cost 17.7 us per halo exchange, this one ~6).
+// A step on rank r:
+//   peer_halo_kernel   one CTA per side: store my first / last owned halo rows into the neighbour's inbox (parity =
+//                      step & 1), system fence, release-store the step number into the neighbour's flag; wait for my
+//                      own flag of that side; copy my inbox rows into my extended slab.  The neighbour cannot run two
+//                      steps ahead (its next push waits for my flag), so two parities are enough.
+//   ... the unchanged stencil / boundary kernels on the extended slab ...
+//   peer_loss_kernel   one CTA: store my [2 + n_slots] loss terms into every rank's inbox row `rank`, fence, flags; wait
+//                      for every rank's flag; add the rows in RANK order (every rank gets the bit-identical sum).
+// Both kernels are plain stream work: the whole multi-rank step is capturable in one CUDA graph.  Waits are bounded
+// (~2 s of polling): on a time-out the kernel sets an error word instead of hanging the GPU.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "tdb200.h"
+
+extern "C" void tdb200_set_error_(const char* msg);
+
+namespace tdb {
+
+constexpr int kPeerMaxLoss = 64;
+constexpr int kPeerMaxWorld = 16;
+
+struct PeerHeader {
+  unsigned int halo_flag[2];  // [side]: last step whose rows the neighbour on that side has pushed into my inbox
+  unsigned int error;         // a wait timed out
+  unsigned int pad;
+  unsigned int loss_flag[kPeerMaxWorld];                 // [rank]: last step whose loss terms that rank has pushed
+  float loss[2][kPeerMaxWorld][kPeerMaxLoss];            // [parity][rank][term]
+};
+
+}  // namespace tdb
+
+struct tdb200_peer {
+  int rank = 0, world = 1, device = 0;
+  long long halo_floats = 0;                    // floats of one side's halo block
+  void* mine = nullptr;                         // my exchange block
+  void* blocks[tdb::kPeerMaxWorld] = {};        // every rank's block as seen from this device (mine included)
+  bool opened[tdb::kPeerMaxWorld] = {};
+  unsigned int* step_dev = nullptr;             // [2] device step counters (halo, loss): advanced by the kernels
+};
+
+namespace tdb {
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+// wait until *flag >= want (sequence numbers only grow); false on time-out
+__device__ __forceinline__ bool wait_seq(const unsigned int* flag, unsigned int want) {
+  const long long t0 = clock64();
+  while ((int)(ld_acquire_sys(flag) - want) < 0) {
+    __nanosleep(200);
+    if (clock64() - t0 > 4000000000LL) return false;
+  }
+  return true;
+}
+
+__device__ __forceinline__ float* halo_box(void* block, int parity, int side, long long halo_floats) {
+  return reinterpret_cast<float*>(reinterpret_cast<char*>(block) + sizeof(PeerHeader)) + ((size_t)parity * 2 + side) * halo_floats;
+}
+
+// side 0: exchange with rank - 1 (my FIRST owned rows go out, its LAST owned rows come in above me); side 1: rank + 1.
+// rows: n_var blocks of `rows_floats` contiguous floats (h rows x n1) at stride `var_stride` inside the extended slab.
+__global__ void __launch_bounds__(1024) peer_halo_kernel(void* mine, void* up_block, void* down_block, unsigned int* step_dev,
+                                                         float* ext, long long var_stride, int n_var, long long rows_floats,
+                                                         long long own_first, long long own_last, long long halo_up,
+                                                         long long halo_down, long long halo_floats) {
+  const int side = blockIdx.x;
+  void* const nb = side == 0 ? up_block : down_block;
+  const unsigned int step = step_dev[0] + 1;
+  const int parity = step & 1;
+  PeerHeader* const hdr = reinterpret_cast<PeerHeader*>(mine);
+  __shared__ unsigned int ok;
+  if (nb) {
+    // push: my rows -> the neighbour's inbox of ITS side towards me (1 - side)
+    float* box = halo_box(nb, parity, 1 - side, halo_floats);
+    const long long src0 = side == 0 ? own_first : own_last;
+    for (int v = 0; v < n_var; ++v) {
+      const float4* s4 = reinterpret_cast<const float4*>(ext + v * var_stride + src0);
+      float4* d4 = reinterpret_cast<float4*>(box + v * rows_floats);
+      for (long long i = threadIdx.x; i < rows_floats / 4; i += blockDim.x) d4[i] = s4[i];
+    }
+    // one thread fences at system scope after the block barrier (the barrier orders the other threads' stores before
+    // it; a fence per thread - 1024 membar.sys - costs tens of microseconds), then the flag goes out
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      st_release_sys(&reinterpret_cast<PeerHeader*>(nb)->halo_flag[1 - side], step);
+      ok = wait_seq(&hdr->halo_flag[side], step) ? 1u : 0u;               // local poll: the neighbour's rows are in
+      if (!ok) hdr->error = 1;
+    }
+    __syncthreads();
+    if (ok) {
+      const float4* in4 = reinterpret_cast<const float4*>(halo_box(mine, parity, side, halo_floats));
+      const long long dst0 = side == 0 ? halo_up : halo_down;
+      for (int v = 0; v < n_var; ++v) {
+        float4* d4 = reinterpret_cast<float4*>(ext + v * var_stride + dst0);
+        for (long long i = threadIdx.x; i < rows_floats / 4; i += blockDim.x) d4[i] = __ldcv(in4 + v * (rows_floats / 4) + i);
+      }
+    }
+  }
+  // the step counter advances once both CTAs are through (the last one to leave bumps it)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int* const leave = step_dev + 2;
+    if (atomicAdd(leave, 1u) + 1 == 2u * step) step_dev[0] = step;
+  }
+}
+
+struct PeerBlocks { void* b[kPeerMaxWorld]; };
+
+__global__ void __launch_bounds__(128) peer_loss_kernel(PeerBlocks blocks, int rank, int world, unsigned int* step_dev,
+                                                        float* out, int n) {
+  const unsigned int step = step_dev[1] + 1;
+  const int parity = step & 1;
+  PeerHeader* const hdr = reinterpret_cast<PeerHeader*>(blocks.b[rank]);
+  for (int i = threadIdx.x; i < world * n; i += blockDim.x) {               // my terms -> row `rank` of every inbox
+    const int r = i / n, t = i - r * n;
+    reinterpret_cast<PeerHeader*>(blocks.b[r])->loss[parity][rank][t] = out[t];
+  }
+  __shared__ unsigned int ok;
+  if (threadIdx.x == 0) ok = 1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    for (int r = 0; r < world; ++r)
+      if (r != rank) st_release_sys(&reinterpret_cast<PeerHeader*>(blocks.b[r])->loss_flag[rank], step);
+  }
+  if ((int)threadIdx.x < world && (int)threadIdx.x != rank)
+    if (!wait_seq(&hdr->loss_flag[threadIdx.x], step)) { ok = 0; hdr->error = 1; }
+  __syncthreads();
+  if ((int)threadIdx.x < n && ok) {
+    float s = 0.f;
+    for (int r = 0; r < world; ++r) s += __ldcv(&hdr->loss[parity][r][threadIdx.x]);     // rank order: bit-identical sums
+    out[threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) step_dev[1] = step;
+}
+
+static int peer_fail(cudaError_t e, const char* what) {
+  tdb200_set_error_((std::string(what) + ": " + cudaGetErrorString(e)).c_str());
+  return TDB200_ERR_CUDA;
+}
+
+}  // namespace tdb
+
+#define PCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return tdb::peer_fail(e_, #x); } while (0)
+
+extern "C" {
+
+int tdb200_peer_create(int32_t rank, int32_t world, int64_t halo_floats, int32_t device, tdb200_peer** out) {
+  if (!out || world < 1 || world > tdb::kPeerMaxWorld || rank < 0 || rank >= world || halo_floats < 0 || halo_floats % 4) {
+    tdb200_set_error_("tdb200_peer_create: bad argument (world <= 16, halo floats a multiple of 4)");
+    return TDB200_ERR_INVALID;
+  }
+  PCU(cudaSetDevice(device));
+  auto* p = new tdb200_peer();
+  p->rank = rank; p->world = world; p->device = device; p->halo_floats = halo_floats;
+  const size_t bytes = sizeof(tdb::PeerHeader) + (size_t)4 * halo_floats * sizeof(float);
+  PCU(cudaMalloc(&p->mine, bytes));
+  PCU(cudaMemset(p->mine, 0, bytes));
+  PCU(cudaMalloc(&p->step_dev, 4 * sizeof(unsigned int)));
+  PCU(cudaMemset(p->step_dev, 0, 4 * sizeof(unsigned int)));
+  PCU(cudaDeviceSynchronize());
+  p->blocks[rank] = p->mine;
+  *out = p;
+  return TDB200_OK;
+}
+
+int tdb200_peer_handle(tdb200_peer* p, void* handle_out_64_bytes) {
+  if (!p || !handle_out_64_bytes) { tdb200_set_error_("null argument"); return TDB200_ERR_INVALID; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t h;
+  PCU(cudaSetDevice(p->device));
+  PCU(cudaIpcGetMemHandle(&h, p->mine));
+  memcpy(handle_out_64_bytes, &h, sizeof(h));
+  return TDB200_OK;
+}
+
+int tdb200_peer_open(tdb200_peer* p, const void* handles_world_x_64_bytes) {
+  if (!p || !handles_world_x_64_bytes) { tdb200_set_error_("null argument"); return TDB200_ERR_INVALID; }
+  PCU(cudaSetDevice(p->device));
+  for (int r = 0; r < p->world; ++r) {
+    if (r == p->rank || p->opened[r]) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, reinterpret_cast<const char*>(handles_world_x_64_bytes) + (size_t)r * 64, sizeof(h));
+    PCU(cudaIpcOpenMemHandle(&p->blocks[r], h, cudaIpcMemLazyEnablePeerAccess));
+    p->opened[r] = true;
+  }
+  return TDB200_OK;
+}
+
+int tdb200_peer_halo(tdb200_peer* p, float* ext_dev, int64_t var_stride, int32_t n_var, int64_t rows_floats,
+                     int64_t own_first, int64_t own_last, int64_t halo_up, int64_t halo_down, void* stream) {
+  if (!p || !ext_dev) { tdb200_set_error_("null argument"); return TDB200_ERR_INVALID; }
+  if (rows_floats % 4 || (int64_t)n_var * rows_floats != p->halo_floats) {
+    tdb200_set_error_("tdb200_peer_halo: n_var * rows_floats must equal the halo size of tdb200_peer_create");
+    return TDB200_ERR_INVALID;
+  }
+  void* up = p->rank > 0 ? p->blocks[p->rank - 1] : nullptr;
+  void* down = p->rank < p->world - 1 ? p->blocks[p->rank + 1] : nullptr;
+  if ((p->rank > 0 && !up) || (p->rank < p->world - 1 && !down)) {
+    tdb200_set_error_("tdb200_peer_halo: tdb200_peer_open was not called");
+    return TDB200_ERR_INVALID;
+  }
+  tdb::peer_halo_kernel<<<2, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      p->mine, up, down, p->step_dev, ext_dev, var_stride, n_var, rows_floats, own_first, own_last, halo_up, halo_down,
+      p->halo_floats);
+  PCU(cudaGetLastError());
+  return TDB200_OK;
+}
+
+int tdb200_peer_allreduce(tdb200_peer* p, float* out_dev, int32_t n, void* stream) {
+  if (!p || !out_dev || n < 1 || n > tdb::kPeerMaxLoss) { tdb200_set_error_("tdb200_peer_allreduce: 1..64 floats"); return TDB200_ERR_INVALID; }
+  tdb::PeerBlocks b{};
+  for (int r = 0; r < p->world; ++r) {
+    if (!p->blocks[r]) { tdb200_set_error_("tdb200_peer_allreduce: tdb200_peer_open was not called"); return TDB200_ERR_INVALID; }
+    b.b[r] = p->blocks[r];
+  }
+  tdb::peer_loss_kernel<<<1, 128, 0, static_cast<cudaStream_t>(stream)>>>(b, p->rank, p->world, p->step_dev, out_dev, n);
+  PCU(cudaGetLastError());
+  return TDB200_OK;
+}
+
+int tdb200_peer_error(tdb200_peer* p, int32_t* error_out) {
+  if (!p || !error_out) { tdb200_set_error_("null argument"); return TDB200_ERR_INVALID; }
+  tdb::PeerHeader h;
+  PCU(cudaSetDevice(p->device));
+  PCU(cudaMemcpy(&h, p->mine, 16, cudaMemcpyDeviceToHost));     // flags + error word
+  *error_out = (int32_t)h.error;
+  return TDB200_OK;
+}
+
+void tdb200_peer_destroy(tdb200_peer* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  for (int r = 0; r < p->world; ++r)
+    if (p->opened[r]) cudaIpcCloseMemHandle(p->blocks[r]);
+  cudaFree(p->mine);
+  cudaFree(p->step_dev);
+  delete p;
+}
+
+}  // extern "C"

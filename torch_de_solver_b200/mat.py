@@ -434,6 +434,44 @@ class MatPlan:
             self._ext = torch.zeros(ir.shape_ext, dtype=torch.float32, device=self.device)
             self._ext[:, up:up + ir.shape[1]] = model.detach()
             model.data = self._ext[:, up:up + ir.shape[1]]
+        self._peer = None
+        self._setup_peer()
+
+    def _setup_peer(self):
+        """Peer-memory exchange (csrc/peer.cu) for the halo rows and the loss terms when the ranks are the GPUs of one
+        box: CUDA-IPC handles of the per-rank exchange blocks travel once over torch.distributed; every step then moves
+        its 2 x halo rows and its [2 + n_slots] loss terms with two small kernels of the library instead of two NCCL
+        collectives.  TDB200_MAT_COLLECTIVE=nccl keeps the library collectives (also the fallback when the handles
+        cannot be opened, e.g. ranks on different hosts)."""
+        import os
+        ir = self.ir
+        rank, world = ir.shard
+        if (world == 1 or self._ext is None or ir.halo == 0 or not self.device.type == 'cuda'
+                or os.environ.get('TDB200_MAT_COLLECTIVE', 'peer') != 'peer' or self.out_size > 64):
+            return
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return
+        n_var, n_ext, n1 = ir.shape_ext
+        if (ir.halo * n1) % 4:
+            return
+        handle = C.c_void_p()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        ok = self.lib.tdb200_peer_create(rank, world, n_var * ir.halo * n1, dev_index, C.byref(handle)) == 0
+        mine = (C.c_char * 64)()
+        ok = ok and self.lib.tdb200_peer_handle(handle, mine) == 0
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (bytes(mine.raw) if ok else None, os.uname().nodename), group=self._pg)
+        same_box = all(g[0] is not None and g[1] == gathered[0][1] for g in gathered)
+        if same_box:
+            buf = b''.join(g[0] for g in gathered)
+            same_box = self.lib.tdb200_peer_open(handle, buf) == 0
+        flags = [None] * world
+        dist.all_gather_object(flags, bool(same_box), group=self._pg)        # all ranks take the same path
+        if all(flags):
+            self._peer = handle
+        elif ok:
+            self.lib.tdb200_peer_destroy(handle)
 
     def _push_bcs(self):
         lam = np.asarray(self.slot_lambda, np.float64)
@@ -495,11 +533,35 @@ class MatPlan:
         if self._lift and u.dim() == 2:
             out, grad = self.loss_grad_ext(u.unsqueeze(-1))
             return out, grad.squeeze(-1)
+        if self._peer is not None and u.data_ptr() == self._own_view_ptr():
+            # halo rows and loss terms over peer memory (two kernels of the library, csrc/peer.cu)
+            ir = self.ir
+            n_var, n_ext, n1 = ir.shape_ext
+            up, n, h = ir.rows[0] - ir.ext[0], ir.rows[1] - ir.rows[0], ir.halo
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _native.check(self.lib.tdb200_peer_halo(self._peer, self._ext.data_ptr(), n_ext * n1, n_var, h * n1, up * n1,
+                                                    (up + n - h) * n1, 0, (up + n) * n1, stream), 'tdb200_peer_halo')
+            out, grad = self.loss_grad_ext(self._ext)
+            _native.check(self.lib.tdb200_peer_allreduce(self._peer, out.data_ptr(), self.out_size, stream),
+                          'tdb200_peer_allreduce')
+            return out, grad
         out, grad = self.loss_grad_ext(exchange_halos(u, self.ir, self._pg, self._ext))
         if self.ir.shard[1] > 1:
             import torch.distributed as dist
             dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self._pg)
         return out, grad
+
+    def _own_view_ptr(self) -> int:
+        up = self.ir.rows[0] - self.ir.ext[0]
+        return self._ext[:, up:up + self.shape[1]].data_ptr()
+
+    def peer_error(self) -> bool:
+        """True if a peer-memory wait timed out (a rank fell out of step); synchronises."""
+        if self._peer is None:
+            return False
+        err = C.c_int32(0)
+        _native.check(self.lib.tdb200_peer_error(self._peer, C.byref(err)), 'tdb200_peer_error')
+        return bool(err.value)
 
     def capture(self, u: torch.Tensor):
         """CUDA graph of one step - halo exchange, the two kernel launches, all-reduce of the loss terms - for training
@@ -544,6 +606,9 @@ class MatPlan:
 
     def __del__(self):
         try:
+            if getattr(self, '_peer', None):
+                self.lib.tdb200_peer_destroy(self._peer)
+                self._peer = None
             if getattr(self, 'handle', None):
                 self.lib.tdb200_mat_plan_destroy(self.handle)
                 self.handle = None
