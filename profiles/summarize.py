@@ -40,9 +40,9 @@ def launches(name):
         f.write(f'# {R}: launches of `python bench.py` ({name}) under `ncu --metrics gpu__time_duration.sum`\n\n')
         f.write('Cold-cache, serialised timings: compare shares, not absolutes.\n\n')
         if name in ('wave', 'bench'):
-            f.write('NOTE: in the real step the boundary-row launches on the side stream (`jet_simt_kernel` on a few CTAs, small '
-                    '`jet_tc_kernel` launches) run CONCURRENTLY with the interior launch and end before it (DESIGN 3.4); ncu '
-                    'serialises them, so their share below is not a share of the step.  The bench command measures every '
+            f.write('NOTE: in the real step the boundary-row launch on the side stream (`jet_simt_kernel` on a few CTAs: periodic / '
+                    'finite-difference groups) runs CONCURRENTLY with the interior launch and ends before it (DESIGN 3.4); ncu '
+                    'serialises them, so its share below is not a share of the step.  The bench command measures every '
                     'BASELINE config one after the other: kernels are listed over the whole run.\n\n')
         f.write('| kernel | launches | total | share |\n|---|---|---|---|\n')
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -82,12 +82,12 @@ def full(name):
 import json
 for n in ('wave', 'bench', 'mat'):
     launches(n)
-for n in ('jet_tc', 'jet_simt', 'jet_tcs', 'jet_tcs_ns', 'wgrad', 'mat'):
+for n in ('jet_tc', 'jet_simt', 'jet_tcs_cfg1', 'jet_tcs', 'jet_tcs_ns', 'wgrad', 'mat'):
     full(n)
 
 # dram traffic per launch of the dominant kernel of each bench workload, read by bench.py (roofline.traffic)
 traffic = {}
-for workload, reps in (('burgers_NN_cfg1', ['jet_tc']), ('wave_autograd_1e6', ['jet_tcs', 'wgrad']),
+for workload, reps in (('burgers_NN_cfg1', ['jet_tcs_cfg1']), ('wave_autograd_1e6', ['jet_tcs', 'wgrad']),
                        ('ns_autograd_1e6', ['jet_tcs_ns']), ('poisson_mat_4096', ['mat'])):
     tot, names = 0.0, []
     for name in reps:
