@@ -273,6 +273,36 @@ def poisson_mat(api, dtype='float32', n=32, derivative_points=2, ny=None):
                    mat_shape=(1, n + 1, ny + 1))
 
 
+def poisson_robin_mat(api, dtype='float32', n=24, ny=31, derivative_points=2):
+    """Poisson in mat mode with `robin` conditions on two edges (alpha * u + beta * bop, tedeous/eval.py:357-388 - the
+    alpha term is counted again inside every beta term, quirk q5)."""
+    dom = api.Domain()
+    dom.variable('x', [0, 1], n, dtype=dtype)
+    dom.variable('y', [0, 1], ny, dtype=dtype)
+
+    def bop(func_coeff, deriv_coeff, axis):
+        return {'u': {'coeff': func_coeff, 'term': [None], 'pow': 1},
+                'du/dn': {'coeff': deriv_coeff, 'term': [axis], 'pow': 1}}
+    bc = api.Conditions()
+    bc.robin({'x': 0, 'y': [0, 1]}, operator=bop(1, -1, 0), value=lambda g: -g[:, 1])
+    bc.robin({'x': 1, 'y': [0, 1]}, operator=bop(2, 0.5, 0), value=0.25)
+    bc.dirichlet({'x': [0, 1], 'y': 0}, value=0)
+    bc.dirichlet({'x': [0, 1], 'y': 1}, value=lambda g: torch.sin(np.pi * g[:, 0]))
+    tdt = torch.float64 if dtype == 'float64' else torch.float32
+    xs = torch.linspace(0, 1, n + 1, dtype=tdt)
+    ys = torch.linspace(0, 1, ny + 1, dtype=tdt)
+    f = -2 * np.pi ** 2 * torch.sin(np.pi * xs)[:, None] * torch.sin(np.pi * ys)[None, :]
+    eq = api.Equation()
+    eq.add({
+        'd2u/dx2': {'coeff': 1, 'term': [0, 0], 'pow': 1},
+        'd2u/dy2': {'coeff': 1, 'term': [1, 1], 'pow': 1},
+        '-f': {'coeff': -f, 'term': [None], 'pow': 0},
+    })
+    return Problem('poisson_robin_mat', dom, bc, eq, 'mat', [],
+                   dict(lambda_operator=1, lambda_bound=[10., 100.], derivative_points=derivative_points),
+                   mat_shape=(1, n + 1, ny + 1))
+
+
 def heat_mat(api, dtype='float32', n=32, nt=32, derivative_points=2):
     """Linear constant-coefficient operator with different stencil reach per axis: u_t - 0.1 u_xx + 0.5 u - f."""
     dom = api.Domain()
@@ -526,6 +556,7 @@ ZOO: Dict[str, Callable] = {
     'nonlinear_mix_autograd': lambda api, dt: nonlinear_mix(api, dt, mode='autograd'),
     'nonlinear_mix_NN': lambda api, dt: nonlinear_mix(api, dt, mode='NN'),
     'poisson_mat_p2': lambda api, dt: poisson_mat(api, dt, n=32, derivative_points=2),
+    'poisson_robin_mat': lambda api, dt: poisson_robin_mat(api, dt),
     'poisson_mat_p3': lambda api, dt: poisson_mat(api, dt, n=24, derivative_points=3),
     'kdv_mat_p2': lambda api, dt: kdv_mat(api, dt, n=24, derivative_points=2),
     'schrodinger_mat_p2': lambda api, dt: schrodinger_mat(api, dt),

@@ -76,3 +76,17 @@ def test_one_dimensional_grid_is_lifted(name):
     assert float(out[0]) == pytest.approx(float(g['loss']), rel=1e-6)
     gref = g['grad']
     assert np.linalg.norm(grad.reshape(-1).numpy() - gref) <= 1e-6 * np.linalg.norm(gref)
+
+
+def test_robin_rows_in_mat_mode():
+    """`robin` conditions in mat mode (tedeous/eval.py:357-388, quirk q5: the alpha term counted again in every beta term)
+    are lowered as boundary-operator rows; the dense fp64 interpretation of the IR reproduces the reference fixture."""
+    import numpy as np
+    from mat_interp import evaluate_mat_ir
+    from test_distributed_cpu import _mat_ir
+    g, ir, u = _mat_ir('poisson_robin_mat', (0, 1))
+    assert ir.bnd_types == ['robin', 'dirichlet']
+    out, grad = evaluate_mat_ir(ir, u)
+    assert float(out[0]) == pytest.approx(float(g['loss']), rel=1e-6)
+    gref = g['grad']
+    assert np.linalg.norm(grad.reshape(-1).numpy() - gref) <= 1e-6 * np.linalg.norm(gref)

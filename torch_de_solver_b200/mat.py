@@ -218,7 +218,7 @@ class MatIR:
             slot = self.bnd_types.index(kind)
             bop = bc['bop']
             if kind == 'robin':
-                raise UnsupportedProblem('robin conditions in mat mode')
+                bop = _robin_operator(bop, int(bc['var']))
             if kind == 'periodic':
                 sides = [cell_indices(grid, b) for b in bc['bnd']]
                 K = len(sides)
@@ -330,6 +330,27 @@ class MatIR:
         self.cells = (torch.cat(cells) if cells else torch.zeros(0, dtype=torch.int64)).to(device, torch.int32).contiguous()
         self.targets = (torch.cat(targets) if targets else torch.zeros(0, device=device)).contiguous()
         self.n_bc_rows = int(self.targets.numel())
+
+
+def _robin_operator(bop: dict, var: int) -> dict:
+    """`Bounds._apply_robin` (tedeous/eval.py:357-388) as a boundary operator: alpha * u + sum_beta beta * (the whole bop
+    applied), alpha and the betas being the coefficients of bop's terms - the alpha * u term is counted again inside
+    every beta term, reproduced.  Numeric alpha / beta (in mat mode the reference would call a callable
+    one on cell positions, not on coordinates)."""
+    labels = list(bop.keys())
+    coeffs = [bop[k]['coeff'] for k in labels]
+    for c in coeffs:
+        if not isinstance(c, (int, float)) and not (isinstance(c, torch.Tensor) and c.numel() == 1):
+            raise UnsupportedProblem('robin conditions in mat mode take numeric coefficients')
+    alpha, betas = float(coeffs[0]), [float(c) for c in coeffs[1:]]
+    dif = list(bop[labels[0]].keys())[1]
+    out = {'robin:alpha*u': {'coeff': alpha, dif: [[None]], 'pow': [1], 'var': [var]}}
+    for i, beta in enumerate(betas):
+        for k in labels:
+            t = dict(bop[k])
+            t['coeff'] = beta * float(t['coeff'])
+            out[f'robin:beta{i}*{k}'] = t
+    return out
 
 
 def exchange_halos(u: torch.Tensor, ir: MatIR, group=None, ext: Optional[torch.Tensor] = None) -> torch.Tensor:
