@@ -240,18 +240,25 @@ void tdb200_mat_plan_destroy(tdb200_mat_plan* plan);
 /* ---- peer-memory exchange for sharded mat mode ("direct peer loads over NVLink") ----------------------
  * One process per GPU on one box.  Every rank creates a peer object (an exchange block in its own memory), publishes its
  * 64-byte CUDA-IPC handle by the host's own means, and opens the handles of all ranks (in rank order, world x 64 bytes).
+ * (halo_floats: one side's halo block of sharded mat mode, 0 if unused; vec_floats: capacity of tdb200_peer_allreduce_vec.)
  * tdb200_peer_halo then moves the halo rows of the slab decomposition (the first / last `rows_floats` owned floats of each
  * of the n_var fields, offsets in floats from ext_dev) into the neighbours' extended slabs, and tdb200_peer_allreduce
  * sums a short vector (<= 64 floats: the loss terms) over all ranks in rank order - each ONE small kernel of this library
  * (flags with system-scope release / acquire over NVLink, bounded waits), plain stream work that a CUDA graph captures.
  * They are collective: every rank must enqueue the same sequence of calls.  The reference has no multi-GPU path. */
 typedef struct tdb200_peer tdb200_peer;
-int tdb200_peer_create(int32_t rank, int32_t world, int64_t halo_floats, int32_t device, tdb200_peer** out);
+int tdb200_peer_create(int32_t rank, int32_t world, int64_t halo_floats, int64_t vec_floats, int32_t device,
+                       tdb200_peer** out);
 int tdb200_peer_handle(tdb200_peer* peer, void* handle_out_64_bytes);
 int tdb200_peer_open(tdb200_peer* peer, const void* handles_world_x_64_bytes);
 int tdb200_peer_halo(tdb200_peer* peer, float* ext_dev, int64_t var_stride, int32_t n_var, int64_t rows_floats,
                      int64_t own_first, int64_t own_last, int64_t halo_up, int64_t halo_down, void* stream);
 int tdb200_peer_allreduce(tdb200_peer* peer, float* out_dev, int32_t n, void* stream);
+/* Sum of a longer vector (<= vec_floats of tdb200_peer_create; the buffer must be readable / writable up to the next
+ * multiple of 4 floats) over all ranks, in rank order; tdb200_plan_set_peer makes tdb200_loss_grad end with it instead of
+ * ncclAllReduce (NN / autograd modes on one box). */
+int tdb200_peer_allreduce_vec(tdb200_peer* peer, float* vec_dev, int64_t n, void* stream);
+int tdb200_plan_set_peer(tdb200_plan* plan, tdb200_peer* peer);
 int tdb200_peer_error(tdb200_peer* peer, int32_t* error_out);     /* 1: a wait timed out (a rank fell out of step) */
 void tdb200_peer_destroy(tdb200_peer* peer);
 

@@ -32,8 +32,13 @@ def main():
     dist.init_process_group('nccl', device_id=dev)
     torch.set_default_device(dev)
     sol_lib = build((rank, world), dev, 'library')
-    assert sol_lib._plan.has_comm
+    assert sol_lib._plan.has_comm and sol_lib._plan._peer is None
     out_lib = sol_lib._run_plan()[0].double().cpu().numpy()
+    os.environ['TDB200_COLLECTIVE'] = 'peer'              # the all-reduce over CUDA-IPC mapped peer memory (csrc/peer.cu)
+    sol_peer = build((rank, world), dev, 'library')
+    assert sol_peer._plan.has_comm and sol_peer._plan._peer is not None
+    out_nccl = sol_peer._run_plan()[0].double().cpu().numpy()
+    os.environ.pop('TDB200_COLLECTIVE')
     sol_t = build((rank, world), dev, 'torch')
     assert not sol_t._plan.has_comm
     out_t = sol_t._run_plan()[0].double().cpu().numpy()
@@ -44,7 +49,7 @@ def main():
     if rank == 0:
         out_1 = build(None, dev)._run_plan()[0].double().cpu().numpy()
         k = 2 + sol_lib._n_slots
-        for what, o in (('library', out_lib), ('torch.distributed', out_t), ('library, CUDA graph', out_graph)):
+        for what, o in (('library', out_lib), ('library (peer memory)', out_nccl), ('torch.distributed', out_t), ('library, CUDA graph', out_graph)):
             rel_l = abs(o[0] - out_1[0]) / abs(out_1[0])
             rel_g = np.linalg.norm(o[k:] - out_1[k:]) / np.linalg.norm(out_1[k:])
             print(f'{world} ranks, {what}: loss {o[0]:.8f} vs single rank {out_1[0]:.8f} (rel {rel_l:.2e}); grad rel err {rel_g:.2e}')

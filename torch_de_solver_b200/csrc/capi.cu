@@ -110,6 +110,7 @@ struct tdb200_plan {
   long long tcs_stream_stride = 0;             // floats per layer array
   int tcs_chunk_tiles = 0;
   void* comm = nullptr;                        // NCCL communicator of the plan (tdb200_plan_comm_init), or none
+  tdb200_peer* peer = nullptr;                 // peer-memory exchange (tdb200_plan_set_peer): replaces the NCCL all-reduce
 };
 
 static int points_per_tile(int J, int K) {
@@ -416,6 +417,11 @@ int tdb200_comm_create(const void* unique_id, int32_t rank, int32_t world, int32
 
 void tdb200_comm_destroy(tdb200_comm* comm) { tdb::comm_destroy(comm); }
 
+int tdb200_plan_set_peer(tdb200_plan* p, tdb200_peer* peer) {
+  if (!p) return fail(TDB200_ERR_INVALID, "null plan");
+  p->peer = peer;                                        // borrowed, like the communicator
+  return TDB200_OK;
+}
 int tdb200_plan_set_comm(tdb200_plan* p, tdb200_comm* comm) {
   if (!p) return fail(TDB200_ERR_INVALID, "null plan");
   p->comm = comm;                                        // borrowed: the caller keeps the communicator alive
@@ -752,6 +758,10 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
     CU(tdb::launch_reduce_partials(p->part_grad, do_grad ? grad_rows : 0, p->part_loss, loss_rows,
                                    do_grad ? a.n_params : 0, a.n_params_pad, p->n_slots, p->d_slot_lambda,
                                    p->d_slot_len, out, s));
+    if (p->peer) {      // one box: sum over peer memory (csrc/peer.cu), one small kernel of the library
+      const int rc = tdb200_peer_allreduce_vec(p->peer, out, (int64_t)(2 + p->n_slots + (do_grad ? a.n_params : 0)), s);
+      if (rc != TDB200_OK) return rc;
+    } else
     if (p->comm) {      // ranks hold row blocks with global denominators: the per-rank vectors simply add
       const int rc = tdb::comm_all_reduce_sum(p->comm, out, (size_t)(2 + p->n_slots + (do_grad ? a.n_params : 0)), s);
       if (rc != TDB200_OK) return rc;

@@ -36,6 +36,7 @@ struct PeerHeader {
   unsigned int error;         // a wait timed out
   unsigned int pad;
   unsigned int loss_flag[kPeerMaxWorld];                 // [rank]: last step whose loss terms that rank has pushed
+  unsigned int vec_flag[kPeerMaxWorld];                  // [rank]: last step whose vector that rank has pushed
   float loss[2][kPeerMaxWorld][kPeerMaxLoss];            // [parity][rank][term]
 };
 
@@ -44,10 +45,11 @@ struct PeerHeader {
 struct tdb200_peer {
   int rank = 0, world = 1, device = 0;
   long long halo_floats = 0;                    // floats of one side's halo block
+  long long vec_floats = 0;                     // capacity of the vector all-reduce (floats, multiple of 4)
   void* mine = nullptr;                         // my exchange block
   void* blocks[tdb::kPeerMaxWorld] = {};        // every rank's block as seen from this device (mine included)
   bool opened[tdb::kPeerMaxWorld] = {};
-  unsigned int* step_dev = nullptr;             // [2] device step counters (halo, loss): advanced by the kernels
+  unsigned int* step_dev = nullptr;             // device step counters (halo, loss, halo-leave, vec, vec-arrive, vec-leave)
 };
 
 namespace tdb {
@@ -153,6 +155,59 @@ __global__ void __launch_bounds__(128) peer_loss_kernel(PeerBlocks blocks, int r
   if (threadIdx.x == 0) step_dev[1] = step;
 }
 
+// All-reduce (sum) of a vector of n floats (the [loss terms | gradient] vector of the NN / autograd modes, 82 KB for the
+// 2-100-100-100-1 net) over all ranks: every CTA pushes its slice of the vector into row `rank` of every rank's inbox,
+// the last CTA to finish (device-scope counter) fences and release-stores the step number into every rank's flag; then
+// every CTA waits for all local flags and adds its slice of the `world` rows in rank order (bit-identical on every
+// rank).  vec inbox: [2 parities][world][vec_floats] behind the halo inbox.
+__global__ void __launch_bounds__(256) peer_vec_kernel(PeerBlocks blocks, int rank, int world, unsigned int* step_dev,
+                                                       float* vec, int n, long long vec_off_floats, long long vec_floats) {
+  const unsigned int step = step_dev[3] + 1;
+  const int parity = step & 1;
+  PeerHeader* const hdr = reinterpret_cast<PeerHeader*>(blocks.b[rank]);
+  const int n4 = (n + 3) / 4;
+  const int per = (n4 + gridDim.x - 1) / gridDim.x;
+  const int i0 = blockIdx.x * per, i1 = min(n4, i0 + per);
+  auto row_of = [&](void* block, int r) {
+    return reinterpret_cast<float4*>(reinterpret_cast<float*>(reinterpret_cast<char*>(block) + sizeof(PeerHeader)) + vec_off_floats +
+                                     ((size_t)parity * world + r) * vec_floats);
+  };
+  // the tail of the last float4 may reach past n: the caller's buffer is padded to a multiple of 4 floats
+  const float4* v4 = reinterpret_cast<const float4*>(vec);
+  for (int r = 0; r < world; ++r) {
+    float4* dst = row_of(blocks.b[r], rank);
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) dst[i] = v4[i];
+  }
+  __shared__ unsigned int ok;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ok = 1;
+    __threadfence_system();
+    if (atomicAdd(step_dev + 4, 1u) + 1 == gridDim.x) {                      // every CTA's slice is out (and fenced)
+      __threadfence_system();
+      for (int r = 0; r < world; ++r) st_release_sys(&reinterpret_cast<PeerHeader*>(blocks.b[r])->vec_flag[rank], step);
+    }
+    for (int r = 0; r < world; ++r)
+      if (!wait_seq(&hdr->vec_flag[r], step)) { ok = 0; hdr->error = 1; }
+  }
+  __syncthreads();
+  if (ok) {
+    float4* out4 = reinterpret_cast<float4*>(vec);
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < world; ++r) {
+        const float4 t = __ldcv(row_of(blocks.b[rank], r) + i);
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+      }
+      out4[i] = s;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(step_dev + 5, 1u) + 1 == gridDim.x) {      // last CTA out: counters for the next call
+    step_dev[4] = 0; step_dev[5] = 0; step_dev[3] = step;
+  }
+}
+
 static int peer_fail(cudaError_t e, const char* what) {
   tdb200_set_error_((std::string(what) + ": " + cudaGetErrorString(e)).c_str());
   return TDB200_ERR_CUDA;
@@ -164,19 +219,21 @@ static int peer_fail(cudaError_t e, const char* what) {
 
 extern "C" {
 
-int tdb200_peer_create(int32_t rank, int32_t world, int64_t halo_floats, int32_t device, tdb200_peer** out) {
-  if (!out || world < 1 || world > tdb::kPeerMaxWorld || rank < 0 || rank >= world || halo_floats < 0 || halo_floats % 4) {
-    tdb200_set_error_("tdb200_peer_create: bad argument (world <= 16, halo floats a multiple of 4)");
+int tdb200_peer_create(int32_t rank, int32_t world, int64_t halo_floats, int64_t vec_floats, int32_t device,
+                       tdb200_peer** out) {
+  if (!out || world < 1 || world > tdb::kPeerMaxWorld || rank < 0 || rank >= world || halo_floats < 0 || halo_floats % 4 ||
+      vec_floats < 0 || vec_floats % 4) {
+    tdb200_set_error_("tdb200_peer_create: bad argument (world <= 16, halo / vector floats multiples of 4)");
     return TDB200_ERR_INVALID;
   }
   PCU(cudaSetDevice(device));
   auto* p = new tdb200_peer();
-  p->rank = rank; p->world = world; p->device = device; p->halo_floats = halo_floats;
-  const size_t bytes = sizeof(tdb::PeerHeader) + (size_t)4 * halo_floats * sizeof(float);
+  p->rank = rank; p->world = world; p->device = device; p->halo_floats = halo_floats; p->vec_floats = vec_floats;
+  const size_t bytes = sizeof(tdb::PeerHeader) + ((size_t)4 * halo_floats + (size_t)2 * world * vec_floats) * sizeof(float);
   PCU(cudaMalloc(&p->mine, bytes));
   PCU(cudaMemset(p->mine, 0, bytes));
-  PCU(cudaMalloc(&p->step_dev, 4 * sizeof(unsigned int)));
-  PCU(cudaMemset(p->step_dev, 0, 4 * sizeof(unsigned int)));
+  PCU(cudaMalloc(&p->step_dev, 8 * sizeof(unsigned int)));
+  PCU(cudaMemset(p->step_dev, 0, 8 * sizeof(unsigned int)));
   PCU(cudaDeviceSynchronize());
   p->blocks[rank] = p->mine;
   *out = p;
@@ -234,6 +291,25 @@ int tdb200_peer_allreduce(tdb200_peer* p, float* out_dev, int32_t n, void* strea
     b.b[r] = p->blocks[r];
   }
   tdb::peer_loss_kernel<<<1, 128, 0, static_cast<cudaStream_t>(stream)>>>(b, p->rank, p->world, p->step_dev, out_dev, n);
+  PCU(cudaGetLastError());
+  return TDB200_OK;
+}
+
+int tdb200_peer_allreduce_vec(tdb200_peer* p, float* vec_dev, int64_t n, void* stream) {
+  if (!p || !vec_dev || n < 1 || n > p->vec_floats) {
+    tdb200_set_error_("tdb200_peer_allreduce_vec: 1 .. vec_floats (tdb200_peer_create) floats");
+    return TDB200_ERR_INVALID;
+  }
+  tdb::PeerBlocks b{};
+  for (int r = 0; r < p->world; ++r) {
+    if (!p->blocks[r]) { tdb200_set_error_("tdb200_peer_allreduce_vec: tdb200_peer_open was not called"); return TDB200_ERR_INVALID; }
+    b.b[r] = p->blocks[r];
+  }
+  const int n4 = (int)((n + 3) / 4);
+  int grid = (n4 + 1023) / 1024;                 // >= 4 float4 per thread
+  grid = grid < 1 ? 1 : grid > 32 ? 32 : grid;
+  tdb::peer_vec_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(b, p->rank, p->world, p->step_dev, vec_dev, (int)n,
+                                                                            4 * p->halo_floats, p->vec_floats);
   PCU(cudaGetLastError());
   return TDB200_OK;
 }

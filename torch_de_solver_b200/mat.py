@@ -332,6 +332,28 @@ class MatIR:
         self.n_bc_rows = int(self.targets.numel())
 
 
+def open_peer(lib, handle, created: bool, world: int, group=None) -> bool:
+    """Collective: exchanges the CUDA-IPC handles of the ranks' exchange blocks over torch.distributed and maps them
+    (csrc/peer.cu).  True on every rank if every rank sits on the same host and could map every block; otherwise the
+    object is destroyed everywhere and False is returned (the callers fall back to NCCL)."""
+    import os
+    import torch.distributed as dist
+    mine = (C.c_char * 64)()
+    ok = created and lib.tdb200_peer_handle(handle, mine) == 0
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (bytes(mine.raw) if ok else None, os.uname().nodename), group=group)
+    same_box = all(g[0] is not None and g[1] == gathered[0][1] for g in gathered)
+    if same_box:
+        same_box = lib.tdb200_peer_open(handle, b''.join(g[0] for g in gathered)) == 0
+    flags = [None] * world
+    dist.all_gather_object(flags, bool(same_box), group=group)               # all ranks take the same path
+    if all(flags):
+        return True
+    if created:
+        lib.tdb200_peer_destroy(handle)
+    return False
+
+
 def _robin_operator(bop: dict, var: int) -> dict:
     """`Bounds._apply_robin` (tedeous/eval.py:357-388) as a boundary operator: alpha * u + sum_beta beta * (the whole bop
     applied), alpha and the betas being the coefficients of bop's terms - the alpha * u term is counted again inside
@@ -478,21 +500,9 @@ class MatPlan:
             return
         handle = C.c_void_p()
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        ok = self.lib.tdb200_peer_create(rank, world, n_var * ir.halo * n1, dev_index, C.byref(handle)) == 0
-        mine = (C.c_char * 64)()
-        ok = ok and self.lib.tdb200_peer_handle(handle, mine) == 0
-        gathered = [None] * world
-        dist.all_gather_object(gathered, (bytes(mine.raw) if ok else None, os.uname().nodename), group=self._pg)
-        same_box = all(g[0] is not None and g[1] == gathered[0][1] for g in gathered)
-        if same_box:
-            buf = b''.join(g[0] for g in gathered)
-            same_box = self.lib.tdb200_peer_open(handle, buf) == 0
-        flags = [None] * world
-        dist.all_gather_object(flags, bool(same_box), group=self._pg)        # all ranks take the same path
-        if all(flags):
+        ok = self.lib.tdb200_peer_create(rank, world, n_var * ir.halo * n1, 0, dev_index, C.byref(handle)) == 0
+        if open_peer(self.lib, handle, ok, world, self._pg):
             self._peer = handle
-        elif ok:
-            self.lib.tdb200_peer_destroy(handle)
 
     def _push_bcs(self):
         lam = np.asarray(self.slot_lambda, np.float64)

@@ -145,11 +145,34 @@ class FusedPlan:
         """Lends the plan this process's NCCL communicator under the C ABI (made once per process group: the 128-byte
         unique id comes from rank 0 through torch.distributed); afterwards every loss_grad call all-reduces its output
         inside the library."""
+        import os
+        # peer-memory all-reduce: opt-in (TDB200_COLLECTIVE=peer).  Measured on 2 GPUs, BASELINE config 1: 0.134 ms per
+        # step against 0.136 ms with ncclAllReduce - the cost of the step over several ranks is the rendezvous itself
+        if os.environ.get('TDB200_COLLECTIVE', 'nccl') == 'peer' and self._peer_init(rank, world, group):
+            self.has_comm = True
+            return
         _native.check(self.lib.tdb200_plan_set_comm(self.handle, library_comm(self.lib, self.device, rank, world, group)),
                       'tdb200_plan_set_comm')
         self.has_comm = True
 
+    def _peer_init(self, rank: int, world: int, group=None) -> bool:
+        """Ranks = GPUs of one box: the all-reduce of the [loss terms | gradient] vector runs over CUDA-IPC mapped peer
+        memory (csrc/peer.cu, `tdb200_peer_allreduce_vec`: every rank pushes its vector into every rank's inbox and adds
+        the rows in rank order) - one small kernel of the library behind the reduction kernel instead of ncclAllReduce.
+        False (nothing changed) when the blocks cannot be mapped, e.g. ranks on different hosts."""
+        from .mat import open_peer
+        handle = C.c_void_p()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        cap = (self.out_size + 3) // 4 * 4
+        created = self.lib.tdb200_peer_create(rank, world, 0, cap, dev_index, C.byref(handle)) == 0
+        if not open_peer(self.lib, handle, created, world, group):
+            return False
+        self._peer = handle
+        _native.check(self.lib.tdb200_plan_set_peer(self.handle, handle), 'tdb200_plan_set_peer')
+        return True
+
     has_comm = False
+    _peer = None
 
     def set_interior_rows(self, pts: torch.Tensor, n_valid: int):
         """Mini-batching (tedeous/eval.py:124-141, 174-182): replace the points of the interior segment by `pts` (as many rows
@@ -188,7 +211,7 @@ class FusedPlan:
 
     def loss_grad(self) -> torch.Tensor:
         """-> flat [2 + n_slots + n_params] tensor (loss, loss_normalized, slot MSEs, gradient)."""
-        out = torch.empty(self.out_size, dtype=torch.float32, device=self.device)
+        out = torch.empty(self.out_size + 3, dtype=torch.float32, device=self.device)[:self.out_size]   # (float4 tail of the peer all-reduce)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _native.check(self.lib.tdb200_loss_grad(self.handle, self._param_ptrs(), out.data_ptr(), stream),
                       'tdb200_loss_grad')
@@ -213,7 +236,7 @@ class FusedPlan:
 
     def eval_fields(self) -> Tuple[torch.Tensor, torch.Tensor]:
         fields = torch.empty(max(self.n_fields, 1), dtype=torch.float32, device=self.device)
-        out = torch.empty(self.out_size, dtype=torch.float32, device=self.device)
+        out = torch.empty(self.out_size + 3, dtype=torch.float32, device=self.device)[:self.out_size]   # (float4 tail of the peer all-reduce)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _native.check(self.lib.tdb200_eval_fields(self.handle, self._param_ptrs(), fields.data_ptr(),
                                                   out.data_ptr(), stream), 'tdb200_eval_fields')
@@ -236,6 +259,9 @@ class FusedPlan:
             if getattr(self, 'handle', None):
                 self.lib.tdb200_plan_destroy(self.handle)
                 self.handle = None
+            if getattr(self, '_peer', None):
+                self.lib.tdb200_peer_destroy(self._peer)
+                self._peer = None
         except Exception:
             pass
 
