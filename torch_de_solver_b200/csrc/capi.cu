@@ -583,7 +583,7 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
     xa.slot_base = p->tcs_slot_base;
     tdb::WgradArgs wa{};
     wa.gs = p->tcs_gs; wa.ys = p->tcs_ys; wa.stream_stride = p->tcs_stream_stride;
-    wa.W = a.widths[1]; wa.Wp = Wp; wa.n_mma = NM; wa.kb = 32; wa.splits = gG / NM > 0 ? gG / NM : 1;
+    wa.W = a.widths[1]; wa.Wp = Wp; wa.n_mma = NM; wa.kb = tdb::wgrad_kb(); wa.splits = gG / NM > 0 ? gG / NM : 1;
     wa.part = p->part_grad + (size_t)rowsA * a.n_params_pad; wa.n_params_pad = a.n_params_pad;
     for (int t = 1; t <= NM; ++t) wa.w_off[t - 1] = a.w_off[t];
     if (gG < NM) return fail(TDB200_ERR_INVALID, "streamed tcgen05 path: fewer CTAs than W x W layers");
@@ -637,7 +637,7 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
       CU(tdb::launch_jet_tcs(xe, xa, e.sig[0], e.sig[1], e.sig[2], ge, s));
       if (do_grad) {
         wa.total4 = (long long)e.tiles * 4 * Qe * Wp;
-        wa.kb = 32;
+        wa.kb = tdb::wgrad_kb();
         wa.accumulate = 1;
         CU(tdb::launch_wgrad_gemm(wa, gG, s));
       }

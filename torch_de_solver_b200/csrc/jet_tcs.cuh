@@ -52,5 +52,6 @@ cudaError_t launch_jet_tcs_g1(const JetArgs& a, const TcsArgs& x, int o0, int o1
 cudaError_t launch_jet_tcs_g2(const JetArgs& a, const TcsArgs& x, int o0, int o1, int o2, int grid, cudaStream_t s);
 cudaError_t launch_jet_tcs_g3(const JetArgs& a, const TcsArgs& x, int o0, int o1, int o2, int grid, cudaStream_t s);
 cudaError_t launch_wgrad_gemm(const WgradArgs& a, int grid, cudaStream_t s);
+int wgrad_kb();                 // K rows (stream columns) per pipeline stage the kernel was built with
 
 }  // namespace tdb

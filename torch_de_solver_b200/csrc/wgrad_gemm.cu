@@ -21,9 +21,15 @@
 
 namespace tdb {
 
-constexpr int kWgKB = 32;                          // rows (K) per stage: four K-steps (16-row stages with a 10-deep raw
+#ifndef TDB_WG_KB
+#define TDB_WG_KB 32
+#endif
+#ifndef TDB_WG_RAW
+#define TDB_WG_RAW 3
+#endif
+constexpr int kWgKB = TDB_WG_KB;                          // rows (K) per stage: four K-steps (16-row stages with a 10-deep raw
                                                    // ring measured slower: 2.32 vs 1.87 ms on the wave workload)
-constexpr int kWgRawStages = 3, kWgImgStages = 2;
+constexpr int kWgRawStages = TDB_WG_RAW, kWgImgStages = 2;
 constexpr int kWgBlock = 4;                        // consecutive stages a CTA takes per round-robin turn
 constexpr int kWgImg = 4 * kWgKB * 32;             // floats of one operand image: 4 MN blocks x 16 K rows x 32
 constexpr int kWgImgStageFloats = 4 * kWgImg;      // A hi, A lo, B hi, B lo = 64 KB
@@ -228,6 +234,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const WgradAr
   }
   if (warp == kWgConvWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" :: "r"(tmem) : "memory");
 }
+
+int wgrad_kb() { return kWgKB; }
 
 cudaError_t launch_wgrad_gemm(const WgradArgs& a, int grid, cudaStream_t s) {
   static bool configured = false;
