@@ -27,7 +27,27 @@ class Problem:
     train_steps: int = 0             # fixture state: weights after this many reference Adam steps (lr 1e-3)
 
 
+class InitWithParams(str):
+    """An `init` name that also carries trainable scalar coefficients (inverse problems, tedeous/models.py:183-195
+    `parameter_registr`): `make_net` registers them on the net and calls `bind(net)`, which puts the live Parameter
+    objects into the equation's terms (the reference example does the same by hand:
+    examples/examples_burgers/example_burgers_1d_inverse.py:59-88)."""
+    def __new__(cls, name, params, bind):
+        obj = super().__new__(cls, name)
+        obj.params, obj.bind = dict(params), bind
+        return obj
+
+
 def make_net(layers: List[int], dtype=torch.float32, init='default', seed=0) -> torch.nn.Sequential:
+    net = _make_net(layers, dtype, init, seed)
+    if isinstance(init, InitWithParams):
+        for key, value in init.params.items():
+            net.register_parameter(key, torch.nn.Parameter(torch.tensor([value], dtype=dtype)))
+        init.bind(net)
+    return net
+
+
+def _make_net(layers: List[int], dtype=torch.float32, init='default', seed=0) -> torch.nn.Sequential:
     torch.manual_seed(seed)
     mods = []
     for i in range(len(layers) - 1):
@@ -86,6 +106,40 @@ def burgers(api, dtype='float32', n=100, mode='NN', layers=(2, 100, 100, 100, 1)
     if tol:
         kw['tol'] = tol                 # causal loss (tedeous/losses.py:137-182)
     return Problem(f'burgers_{mode}', dom, bc, eq, mode, list(layers), kw)
+
+
+# --- inverse problem: trainable coefficients (examples/examples_burgers/example_burgers_1d_inverse.py:59-88) -----
+def burgers_inverse(api, dtype='float32', n=30, mode='autograd', layers=(2, 100, 100, 100, 1), h=0.01):
+    """Burgers with the convection and diffusion coefficients as trainable scalars registered on the net, a `data`
+    condition on scattered points next to the Dirichlet ones."""
+    dom = api.Domain()
+    dom.variable('x', [-1, 1], n, dtype=dtype)
+    dom.variable('t', [0, 1], n, dtype=dtype)
+    tdt = torch.float64 if dtype == 'float64' else torch.float32
+    bc = api.Conditions()
+    bc.dirichlet({'x': [-1, 1], 't': 0}, value=lambda g: -torch.sin(np.pi * g[:, 0]))
+    bc.dirichlet({'x': -1, 't': [0, 1]}, value=0)
+    gen = torch.Generator(device='cpu').manual_seed(7)
+    pts = torch.rand(40, 2, generator=gen, dtype=torch.float64, device='cpu').to(torch.empty(0).device)
+    pts[:, 0] = 2 * pts[:, 0] - 1
+    vals = -torch.sin(np.pi * pts[:, 0]) * torch.exp(-pts[:, 1])
+    bc.data(bnd=pts.to(tdt), operator=None, value=vals.to(tdt))
+    eq_dict = {
+        'du/dt**1': {'coeff': 1., 'du/dt': [1], 'pow': 1, 'var': 0},
+        '+lam1*u*du/dx': {'coeff': None, 'u*du/dx': [[None], [0]], 'pow': [1, 1], 'var': [0, 0]},
+        '-lam2*d2u/dx2': {'coeff': None, 'd2u/dx2': [0, 0], 'pow': 1, 'var': 0},
+    }
+    eq = api.Equation()
+    eq.add(eq_dict)
+
+    def bind(net):
+        eq_dict['+lam1*u*du/dx']['coeff'] = net.lam1
+        eq_dict['-lam2*d2u/dx2']['coeff'] = net.lam2
+    kw = dict(lambda_operator=1, lambda_bound=100)
+    if mode == 'NN':
+        kw['h'] = h
+    return Problem(f'burgers_inverse_{mode}', dom, bc, eq, mode, list(layers), kw,
+                   init=InitWithParams('xavier_b', {'lam1': 2., 'lam2': -0.2}, bind))
 
 
 # --- config 2: wave (examples/examples_wave/example_wave_1d_basic.py:36-97) ---------------------------------
@@ -526,6 +580,7 @@ ZOO: Dict[str, Callable] = {
     'mixed_elliptic_autograd': lambda api, dt: mixed_elliptic(api, dt, mode='autograd'),
     'mixed_elliptic_NN': lambda api, dt: mixed_elliptic(api, dt, n=16, mode='NN', layers=(2, 32, 32, 1)),
     'mixed_bbm_autograd': lambda api, dt: mixed_bbm(api, dt),
+    'burgers_inverse_autograd': lambda api, dt: burgers_inverse(api, dt, mode='autograd'),
     'heat_callable_autograd': lambda api, dt: heat_callable_pow(api, dt, mode='autograd'),
     'heat_callable_NN': lambda api, dt: heat_callable_pow(api, dt, n=16, mode='NN'),
     # ~10^5 points: the sizes at which the tensor-core kernels are chosen automatically (impl = 0)

@@ -740,7 +740,8 @@ def test_mini_batches_match_reference(cuda_default):
     assert float(m2.solution_cls.evaluate()[0]) == pytest.approx(float(g2['loss']), rel=LOSS_RTOL)
 
 
-@pytest.mark.parametrize('name', ['kdv_autograd', 'navier_stokes_autograd', 'burgers_NN_small', 'wave_autograd'])
+@pytest.mark.parametrize('name', ['kdv_autograd', 'navier_stokes_autograd', 'burgers_NN_small', 'wave_autograd',
+                                  'burgers_inverse_autograd'])
 def test_residual_jacobian_rows(name, cuda_default):
     """per-residual Jacobian rows (tdb200_jacobian_rows) against torch autograd through the oracle - sampled
     rows one by one (what NGD.gram_factory does, tedeous/optimizers/ngd.py:57-77), J^T c against one reverse sweep, and

@@ -716,7 +716,8 @@ class Solution:
 
     def residual_jacobian(self) -> Tuple[torch.Tensor, torch.Tensor]:
         """(J_op [N * n_eq, P], J_bnd [max_len * n_types, P]): the Jacobians of `op.reshape(-1)` and of
-        `(bval - true_bval).reshape(-1)` with respect to the flat parameter vector (`parameters_to_vector` order; rows
+        `(bval - true_bval).reshape(-1)` with respect to the flat parameter vector (`parameters_to_vector(model.parameters())`
+        order - trainable coefficients registered on the net come first there; rows
         of the zero padding of `bval` are zero) - what `NGD.gram_factory` (tedeous/optimizers/ngd.py:57-77) assembles
         from one `autograd.grad` per residual.  One SIMT launch per (segment, residual column)."""
         if self.mode == 'mat':
@@ -738,7 +739,22 @@ class Solution:
             else:
                 idx = s.row_index.to(plan.device)
                 j_bnd[idx, s.slots[0] - ir.n_eq] = plan.jacobian_rows(si, 0)
-        return j_op, j_bnd.reshape(-1, P)
+        perm = self._param_order()
+        j_bnd = j_bnd.reshape(-1, P)
+        return (j_op, j_bnd) if perm is None else (j_op[:, perm], j_bnd[:, perm])
+
+    def _param_order(self):
+        """Columns of the plan's flat gradient (W0, b0, ..., trainable coefficients last) in the order of
+        `model.parameters()` / `parameters_to_vector` (parameters registered on the net itself come FIRST there,
+        tedeous/models.py:183-195); None if the orders agree."""
+        offs, o = {}, 0
+        for p in self._plan.ir.net.param_tensors():
+            offs[id(p)] = (o, p.numel())
+            o += p.numel()
+        idx = [torch.arange(*(lambda sn: (sn[0], sn[0] + sn[1]))(offs[id(p)]), device=self._plan.device)
+               for p in self.model.parameters()]
+        idx = torch.cat(idx)
+        return None if torch.equal(idx, torch.arange(idx.numel(), device=idx.device)) else idx
 
     def residual_jvp(self, v: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """(J_op v, J_bnd v) for a flat parameter-space vector v: the directional derivative of every residual."""
