@@ -538,7 +538,7 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
     const int gA = p->tc_grid - reserve;
     const int gG = gA;
     const int rowsA = tdb::jet_tc_partial_rows() * gA;
-    grad_rows = rowsA + (do_grad ? gG : 0);
+    grad_rows = rowsA;                     // the weight-gradient GEMM writes its dW blocks into the SAME partial rows
     loss_rows = gA;
     cudaStream_t ss = s;
     if (fork) {
@@ -584,7 +584,7 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
     tdb::WgradArgs wa{};
     wa.gs = p->tcs_gs; wa.ys = p->tcs_ys; wa.stream_stride = p->tcs_stream_stride;
     wa.W = a.widths[1]; wa.Wp = Wp; wa.n_mma = NM; wa.kb = tdb::wgrad_kb(); wa.splits = gG / NM > 0 ? gG / NM : 1;
-    wa.part = p->part_grad + (size_t)rowsA * a.n_params_pad; wa.n_params_pad = a.n_params_pad;
+    wa.part = p->part_grad; wa.n_params_pad = a.n_params_pad;         // CTA b -> row b (zero-filled by jet_tcs CTA b)
     for (int t = 1; t <= NM; ++t) wa.w_off[t - 1] = a.w_off[t];
     if (gG < NM) return fail(TDB200_ERR_INVALID, "streamed tcgen05 path: fewer CTAs than W x W layers");
     int chunk = 0;

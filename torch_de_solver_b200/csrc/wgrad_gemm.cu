@@ -14,8 +14,8 @@
 //   * warp 8 issues, per K-step of 8 rows,
 //         D[128 x 112] += gZ_hi^T Y_hi + gZ_hi^T Y_lo + gZ_lo^T Y_hi        (A = gZ image, B = Y image, both MN-major)
 //     and releases the image stage with tcgen05.commit.
-// The CTA's partial dW goes to its own row of the gradient partial buffer (reduced in a fixed order by
-// reduce_partials_kernel -> bit-reproducible).
+// The CTA's partial dW goes to its layer's block of partial row blockIdx.x, a row it shares with CTA blockIdx.x of
+// jet_tcs_kernel (reduced in a fixed order by reduce_partials_kernel -> bit-reproducible).
 #include "jet_tc_kernel.cuh"
 #include "jet_tcs.cuh"
 
@@ -60,9 +60,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const WgradAr
 
   const int layer = blockIdx.x % a.n_mma;          // 0-based: dW of W x W layer `layer + 1`
   const int split = blockIdx.x / a.n_mma;
-  if (!a.accumulate)                               // first chunk of a call: the row holds nothing but this CTA's dW block
-    for (int i = tid; i < a.n_params_pad; i += kWgThreads) a.part[(size_t)blockIdx.x * a.n_params_pad + i] = 0.f;
-  if (split >= a.splits) return;                   // idle CTA: its partial row stays zero
+  // The partial rows are shared with jet_tcs_kernel: its CTA b has zero-filled row b (first chunk of a call) and owns the
+  // bias / first-layer / last-layer entries; this CTA b owns the dW block of its layer in the same row - half the rows
+  // for reduce_partials_kernel to read and no second zero fill.
+  if (split >= a.splits) return;                   // idle CTA
   const int KB = a.kb, Wp = a.Wp;
   const int F = KB * Wp / 4;                       // float4 per operand and stage
   const long long n_kb = (a.total4 + F - 1) / F;
