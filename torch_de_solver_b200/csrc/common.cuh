@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "tdb200.h"
 
 namespace tdb {
@@ -57,6 +58,27 @@ struct JetArgs {
   int jac_seg, jac_col;
   long long* dbg;                      // optional [gridDim.x][16] phase cycle counters (TDB200_TC_TIMING=1)
 };
+
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream still runs - once every CTA of the predecessor has executed
+// pdl_launch_dependents() (or exited) and SM resources are free; everything it does before pdl_wait() must be
+// independent of the predecessor's output.  pdl_wait() returns when the predecessor has completed and its memory
+// operations are visible.  Used to run the set-up of jet_tcs / wgrad_gemm / reduce_partials (shared-memory zero fill,
+// barrier and TMEM allocation) on SMs the predecessor has already left.  Both are no-ops in a normal launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// launch with the programmatic-serialization attribute (TDB200_NO_PDL=1: plain launch)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  static const bool off = getenv("TDB200_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = off ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // tensor-core weight images (jet_tc_kernel.cuh): K-major SWIZZLE_128B, [4 k-blocks][104 rows][32 floats] per image
 constexpr int kTcWRows = 104;                    // rows of the weight image (neurons padded to 8)

@@ -23,6 +23,7 @@ namespace tdb {
 // the transposed weights the forward GEMMs stream.
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_params_kernel(PackArgs a) {
+  pdl_launch_dependents();             // the fused kernel behind may run its set-up next to this launch
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nth = gridDim.x * blockDim.x;
   for (int l = 0; l < a.n_layers; ++l) {
@@ -592,6 +593,7 @@ reduce_partials_kernel(const float* __restrict__ part_grad, int n_grad_rows, con
                        int n_loss_rows, int n_params, int n_params_pad, int n_slots,
                        const double* __restrict__ slot_lambda, const double* __restrict__ slot_len,
                        float* __restrict__ out) {
+  pdl_wait();
   __shared__ float gsum[kRedGroups][kRedParams];
   const int pl = threadIdx.x % kRedParams, g = threadIdx.x / kRedParams;
   const int i = blockIdx.x * kRedParams + pl;
@@ -639,7 +641,7 @@ cudaError_t launch_reduce_partials(const float* part_grad, int n_grad_rows, cons
                                    int n_loss_rows, int n_params, int n_params_pad, int n_slots,
                                    const double* slot_lambda, const double* slot_len, float* out, cudaStream_t s) {
   const int blocks = max(1, (n_params + kRedParams - 1) / kRedParams);
-  reduce_partials_kernel<<<blocks, kRedParams * kRedGroups, 0, s>>>(part_grad, n_grad_rows, part_loss, n_loss_rows, n_params,
+  return launch_pdl(reduce_partials_kernel, dim3(blocks), dim3(kRedParams * kRedGroups), 0, s, part_grad, n_grad_rows, part_loss, n_loss_rows, n_params,
                                                                    n_params_pad, n_slots, slot_lambda, slot_len, out);
   return cudaGetLastError();
 }

@@ -198,7 +198,6 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
   if (tid < kMaxCParams) (sbase + kSOffCg)[tid] = 0.f;
   for (int i = tid; i < 6 * kTcMaxPts * 4; i += kTsThreads) (sbase + kSOffX)[i] = 0.f;     // axes >= d stay zero
   for (int i = tid; i < 2 * kTcMaxOut * kTcCols; i += kTsThreads) (sbase + kSOffGu)[i] = 0.f;
-  if (tid < kTcMaxOut) (sbase + kSOffBl)[tid] = tid < n_out ? a.arena[a.b_off[L - 1] + tid] : 0.f;
   for (int i = tid; i < min(kTcMaxTerms, a.n_terms); i += kTsThreads) termS[i] = a.terms[i];
   for (int i = tid; i < min(kTcMaxFactors, a.n_factors); i += kTsThreads) facS[i] = a.factors[i];
   for (int i = tid; i < (int)(sizeof(tdb200_segment) / 4); i += kTsThreads)
@@ -216,6 +215,11 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_ptr)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // Everything above is independent of the kernel in front (pack_params_kernel, or the weight-gradient GEMM of the
+  // previous chunk, which still reads the stream buffers): with a programmatic launch it has run next to it.
+  pdl_wait();
+  pdl_launch_dependents();             // the weight-gradient GEMM behind sets itself up on the SMs this grid leaves first
+  if (tid < kTcMaxOut) (sbase + kSOffBl)[tid] = tid < n_out ? a.arena[a.b_off[L - 1] + tid] : 0.f;
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   fence_async_smem();
   tc_fence_before();
@@ -907,8 +911,7 @@ static cudaError_t launch_tcs_sig(const JetArgs& a, const TcsArgs& x, int grid, 
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  jet_tcs_kernel<O0, O1, O2, TM><<<grid, kTsThreads, kTsSmemBytes, s>>>(a, x);
-  return cudaGetLastError();
+  return launch_pdl(jet_tcs_kernel<O0, O1, O2, TM>, dim3(grid), dim3(kTsThreads), kTsSmemBytes, s, a, x);
 }
 
 #define TDB_TCS_DEFINE_GROUP(NAME, SIGS)                                                                        \

@@ -102,6 +102,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const WgradAr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
+  pdl_wait();                          // the streams (and the zero-filled partial rows) of the fused kernel are complete
+  pdl_launch_dependents();
 
   if (warp == kWgConvWarps + 1) {
     // ---- producer: HBM -> raw ring ------------------------------------------------------------------------------
@@ -245,8 +247,7 @@ cudaError_t launch_wgrad_gemm(const WgradArgs& a, int grid, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  wgrad_gemm_kernel<<<grid, kWgThreads, kWgSmemBytes, s>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(wgrad_gemm_kernel, dim3(grid), dim3(kWgThreads), kWgSmemBytes, s, a);
 }
 
 }  // namespace tdb
