@@ -297,8 +297,9 @@ def measure_nn(ctx, workload, steps, warmup, with_cpu):
     # where the step is launch bound and captured, the replay of `Solution.capture_step()` (what Model.train replays,
     # with the optimiser update behind it).
     flat = plan.flat
-    host_in = [t.detach().cpu().pin_memory() for t in (flat.points, flat.targets, flat.coeffs)]
-    dev_in = [flat.points, flat.targets, flat.coeffs]
+    # (points, targets and coefficient buffers are views of one device buffer, `flat.inputs`: one copy per step)
+    host_in = [flat.inputs.detach().cpu().pin_memory()]
+    dev_in = [flat.inputs]
     host_out = torch.empty(plan.out_size, dtype=torch.float32, device='cpu').pin_memory()
     h2d = sum(t.numel() * 4 for t in host_in)
     d2h = host_out.numel() * 4

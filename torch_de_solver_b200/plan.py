@@ -754,6 +754,7 @@ class FlatIR:
     n_fields: int
     cparam_index: Dict[int, int]
     coeff_fns: list = None           # [(offset, numel, callable, rows, (lo, hi) | None, segment)]: callable-coefficient buffers
+    inputs: torch.Tensor = None      # points | targets | coeffs as one buffer (the three tensors above are views of it)
 
 
 def flatten(ir: ProblemIR, device) -> FlatIR:
@@ -816,7 +817,22 @@ def flatten(ir: ProblemIR, device) -> FlatIR:
 
     def cat(lst):
         return torch.cat(lst).contiguous() if lst else torch.zeros(1, dtype=torch.float32, device=device)
-    return FlatIR(seg, np.array(terms, dtype=TERM_DTYPE) if terms else np.zeros(0, TERM_DTYPE),
+    # the per-step inputs - points, targets, coefficient buffers - are views of ONE device buffer (`inputs`), so a host
+    # that refreshes them every step (a data loader, bench.py's end-to-end leg) needs a single host-to-device copy
+    p_all, t_all, c_all = torch.cat(pts).contiguous(), cat(tgts), cat(coefs)
+    d_in = p_all.shape[1]
+    n_p, n_t, n_c = p_all.numel(), t_all.numel(), c_all.numel()
+    pad = lambda n: (n + 3) // 4 * 4
+    inputs = torch.zeros(pad(n_p) + pad(n_t) + pad(n_c), dtype=torch.float32, device=device)
+    inputs[:n_p] = p_all.reshape(-1)
+    inputs[pad(n_p):pad(n_p) + n_t] = t_all
+    inputs[pad(n_p) + pad(n_t):pad(n_p) + pad(n_t) + n_c] = c_all
+    p_all = inputs[:n_p].view(-1, d_in)
+    t_all = inputs[pad(n_p):pad(n_p) + n_t]
+    c_all = inputs[pad(n_p) + pad(n_t):pad(n_p) + pad(n_t) + n_c]
+    flat = FlatIR(seg, np.array(terms, dtype=TERM_DTYPE) if terms else np.zeros(0, TERM_DTYPE),
                   np.array(factors, dtype=FACTOR_DTYPE) if factors else np.zeros(0, FACTOR_DTYPE),
                   np.concatenate(comb).astype(np.float32) if comb else np.zeros(1, np.float32),
-                  torch.cat(pts).contiguous(), cat(tgts), cat(coefs), field_off, cparam_index, coeff_fns)
+                  p_all, t_all, c_all, field_off, cparam_index, coeff_fns)
+    flat.inputs = inputs
+    return flat
