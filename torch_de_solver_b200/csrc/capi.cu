@@ -455,6 +455,38 @@ static bool use_tc(const tdb200_plan* p) {
   if (!p->tc_eligible || p->impl == 1 || use_tcs(p)) return false;
   return p->impl == 2 || p->segs[0].n_groups >= 4096;
 }
+// Boundary segments with a launch pair of their own, grouped: consecutive segments of one jet signature whose loss slots
+// span < TDB200_MAX_COLS (and whose streams fit the chunk buffers) share ONE jet_tcs + wgrad launch pair.  -> [begin, end)
+// index ranges into p->tcs_extra
+static std::vector<std::pair<int, int>> tcs_extra_groups(const tdb200_plan* p) {
+  std::vector<std::pair<int, int>> out;
+  const int Wp = (p->args.widths[1] + 3) / 4 * 4;
+  for (size_t i = 0; i < p->tcs_extra.size();) {
+    const auto& e0 = p->tcs_extra[i];
+    const int Qe = (tdb::jet_tc_columns_per_part(e0.sig[0], e0.sig[1], e0.sig[2]) + 3) / 4;
+    const long long per_tile = 4LL * Qe * Wp * 4;
+    long long tiles = 0;
+    int lo = 1 << 30, hi = -1, n = 0;
+    size_t j = i;
+    for (; j < p->tcs_extra.size() && n < tdb::kTcsMaxSegs; ++j, ++n) {
+      const auto& e = p->tcs_extra[j];
+      const tdb200_segment& sg = p->segs[e.seg];
+      if (e.sig[0] != e0.sig[0] || e.sig[1] != e0.sig[1] || e.sig[2] != e0.sig[2]) break;
+      const tdb200_segment& s0 = p->segs[e0.seg];     // the launch propagates the jets of its FIRST segment's directions
+      if (j > i && (sg.n_dirs != s0.n_dirs || memcmp(sg.dir_vec, s0.dir_vec, sizeof(sg.dir_vec)) != 0 ||
+                    memcmp(sg.dir_order, s0.dir_order, sizeof(sg.dir_order)) != 0)) break;
+      int l2 = lo, h2 = hi;
+      for (int c = 0; c < sg.n_cols; ++c) { l2 = std::min(l2, sg.col_slot[c]); h2 = std::max(h2, sg.col_slot[c]); }
+      if (j > i && (h2 - l2 >= TDB200_MAX_COLS || getenv("TDB200_TCS_NO_MERGE") ||
+                    (p->tcs_stream_stride > 0 && (tiles + e.tiles) * per_tile > p->tcs_stream_stride))) break;
+      lo = l2; hi = h2;
+      tiles += e.tiles;
+    }
+    out.push_back({(int)i, (int)j});
+    i = j;
+  }
+  return out;
+}
 static int tcs_chunks(const tdb200_plan* p) {
   return p->tcs_chunk_tiles > 0 ? (p->tcs_tiles + p->tcs_chunk_tiles - 1) / p->tcs_chunk_tiles : 1;
 }
@@ -488,7 +520,7 @@ int32_t tdb200_plan_kernel_path(const tdb200_plan* p) {
 }
 int32_t tdb200_plan_launches_per_call(const tdb200_plan* p) {
   if (!p) return 0;
-  if (use_tcs(p)) return 2 + 2 * tcs_chunks(p) + 2 * (int)p->tcs_extra.size() + (p->simt_rest_all_tiles > 0 ? 1 : 0);
+  if (use_tcs(p)) return 2 + 2 * tcs_chunks(p) + 2 * (int)tcs_extra_groups(p).size() + (p->simt_rest_all_tiles > 0 ? 1 : 0);
   if (!use_tc(p)) return 3;
   return 3 + (int)p->tc_extra.size() + (p->simt_rest_tiles > 0 ? 1 : 0);
 }
@@ -620,23 +652,35 @@ static int run(tdb200_plan* p, const float* const* params, float* fields, float*
     if (dbg) cudaFree(dbg);
     // boundary segments of identity rows: the same two kernels in stream order (the stream buffers are reused), adding
     // to the partial rows of the interior launches
-    for (const auto& e : p->tcs_extra) {
-      const int Qe = (tdb::jet_tc_columns_per_part(e.sig[0], e.sig[1], e.sig[2]) + 3) / 4;
-      const long long need = (long long)e.tiles * 4 * Qe * Wp * 4;
-      if (need > p->tcs_stream_stride) return fail(TDB200_ERR_INVALID, "streamed tcgen05 path: a boundary segment exceeds the stream chunk");
+    // (consecutive segments of one jet signature - e.g. the eight Dirichlet conditions of the Navier-Stokes config - share
+    // ONE launch pair: jet_tcs_kernel walks several segments, see TcsArgs::mseg_*)
+    for (const auto& grp : tcs_extra_groups(p)) {
+      const auto& e0 = p->tcs_extra[grp.first];
+      const int Qe = (tdb::jet_tc_columns_per_part(e0.sig[0], e0.sig[1], e0.sig[2]) + 3) / 4;
+      const long long per_tile = 4LL * Qe * Wp * 4;
       tdb::JetArgs xe = call;
-      xe.segs = a.segs + e.seg;
       xe.row_weight = nullptr;
       xe.dbg = nullptr;
-      xa.tile0 = 0; xa.tile1 = e.tiles; xa.zero_partials = 0;
-      xa.n_msegs = 1; xa.mseg_index[0] = 0; xa.mseg_tile_begin[0] = 0; xa.mseg_tile_begin[1] = e.tiles;
-      xa.term_end = p->segs[e.seg].col_term_end[p->segs[e.seg].n_cols - 1];
-      xa.slot_base = p->segs[e.seg].col_slot[0];
-      for (int c = 0; c < p->segs[e.seg].n_cols; ++c) xa.slot_base = std::min(xa.slot_base, p->segs[e.seg].col_slot[c]);
-      const int ge = e.grid < gA ? e.grid : gA;
-      CU(tdb::launch_jet_tcs(xe, xa, e.sig[0], e.sig[1], e.sig[2], ge, s));
+      xa.n_msegs = 0; xa.term_end = 0;
+      int tiles = 0, slot_lo = 1 << 30;
+      for (int j = grp.first; j < grp.second; ++j) {
+        const auto& e = p->tcs_extra[j];
+        const tdb200_segment& sg = p->segs[e.seg];
+        for (int c = 0; c < sg.n_cols; ++c) slot_lo = std::min(slot_lo, sg.col_slot[c]);
+        xa.mseg_index[xa.n_msegs] = e.seg;
+        xa.mseg_tile_begin[xa.n_msegs] = tiles;
+        ++xa.n_msegs;
+        tiles += e.tiles;
+        xa.term_end = std::max(xa.term_end, (int)sg.col_term_end[sg.n_cols - 1]);
+      }
+      xa.mseg_tile_begin[xa.n_msegs] = tiles;
+      xa.slot_base = slot_lo;
+      if ((long long)tiles * per_tile > p->tcs_stream_stride) return fail(TDB200_ERR_INVALID, "streamed tcgen05 path: a boundary segment exceeds the stream chunk");
+      xa.tile0 = 0; xa.tile1 = tiles; xa.zero_partials = 0;
+      const int ge = tiles < gA ? tiles : gA;
+      CU(tdb::launch_jet_tcs(xe, xa, e0.sig[0], e0.sig[1], e0.sig[2], ge, s));
       if (do_grad) {
-        wa.total4 = (long long)e.tiles * 4 * Qe * Wp;
+        wa.total4 = (long long)tiles * 4 * Qe * Wp;
         wa.kb = tdb::wgrad_kb();
         wa.accumulate = 1;
         CU(tdb::launch_wgrad_gemm(wa, gG, s));
