@@ -391,7 +391,70 @@ __global__ void __launch_bounds__(kTsThreads, 1) jet_tcs_kernel(const JetArgs a,
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(up_free);
-      if (lane < p_valid && fast_op) {
+      if (fast_op && ncols > 1) {
+        // Systems (Navier-Stokes: 3 equations, ~25 terms): one lane per (point, residual column) instead of one per point
+        // - the event trace showed the 16 epilogue warps waiting ~12 k cycles per tile for a warp in which 8 lanes walked
+        // all terms.  Values, residuals, seeds and the per-term gradient factors are computed in parallel; only the
+        // additions into the adjoint seeds Gu - the columns of one point share entries - happen in a fixed order
+        // (term k of column 0, 1, ...): deterministic, and two shared-memory updates per round.
+        auto pw = [](float xx, int i) { const float x2 = xx * xx; return i == 1 ? xx : i == 2 ? x2 : i == 3 ? x2 * xx : 1.f; };
+        auto dpw = [](float xx, int i) { return i == 1 ? 1.f : i == 2 ? 2.f * xx : i == 3 ? 3.f * xx * xx : 0.f; };
+        const int items = p_valid * ncols;
+        int tmax = 0;
+        for (int c = 0; c < ncols; ++c) tmax = max(tmax, sg.col_term_end[c] - sg.col_term_begin[c]);
+        for (int w0 = 0; w0 < items; w0 += 32) {
+          const int w = w0 + lane;
+          const bool act = w < items;
+          const int p = act ? w / ncols : 0, col = act ? w - p * ncols : 0;
+          const int pc = (p / PH) * kTcPC + (p % PH) * J;
+          const long long row = g_first + p;
+          const float* u = Us + pc;
+          float* gu = Gus + pc;
+          const int tb = sg.col_term_begin[col], te = sg.col_term_end[col];
+          float seed = 0.f;
+          if (act) {
+            float val = 0.f;
+            for (int t = tb; t < te; ++t) {
+              const int4 r = recS[t];
+              const float cf = r.y == 0 ? __int_as_float(r.x) : r.y == 1 ? __ldg(a.coeffs + r.x + row) : a.arena[a.n_net_params + r.x];
+              const int o0 = r.z & 0xFFFF, o1 = (r.z >> 16) & 0xFFFF;
+              const float x0 = o0 != 0xFFFF ? u[o0] : 1.f, x1 = o1 != 0xFFFF ? u[o1] : 1.f;
+              val = fmaf(cf * pw(x0, r.w & 255), pw(x1, r.w >> 8), val);
+            }
+            if (a.fields) a.fields[sg.field_off + row * ncols + col] = val;
+            const float tgt = sg.tgt_off >= 0 ? __ldg(a.targets + sg.tgt_off + row * ncols + col) : 0.f;
+            const float res = val - tgt;
+            const float rw = row_w ? __ldg(row_w + row) : 1.f;
+            lacc[sg.col_slot[col] - x.slot_base] += (double)rw * (double)res * (double)res;
+            seed = a.field_seed ? __ldg(a.field_seed + sg.field_off + row * ncols + col)
+                                : 2.f * scaleS[sg.col_slot[col]] * rw * res;
+          }
+          if (a.do_grad) {
+            for (int k = 0; k < tmax; ++k) {
+              int o0 = 0xFFFF, o1 = 0xFFFF;
+              float v0 = 0.f, v1 = 0.f;
+              if (act && tb + k < te) {
+                const int4 r = recS[tb + k];
+                const float cf = r.y == 0 ? __int_as_float(r.x) : r.y == 1 ? __ldg(a.coeffs + r.x + row) : a.arena[a.n_net_params + r.x];
+                o0 = r.z & 0xFFFF; o1 = (r.z >> 16) & 0xFFFF;
+                const float x0 = o0 != 0xFFFF ? u[o0] : 1.f, x1 = o1 != 0xFFFF ? u[o1] : 1.f;
+                const float p0 = pw(x0, r.w & 255), p1 = pw(x1, r.w >> 8), sc = seed * cf;
+                v0 = sc * dpw(x0, r.w & 255) * p1;
+                v1 = sc * p0 * dpw(x1, r.w >> 8);
+                if (r.y == 2) atomicAdd(&(sbase + kSOffCg)[r.x], seed * p0 * p1);
+              }
+              for (int c = 0; c < ncols; ++c) {
+                if (act && col == c) {
+                  if (o0 != 0xFFFF) gu[o0] += v0;
+                  if (o1 != 0xFFFF) gu[o1] += v1;
+                }
+                __syncwarp();
+              }
+            }
+          }
+          __syncwarp();
+        }
+      } else if (lane < p_valid && fast_op) {
         const int p = lane;
         const int pc = (p / PH) * kTcPC + (p % PH) * J;
         const long long row = g_first + p;
