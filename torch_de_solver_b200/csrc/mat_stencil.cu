@@ -1030,12 +1030,22 @@ __device__ __forceinline__ double mw_march_item(const MatArgs& a, const int ch, 
 template <int HY, int HX, unsigned MY, unsigned MX, int P>
 __global__ void __launch_bounds__(kMwThreads, 2) mat_march_kernel(const MatArgs a, const int ch, const int n_strips,
                                                                   const int n_items, const int n_edge_blocks,
-                                                                  float* __restrict__ edge_seeds) {
+                                                                  float* __restrict__ edge_seeds, const int pdl_halo) {
   __shared__ double red[kMwWarps];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int item = (int)blockIdx.x * kMwWarps + warp;
   const int first_edge_block = (int)gridDim.x - n_edge_blocks;
   double dacc = 0.0;
+  // Slab of a sharded grid (pdl_halo): the launch is a programmatic dependent of the halo exchange in front of it
+  // (peer_halo_kernel, csrc/peer.cu) - only the warps that READ halo rows wait for it, the rest of the slab is marched
+  // while the rows cross NVLink.
+  if (pdl_halo) {
+    if ((int)blockIdx.x >= first_edge_block) pdl_wait();
+    else if (item < n_items) {
+      const int y0 = (item / n_strips) * ch, y1 = min(y0 + ch, a.n0);
+      if (y0 - 2 * HY < a.row_lo || y1 + 2 * HY > a.row_hi) pdl_wait();
+    }
+  }
   if ((int)blockIdx.x >= first_edge_block) {                 // phase A of the edge treatment: the trailing CTAs fill the
     dacc = mw_edge_seeds(a, a.edge_y + HY, a.edge_x + HX, edge_seeds, (int)blockIdx.x - first_edge_block, n_edge_blocks);   // tail
   } else if (item < n_items) {                               // warp-uniform
@@ -1081,8 +1091,14 @@ static cudaError_t launch_mat_march_t(const MatArgs& a, int n_sms, float* edge_s
   const int grid = kMwEdgeBlocks + (n_items + kMwWarps - 1) / kMwWarps;
   // P = 5 rows of register prefetch: the deepest ring that does not spill at 128 registers (measured at 4096^2: P = 3
   // 65.6 us per step, 4: 63.4, 5: 62.6; P = 6 spills)
-  mat_march_kernel<HY, HX, MY, MX, 5><<<grid, kMwThreads, 0, s>>>(a, ch, n_strips, n_items, kMwEdgeBlocks, edge_seeds);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e;
+  if ((a.row_lo > 0 || a.row_hi < a.n0) && !getenv("TDB200_NO_PDL")) {
+    e = launch_pdl(mat_march_kernel<HY, HX, MY, MX, 5>, dim3(grid), dim3(kMwThreads), 0, s, a, ch, n_strips, n_items,
+                   (int)kMwEdgeBlocks, edge_seeds, 1);
+  } else {
+    mat_march_kernel<HY, HX, MY, MX, 5><<<grid, kMwThreads, 0, s>>>(a, ch, n_strips, n_items, kMwEdgeBlocks, edge_seeds, 0);
+    e = cudaGetLastError();
+  }
   if (e == cudaSuccess && after_stencil) e = cudaEventRecord(after_stencil, s);
   if (e != cudaSuccess || !a.grad || main_only) return e;
   mat_march_edge_kernel<<<kMwEdgeBlocks, 128, 0, s>>>(a, a.edge_y + HY, a.edge_x + HX, edge_seeds);

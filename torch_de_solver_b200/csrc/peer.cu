@@ -82,6 +82,8 @@ __global__ void __launch_bounds__(1024) peer_halo_kernel(void* mine, void* up_bl
                                                          float* ext, long long var_stride, int n_var, long long rows_floats,
                                                          long long own_first, long long own_last, long long halo_up,
                                                          long long halo_down, long long halo_floats) {
+  // the stencil launch behind may start now: its warps that read halo rows wait for this grid (griddepcontrol.wait)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int side = blockIdx.x;
   void* const nb = side == 0 ? up_block : down_block;
   const unsigned int step = step_dev[0] + 1;
