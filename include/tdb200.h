@@ -254,6 +254,10 @@ int tdb200_peer_open(tdb200_peer* peer, const void* handles_world_x_64_bytes);
 int tdb200_peer_halo(tdb200_peer* peer, float* ext_dev, int64_t var_stride, int32_t n_var, int64_t rows_floats,
                      int64_t own_first, int64_t own_last, int64_t halo_up, int64_t halo_down, void* stream);
 int tdb200_peer_allreduce(tdb200_peer* peer, float* out_dev, int32_t n, void* stream);
+/* Lets tdb200_mat_loss_grad sum its loss terms over the ranks itself: the finalizing block of the boundary kernel does
+ * what tdb200_peer_allreduce does, one launch less per step.  *inline_out = 1 if the plan's kernel schedule supports it
+ * (then the caller must NOT call tdb200_peer_allreduce on the same output), 0 otherwise. */
+int tdb200_mat_plan_set_peer(tdb200_mat_plan* plan, tdb200_peer* peer, int32_t* inline_out);
 /* Sum of a longer vector (<= vec_floats of tdb200_peer_create; the buffer must be readable / writable up to the next
  * multiple of 4 floats) over all ranks, in rank order; tdb200_plan_set_peer makes tdb200_loss_grad end with it instead of
  * ncclAllReduce (NN / autograd modes on one box). */

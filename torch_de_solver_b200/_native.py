@@ -36,7 +36,7 @@ EXPORTS = [
     'tdb200_mat_plan_out_size', 'tdb200_mat_plan_launches_per_call', 'tdb200_mat_plan_kernel_kind', 'tdb200_mat_plan_set_row_window',
     'tdb200_mat_plan_set_timing', 'tdb200_mat_plan_stencil_ms', 'tdb200_mat_time_stencil',
     'tdb200_mat_plan_destroy', 'tdb200_optimizer_step',
-    'tdb200_peer_create', 'tdb200_peer_handle', 'tdb200_peer_open', 'tdb200_peer_halo', 'tdb200_peer_allreduce', 'tdb200_peer_allreduce_vec', 'tdb200_plan_set_peer',
+    'tdb200_peer_create', 'tdb200_peer_handle', 'tdb200_peer_open', 'tdb200_peer_halo', 'tdb200_peer_allreduce', 'tdb200_peer_allreduce_vec', 'tdb200_plan_set_peer', 'tdb200_mat_plan_set_peer',
     'tdb200_peer_error', 'tdb200_peer_destroy',
     'tdb200_last_error', 'tdb200_version',
 ]
@@ -99,6 +99,7 @@ def load():
     lib.tdb200_peer_allreduce.argtypes = [vp, vp, i32, vp]
     lib.tdb200_peer_allreduce_vec.argtypes = [vp, vp, i64, vp]
     lib.tdb200_plan_set_peer.argtypes = [vp, vp]
+    lib.tdb200_mat_plan_set_peer.argtypes = [vp, vp, vp]
     lib.tdb200_peer_error.argtypes = [vp, vp]
     lib.tdb200_peer_destroy.argtypes = [vp]
     lib.tdb200_peer_destroy.restype = None

@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 #include "common.cuh"
+#include "peer_dev.cuh"
 
 namespace tdb {
 
@@ -1349,6 +1350,8 @@ struct MatBcArgs {
   float* out;
   unsigned int* ticket;                    // zero on entry, reset by the finalizing block
   unsigned int* tile_ctr;                  // tile scheduler counter of the persistent kernel, reset likewise
+  PeerLossArgs peer;                       // several ranks on one box (tdb200_mat_plan_set_peer): the finalizing block sums
+                                           // the loss terms over the ranks through peer memory (world <= 1: off)
 };
 
 __device__ float global_field(const MatBcArgs& a, const tdb200_mat_field& f, int cell) {
@@ -1567,6 +1570,10 @@ __global__ void __launch_bounds__(128) mat_edge_bc_kernel(const MatBcArgs a, con
   __threadfence();
   if (threadIdx.x == 0) { *a.ticket = 0u; *a.tile_ctr = 0u; }
   mat_finalize_block(a.part_loss, a.n_ctas, a.n_eq, a.n_cells, a.slot_sum, a.n_bc_slots, a.slot_lambda, a.slot_len, a.out);
+  if (a.peer.world > 1) {                  // (block-uniform) loss terms of all ranks, summed in rank order
+    __syncthreads();
+    peer_loss_block(a.peer.blocks, a.peer.rank, a.peer.world, a.peer.step_dev, a.out, 2 + a.n_eq + a.n_bc_slots);
+  }
 }
 
 // ordered reduction of the per-CTA loss partials + loss assembly, by one block of any size <= 256
@@ -1777,7 +1784,11 @@ thread_local std::string g_mat_err;
 extern "C" const char* tdb200_last_error(void);
 extern "C" void tdb200_set_error_(const char* msg);
 
+struct tdb200_peer;
+extern "C" int tdb200_peer_export_(tdb200_peer* p, tdb::PeerLossArgs* out);
+
 struct tdb200_mat_plan {
+  tdb200_peer* peer = nullptr;             // borrowed (tdb200_mat_plan_set_peer)
   tdb200_mat_desc desc{};
   int device = 0;
   tdb::MatArgs args{};
@@ -2207,8 +2218,10 @@ static int mat_run(tdb200_mat_plan* p, const float* u, float* grad, float* op_ou
     b.part_loss = p->d_part_loss; b.n_ctas = n_ctas; b.n_bc_slots = p->n_bc_slots;
     b.n_cells = (double)p->desc.n0 * (double)p->desc.n1;
     b.slot_lambda = p->d_slot_lambda; b.slot_len = p->d_slot_len; b.out = out; b.ticket = p->d_ticket; b.tile_ctr = p->d_ticket + 1;
+    b.peer.world = 0;
     const int blocks = (int)((p->n_bc_rows + 127) / 128);
     if (merged) {
+      if (p->peer && out) { const int rc = tdb200_peer_export_(p->peer, &b.peer); if (rc != TDB200_OK) return rc; }
       tdb::MwEdgeBc eb{};
       eb.zy3 = a.edge_y + p->cx_hy; eb.zx3 = a.edge_x + p->cx_hx; eb.n_frame_blocks = p->n_frame_blocks;
       eb.es = p->d_edge_seed; eb.csr_off = p->d_csr_off; eb.csr_ent = p->d_csr_ent;
@@ -2217,6 +2230,10 @@ static int mat_run(tdb200_mat_plan* p, const float* u, float* grad, float* op_ou
       tdb::mat_bc_kernel<<<blocks < 1184 ? blocks : 1184, 128, 0, s>>>(b);
     }
     MCU(cudaGetLastError());
+    if (p->peer && out && !merged) {       // a schedule without the inline exchange: the separate exchange kernel
+      const int rc = tdb200_peer_allreduce(p->peer, out, 2 + p->n_slots, s);
+      if (rc != TDB200_OK) return rc;
+    }
   } else {
     tdb::mat_finalize_kernel<<<1, 256, 0, s>>>(p->d_part_loss, n_ctas, p->desc.n_eq,
                                               (double)p->desc.n0 * (double)p->desc.n1, p->d_bc_sum, p->n_bc_slots,
@@ -2242,6 +2259,15 @@ int32_t tdb200_mat_plan_launches_per_call(const tdb200_mat_plan* p) {
   if (p->march && p->edge_bc && p->args.lin1 && getenv("TDB200_MAT_FUSED") && (p->args.edge_x + p->cx_hx) % 4 == 0 &&
       tdb::mat_march_fused_ctas(p->args, p->n_sms) <= 2 * p->n_sms) return 1;
   return p->args.lin1 && p->march && !p->edge_bc ? 3 : 2;
+}
+
+int tdb200_mat_plan_set_peer(tdb200_mat_plan* p, tdb200_peer* peer, int32_t* inline_out) {
+  if (!p) return mat_invalid("null plan");
+  // the loss exchange runs inside the boundary kernel only on the two-launch schedule (mat_march + mat_edge_bc)
+  const bool ok = p->march && p->edge_bc && p->n_bc_rows > 0;
+  p->peer = ok ? peer : nullptr;
+  if (inline_out) *inline_out = ok && peer ? 1 : 0;
+  return TDB200_OK;
 }
 
 int tdb200_mat_plan_set_row_window(tdb200_mat_plan* p, int32_t row_lo, int32_t row_hi) {

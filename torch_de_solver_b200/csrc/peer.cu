@@ -26,20 +26,9 @@
 
 extern "C" void tdb200_set_error_(const char* msg);
 
+#include "peer_dev.cuh"
+
 namespace tdb {
-
-constexpr int kPeerMaxLoss = 64;
-constexpr int kPeerMaxWorld = 16;
-
-struct PeerHeader {
-  unsigned int halo_flag[2];  // [side]: last step whose rows the neighbour on that side has pushed into my inbox
-  unsigned int error;         // a wait timed out
-  unsigned int pad;
-  unsigned int loss_flag[kPeerMaxWorld];                 // [rank]: last step whose loss terms that rank has pushed
-  unsigned int vec_flag[kPeerMaxWorld];                  // [rank]: last step whose vector that rank has pushed
-  float loss[2][kPeerMaxWorld][kPeerMaxLoss];            // [parity][rank][term]
-};
-
 }  // namespace tdb
 
 struct tdb200_peer {
@@ -53,24 +42,6 @@ struct tdb200_peer {
 };
 
 namespace tdb {
-
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
-// wait until *flag >= want (sequence numbers only grow); false on time-out
-__device__ __forceinline__ bool wait_seq(const unsigned int* flag, unsigned int want) {
-  const long long t0 = clock64();
-  while ((int)(ld_acquire_sys(flag) - want) < 0) {
-    __nanosleep(200);
-    if (clock64() - t0 > 4000000000LL) return false;
-  }
-  return true;
-}
 
 __device__ __forceinline__ float* halo_box(void* block, int parity, int side, long long halo_floats) {
   return reinterpret_cast<float*>(reinterpret_cast<char*>(block) + sizeof(PeerHeader)) + ((size_t)parity * 2 + side) * halo_floats;
@@ -126,35 +97,9 @@ __global__ void __launch_bounds__(1024) peer_halo_kernel(void* mine, void* up_bl
   }
 }
 
-struct PeerBlocks { void* b[kPeerMaxWorld]; };
-
 __global__ void __launch_bounds__(128) peer_loss_kernel(PeerBlocks blocks, int rank, int world, unsigned int* step_dev,
                                                         float* out, int n) {
-  const unsigned int step = step_dev[1] + 1;
-  const int parity = step & 1;
-  PeerHeader* const hdr = reinterpret_cast<PeerHeader*>(blocks.b[rank]);
-  for (int i = threadIdx.x; i < world * n; i += blockDim.x) {               // my terms -> row `rank` of every inbox
-    const int r = i / n, t = i - r * n;
-    reinterpret_cast<PeerHeader*>(blocks.b[r])->loss[parity][rank][t] = out[t];
-  }
-  __shared__ unsigned int ok;
-  if (threadIdx.x == 0) ok = 1;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    for (int r = 0; r < world; ++r)
-      if (r != rank) st_release_sys(&reinterpret_cast<PeerHeader*>(blocks.b[r])->loss_flag[rank], step);
-  }
-  if ((int)threadIdx.x < world && (int)threadIdx.x != rank)
-    if (!wait_seq(&hdr->loss_flag[threadIdx.x], step)) { ok = 0; hdr->error = 1; }
-  __syncthreads();
-  if ((int)threadIdx.x < n && ok) {
-    float s = 0.f;
-    for (int r = 0; r < world; ++r) s += __ldcv(&hdr->loss[parity][r][threadIdx.x]);     // rank order: bit-identical sums
-    out[threadIdx.x] = s;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) step_dev[1] = step;
+  peer_loss_block(blocks, rank, world, step_dev, out, n);
 }
 
 // All-reduce (sum) of a vector of n floats (the [loss terms | gradient] vector of the NN / autograd modes, 82 KB for the
@@ -313,6 +258,17 @@ int tdb200_peer_allreduce_vec(tdb200_peer* p, float* vec_dev, int64_t n, void* s
   tdb::peer_vec_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(b, p->rank, p->world, p->step_dev, vec_dev, (int)n,
                                                                             4 * p->halo_floats, p->vec_floats);
   PCU(cudaGetLastError());
+  return TDB200_OK;
+}
+
+// internal (mat_stencil.cu): what the finalizing block of the boundary kernel needs to exchange the loss terms itself
+int tdb200_peer_export_(tdb200_peer* p, tdb::PeerLossArgs* out) {
+  if (!p || !out) { tdb200_set_error_("null argument"); return TDB200_ERR_INVALID; }
+  for (int r = 0; r < p->world; ++r) {
+    if (!p->blocks[r]) { tdb200_set_error_("tdb200_peer_open was not called"); return TDB200_ERR_INVALID; }
+    out->blocks.b[r] = p->blocks[r];
+  }
+  out->rank = p->rank; out->world = p->world; out->step_dev = p->step_dev;
   return TDB200_OK;
 }
 

@@ -478,6 +478,7 @@ class MatPlan:
             self._ext[:, up:up + ir.shape[1]] = model.detach()
             model.data = self._ext[:, up:up + ir.shape[1]]
         self._peer = None
+        self._peer_loss_inline = False
         self._setup_peer()
 
     def _setup_peer(self):
@@ -503,6 +504,10 @@ class MatPlan:
         ok = self.lib.tdb200_peer_create(rank, world, n_var * ir.halo * n1, 0, dev_index, C.byref(handle)) == 0
         if open_peer(self.lib, handle, ok, world, self._pg):
             self._peer = handle
+            # the finalizing block of the boundary kernel exchanges the loss terms itself where the schedule allows it
+            flag = C.c_int32(0)
+            _native.check(self.lib.tdb200_mat_plan_set_peer(self.handle, handle, C.byref(flag)), 'tdb200_mat_plan_set_peer')
+            self._peer_loss_inline = bool(flag.value)
 
     def _push_bcs(self):
         lam = np.asarray(self.slot_lambda, np.float64)
@@ -573,8 +578,9 @@ class MatPlan:
             _native.check(self.lib.tdb200_peer_halo(self._peer, self._ext.data_ptr(), n_ext * n1, n_var, h * n1, up * n1,
                                                     (up + n - h) * n1, 0, (up + n) * n1, stream), 'tdb200_peer_halo')
             out, grad = self.loss_grad_ext(self._ext)
-            _native.check(self.lib.tdb200_peer_allreduce(self._peer, out.data_ptr(), self.out_size, stream),
-                          'tdb200_peer_allreduce')
+            if not self._peer_loss_inline:
+                _native.check(self.lib.tdb200_peer_allreduce(self._peer, out.data_ptr(), self.out_size, stream),
+                              'tdb200_peer_allreduce')
             return out, grad
         out, grad = self.loss_grad_ext(exchange_halos(u, self.ir, self._pg, self._ext))
         if self.ir.shard[1] > 1:
