@@ -936,14 +936,28 @@ __global__ void __launch_bounds__(128) mat_march_edge_kernel(const MatArgs a, co
 // One march item (a warp's column strip over a chunk of rows) of the register-marching kernel; returns the warp lane's
 // share of the loss.  SKIP: gradient cells of the edge frame (rows < fzy from the top / bottom, columns < fzx from the
 // left / right) are NOT stored - the edge CTAs of mat_march_fused_kernel own them.
+// Rows [y0, y1) of row chunk `chunk`.  er == 0: uniform chunks of ch rows.  er > 0 (slab of a sharded grid): a short
+// first and last chunk of er rows - the only ones whose stencils read halo rows, so the only warps that wait for the
+// halo exchange, and they have a fraction of a regular chunk's work - and regular chunks of ch rows in between.
+__host__ __device__ __forceinline__ void mw_chunk_rows(int n0, int ch, int er, int chunk, int& y0, int& y1) {
+  if (er == 0) { y0 = chunk * ch; y1 = y0 + ch < n0 ? y0 + ch : n0; return; }
+  const int nm = (n0 - 2 * er + ch - 1) / ch;              // regular chunks
+  if (chunk == 0) { y0 = 0; y1 = er; }
+  else if (chunk <= nm) { y0 = er + (chunk - 1) * ch; y1 = y0 + ch < n0 - er ? y0 + ch : n0 - er; }
+  else { y0 = n0 - er; y1 = n0; }
+}
+__host__ __device__ __forceinline__ int mw_n_chunks(int n0, int ch, int er) {
+  return er == 0 ? (n0 + ch - 1) / ch : 2 + (n0 - 2 * er + ch - 1) / ch;
+}
 template <int HY, int HX, unsigned MY, unsigned MX, int P, bool SKIP>
 __device__ __forceinline__ double mw_march_item(const MatArgs& a, const int ch, const int n_strips, const int item,
-                                                const int lane, const int fzy, const int fzx) {
+                                                const int lane, const int fzy, const int fzx, const int er = 0) {
   constexpr int R = 2 * HY + 1 + P;                          // ring length = unroll factor of the row loop
   const int n0 = a.n0, n1 = a.n1;
   double dacc = 0.0;
   const int chunk = item / n_strips, strip = item - chunk * n_strips;
-  const int y0 = chunk * ch, y1 = min(y0 + ch, n0);
+  int y0, y1;
+  mw_chunk_rows(n0, ch, er, chunk, y0, y1);
   const int x = strip * kMwOutW - 4 + 4 * lane;            // column of this thread's first element
   const bool col_ok = x >= 0 && x < n1;                    // n1 % 4 == 0: the float4 is entirely inside or outside
   const bool own = col_ok && lane >= 1 && lane < 1 + kMwOutLanes;
@@ -1032,6 +1046,7 @@ template <int HY, int HX, unsigned MY, unsigned MX, int P>
 __global__ void __launch_bounds__(kMwThreads, 2) mat_march_kernel(const MatArgs a, const int ch, const int n_strips,
                                                                   const int n_items, const int n_edge_blocks,
                                                                   float* __restrict__ edge_seeds, const int pdl_halo) {
+  // pdl_halo: 0, or the rows of the short first / last chunk of a slab (see mw_chunk_rows)
   __shared__ double red[kMwWarps];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int item = (int)blockIdx.x * kMwWarps + warp;
@@ -1043,14 +1058,15 @@ __global__ void __launch_bounds__(kMwThreads, 2) mat_march_kernel(const MatArgs 
   if (pdl_halo) {
     if ((int)blockIdx.x >= first_edge_block) pdl_wait();
     else if (item < n_items) {
-      const int y0 = (item / n_strips) * ch, y1 = min(y0 + ch, a.n0);
+      int y0, y1;
+      mw_chunk_rows(a.n0, ch, pdl_halo, item / n_strips, y0, y1);
       if (y0 - 2 * HY < a.row_lo || y1 + 2 * HY > a.row_hi) pdl_wait();
     }
   }
   if ((int)blockIdx.x >= first_edge_block) {                 // phase A of the edge treatment: the trailing CTAs fill the
     dacc = mw_edge_seeds(a, a.edge_y + HY, a.edge_x + HX, edge_seeds, (int)blockIdx.x - first_edge_block, n_edge_blocks);   // tail
   } else if (item < n_items) {                               // warp-uniform
-    dacc = mw_march_item<HY, HX, MY, MX, P, false>(a, ch, n_strips, item, lane, 0, 0);
+    dacc = mw_march_item<HY, HX, MY, MX, P, false>(a, ch, n_strips, item, lane, 0, 0, pdl_halo);
   }
   for (int o = 16; o; o >>= 1) dacc += __shfl_xor_sync(kFullMask, dacc, o);
   if (lane == 0) red[warp] = dacc;
@@ -1073,9 +1089,16 @@ static int mat_march_chunk(const MatArgs& a, int n_sms) {
   if (ch < 32) ch = 32;
   return (int)ch;
 }
-static int mat_march_ctas(const MatArgs& a, int n_sms) {         // loss partials written by the march launch
+// slab of a sharded grid: rows of the short end chunks (halo rows + the rows whose stencils reach them), else 0
+static int mat_march_edge_rows(const MatArgs& a, int hy, int ch) {
+  if ((a.row_lo <= 0 && a.row_hi >= a.n0) || getenv("TDB200_NO_PDL")) return 0;
+  const int halo = a.row_lo > a.n0 - a.row_hi ? a.row_lo : a.n0 - a.row_hi;
+  const int er = (halo + 2 * hy + 7) / 8 * 8;
+  return a.n0 - 2 * er >= ch ? er : 0;
+}
+static int mat_march_ctas(const MatArgs& a, int n_sms, int hy = 2) {         // loss partials written by the march launch
   const int ch = mat_march_chunk(a, n_sms), n_strips = (a.n1 + kMwOutW - 1) / kMwOutW;
-  const int n_items = n_strips * ((a.n0 + ch - 1) / ch);
+  const int n_items = n_strips * mw_n_chunks(a.n0, ch, mat_march_edge_rows(a, hy, ch));
   return kMwEdgeBlocks + (n_items + kMwWarps - 1) / kMwWarps;
 }
 static size_t mat_march_frame_cells(const MatArgs& a, int hy, int hx) {
@@ -1088,14 +1111,15 @@ template <int HY, int HX, unsigned MY, unsigned MX>
 static cudaError_t launch_mat_march_t(const MatArgs& a, int n_sms, float* edge_seeds, cudaEvent_t after_stencil, bool main_only,
                                       cudaStream_t s) {
   const int ch = mat_march_chunk(a, n_sms), n_strips = (a.n1 + kMwOutW - 1) / kMwOutW;
-  const int n_items = n_strips * ((a.n0 + ch - 1) / ch);
+  const int er = mat_march_edge_rows(a, HY, ch);
+  const int n_items = n_strips * mw_n_chunks(a.n0, ch, er);
   const int grid = kMwEdgeBlocks + (n_items + kMwWarps - 1) / kMwWarps;
   // P = 5 rows of register prefetch: the deepest ring that does not spill at 128 registers (measured at 4096^2: P = 3
   // 65.6 us per step, 4: 63.4, 5: 62.6; P = 6 spills)
   cudaError_t e;
-  if ((a.row_lo > 0 || a.row_hi < a.n0) && !getenv("TDB200_NO_PDL")) {
+  if (er > 0) {
     e = launch_pdl(mat_march_kernel<HY, HX, MY, MX, 5>, dim3(grid), dim3(kMwThreads), 0, s, a, ch, n_strips, n_items,
-                   (int)kMwEdgeBlocks, edge_seeds, 1);
+                   (int)kMwEdgeBlocks, edge_seeds, er);
   } else {
     mat_march_kernel<HY, HX, MY, MX, 5><<<grid, kMwThreads, 0, s>>>(a, ch, n_strips, n_items, kMwEdgeBlocks, edge_seeds, 0);
     e = cudaGetLastError();
@@ -1980,7 +2004,8 @@ int tdb200_mat_plan_create(const tdb200_mat_desc* desc, const tdb200_mat_field* 
   {
     int l1 = a.lin1 ? tdb::mat_lin1_ctas(a) : 0;         // (the cross kernel uses the same tiling)
     if (p->march) {
-      const int m = tdb::mat_march_ctas(a, p->n_sms);
+      // (+ the CTAs of the two short end chunks a row window adds later, see mw_chunk_rows)
+      const int m = tdb::mat_march_ctas(a, p->n_sms) + 2 * (((a.n1 + tdb::kMwOutW - 1) / tdb::kMwOutW + tdb::kMwWarps - 1) / tdb::kMwWarps) + 2;
       l1 = m > l1 ? m : l1;
       MCU(cudaMalloc(&p->d_edge_seed, sizeof(float) * (tdb::mat_march_frame_cells(a, 2 * hy, 2 * hx) + 1)));   // extended frame
     }
@@ -2140,7 +2165,7 @@ static int mat_stencil(tdb200_mat_plan* p, tdb::MatArgs& a, const float* u, floa
                                 main_only || p->edge_bc, s));
       if (ran_march) *ran_march = true;
       ev1_done = true;
-      n_ctas = tdb::mat_march_ctas(a, p->n_sms);
+      n_ctas = tdb::mat_march_ctas(a, p->n_sms, p->cx_hy);
     } else if (tma) {
       MCU(tdb::launch_mat_cross_tma(a, p->cx_hy, p->cx_hx, p->cx_my, p->cx_mx, p->map_u, a.l1_fbuf[0] ? p->map_f : p->map_u,
                                     p->n_sms, &n_ctas, s));
