@@ -15,7 +15,7 @@
 //   peer_loss_kernel   one CTA: store my [2 + n_slots] loss terms into every rank's inbox row `rank`, fence, flags; wait
 //                      for every rank's flag; add the rows in RANK order (every rank gets the bit-identical sum).
 // Both kernels are plain stream work: the whole multi-rank step is capturable in one CUDA graph.  Waits are bounded
-// (~2 s of polling): on a time-out the kernel sets an error word instead of hanging the GPU.
+// (~20 s of polling): on a time-out the kernel sets an error word instead of hanging the GPU.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>

@@ -34,12 +34,14 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
-// wait until *flag >= want (sequence numbers only grow); false on time-out (~2 s)
+// wait until *flag >= want (sequence numbers only grow); false on time-out.  The bound (~20 s of SM clocks) is far above
+// any start-up skew between the ranks of one job - a rank that arrives late must find its neighbours still waiting, as
+// it would inside an NCCL collective - and still finite, so a rank that died cannot hang the others' GPUs for good.
 __device__ __forceinline__ bool wait_seq(const unsigned int* flag, unsigned int want) {
   const long long t0 = clock64();
   while ((int)(ld_acquire_sys(flag) - want) < 0) {
     __nanosleep(200);
-    if (clock64() - t0 > 4000000000LL) return false;
+    if (clock64() - t0 > 40000000000LL) return false;
   }
   return true;
 }
