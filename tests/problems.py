@@ -379,6 +379,30 @@ def heat_mat(api, dtype='float32', n=32, nt=32, derivative_points=2):
                    mat_shape=(1, n + 1, nt + 1))
 
 
+def heat_mat_causal(api, dtype='float32', n=24, nt=20, tol=0.02):
+    """Causal loss in mat mode (tedeous/losses.py:137-182, n_t = grid.shape[1]: grid axis 0 is time): u_t - 0.1 u_xx + u^2
+    = f with a tensor coefficient, time as the FIRST variable."""
+    dom = api.Domain()
+    dom.variable('t', [0, 1], nt, dtype=dtype)
+    dom.variable('x', [0, 1], n, dtype=dtype)
+    bc = api.Conditions()
+    bc.dirichlet({'t': 0, 'x': [0, 1]}, value=lambda g: torch.sin(np.pi * g[:, 1]))
+    bc.dirichlet({'t': [0, 1], 'x': 0}, value=0)
+    bc.dirichlet({'t': [0, 1], 'x': 1}, value=0)
+    tdt = torch.float64 if dtype == 'float64' else torch.float32
+    c = 0.5 + torch.linspace(0, 1, (nt + 1) * (n + 1), dtype=tdt).reshape(nt + 1, n + 1)
+    eq = api.Equation()
+    eq.add({
+        'du/dt': {'coeff': 1, 'term': [0], 'pow': 1},
+        '-a*d2u/dx2': {'coeff': -0.1, 'term': [1, 1], 'pow': 1},
+        'c(t,x)*u^2': {'coeff': c, 'term': [None], 'pow': 2},
+        '-f': {'coeff': lambda g: -torch.sin(np.pi * g[1]) * torch.exp(-g[0]), 'term': [None], 'pow': 0},
+    })
+    return Problem('heat_mat_causal', dom, bc, eq, 'mat', [],
+                   dict(lambda_operator=1, lambda_bound=10, derivative_points=2, tol=tol),
+                   mat_shape=(1, nt + 1, n + 1))
+
+
 def schrodinger_mat(api, dtype='float32', n=20, nt=28, derivative_points=2):
     """Two coupled fields on a 2-D grid in mat mode: u_t + 0.5 v_xx + (u^2 + v^2) v = 0, v_t - 0.5 u_xx - (u^2 + v^2) u = 0
     (examples/examples_schrodinger/example_schrodinger_matrix.py pattern: products of powers across fields)."""
@@ -612,6 +636,7 @@ ZOO: Dict[str, Callable] = {
     'nonlinear_mix_NN': lambda api, dt: nonlinear_mix(api, dt, mode='NN'),
     'poisson_mat_p2': lambda api, dt: poisson_mat(api, dt, n=32, derivative_points=2),
     'poisson_robin_mat': lambda api, dt: poisson_robin_mat(api, dt),
+    'heat_mat_causal': lambda api, dt: heat_mat_causal(api, dt),
     'poisson_mat_p3': lambda api, dt: poisson_mat(api, dt, n=24, derivative_points=3),
     'kdv_mat_p2': lambda api, dt: kdv_mat(api, dt, n=24, derivative_points=2),
     'schrodinger_mat_p2': lambda api, dt: schrodinger_mat(api, dt),

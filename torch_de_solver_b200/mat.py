@@ -141,7 +141,8 @@ class MatIR:
     `u` from each neighbour plus one all-reduce of the loss terms."""
 
     def __init__(self, grid: torch.Tensor, prepared_operator: List[dict], bconds: List[dict], n_var: int,
-                 device, lambda_operator, lambda_bound, derivative_points: int = 2, shard=(0, 1)):
+                 device, lambda_operator, lambda_bound, derivative_points: int = 2, shard=(0, 1),
+                 per_cell_coeffs: bool = False):
         self.lifted = grid.dim() == 2                      # 1-D grid [1, N0] -> [2, N0, 1] with a dummy second axis
         grid_user = grid                                   # what callable coefficients are evaluated on (derivative.py:319)
         if self.lifted:
@@ -174,7 +175,7 @@ class MatIR:
                 self.fields.append(key)
             return self.fields.index(key)
 
-        def add_terms(op: dict):
+        def add_terms(op: dict, per_cell: bool = False):
             begin = len(terms)
             for label, term in op.items():
                 dif = list(term.keys())[1]
@@ -194,6 +195,8 @@ class MatIR:
                     raise UnsupportedProblem('trainable coefficients in mat mode')
                 if callable(c) and not isinstance(c, torch.Tensor):
                     c = c(grid_user)
+                if per_cell and not (isinstance(c, torch.Tensor) and c.numel() > 1):
+                    c = torch.full((n0, n1), float(c), dtype=torch.float32, device=device)   # a buffer for every term
                 if isinstance(c, torch.Tensor) and c.numel() > 1:
                     terms.append([0.0, 1, len(coefs_full), fb, len(factors)])       # idx = buffer number for now
                     c = c.to(device, torch.float32)
@@ -204,7 +207,10 @@ class MatIR:
                     terms.append([float(c), 0, 0, fb, len(factors)])
             return begin, len(terms)
 
-        self.eq_ranges = [add_terms(eq) for eq in prepared_operator]
+        # per_cell_coeffs (causal loss): every equation term reads its coefficient from a per-cell buffer, so that the
+        # no-grad causal weights can enter as a per-cell factor of the coefficients (MatPlan.set_cell_weights)
+        self.eq_ranges = [add_terms(eq, per_cell_coeffs) for eq in prepared_operator]
+        self.n_eq_buffers = len(coefs_full) if per_cell_coeffs else 0     # the first buffers belong to the equations
 
         # ---- boundary rows (global), operator terms of the conditions --------------------------------
         self.bnd_types: List[str] = []
@@ -414,7 +420,8 @@ class MatPlan:
     """Owns one tdb200_mat_plan (built from the `MatIR` of this rank)."""
 
     def __init__(self, grid: torch.Tensor, prepared_operator: List[dict], bconds: List[dict], model: torch.Tensor,
-                 lambda_operator, lambda_bound, derivative_points: int = 2, shard=None, process_group=None):
+                 lambda_operator, lambda_bound, derivative_points: int = 2, shard=None, process_group=None,
+                 per_cell_coeffs: bool = False):
         # 1-D grids ([1, N0], model [n_eq, N0]: the ODE examples, example_ODE_Legendre_matrix.py, example_LV_mat.py) run as
         # [N0, 1] grids with a dummy second axis - same memory, no derivative field along it
         self._lift = grid.dim() == 2 and model.dim() == 2
@@ -432,7 +439,7 @@ class MatPlan:
         self.grid = grid
         self._pg = process_group
         ir = MatIR(grid, prepared_operator, bconds, int(model.shape[0]), model.device, lambda_operator, lambda_bound,
-                   derivative_points, shard)
+                   derivative_points, shard, per_cell_coeffs)
         self.ir = ir
         if tuple(model.shape) != ir.shape:
             raise UnsupportedProblem(f'rank {shard[0]} of {shard[1]} owns grid rows {ir.rows}: its model tensor must be '
@@ -508,6 +515,27 @@ class MatPlan:
             flag = C.c_int32(0)
             _native.check(self.lib.tdb200_mat_plan_set_peer(self.handle, handle, C.byref(flag)), 'tdb200_mat_plan_set_peer')
             self._peer_loss_inline = bool(flag.value)
+
+    def set_cell_weights(self, w: Optional[torch.Tensor]):
+        """Causal loss in mat mode (tedeous/losses.py:137-182 with `n_t = grid.shape[1]`, solution.py:58-60): the operator part
+        of the loss becomes sum_cells w * sum_eq res^2 / N with no-grad weights w [N0, N1].  Every equation term reads its
+        coefficient from a per-cell buffer (`per_cell_coeffs`), and res is linear in those coefficients, so scaling them
+        by sqrt(w) makes the unchanged kernels evaluate exactly that loss and its gradient.  None restores the plain
+        coefficients."""
+        nb = self.ir.n_eq_buffers
+        if nb == 0:
+            raise UnsupportedProblem('set_cell_weights needs a plan built with per_cell_coeffs=True')
+        n_cells = self.ir.shape_ext[1] * self.ir.shape_ext[2]
+        if getattr(self, '_coeffs_base', None) is None:
+            self._coeffs_base = self._coeffs.clone()
+        if w is None:
+            self._coeffs.copy_(self._coeffs_base)
+            return
+        sw = torch.sqrt(w.detach().to(self.device, torch.float32)).reshape(-1)
+        if sw.numel() != n_cells:
+            raise ValueError('one weight per grid cell expected')
+        view, base = self._coeffs[:nb * n_cells].view(nb, n_cells), self._coeffs_base[:nb * n_cells].view(nb, n_cells)
+        torch.mul(base, sw, out=view)
 
     def _push_bcs(self):
         lam = np.asarray(self.slot_lambda, np.float64)

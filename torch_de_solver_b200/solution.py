@@ -364,8 +364,8 @@ class Solution:
             raise UnsupportedProblem('weak-form loss is implemented for modes NN / autograd only (SURVEY 8 a11)')
         if weak and (tol != 0 or (shard is not None and shard[1] > 1)):
             raise UnsupportedProblem('weak-form loss: no causal weights, not sharded over ranks')
-        if tol != 0 and mode == 'mat':
-            raise UnsupportedProblem('causal loss (tol != 0) is implemented for modes NN / autograd only (SURVEY 8 a10)')
+        if tol != 0 and mode == 'mat' and shard is not None and shard[1] > 1:
+            raise UnsupportedProblem('causal loss (tol != 0) in mat mode is not sharded over ranks')
         self.grid = check_device(grid)
         # Mini-batches (tedeous/eval.py:124-141, 174-182; solution.py:159-166): mode 'autograd' draws shuffled batches of the
         # grid rows for the operator; in mode 'NN' the reference's batches never reach the operator (Derivative_NN ignores
@@ -423,7 +423,7 @@ class Solution:
             _require_cuda(self.model, 'mat-mode model tensor')
             self._plan = MatPlan(self.grid, self._prepared_operator, self.prepared_bconds, self.model,
                                  self.lambda_operator, self.lambda_bound, self.derivative_points,
-                                 shard=self._shard, process_group=self._pg)
+                                 shard=self._shard, process_group=self._pg, per_cell_coeffs=self.tol != 0)
             self._n_slots = self._plan.n_slots
             self.bval_keys = list(self._plan.bnd_types)
             self.bval_length = list(self._plan.type_len)
@@ -504,6 +504,8 @@ class Solution:
     def _run_plan(self) -> Tuple[torch.Tensor, torch.Tensor]:
         """-> (out [2 + n_slots (+ n_params)], flat gradient)."""
         if self.mode == 'mat':
+            if self.tol != 0:
+                self._causal_weights_mat()
             return self._plan.loss_grad_raw(self.model)
         if self.tol != 0:
             self._causal_weights()
@@ -552,6 +554,19 @@ class Solution:
         w = causal_row_weights((op * op).sum(1), self.tol, self._ir.n_t, self._ir.n_interior,
                                getattr(seg, 'shard_range', None), self._shard[1], self._pg)
         self._plan.set_row_weights(w)
+
+    def _causal_weights_mat(self):
+        """Causal loss in mat mode (losses.py:137-182 with n_t = grid.shape[1], solution.py:58-60): the no-grad weights
+        w[t, j] = exp(-tol * sum_{s < t} sum_eq op^2[s, j]) over the grid rows of axis 0, from a forward-only launch with the
+        plain coefficients; they enter the loss + gradient launch as a per-cell factor sqrt(w) of every equation
+        coefficient (`MatPlan.set_cell_weights`); lambda_operator is not used by this loss."""
+        plan = self._plan
+        plan.set_cell_weights(None)
+        op = plan.eval_fields(self.model)[0]
+        n0, n1 = plan.ir.shape_ext[1], plan.ir.shape_ext[2]
+        res = (op[:n0 * n1] ** 2).sum(1).reshape(n0, n1)
+        w = torch.exp(-self.tol * (torch.cumsum(res, 0) - res))
+        plan.set_cell_weights(w)
 
     def _sync_lambdas(self):
         """Push lambda_operator / lambda_bound to the plan when they changed (callbacks such as AdaptiveLambda assign new
@@ -698,6 +713,8 @@ class Solution:
             if self._shard[1] > 1:
                 raise UnsupportedProblem('per-point fields are not gathered across ranks')
             if self.mode == 'mat':
+                if self.tol != 0:
+                    self._plan.set_cell_weights(None)          # fields are those of the plain coefficients
                 self._fields_cache = self._plan.eval_fields(self.model)
             else:
                 op, bval, tval = _assemble_fields(self._plan)
