@@ -152,3 +152,46 @@ def test_scheme_choose_equals_reference_table():
         got = Finite_diffs(c['term'], c['nvars'], c['type']).scheme_choose(c['order'], h=c['h'])
         assert got[0] == c['scheme'], c
         assert got[1] == c['sign'], c
+
+
+@pytest.mark.parametrize('n,qs,have', [(2, [1], (2, 2)), (2, [1], (0, 0)), (3, [1], (2, 1)), (3, [1, 2], (3, 3)),
+                                       (4, [1, 2, 3], (4, 4)), (4, [2], (2, 2))])
+def test_mixed_partials_as_directional_derivatives(n, qs, have):
+    """`plan._mixed_plan`: d^n / dx^(n-q) dy^q = sum_j c_j D_{v_j}^n (polarisation) - checked on a random polynomial of
+    degree 5 in two variables with torch autograd in fp64, for every direction set the search returns."""
+    import itertools
+    from torch_de_solver_b200.plan import _mixed_plan
+    torch.manual_seed(n * 10 + len(qs))
+    coef = torch.randn(6, 6, dtype=torch.float64)
+
+    def poly(p):
+        x, y = p[..., 0], p[..., 1]
+        return sum(coef[i, j] * x ** i * y ** j for i, j in itertools.product(range(6), range(6)) if i + j <= 5)
+
+    def directional(p, v, order):
+        p = p.clone().requires_grad_(True)
+        f = poly(p)
+        for _ in range(order):
+            g, = torch.autograd.grad(f.sum(), p, create_graph=True)
+            f = g @ torch.as_tensor(v, dtype=torch.float64)
+        return f.detach()
+
+    def partial(p, axes):
+        p = p.clone().requires_grad_(True)
+        f = poly(p)
+        for a in axes:
+            g, = torch.autograd.grad(f.sum(), p, create_graph=True)
+            f = g[..., a]
+        return f.detach()
+    pts = torch.rand(7, 2, dtype=torch.float64)
+    cands, sol = _mixed_plan(n, qs, *have)
+    vecs = [(1.0, 0.0) if c == 'a' else (0.0, 1.0) if c == 'b' else (1.0, float(c)) for c in cands]
+    for q in qs:
+        got = sum(float(c) * directional(pts, v, n) for c, v in zip(sol[q], vecs))
+        ref = partial(pts, [0] * (n - q) + [1] * q)
+        assert torch.allclose(got, ref, rtol=1e-9, atol=1e-9), (n, q, cands)
+    # pure directions the operator needs anyway are free: with both present a second-order mixed partial adds ONE direction
+    if n == 2 and have == (2, 2):
+        assert sorted(map(str, cands)) == sorted(['a', 'b', '1.0'])
+    if n == 2 and have == (0, 0):
+        assert sorted(cands) == [-1.0, 1.0]
