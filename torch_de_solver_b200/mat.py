@@ -116,7 +116,7 @@ def cell_indices(grid: torch.Tensor, bnd: torch.Tensor) -> torch.Tensor:
         if c.numel() == 1 or a >= bnd.shape[1]:            # dummy axis of a lifted 1-D grid
             flat = flat * shape[a]
             continue
-        x = bnd[:, a].float()
+        x = bnd[:, a].float().contiguous()
         order = torch.argsort(c)
         cs = c[order]
         pos = torch.searchsorted(cs, x).clamp(1, cs.numel() - 1)
