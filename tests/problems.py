@@ -565,6 +565,29 @@ def mixed_bbm(api, dtype='float32', n=16, layers=(2, 32, 32, 1)):
                    init='xavier_b')
 
 
+def monge_ampere(api, dtype='float32', n=20, layers=(2, 64, 64, 64, 1)):
+    """Monge-Ampere equation u_xx u_yy - (u_xy)^2 = f: a SQUARED mixed partial (the power of the polarisation sum is
+    expanded into products of directional derivatives), autograd mode."""
+    dom = api.Domain()
+    dom.variable('x', [0, 1], n, dtype=dtype)
+    dom.variable('y', [0, 1], n, dtype=dtype)
+    bc = api.Conditions()
+    exact = lambda g: torch.exp(0.5 * (g[:, 0] ** 2 + g[:, 1] ** 2))
+    bc.dirichlet({'x': 0, 'y': [0, 1]}, value=exact)
+    bc.dirichlet({'x': 1, 'y': [0, 1]}, value=exact)
+    bc.dirichlet({'x': [0, 1], 'y': 0}, value=exact)
+    bc.dirichlet({'x': [0, 1], 'y': 1}, value=exact)
+    eq = api.Equation()
+    eq.add({
+        'uxx*uyy': {'coeff': 1, 'term': [[0, 0], [1, 1]], 'pow': [1, 1], 'var': [0, 0]},
+        '-uxy^2': {'coeff': -1, 'term': [0, 1], 'pow': 2, 'var': 0},
+        '-f': {'coeff': lambda g: -(1 + g[:, 0] ** 2 + g[:, 1] ** 2) * torch.exp(g[:, 0] ** 2 + g[:, 1] ** 2),
+               'term': [None], 'pow': 0},
+    })
+    return Problem('monge_ampere_autograd', dom, bc, eq, 'autograd', list(layers), dict(lambda_operator=1, lambda_bound=10),
+                   init='xavier_b')
+
+
 # --- callable 'pow' (examples/examples_heat/example_heat_2d_long_time.py:94-99) ------------------------------------------
 def heat_callable_pow(api, dtype='float32', n=20, mode='autograd', layers=(2, 32, 32, 1), h=0.01):
     """u_t - 0.05 u_xx + c(x, t) sin(3 u^2) + 0.3 tanh(u) u_x^2 = 0: a callable power on the value (the shipped example's
@@ -604,6 +627,7 @@ ZOO: Dict[str, Callable] = {
     'mixed_elliptic_autograd': lambda api, dt: mixed_elliptic(api, dt, mode='autograd'),
     'mixed_elliptic_NN': lambda api, dt: mixed_elliptic(api, dt, n=16, mode='NN', layers=(2, 32, 32, 1)),
     'mixed_bbm_autograd': lambda api, dt: mixed_bbm(api, dt),
+    'monge_ampere_autograd': lambda api, dt: monge_ampere(api, dt),
     'burgers_inverse_autograd': lambda api, dt: burgers_inverse(api, dt, mode='autograd'),
     'heat_callable_autograd': lambda api, dt: heat_callable_pow(api, dt, mode='autograd'),
     'heat_callable_NN': lambda api, dt: heat_callable_pow(api, dt, n=16, mode='NN'),

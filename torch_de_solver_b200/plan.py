@@ -304,8 +304,10 @@ def _mixed_plan(n: int, need_q: Sequence[int], have_a: int, have_b: int):
 def lower_mixed(term_lists: Sequence[List[TermIR]], d: int) -> List[List[TermIR]]:
     """Rewrites every factor that is a MIXED partial (reference: any axis list, tedeous/derivative.py:92-97, e.g. [0, 1])
     as a linear combination of pure directional derivatives of the same order (polarisation), so that the kernels only
-    ever propagate 1-D Taylor jets: a term `c * u_xy * rest` becomes `sum_j (c * c_j) * D_{v_j}^2 u * rest`.  Mixed
-    factors must enter with power 1 (a power of a sum is not a product of channels) and mix two axes."""
+    ever propagate 1-D Taylor jets: a term `c * u_xy * rest` becomes `sum_j (c * c_j) * D_{v_j}^2 u * rest`.  A mixed
+    factor under a power p = 2 or 3 is written as p factors of power 1 first, so the power of the sum comes out as the
+    k^p products of its k directional derivatives (equal factors of a product are merged back into one power); other
+    powers of a mixed partial are not a finite sum of channel products and raise.  Two axes per mixed partial."""
     pure: Dict[int, int] = {}
     mixed: Dict[Tuple[int, int, int], set] = {}
     for terms in term_lists:
@@ -317,8 +319,8 @@ def lower_mixed(term_lists: Sequence[List[TermIR]], d: int) -> List[List[TermIR]
                 if len(ax) == 1:
                     pure[ax[0]] = max(pure.get(ax[0], 0), len(f.axes))
                 elif len(ax) == 2:
-                    if f.pow != 1.0:
-                        raise UnsupportedProblem(f'mixed partial {list(f.axes)} with power {f.pow} (power 1 only)')
+                    if f.pow not in (1.0, 2.0, 3.0):
+                        raise UnsupportedProblem(f'mixed partial {list(f.axes)} with power {f.pow} (1, 2 or 3 only)')
                     if len(f.axes) > MAX_ORDER:
                         raise UnsupportedProblem(f'derivative order {len(f.axes)} > {MAX_ORDER}')
                     mixed.setdefault((ax[0], ax[1], len(f.axes)), set()).add(sum(1 for x in f.axes if x == ax[1]))
@@ -348,6 +350,9 @@ def lower_mixed(term_lists: Sequence[List[TermIR]], d: int) -> List[List[TermIR]
             ax = sorted(set(f.axes))
             if len(ax) != 2 or f.dirvec is not None:
                 continue
+            if f.pow != 1.0:
+                copies = [FactorIR(f.var, tuple(f.axes), 1.0) for _ in range(int(f.pow))]
+                return expand(TermIR(t.coeff, t.factors[:i] + copies + t.factors[i + 1:], t.coeff_fn))
             n, q = len(f.axes), sum(1 for x in f.axes if x == ax[1])
             vecs, sol = plans[(ax[0], ax[1], n)]
             out = []
@@ -370,7 +375,23 @@ def lower_mixed(term_lists: Sequence[List[TermIR]], d: int) -> List[List[TermIR]
                 out += expand(nt)                     # further mixed factors of the same term
             return out
         return [t]
-    return [[e for t in terms for e in expand(t)] for terms in term_lists]
+
+    def merged(t: TermIR) -> TermIR:
+        facs: List[FactorIR] = []
+        for f in t.factors:
+            for g in facs:
+                if (g.var, g.axes, g.dirvec) == (f.var, f.axes, f.dirvec) and f.dirvec is not None:
+                    g.pow += f.pow
+                    break
+            else:
+                facs.append(FactorIR(f.var, f.axes, f.pow, dirvec=f.dirvec) if f.dirvec is not None else f)
+        t.factors = facs
+        return t
+
+    def lowered(t: TermIR) -> List[TermIR]:
+        out = expand(t)
+        return out if len(out) == 1 and out[0] is t else [merged(e) for e in out]
+    return [[e for t in terms for e in lowered(t)] for terms in term_lists]
 
 
 # ----------------------------------------------------------------------------------------------------
