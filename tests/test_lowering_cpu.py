@@ -195,3 +195,20 @@ def test_mixed_partials_as_directional_derivatives(n, qs, have):
         assert sorted(map(str, cands)) == sorted(['a', 'b', '1.0'])
     if n == 2 and have == (0, 0):
         assert sorted(cands) == [-1.0, 1.0]
+
+
+def test_power_of_a_mixed_partial_expands_into_products():
+    """(u_xy)^2 with the polarisation u_xy = sum_j c_j D_j^2 u becomes sum_jk c_j c_k D_j^2 u D_k^2 u; a fractional power of a
+    mixed partial has no such expansion and raises (no silent fallback)."""
+    from torch_de_solver_b200.plan import FactorIR, TermIR, lower_mixed, UnsupportedProblem
+    pure = TermIR(1.0, [FactorIR(0, (0, 0), 1.0), FactorIR(0, (1, 1), 1.0)])
+    sq = TermIR(-1.0, [FactorIR(0, (0, 1), 2.0)])
+    (out,) = lower_mixed([[pure, sq]], 2)
+    assert out[0] is pure
+    terms = out[1:]
+    assert len(terms) in (4, 9)                    # k = 2 or 3 directions for u_xy, squared
+    for t in terms:
+        assert all(f.dirvec is not None or len(set(f.axes)) == 1 for f in t.factors)
+        assert sum(f.pow for f in t.factors) == 2.0
+    with pytest.raises(UnsupportedProblem):
+        lower_mixed([[TermIR(1.0, [FactorIR(0, (0, 1), 1.5)])]], 2)
